@@ -1,0 +1,99 @@
+#!/usr/bin/env python3
+"""Build ``oracle/_ref/libbroadcast_ref.so`` from the reference's own Fortran sources.
+
+TEST INFRASTRUCTURE ONLY.  Reads the Fortran files in place under /root/reference
+(never copies them), machine-translates them to C with ``oracle/f90_to_c.py`` and
+compiles the result with gcc.  All outputs go to the git-ignored ``oracle/_ref/``:
+
+    oracle/_ref/broadcast_ref.c          generated C (one function per Fortran subroutine)
+    oracle/_ref/manifest.json            argument lists / types / bounds of every routine
+    oracle/_ref/libbroadcast_ref.so      parity build:  -O2 -ffp-contract=off  (no FMA, no fast-math)
+    oracle/_ref/libbroadcast_ref_fast.so timing build:  -O3 -march=native       (what a user's f2py build does)
+
+The GPU box has no /root/reference: there the prebuilt files travel with the snapshot and
+this script is a no-op (returns False) when the reference tree is absent.
+"""
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("BROADCAST_REFERENCE", "/root/reference")
+OUT = os.path.join(HERE, "_ref")
+
+# (path relative to the reference root, subroutines to take or None = all)
+FILES = [
+    ("srcfv/prepro/flux_num_dnc5.f90", None),
+    ("srcfv/prepro/flux_num_dnc5_nowall.f90", None),
+    ("srcfv/tangent/flux_num_dnc5_d.f90", None),
+    ("srcfv/tangent/flux_num_dnc5_nowall_d.f90", None),
+    ("srcfv/prepro/bc_wall_viscous.f90", ["bc_wall_viscous_adia_2d"]),
+    ("srcfv/prepro/bc_no_reflexion.f90", ["bc_no_reflexion_2d"]),
+    ("srcfv/prepro/bc_supandsubinlet.f90", ["bc_supandsubinlet_2d"]),
+    ("srcfv/prepro/bc_extrapolate.f90", ["bc_extrapolate_o2_2d"]),
+    ("srcfv/prepro/bc_general.f90", ["bc_general_2d"]),
+    ("srcfv/prepro/jn_match.f90", ["jn_match_2d"]),
+    ("srcfv/prepro/jn_match_geom.f90", ["jn_match_geom_2d"]),
+    ("srcfv/tangent/bc_wall_viscous_d.f90", None),
+    ("srcfv/tangent/bc_no_reflexion_d.f90", None),
+    ("srcfv/tangent/bc_supandsubinlet_d.f90", None),
+    ("srcfv/tangent/bc_extrapolateo2_d.f90", None),
+    ("srcfv/tangent/bc_general_d.f90", None),
+    ("srcfv/tangent/jn_match_2d_d.f90", None),
+    ("srcfv/prepro/computegeom.f90", None),
+    ("misc/ComputeJacobian.f90", [
+        "testvector", "testvector_partial", "computejacobianfromjv", "computejacobianfromjv_relaxed",
+        "computejacobianfromjv_relaxed_dbyvol", "computejacobianfromjv_dbyvol", "computejacobianfromdz",
+        "computejacobianfromjv_relaxed_withjn", "computejacobianfromjv_withjn",
+        "computejacobianfromjv_withjn_dbyvol", "computejacobianfromjv_relaxed_withjnandcheck"]),
+    ("srcfv/dz/function_5p_dz_d.f90", None),
+    ("srcfv/dz/function_5p_dz2_d.f90", None),
+    ("srcfv/prepro_dz/coeffs_5p_dz.f90", ["coeffs_5p_dz"]),
+    ("srcfv/prepro_dz/coeffs_5p_dz2.f90", ["coeffs_5p_dz2"]),
+    ("srcfv/norm.F90", None),
+    ("set_bnd.f90", None),
+    ("initialisation.f90", None),
+]
+
+
+def have_reference() -> bool:
+    return os.path.isdir(os.path.join(REF, "srcfv", "prepro"))
+
+
+def build(verbose: bool = True) -> bool:
+    if not have_reference():
+        if verbose:
+            print(f"[oracle/_ref] reference tree {REF} absent: keeping prebuilt files, nothing to do")
+        return False
+    sys.path.insert(0, HERE)
+    import f90_to_c
+
+    os.makedirs(OUT, exist_ok=True)
+    files = [(os.path.join(REF, p), subs) for p, subs in FILES]
+    ctext, manifest = f90_to_c.translate(files)
+    cpath = os.path.join(OUT, "broadcast_ref.c")
+    with open(cpath, "w") as fh:
+        fh.write(ctext)
+    for m in manifest:
+        m["src"] = os.path.relpath(m["src"], REF)
+    with open(os.path.join(OUT, "manifest.json"), "w") as fh:
+        json.dump(manifest, fh, indent=1)
+    common = ["gcc", "-std=gnu11", "-shared", "-fPIC", "-fno-fast-math", "-w", cpath, "-lm"]
+    builds = [
+        ("libbroadcast_ref.so", ["-O2", "-ffp-contract=off"]),
+        ("libbroadcast_ref_fast.so", ["-O3", "-march=x86-64-v3", "-funroll-loops"]),
+    ]
+    for name, flags in builds:
+        cmd = common + flags + ["-o", os.path.join(OUT, name)]
+        if verbose:
+            print("[oracle/_ref]", " ".join(cmd))
+        subprocess.check_call(cmd)
+    return True
+
+
+if __name__ == "__main__":
+    ok = build()
+    sys.exit(0 if ok or os.path.exists(os.path.join(OUT, "libbroadcast_ref.so")) else 1)
