@@ -1,0 +1,166 @@
+// Generic residual / tangent pipeline, instantiated once per tangent width BCAST_N by
+// generic_n0.cu / generic_n1.cu / generic_n5.cu (separate translation units keep build times low).
+#include "kernels.cuh"
+
+namespace bcast {
+
+// ---------------------------------------------------------------------------------------------
+// primitives over every cell including ghosts (rhs/primvisc.F:2-9)
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__global__ void k_prims(GridDesc g, SchemeConsts c, const double* __restrict__ w, const double* __restrict__ wd, double* __restrict__ prim,
+                        double* __restrict__ primd) {
+  using DT = TanOf<N>;
+  const int ii = blockIdx.x * blockDim.x + threadIdx.x;
+  const int jj = blockIdx.y * blockDim.y + threadIdx.y;
+  if (ii >= g.ni() || jj >= g.nj()) return;
+  const long long k = ii + (long long)jj * g.ldc;
+  Var<DT> q[5];
+#pragma unroll
+  for (int e = 0; e < 5; ++e) {
+    q[e].v = w[e * g.sc + k];
+    if constexpr (N > 0) {
+#pragma unroll
+      for (int n = 0; n < N; ++n) q[e].d.d[n] = wd[(long long)(n * 5 + e) * g.sc + k];
+    }
+  }
+  const CellPrims<DT> p = cell_prims(q, c);
+  const Var<DT> out[NPRIM] = {p.u, p.v, p.w, p.t, p.p, p.mu, p.h};
+#pragma unroll
+  for (int s = 0; s < NPRIM; ++s) {
+    prim[s * g.sc + k] = out[s].v;
+    if constexpr (N > 0) {
+#pragma unroll
+      for (int n = 0; n < N; ++n) primd[(long long)(n * NPRIM + s) * g.sc + k] = out[s].d.d[n];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// gradients of velx, vely on interior cells (flux_num_dnc5.F90:124-137)
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__global__ void k_grads(GridDesc g, FieldPtrs f, double* __restrict__ grad, double* __restrict__ gradd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (i > g.im || j > g.jm) return;
+  GlobalAcc<N> a(f, g, i, j);
+  const auto r = cell_gradients<0, 0>(a);
+  const long long k = g.cidx(i, j);
+  const decltype(r.u0) out[NGRAD] = {r.u0, r.u1, r.v0, r.v1};
+#pragma unroll
+  for (int s = 0; s < NGRAD; ++s) {
+    grad[s * g.sc + k] = out[s].v;
+    if constexpr (N > 0) {
+#pragma unroll
+      for (int n = 0; n < N; ++n) gradd[(long long)(n * NGRAD + s) * g.sc + k] = out[s].d.d[n];
+    }
+  }
+}
+
+// first ghost layer of the gradients by linear extrapolation (rhs/gradveloingh.F:1-19).  Only layer
+// h = 1 at non-corner positions is ever read by the faces (sensor at faces i = 1, im+1, j = 1, jm+1).
+static __global__ void k_grad_ghost(GridDesc g, double* __restrict__ grad, int nplanes_total) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int plane = blockIdx.y;
+  if (plane >= nplanes_total) return;
+  double* p = grad + (long long)plane * g.sc;
+  const int im = g.im, jm = g.jm;
+  if (t < im) {  // j sides
+    const int i = t + 1;
+    p[g.cidx(i, 0)] = 2.0 * p[g.cidx(i, 1)] - p[g.cidx(i, 2)];
+    p[g.cidx(i, jm + 1)] = 2.0 * p[g.cidx(i, jm)] - p[g.cidx(i, jm - 1)];
+  } else if (t < im + jm) {  // i sides
+    const int j = t - im + 1;
+    p[g.cidx(0, j)] = 2.0 * p[g.cidx(1, j)] - p[g.cidx(2, j)];
+    p[g.cidx(im + 1, j)] = 2.0 * p[g.cidx(im, j)] - p[g.cidx(im - 1, j)];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cell-centred balance (rhs/balance.F:2-15) of the four face fluxes of each cell
+// ---------------------------------------------------------------------------------------------
+template <int N, int DIR, class RD>
+__device__ __forceinline__ void face_dispatch(const FieldPtrs& f, const GridDesc& g, const SchemeConsts& c, bool wall, int i, int j,
+                                              Var<RD> (&hn)[5]) {
+  GlobalAcc<N> a(f, g, i, j);
+  if (DIR == 0) {
+    if (wall && j <= 2)
+      face_flux<0, true, FACE_MAIN>(a, c, hn);
+    else
+      face_flux<0, false, FACE_MAIN>(a, c, hn);
+  } else {
+    if (wall && j == 1)
+      face_flux<1, true, FACE_WALL>(a, c, hn);
+    else if (wall && j == 2)
+      face_flux<1, true, FACE_NEAR3>(a, c, hn);
+    else if (wall && j == 3)
+      face_flux<1, false, FACE_NEAR5>(a, c, hn);
+    else
+      face_flux<1, false, FACE_MAIN>(a, c, hn);
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(128) k_balance(GridDesc g, SchemeConsts c, FieldPtrs f, bool wall, Rect rc, double* __restrict__ out) {
+  using DT = TanOf<N>;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + rc.i0;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + rc.j0;
+  if (i > rc.i1 || j > rc.j1) return;
+  Var<DT> a0[5], a1[5], b0[5], b1[5];
+  face_dispatch<N, 0>(f, g, c, wall, i, j, a0);
+  face_dispatch<N, 0>(f, g, c, wall, i + 1, j, a1);
+  face_dispatch<N, 1>(f, g, c, wall, i, j, b0);
+  face_dispatch<N, 1>(f, g, c, wall, i, j + 1, b1);
+  const long long k = g.cidx(i, j);
+#pragma unroll
+  for (int e = 0; e < 5; ++e) {
+    const Var<DT> r = -(a1[e] - a0[e]) - (b1[e] - b0[e]);
+    if constexpr (N == 0) {
+      out[e * g.sc + k] = r.v;
+    } else {
+#pragma unroll
+      for (int n = 0; n < N; ++n) out[(long long)(n * 5 + e) * g.sc + k] = r.d.d[n];
+    }
+  }
+}
+
+template <int N>
+cudaError_t residual_generic_t(const GridDesc& g, const SchemeArgs& a, bool wall, double* out, const double* w, const double* wd,
+                                      const double* nx, const double* ny, const double* vol, const double* volf, const Rect* rect,
+                                      cudaStream_t st) {
+  const SchemeConsts c = make_consts(a.cp, a.cv, a.prandtl, a.gam, a.rgaz, a.cs, a.muref, a.tref, a.s_suth, a.k2, a.k4);
+  double* prim = scratch_doubles(0, (size_t)g.sc * NPRIM);
+  double* grad = scratch_doubles(1, (size_t)g.sc * NGRAD);
+  double* primd = N ? scratch_doubles(2, (size_t)g.sc * NPRIM * N) : nullptr;
+  double* gradd = N ? scratch_doubles(3, (size_t)g.sc * NGRAD * N) : nullptr;
+  if (!prim || !grad || (N && (!primd || !gradd))) return cudaErrorMemoryAllocation;
+  dim3 blk(32, 4);
+  dim3 gall((g.ni() + 31) / 32, (g.nj() + 3) / 4);
+  k_prims<N><<<gall, blk, 0, st>>>(g, c, w, wd, prim, primd);
+  FieldPtrs f{w, prim, grad, nx, ny, vol, volf, wd, primd, gradd};
+  dim3 gint((g.im + 31) / 32, (g.jm + 3) / 4);
+  k_grads<N><<<gint, blk, 0, st>>>(g, f, grad, gradd);
+  {
+    const int nt = g.im + g.jm;
+    k_grad_ghost<<<dim3((nt + 127) / 128, NGRAD), 128, 0, st>>>(g, grad, NGRAD);
+    if (N) k_grad_ghost<<<dim3((nt + 127) / 128, NGRAD * N), 128, 0, st>>>(g, gradd, NGRAD * N);
+  }
+  Rect rc = rect ? *rect : Rect{1, g.im, 1, g.jm};
+  if (rc.i1 >= rc.i0 && rc.j1 >= rc.j0) {
+    dim3 gb((rc.i1 - rc.i0 + 32) / 32, (rc.j1 - rc.j0 + 4) / 4);
+    k_balance<N><<<gb, blk, 0, st>>>(g, c, f, wall, rc, out);
+  }
+  return cudaGetLastError();
+}
+
+
+#define BCAST_CAT2(a, b) a##b
+#define BCAST_CAT(a, b) BCAST_CAT2(a, b)
+cudaError_t BCAST_CAT(residual_generic_, BCAST_N)(const GridDesc& g, const SchemeArgs& a, bool wall, double* out, const double* w,
+                                                 const double* wd, const double* nx, const double* ny, const double* vol,
+                                                 const double* volf, const Rect* rect, cudaStream_t st) {
+  return residual_generic_t<BCAST_N>(g, a, wall, out, w, wd, nx, ny, vol, volf, rect, st);
+}
+
+}  // namespace bcast

@@ -1,0 +1,98 @@
+// Device-side description of one structured block and the accessors the scheme templates use.
+//
+// Layout in HBM (structure of arrays, i fastest -- the reference's Fortran order):
+//   cell arrays   (im+2gh)   x (jm+2gh)   [x planes]   leading dimension ldc, plane stride sc
+//   node arrays   (im+2gh+1) x (jm+2gh+1) [x planes]   leading dimension ldn, plane stride sn
+// Fortran index (i,j) (lower bound 1-gh) <-> linear (i-1+gh) + (j-1+gh)*ld.
+#pragma once
+#include "dual.cuh"
+#include <type_traits>
+
+namespace bcast {
+
+struct GridDesc {
+  int im, jm, gh;
+  int ldc, ldn;
+  long long sc, sn;
+  BC_HD long long cidx(int i, int j) const { return (long long)(i - 1 + gh) + (long long)(j - 1 + gh) * ldc; }
+  BC_HD long long nidx(int i, int j) const { return (long long)(i - 1 + gh) + (long long)(j - 1 + gh) * ldn; }
+  BC_HD int ni() const { return im + 2 * gh; }
+  BC_HD int nj() const { return jm + 2 * gh; }
+};
+
+inline GridDesc make_grid(int im, int jm, int gh) {
+  GridDesc g;
+  g.im = im;
+  g.jm = jm;
+  g.gh = gh;
+  g.ldc = im + 2 * gh;
+  g.ldn = im + 2 * gh + 1;
+  g.sc = (long long)g.ldc * (jm + 2 * gh);
+  g.sn = (long long)g.ldn * (jm + 2 * gh + 1);
+  return g;
+}
+
+// number of primitive planes: u, v, w, T, p, mu, htot
+constexpr int NPRIM = 7;
+enum { PR_U = 0, PR_V = 1, PR_W = 2, PR_T = 3, PR_P = 4, PR_MU = 5, PR_H = 6 };
+// gradient planes: gradu(.,1), gradu(.,2), gradv(.,1), gradv(.,2)
+constexpr int NGRAD = 4;
+
+struct FieldPtrs {
+  const double* w;      // 5 planes
+  const double* prim;   // NPRIM planes
+  const double* grad;   // NGRAD planes
+  const double* nx;     // 2 planes (node layout)
+  const double* ny;     // 2 planes
+  const double* vol;    // 1 plane
+  const double* volf;   // 2 planes (cell layout)
+  // tangents: direction-major [n][plane]
+  const double* wd;
+  const double* primd;
+  const double* gradd;
+};
+
+template <int N>
+using TanOf = std::conditional_t<N == 0, Zero, Tan<(N == 0 ? 1 : N)>>;
+
+// Accessor over global arrays; every cell carries the same tangent type (none if N == 0).
+template <int N>
+struct GlobalAcc {
+  using DT = TanOf<N>;
+  FieldPtrs f;
+  long long c, n;  // linear indices of the base cell in cell / node layout
+  int ldc, ldn;
+  long long sc, sn;
+
+  __device__ __forceinline__ GlobalAcc(const FieldPtrs& f_, const GridDesc& g, int i, int j)
+      : f(f_), c(g.cidx(i, j)), n(g.nidx(i, j)), ldc(g.ldc), ldn(g.ldn), sc(g.sc), sn(g.sn) {}
+
+  __device__ __forceinline__ Var<DT> load(const double* v, const double* d, int plane, int nplanes, long long k) const {
+    Var<DT> r;
+    r.v = __ldg(v + plane * sc + k);
+    if constexpr (N > 0) {
+#pragma unroll
+      for (int q = 0; q < N; ++q) r.d.d[q] = __ldg(d + (long long)(q * nplanes + plane) * sc + k);
+    }
+    return r;
+  }
+  template <int OI, int OJ> __device__ __forceinline__ long long ck() const { return c + OI + (long long)OJ * ldc; }
+  template <int OI, int OJ> __device__ __forceinline__ long long nk() const { return n + OI + (long long)OJ * ldn; }
+
+  template <int OI, int OJ> __device__ __forceinline__ Var<DT> W(int e) const { return load(f.w, f.wd, e, 5, ck<OI, OJ>()); }
+  template <int OI, int OJ> __device__ __forceinline__ Var<DT> U() const { return load(f.prim, f.primd, PR_U, NPRIM, ck<OI, OJ>()); }
+  template <int OI, int OJ> __device__ __forceinline__ Var<DT> V() const { return load(f.prim, f.primd, PR_V, NPRIM, ck<OI, OJ>()); }
+  template <int OI, int OJ> __device__ __forceinline__ Var<DT> Wz() const { return load(f.prim, f.primd, PR_W, NPRIM, ck<OI, OJ>()); }
+  template <int OI, int OJ> __device__ __forceinline__ Var<DT> T() const { return load(f.prim, f.primd, PR_T, NPRIM, ck<OI, OJ>()); }
+  template <int OI, int OJ> __device__ __forceinline__ Var<DT> P() const { return load(f.prim, f.primd, PR_P, NPRIM, ck<OI, OJ>()); }
+  template <int OI, int OJ> __device__ __forceinline__ Var<DT> Mu() const { return load(f.prim, f.primd, PR_MU, NPRIM, ck<OI, OJ>()); }
+  template <int OI, int OJ> __device__ __forceinline__ Var<DT> H() const { return load(f.prim, f.primd, PR_H, NPRIM, ck<OI, OJ>()); }
+  template <int OI, int OJ> __device__ __forceinline__ Var<DT> GU(int cc) const { return load(f.grad, f.gradd, cc, NGRAD, ck<OI, OJ>()); }
+  template <int OI, int OJ> __device__ __forceinline__ Var<DT> GV(int cc) const { return load(f.grad, f.gradd, 2 + cc, NGRAD, ck<OI, OJ>()); }
+  template <int OI, int OJ> __device__ __forceinline__ double NX(int k) const { return __ldg(f.nx + k * sn + nk<OI, OJ>()); }
+  template <int OI, int OJ> __device__ __forceinline__ double NY(int k) const { return __ldg(f.ny + k * sn + nk<OI, OJ>()); }
+  template <int OI, int OJ> __device__ __forceinline__ double VOL() const { return __ldg(f.vol + ck<OI, OJ>()); }
+  template <int OI, int OJ> __device__ __forceinline__ double VOLF(int k) const { return __ldg(f.volf + k * sc + ck<OI, OJ>()); }
+};
+
+}  // namespace bcast

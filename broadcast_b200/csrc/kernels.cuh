@@ -1,0 +1,70 @@
+// Internal C++ interface between the translation units of libbroadcast_b200 (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include "bc.cuh"
+#include "grid.cuh"
+#include "scheme.cuh"
+
+namespace bcast {
+
+// grow-only per-device scratch arena (prims / gradients / tangents of the generic path)
+double* scratch_doubles(int slot, size_t count);
+void scratch_release_all();
+
+struct SchemeArgs {
+  double cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4;
+};
+
+// rectangle of interior cells (Fortran indices, inclusive) a kernel is restricted to
+struct Rect {
+  int i0, i1, j0, j1;
+};
+
+// Generic ("reference-shaped") residual and tangent: prims -> gradients (+ ghost-layer extrapolation)
+// -> cell-centred balance of four face fluxes.  ndir == 0: residual into `out` (5 planes, interior
+// cells of `rect` only).  ndir in {1,5}: tangent(s) into `out` ([ndir][5] planes).
+cudaError_t launch_residual_generic(const GridDesc& g, const SchemeArgs& a, bool wall, int ndir, double* out, const double* w,
+                                    const double* wd, const double* nx, const double* ny, const double* vol, const double* volf,
+                                    const Rect* rect, cudaStream_t st);
+
+// boundary fills, ndir == 0 primal, else tangent (w and wd ghosts are both written)
+cudaError_t launch_bc_wall(const GridDesc& g, const BcLine& b, double gam, int ndir, double* w, double* wd, cudaStream_t st);
+cudaError_t launch_bc_noref(const GridDesc& g, const BcLine& b, double gam, int ndir, double* w, double* wd, const double* wbd, int lm,
+                            const double* nx, const double* ny, cudaStream_t st);
+cudaError_t launch_bc_inlet(const GridDesc& g, const BcLine& b, double gam, int ndir, double* w, double* wd, const double* field, int lm,
+                            const double* nx, const double* ny, cudaStream_t st);
+cudaError_t launch_bc_extrap(const GridDesc& g, const BcLine& b, int ndir, double* w, double* wd, cudaStream_t st);
+
+// rectangular window copy (jn_match): arrays described by (ld, plane stride, origin offsets)
+struct Window {
+  int ld;            // leading dimension
+  long long stride;  // plane stride
+  int lo_i, lo_j;    // Fortran lower bounds of the two dimensions
+};
+cudaError_t launch_jn_match(double* wr, const Window& r, const int prr[4], const double* wd, const Window& d, const int prd[4],
+                            const int tr[2], int em, cudaStream_t st);
+
+// colouring seeds and COO scatter (misc/ComputeJacobian.f90)
+cudaError_t launch_testvector(const GridDesc& g, double* wd, int ndir, int m, int l, int k, const int* zone /*null or istart,iend,jstart,jend*/,
+                              cudaStream_t st);
+enum ScatterKind {
+  SCATTER_JV = 0,            // computejacobianfromjv            :292-355
+  SCATTER_JV_RELAXED = 1,    // computejacobianfromjv_relaxed    :503-570
+  SCATTER_DZ = 2,            // computejacobianfromdz            :708-779
+  SCATTER_JV_RELAXED_JN = 3, // computejacobianfromjv_relaxed_withjn :847-926
+  SCATTER_JV_JN = 4,         // computejacobianfromjv_withjn     :929-999
+  SCATTER_JV_DBYVOL = 5,     // computejacobianfromjv_dbyvol     :643-706
+  SCATTER_JV_RELAXED_DBYVOL = 6,
+};
+// writes the contiguous slot range [base, base + 5*im*jm) of colour (m,l,k) into seg_* (length 5*im*jm)
+cudaError_t launch_scatter(const GridDesc& g, int kind, double* seg_jac, int* seg_ia, int* seg_ja, const double* resd, int m, int l,
+                           int k, const double* coefdiag /*im x jm or null*/, const double* vol /*cell layout or null*/, cudaStream_t st);
+
+// norms (srcfv/norm.F90)
+cudaError_t launch_norms(const GridDesc& g, const double* res, double* out10 /*device: sum r^2 [5], sum r^10 [5]*/, cudaStream_t st);
+
+// fused, shared-memory tiled primal residual (residual_tile.cu)
+cudaError_t launch_residual_tiled(const GridDesc& g, const SchemeArgs& a, bool wall, double* res, const double* w, const double* nx,
+                                  const double* ny, const double* vol, const double* volf, cudaStream_t st);
+
+}  // namespace bcast

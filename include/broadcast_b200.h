@@ -1,0 +1,155 @@
+/* broadcast_b200 -- C ABI of the B200 (sm_100a) implementation of BROADCAST's finite-volume hot path.
+ *
+ * Drop-in boundary: the reference (onera/Broadcast) exposes its Fortran kernels to Python through
+ * f2py modules (srcfv.f_sch, srcfv.f_lin, srcfv.f_bnd, srcfv.f_geom, srcfv.f_norm, misc.f_misc ...).
+ * Every `bc_*` function below replaces ONE of those f2py entry points: same name (prefixed), same
+ * argument order as the Fortran dummy list, same array conventions:
+ *
+ *   - all arrays are caller-owned HOST memory, float64 / int32, column-major (Fortran order),
+ *     padded shapes  cell arrays (im+2gh, jm+2gh[,5]),  node/face arrays (im+2gh+1, jm+2gh+1[,2]),
+ *     Fortran lower bound 1-gh;  `inout` arrays are modified in place;
+ *   - `interf`, `prr`, `prd` are int32[4] = {imin, jmin, imax, jmax} (1-based, inclusive: the Fortran
+ *     integer(2,2) read as p(1,1), p(1,2), p(2,1), p(2,2), i.e. the C-order image of the numpy array
+ *     [[imin,jmin],[imax,jmax]] the drivers build);  `loc` is one of "Ilo","Ihi","Jlo","Jhi";
+ *   - return value: 0 on success, otherwise a negative BC_ERR_* code or a positive cudaError_t
+ *     (the Fortran has no error path; the Python shim raises on non-zero).
+ *
+ * The `bcd_*` functions are the same operations on DEVICE pointers (dense layout identical to the
+ * host layout), asynchronous on `stream` (a cudaStream_t passed as void*): this is the resident mode
+ * used for whole Newton/Jacobian steps without host round trips.
+ *
+ * There is no CPU fallback: every entry point returns an error if no CUDA device is usable.
+ */
+#ifndef BROADCAST_B200_H
+#define BROADCAST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BC_OK 0
+#define BC_ERR_ARG (-1)     /* invalid argument (bad loc string, non-positive size, unsupported gh ...) */
+#define BC_ERR_NODEV (-2)   /* no CUDA device */
+#define BC_ERR_ALLOC (-3)   /* device allocation failed */
+#define BC_ERR_UNSUPPORTED (-4)
+
+/* library / device info */
+int bc_version(void);
+int bc_device_count(void);
+const char* bc_last_error(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+long long bc_launch_count(void);
+
+/* ---- residual: srcfv/rhs/flux_num_dnc5.F90:7-226 (f_sch.flux_num_dnc5_2d),
+ *      srcfv/rhs/flux_num_dnc5_nowall.F90:120-157 (f_sch.flux_num_dnc5_nowall_2d).
+ *      x0,y0,xc,yc are accepted and ignored (unused by the reference body). residu ghosts untouched. */
+int bc_flux_num_dnc5_2d(double* residu, const double* w, const double* x0, const double* y0, const double* nx,
+                        const double* ny, const double* xc, const double* yc, const double* vol, const double* volf,
+                        int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
+                        double muref, double tref, double s_suth, double k2, double k4, int im, int jm);
+int bc_flux_num_dnc5_nowall_2d(double* residu, const double* w, const double* x0, const double* y0, const double* nx,
+                               const double* ny, const double* xc, const double* yc, const double* vol,
+                               const double* volf, int gh, double cp, double cv, double prandtl, double gam,
+                               double rgaz, double cs, double muref, double tref, double s_suth, double k2, double k4,
+                               int im, int jm);
+
+/* ---- tangent: srcfv/tangent/flux_num_dnc5_d.f90:15-3870 (f_lin.flux_num_dnc5_2d_d).
+ *      residud is zeroed everywhere then filled on interior cells; residu is NOT written (:3853-3868). */
+int bc_flux_num_dnc5_2d_d(double* residu, double* residud, const double* w, const double* wd, const double* x0,
+                          const double* y0, const double* nx, const double* ny, const double* xc, const double* yc,
+                          const double* vol, const double* volf, int gh, double cp, double cv, double prandtl,
+                          double gam, double rgaz, double cs, double muref, double tref, double s_suth, double k2,
+                          double k4, int im, int jm);
+int bc_flux_num_dnc5_nowall_2d_d(double* residu, double* residud, const double* w, const double* wd, const double* x0,
+                                 const double* y0, const double* nx, const double* ny, const double* xc,
+                                 const double* yc, const double* vol, const double* volf, int gh, double cp, double cv,
+                                 double prandtl, double gam, double rgaz, double cs, double muref, double tref,
+                                 double s_suth, double k2, double k4, int im, int jm);
+
+/* ---- boundary fills (f_bnd.*) and their tangents (f_lin.*_d): srcfv/borders/*.F90, srcfv/tangent/bc_*_d.f90 */
+int bc_bc_wall_viscous_adia_2d(double* w, const char* loc, double gam, const int32_t* interf, int gh, int im, int jm);
+int bc_bc_wall_viscous_adia_2d_d(double* w, double* wd, const char* loc, double gam, const int32_t* interf, int gh,
+                                 int im, int jm);
+int bc_bc_no_reflexion_2d(double* w, const double* wbd, const char* loc, const int32_t* interf, const double* nx,
+                          const double* ny, double gam, int gh, int im, int jm, int lm);
+int bc_bc_no_reflexion_2d_d(double* w, double* wd, const double* wbd, const char* loc, const int32_t* interf,
+                            const double* nx, const double* ny, double gam, int gh, int im, int jm, int lm);
+int bc_bc_supandsubinlet_2d(double* w, const char* loc, const int32_t* interf, const double* field, const double* nx,
+                            const double* ny, double gam, int im, int jm, int lm, int gh);
+int bc_bc_supandsubinlet_2d_d(double* w, double* wd, const char* loc, const int32_t* interf, const double* field,
+                              const double* nx, const double* ny, double gam, int im, int jm, int lm, int gh);
+int bc_bc_extrapolate_o2_2d(double* w, const char* loc, const int32_t* interf, int im, int jm, int gh, int em);
+int bc_bc_extrapolate_o2_2d_d(double* w, double* wd, const char* loc, const int32_t* interf, int im, int jm, int gh,
+                              int em);
+/* srcfv/borders/jn_match.F90:3-66 (3-D arrays, em planes) and jn_match_geom.F90:7-69 (2-D arrays) */
+int bc_jn_match_2d(double* wr, const int32_t* prr, int gh1r, int gh2r, int gh3r, int gh4r, int imr, int jmr,
+                   const double* wd, const int32_t* prd, int gh1d, int gh2d, int gh3d, int gh4d, int imd, int jmd,
+                   const int32_t* tr, int em);
+int bc_jn_match_geom_2d(double* wr, const int32_t* prr, int gh1r, int gh2r, int gh3r, int gh4r, int imr, int jmr,
+                        const double* wd, const int32_t* prd, int gh1d, int gh2d, int gh3d, int gh4d, int imd, int jmd,
+                        const int32_t* tr);
+
+/* ---- geometry: srcfv/geom/computegeom.F90:3-104 (f_geom.computegeom_2d), all arrays in place */
+int bc_computegeom_2d(double* x0, double* y0, double* nx, double* ny, double* xc, double* yc, double* vol,
+                      double* volf, int im, int jm, int gh);
+
+/* ---- colouring seeds and COO scatter: misc/ComputeJacobian.f90 (f_misc.*); m,l,k are 0-based.
+ *      jac/ia/ja have nbentry = 25*(2gh+1)^2*im*jm entries; one call writes the contiguous slot range of
+ *      colour (m,l,k) (:524). */
+int bc_testvector(double* wd, int m, int l, int k, int gh, int im, int jm);
+int bc_testvector_partial(double* wd, int m, int l, int k, int gh, int im, int jm, int istart, int iend, int jstart,
+                          int jend);
+int bc_computejacobianfromjv(double* jac, int32_t* ia, int32_t* ja, const double* resd, int m, int l, int k, int gh,
+                             int im, int jm, int64_t nbentry);
+int bc_computejacobianfromjv_relaxed(double* jac, int32_t* ia, int32_t* ja, const double* resd, int m, int l, int k,
+                                     int gh, int im, int jm, int64_t nbentry, const double* coefdiag);
+int bc_computejacobianfromjv_relaxed_withjn(double* jac, int32_t* ia, int32_t* ja, const double* resd, int m, int l,
+                                            int k, int gh, int im, int jm, int64_t nbentry, const double* coefdiag);
+int bc_computejacobianfromjv_withjn(double* jac, int32_t* ia, int32_t* ja, const double* resd, int m, int l, int k,
+                                    int gh, int im, int jm, int64_t nbentry);
+int bc_computejacobianfromdz(double* jac, int32_t* ia, int32_t* ja, const double* dz, int m, int l, int k, int gh,
+                             int im, int jm, int64_t nbentry);
+
+/* ---- norms: srcfv/norm.F90:2-77 (f_norm.compute_norml2 / compute_norml2inf).  Reduction order on the
+ *      device is a tree (the Fortran sums j-outer, i-inner sequentially). */
+int bc_compute_norml2(double* norm, double* nmoy, const double* rhs, int im, int jm, int gh);
+int bc_compute_norml2inf(double* norm, double* ninf, const double* rhs, int im, int jm, int gh);
+
+/* =====================================================================================================
+ * Device-pointer (resident) API.  Same semantics, no host transfers, asynchronous on `stream`.
+ * `ndir` = 0 primal; 1 or 5 = number of tangent directions held in wd / residud as [ndir][5] planes.
+ * ===================================================================================================== */
+int bcd_residual(double* residu, const double* w, const double* nx, const double* ny, const double* vol,
+                 const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
+                 double muref, double tref, double s_suth, double k2, double k4, int im, int jm, int wall,
+                 int use_generic, void* stream);
+int bcd_tangent(double* residud, const double* w, const double* wd, int ndir, const double* nx, const double* ny,
+                const double* vol, const double* volf, int gh, double cp, double cv, double prandtl, double gam,
+                double rgaz, double cs, double muref, double tref, double s_suth, double k2, double k4, int im, int jm,
+                int wall, const int32_t* rect /* null or {i0,i1,j0,j1} */, void* stream);
+int bcd_bc_wall_viscous_adia(double* w, double* wd, int ndir, const char* loc, double gam, const int32_t* interf,
+                             int gh, int im, int jm, void* stream);
+int bcd_bc_no_reflexion(double* w, double* wd, int ndir, const double* wbd, const char* loc, const int32_t* interf,
+                        const double* nx, const double* ny, double gam, int gh, int im, int jm, int lm, void* stream);
+int bcd_bc_supandsubinlet(double* w, double* wd, int ndir, const char* loc, const int32_t* interf,
+                          const double* field, const double* nx, const double* ny, double gam, int im, int jm, int lm,
+                          int gh, void* stream);
+int bcd_bc_extrapolate_o2(double* w, double* wd, int ndir, const char* loc, const int32_t* interf, int im, int jm,
+                          int gh, void* stream);
+int bcd_jn_match(double* wr, const int32_t* prr, int gh1r, int gh2r, int gh3r, int gh4r, int imr, int jmr,
+                 const double* wd, const int32_t* prd, int gh1d, int gh2d, int gh3d, int gh4d, int imd, int jmd,
+                 const int32_t* tr, int em, void* stream);
+int bcd_testvector(double* wd, int ndir, int m, int l, int k, int gh, int im, int jm, const int32_t* zone,
+                   void* stream);
+/* kind: 0 jv, 1 jv_relaxed, 2 dz, 3 jv_relaxed_withjn, 4 jv_withjn, 5 jv_dbyvol, 6 jv_relaxed_dbyvol */
+int bcd_scatter(int kind, double* seg_jac, int32_t* seg_ia, int32_t* seg_ja, const double* resd, int m, int l, int k,
+                int gh, int im, int jm, const double* coefdiag, const double* vol, void* stream);
+/* out10 (device): sum r^2 per equation [5], sum r^10 per equation [5] */
+int bcd_norm_sums(double* out10, const double* rhs, int im, int jm, int gh, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BROADCAST_B200_H */

@@ -1,0 +1,126 @@
+"""GPU parity tests: the CUDA path through the C ABI vs the CPU oracle (oracle/_ref) on the same
+seeded inputs.  Tolerance: 1e-12 relative to the max magnitude of each equation plane (the bound
+BASELINE.json's north_star states); integer outputs (colouring, IA, JA) bit-exact."""
+import numpy as np
+import pytest
+
+import helpers as H
+from broadcast_b200 import cases
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+CASES = [("bl", 60, 40), ("bl", 97, 33), ("cyl", 70, 40)]
+
+
+@pytest.mark.parametrize("kind,im,jm", CASES)
+def test_geometry_bit_exact(gpu, ref, kind, im, jm):
+    a = H.make_case(kind, im, jm, gpu)
+    b = H.make_case(kind, im, jm, ref)
+    for name in ("x0", "y0", "nx", "ny", "xc", "yc", "vol", "volf"):
+        x, y = getattr(a, name), getattr(b, name)
+        assert np.array_equal(x, y), (name, np.abs(x - y).max())
+
+
+@pytest.mark.parametrize("kind,im,jm", CASES)
+def test_boundary_fill_and_residual(gpu, ref, kind, im, jm):
+    a = H.make_case(kind, im, jm, gpu)
+    b = H.make_case(kind, im, jm, ref)
+    wa, ra = H.residual_sequence(gpu, a)
+    wb, rb = H.residual_sequence(ref, b)
+    assert np.all(H.rel_err(wa, wb) < 1e-14), H.rel_err(wa, wb)
+    assert np.all(H.rel_err(ra, rb) < TOL), H.rel_err(ra, rb)
+    # ghosts of the residual are never written
+    gh = a.gh
+    assert np.all(ra[:gh] == 0) and np.all(ra[:, :gh] == 0)
+
+
+@pytest.mark.parametrize("kind,im,jm", CASES[:2])
+def test_residual_nowall(gpu, ref, kind, im, jm):
+    a = H.make_case(kind, im, jm, gpu)
+    b = H.make_case(kind, im, jm, ref)
+    _, ra = H.residual_sequence(gpu, a, "flux_num_dnc5_nowall_2d")
+    _, rb = H.residual_sequence(ref, b, "flux_num_dnc5_nowall_2d")
+    assert np.all(H.rel_err(ra, rb) < TOL), H.rel_err(ra, rb)
+
+
+def test_residual_with_spanwise_velocity(gpu, ref):
+    a = H.make_case("bl", 60, 40, gpu, with_w=True)
+    b = H.make_case("bl", 60, 40, ref, with_w=True)
+    _, ra = H.residual_sequence(gpu, a)
+    _, rb = H.residual_sequence(ref, b)
+    assert np.abs(rb[..., 3]).max() > 0
+    assert np.all(H.rel_err(ra, rb) < TOL), H.rel_err(ra, rb)
+
+
+@pytest.mark.parametrize("kind,im,jm", CASES)
+def test_tangent_random_direction(gpu, ref, kind, im, jm):
+    a = H.make_case(kind, im, jm, gpu, with_w=True)
+    b = H.make_case(kind, im, jm, ref, with_w=True)
+    wa, _ = H.residual_sequence(gpu, a)
+    wb, _ = H.residual_sequence(ref, b)
+    rng = np.random.default_rng(1)
+    wd = np.asfortranarray(rng.standard_normal(wa.shape))
+    wda, rda = H.tangent_sequence(gpu, a, wa, wd)
+    wdb, rdb = H.tangent_sequence(ref, b, wb, wd)
+    assert np.all(H.rel_err(wda, wdb) < 1e-13), H.rel_err(wda, wdb)
+    assert np.all(H.rel_err(rda, rdb) < TOL), H.rel_err(rda, rdb)
+
+
+@pytest.mark.parametrize("kind,im,jm", [("bl", 60, 40), ("cyl", 70, 40)])
+def test_colour_loop_coo(gpu, ref, kind, im, jm):
+    """a sample of colours through the full drop-in sequence: IA/JA bit-exact, values to TOL"""
+    a = H.make_case(kind, im, jm, gpu)
+    b = H.make_case(kind, im, jm, ref)
+    wa, _ = H.residual_sequence(gpu, a)
+    wb, _ = H.residual_sequence(ref, b)
+    colours = [(0, 0, 0), (1, 3, 2), (4, 6, 6), (2, 5, 0), (3, 0, 4), (4, 4, 1)]
+    rng = np.random.default_rng(2)
+    coef = np.asfortranarray(rng.uniform(0.5, 1.5, size=(im, jm)))
+    ja_, ia_a, ja_a = H.jacobian_sequence(gpu, a, wa, colours, coef)
+    jb_, ia_b, ja_b = H.jacobian_sequence(ref, b, wb, colours, coef)
+    assert np.array_equal(ia_a, ia_b)
+    assert np.array_equal(ja_a, ja_b)
+    scale = np.abs(jb_).max()
+    assert np.abs(ja_ - jb_).max() < TOL * scale
+
+
+def test_scatter_variants_integer_exact(gpu, ref):
+    im, jm, gh = 35, 23, 3
+    s = 2 * gh + 1
+    rng = np.random.default_rng(3)
+    resd = np.asfortranarray(rng.standard_normal((im + 2 * gh, jm + 2 * gh, 5)))
+    coef = np.asfortranarray(rng.uniform(0.5, 1.5, size=(im, jm)))
+    nb = 25 * s * s * im * jm
+    for name, extra in (("computejacobianfromjv", (im, jm)), ("computejacobianfromjv_relaxed", (coef,)),
+                        ("computejacobianfromjv_relaxed_withjn", (coef,)), ("computejacobianfromjv_withjn", (im, jm)),
+                        ("computejacobianfromdz", (im, jm))):
+        out = []
+        for mods in (gpu, ref):
+            jac, ia, ja = np.zeros(nb), np.zeros(nb, np.int32), np.zeros(nb, np.int32)
+            for (m, l, k) in [(0, 0, 0), (2, 3, 3), (4, 6, 5), (1, 4, 0), (3, 0, 6), (4, 6, 6)]:
+                getattr(mods["f_misc"], name)(jac, ia, ja, resd, m, l, k, gh, *extra)
+            out.append((jac, ia, ja))
+        assert np.array_equal(out[0][1], out[1][1]), name
+        assert np.array_equal(out[0][2], out[1][2]), name
+        assert np.array_equal(out[0][0], out[1][0]), name
+
+
+def test_testvector(gpu, ref):
+    im, jm, gh = 30, 22, 3
+    for (m, l, k) in [(0, 0, 0), (4, 6, 6), (2, 3, 1)]:
+        a = np.asfortranarray(np.ones((im + 2 * gh, jm + 2 * gh, 5)))
+        b = a.copy(order="F")
+        gpu["f_misc"].testvector(a, m, l, k, gh, im, jm)
+        ref["f_misc"].testvector(b, m, l, k, gh, im, jm)
+        assert np.array_equal(a, b)
+        assert a.sum() == len(range(l + 1, im + 1, 7)) * len(range(k + 1, jm + 1, 7))
+
+
+def test_norms(gpu, ref):
+    a = H.make_case("bl", 60, 40, gpu)
+    _, ra = H.residual_sequence(gpu, a)
+    na, ia = gpu["f_norm"].compute_norml2inf(ra, a.im, a.jm, a.gh)
+    nb, ib = ref["f_norm"].compute_norml2inf(ra, a.im, a.jm, a.gh)
+    assert np.allclose(na, nb, rtol=1e-13, atol=0)
+    assert np.allclose(ia, ib, rtol=1e-13, atol=0)
