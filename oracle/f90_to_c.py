@@ -323,6 +323,7 @@ class Var:
     intent: str = ""
     is_arg: bool = False
     assigned: bool = False
+    is_pointer: bool = False
 
 
 @dataclass
@@ -389,8 +390,11 @@ def parse_decl(stmt: str, vars_: Dict[str, Var]) -> bool:
         ents = rest
     dims = None
     intent = ""
+    is_pointer = False
     for a in split_top(attrs.strip().lstrip(",")):
         a = a.strip()
+        if a == "pointer":
+            is_pointer = True
         if a.startswith("dimension"):
             dims = parse_dims(a[a.index("(") + 1 : a.rindex(")")])
         elif a.startswith("intent"):
@@ -408,10 +412,12 @@ def parse_decl(stmt: str, vars_: Dict[str, Var]) -> bool:
         v = vars_.get(nm)
         if v is None:
             vars_[nm] = Var(nm, typ, edims, intent)
+            v = vars_[nm]
         else:
             v.typ = typ
             v.dims = edims
             v.intent = intent
+        v.is_pointer = is_pointer
     return True
 
 
@@ -790,7 +796,10 @@ class Emitter:
         if s == "continue":
             return
         if "=>" in s:
-            return  # pointer association, never dereferenced in the supported files
+            # scalar pointer association  p => t  (jn_match_geom.F90:46-52 dereferences them)
+            lhs, rhs = [t.strip() for t in s.split("=>", 1)]
+            self.emit(f"{lhs}_q = &{self.cname(rhs)};")
+            return
         # assignment: find top-level '=' that is not part of ==, /=, <=, >=
         depth = 0
         for i, ch in enumerate(s):
@@ -846,7 +855,12 @@ class Emitter:
                         hdr.append(f"#define {name}_ (*{name}_r)")
                         undef.append(f"{name}_")
                     continue
-                if v.typ == "char":
+                if v.is_pointer:
+                    ct = 'double' if v.typ == 'real' else 'int'
+                    hdr.append(f"  {ct} {name}_dummy = 0; {ct} *{name}_q = &{name}_dummy;")
+                    hdr.append(f"#define {name}_ (*{name}_q)")
+                    undef.append(f"{name}_")
+                elif v.typ == "char":
                     hdr.append(f"  const char *{name}_ = \"\"; (void){name}_;")
                 else:
                     hdr.append(f"  {'double' if v.typ == 'real' else 'int'} {name}_ = 0; (void){name}_;")
