@@ -1,0 +1,147 @@
+// Device-resident colour loop: the reference algorithm (seed -> linearised boundary fills -> tangent
+// -> scatter; BROADCAST_npz.py:1068-1127, misc/ComputeJacobian.f90) with the five variables of a
+// colour (l,k) carried together as five tangent directions, so 49 passes instead of 245.
+#include <vector>
+#include "../../include/broadcast_b200.h"
+#include "kernels.cuh"
+
+namespace bcast {
+void count_launches(int n);
+
+static cudaError_t apply_bc_list(const GridDesc& g, double gam, int ndir, double* w, double* wd, const double* nx, const double* ny,
+                                 const bc_desc_t* bcs, int nbcs, cudaStream_t st) {
+  for (int b = 0; b < nbcs; ++b) {
+    const bc_desc_t& d = bcs[b];
+    cudaError_t e = cudaSuccess;
+    if (d.kind == BC_KIND_JOIN) {
+      Window win{g.ldc, g.sc, 1 - g.gh, 1 - g.gh};
+      if (ndir > 0) e = launch_jn_match(wd, win, d.window, wd, win, d.prd, d.tr, 5 * ndir, st);
+      if (e == cudaSuccess) e = launch_jn_match(w, win, d.window, w, win, d.prd, d.tr, 5, st);
+      count_launches(ndir > 0 ? 2 : 1);
+    } else {
+      BcLine line;
+      if (!decode_interface(d.loc, d.window, line)) return cudaErrorInvalidValue;
+      switch (d.kind) {
+        case BC_KIND_INLET: e = launch_bc_inlet(g, line, gam, ndir, w, wd, d.table, d.lm, nx, ny, st); break;
+        case BC_KIND_NOREF: e = launch_bc_noref(g, line, gam, ndir, w, wd, d.table, d.lm, nx, ny, st); break;
+        case BC_KIND_EXTRAP: e = launch_bc_extrap(g, line, ndir, w, wd, st); break;
+        case BC_KIND_WALL: e = launch_bc_wall(g, line, gam, ndir, w, wd, st); break;
+        default: return cudaErrorInvalidValue;
+      }
+      count_launches(1);
+    }
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+// scatter of the five directions of colour (l,k): same integer rules as k_scatter, writing straight
+// into the reference's slot order for m = 0..4
+__global__ void k_scatter5(GridDesc g, int kind, double* __restrict__ jac, int* __restrict__ ia, int* __restrict__ ja,
+                           const double* __restrict__ resd5, int l, int k, const double* __restrict__ coefdiag,
+                           const double* __restrict__ vol, Rect rc) {
+  const int im = g.im, jm = g.jm, gh = g.gh, s = 2 * gh + 1;
+  const int wi = rc.i1 - rc.i0 + 1, wj = rc.j1 - rc.j0 + 1;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= 5LL * wi * wj) return;
+  const int i = (int)(t % wi) + rc.i0;
+  const int j = (int)((t / wi) % wj) + rc.j0;
+  const int e = (int)(t / ((long long)wi * wj)) + 1;
+  const bool withjn = kind == SCATTER_JV_RELAXED_JN || kind == SCATTER_JV_JN;
+  const int dummy_ia = 5 * im * jm - (withjn ? 2 : 1);
+  const int row = e - 1 + (j - 1) * 5 + (i - 1) * jm * 5;
+  bool ok = true;
+  int valj, vali = 0;
+  if (kind == SCATTER_DZ) {
+    if (k <= gh) valj = (j <= k + 1 + gh) ? k : (j - (k + 1) + gh) / s * s + k;
+    else valj = (j <= k - gh) ? jm + 1 : (j - (k + 1) + gh) / s * s + k;
+  } else {
+    valj = (j <= k + 1 + gh) ? k : (j - gh - (k + 1) + 2 * gh) / s * s + k;
+  }
+  if (valj >= jm) ok = false;
+  if (ok) {
+    if (l <= gh) {
+      vali = (i <= l + 1 + gh) ? l : (i - (l + 1) + gh) / s * s + l;
+    } else {
+      if (i <= l - gh) vali = withjn ? im - 1 - 2 * gh + l : im + 1;
+      else vali = (i - (l + 1) + gh) / s * s + l;
+    }
+    if (vali >= im) {
+      if (withjn && vali - im <= gh - 1) vali = l;
+      else ok = false;
+    }
+  }
+  const long long n = 5LL * im * jm;
+  const long long cell = (long long)(i - 1) + (long long)(j - 1) * im + (long long)(e - 1) * im * jm;
+  const long long kc = g.cidx(i, j);
+#pragma unroll
+  for (int m = 0; m < 5; ++m) {
+    const long long slot = cell + (long long)k * n + (long long)l * n * s + (long long)m * n * s * s;
+    if (ok) {
+      const int col = m + valj * 5 + vali * jm * 5;
+      const double r = resd5[(long long)(m * 5 + (e - 1)) * g.sc + kc];
+      double val;
+      if (kind == SCATTER_DZ) {
+        val = r;
+      } else {
+        val = -r;
+        if ((kind == SCATTER_JV_RELAXED || kind == SCATTER_JV_RELAXED_JN || kind == SCATTER_JV_RELAXED_DBYVOL) && row == col)
+          val = -r + coefdiag[(i - 1) + (long long)(j - 1) * im];
+        if (kind == SCATTER_JV_DBYVOL || kind == SCATTER_JV_RELAXED_DBYVOL) val = val / vol[kc];
+      }
+      jac[slot] = val;
+      ia[slot] = row;
+      ja[slot] = col;
+    } else {
+      jac[slot] = 0.0;
+      ia[slot] = dummy_ia;
+      ja[slot] = 0;
+    }
+  }
+}
+
+}  // namespace bcast
+
+using namespace bcast;
+
+extern "C" int bcd_apply_bcs(double* w, const double* nx, const double* ny, double gam, int gh, int im, int jm, const bc_desc_t* bcs,
+                             int nbcs, void* stream) {
+  if (im < 1 || jm < 1 || gh != 3) return BC_ERR_ARG;
+  const GridDesc g = make_grid(im, jm, gh);
+  cudaError_t e = apply_bc_list(g, gam, 0, w, nullptr, nx, ny, bcs, nbcs, (cudaStream_t)stream);
+  return e == cudaSuccess ? BC_OK : (int)e;
+}
+
+extern "C" int bcd_jacobian_coo(double* jac, int32_t* ia, int32_t* ja, double* w, const double* nx, const double* ny, const double* vol,
+                                const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
+                                double muref, double tref, double s_suth, double k2, double k4, int im, int jm, int wall,
+                                const bc_desc_t* bcs, int nbcs, int scatter_kind, const double* coefdiag, const int32_t* rect,
+                                void* stream) {
+  if (im < 1 || jm < 1 || gh != 3) return BC_ERR_ARG;
+  if (scatter_kind < 0 || scatter_kind > 6) return BC_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const GridDesc g = make_grid(im, jm, gh);
+  const SchemeArgs a{cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4};
+  const int s = 2 * gh + 1;
+  double* wd5 = scratch_doubles(20, (size_t)g.sc * 25);
+  double* resd5 = scratch_doubles(21, (size_t)g.sc * 25);
+  if (!wd5 || !resd5) return BC_ERR_ALLOC;
+  Rect rc{1, im, 1, jm};
+  if (rect) rc = Rect{rect[0], rect[1], rect[2], rect[3]};
+  if (rc.i1 < rc.i0 || rc.j1 < rc.j0) return BC_OK;
+  const long long nt = 5LL * (rc.i1 - rc.i0 + 1) * (rc.j1 - rc.j0 + 1);
+  for (int l = 0; l < s; ++l)
+    for (int k = 0; k < s; ++k) {
+      cudaError_t e = launch_testvector(g, wd5, 5, 0, l, k, nullptr, st);
+      if (e != cudaSuccess) return (int)e;
+      e = apply_bc_list(g, gam, 5, w, wd5, nx, ny, bcs, nbcs, st);
+      if (e != cudaSuccess) return (int)e;
+      e = launch_residual_generic(g, a, wall != 0, 5, resd5, w, wd5, nx, ny, vol, volf, &rc, st);
+      if (e != cudaSuccess) return (int)e;
+      k_scatter5<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(g, scatter_kind, jac, ia, ja, resd5, l, k, coefdiag, vol, rc);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return (int)e;
+      count_launches(7);
+    }
+  return BC_OK;
+}

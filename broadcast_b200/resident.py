@@ -148,3 +148,76 @@ class Block:
         self.step()
         res_pinned.copy_(self.res, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
+
+
+# ----------------------------------------------------------------------------------------------
+# whole colour loop on the device
+# ----------------------------------------------------------------------------------------------
+class _BcDesc(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("loc", ctypes.c_char * 4), ("window", ctypes.c_int32 * 4), ("prd", ctypes.c_int32 * 4),
+                ("tr", ctypes.c_int32 * 2), ("lm", ctypes.c_int32), ("table", ctypes.c_void_p)]
+
+
+_KIND = {"inflow": 1, "noref": 2, "outflow": 3, "wall": 4, "jn": 5}
+SCATTER = {"jv": 0, "jv_relaxed": 1, "dz": 2, "jv_relaxed_withjn": 3, "jv_withjn": 4, "jv_dbyvol": 5, "jv_relaxed_dbyvol": 6}
+
+
+def _bc_descs(blk: "Block"):
+    out = []
+    for bc in blk.bcs:
+        kind = bc[0]
+        if kind == "jn":
+            for prr, prd, tr in bc[1]:
+                d = _BcDesc()
+                d.kind = 5
+                d.window[:] = [int(v) for v in prr]
+                d.prd[:] = [int(v) for v in prd]
+                d.tr[:] = [int(v) for v in tr]
+                out.append(d)
+        else:
+            d = _BcDesc()
+            d.kind = _KIND[kind]
+            d.loc = bc[1]
+            d.window[:] = [int(v) for v in bc[2]]
+            if kind in ("inflow", "noref"):
+                d.table = bc[3].data_ptr()
+                d.lm = int(bc[4])
+            out.append(d)
+    arr = (_BcDesc * len(out))(*out)
+    return arr, len(out)
+
+
+def jacobian_coo(blk: "Block", coefdiag=None, kind=None, rect=None, out=None):
+    """The reference's COO lists (Jac, IA, JA; slot order of misc/ComputeJacobian.f90:524) assembled
+    on the device by the colour loop of BROADCAST_npz.py:1068-1127 with 5 directions per pass.
+    ``blk.w`` must hold the state with its ghosts filled (``blk.apply_bcs()``)."""
+    im, jm, gh = blk.im, blk.jm, blk.gh
+    s = 2 * gh + 1
+    nb = 25 * s * s * im * jm
+    if nb >= 2 ** 31:
+        raise _lib.BroadcastB200Error("the reference COO layout overflows 32-bit slots at this size; use the block-CSR assembly")
+    if kind is None:
+        kind = "jv_relaxed_withjn" if blk.case.periodic_i else "jv_relaxed"
+    if out is None:
+        jac = torch.zeros(nb, dtype=torch.float64, device=blk.device)
+        ia = torch.zeros(nb, dtype=torch.int32, device=blk.device)
+        ja = torch.zeros(nb, dtype=torch.int32, device=blk.device)
+    else:
+        jac, ia, ja = out
+    if coefdiag is None and "relaxed" in kind:
+        coefdiag = torch.zeros((jm, im), dtype=torch.float64, device=blk.device)
+    elif coefdiag is not None and not isinstance(coefdiag, torch.Tensor):
+        coefdiag = _t(coefdiag, blk.device)
+    descs, n = _bc_descs(blk)
+    r = np.asarray(rect, dtype=np.int32) if rect is not None else None
+    rc = blk.lib.bcd_jacobian_coo(_p(jac), _p(ia), _p(ja), _p(blk.w), _p(blk.nx), _p(blk.ny), _p(blk.vol), _p(blk.volf), gh, *blk._phys,
+                                  im, jm, blk.wall, descs, n, SCATTER[kind], _p(coefdiag),
+                                  r.ctypes.data_as(ctypes.c_void_p) if r is not None else ctypes.c_void_p(None), blk._stream())
+    _lib.check(rc, "bcd_jacobian_coo")
+    return jac, ia, ja
+
+
+def remove_zero_jac(jac, ia, ja, thresh=2e-16):
+    """BROADCAST_npz.py:129-135 on the device"""
+    keep = jac.abs() > thresh
+    return jac[keep], ia[keep], ja[keep]

@@ -149,6 +149,43 @@ int bcd_scatter(int kind, double* seg_jac, int32_t* seg_ia, int32_t* seg_ja, con
 /* out10 (device): sum r^2 per equation [5], sum r^10 per equation [5] */
 int bcd_norm_sums(double* out10, const double* rhs, int im, int jm, int gh, void* stream);
 
+/* =====================================================================================================
+ * Whole colour loop on the device (resident mode).
+ *
+ * bc_desc_t describes one boundary operation of the driver's ordered list (BROADCAST_npz.py:1018-1021,
+ * 1079-1082; handleBC.py:129-242).  Tables are DEVICE pointers.
+ * ===================================================================================================== */
+#define BC_KIND_INLET 1   /* bc_supandsubinlet_2d   table = field(lm,gh,5) */
+#define BC_KIND_NOREF 2   /* bc_no_reflexion_2d     table = wbd(lm,5)      */
+#define BC_KIND_EXTRAP 3  /* bc_extrapolate_o2_2d                          */
+#define BC_KIND_WALL 4    /* bc_wall_viscous_adia_2d                       */
+#define BC_KIND_JOIN 5    /* jn_match_2d of the block onto itself: window = receiver, prd = donor */
+typedef struct {
+  int32_t kind;
+  char loc[4];
+  int32_t window[4]; /* interf (kinds 1-4) or prr (kind 5): imin, jmin, imax, jmax */
+  int32_t prd[4];    /* kind 5 only */
+  int32_t tr[2];     /* kind 5 only */
+  int32_t lm;
+  const double* table;
+} bc_desc_t;
+
+/* Reference colour loop (BROADCAST_npz.py:1068-1127 / cylinder.py:941-978) entirely on the device:
+ * for every colour (l,k): seeds for the 5 variables at once (vector tangent mode), linearised boundary
+ * fills in list order, tangent of the residual, scatter.  Output = the reference's own COO arrays
+ * (jac, ia, ja of length 25*(2gh+1)^2*im*jm, slot order of misc/ComputeJacobian.f90:524), on the device.
+ * scatter_kind as in bcd_scatter.  handle_bc_style != 0 reproduces handleBC.applyBC(mode 1): the primal
+ * fill is re-applied after each linearised one (cylinder driver).  rect (or null) restricts the rows
+ * that are evaluated to cells i0..i1 x j0..j1 (others keep their previous content). */
+int bcd_jacobian_coo(double* jac, int32_t* ia, int32_t* ja, double* w, const double* nx, const double* ny,
+                     const double* vol, const double* volf, int gh, double cp, double cv, double prandtl, double gam,
+                     double rgaz, double cs, double muref, double tref, double s_suth, double k2, double k4, int im,
+                     int jm, int wall, const bc_desc_t* bcs, int nbcs, int scatter_kind, const double* coefdiag,
+                     const int32_t* rect, void* stream);
+/* primal boundary fill of a whole list */
+int bcd_apply_bcs(double* w, const double* nx, const double* ny, double gam, int gh, int im, int jm,
+                  const bc_desc_t* bcs, int nbcs, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
