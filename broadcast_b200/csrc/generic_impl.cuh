@@ -155,6 +155,25 @@ cudaError_t residual_generic_t(const GridDesc& g, const SchemeArgs& a, bool wall
 }
 
 
+#if BCAST_N == 0
+// passive prims + gradients into the scratch arena, for kernels that read them (jac_interior.cu)
+cudaError_t prepare_prims_grads(const GridDesc& g, const SchemeArgs& a, const double* w, const double* nx, const double* ny,
+                                const double* vol, const double* volf, FieldPtrs& f, cudaStream_t st) {
+  const SchemeConsts c = make_consts(a.cp, a.cv, a.prandtl, a.gam, a.rgaz, a.cs, a.muref, a.tref, a.s_suth, a.k2, a.k4);
+  double* prim = scratch_doubles(0, (size_t)g.sc * NPRIM);
+  double* grad = scratch_doubles(1, (size_t)g.sc * NGRAD);
+  if (!prim || !grad) return cudaErrorMemoryAllocation;
+  dim3 blk(32, 4);
+  dim3 gall((g.ni() + 31) / 32, (g.nj() + 3) / 4);
+  k_prims<0><<<gall, blk, 0, st>>>(g, c, w, nullptr, prim, nullptr);
+  f = FieldPtrs{w, prim, grad, nx, ny, vol, volf, nullptr, nullptr, nullptr};
+  dim3 gint((g.im + 31) / 32, (g.jm + 3) / 4);
+  k_grads<0><<<gint, blk, 0, st>>>(g, f, grad, nullptr);
+  k_grad_ghost<<<dim3((g.im + g.jm + 127) / 128, NGRAD), 128, 0, st>>>(g, grad, NGRAD);
+  return cudaGetLastError();
+}
+#endif
+
 #define BCAST_CAT2(a, b) a##b
 #define BCAST_CAT(a, b) BCAST_CAT2(a, b)
 cudaError_t BCAST_CAT(residual_generic_, BCAST_N)(const GridDesc& g, const SchemeArgs& a, bool wall, double* out, const double* w,

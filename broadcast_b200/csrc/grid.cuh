@@ -89,6 +89,10 @@ struct GlobalAcc {
   template <int OI, int OJ> __device__ __forceinline__ Var<DT> H() const { return load(f.prim, f.primd, PR_H, NPRIM, ck<OI, OJ>()); }
   template <int OI, int OJ> __device__ __forceinline__ Var<DT> GU(int cc) const { return load(f.grad, f.gradd, cc, NGRAD, ck<OI, OJ>()); }
   template <int OI, int OJ> __device__ __forceinline__ Var<DT> GV(int cc) const { return load(f.grad, f.gradd, 2 + cc, NGRAD, ck<OI, OJ>()); }
+  template <int OI, int OJ> __device__ __forceinline__ auto GR() const {
+    struct R { Var<DT> u0, u1, v0, v1; };
+    return R{GU<OI, OJ>(0), GU<OI, OJ>(1), GV<OI, OJ>(0), GV<OI, OJ>(1)};
+  }
   template <int OI, int OJ> __device__ __forceinline__ double NX(int k) const { return __ldg(f.nx + k * sn + nk<OI, OJ>()); }
   template <int OI, int OJ> __device__ __forceinline__ double NY(int k) const { return __ldg(f.ny + k * sn + nk<OI, OJ>()); }
   template <int OI, int OJ> __device__ __forceinline__ double VOL() const { return __ldg(f.vol + ck<OI, OJ>()); }

@@ -1,0 +1,64 @@
+// Block-Jacobian assembly of the regular interior rows into the fixed 29-slot pattern
+// (values only, structure of arrays: V[slot][e][m][cell]).
+#include "../../include/broadcast_b200.h"
+#include "jac_blocks.cuh"
+
+namespace bcast {
+void count_launches(int n);
+cudaError_t prepare_prims_grads(const GridDesc& g, const SchemeArgs& a, const double* w, const double* nx, const double* ny,
+                                const double* vol, const double* volf, FieldPtrs& f, cudaStream_t st);
+#define DECL(G) jac_block_fn jac_block_launcher_g##G(int, int);
+DECL(0) DECL(1) DECL(2) DECL(3) DECL(4) DECL(5) DECL(6) DECL(7)
+#undef DECL
+jac_block_fn jac_block_launcher(int di, int dj) {
+  jac_block_fn f = nullptr;
+#define TRY(G) if (!f) f = jac_block_launcher_g##G(di, dj);
+  TRY(0) TRY(1) TRY(2) TRY(3) TRY(4) TRY(5) TRY(6) TRY(7)
+#undef TRY
+  return f;
+}
+static const int kOffsets[JAC_NSLOT][2] = {
+#define X(a, b) {a, b},
+    BCAST_JAC_OFFSETS(X)
+#undef X
+};
+}  // namespace bcast
+
+using namespace bcast;
+
+extern "C" int bcd_jacobian_slots(int32_t* offsets /* [29][2] */) {
+  for (int s = 0; s < JAC_NSLOT; ++s) {
+    offsets[2 * s] = kOffsets[s][0];
+    offsets[2 * s + 1] = kOffsets[s][1];
+  }
+  return JAC_NSLOT;
+}
+
+extern "C" int bcd_jacobian_interior(double* values, const double* w, const double* nx, const double* ny, const double* vol,
+                                     const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
+                                     double muref, double tref, double s_suth, double k2, double k4, int im, int jm,
+                                     const double* coefdiag, const int32_t* rect, void* stream) {
+  if (im < 1 || jm < 1 || gh != 3) return BC_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const GridDesc g = make_grid(im, jm, gh);
+  const SchemeArgs a{cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4};
+  const SchemeConsts c = make_consts(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4);
+  Rect rc{gh + 1, im - gh, gh + 1, jm - gh};
+  if (rect) {
+    rc = Rect{rect[0], rect[1], rect[2], rect[3]};
+    if (rc.i0 < gh + 1 || rc.i1 > im - gh || rc.j0 < gh + 1 || rc.j1 > jm - gh) return BC_ERR_ARG;
+  }
+  if (rc.i1 < rc.i0 || rc.j1 < rc.j0) return BC_OK;
+  FieldPtrs f;
+  cudaError_t e = prepare_prims_grads(g, a, w, nx, ny, vol, volf, f, st);
+  if (e != cudaSuccess) return (int)e;
+  const long long slot_stride = 25LL * im * jm;
+  for (int s = 0; s < JAC_NSLOT; ++s) {
+    jac_block_fn fn = jac_block_launcher(kOffsets[s][0], kOffsets[s][1]);
+    if (!fn) return BC_ERR_UNSUPPORTED;
+    e = fn(g, c, f, rc, values + s * slot_stride, coefdiag, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  count_launches(3 + JAC_NSLOT);
+  return BC_OK;
+}

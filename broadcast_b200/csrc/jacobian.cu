@@ -39,7 +39,7 @@ static cudaError_t apply_bc_list(const GridDesc& g, double gam, int ndir, double
 // into the reference's slot order for m = 0..4
 __global__ void k_scatter5(GridDesc g, int kind, double* __restrict__ jac, int* __restrict__ ia, int* __restrict__ ja,
                            const double* __restrict__ resd5, int l, int k, const double* __restrict__ coefdiag,
-                           const double* __restrict__ vol, Rect rc) {
+                           const double* __restrict__ vol, Rect rc, int compact) {
   const int im = g.im, jm = g.jm, gh = g.gh, s = 2 * gh + 1;
   const int wi = rc.i1 - rc.i0 + 1, wj = rc.j1 - rc.j0 + 1;
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -71,8 +71,10 @@ __global__ void k_scatter5(GridDesc g, int kind, double* __restrict__ jac, int* 
       else ok = false;
     }
   }
-  const long long n = 5LL * im * jm;
-  const long long cell = (long long)(i - 1) + (long long)(j - 1) * im + (long long)(e - 1) * im * jm;
+  // reference slot order (ComputeJacobian.f90:524), over the whole grid or (compact) over the rectangle only
+  const long long n = compact ? 5LL * wi * wj : 5LL * im * jm;
+  const long long cell = compact ? (long long)(i - rc.i0) + (long long)(j - rc.j0) * wi + (long long)(e - 1) * wi * wj
+                                 : (long long)(i - 1) + (long long)(j - 1) * im + (long long)(e - 1) * im * jm;
   const long long kc = g.cidx(i, j);
 #pragma unroll
   for (int m = 0; m < 5; ++m) {
@@ -116,7 +118,7 @@ extern "C" int bcd_jacobian_coo(double* jac, int32_t* ia, int32_t* ja, double* w
                                 const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
                                 double muref, double tref, double s_suth, double k2, double k4, int im, int jm, int wall,
                                 const bc_desc_t* bcs, int nbcs, int scatter_kind, const double* coefdiag, const int32_t* rect,
-                                void* stream) {
+                                int compact, void* stream) {
   if (im < 1 || jm < 1 || gh != 3) return BC_ERR_ARG;
   if (scatter_kind < 0 || scatter_kind > 6) return BC_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
@@ -138,7 +140,7 @@ extern "C" int bcd_jacobian_coo(double* jac, int32_t* ia, int32_t* ja, double* w
       if (e != cudaSuccess) return (int)e;
       e = launch_residual_generic(g, a, wall != 0, 5, resd5, w, wd5, nx, ny, vol, volf, &rc, st);
       if (e != cudaSuccess) return (int)e;
-      k_scatter5<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(g, scatter_kind, jac, ia, ja, resd5, l, k, coefdiag, vol, rc);
+      k_scatter5<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(g, scatter_kind, jac, ia, ja, resd5, l, k, coefdiag, vol, rc, (rect && compact) ? 1 : 0);
       e = cudaGetLastError();
       if (e != cudaSuccess) return (int)e;
       count_launches(7);

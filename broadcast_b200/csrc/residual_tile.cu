@@ -49,6 +49,10 @@ struct SmemAcc {
   template <int OI, int OJ> __device__ __forceinline__ PVar H() const { return ld<OI, OJ>(A_H); }
   template <int OI, int OJ> __device__ __forceinline__ PVar GU(int cc) const { return ld<OI, OJ>(A_G + cc); }
   template <int OI, int OJ> __device__ __forceinline__ PVar GV(int cc) const { return ld<OI, OJ>(A_G + 2 + cc); }
+  template <int OI, int OJ> __device__ __forceinline__ auto GR() const {
+    struct R { PVar u0, u1, v0, v1; };
+    return R{GU<OI, OJ>(0), GU<OI, OJ>(1), GV<OI, OJ>(0), GV<OI, OJ>(1)};
+  }
   template <int OI, int OJ> __device__ __forceinline__ double NX(int kk) const { return __ldg(nx + kk * sn + n + OI + (long long)OJ * ldn); }
   template <int OI, int OJ> __device__ __forceinline__ double NY(int kk) const { return __ldg(ny + kk * sn + n + OI + (long long)OJ * ldn); }
   template <int OI, int OJ> __device__ __forceinline__ double VOL() const { return __ldg(vol + c + OI + (long long)OJ * ldc); }

@@ -74,6 +74,11 @@ BC_HD CellPrims<D> cell_prims(const Var<D> (&q)[5], const SchemeConsts& c) {
 // 5-point gradients of (velx, vely) at a cell (gradop_5pi.F, gradop_5pj.F, gradient.F, dxdy.F).
 // Offsets are relative to the accessor's base cell plus (CI,CJ).
 // ---------------------------------------------------------------------------------------------
+template <class D>
+struct Grad4 {
+  Var<D> u0, u1, v0, v1;  // gradu(.,1), gradu(.,2), gradv(.,1), gradv(.,2)
+};
+
 template <int CI, int CJ, class A>
 BC_HD auto cell_gradients(const A& a) {
   constexpr double b1 = 8.0 * (1.0 / 12.0);
@@ -92,10 +97,7 @@ BC_HD auto cell_gradients(const A& a) {
   auto gu1 = dym1 * gui + dym2 * guj;
   auto gv1 = dym1 * gvi + dym2 * gvj;
   using D = decltype(gu0.d);
-  struct R {
-    Var<D> u0, u1, v0, v1;  // gradu(.,1), gradu(.,2), gradv(.,1), gradv(.,2)
-  };
-  return R{gu0, gu1, gv0, gv1};
+  return Grad4<D>{gu0, gu1, gv0, gv1};
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -302,25 +304,25 @@ BC_HD void face_flux(const A& a, const SchemeConsts& c, Var<RD> (&hn)[5]) {
     auto k_sensor1 = fabs(p_m1 - 2.0 * p_0 + p_p1) / fabs(p_m1 + 2.0 * p_0 + p_p1);
     auto k_sensor2 = fabs(p_m2 - 2.0 * p_m1 + p_0) / fabs(p_m2 + 2.0 * p_m1 + p_0);
 
-    auto sens_cell = [&](auto gu0, auto gu1, auto gv0, auto gv1, double vol, auto c2, auto& ducros, auto& dxm) {
-      auto divu = gu0 + gv1;
+    auto sens_cell = [&](auto gr, double vol, auto c2, auto& ducros, auto& dxm) {
+      auto divu = gr.u0 + gr.v1;
       auto divu2 = divu * divu;
-      auto vort2 = (gv0 - gu1) * (gv0 - gu1);
+      auto vort2 = (gr.v0 - gr.u1) * (gr.v0 - gr.u1);
       ducros = divu2 / (divu2 + vort2 + 1e-15);
       dxm = 0.5 * (1.0 - tanh(2.5 + 10.0 * vol / (sqrt(c2 * nx2) + 1e-15) * divu));
     };
-    using GD0 = decltype(a.template GU<0, 0>(0).d);
-    using GD1 = decltype(a.template GU<AT(-1, 0)>(0).d);
-    using SD0 = decltype((a.template GU<0, 0>(0) * c2r).d);
-    using SD1 = decltype((a.template GU<AT(-1, 0)>(0) * c2l).d);
+    const auto gr0 = a.template GR<0, 0>();
+    const auto gr1 = a.template GR<AT(-1, 0)>();
+    using GD0 = decltype(gr0.u0.d);
+    using GD1 = decltype(gr1.u0.d);
+    using SD0 = decltype((gr0.u0 * c2r).d);
+    using SD1 = decltype((gr1.u0 * c2l).d);
     Var<GD0> ducros1;
     Var<SD0> dxm1;
     Var<GD1> ducros2;
     Var<SD1> dxm2;
-    sens_cell(a.template GU<0, 0>(0), a.template GU<0, 0>(1), a.template GV<0, 0>(0), a.template GV<0, 0>(1),
-              a.template VOL<0, 0>(), c2r, ducros1, dxm1);
-    sens_cell(a.template GU<AT(-1, 0)>(0), a.template GU<AT(-1, 0)>(1), a.template GV<AT(-1, 0)>(0),
-              a.template GV<AT(-1, 0)>(1), a.template VOL<AT(-1, 0)>(), c2l, ducros2, dxm2);
+    sens_cell(gr0, a.template VOL<0, 0>(), c2r, ducros1, dxm1);
+    sens_cell(gr1, a.template VOL<AT(-1, 0)>(), c2l, ducros2, dxm2);
     auto coef = fmax(k_sensor1, k_sensor2) * fmax(ducros1, ducros2) * fmax(dxm1, dxm2);
     auto eps2 = c.k2 * coef;
     auto eps4 = fmax(0.0, c.k4 - eps2 * 12.0);

@@ -187,13 +187,15 @@ def _bc_descs(blk: "Block"):
     return arr, len(out)
 
 
-def jacobian_coo(blk: "Block", coefdiag=None, kind=None, rect=None, out=None):
+def jacobian_coo(blk: "Block", coefdiag=None, kind=None, rect=None, out=None, compact=False):
     """The reference's COO lists (Jac, IA, JA; slot order of misc/ComputeJacobian.f90:524) assembled
     on the device by the colour loop of BROADCAST_npz.py:1068-1127 with 5 directions per pass.
     ``blk.w`` must hold the state with its ghosts filled (``blk.apply_bcs()``)."""
     im, jm, gh = blk.im, blk.jm, blk.gh
     s = 2 * gh + 1
     nb = 25 * s * s * im * jm
+    if rect is not None and compact:
+        nb = 25 * s * s * max(0, rect[1] - rect[0] + 1) * max(0, rect[3] - rect[2] + 1)
     if nb >= 2 ** 31:
         raise _lib.BroadcastB200Error("the reference COO layout overflows 32-bit slots at this size; use the block-CSR assembly")
     if kind is None:
@@ -212,7 +214,8 @@ def jacobian_coo(blk: "Block", coefdiag=None, kind=None, rect=None, out=None):
     r = np.asarray(rect, dtype=np.int32) if rect is not None else None
     rc = blk.lib.bcd_jacobian_coo(_p(jac), _p(ia), _p(ja), _p(blk.w), _p(blk.nx), _p(blk.ny), _p(blk.vol), _p(blk.volf), gh, *blk._phys,
                                   im, jm, blk.wall, descs, n, SCATTER[kind], _p(coefdiag),
-                                  r.ctypes.data_as(ctypes.c_void_p) if r is not None else ctypes.c_void_p(None), blk._stream())
+                                  r.ctypes.data_as(ctypes.c_void_p) if r is not None else ctypes.c_void_p(None), 1 if compact else 0,
+                                  blk._stream())
     _lib.check(rc, "bcd_jacobian_coo")
     return jac, ia, ja
 
@@ -221,3 +224,81 @@ def remove_zero_jac(jac, ia, ja, thresh=2e-16):
     """BROADCAST_npz.py:129-135 on the device"""
     keep = jac.abs() > thresh
     return jac[keep], ia[keep], ja[keep]
+
+
+# ----------------------------------------------------------------------------------------------
+# hybrid assembly: direct block kernels on the regular interior + colour loop on the boundary strips
+# ----------------------------------------------------------------------------------------------
+def jacobian_slots(blk: "Block"):
+    off = np.zeros((29, 2), dtype=np.int32)
+    n = blk.lib.bcd_jacobian_slots(off.ctypes.data_as(ctypes.c_void_p))
+    return off[:n]
+
+
+class HybridJacobian:
+    """fixed-pattern block Jacobian: ``blocks[slot, e, m, j-1, i-1]`` for the regular interior rows
+    (gh+1..im-gh x gh+1..jm-gh; other rows of ``blocks`` are unused) and reference-ordered COO lists for
+    the four boundary strips."""
+
+    def __init__(self, blk, blocks, offsets, strips, region):
+        self.blk, self.blocks, self.offsets, self.strips, self.region = blk, blocks, offsets, strips, region
+
+    def to_coo(self, thresh=2e-16):
+        """filtered COO (remove_zero_jac semantics) on the device, reference numbering of rows/columns"""
+        blk = self.blk
+        im, jm = blk.im, blk.jm
+        i0, i1, j0, j1 = self.region
+        vals, rows, cols = [], [], []
+        if i1 >= i0 and j1 >= j0:
+            dev = blk.device
+            I = torch.arange(i0, i1 + 1, device=dev, dtype=torch.int64)[None, :]
+            J = torch.arange(j0, j1 + 1, device=dev, dtype=torch.int64)[:, None]
+            for s, (di, dj) in enumerate(self.offsets):
+                for e in range(5):
+                    ia = (e + 5 * (J - 1) + 5 * jm * (I - 1)).expand(j1 - j0 + 1, i1 - i0 + 1)
+                    for m in range(5):
+                        v = self.blocks[s, e, m, j0 - 1:j1, i0 - 1:i1]
+                        keep = v.abs() > thresh
+                        ja = (m + 5 * (J + int(dj) - 1) + 5 * jm * (I + int(di) - 1)).expand_as(v)
+                        vals.append(v[keep])
+                        rows.append(ia[keep])
+                        cols.append(ja[keep])
+        for jac, ia, ja in self.strips:
+            keep = jac.abs() > thresh
+            vals.append(jac[keep])
+            rows.append(ia[keep].to(torch.int64))
+            cols.append(ja[keep].to(torch.int64))
+        return torch.cat(vals), torch.cat(rows), torch.cat(cols)
+
+    def to_scipy_csr(self, thresh=2e-16):
+        import scipy.sparse as sp
+        v, r, c = self.to_coo(thresh)
+        n = 5 * self.blk.im * self.blk.jm
+        return sp.csr_matrix((v.cpu().numpy(), (r.cpu().numpy(), c.cpu().numpy())), shape=(n, n))
+
+
+def jacobian_hybrid(blk: "Block", coefdiag=None, kind=None, blocks=None):
+    """Jacobian of the current state: interior rows by the direct block kernels (one launch per
+    structural column offset, no colouring), boundary strips (gh rows/columns along each side) by the
+    reference colour loop restricted to those rows."""
+    im, jm, gh = blk.im, blk.jm, blk.gh
+    if kind is None:
+        kind = "jv_relaxed_withjn" if blk.case.periodic_i else "jv_relaxed"
+    relaxed = "relaxed" in kind
+    cd = None
+    if coefdiag is not None:
+        cd = coefdiag if isinstance(coefdiag, torch.Tensor) else _t(coefdiag, blk.device)
+    elif relaxed:
+        cd = torch.zeros((jm, im), dtype=torch.float64, device=blk.device)
+    region = (gh + 1, im - gh, gh + 1, jm - gh)
+    if blocks is None:
+        blocks = torch.zeros((29, 5, 5, jm, im), dtype=torch.float64, device=blk.device)
+    rc = blk.lib.bcd_jacobian_interior(_p(blocks), _p(blk.w), _p(blk.nx), _p(blk.ny), _p(blk.vol), _p(blk.volf), gh, *blk._phys, im, jm,
+                                       _p(cd if relaxed else None), ctypes.c_void_p(None), blk._stream())
+    _lib.check(rc, "bcd_jacobian_interior")
+    rects = [(1, im, 1, gh), (1, im, jm - gh + 1, jm), (1, gh, gh + 1, jm - gh), (im - gh + 1, im, gh + 1, jm - gh)]
+    strips = []
+    for r in rects:
+        if r[1] >= r[0] and r[3] >= r[2]:
+            strips.append(jacobian_coo(blk, coefdiag=cd, kind=kind, rect=r, compact=True))
+    return HybridJacobian(blk, blocks, jacobian_slots(blk), strips, region)

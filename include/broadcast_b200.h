@@ -176,12 +176,25 @@ typedef struct {
  * (jac, ia, ja of length 25*(2gh+1)^2*im*jm, slot order of misc/ComputeJacobian.f90:524), on the device.
  * scatter_kind as in bcd_scatter.  handle_bc_style != 0 reproduces handleBC.applyBC(mode 1): the primal
  * fill is re-applied after each linearised one (cylinder driver).  rect (or null) restricts the rows
- * that are evaluated to cells i0..i1 x j0..j1 (others keep their previous content). */
+ * that are evaluated to cells i0..i1 x j0..j1 (others keep their previous content); with compact != 0 the
+ * outputs have 25*(2gh+1)^2*wi*wj entries, slot order as above over the rectangle's own (wi x wj) index space
+ * (ia/ja stay global). */
 int bcd_jacobian_coo(double* jac, int32_t* ia, int32_t* ja, double* w, const double* nx, const double* ny,
                      const double* vol, const double* volf, int gh, double cp, double cv, double prandtl, double gam,
                      double rgaz, double cs, double muref, double tref, double s_suth, double k2, double k4, int im,
                      int jm, int wall, const bc_desc_t* bcs, int nbcs, int scatter_kind, const double* coefdiag,
-                     const int32_t* rect, void* stream);
+                     const int32_t* rect, int compact, void* stream);
+/* Direct block-Jacobian of the regular interior rows (rows whose stencil touches neither ghost cells nor
+ * the wall rows: gh+1 <= i <= im-gh, gh+1 <= j <= jm-gh) into the fixed 29-slot pattern, without colouring:
+ * values[slot][e][m][cell], cell = (i-1) + (j-1)*im, slot s <-> column-cell offset given by
+ * bcd_jacobian_slots().  Entry (e,m) of a block is jac = -d residu(i,j,e) / d w(i+di,j+dj,m) (+ coefdiag(i,j)
+ * on the diagonal if coefdiag != null): what the reference's colour loop + computejacobianfromjv_relaxed
+ * attribute to that pair (misc/ComputeJacobian.f90:518-569).  rect (or null) restricts the rows. */
+int bcd_jacobian_slots(int32_t* offsets /* [29][2] (di,dj) */);
+int bcd_jacobian_interior(double* values, const double* w, const double* nx, const double* ny, const double* vol,
+                          const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz,
+                          double cs, double muref, double tref, double s_suth, double k2, double k4, int im, int jm,
+                          const double* coefdiag, const int32_t* rect, void* stream);
 /* primal boundary fill of a whole list */
 int bcd_apply_bcs(double* w, const double* nx, const double* ny, double gam, int gh, int im, int jm,
                   const bc_desc_t* bcs, int nbcs, void* stream);

@@ -163,3 +163,35 @@ def test_full_jacobian_device_colour_loop(gpu, ref, kind, im, jm):
     # blockwise relative accuracy of the significant entries
     big = np.abs(jb) > 1e-6 * scale
     assert np.max(np.abs(jac[big] - jb[big]) / np.abs(jb[big])) < 1e-9
+
+
+@pytest.mark.parametrize("kind,im,jm", [("bl", 40, 30), ("cyl", 42, 30)])
+def test_hybrid_jacobian_matches_reference_loop(gpu, ref, kind, im, jm):
+    """direct block kernels (interior) + strip colour loop == the reference's 245-colour loop, compared
+    as canonical CSR after the reference's 2e-16 filter: identical pattern, values to TOL."""
+    import scipy.sparse as sp
+    from broadcast_b200.resident import Block, jacobian_hybrid
+    a = H.make_case(kind, im, jm, gpu, with_w=True)
+    b = H.make_case(kind, im, jm, ref, with_w=True)
+    rng = np.random.default_rng(5)
+    coef = np.asfortranarray(rng.uniform(0.5, 1.5, size=(im, jm)))
+    blk = Block(a)
+    blk.apply_bcs()
+    A = jacobian_hybrid(blk, coefdiag=coef).to_scipy_csr()
+    wb, _ = H.residual_sequence(ref, b)
+    jb, ib, jbb = H.jacobian_sequence(ref, b, wb, None, coef)
+    keep = np.abs(jb) > 2e-16
+    n = 5 * im * jm
+    B = sp.csr_matrix((jb[keep], (ib[keep], jbb[keep])), shape=(n, n))
+    A.sort_indices(); B.sort_indices()
+    D = (A - B).tocoo()
+    scale = np.abs(B.data).max()
+    assert np.abs(D.data).max() < TOL * scale, np.abs(D.data).max() / scale
+    # pattern: entries present in one and absent in the other must be at rounding level
+    PA = sp.csr_matrix((np.ones_like(A.data), A.indices, A.indptr), shape=A.shape)
+    PB = sp.csr_matrix((np.ones_like(B.data), B.indices, B.indptr), shape=B.shape)
+    X = (PA - PB).tocoo()
+    odd = X.data != 0
+    if odd.any():
+        vals = np.abs(np.asarray((A + B)[X.row[odd], X.col[odd]])).ravel()
+        assert vals.max() < 1e-15, (odd.sum(), vals.max())
