@@ -8,12 +8,13 @@ namespace bcast {
 // primitives over every cell including ghosts (rhs/primvisc.F:2-9)
 // ---------------------------------------------------------------------------------------------
 template <int N>
-__global__ void k_prims(GridDesc g, SchemeConsts c, const double* __restrict__ w, const double* __restrict__ wd, double* __restrict__ prim,
+__global__ void k_prims(GridDesc g, SchemeConsts c, Rect rc /* storage (0-based) index window, inclusive */,
+                        const double* __restrict__ w, const double* __restrict__ wd, double* __restrict__ prim,
                         double* __restrict__ primd) {
   using DT = TanOf<N>;
-  const int ii = blockIdx.x * blockDim.x + threadIdx.x;
-  const int jj = blockIdx.y * blockDim.y + threadIdx.y;
-  if (ii >= g.ni() || jj >= g.nj()) return;
+  const int ii = blockIdx.x * blockDim.x + threadIdx.x + rc.i0;
+  const int jj = blockIdx.y * blockDim.y + threadIdx.y + rc.j0;
+  if (ii > rc.i1 || jj > rc.j1) return;
   const long long k = ii + (long long)jj * g.ldc;
   Var<DT> q[5];
 #pragma unroll
@@ -40,10 +41,11 @@ __global__ void k_prims(GridDesc g, SchemeConsts c, const double* __restrict__ w
 // gradients of velx, vely on interior cells (flux_num_dnc5.F90:124-137)
 // ---------------------------------------------------------------------------------------------
 template <int N>
-__global__ void k_grads(GridDesc g, FieldPtrs f, double* __restrict__ grad, double* __restrict__ gradd) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
-  if (i > g.im || j > g.jm) return;
+__global__ void k_grads(GridDesc g, FieldPtrs f, Rect rc /* interior cells, Fortran indices */, double* __restrict__ grad,
+                        double* __restrict__ gradd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + rc.i0;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + rc.j0;
+  if (i > rc.i1 || j > rc.j1) return;
   GlobalAcc<N> a(f, g, i, j);
   const auto r = cell_gradients<0, 0>(a);
   const long long k = g.cidx(i, j);
@@ -136,18 +138,23 @@ cudaError_t residual_generic_t(const GridDesc& g, const SchemeArgs& a, bool wall
   double* gradd = N ? scratch_doubles(3, (size_t)g.sc * NGRAD * N) : nullptr;
   if (!prim || !grad || (N && (!primd || !gradd))) return cudaErrorMemoryAllocation;
   dim3 blk(32, 4);
-  dim3 gall((g.ni() + 31) / 32, (g.nj() + 3) / 4);
-  k_prims<N><<<gall, blk, 0, st>>>(g, c, w, wd, prim, primd);
+  Rect rc = rect ? *rect : Rect{1, g.im, 1, g.jm};
+  if (rc.i1 < rc.i0 || rc.j1 < rc.j0) return cudaSuccess;
+  // the balance of a cell reads gradients of its 4-neighbourhood (sensor) and primitives up to gh = 3
+  // cells away; a gradient reads primitives 2 cells away: restrict both passes to what `rect` needs
+  const Rect rg{max(1, rc.i0 - 1), min(g.im, rc.i1 + 1), max(1, rc.j0 - 1), min(g.jm, rc.j1 + 1)};
+  const Rect rp{max(0, rc.i0 - 5 + g.gh), min(g.ni() - 1, rc.i1 + 3 + g.gh), max(0, rc.j0 - 5 + g.gh), min(g.nj() - 1, rc.j1 + 3 + g.gh)};  // +-4 (wall row 1 reads row 5)
+  dim3 gall((rp.i1 - rp.i0 + 32) / 32, (rp.j1 - rp.j0 + 4) / 4);
+  k_prims<N><<<gall, blk, 0, st>>>(g, c, rp, w, wd, prim, primd);
   FieldPtrs f{w, prim, grad, nx, ny, vol, volf, wd, primd, gradd};
-  dim3 gint((g.im + 31) / 32, (g.jm + 3) / 4);
-  k_grads<N><<<gint, blk, 0, st>>>(g, f, grad, gradd);
+  dim3 gint((rg.i1 - rg.i0 + 32) / 32, (rg.j1 - rg.j0 + 4) / 4);
+  k_grads<N><<<gint, blk, 0, st>>>(g, f, rg, grad, gradd);
   {
     const int nt = g.im + g.jm;
     k_grad_ghost<<<dim3((nt + 127) / 128, NGRAD), 128, 0, st>>>(g, grad, NGRAD);
     if (N) k_grad_ghost<<<dim3((nt + 127) / 128, NGRAD * N), 128, 0, st>>>(g, gradd, NGRAD * N);
   }
-  Rect rc = rect ? *rect : Rect{1, g.im, 1, g.jm};
-  if (rc.i1 >= rc.i0 && rc.j1 >= rc.j0) {
+  {
     dim3 gb((rc.i1 - rc.i0 + 32) / 32, (rc.j1 - rc.j0 + 4) / 4);
     k_balance<N><<<gb, blk, 0, st>>>(g, c, f, wall, rc, out);
   }
@@ -165,10 +172,10 @@ cudaError_t prepare_prims_grads(const GridDesc& g, const SchemeArgs& a, const do
   if (!prim || !grad) return cudaErrorMemoryAllocation;
   dim3 blk(32, 4);
   dim3 gall((g.ni() + 31) / 32, (g.nj() + 3) / 4);
-  k_prims<0><<<gall, blk, 0, st>>>(g, c, w, nullptr, prim, nullptr);
+  k_prims<0><<<gall, blk, 0, st>>>(g, c, Rect{0, g.ni() - 1, 0, g.nj() - 1}, w, nullptr, prim, nullptr);
   f = FieldPtrs{w, prim, grad, nx, ny, vol, volf, nullptr, nullptr, nullptr};
   dim3 gint((g.im + 31) / 32, (g.jm + 3) / 4);
-  k_grads<0><<<gint, blk, 0, st>>>(g, f, grad, nullptr);
+  k_grads<0><<<gint, blk, 0, st>>>(g, f, Rect{1, g.im, 1, g.jm}, grad, nullptr);
   k_grad_ghost<<<dim3((g.im + g.jm + 127) / 128, NGRAD), 128, 0, st>>>(g, grad, NGRAD);
   return cudaGetLastError();
 }

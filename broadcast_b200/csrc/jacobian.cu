@@ -134,7 +134,7 @@ extern "C" int bcd_jacobian_coo(double* jac, int32_t* ia, int32_t* ja, double* w
   const long long nt = 5LL * (rc.i1 - rc.i0 + 1) * (rc.j1 - rc.j0 + 1);
   for (int l = 0; l < s; ++l)
     for (int k = 0; k < s; ++k) {
-      cudaError_t e = launch_testvector(g, wd5, 5, 0, l, k, nullptr, st);
+      cudaError_t e = launch_testvector(g, wd5, 5, 0, l, k, nullptr, st, rect ? &rc : nullptr);
       if (e != cudaSuccess) return (int)e;
       e = apply_bc_list(g, gam, 5, w, wd5, nx, ny, bcs, nbcs, st);
       if (e != cudaSuccess) return (int)e;

@@ -151,10 +151,11 @@ cudaError_t launch_jn_match(double* wr, const Window& r, const int prr[4], const
 // colouring seeds (misc/ComputeJacobian.f90:357-374, 1075-1092).  ndir == 5: direction n seeds
 // variable n (vector mode), m ignored.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_testvector(GridDesc g, double* __restrict__ wd, int ndir, int m, int l, int k, int is, int ie, int js, int je) {
-  const int ii = blockIdx.x * blockDim.x + threadIdx.x;
-  const int jj = blockIdx.y * blockDim.y + threadIdx.y;
-  if (ii >= g.ni() || jj >= g.nj()) return;
+__global__ void k_testvector(GridDesc g, double* __restrict__ wd, int ndir, int m, int l, int k, int is, int ie, int js, int je,
+                             Rect win /* storage index window that is written */) {
+  const int ii = blockIdx.x * blockDim.x + threadIdx.x + win.i0;
+  const int jj = blockIdx.y * blockDim.y + threadIdx.y + win.j0;
+  if (ii > win.i1 || jj > win.j1) return;
   const int i = ii + 1 - g.gh, j = jj + 1 - g.gh;
   const int s = 2 * g.gh + 1;
   const bool seed = i >= is + l + 1 && i <= ie && j >= js + k + 1 && j <= je && (i - (is + l + 1)) % s == 0 && (j - (js + k + 1)) % s == 0;
@@ -169,8 +170,14 @@ __global__ void k_testvector(GridDesc g, double* __restrict__ wd, int ndir, int 
   }
 }
 
-cudaError_t launch_testvector(const GridDesc& g, double* wd, int ndir, int m, int l, int k, const int* zone, cudaStream_t st) {
-  dim3 blk(32, 4), grd((g.ni() + 31) / 32, (g.nj() + 3) / 4);
+cudaError_t launch_testvector(const GridDesc& g, double* wd, int ndir, int m, int l, int k, const int* zone, cudaStream_t st,
+                              const Rect* rows) {
+  // rows (optional): only the cells a tangent restricted to these rows can read are (re)written
+  Rect win{0, g.ni() - 1, 0, g.nj() - 1};
+  if (rows)
+    win = Rect{max(0, rows->i0 - 5 + g.gh), min(g.ni() - 1, rows->i1 + 3 + g.gh), max(0, rows->j0 - 5 + g.gh),
+               min(g.nj() - 1, rows->j1 + 3 + g.gh)};
+  dim3 blk(32, 4), grd((win.i1 - win.i0 + 32) / 32, (win.j1 - win.j0 + 4) / 4);
   int is = 0, ie = g.im, js = 0, je = g.jm;
   if (zone) {  // testvector_partial: i = istart+l+1 .. iend+1, j = jstart+k+1 .. jend+1
     is = zone[0];
@@ -178,7 +185,7 @@ cudaError_t launch_testvector(const GridDesc& g, double* wd, int ndir, int m, in
     js = zone[2];
     je = zone[3] + 1;
   }
-  k_testvector<<<grd, blk, 0, st>>>(g, wd, ndir, m, l, k, is, ie, js, je);
+  k_testvector<<<grd, blk, 0, st>>>(g, wd, ndir, m, l, k, is, ie, js, je, win);
   return cudaGetLastError();
 }
 

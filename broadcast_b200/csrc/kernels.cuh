@@ -46,7 +46,7 @@ cudaError_t launch_jn_match(double* wr, const Window& r, const int prr[4], const
 
 // colouring seeds and COO scatter (misc/ComputeJacobian.f90)
 cudaError_t launch_testvector(const GridDesc& g, double* wd, int ndir, int m, int l, int k, const int* zone /*null or istart,iend,jstart,jend*/,
-                              cudaStream_t st);
+                              cudaStream_t st, const Rect* rows = nullptr);
 enum ScatterKind {
   SCATTER_JV = 0,            // computejacobianfromjv            :292-355
   SCATTER_JV_RELAXED = 1,    // computejacobianfromjv_relaxed    :503-570
