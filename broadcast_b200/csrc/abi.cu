@@ -187,6 +187,17 @@ void count_launches(int n) { g_launches += n; }
 
 extern "C" {
 
+int bc_set_bndbl_2d(const double* w, double* field, double* wbd, int im, int jm, int gh) {
+  if (im < 1 || jm < 1 || gh < 1) return fail(BC_ERR_ARG, "im, jm, gh must be positive");
+  const GridDesc g = make_grid(im, jm, gh);
+  for (int e = 0; e < 5; ++e) {
+    for (int depth = 1; depth <= gh; ++depth)
+      for (int j = 1; j <= jm; ++j) field[(j - 1) + (size_t)(depth - 1) * jm + (size_t)e * jm * gh] = w[e * g.sc + g.cidx(1 - depth, j)];
+    for (int i = 1; i <= im + gh; ++i) wbd[(i - 1) + (size_t)e * (im + gh)] = w[e * g.sc + g.cidx(i - gh, jm)];
+  }
+  return BC_OK;
+}
+
 int bc_version(void) { return 100; }
 int bc_device_count(void) {
   int n = 0;

@@ -1,0 +1,87 @@
+// Block-Jacobian assembly of the regular interior rows by face linearisation (facejac.cuh):
+//   k_face_packages  one thread per cell: linearisation packages of its i-face and j-face -> HBM (SoA planes)
+//   k_jac_assemble   one thread per row cell: the 29 structural 5x5 blocks from the packages of its four faces,
+//                    written as values[slot][e*5+m][cell] (coalesced 8-byte stores, cell = (i-1) + (j-1)*im)
+// Replaces the 29 direct AD kernels of jac_blocks.cuh (kept as a cross-check: bcd_jacobian_interior(..., method=1)).
+#include "../../include/broadcast_b200.h"
+#include "facejac.cuh"
+#include "kernels.cuh"
+
+namespace bcast {
+void count_launches(int n);
+cudaError_t prepare_prims_grads(const GridDesc& g, const SchemeArgs& a, const double* w, const double* nx, const double* ny,
+                                const double* vol, const double* volf, FieldPtrs& f, cudaStream_t st);
+
+__global__ void __launch_bounds__(128) k_face_packages(GridDesc g, SchemeConsts c, FieldPtrs f, Rect rc, double* __restrict__ pkg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + rc.i0;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + rc.j0;
+  if (i > rc.i1 || j > rc.j1) return;
+  const GlobalAcc<0> a(f, g, i, j);
+  const long long k = g.cidx(i, j);
+  double* p0 = pkg + k;
+  double* p1 = pkg + (long long)FPK_N * g.sc + k;
+  const long long sc = g.sc;
+  face_package<0>(a, c, [&](int fld, double v) { p0[fld * sc] = v; });
+  face_package<1>(a, c, [&](int fld, double v) { p1[fld * sc] = v; });
+}
+
+template <int DIR>
+__device__ __forceinline__ FaceCtx make_ctx(const FieldPtrs& f, const GridDesc& g, const double* pkg, int i, int j) {
+  const GlobalAcc<0> a(f, g, i, j);
+  FaceCtx x;
+  x.nxf = a.template NX<0, 0>(DIR);
+  x.nyf = a.template NY<0, 0>(DIR);
+  x.dn = dual_normals<DIR>(a);
+  x.pk = pkg + (long long)DIR * FPK_N * g.sc + g.cidx(i, j);
+  x.stride = g.sc;
+  return x;
+}
+
+__global__ void __launch_bounds__(128) k_jac_assemble(GridDesc g, SchemeConsts c, FieldPtrs f, Rect rc, const double* __restrict__ pkg,
+                                                      double* __restrict__ V, const double* __restrict__ coefdiag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + rc.i0;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + rc.j0;
+  if (i > rc.i1 || j > rc.j1) return;
+  const FaceCtx fi0 = make_ctx<0>(f, g, pkg, i, j), fi1 = make_ctx<0>(f, g, pkg, i + 1, j);
+  const FaceCtx fj0 = make_ctx<1>(f, g, pkg, i, j), fj1 = make_ctx<1>(f, g, pkg, i, j + 1);
+  const long long ncell = (long long)g.im * g.jm;
+  const long long cell = (long long)(i - 1) + (long long)(j - 1) * g.im;
+  const double cd = coefdiag ? coefdiag[cell] : 0.0;
+  int slot = 0;
+#define X(DI, DJ)                                                                       \
+  {                                                                                     \
+    double wc[5], B[25];                                                                \
+    const long long kc = g.cidx(i + (DI), j + (DJ));                                    \
+    _Pragma("unroll") for (int e = 0; e < 5; ++e) wc[e] = __ldg(f.w + e * g.sc + kc);   \
+    block_of<DI, DJ>(fi0, fi1, fj0, fj1, wc, c, B);                                     \
+    if (DI == 0 && DJ == 0) {                                                           \
+      _Pragma("unroll") for (int e = 0; e < 5; ++e) B[e * 6] += cd;                     \
+    }                                                                                   \
+    double* out = V + ((long long)slot * 25) * ncell + cell;                            \
+    _Pragma("unroll") for (int q = 0; q < 25; ++q) out[q * ncell] = B[q];               \
+    ++slot;                                                                             \
+  }
+  BCAST_JAC_OFFSETS(X)
+#undef X
+}
+
+cudaError_t launch_jacobian_faces(const GridDesc& g, const SchemeArgs& a, const double* w, const double* nx, const double* ny,
+                                  const double* vol, const double* volf, const Rect& rc, double* values, const double* coefdiag,
+                                  cudaStream_t st) {
+  const SchemeConsts c = make_consts(a.cp, a.cv, a.prandtl, a.gam, a.rgaz, a.cs, a.muref, a.tref, a.s_suth, a.k2, a.k4);
+  FieldPtrs f;
+  cudaError_t e = prepare_prims_grads(g, a, w, nx, ny, vol, volf, f, st);
+  if (e != cudaSuccess) return e;
+  double* pkg = scratch_doubles(30, (size_t)2 * FPK_N * g.sc);
+  if (!pkg) return cudaErrorMemoryAllocation;
+  const Rect rf{rc.i0, rc.i1 + 1, rc.j0, rc.j1 + 1};
+  dim3 blk(32, 4);
+  dim3 gf((rf.i1 - rf.i0 + 32) / 32, (rf.j1 - rf.j0 + 4) / 4);
+  k_face_packages<<<gf, blk, 0, st>>>(g, c, f, rf, pkg);
+  dim3 gr((rc.i1 - rc.i0 + 32) / 32, (rc.j1 - rc.j0 + 4) / 4);
+  k_jac_assemble<<<gr, blk, 0, st>>>(g, c, f, rc, pkg, values, coefdiag);
+  count_launches(5);
+  return cudaGetLastError();
+}
+
+}  // namespace bcast

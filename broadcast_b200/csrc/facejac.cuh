@@ -1,0 +1,398 @@
+// Semi-analytic block Jacobian of the order-5 scheme on regular interior rows (FACE_MAIN faces, compact o4
+// viscous fluxes), organised per FACE instead of per (row, column) pair:
+//
+//   producer  face_package<DIR>()   one face -> 44 doubles: everything NON-LINEAR about that face flux,
+//             differentiated once (spectral radius and sensor by forward AD on a handful of scalars with the
+//             Tapenade conventions of dual.cuh; viscous stresses by their closed form);
+//   consumer  face_contrib<DIR,S,T>()  adds d hn / d (primitives, conservatives of stencil cell (S,T)) of one face
+//             into the accumulators of a (row cell, column cell) block using only compile-time stencil weights,
+//             because every face scalar is LINEAR in the cell primitives with constant coefficients;
+//   chain     block_finish()        accumulators x d primitives / d conservatives of the column cell -> 5x5 block.
+//
+// Entry (e,m) of the block of row cell (i,j) and column cell (i+DI, j+DJ) is
+//     -d residu(i,j,e) / d w(i+DI,j+DJ,m)  =  d[hn_i(i+1,j) - hn_i(i,j) + hn_j(i,j+1) - hn_j(i,j)]_e / d w_m
+// i.e. what the reference's colour loop + computejacobianfromjv attribute to that pair
+// (srcfv/tangent/flux_num_dnc5_d.f90, misc/ComputeJacobian.f90:518-569), at ~1/100 of the arithmetic: the
+// reference re-evaluates the whole tangent for 245 seed vectors, the direct AD kernels (jac_blocks.cuh)
+// re-evaluate the passive part of four faces for each of 29 column offsets.
+//
+// hn_e = fx_e - rspec (eps2 diff_e + eps4 pred_e) - visc_e       (scheme.cuh, face_flux<DIR,false,FACE_MAIN>)
+#pragma once
+#include "grid.cuh"
+#include "scheme.cuh"
+
+// the 29 structural offsets in column order (di major, dj minor): slot index = position in this list
+#define BCAST_JAC_OFFSETS(X)                                                                                      \
+  X(-3, 0) X(-2, -2) X(-2, -1) X(-2, 0) X(-2, 1) X(-2, 2) X(-1, -2) X(-1, -1) X(-1, 0) X(-1, 1) X(-1, 2) X(0, -3) \
+  X(0, -2) X(0, -1) X(0, 0) X(0, 1) X(0, 2) X(0, 3) X(1, -2) X(1, -1) X(1, 0) X(1, 1) X(1, 2) X(2, -2) X(2, -1)   \
+  X(2, 0) X(2, 1) X(2, 2) X(3, 0)
+
+namespace bcast {
+
+constexpr int JAC_NSLOT = 29;
+constexpr int FPK_N = 44;
+enum {
+  FPK_RSE2 = 0,   // rspec * eps2
+  FPK_RSE4 = 1,   // rspec * eps4
+  FPK_SD = 2,     // [5] eps2 diff_e + eps4 pred_e              (x d rspec)
+  FPK_SE = 7,     // [5] rspec (diff_e - 12 chi pred_e)          (x d eps2),  chi = [eps4 > 0]
+  FPK_DRS = 12,   // [2][5] d rspec / d w_m of along-cells -1, 0
+  FPK_DEP = 22,   // [4] d eps2 / d p(s), s = -2..1
+  FPK_DET = 26,   // [2] d eps2 / d T(s), s = -1, 0
+  FPK_DEG = 28,   // [2][4] sensor cell s = -1, 0: coefficients of (wI, wJ) in d eps2/dU_c and in d eps2/dV_c
+  FPK_MMU = 36, FPK_UU = 37, FPK_VV = 38, FPK_WW = 39,
+  FPK_V1M = 40, FPK_V2M = 41, FPK_V3M = 42, FPK_V4M = 43,  // visc_e / mmu
+};
+
+// a single cell seen through the accessor interface (for flux_f / flux_g)
+struct OneCell {
+  const Var<Tan<5>>* q;
+  const CellPrims<Tan<5>>* pp;
+  template <int OI, int OJ> BC_HD Var<Tan<5>> W(int e) const { return q[e]; }
+  template <int OI, int OJ> BC_HD Var<Tan<5>> U() const { return pp->u; }
+  template <int OI, int OJ> BC_HD Var<Tan<5>> V() const { return pp->v; }
+  template <int OI, int OJ> BC_HD Var<Tan<5>> Wz() const { return pp->w; }
+  template <int OI, int OJ> BC_HD Var<Tan<5>> P() const { return pp->p; }
+  template <int OI, int OJ> BC_HD Var<Tan<5>> H() const { return pp->h; }
+};
+
+BC_HD void seed_cell(const double (&w5)[5], Var<Tan<5>> (&q)[5]) {
+#pragma unroll
+  for (int e = 0; e < 5; ++e) {
+    q[e].v = w5[e];
+#pragma unroll
+    for (int m = 0; m < 5; ++m) q[e].d.d[m] = (e == m) ? 1.0 : 0.0;
+  }
+}
+
+// 5-point gradient metric of a cell (geom/dxdy.F): gradient = (dxm1 d/di + dxm2 d/dj, dym1 d/di + dym2 d/dj)
+template <int CI, int CJ, class A>
+BC_HD void cell_metric(const A& a, double& dxm1, double& dxm2, double& dym1, double& dym2) {
+  const double volm1 = 1.0 / a.template VOL<CI, CJ>();
+  dxm1 = 0.5 * (a.template NX<CI, CJ>(0) + a.template NX<CI + 1, CJ>(0)) * volm1;
+  dxm2 = 0.5 * (a.template NX<CI, CJ>(1) + a.template NX<CI, CJ + 1>(1)) * volm1;
+  dym1 = 0.5 * (a.template NY<CI, CJ>(0) + a.template NY<CI + 1, CJ>(0)) * volm1;
+  dym2 = 0.5 * (a.template NY<CI, CJ>(1) + a.template NY<CI, CJ + 1>(1)) * volm1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// producer: `a` is a PASSIVE accessor based at the face cell; out(field) = value
+// ---------------------------------------------------------------------------------------------
+template <int DIR, class A, class OUT>
+BC_HD void face_package(const A& a, const SchemeConsts& c, OUT&& out) {
+  constexpr double denom = 1.0 / 60.0;
+  constexpr double d1 = 10.0 * denom, d2 = 5.0 * denom, d3 = denom;
+  const double nxf = a.template NX<0, 0>(DIR);
+  const double nyf = a.template NY<0, 0>(DIR);
+  const double nx2 = nxf * nxf + nyf * nyf;
+
+  double wr[5], wl[5];
+#pragma unroll
+  for (int e = 0; e < 5; ++e) {
+    wr[e] = a.template W<0, 0>(e).v;
+    wl[e] = a.template W<AT(-1, 0)>(e).v;
+  }
+  const PVar tr = a.template T<0, 0>(), tl = a.template T<AT(-1, 0)>();
+
+  // ---- spectral radius: value and gradient w.r.t. the conservative variables of the two face cells
+  const PVar rspec = spectral_radius(cst(wr[0]), cst(wr[1]), cst(wr[2]), tr, cst(wl[0]), cst(wl[1]), cst(wl[2]), tl, nxf, nyf, c);
+  {
+    Var<Tan<5>> q[5];
+    seed_cell(wr, q);
+    const CellPrims<Tan<5>> pp = cell_prims(q, c);
+    const auto rs = spectral_radius(q[0], q[1], q[2], pp.t, cst(wl[0]), cst(wl[1]), cst(wl[2]), tl, nxf, nyf, c);
+#pragma unroll
+    for (int m = 0; m < 5; ++m) out(FPK_DRS + 5 + m, rs.d.d[m]);
+  }
+  {
+    Var<Tan<5>> q[5];
+    seed_cell(wl, q);
+    const CellPrims<Tan<5>> pp = cell_prims(q, c);
+    const auto rs = spectral_radius(cst(wr[0]), cst(wr[1]), cst(wr[2]), tr, q[0], q[1], q[2], pp.t, nxf, nyf, c);
+#pragma unroll
+    for (int m = 0; m < 5; ++m) out(FPK_DRS + m, rs.d.d[m]);
+  }
+
+  // ---- sensor: eps2 as a function of 10 face-level scalars, differentiated in vector forward mode
+  using T10 = Tan<10>;
+  auto seed = [](double v, int k) {
+    Var<T10> r;
+    r.v = v;
+#pragma unroll
+    for (int n = 0; n < 10; ++n) r.d.d[n] = (n == k) ? 1.0 : 0.0;
+    return r;
+  };
+  struct G10 {
+    Var<T10> u0, u1, v0, v1;
+  };
+  const auto g0p = a.template GR<0, 0>();
+  const auto g1p = a.template GR<AT(-1, 0)>();
+  // directions: 0..3 p(-2..1), 4 T(-1), 5 T(0), 6 divu(-1), 7 vort(-1), 8 divu(0), 9 vort(0)   (vort = gv0 - gu1)
+  const G10 gr1{seed(g1p.u0.v, 6), seed(g1p.u1.v, -1), seed(g1p.v0.v, 7), seed(g1p.v1.v, -1)};
+  const G10 gr0{seed(g0p.u0.v, 8), seed(g0p.u1.v, -1), seed(g0p.v0.v, 9), seed(g0p.v1.v, -1)};
+  const auto c2l = c.gam * c.rgaz * seed(tl.v, 4);
+  const auto c2r = c.gam * c.rgaz * seed(tr.v, 5);
+  const auto coef = sensor_coef(seed(a.template P<AT(-2, 0)>().v, 0), seed(a.template P<AT(-1, 0)>().v, 1), seed(a.template P<0, 0>().v, 2),
+                                seed(a.template P<AT(1, 0)>().v, 3), gr0, gr1, a.template VOL<0, 0>(), a.template VOL<AT(-1, 0)>(), c2r, c2l,
+                                nx2);
+  const auto eps2 = c.k2 * coef;
+  const auto eps4 = fmax(0.0, c.k4 - eps2 * 12.0);
+  const bool chi = eps4.v > 0.0;
+
+  out(FPK_RSE2, rspec.v * eps2.v);
+  out(FPK_RSE4, rspec.v * eps4.v);
+#pragma unroll
+  for (int e = 0; e < 5; ++e) {
+    const double pred = -d3 * a.template W<AT(-3, 0)>(e).v + d2 * a.template W<AT(-2, 0)>(e).v - d1 * wl[e] + d1 * wr[e] -
+                        d2 * a.template W<AT(1, 0)>(e).v + d3 * a.template W<AT(2, 0)>(e).v;
+    const double diff = 0.5 * (wr[e] - wl[e]);
+    out(FPK_SD + e, eps2.v * diff + eps4.v * pred);
+    out(FPK_SE + e, rspec.v * (chi ? diff - 12.0 * pred : diff));
+  }
+#pragma unroll
+  for (int n = 0; n < 4; ++n) out(FPK_DEP + n, eps2.d.d[n]);
+  out(FPK_DET + 0, eps2.d.d[4]);
+  out(FPK_DET + 1, eps2.d.d[5]);
+  {
+    double dxm1, dxm2, dym1, dym2;
+    cell_metric<AT(-1, 0)>(a, dxm1, dxm2, dym1, dym2);
+    const double dv = eps2.d.d[6], vo = eps2.d.d[7];
+    out(FPK_DEG + 0, dv * dxm1 - vo * dym1);  // wI in d eps2 / dU_c
+    out(FPK_DEG + 1, dv * dxm2 - vo * dym2);  // wJ in d eps2 / dU_c
+    out(FPK_DEG + 2, dv * dym1 + vo * dxm1);  // wI in d eps2 / dV_c
+    out(FPK_DEG + 3, dv * dym2 + vo * dxm2);  // wJ in d eps2 / dV_c
+  }
+  {
+    double dxm1, dxm2, dym1, dym2;
+    cell_metric<0, 0>(a, dxm1, dxm2, dym1, dym2);
+    const double dv = eps2.d.d[8], vo = eps2.d.d[9];
+    out(FPK_DEG + 4, dv * dxm1 - vo * dym1);
+    out(FPK_DEG + 5, dv * dxm2 - vo * dym2);
+    out(FPK_DEG + 6, dv * dym1 + vo * dxm1);
+    out(FPK_DEG + 7, dv * dym2 + vo * dxm2);
+  }
+
+  // ---- viscous part
+  const DualNormals dn = dual_normals<DIR>(a);
+  const auto s = visc_scalars<DIR, false>(a, dn);
+  constexpr double TWOTHIRD = 2.0 / 3.0;
+  const double v1m = TWOTHIRD * (2.0 * s.ux.v - s.vy.v) * nxf + (s.uy.v + s.vx.v) * nyf;
+  const double v2m = (s.uy.v + s.vx.v) * nxf + TWOTHIRD * (-s.ux.v + 2.0 * s.vy.v) * nyf;
+  const double v3m = s.wx.v * nxf + s.wy.v * nyf;
+  const double v4m = c.cpprandtl * (s.tx.v * nxf + s.ty.v * nyf) + s.uu.v * v1m + s.vv.v * v2m + s.ww.v * v3m;
+  out(FPK_MMU, s.mmu.v);
+  out(FPK_UU, s.uu.v);
+  out(FPK_VV, s.vv.v);
+  out(FPK_WW, s.ww.v);
+  out(FPK_V1M, v1m);
+  out(FPK_V2M, v2m);
+  out(FPK_V3M, v3m);
+  out(FPK_V4M, v4m);
+}
+
+// ---------------------------------------------------------------------------------------------
+// consumer
+// ---------------------------------------------------------------------------------------------
+struct ColAcc {
+  double gU[5], gV[5], gW[5], gT[5], gMu[5], gP[5];  // sum over faces of sgn * d hn_e / d primitive of the column cell
+  double diag;                                       // coefficient of delta_em
+  double Nx, Ny;                                     // Euler: sum of sgn * c(s) * face normal
+  double dir[5][5];                                  // conservative-level rank-1 terms (SD x d rspec)
+  BC_HD void clear() {
+#pragma unroll
+    for (int e = 0; e < 5; ++e) {
+      gU[e] = gV[e] = gW[e] = gT[e] = gMu[e] = gP[e] = 0.0;
+#pragma unroll
+      for (int m = 0; m < 5; ++m) dir[e][m] = 0.0;
+    }
+    diag = Nx = Ny = 0.0;
+  }
+};
+
+// per-face data the consumer keeps at hand
+struct FaceCtx {
+  double nxf, nyf;
+  DualNormals dn;
+  const double* pk;   // package of this face: field f at pk[f * stride]
+  long long stride;
+  BC_HD double operator()(int f) const { return BC_LDG(pk + f * stride); }
+};
+
+namespace fj {
+constexpr double kDen = 1.0 / 60.0;
+constexpr double euler_c(int s) { return (s == 0 || s == -1) ? 37.0 * kDen : ((s == 1 || s == -2) ? -8.0 * kDen : ((s == 2 || s == -3) ? kDen : 0.0)); }
+constexpr double pred_c(int s) {
+  return s == -3 ? -kDen : s == -2 ? 5.0 * kDen : s == -1 ? -10.0 * kDen : s == 0 ? 10.0 * kDen : s == 1 ? -5.0 * kDen : s == 2 ? kDen : 0.0;
+}
+constexpr double diff_c(int s) { return s == 0 ? 0.5 : (s == -1 ? -0.5 : 0.0); }
+constexpr double grad_w(int d) { return d == 1 ? 8.0 / 12.0 : d == -1 ? -8.0 / 12.0 : d == 2 ? -1.0 / 12.0 : d == -2 ? 1.0 / 12.0 : 0.0; }
+// compact o4 interpolation weights (flux_visqueux_o4_{i,j}.F): along-rows r(s), cross m(t)
+constexpr double o4_r(int s) { return (s == -2 || s == 1) ? -1.0 : ((s == -1 || s == 0) ? 9.0 : 0.0); }
+constexpr double o4_mCm(int t) { return (t == -2 || t == 1) ? -1.0 : ((t == -1 || t == 0) ? 7.0 : 0.0); }
+constexpr double o4_mCp(int t) { return (t == -1 || t == 2) ? -1.0 : ((t == 0 || t == 1) ? 7.0 : 0.0); }
+constexpr double o4_Ap(int s, int t) { return t != 0 ? 0.0 : (s == 0 ? 26.0 / 24.0 : ((s == 1 || s == -1) ? -1.0 / 24.0 : 0.0)); }
+constexpr double o4_Am(int s, int t) { return t != 0 ? 0.0 : (s == -1 ? 26.0 / 24.0 : ((s == 0 || s == -2) ? -1.0 / 24.0 : 0.0)); }
+constexpr double kCross = (0.25 / 3.0) * 0.0625;
+constexpr double o4_Cm(int s, int t) { return kCross * o4_r(s) * o4_mCm(t); }
+constexpr double o4_Cp(int s, int t) { return kCross * o4_r(s) * o4_mCp(t); }
+constexpr bool in_visc(int s, int t) { return s >= -2 && s <= 1 && t >= -2 && t <= 2; }
+constexpr bool in_face(int s, int t) { return (t == 0 && s >= -3 && s <= 2) || in_visc(s, t); }
+}  // namespace fj
+
+// contribution of one face (direction DIR, sign sgn in the row balance) to the column cell at
+// (along, cross) = (S, T) from the face cell
+template <int DIR, int S, int T>
+BC_HD void face_contrib(const FaceCtx& f, const SchemeConsts& c, double sgn, ColAcc& acc) {
+  using namespace fj;
+  if constexpr (!in_face(S, T)) {
+    return;
+  } else {
+    if constexpr (T == 0 && S >= -3 && S <= 2) {
+      constexpr double cE = euler_c(S), dd = diff_c(S), dp = pred_c(S);
+      acc.Nx += sgn * cE * f.nxf;
+      acc.Ny += sgn * cE * f.nyf;
+      if constexpr (dd != 0.0)
+        acc.diag -= sgn * (f(FPK_RSE2) * dd + f(FPK_RSE4) * dp);
+      else
+        acc.diag -= sgn * (f(FPK_RSE4) * dp);
+    }
+    if constexpr (T == 0 && (S == 0 || S == -1)) {
+      double drs[5];
+#pragma unroll
+      for (int m = 0; m < 5; ++m) drs[m] = f(FPK_DRS + (S + 1) * 5 + m);
+      const double det = f(FPK_DET + (S + 1));
+#pragma unroll
+      for (int e = 0; e < 5; ++e) {
+        const double sd = sgn * f(FPK_SD + e);
+#pragma unroll
+        for (int m = 0; m < 5; ++m) acc.dir[e][m] -= sd * drs[m];
+        acc.gT[e] -= sgn * f(FPK_SE + e) * det;
+      }
+    }
+    if constexpr (T == 0 && S >= -2 && S <= 1) {
+      const double dep = f(FPK_DEP + (S + 2));
+#pragma unroll
+      for (int e = 0; e < 5; ++e) acc.gP[e] -= sgn * f(FPK_SE + e) * dep;
+    }
+    // sensor: velocity gradients of the along-cells -1 and 0 (5-point crosses in GRID directions)
+    {
+      constexpr int daL = S + 1, daR = S;                 // along offset from sensor cell -1 / 0
+      constexpr int diL = DIR == 0 ? daL : T, djL = DIR == 0 ? T : daL;
+      constexpr int diR = DIR == 0 ? daR : T, djR = DIR == 0 ? T : daR;
+      constexpr double wIL = djL == 0 ? grad_w(diL) : 0.0, wJL = diL == 0 ? grad_w(djL) : 0.0;
+      constexpr double wIR = djR == 0 ? grad_w(diR) : 0.0, wJR = diR == 0 ? grad_w(djR) : 0.0;
+      constexpr bool anyL = wIL != 0.0 || wJL != 0.0, anyR = wIR != 0.0 || wJR != 0.0;
+      if constexpr (anyL || anyR) {
+        double eU = 0.0, eV = 0.0;
+        if constexpr (anyL) {
+          eU += f(FPK_DEG + 0) * wIL + f(FPK_DEG + 1) * wJL;
+          eV += f(FPK_DEG + 2) * wIL + f(FPK_DEG + 3) * wJL;
+        }
+        if constexpr (anyR) {
+          eU += f(FPK_DEG + 4) * wIR + f(FPK_DEG + 5) * wJR;
+          eV += f(FPK_DEG + 6) * wIR + f(FPK_DEG + 7) * wJR;
+        }
+#pragma unroll
+        for (int e = 0; e < 5; ++e) {
+          const double se = sgn * f(FPK_SE + e);
+          acc.gU[e] -= se * eU;
+          acc.gV[e] -= se * eV;
+        }
+      }
+    }
+    if constexpr (in_visc(S, T)) {
+      constexpr double aAp = o4_Ap(S, T), aAm = o4_Am(S, T), aCp = o4_Cp(S, T), aCm = o4_Cm(S, T);
+      constexpr double c0 = T == 0 ? o4_r(S) * 0.0625 : 0.0;
+      double cx = aCp * f.dn.nCp_x + aCm * f.dn.nCm_x;
+      double cy = aCp * f.dn.nCp_y + aCm * f.dn.nCm_y;
+      if constexpr (aAp != 0.0) {
+        cx += aAp * f.dn.nAp_x;
+        cy += aAp * f.dn.nAp_y;
+      }
+      if constexpr (aAm != 0.0) {
+        cx += aAm * f.dn.nAm_x;
+        cy += aAm * f.dn.nAm_y;
+      }
+      cx *= f.dn.volm1;
+      cy *= f.dn.volm1;
+      const double mmu = f(FPK_MMU), uu = f(FPK_UU), vv = f(FPK_VV), ww = f(FPK_WW);
+      const double a_ = f.nxf * cx, b_ = f.nyf * cy, c_ = f.nyf * cx, d_ = f.nxf * cy;
+      constexpr double FT = 4.0 / 3.0, TT = 2.0 / 3.0;
+      const double al = sgn * mmu * (FT * a_ + b_);   // d visc_1 / dU
+      const double be = sgn * mmu * (c_ - TT * d_);   // d visc_1 / dV
+      const double ga = sgn * mmu * (d_ - TT * c_);   // d visc_2 / dU
+      const double de = sgn * mmu * (a_ + FT * b_);   // d visc_2 / dV
+      const double ep = sgn * mmu * (a_ + b_);        // d visc_3 / dWz
+      acc.gU[1] -= al;
+      acc.gV[1] -= be;
+      acc.gU[2] -= ga;
+      acc.gV[2] -= de;
+      acc.gW[3] -= ep;
+      double g4U = uu * al + vv * ga, g4V = uu * be + vv * de, g4W = ww * ep;
+      if constexpr (c0 != 0.0) {
+        const double v1m = f(FPK_V1M), v2m = f(FPK_V2M), v3m = f(FPK_V3M), v4m = f(FPK_V4M);
+        const double k = sgn * c0;
+        g4U += k * mmu * v1m;
+        g4V += k * mmu * v2m;
+        g4W += k * mmu * v3m;
+        acc.gMu[1] -= k * v1m;
+        acc.gMu[2] -= k * v2m;
+        acc.gMu[3] -= k * v3m;
+        acc.gMu[4] -= k * v4m;
+      }
+      acc.gU[4] -= g4U;
+      acc.gV[4] -= g4V;
+      acc.gW[4] -= g4W;
+      acc.gT[4] -= c.cpprandtl * ep;
+    }
+  }
+}
+
+// which of the four faces of a row cell see the column offset (DI, DJ), and where
+template <int DI, int DJ>
+struct BlockFaces {
+  static constexpr bool iL = fj::in_face(DI, DJ);        // i-face (i,j):   (S,T) = (DI, DJ),   sign -
+  static constexpr bool iR = fj::in_face(DI - 1, DJ);    // i-face (i+1,j): (S,T) = (DI-1, DJ), sign +
+  static constexpr bool jL = fj::in_face(DJ, DI);        // j-face (i,j):   (S,T) = (DJ, DI),   sign -
+  static constexpr bool jR = fj::in_face(DJ - 1, DI);    // j-face (i,j+1): (S,T) = (DJ-1, DI), sign +
+};
+
+// chain rule with the column cell: B[e][m] (row-major 25) = -d residu_e / d w_m
+BC_HD void block_finish(const ColAcc& acc, const double (&wc)[5], const SchemeConsts& c, bool euler, double (&B)[25]) {
+  Var<Tan<5>> q[5];
+  seed_cell(wc, q);
+  const CellPrims<Tan<5>> pp = cell_prims(q, c);
+#pragma unroll
+  for (int e = 0; e < 5; ++e)
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+      double v = acc.dir[e][m] + acc.gU[e] * pp.u.d.d[m] + acc.gV[e] * pp.v.d.d[m] + acc.gW[e] * pp.w.d.d[m] + acc.gT[e] * pp.t.d.d[m] +
+                 acc.gMu[e] * pp.mu.d.d[m] + acc.gP[e] * pp.p.d.d[m];
+      if (e == m) v += acc.diag;
+      B[e * 5 + m] = v;
+    }
+  if (euler) {
+    const OneCell oc{q, &pp};
+#pragma unroll
+    for (int e = 0; e < 5; ++e) {
+      const auto F = flux_f<0, 0>(oc, e) * acc.Nx + flux_g<0, 0>(oc, e) * acc.Ny;
+#pragma unroll
+      for (int m = 0; m < 5; ++m) B[e * 5 + m] += F.d.d[m];
+    }
+  }
+}
+
+// whole block of row cell (i,j), column offset (DI,DJ).  fi0/fi1/fj0/fj1: contexts of faces i, i+1, j, j+1.
+template <int DI, int DJ>
+BC_HD void block_of(const FaceCtx& fi0, const FaceCtx& fi1, const FaceCtx& fj0, const FaceCtx& fj1, const double (&wc)[5],
+                    const SchemeConsts& c, double (&B)[25]) {
+  ColAcc acc;
+  acc.clear();
+  face_contrib<0, DI, DJ>(fi0, c, -1.0, acc);
+  face_contrib<0, DI - 1, DJ>(fi1, c, 1.0, acc);
+  face_contrib<1, DJ, DI>(fj0, c, -1.0, acc);
+  face_contrib<1, DJ - 1, DI>(fj1, c, 1.0, acc);
+  block_finish(acc, wc, c, DI == 0 || DJ == 0, B);
+}
+
+}  // namespace bcast

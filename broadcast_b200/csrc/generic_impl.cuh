@@ -162,6 +162,131 @@ cudaError_t residual_generic_t(const GridDesc& g, const SchemeArgs& a, bool wall
 }
 
 
+#define BCAST_CAT2(a, b) a##b
+#define BCAST_CAT(a, b) BCAST_CAT2(a, b)
+
+// ---------------------------------------------------------------------------------------------
+// spanwise operators (srcfv/dz/coeffs_5p_dz.F90:10-174, coeffs_5p_dz2.F90): per interior cell
+//   dz_out(e) = sum_k coeffs_k(w)(e) * d func_k(w)[wd](e)
+// coefficient tables dz/coeffs_dz.F, dz/coeffs_dz2.F; functions matrix_dz/function_dz.F,
+// matrix_dz2/function_dz2.F (their tangents: dz/function_5p_dz_d.f90:155-401, function_5p_dz2_d.f90).
+// WHICH = 1: d/dz rows (cell + 5-point cross), WHICH = 2: d2/dz2 rows (cell-local).
+// ---------------------------------------------------------------------------------------------
+#if BCAST_N > 0
+template <int N, int WHICH>
+__global__ void __launch_bounds__(128) k_dz(GridDesc g, SchemeConsts c, FieldPtrs f, Rect rc, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + rc.i0;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + rc.j0;
+  if (i > rc.i1 || j > rc.j1) return;
+  using DT = Tan<N>;
+  const GlobalAcc<N> a(f, g, i, j);
+  const long long k = g.cidx(i, j);
+  const Var<DT> u = a.template U<0, 0>(), v = a.template V<0, 0>(), wz = a.template Wz<0, 0>();
+  const Var<DT> mu = a.template Mu<0, 0>();
+  constexpr double TWOTHIRD = 2.0 / 3.0;
+  double r[5][N];
+  if constexpr (WHICH == 2) {
+    const Var<DT> t = a.template T<0, 0>();
+    const double c1[5] = {0.0, -mu.v, -mu.v, -2.0 * TWOTHIRD * mu.v, -mu.v * c.cpprandtl};
+    const double c2 = -mu.v * u.v, c3 = -mu.v * v.v, c4 = -2.0 * TWOTHIRD * mu.v * wz.v;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      r[0][n] = c1[0] * 0.0;
+      r[1][n] = c1[1] * u.d.d[n];
+      r[2][n] = c1[2] * v.d.d[n];
+      r[3][n] = c1[3] * wz.d.d[n];
+      r[4][n] = c1[4] * t.d.d[n] + c2 * u.d.d[n] + c3 * v.d.d[n] + c4 * wz.d.d[n];
+    }
+  } else {
+    const Var<DT> p = a.template P<0, 0>();
+    Var<DT> q[5];
+#pragma unroll
+    for (int e = 0; e < 5; ++e) q[e] = a.template W<0, 0>(e);
+    // 5-point gradients (gradop_5pi.F, gradop_5pj.F, gradient.F, dxdy.F)
+    constexpr double b1 = 8.0 * (1.0 / 12.0), b2 = -(1.0 / 12.0);
+    const double volm1 = 1.0 / a.template VOL<0, 0>();
+    const double dxm1 = 0.5 * (a.template NX<0, 0>(0) + a.template NX<1, 0>(0)) * volm1;
+    const double dxm2 = 0.5 * (a.template NX<0, 0>(1) + a.template NX<0, 1>(1)) * volm1;
+    const double dym1 = 0.5 * (a.template NY<0, 0>(0) + a.template NY<1, 0>(0)) * volm1;
+    const double dym2 = 0.5 * (a.template NY<0, 0>(1) + a.template NY<0, 1>(1)) * volm1;
+#define BC_GRAD(Q, G0, G1)                                                                                                        \
+  auto G0##_i = b1 * (a.template Q<1, 0>() - a.template Q<-1, 0>()) + b2 * (a.template Q<2, 0>() - a.template Q<-2, 0>());       \
+  auto G0##_j = b1 * (a.template Q<0, 1>() - a.template Q<0, -1>()) + b2 * (a.template Q<0, 2>() - a.template Q<0, -2>());       \
+  auto G0 = dxm1 * G0##_i + dxm2 * G0##_j;                                                                                        \
+  auto G1 = dym1 * G0##_i + dym2 * G0##_j;
+    BC_GRAD(U, gu0, gu1)
+    BC_GRAD(V, gv0, gv1)
+    BC_GRAD(Wz, gw0, gw1)
+    BC_GRAD(Mu, gm0, gm1)
+#undef BC_GRAD
+    (void)gu1;
+    (void)gv0;
+    const auto divu = gu0 + gv1;
+    // functions (matrix_dz/function_dz.F) in tangent arithmetic
+    const auto f0_1 = q[1] * wz - mu * gw0;
+    const auto f0_2 = q[2] * wz - mu * gw1;
+    const auto f0_3 = q[3] * wz + p + TWOTHIRD * mu * divu;
+    const auto f0_4 = (q[4] + p) * wz;
+    const auto f10 = mu * gw0;
+    const auto f12 = mu * gw1;
+    // coefficients (dz/coeffs_dz.F), passive
+    const double muv = mu.v, uv = u.v, vv = v.v, wv = wz.v, gm0v = gm0.v, gm1v = gm1.v;
+    const double k2_[5] = {0.0, TWOTHIRD * gm0v, TWOTHIRD * gm1v, -gm0v, TWOTHIRD * (gm0v * uv + muv * gu0.v)};
+    const double k3_[5] = {0.0, TWOTHIRD * muv, TWOTHIRD * muv, -gm1v, TWOTHIRD * muv * uv};
+    const double k4_3 = -muv, k4_4 = -(gm0v * wv + muv * gw0.v);
+    const double k5 = -muv * wv;
+    const double k6 = TWOTHIRD * (gm1v * vv + muv * gv1.v);
+    const double k7 = TWOTHIRD * muv * vv;
+    const double k8 = -(gm1v * wv + muv * gw1.v);
+    const double k9 = -muv * wv;
+    const double k10 = -muv * gw0.v;
+    const double k11 = -uv;
+    const double k12 = -muv * gw1.v;
+    const double k13 = -vv;
+    const double k14 = TWOTHIRD * muv * divu.v;
+    const double k15 = TWOTHIRD * wv * divu.v;
+    const double k16 = TWOTHIRD * muv * wv;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      r[0][n] = q[3].d.d[n];
+      r[1][n] = f0_1.d.d[n] + k2_[1] * wz.d.d[n] + k3_[1] * gw0.d.d[n];
+      r[2][n] = f0_2.d.d[n] + k2_[2] * wz.d.d[n] + k3_[2] * gw1.d.d[n];
+      r[3][n] = f0_3.d.d[n] + k2_[3] * u.d.d[n] + k3_[3] * v.d.d[n] + k4_3 * divu.d.d[n];
+      r[4][n] = f0_4.d.d[n] + k2_[4] * wz.d.d[n] + k3_[4] * gw0.d.d[n] + k4_4 * u.d.d[n] + k5 * gu0.d.d[n] + k6 * wz.d.d[n] +
+                k7 * gw1.d.d[n] + k8 * v.d.d[n] + k9 * gv1.d.d[n] + k10 * u.d.d[n] + k11 * f10.d.d[n] + k12 * v.d.d[n] +
+                k13 * f12.d.d[n] + k14 * wz.d.d[n] + k15 * mu.d.d[n] + k16 * divu.d.d[n];
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < N; ++n)
+#pragma unroll
+    for (int e = 0; e < 5; ++e) out[(long long)(n * 5 + e) * g.sc + k] = r[e][n];
+}
+
+cudaError_t BCAST_CAT(dz_generic_, BCAST_N)(const GridDesc& g, const SchemeArgs& a, int which, double* out, const double* w, const double* wd,
+                                           const double* nx, const double* ny, const double* vol, const double* volf, const Rect* rect,
+                                           cudaStream_t st) {
+  constexpr int N = BCAST_N;
+  const SchemeConsts c = make_consts(a.cp, a.cv, a.prandtl, a.gam, a.rgaz, a.cs, a.muref, a.tref, a.s_suth, a.k2, a.k4);
+  double* prim = scratch_doubles(0, (size_t)g.sc * NPRIM);
+  double* primd = scratch_doubles(2, (size_t)g.sc * NPRIM * N);
+  if (!prim || !primd) return cudaErrorMemoryAllocation;
+  Rect rc = rect ? *rect : Rect{1, g.im, 1, g.jm};
+  if (rc.i1 < rc.i0 || rc.j1 < rc.j0) return cudaSuccess;
+  const Rect rp{max(0, rc.i0 - 3 + g.gh), min(g.ni() - 1, rc.i1 + 1 + g.gh), max(0, rc.j0 - 3 + g.gh), min(g.nj() - 1, rc.j1 + 1 + g.gh)};
+  dim3 blk(32, 4);
+  dim3 gall((rp.i1 - rp.i0 + 32) / 32, (rp.j1 - rp.j0 + 4) / 4);
+  k_prims<N><<<gall, blk, 0, st>>>(g, c, rp, w, wd, prim, primd);
+  FieldPtrs f{w, prim, nullptr, nx, ny, vol, volf, wd, primd, nullptr};
+  dim3 gb((rc.i1 - rc.i0 + 32) / 32, (rc.j1 - rc.j0 + 4) / 4);
+  if (which == 1)
+    k_dz<N, 1><<<gb, blk, 0, st>>>(g, c, f, rc, out);
+  else
+    k_dz<N, 2><<<gb, blk, 0, st>>>(g, c, f, rc, out);
+  return cudaGetLastError();
+}
+#endif
+
 #if BCAST_N == 0
 // passive prims + gradients into the scratch arena, for kernels that read them (jac_interior.cu)
 cudaError_t prepare_prims_grads(const GridDesc& g, const SchemeArgs& a, const double* w, const double* nx, const double* ny,
@@ -181,8 +306,6 @@ cudaError_t prepare_prims_grads(const GridDesc& g, const SchemeArgs& a, const do
 }
 #endif
 
-#define BCAST_CAT2(a, b) a##b
-#define BCAST_CAT(a, b) BCAST_CAT2(a, b)
 cudaError_t BCAST_CAT(residual_generic_, BCAST_N)(const GridDesc& g, const SchemeArgs& a, bool wall, double* out, const double* w,
                                                  const double* wd, const double* nx, const double* ny, const double* vol,
                                                  const double* volf, const Rect* rect, cudaStream_t st) {

@@ -10,6 +10,15 @@
 
 namespace bcast {
 
+// read-only load (LDG.NC on the device, plain load on the host build used by the CPU-side tests)
+BC_HD double BC_LDG(const double* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
 struct GridDesc {
   int im, jm, gh;
   int ldc, ldn;
@@ -64,39 +73,39 @@ struct GlobalAcc {
   int ldc, ldn;
   long long sc, sn;
 
-  __device__ __forceinline__ GlobalAcc(const FieldPtrs& f_, const GridDesc& g, int i, int j)
+  BC_HD GlobalAcc(const FieldPtrs& f_, const GridDesc& g, int i, int j)
       : f(f_), c(g.cidx(i, j)), n(g.nidx(i, j)), ldc(g.ldc), ldn(g.ldn), sc(g.sc), sn(g.sn) {}
 
-  __device__ __forceinline__ Var<DT> load(const double* v, const double* d, int plane, int nplanes, long long k) const {
+  BC_HD Var<DT> load(const double* v, const double* d, int plane, int nplanes, long long k) const {
     Var<DT> r;
-    r.v = __ldg(v + plane * sc + k);
+    r.v = BC_LDG(v + plane * sc + k);
     if constexpr (N > 0) {
 #pragma unroll
-      for (int q = 0; q < N; ++q) r.d.d[q] = __ldg(d + (long long)(q * nplanes + plane) * sc + k);
+      for (int q = 0; q < N; ++q) r.d.d[q] = BC_LDG(d + (long long)(q * nplanes + plane) * sc + k);
     }
     return r;
   }
-  template <int OI, int OJ> __device__ __forceinline__ long long ck() const { return c + OI + (long long)OJ * ldc; }
-  template <int OI, int OJ> __device__ __forceinline__ long long nk() const { return n + OI + (long long)OJ * ldn; }
+  template <int OI, int OJ> BC_HD long long ck() const { return c + OI + (long long)OJ * ldc; }
+  template <int OI, int OJ> BC_HD long long nk() const { return n + OI + (long long)OJ * ldn; }
 
-  template <int OI, int OJ> __device__ __forceinline__ Var<DT> W(int e) const { return load(f.w, f.wd, e, 5, ck<OI, OJ>()); }
-  template <int OI, int OJ> __device__ __forceinline__ Var<DT> U() const { return load(f.prim, f.primd, PR_U, NPRIM, ck<OI, OJ>()); }
-  template <int OI, int OJ> __device__ __forceinline__ Var<DT> V() const { return load(f.prim, f.primd, PR_V, NPRIM, ck<OI, OJ>()); }
-  template <int OI, int OJ> __device__ __forceinline__ Var<DT> Wz() const { return load(f.prim, f.primd, PR_W, NPRIM, ck<OI, OJ>()); }
-  template <int OI, int OJ> __device__ __forceinline__ Var<DT> T() const { return load(f.prim, f.primd, PR_T, NPRIM, ck<OI, OJ>()); }
-  template <int OI, int OJ> __device__ __forceinline__ Var<DT> P() const { return load(f.prim, f.primd, PR_P, NPRIM, ck<OI, OJ>()); }
-  template <int OI, int OJ> __device__ __forceinline__ Var<DT> Mu() const { return load(f.prim, f.primd, PR_MU, NPRIM, ck<OI, OJ>()); }
-  template <int OI, int OJ> __device__ __forceinline__ Var<DT> H() const { return load(f.prim, f.primd, PR_H, NPRIM, ck<OI, OJ>()); }
-  template <int OI, int OJ> __device__ __forceinline__ Var<DT> GU(int cc) const { return load(f.grad, f.gradd, cc, NGRAD, ck<OI, OJ>()); }
-  template <int OI, int OJ> __device__ __forceinline__ Var<DT> GV(int cc) const { return load(f.grad, f.gradd, 2 + cc, NGRAD, ck<OI, OJ>()); }
-  template <int OI, int OJ> __device__ __forceinline__ auto GR() const {
+  template <int OI, int OJ> BC_HD Var<DT> W(int e) const { return load(f.w, f.wd, e, 5, ck<OI, OJ>()); }
+  template <int OI, int OJ> BC_HD Var<DT> U() const { return load(f.prim, f.primd, PR_U, NPRIM, ck<OI, OJ>()); }
+  template <int OI, int OJ> BC_HD Var<DT> V() const { return load(f.prim, f.primd, PR_V, NPRIM, ck<OI, OJ>()); }
+  template <int OI, int OJ> BC_HD Var<DT> Wz() const { return load(f.prim, f.primd, PR_W, NPRIM, ck<OI, OJ>()); }
+  template <int OI, int OJ> BC_HD Var<DT> T() const { return load(f.prim, f.primd, PR_T, NPRIM, ck<OI, OJ>()); }
+  template <int OI, int OJ> BC_HD Var<DT> P() const { return load(f.prim, f.primd, PR_P, NPRIM, ck<OI, OJ>()); }
+  template <int OI, int OJ> BC_HD Var<DT> Mu() const { return load(f.prim, f.primd, PR_MU, NPRIM, ck<OI, OJ>()); }
+  template <int OI, int OJ> BC_HD Var<DT> H() const { return load(f.prim, f.primd, PR_H, NPRIM, ck<OI, OJ>()); }
+  template <int OI, int OJ> BC_HD Var<DT> GU(int cc) const { return load(f.grad, f.gradd, cc, NGRAD, ck<OI, OJ>()); }
+  template <int OI, int OJ> BC_HD Var<DT> GV(int cc) const { return load(f.grad, f.gradd, 2 + cc, NGRAD, ck<OI, OJ>()); }
+  template <int OI, int OJ> BC_HD auto GR() const {
     struct R { Var<DT> u0, u1, v0, v1; };
     return R{GU<OI, OJ>(0), GU<OI, OJ>(1), GV<OI, OJ>(0), GV<OI, OJ>(1)};
   }
-  template <int OI, int OJ> __device__ __forceinline__ double NX(int k) const { return __ldg(f.nx + k * sn + nk<OI, OJ>()); }
-  template <int OI, int OJ> __device__ __forceinline__ double NY(int k) const { return __ldg(f.ny + k * sn + nk<OI, OJ>()); }
-  template <int OI, int OJ> __device__ __forceinline__ double VOL() const { return __ldg(f.vol + ck<OI, OJ>()); }
-  template <int OI, int OJ> __device__ __forceinline__ double VOLF(int k) const { return __ldg(f.volf + k * sc + ck<OI, OJ>()); }
+  template <int OI, int OJ> BC_HD double NX(int k) const { return BC_LDG(f.nx + k * sn + nk<OI, OJ>()); }
+  template <int OI, int OJ> BC_HD double NY(int k) const { return BC_LDG(f.ny + k * sn + nk<OI, OJ>()); }
+  template <int OI, int OJ> BC_HD double VOL() const { return BC_LDG(f.vol + ck<OI, OJ>()); }
+  template <int OI, int OJ> BC_HD double VOLF(int k) const { return BC_LDG(f.volf + k * sc + ck<OI, OJ>()); }
 };
 
 }  // namespace bcast

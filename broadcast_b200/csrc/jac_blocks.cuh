@@ -11,6 +11,7 @@
 // (misc/ComputeJacobian.f90:558-563, srcfv/tangent/flux_num_dnc5_d.f90).
 #pragma once
 #include "kernels.cuh"
+#include "facejac.cuh"
 
 namespace bcast {
 
@@ -149,12 +150,7 @@ cudaError_t launch_jac_block(const GridDesc& g, const SchemeConsts& c, const Fie
   return cudaGetLastError();
 }
 
-// the 29 structural offsets in column order (di major, dj minor): slot index = position in this list
-#define BCAST_JAC_OFFSETS(X)                                                                                      \
-  X(-3, 0) X(-2, -2) X(-2, -1) X(-2, 0) X(-2, 1) X(-2, 2) X(-1, -2) X(-1, -1) X(-1, 0) X(-1, 1) X(-1, 2) X(0, -3) \
-  X(0, -2) X(0, -1) X(0, 0) X(0, 1) X(0, 2) X(0, 3) X(1, -2) X(1, -1) X(1, 0) X(1, 1) X(1, 2) X(2, -2) X(2, -1)   \
-  X(2, 0) X(2, 1) X(2, 2) X(3, 0)
-constexpr int JAC_NSLOT = 29;
+// the 29 structural offsets: BCAST_JAC_OFFSETS / JAC_NSLOT in facejac.cuh
 
 typedef cudaError_t (*jac_block_fn)(const GridDesc&, const SchemeConsts&, const FieldPtrs&, const Rect&, double*, const double*, cudaStream_t);
 jac_block_fn jac_block_launcher(int di, int dj);

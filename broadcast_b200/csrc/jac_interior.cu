@@ -7,6 +7,9 @@ namespace bcast {
 void count_launches(int n);
 cudaError_t prepare_prims_grads(const GridDesc& g, const SchemeArgs& a, const double* w, const double* nx, const double* ny,
                                 const double* vol, const double* volf, FieldPtrs& f, cudaStream_t st);
+cudaError_t launch_jacobian_faces(const GridDesc& g, const SchemeArgs& a, const double* w, const double* nx, const double* ny,
+                                  const double* vol, const double* volf, const Rect& rc, double* values, const double* coefdiag,
+                                  cudaStream_t st);
 #define DECL(G) jac_block_fn jac_block_launcher_g##G(int, int);
 DECL(0) DECL(1) DECL(2) DECL(3) DECL(4) DECL(5) DECL(6) DECL(7)
 #undef DECL
@@ -35,6 +38,23 @@ extern "C" int bcd_jacobian_slots(int32_t* offsets /* [29][2] */) {
 }
 
 extern "C" int bcd_jacobian_interior(double* values, const double* w, const double* nx, const double* ny, const double* vol,
+                                     const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
+                                     double muref, double tref, double s_suth, double k2, double k4, int im, int jm,
+                                     const double* coefdiag, const int32_t* rect, void* stream) {
+  if (im < 1 || jm < 1 || gh != 3) return BC_ERR_ARG;
+  const GridDesc g = make_grid(im, jm, gh);
+  const SchemeArgs a{cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4};
+  Rect rc{gh + 1, im - gh, gh + 1, jm - gh};
+  if (rect) {
+    rc = Rect{rect[0], rect[1], rect[2], rect[3]};
+    if (rc.i0 < gh + 1 || rc.i1 > im - gh || rc.j0 < gh + 1 || rc.j1 > jm - gh) return BC_ERR_ARG;
+  }
+  if (rc.i1 < rc.i0 || rc.j1 < rc.j0) return BC_OK;
+  cudaError_t e = launch_jacobian_faces(g, a, w, nx, ny, vol, volf, rc, values, coefdiag, (cudaStream_t)stream);
+  return e == cudaSuccess ? BC_OK : (int)e;
+}
+
+extern "C" int bcd_jacobian_interior_ad(double* values, const double* w, const double* nx, const double* ny, const double* vol,
                                      const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
                                      double muref, double tref, double s_suth, double k2, double k4, int im, int jm,
                                      const double* coefdiag, const int32_t* rect, void* stream) {

@@ -7,6 +7,8 @@
 
 namespace bcast {
 void count_launches(int n);
+cudaError_t launch_dz(const GridDesc& g, const SchemeArgs& a, int which, int ndir, double* out, const double* w, const double* wd,
+                      const double* nx, const double* ny, const double* vol, const double* volf, const Rect* rect, cudaStream_t st);
 
 static cudaError_t apply_bc_list(const GridDesc& g, double gam, int ndir, double* w, double* wd, const double* nx, const double* ny,
                                  const bc_desc_t* bcs, int nbcs, cudaStream_t st) {
@@ -144,6 +146,45 @@ extern "C" int bcd_jacobian_coo(double* jac, int32_t* ia, int32_t* ja, double* w
       e = cudaGetLastError();
       if (e != cudaSuccess) return (int)e;
       count_launches(7);
+    }
+  return BC_OK;
+}
+
+// Colour loop of the spanwise operators (BROADCAST_npz.py:1231-1246): seeds -> linearised boundary fills ->
+// coeffs_5p_dz / coeffs_5p_dz2 -> computejacobianfromdz, five variables per pass; both COO triplets at once.
+extern "C" int bcd_dz_coo(double* jac1, int32_t* ia1, int32_t* ja1, double* jac2, int32_t* ia2, int32_t* ja2, double* w, const double* nx,
+                          const double* ny, const double* vol, const double* volf, int gh, double cp, double cv, double prandtl, double gam,
+                          double rgaz, double cs, double muref, double tref, double s_suth, int im, int jm, const bc_desc_t* bcs, int nbcs,
+                          void* stream) {
+  if (im < 1 || jm < 1 || gh != 3) return BC_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const GridDesc g = make_grid(im, jm, gh);
+  const SchemeArgs a{cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, 0.0, 0.0};
+  const int s = 2 * gh + 1;
+  double* wd5 = scratch_doubles(20, (size_t)g.sc * 25);
+  double* out5 = scratch_doubles(21, (size_t)g.sc * 25);
+  if (!wd5 || !out5) return BC_ERR_ALLOC;
+  const Rect rc{1, im, 1, jm};
+  const long long nt = 5LL * im * jm;
+  for (int l = 0; l < s; ++l)
+    for (int k = 0; k < s; ++k) {
+      cudaError_t e = launch_testvector(g, wd5, 5, 0, l, k, nullptr, st);
+      if (e != cudaSuccess) return (int)e;
+      e = apply_bc_list(g, gam, 5, w, wd5, nx, ny, bcs, nbcs, st);
+      if (e != cudaSuccess) return (int)e;
+      for (int which = 1; which <= 2; ++which) {
+        double* jac = which == 1 ? jac1 : jac2;
+        int32_t* ia = which == 1 ? ia1 : ia2;
+        int32_t* ja = which == 1 ? ja1 : ja2;
+        if (!jac) continue;
+        e = launch_dz(g, a, which, 5, out5, w, wd5, nx, ny, vol, volf, &rc, st);
+        if (e != cudaSuccess) return (int)e;
+        k_scatter5<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(g, SCATTER_DZ, jac, ia, ja, out5, l, k, nullptr, vol, rc, 0);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+        count_launches(1);
+      }
+      count_launches(1);
     }
   return BC_OK;
 }

@@ -128,6 +128,174 @@ BC_HD auto flux_g(const A& a, int e) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Pieces of a face flux that the block-Jacobian assembly (facejac.cuh) also needs on their own.
+// face_flux() below is written in terms of them, so both paths evaluate the same expressions.
+// ---------------------------------------------------------------------------------------------
+
+// normals of the face-centred dual cell used by the viscous Green-Gauss gradients
+// (flux_visqueux_o4_{i,j}.F / flux_visqueux_o2_{i,j}.F): A = along the face normal direction, C = across
+struct DualNormals {
+  double volm1;
+  double nAp_x, nAm_x, nCp_x, nCm_x, nAp_y, nAm_y, nCp_y, nCm_y;
+};
+template <int DIR, class A>
+BC_HD DualNormals dual_normals(const A& a) {
+  constexpr int kA = DIR, kC = 1 - DIR;
+  DualNormals n;
+  n.volm1 = a.template VOLF<0, 0>(DIR);
+  n.nAp_x = 0.5 * (a.template NX<AT(1, 0)>(kA) + a.template NX<0, 0>(kA));
+  n.nAm_x = -0.5 * (a.template NX<AT(-1, 0)>(kA) + a.template NX<0, 0>(kA));
+  n.nCp_x = 0.5 * (a.template NX<AT(-1, 1)>(kC) + a.template NX<AT(0, 1)>(kC));
+  n.nCm_x = -0.5 * (a.template NX<AT(-1, 0)>(kC) + a.template NX<0, 0>(kC));
+  n.nAp_y = 0.5 * (a.template NY<AT(1, 0)>(kA) + a.template NY<0, 0>(kA));
+  n.nAm_y = -0.5 * (a.template NY<AT(-1, 0)>(kA) + a.template NY<0, 0>(kA));
+  n.nCp_y = 0.5 * (a.template NY<AT(-1, 1)>(kC) + a.template NY<AT(0, 1)>(kC));
+  n.nCm_y = -0.5 * (a.template NY<AT(-1, 0)>(kC) + a.template NY<0, 0>(kC));
+  return n;
+}
+
+// face values of the velocity / temperature gradients and of u, v, w, mu (compact o4, or o2 near a wall)
+template <class A1, class A2, class A3, class A4, class A5, class A6, class A7, class A8, class A9, class A10, class A11, class A12>
+struct ViscScalarsT {
+  A1 ux; A2 uy; A3 vx; A4 vy; A5 wx; A6 wy; A7 tx; A8 ty; A9 uu; A10 vv; A11 ww; A12 mmu;
+};
+template <class... Ts>
+BC_HD ViscScalarsT<Ts...> make_visc_scalars(Ts... v) {
+  return ViscScalarsT<Ts...>{v...};
+}
+template <int DIR, bool VISC_O2, class A>
+BC_HD auto visc_scalars(const A& a, const DualNormals& n) {
+  const double volm1 = n.volm1;
+  // Green-Gauss gradient of one scalar from its four dual-cell side values; the reference sums
+  // N,S,O,E which is (A+,A-,C+,C-) for i-faces and (C+,C-,A+,A-) for j-faces.
+  auto gg = [&](auto vAp, auto vAm, auto vCp, auto vCm, double nAp, double nAm, double nCp, double nCm) {
+    if constexpr (DIR == 0)
+      return (vAp * nAp + vAm * nAm + vCp * nCp + vCm * nCm) * volm1;
+    else
+      return (vCp * nCp + vCm * nCm + vAp * nAp + vAm * nAm) * volm1;
+  };
+  constexpr double TWENTYFOURTH = 1.0 / 24.0;
+  constexpr double TWELFTH = 0.25 / 3.0;
+  constexpr double ccross = TWELFTH * 0.0625;
+  (void)TWENTYFOURTH;
+  (void)ccross;
+#define BC_O4_ROW(Q, T_) (-a.template Q<AT(-2, T_)>() + 9.0 * a.template Q<AT(-1, T_)>() + 9.0 * a.template Q<AT(0, T_)>() - a.template Q<AT(1, T_)>())
+#define BC_O4_SIDES(Q)                                                                                              \
+  auto Q##_Ap = TWENTYFOURTH * (-a.template Q<AT(1, 0)>() + 26.0 * a.template Q<AT(0, 0)>() - a.template Q<AT(-1, 0)>());  \
+  auto Q##_Am = TWENTYFOURTH * (-a.template Q<AT(0, 0)>() + 26.0 * a.template Q<AT(-1, 0)>() - a.template Q<AT(-2, 0)>()); \
+  auto Q##_Cm = ccross * (-BC_O4_ROW(Q, -2) + 7.0 * BC_O4_ROW(Q, -1) + 7.0 * BC_O4_ROW(Q, 0) - BC_O4_ROW(Q, 1));       \
+  auto Q##_Cp = ccross * (-BC_O4_ROW(Q, -1) + 7.0 * BC_O4_ROW(Q, 0) + 7.0 * BC_O4_ROW(Q, 1) - BC_O4_ROW(Q, 2));
+#define BC_O2_SIDES(Q)                                                                                                          \
+  auto Q##_Ap = a.template Q<AT(0, 0)>();                                                                                       \
+  auto Q##_Am = a.template Q<AT(-1, 0)>();                                                                                      \
+  auto Q##_Cm = 0.25 * (a.template Q<AT(0, 0)>() + a.template Q<AT(0, -1)>() + a.template Q<AT(-1, 0)>() + a.template Q<AT(-1, -1)>()); \
+  auto Q##_Cp = 0.25 * (a.template Q<AT(0, 0)>() + a.template Q<AT(0, 1)>() + a.template Q<AT(-1, 0)>() + a.template Q<AT(-1, 1)>());
+#define BC_GRADS(Q, GX, GY)                                                \
+  auto GX = gg(Q##_Ap, Q##_Am, Q##_Cp, Q##_Cm, n.nAp_x, n.nAm_x, n.nCp_x, n.nCm_x); \
+  auto GY = gg(Q##_Ap, Q##_Am, Q##_Cp, Q##_Cm, n.nAp_y, n.nAm_y, n.nCp_y, n.nCm_y);
+#define BC_VS_RETURN return make_visc_scalars(ux, uy, vx, vy, wx, wy, tx, ty, uu, vv, ww, mmu);
+  if constexpr (!VISC_O2) {
+    BC_O4_SIDES(U) BC_GRADS(U, ux, uy)
+    BC_O4_SIDES(V) BC_GRADS(V, vx, vy)
+    BC_O4_SIDES(Wz) BC_GRADS(Wz, wx, wy)
+    BC_O4_SIDES(T) BC_GRADS(T, tx, ty)
+    auto uu = 0.0625 * BC_O4_ROW(U, 0);
+    auto vv = 0.0625 * BC_O4_ROW(V, 0);
+    auto ww = 0.0625 * BC_O4_ROW(Wz, 0);
+    auto mmu = 0.0625 * BC_O4_ROW(Mu, 0);
+    BC_VS_RETURN
+  } else {
+    BC_O2_SIDES(U) BC_GRADS(U, ux, uy)
+    BC_O2_SIDES(V) BC_GRADS(V, vx, vy)
+    BC_O2_SIDES(Wz) BC_GRADS(Wz, wx, wy)
+    BC_O2_SIDES(T) BC_GRADS(T, tx, ty)
+    auto uu = 0.5 * (a.template U<0, 0>() + a.template U<AT(-1, 0)>());
+    auto vv = 0.5 * (a.template V<0, 0>() + a.template V<AT(-1, 0)>());
+    auto ww = 0.5 * (a.template Wz<0, 0>() + a.template Wz<AT(-1, 0)>());
+    auto mmu = 0.5 * (a.template Mu<0, 0>() + a.template Mu<AT(-1, 0)>());
+    BC_VS_RETURN
+  }
+#undef BC_O4_ROW
+#undef BC_O4_SIDES
+#undef BC_O2_SIDES
+#undef BC_GRADS
+#undef BC_VS_RETURN
+}
+
+// viscous stresses and heat flux from the face scalars: f[1..4], g[1..4] (mass components unused)
+template <class VS>
+BC_HD auto visc_stress(const VS& s, const SchemeConsts& c) {
+  constexpr double TWOTHIRD = 2.0 / 3.0;
+  auto lambda = s.mmu * c.cpprandtl;
+  auto fvrou = TWOTHIRD * s.mmu * (2.0 * s.ux - s.vy);
+  auto fvrov = s.mmu * (s.uy + s.vx);
+  auto fvrow = s.mmu * s.wx;
+  auto fvroe = lambda * s.tx + s.uu * fvrou + s.vv * fvrov + s.ww * fvrow;
+  auto gvrou = s.mmu * (s.uy + s.vx);
+  auto gvrov = TWOTHIRD * s.mmu * (-s.ux + 2.0 * s.vy);
+  auto gvrow = s.mmu * s.wy;
+  auto gvroe = lambda * s.ty + s.uu * gvrou + s.vv * gvrov + s.ww * gvrow;
+  using D = decltype((fvroe + gvroe).d);
+  struct R {
+    Var<D> f[5], g[5];
+  };
+  R r;
+  r.f[1] = promote<D>(fvrou); r.f[2] = promote<D>(fvrov); r.f[3] = promote<D>(fvrow); r.f[4] = promote<D>(fvroe);
+  r.g[1] = promote<D>(gvrou); r.g[2] = promote<D>(gvrov); r.g[3] = promote<D>(gvrow); r.g[4] = promote<D>(gvroe);
+  return r;
+}
+
+// Roe-averaged spectral radius of a face (spectralradius_{i,j}.F); r = right (face cell), l = left
+template <class R0, class R1, class R2, class TR, class L0, class L1, class L2, class TL>
+BC_HD auto spectral_radius(Var<R0> rhomr, Var<R1> w1r, Var<R2> w2r, Var<TR> tr, Var<L0> rhoml, Var<L1> w1l, Var<L2> w2l, Var<TL> tl,
+                           double nxf, double nyf, const SchemeConsts& c) {
+  auto ur = w1r / rhomr;
+  auto vr = w2r / rhomr;
+  auto c2r = c.gam * c.rgaz * tr;
+  auto ul = w1l / rhoml;
+  auto vl = w2l / rhoml;
+  auto c2l = c.gam * c.rgaz * tl;
+  auto r = sqrt(rhomr / rhoml);
+  auto rr = 1.0 / (1.0 + r);
+  auto omrr = 1.0 - rr;
+  auto u = ul * rr + ur * omrr;
+  auto v = vl * rr + vr * omrr;
+  auto c2x = c2l * rr + c2r * omrr;
+  const double nx2 = nxf * nxf + nyf * nyf;
+  auto ab = fabs(nxf * u + nyf * v);
+  auto sq = sqrt(c2x * nx2);
+  return ab + sq;
+}
+
+// Jameson pressure sensor x Ducros x dilatation switch (ducrosfordnc_{i,j}.F): the factor `coef` of eps2.
+// gr0 / gr1: velocity gradients (u0,u1,v0,v1) of the face cell and of its along-neighbour -1.
+template <class P2, class P1, class P0, class PP, class G0, class G1, class C0, class C1>
+BC_HD auto sensor_coef(Var<P2> p_m2, Var<P1> p_m1, Var<P0> p_0, Var<PP> p_p1, const G0& gr0, const G1& gr1, double vol0, double vol1,
+                       Var<C0> c2r, Var<C1> c2l, double nx2) {
+  auto k_sensor1 = fabs(p_m1 - 2.0 * p_0 + p_p1) / fabs(p_m1 + 2.0 * p_0 + p_p1);
+  auto k_sensor2 = fabs(p_m2 - 2.0 * p_m1 + p_0) / fabs(p_m2 + 2.0 * p_m1 + p_0);
+  auto sens_cell = [&](auto gr, double vol, auto c2, auto& ducros, auto& dxm) {
+    auto divu = gr.u0 + gr.v1;
+    auto divu2 = divu * divu;
+    auto vort2 = (gr.v0 - gr.u1) * (gr.v0 - gr.u1);
+    ducros = divu2 / (divu2 + vort2 + 1e-15);
+    dxm = 0.5 * (1.0 - tanh(2.5 + 10.0 * vol / (sqrt(c2 * nx2) + 1e-15) * divu));
+  };
+  using GD0 = decltype(gr0.u0.d);
+  using GD1 = decltype(gr1.u0.d);
+  using SD0 = decltype((gr0.u0 * c2r).d);
+  using SD1 = decltype((gr1.u0 * c2l).d);
+  Var<GD0> ducros1;
+  Var<SD0> dxm1;
+  Var<GD1> ducros2;
+  Var<SD1> dxm2;
+  sens_cell(gr0, vol0, c2r, ducros1, dxm1);
+  sens_cell(gr1, vol1, c2l, ducros2, dxm2);
+  return fmax(k_sensor1, k_sensor2) * fmax(ducros1, ducros2) * fmax(dxm1, dxm2);
+}
+
 enum FaceMode { FACE_MAIN = 0, FACE_NEAR5 = 1, FACE_NEAR3 = 2, FACE_WALL = 3 };
 
 // ---------------------------------------------------------------------------------------------
@@ -172,158 +340,23 @@ BC_HD void face_flux(const A& a, const SchemeConsts& c, Var<RD> (&hn)[5]) {
     constexpr double c1 = 37.0 * denom, c2 = -8.0 * denom, c3 = denom;
     constexpr double d1 = 10.0 * denom, d2 = 5.0 * denom, d3 = denom;
 
-    // ---- viscous face gradients ----------------------------------------------------------------
-    const double volm1 = a.template VOLF<0, 0>(DIR);
-    constexpr int kA = DIR, kC = 1 - DIR;
-    const double nAp_x = 0.5 * (a.template NX<AT(1, 0)>(kA) + a.template NX<0, 0>(kA));
-    const double nAm_x = -0.5 * (a.template NX<AT(-1, 0)>(kA) + a.template NX<0, 0>(kA));
-    const double nCp_x = 0.5 * (a.template NX<AT(-1, 1)>(kC) + a.template NX<AT(0, 1)>(kC));
-    const double nCm_x = -0.5 * (a.template NX<AT(-1, 0)>(kC) + a.template NX<0, 0>(kC));
-    const double nAp_y = 0.5 * (a.template NY<AT(1, 0)>(kA) + a.template NY<0, 0>(kA));
-    const double nAm_y = -0.5 * (a.template NY<AT(-1, 0)>(kA) + a.template NY<0, 0>(kA));
-    const double nCp_y = 0.5 * (a.template NY<AT(-1, 1)>(kC) + a.template NY<AT(0, 1)>(kC));
-    const double nCm_y = -0.5 * (a.template NY<AT(-1, 0)>(kC) + a.template NY<0, 0>(kC));
-
-    // Green-Gauss gradient of one scalar from its four dual-cell side values; the reference sums
-    // N,S,O,E which is (A+,A-,C+,C-) for i-faces and (C+,C-,A+,A-) for j-faces.
-    auto gg = [&](auto vAp, auto vAm, auto vCp, auto vCm, double nAp, double nAm, double nCp, double nCm) {
-      if constexpr (DIR == 0)
-        return (vAp * nAp + vAm * nAm + vCp * nCp + vCm * nCm) * volm1;
-      else
-        return (vCp * nCp + vCm * nCm + vAp * nAp + vAm * nAm) * volm1;
-    };
-
-#define BC_O4_ROW(Q, T_) (-a.template Q<AT(-2, T_)>() + 9.0 * a.template Q<AT(-1, T_)>() + 9.0 * a.template Q<AT(0, T_)>() - a.template Q<AT(1, T_)>())
-#define BC_O4_SIDES(Q)                                                                                              \
-  auto Q##_Ap = TWENTYFOURTH * (-a.template Q<AT(1, 0)>() + 26.0 * a.template Q<AT(0, 0)>() - a.template Q<AT(-1, 0)>());  \
-  auto Q##_Am = TWENTYFOURTH * (-a.template Q<AT(0, 0)>() + 26.0 * a.template Q<AT(-1, 0)>() - a.template Q<AT(-2, 0)>()); \
-  auto Q##_Cm = ccross * (-BC_O4_ROW(Q, -2) + 7.0 * BC_O4_ROW(Q, -1) + 7.0 * BC_O4_ROW(Q, 0) - BC_O4_ROW(Q, 1));       \
-  auto Q##_Cp = ccross * (-BC_O4_ROW(Q, -1) + 7.0 * BC_O4_ROW(Q, 0) + 7.0 * BC_O4_ROW(Q, 1) - BC_O4_ROW(Q, 2));
-#define BC_O2_SIDES(Q)                                                                                                          \
-  auto Q##_Ap = a.template Q<AT(0, 0)>();                                                                                       \
-  auto Q##_Am = a.template Q<AT(-1, 0)>();                                                                                      \
-  auto Q##_Cm = 0.25 * (a.template Q<AT(0, 0)>() + a.template Q<AT(0, -1)>() + a.template Q<AT(-1, 0)>() + a.template Q<AT(-1, -1)>()); \
-  auto Q##_Cp = 0.25 * (a.template Q<AT(0, 0)>() + a.template Q<AT(0, 1)>() + a.template Q<AT(-1, 0)>() + a.template Q<AT(-1, 1)>());
-#define BC_GRADS(Q, GX, GY)                                                \
-  auto GX = gg(Q##_Ap, Q##_Am, Q##_Cp, Q##_Cm, nAp_x, nAm_x, nCp_x, nCm_x); \
-  auto GY = gg(Q##_Ap, Q##_Am, Q##_Cp, Q##_Cm, nAp_y, nAm_y, nCp_y, nCm_y);
-
-    constexpr double TWENTYFOURTH = 1.0 / 24.0;
-    constexpr double TWELFTH = 0.25 / 3.0;
-    constexpr double ccross = TWELFTH * 0.0625;
-    constexpr double TWOTHIRD = 2.0 / 3.0;
-    (void)TWENTYFOURTH;
-    (void)ccross;
-
-    auto visc = [&]() {
-      if constexpr (!VISC_O2) {
-        BC_O4_SIDES(U) BC_GRADS(U, ux, uy)
-        BC_O4_SIDES(V) BC_GRADS(V, vx, vy)
-        BC_O4_SIDES(Wz) BC_GRADS(Wz, wx, wy)
-        BC_O4_SIDES(T) BC_GRADS(T, tx, ty)
-        auto uu = 0.0625 * BC_O4_ROW(U, 0);
-        auto vv = 0.0625 * BC_O4_ROW(V, 0);
-        auto ww = 0.0625 * BC_O4_ROW(Wz, 0);
-        auto mmu = 0.0625 * BC_O4_ROW(Mu, 0);
-        auto lambda = mmu * c.cpprandtl;
-        auto fvrou = TWOTHIRD * mmu * (2.0 * ux - vy);
-        auto fvrov = mmu * (uy + vx);
-        auto fvrow = mmu * wx;
-        auto fvroe = lambda * tx + uu * fvrou + vv * fvrov + ww * fvrow;
-        auto gvrou = mmu * (uy + vx);
-        auto gvrov = TWOTHIRD * mmu * (-ux + 2.0 * vy);
-        auto gvrow = mmu * wy;
-        auto gvroe = lambda * ty + uu * gvrou + vv * gvrov + ww * gvrow;
-        using D = decltype(fvroe.d);
-        struct R {
-          Var<D> f[5], g[5];
-        };
-        R r;
-        r.f[1] = promote<D>(fvrou); r.f[2] = promote<D>(fvrov); r.f[3] = promote<D>(fvrow); r.f[4] = fvroe;
-        r.g[1] = promote<D>(gvrou); r.g[2] = promote<D>(gvrov); r.g[3] = promote<D>(gvrow); r.g[4] = promote<D>(gvroe);
-        return r;
-      } else {
-        BC_O2_SIDES(U) BC_GRADS(U, ux, uy)
-        BC_O2_SIDES(V) BC_GRADS(V, vx, vy)
-        BC_O2_SIDES(Wz) BC_GRADS(Wz, wx, wy)
-        BC_O2_SIDES(T) BC_GRADS(T, tx, ty)
-        auto uu = 0.5 * (a.template U<0, 0>() + a.template U<AT(-1, 0)>());
-        auto vv = 0.5 * (a.template V<0, 0>() + a.template V<AT(-1, 0)>());
-        auto ww = 0.5 * (a.template Wz<0, 0>() + a.template Wz<AT(-1, 0)>());
-        auto mmu = 0.5 * (a.template Mu<0, 0>() + a.template Mu<AT(-1, 0)>());
-        auto lambda = 0.5 * (a.template Mu<0, 0>() + a.template Mu<AT(-1, 0)>()) * c.cpprandtl;
-        auto fvrou = TWOTHIRD * mmu * (2.0 * ux - vy);
-        auto fvrov = mmu * (uy + vx);
-        auto fvrow = mmu * wx;
-        auto fvroe = lambda * tx + uu * fvrou + vv * fvrov + ww * fvrow;
-        auto gvrou = mmu * (uy + vx);
-        auto gvrov = TWOTHIRD * mmu * (-ux + 2.0 * vy);
-        auto gvrow = mmu * wy;
-        auto gvroe = lambda * ty + uu * gvrou + vv * gvrov + ww * gvrow;
-        using D = decltype(fvroe.d);
-        struct R {
-          Var<D> f[5], g[5];
-        };
-        R r;
-        r.f[1] = promote<D>(fvrou); r.f[2] = promote<D>(fvrov); r.f[3] = promote<D>(fvrow); r.f[4] = fvroe;
-        r.g[1] = promote<D>(gvrou); r.g[2] = promote<D>(gvrov); r.g[3] = promote<D>(gvrow); r.g[4] = promote<D>(gvroe);
-        return r;
-      }
-    };
-    const auto vs = visc();
-#undef BC_O4_ROW
-#undef BC_O4_SIDES
-#undef BC_O2_SIDES
-#undef BC_GRADS
+    // ---- viscous face gradients, stresses --------------------------------------------------------
+    const DualNormals dn = dual_normals<DIR>(a);
+    const auto vsc = visc_scalars<DIR, VISC_O2>(a, dn);
+    const auto vs = visc_stress(vsc, c);
 
     // ---- scalar dissipation: Roe spectral radius (spectralradius_{i,j}.F) -------------------------
-    auto rhomr = a.template W<0, 0>(0);
-    auto ur = a.template W<0, 0>(1) / rhomr;
-    auto vr = a.template W<0, 0>(2) / rhomr;
-    auto c2r = c.gam * c.rgaz * a.template T<0, 0>();
-    auto rhoml = a.template W<AT(-1, 0)>(0);
-    auto ul = a.template W<AT(-1, 0)>(1) / rhoml;
-    auto vl = a.template W<AT(-1, 0)>(2) / rhoml;
-    auto c2l = c.gam * c.rgaz * a.template T<AT(-1, 0)>();
-    auto r = sqrt(rhomr / rhoml);
-    auto rr = 1.0 / (1.0 + r);
-    auto omrr = 1.0 - rr;
-    auto u = ul * rr + ur * omrr;
-    auto v = vl * rr + vr * omrr;
-    auto c2x = c2l * rr + c2r * omrr;
+    auto rspec = spectral_radius(a.template W<0, 0>(0), a.template W<0, 0>(1), a.template W<0, 0>(2), a.template T<0, 0>(),
+                                 a.template W<AT(-1, 0)>(0), a.template W<AT(-1, 0)>(1), a.template W<AT(-1, 0)>(2),
+                                 a.template T<AT(-1, 0)>(), nxf, nyf, c);
     const double nx2 = nxf * nxf + nyf * nyf;
-    auto ab = fabs(nxf * u + nyf * v);
-    auto sq = sqrt(c2x * nx2);
-    auto rspec = ab + sq;
 
     // ---- Jameson / Ducros / dilatation sensor (ducrosfordnc_{i,j}.F) ------------------------------
-    auto p_m2 = a.template P<AT(-2, 0)>();
-    auto p_m1 = a.template P<AT(-1, 0)>();
-    auto p_0 = a.template P<AT(0, 0)>();
-    auto p_p1 = a.template P<AT(1, 0)>();
-    auto k_sensor1 = fabs(p_m1 - 2.0 * p_0 + p_p1) / fabs(p_m1 + 2.0 * p_0 + p_p1);
-    auto k_sensor2 = fabs(p_m2 - 2.0 * p_m1 + p_0) / fabs(p_m2 + 2.0 * p_m1 + p_0);
-
-    auto sens_cell = [&](auto gr, double vol, auto c2, auto& ducros, auto& dxm) {
-      auto divu = gr.u0 + gr.v1;
-      auto divu2 = divu * divu;
-      auto vort2 = (gr.v0 - gr.u1) * (gr.v0 - gr.u1);
-      ducros = divu2 / (divu2 + vort2 + 1e-15);
-      dxm = 0.5 * (1.0 - tanh(2.5 + 10.0 * vol / (sqrt(c2 * nx2) + 1e-15) * divu));
-    };
-    const auto gr0 = a.template GR<0, 0>();
-    const auto gr1 = a.template GR<AT(-1, 0)>();
-    using GD0 = decltype(gr0.u0.d);
-    using GD1 = decltype(gr1.u0.d);
-    using SD0 = decltype((gr0.u0 * c2r).d);
-    using SD1 = decltype((gr1.u0 * c2l).d);
-    Var<GD0> ducros1;
-    Var<SD0> dxm1;
-    Var<GD1> ducros2;
-    Var<SD1> dxm2;
-    sens_cell(gr0, a.template VOL<0, 0>(), c2r, ducros1, dxm1);
-    sens_cell(gr1, a.template VOL<AT(-1, 0)>(), c2l, ducros2, dxm2);
-    auto coef = fmax(k_sensor1, k_sensor2) * fmax(ducros1, ducros2) * fmax(dxm1, dxm2);
+    auto c2r = c.gam * c.rgaz * a.template T<0, 0>();
+    auto c2l = c.gam * c.rgaz * a.template T<AT(-1, 0)>();
+    auto coef = sensor_coef(a.template P<AT(-2, 0)>(), a.template P<AT(-1, 0)>(), a.template P<AT(0, 0)>(), a.template P<AT(1, 0)>(),
+                            a.template GR<0, 0>(), a.template GR<AT(-1, 0)>(), a.template VOL<0, 0>(), a.template VOL<AT(-1, 0)>(),
+                            c2r, c2l, nx2);
     auto eps2 = c.k2 * coef;
     auto eps4 = fmax(0.0, c.k4 - eps2 * 12.0);
 

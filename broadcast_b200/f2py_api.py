@@ -257,4 +257,33 @@ def build(backend):
         computejacobianfromjv_relaxed_withjn=_relaxed("computejacobianfromjv_relaxed_withjn"),
         computejacobianfromjv_withjn=computejacobianfromjv_withjn, computejacobianfromdz=computejacobianfromdz)
 
-    return dict(f_sch=f_sch, f_lin=f_lin, f_bnd=f_bnd, f_geom=f_geom, f_norm=f_norm, f_misc=f_misc)
+    # ------------------------------------------------------------------ f_dz (spanwise operator rows)
+    def _dz(name):
+        def f(dz, w, wd, x0, y0, nx, ny, xc, yc, vol, volf, gh, cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth,
+              im=None, jm=None):
+            gh = int(gh)
+            im = int(im) if im is not None else w.shape[0] - 2 * gh
+            jm = int(jm) if jm is not None else w.shape[1] - 2 * gh
+            _check_cells(_state(dz, "dz_out"), im, jm, gh, "dz_out")
+            w, wd = _in(w), _in(wd)
+            _check_cells(w, im, jm, gh, "w")
+            _check_cells(wd, im, jm, gh, "wd")
+            B(name, dz, w, wd, _in(x0), _in(y0), _in(nx), _in(ny), _in(xc), _in(yc), _in(vol), _in(volf), gh, cp, cv, prandtl,
+              gam, rgaz, cs, muref, tref, s_suth, im, jm)
+        f.__name__ = name
+        return f
+
+    f_dz = types.SimpleNamespace(coeffs_5p_dz=_dz("coeffs_5p_dz"), coeffs_5p_dz2=_dz("coeffs_5p_dz2"))
+
+    # ------------------------------------------------------------------ f_init (boundary tables from the initial field)
+    def set_bndbl_2d(w, field, wbd, im, jm=None, gh=None):
+        w = _in(w)
+        _state(field, "field")
+        _state(wbd, "wbd", ndim=2)
+        gh = int(gh) if gh is not None else field.shape[1]
+        jm = int(jm) if jm is not None else field.shape[0]
+        B("set_bndbl_2d", w, field, wbd, int(im), jm, gh)
+
+    f_init = types.SimpleNamespace(set_bndbl_2d=set_bndbl_2d)
+
+    return dict(f_sch=f_sch, f_lin=f_lin, f_bnd=f_bnd, f_geom=f_geom, f_norm=f_norm, f_misc=f_misc, f_dz=f_dz, f_init=f_init)

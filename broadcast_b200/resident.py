@@ -220,6 +220,28 @@ def jacobian_coo(blk: "Block", coefdiag=None, kind=None, rect=None, out=None, co
     return jac, ia, ja
 
 
+def dz_coo(blk: "Block", which=(1, 2)):
+    """COO lists of the spanwise operators Dz (which 1) and Dz2 (which 2) by the colour loop of
+    BROADCAST_npz.py:1231-1246 on the device.  Returns {1: (jac, ia, ja), 2: (jac, ia, ja)}."""
+    im, jm, gh = blk.im, blk.jm, blk.gh
+    s = 2 * gh + 1
+    nb = 25 * s * s * im * jm
+    if nb >= 2 ** 31:
+        raise _lib.BroadcastB200Error("the reference COO layout overflows 32-bit slots at this size")
+    out = {}
+    for wh in (1, 2):
+        if wh in which:
+            out[wh] = (torch.zeros(nb, dtype=torch.float64, device=blk.device), torch.zeros(nb, dtype=torch.int32, device=blk.device),
+                       torch.zeros(nb, dtype=torch.int32, device=blk.device))
+    descs, n = _bc_descs(blk)
+    a = [(_p(t) for t in out[wh]) if wh in out else (ctypes.c_void_p(None),) * 3 for wh in (1, 2)]
+    args = [x for trip in a for x in trip]
+    rc = blk.lib.bcd_dz_coo(*args, _p(blk.w), _p(blk.nx), _p(blk.ny), _p(blk.vol), _p(blk.volf), gh, *blk._phys[:9], im, jm, descs, n,
+                            blk._stream())
+    _lib.check(rc, "bcd_dz_coo")
+    return out
+
+
 def remove_zero_jac(jac, ia, ja, thresh=2e-16):
     """BROADCAST_npz.py:129-135 on the device"""
     keep = jac.abs() > thresh
@@ -277,7 +299,7 @@ class HybridJacobian:
         return sp.csr_matrix((v.cpu().numpy(), (r.cpu().numpy(), c.cpu().numpy())), shape=(n, n))
 
 
-def jacobian_hybrid(blk: "Block", coefdiag=None, kind=None, blocks=None):
+def jacobian_hybrid(blk: "Block", coefdiag=None, kind=None, blocks=None, interior="faces"):
     """Jacobian of the current state: interior rows by the direct block kernels (one launch per
     structural column offset, no colouring), boundary strips (gh rows/columns along each side) by the
     reference colour loop restricted to those rows."""
@@ -293,7 +315,8 @@ def jacobian_hybrid(blk: "Block", coefdiag=None, kind=None, blocks=None):
     region = (gh + 1, im - gh, gh + 1, jm - gh)
     if blocks is None:
         blocks = torch.zeros((29, 5, 5, jm, im), dtype=torch.float64, device=blk.device)
-    rc = blk.lib.bcd_jacobian_interior(_p(blocks), _p(blk.w), _p(blk.nx), _p(blk.ny), _p(blk.vol), _p(blk.volf), gh, *blk._phys, im, jm,
+    fn = blk.lib.bcd_jacobian_interior if interior == "faces" else blk.lib.bcd_jacobian_interior_ad
+    rc = fn(_p(blocks), _p(blk.w), _p(blk.nx), _p(blk.ny), _p(blk.vol), _p(blk.volf), gh, *blk._phys, im, jm,
                                        _p(cd if relaxed else None), ctypes.c_void_p(None), blk._stream())
     _lib.check(rc, "bcd_jacobian_interior")
     rects = [(1, im, 1, gh), (1, im, jm - gh + 1, jm), (1, gh, gh + 1, jm - gh), (im - gh + 1, im, gh + 1, jm - gh)]

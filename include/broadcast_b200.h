@@ -112,6 +112,21 @@ int bc_computejacobianfromjv_withjn(double* jac, int32_t* ia, int32_t* ja, const
 int bc_computejacobianfromdz(double* jac, int32_t* ia, int32_t* ja, const double* dz, int m, int l, int k, int gh,
                              int im, int jm, int64_t nbentry);
 
+/* ---- spanwise operator rows: srcfv/dz/coeffs_5p_dz.F90:10-174, srcfv/dz/coeffs_5p_dz2.F90 (f_dz.coeffs_5p_dz,
+ *      f_dz.coeffs_5p_dz2; BROADCAST_npz.py:1242-1243).  dz_out interior cells are written, its ghosts untouched. */
+int bc_coeffs_5p_dz(double* dz_out, const double* w, const double* wd, const double* x0, const double* y0, const double* nx,
+                    const double* ny, const double* xc, const double* yc, const double* vol, const double* volf, int gh, double cp,
+                    double cv, double prandtl, double gam, double rgaz, double cs, double muref, double tref, double s_suth, int im,
+                    int jm);
+int bc_coeffs_5p_dz2(double* dz_out, const double* w, const double* wd, const double* x0, const double* y0, const double* nx,
+                     const double* ny, const double* xc, const double* yc, const double* vol, const double* volf, int gh, double cp,
+                     double cv, double prandtl, double gam, double rgaz, double cs, double muref, double tref, double s_suth, int im,
+                     int jm);
+
+/* ---- boundary tables from the initial field: set_bnd.f90:2-24 (f_init.set_bndbl_2d).  A host-side copy
+ *      (field(j,depth,:) = w(1-depth,j,:), wbd(i,:) = w(i-gh,jm,:)); set-up, not on the device path. */
+int bc_set_bndbl_2d(const double* w, double* field, double* wbd, int im, int jm, int gh);
+
 /* ---- norms: srcfv/norm.F90:2-77 (f_norm.compute_norml2 / compute_norml2inf).  Reduction order on the
  *      device is a tree (the Fortran sums j-outer, i-inner sequentially). */
 int bc_compute_norml2(double* norm, double* nmoy, const double* rhs, int im, int jm, int gh);
@@ -146,6 +161,10 @@ int bcd_testvector(double* wd, int ndir, int m, int l, int k, int gh, int im, in
 /* kind: 0 jv, 1 jv_relaxed, 2 dz, 3 jv_relaxed_withjn, 4 jv_withjn, 5 jv_dbyvol, 6 jv_relaxed_dbyvol */
 int bcd_scatter(int kind, double* seg_jac, int32_t* seg_ia, int32_t* seg_ja, const double* resd, int m, int l, int k,
                 int gh, int im, int jm, const double* coefdiag, const double* vol, void* stream);
+/* spanwise operator rows on the device: which = 1 (d/dz) or 2 (d2/dz2); ndir = 1 or 5 tangent directions in wd / dz_out */
+int bcd_dz(double* dz_out, const double* w, const double* wd, int ndir, int which, const double* nx, const double* ny,
+           const double* vol, const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
+           double muref, double tref, double s_suth, int im, int jm, const int32_t* rect, void* stream);
 /* out10 (device): sum r^2 per equation [5], sum r^10 per equation [5] */
 int bcd_norm_sums(double* out10, const double* rhs, int im, int jm, int gh, void* stream);
 
@@ -184,6 +203,13 @@ int bcd_jacobian_coo(double* jac, int32_t* ia, int32_t* ja, double* w, const dou
                      double rgaz, double cs, double muref, double tref, double s_suth, double k2, double k4, int im,
                      int jm, int wall, const bc_desc_t* bcs, int nbcs, int scatter_kind, const double* coefdiag,
                      const int32_t* rect, int compact, void* stream);
+/* Colour loop of the spanwise operators (BROADCAST_npz.py:1231-1246) on the device: COO triplets of Dz (jac1, ia1, ja1)
+ * and Dz2 (jac2, ia2, ja2) in the reference's slot order, scatter rule computejacobianfromdz (misc/ComputeJacobian.f90:708-779).
+ * Either triplet may be null. */
+int bcd_dz_coo(double* jac1, int32_t* ia1, int32_t* ja1, double* jac2, int32_t* ia2, int32_t* ja2, double* w, const double* nx,
+               const double* ny, const double* vol, const double* volf, int gh, double cp, double cv, double prandtl, double gam,
+               double rgaz, double cs, double muref, double tref, double s_suth, int im, int jm, const bc_desc_t* bcs, int nbcs,
+               void* stream);
 /* Direct block-Jacobian of the regular interior rows (rows whose stencil touches neither ghost cells nor
  * the wall rows: gh+1 <= i <= im-gh, gh+1 <= j <= jm-gh) into the fixed 29-slot pattern, without colouring:
  * values[slot][e][m][cell], cell = (i-1) + (j-1)*im, slot s <-> column-cell offset given by
@@ -195,6 +221,12 @@ int bcd_jacobian_interior(double* values, const double* w, const double* nx, con
                           const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz,
                           double cs, double muref, double tref, double s_suth, double k2, double k4, int im, int jm,
                           const double* coefdiag, const int32_t* rect, void* stream);
+/* Same result by the direct forward-AD kernels (one launch per column offset, every other cell passive at
+ * compile time): the slower cross-check of the face-linearisation path used by bcd_jacobian_interior. */
+int bcd_jacobian_interior_ad(double* values, const double* w, const double* nx, const double* ny, const double* vol,
+                             const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz,
+                             double cs, double muref, double tref, double s_suth, double k2, double k4, int im, int jm,
+                             const double* coefdiag, const int32_t* rect, void* stream);
 /* primal boundary fill of a whole list */
 int bcd_apply_bcs(double* w, const double* nx, const double* ny, double gam, int gh, int im, int jm,
                   const bc_desc_t* bcs, int nbcs, void* stream);

@@ -49,10 +49,10 @@ FILES = [
         "computejacobianfromjv_relaxed_dbyvol", "computejacobianfromjv_dbyvol", "computejacobianfromdz",
         "computejacobianfromjv_relaxed_withjn", "computejacobianfromjv_withjn",
         "computejacobianfromjv_withjn_dbyvol", "computejacobianfromjv_relaxed_withjnandcheck"]),
-    ("srcfv/dz/function_5p_dz_d.f90", None),
-    ("srcfv/dz/function_5p_dz2_d.f90", None),
-    ("srcfv/prepro_dz/coeffs_5p_dz.f90", ["coeffs_5p_dz"]),
-    ("srcfv/prepro_dz/coeffs_5p_dz2.f90", ["coeffs_5p_dz2"]),
+    # the shipped srcfv/prepro_dz/*.f90 are stale fpp outputs (array bounds differ from srcfv/dz/function_5p_dz*_d.f90):
+    # expand the authoritative srcfv/dz/*.F90 here exactly as srcfv/compile_dz.py does (fpp -I srcfv -P)
+    ("cpp:srcfv/dz/coeffs_5p_dz.F90", None),
+    ("cpp:srcfv/dz/coeffs_5p_dz2.F90", None),
     ("srcfv/norm.F90", None),
     ("set_bnd.f90", None),
     ("initialisation.f90", None),
@@ -61,6 +61,26 @@ FILES = [
 
 def have_reference() -> bool:
     return os.path.isdir(os.path.join(REF, "srcfv", "prepro"))
+
+
+def expand_includes(path: str, incdir: str, depth: int = 0) -> str:
+    """what `fpp -I incdir -P` does to these files: textual #include expansion (they use no other directive)"""
+    import re
+    out = []
+    with open(path, "r", errors="replace") as fh:
+        for line in fh:
+            m = re.match(r'\s*#\s*include\s+"([^"]+)"', line)
+            if m:
+                if depth > 8:
+                    raise RuntimeError("include depth")
+                out.append(expand_includes(os.path.join(incdir, m.group(1)), incdir, depth + 1))
+                if not out[-1].endswith("\n"):
+                    out.append("\n")
+            elif re.match(r"\s*#", line):
+                raise RuntimeError(f"unsupported preprocessor line in {path}: {line!r}")
+            else:
+                out.append(line)
+    return "".join(out)
 
 
 def build(verbose: bool = True) -> bool:
@@ -72,13 +92,24 @@ def build(verbose: bool = True) -> bool:
     import f90_to_c
 
     os.makedirs(OUT, exist_ok=True)
-    files = [(os.path.join(REF, p), subs) for p, subs in FILES]
+    files = []
+    for p, subs in FILES:
+        if p.startswith("cpp:"):
+            rel = p[4:]
+            text = expand_includes(os.path.join(REF, rel), os.path.join(REF, "srcfv"))
+            os.makedirs(os.path.join(OUT, "pp"), exist_ok=True)
+            pp = os.path.join(OUT, "pp", os.path.splitext(os.path.basename(rel))[0] + ".f90")
+            with open(pp, "w") as fh:
+                fh.write(text)
+            files.append((pp, subs))
+        else:
+            files.append((os.path.join(REF, p), subs))
     ctext, manifest = f90_to_c.translate(files)
     cpath = os.path.join(OUT, "broadcast_ref.c")
     with open(cpath, "w") as fh:
         fh.write(ctext)
     for m in manifest:
-        m["src"] = os.path.relpath(m["src"], REF)
+        m["src"] = os.path.relpath(m["src"], OUT if m["src"].startswith(OUT) else REF)
     with open(os.path.join(OUT, "manifest.json"), "w") as fh:
         json.dump(manifest, fh, indent=1)
     common = ["gcc", "-std=gnu11", "-shared", "-fPIC", "-fno-fast-math", "-w", cpath, "-lm"]

@@ -46,6 +46,17 @@ def test_ref_reproduces_golden(ref, path):
     jac, ia, ja = H.jacobian_sequence(ref, c, w, [tuple(x) for x in g["colours"]], np.asfortranarray(g["coefdiag"]))
     assert np.array_equal(ia, g["coo_ia"]) and np.array_equal(ja, g["coo_ja"])
     assert np.abs(jac - g["coo_jac"]).max() < 1e-13 * np.abs(g["coo_jac"]).max()
+    # spanwise operator rows of one colour (srcfv/dz/coeffs_5p_dz.F90, coeffs_5p_dz2.F90)
+    m, l, k = (int(x) for x in g["dz_colour"])
+    wd = c.zeros_state()
+    ref["f_misc"].testvector(wd, m, l, k, c.gh, c.im, c.jm)
+    a = c.scheme_args()
+    dzargs = a[:18] + a[20:]
+    for name, key in (("coeffs_5p_dz", "dz"), ("coeffs_5p_dz2", "dz2")):
+        z = c.zeros_state()
+        getattr(ref["f_dz"], name)(z, w, wd, *dzargs)
+        assert np.abs(g[key]).max() > 0
+        assert np.all(H.rel_err(z, g[key]) < 1e-13), name
 
 
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])

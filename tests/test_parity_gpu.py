@@ -195,3 +195,92 @@ def test_hybrid_jacobian_matches_reference_loop(gpu, ref, kind, im, jm):
     if odd.any():
         vals = np.abs(np.asarray((A + B)[X.row[odd], X.col[odd]])).ravel()
         assert vals.max() < 1e-15, (odd.sum(), vals.max())
+
+
+def _dz_args(c):
+    a = c.scheme_args()
+    return a[:18] + a[20:]   # coeffs_5p_dz takes no k2, k4 (BROADCAST_npz.py:1242-1243)
+
+
+@pytest.mark.parametrize("kind,im,jm", CASES)
+def test_dz_operator_rows(gpu, ref, kind, im, jm):
+    """f_dz.coeffs_5p_dz / coeffs_5p_dz2 on a seeded random direction and on a colour seed, vs the reference"""
+    a = H.make_case(kind, im, jm, gpu, with_w=True)
+    b = H.make_case(kind, im, jm, ref, with_w=True)
+    wa, _ = H.residual_sequence(gpu, a)
+    wb, _ = H.residual_sequence(ref, b)
+    rng = np.random.default_rng(8)
+    wd = np.asfortranarray(rng.standard_normal(wa.shape))
+    wds = a.zeros_state()
+    gpu["f_misc"].testvector(wds, 2, 3, 1, a.gh, im, jm)
+    for d in (wd, wds):
+        for name in ("coeffs_5p_dz", "coeffs_5p_dz2"):
+            za = np.asfortranarray(np.full(wa.shape, 7.0))
+            zb = za.copy(order="F")
+            getattr(gpu["f_dz"], name)(za, wa, d, *_dz_args(a))
+            getattr(ref["f_dz"], name)(zb, wb, d, *_dz_args(b))
+            assert np.all(za[:a.gh] == 7.0) and np.all(za[:, :a.gh] == 7.0)   # ghosts untouched
+            assert np.all(H.rel_err(za, zb) < TOL), (name, H.rel_err(za, zb))
+
+
+def test_dz_colour_loop_device(gpu, ref):
+    """device colour loop of the spanwise operators vs the reference loop of BROADCAST_npz.py:1231-1246"""
+    from broadcast_b200.resident import Block, dz_coo
+    im, jm = 30, 22
+    a = H.make_case("bl", im, jm, gpu, with_w=True)
+    b = H.make_case("bl", im, jm, ref, with_w=True)
+    blk = Block(a)
+    blk.apply_bcs()
+    out = dz_coo(blk)
+    wb, _ = H.residual_sequence(ref, b)
+    gh = b.gh
+    s = 2 * gh + 1
+    nb = 25 * s * s * im * jm
+    J1, I1, K1 = np.zeros(nb), np.zeros(nb, np.int32), np.zeros(nb, np.int32)
+    J2, I2, K2 = np.zeros(nb), np.zeros(nb, np.int32), np.zeros(nb, np.int32)
+    wd = b.zeros_state()
+    dz, dz2 = b.zeros_state(), b.zeros_state()
+    for m in range(5):
+        for l in range(s):
+            for k in range(s):
+                wd *= 0.0
+                ref["f_misc"].testvector(wd, m, l, k, gh, im, jm)
+                ww = wb.copy(order="F")
+                cases.apply_bcs_lin(b, ww, wd, ref["f_bnd"], ref["f_lin"])
+                ref["f_dz"].coeffs_5p_dz(dz, ww, wd, *_dz_args(b))
+                ref["f_dz"].coeffs_5p_dz2(dz2, ww, wd, *_dz_args(b))
+                ref["f_misc"].computejacobianfromdz(J1, I1, K1, dz, m, l, k, gh, im, jm)
+                ref["f_misc"].computejacobianfromdz(J2, I2, K2, dz2, m, l, k, gh, im, jm)
+    for wh, (J, I, K) in ((1, (J1, I1, K1)), (2, (J2, I2, K2))):
+        jac, ia, ja = (t.cpu().numpy() for t in out[wh])
+        assert np.array_equal(ia, I) and np.array_equal(ja, K)
+        assert np.abs(jac - J).max() < TOL * np.abs(J).max()
+
+
+@pytest.mark.parametrize("kind,im,jm", [("bl", 40, 30), ("cyl", 42, 30)])
+def test_face_linearisation_matches_direct_ad_blocks(gpu, kind, im, jm):
+    """interior blocks: semi-analytic face linearisation (facejac.cuh) == direct forward-AD kernels (jac_blocks.cuh)"""
+    import torch
+    from broadcast_b200.resident import Block, jacobian_hybrid
+    a = H.make_case(kind, im, jm, gpu, with_w=True)
+    blk = Block(a)
+    blk.apply_bcs()
+    coef = np.asfortranarray(np.random.default_rng(5).uniform(0.5, 1.5, size=(im, jm)))
+    A = jacobian_hybrid(blk, coefdiag=coef, interior="faces")
+    B = jacobian_hybrid(blk, coefdiag=coef, interior="ad")
+    gh = a.gh
+    x = A.blocks[:, :, :, gh:jm - gh, gh:im - gh]
+    y = B.blocks[:, :, :, gh:jm - gh, gh:im - gh]
+    scale = y.abs().max().item()
+    assert (x - y).abs().max().item() < TOL * scale
+    # structurally empty entries agree exactly
+    assert torch.equal(x == 0, y == 0) or ((x == 0) != (y == 0)).sum().item() < 1e-3 * x.numel()
+
+
+def test_set_bndbl(gpu, ref):
+    a = H.make_case("bl", 30, 22, gpu)
+    f1, w1 = np.zeros((22, 3, 5), order="F"), np.zeros((33, 5), order="F")
+    f2, w2 = f1.copy(order="F"), w1.copy(order="F")
+    gpu["f_init"].set_bndbl_2d(a.w, f1, w1, 30)
+    ref["f_init"].set_bndbl_2d(a.w, f2, w2, 30)
+    assert np.array_equal(f1, f2) and np.array_equal(w1, w2)
