@@ -187,6 +187,16 @@ void count_launches(int n) { g_launches += n; }
 
 extern "C" {
 
+int bcd_slab_begin(int ioff, int im_global, int edges) {
+  if (ioff < 0 || im_global < 1 || edges < 0 || edges > 3) return fail(BC_ERR_ARG, "bad slab descriptor");
+  current_slab() = SlabInfo{ioff, im_global, edges};
+  return BC_OK;
+}
+int bcd_slab_end(void) {
+  current_slab() = SlabInfo{0, 0, 0};
+  return BC_OK;
+}
+
 int bc_set_bndbl_2d(const double* w, double* field, double* wbd, int im, int jm, int gh) {
   if (im < 1 || jm < 1 || gh < 1) return fail(BC_ERR_ARG, "im, jm, gh must be positive");
   const GridDesc g = make_grid(im, jm, gh);
@@ -212,7 +222,7 @@ int bcd_residual(double* residu, const double* w, const double* nx, const double
                  double cp, double cv, double prandtl, double gam, double rgaz, double cs, double muref, double tref, double s_suth,
                  double k2, double k4, int im, int jm, int wall, int use_generic, void* stream) {
   if (int rc = check_dims(im, jm, gh)) return rc;
-  const GridDesc g = make_grid(im, jm, gh);
+  const GridDesc g = make_grid_ctx(im, jm, gh);
   const SchemeArgs a = sargs(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4);
   cudaError_t e;
   if (use_generic) {
@@ -231,7 +241,7 @@ int bcd_tangent(double* residud, const double* w, const double* wd, int ndir, co
                 double tref, double s_suth, double k2, double k4, int im, int jm, int wall, const int32_t* rect, void* stream) {
   if (int rc = check_dims(im, jm, gh)) return rc;
   if (ndir != 1 && ndir != 5) return fail(BC_ERR_ARG, "ndir must be 1 or 5");
-  const GridDesc g = make_grid(im, jm, gh);
+  const GridDesc g = make_grid_ctx(im, jm, gh);
   const SchemeArgs a = sargs(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4);
   Rect rc{1, im, 1, jm};
   if (rect) rc = Rect{rect[0], rect[1], rect[2], rect[3]};
@@ -291,7 +301,7 @@ int bcd_jn_match(double* wr, const int32_t* prr, int gh1r, int gh2r, int gh3r, i
 
 int bcd_testvector(double* wd, int ndir, int m, int l, int k, int gh, int im, int jm, const int32_t* zone, void* stream) {
   if (int rc = check_dims(im, jm, gh)) return rc;
-  const GridDesc g = make_grid(im, jm, gh);
+  const GridDesc g = make_grid_ctx(im, jm, gh);
   cudaError_t e = launch_testvector(g, wd, ndir, m, l, k, zone, (cudaStream_t)stream);
   g_launches += 1;
   return e == cudaSuccess ? BC_OK : cuda_fail(e, "bcd_testvector");
@@ -304,7 +314,7 @@ int bcd_scatter(int kind, double* seg_jac, int32_t* seg_ia, int32_t* seg_ja, con
   if ((kind == SCATTER_JV_RELAXED || kind == SCATTER_JV_RELAXED_JN || kind == SCATTER_JV_RELAXED_DBYVOL) && !coefdiag)
     return fail(BC_ERR_ARG, "coefdiag is null");
   if ((kind == SCATTER_JV_DBYVOL || kind == SCATTER_JV_RELAXED_DBYVOL) && !vol) return fail(BC_ERR_ARG, "vol is null");
-  const GridDesc g = make_grid(im, jm, gh);
+  const GridDesc g = make_grid_ctx(im, jm, gh);
   cudaError_t e = launch_scatter(g, kind, seg_jac, seg_ia, seg_ja, resd, m, l, k, coefdiag, vol, (cudaStream_t)stream);
   g_launches += 1;
   return e == cudaSuccess ? BC_OK : cuda_fail(e, "bcd_scatter");
@@ -312,7 +322,7 @@ int bcd_scatter(int kind, double* seg_jac, int32_t* seg_ia, int32_t* seg_ja, con
 
 int bcd_norm_sums(double* out10, const double* rhs, int im, int jm, int gh, void* stream) {
   if (int rc = check_dims(im, jm, gh)) return rc;
-  const GridDesc g = make_grid(im, jm, gh);
+  const GridDesc g = make_grid_ctx(im, jm, gh);
   cudaError_t e = launch_norms(g, rhs, out10, (cudaStream_t)stream);
   g_launches += 1;
   return e == cudaSuccess ? BC_OK : cuda_fail(e, "bcd_norm_sums");

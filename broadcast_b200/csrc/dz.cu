@@ -26,7 +26,7 @@ extern "C" int bcd_dz(double* dz_out, const double* w, const double* wd, int ndi
                       const double* vol, const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz,
                       double cs, double muref, double tref, double s_suth, int im, int jm, const int32_t* rect, void* stream) {
   if (im < 1 || jm < 1 || gh != 3 || (which != 1 && which != 2) || (ndir != 1 && ndir != 5)) return BC_ERR_ARG;
-  const GridDesc g = make_grid(im, jm, gh);
+  const GridDesc g = make_grid_ctx(im, jm, gh);
   const SchemeArgs a{cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, 0.0, 0.0};
   Rect rc{1, im, 1, jm};
   if (rect) rc = Rect{rect[0], rect[1], rect[2], rect[3]};

@@ -6,6 +6,7 @@
 #include "../../include/broadcast_b200.h"
 #include "facejac.cuh"
 #include "kernels.cuh"
+#include <cstdlib>
 
 namespace bcast {
 void count_launches(int n);
@@ -65,6 +66,36 @@ __global__ void __launch_bounds__(128) k_jac_assemble(GridDesc g, SchemeConsts c
 #undef X
 }
 
+__constant__ JacTab kJacTabDev = fj::make_jac_tab();
+
+// table-driven assembly: one runtime loop over the 29 column slots (see facejac.cuh)
+__global__ void __launch_bounds__(128) k_jac_assemble_rt(GridDesc g, SchemeConsts c, FieldPtrs f, Rect rc, const double* __restrict__ pkg,
+                                                         double* __restrict__ V, const double* __restrict__ coefdiag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + rc.i0;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + rc.j0;
+  if (i > rc.i1 || j > rc.j1) return;
+  const FaceCtx fi0 = make_ctx<0>(f, g, pkg, i, j), fi1 = make_ctx<0>(f, g, pkg, i + 1, j);
+  const FaceCtx fj0 = make_ctx<1>(f, g, pkg, i, j), fj1 = make_ctx<1>(f, g, pkg, i, j + 1);
+  const long long ncell = (long long)g.im * g.jm;
+  const long long cell = (long long)(i - 1) + (long long)(j - 1) * g.im;
+  const double cd = coefdiag ? coefdiag[cell] : 0.0;
+#pragma unroll 1
+  for (int s = 0; s < JAC_NSLOT; ++s) {
+    double wc[5], B[25];
+    const long long kc = g.cidx(i + kJacTabDev.di[s], j + kJacTabDev.dj[s]);
+#pragma unroll
+    for (int e = 0; e < 5; ++e) wc[e] = __ldg(f.w + e * g.sc + kc);
+    block_of_rt(kJacTabDev, s, fi0, fi1, fj0, fj1, wc, c, B);
+    if (kJacTabDev.di[s] == 0 && kJacTabDev.dj[s] == 0) {
+#pragma unroll
+      for (int e = 0; e < 5; ++e) B[e * 6] += cd;
+    }
+    double* out = V + ((long long)s * 25) * ncell + cell;
+#pragma unroll
+    for (int q = 0; q < 25; ++q) out[q * ncell] = B[q];
+  }
+}
+
 cudaError_t launch_jacobian_faces(const GridDesc& g, const SchemeArgs& a, const double* w, const double* nx, const double* ny,
                                   const double* vol, const double* volf, const Rect& rc, double* values, const double* coefdiag,
                                   cudaStream_t st) {
@@ -79,7 +110,11 @@ cudaError_t launch_jacobian_faces(const GridDesc& g, const SchemeArgs& a, const 
   dim3 gf((rf.i1 - rf.i0 + 32) / 32, (rf.j1 - rf.j0 + 4) / 4);
   k_face_packages<<<gf, blk, 0, st>>>(g, c, f, rf, pkg);
   dim3 gr((rc.i1 - rc.i0 + 32) / 32, (rc.j1 - rc.j0 + 4) / 4);
-  k_jac_assemble<<<gr, blk, 0, st>>>(g, c, f, rc, pkg, values, coefdiag);
+  static const bool unrolled = getenv("BROADCAST_B200_JAC_UNROLLED") != nullptr;   // template-unrolled variant (cross-check)
+  if (unrolled)
+    k_jac_assemble<<<gr, blk, 0, st>>>(g, c, f, rc, pkg, values, coefdiag);
+  else
+    k_jac_assemble_rt<<<gr, blk, 0, st>>>(g, c, f, rc, pkg, values, coefdiag);
   count_launches(5);
   return cudaGetLastError();
 }

@@ -395,4 +395,224 @@ BC_HD void block_of(const FaceCtx& fi0, const FaceCtx& fi1, const FaceCtx& fj0, 
   block_finish(acc, wc, c, DI == 0 || DJ == 0, B);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Table-driven consumer: the same arithmetic as face_contrib<DIR,S,T> / block_finish with the compile-time
+// stencil weights moved into a constant table indexed by (face, column slot), so that the assembly kernel is ONE
+// short runtime loop over the 29 column offsets (the fully unrolled template version is ~25 000 SASS instructions
+// and stalls on instruction fetch).  All branches depend on (face, slot) only: they are warp-uniform.
+// ---------------------------------------------------------------------------------------------
+struct FaceTab {
+  double cE, dd, dp;              // Euler / diff / pred weights of this cell in the face's along-line
+  double wIL, wJL, wIR, wJR;      // 5-point gradient weights of this cell in the sensor cells -1 (L) and 0 (R)
+  double aAp, aAm, aCp, aCm, c0;  // compact o4 interpolation weights (dual-cell sides A+, A-, C+, C-; face value)
+  int side;                       // -1, or 0 / 1: this cell is the face's along-cell -1 / 0 (spectral radius, sensor T)
+  int pk;                         // -1, or index 0..3 of this cell in the pressure sensor line
+  int flags;                      // FT_* bits
+  int pad;
+};
+enum { FT_ANY = 1, FT_LINE = 2, FT_SENS = 4, FT_VISC = 8, FT_C0 = 16 };
+struct JacTab {
+  FaceTab t[JAC_NSLOT][4];
+  int di[JAC_NSLOT], dj[JAC_NSLOT];
+  int euler[JAC_NSLOT];           // column cell on a grid axis through the row cell: Euler part present
+};
+
+namespace fj {
+constexpr FaceTab make_face_tab(int dir, int S, int T) {
+  FaceTab t{};
+  t.side = -1;
+  t.pk = -1;
+  if (!in_face(S, T)) return t;
+  t.flags = FT_ANY;
+  if (T == 0 && S >= -3 && S <= 2) {
+    t.flags |= FT_LINE;
+    t.cE = euler_c(S);
+    t.dd = diff_c(S);
+    t.dp = pred_c(S);
+  }
+  if (T == 0 && (S == 0 || S == -1)) t.side = S + 1;
+  if (T == 0 && S >= -2 && S <= 1) t.pk = S + 2;
+  const int daL = S + 1, daR = S;
+  const int diL = dir == 0 ? daL : T, djL = dir == 0 ? T : daL;
+  const int diR = dir == 0 ? daR : T, djR = dir == 0 ? T : daR;
+  t.wIL = djL == 0 ? grad_w(diL) : 0.0;
+  t.wJL = diL == 0 ? grad_w(djL) : 0.0;
+  t.wIR = djR == 0 ? grad_w(diR) : 0.0;
+  t.wJR = diR == 0 ? grad_w(djR) : 0.0;
+  if (t.wIL != 0.0 || t.wJL != 0.0 || t.wIR != 0.0 || t.wJR != 0.0) t.flags |= FT_SENS;
+  if (in_visc(S, T)) {
+    t.flags |= FT_VISC;
+    t.aAp = o4_Ap(S, T);
+    t.aAm = o4_Am(S, T);
+    t.aCp = o4_Cp(S, T);
+    t.aCm = o4_Cm(S, T);
+    if (T == 0) {
+      t.c0 = o4_r(S) * 0.0625;
+      t.flags |= FT_C0;
+    }
+  }
+  return t;
+}
+constexpr JacTab make_jac_tab() {
+  JacTab J{};
+  int s = 0;
+#define X(DI, DJ)                                   \
+  J.di[s] = (DI);                                   \
+  J.dj[s] = (DJ);                                   \
+  J.euler[s] = ((DI) == 0 || (DJ) == 0) ? 1 : 0;    \
+  J.t[s][0] = make_face_tab(0, (DI), (DJ));         \
+  J.t[s][1] = make_face_tab(0, (DI)-1, (DJ));       \
+  J.t[s][2] = make_face_tab(1, (DJ), (DI));         \
+  J.t[s][3] = make_face_tab(1, (DJ)-1, (DI));       \
+  ++s;
+  BCAST_JAC_OFFSETS(X)
+#undef X
+  return J;
+}
+}  // namespace fj
+
+// runtime-table version of face_contrib
+BC_HD void face_contrib_rt(const FaceCtx& f, const FaceTab& t, const SchemeConsts& c, double sgn, ColAcc& acc) {
+  if (!(t.flags & FT_ANY)) return;
+  if (t.flags & FT_LINE) {
+    acc.Nx += sgn * t.cE * f.nxf;
+    acc.Ny += sgn * t.cE * f.nyf;
+    acc.diag -= sgn * (f(FPK_RSE2) * t.dd + f(FPK_RSE4) * t.dp);
+  }
+  if (t.side >= 0) {
+    double drs[5];
+#pragma unroll
+    for (int m = 0; m < 5; ++m) drs[m] = f(FPK_DRS + t.side * 5 + m);
+    const double det = f(FPK_DET + t.side);
+#pragma unroll
+    for (int e = 0; e < 5; ++e) {
+      const double sd = sgn * f(FPK_SD + e);
+#pragma unroll
+      for (int m = 0; m < 5; ++m) acc.dir[e][m] -= sd * drs[m];
+      acc.gT[e] -= sgn * f(FPK_SE + e) * det;
+    }
+  }
+  if (t.pk >= 0 || (t.flags & FT_SENS)) {
+    double eP = 0.0, eU = 0.0, eV = 0.0;
+    if (t.pk >= 0) eP = f(FPK_DEP + t.pk);
+    if (t.flags & FT_SENS) {
+      eU = f(FPK_DEG + 0) * t.wIL + f(FPK_DEG + 1) * t.wJL + f(FPK_DEG + 4) * t.wIR + f(FPK_DEG + 5) * t.wJR;
+      eV = f(FPK_DEG + 2) * t.wIL + f(FPK_DEG + 3) * t.wJL + f(FPK_DEG + 6) * t.wIR + f(FPK_DEG + 7) * t.wJR;
+    }
+#pragma unroll
+    for (int e = 0; e < 5; ++e) {
+      const double se = sgn * f(FPK_SE + e);
+      acc.gP[e] -= se * eP;
+      acc.gU[e] -= se * eU;
+      acc.gV[e] -= se * eV;
+    }
+  }
+  if (t.flags & FT_VISC) {
+    const double cx = (t.aCp * f.dn.nCp_x + t.aCm * f.dn.nCm_x + t.aAp * f.dn.nAp_x + t.aAm * f.dn.nAm_x) * f.dn.volm1;
+    const double cy = (t.aCp * f.dn.nCp_y + t.aCm * f.dn.nCm_y + t.aAp * f.dn.nAp_y + t.aAm * f.dn.nAm_y) * f.dn.volm1;
+    const double mmu = f(FPK_MMU), uu = f(FPK_UU), vv = f(FPK_VV), ww = f(FPK_WW);
+    const double a_ = f.nxf * cx, b_ = f.nyf * cy, c_ = f.nyf * cx, d_ = f.nxf * cy;
+    constexpr double FT = 4.0 / 3.0, TT = 2.0 / 3.0;
+    const double al = sgn * mmu * (FT * a_ + b_);
+    const double be = sgn * mmu * (c_ - TT * d_);
+    const double ga = sgn * mmu * (d_ - TT * c_);
+    const double de = sgn * mmu * (a_ + FT * b_);
+    const double ep = sgn * mmu * (a_ + b_);
+    acc.gU[1] -= al;
+    acc.gV[1] -= be;
+    acc.gU[2] -= ga;
+    acc.gV[2] -= de;
+    acc.gW[3] -= ep;
+    double g4U = uu * al + vv * ga, g4V = uu * be + vv * de, g4W = ww * ep;
+    if (t.flags & FT_C0) {
+      const double v1m = f(FPK_V1M), v2m = f(FPK_V2M), v3m = f(FPK_V3M), v4m = f(FPK_V4M);
+      const double k = sgn * t.c0;
+      g4U += k * mmu * v1m;
+      g4V += k * mmu * v2m;
+      g4W += k * mmu * v3m;
+      acc.gMu[1] -= k * v1m;
+      acc.gMu[2] -= k * v2m;
+      acc.gMu[3] -= k * v3m;
+      acc.gMu[4] -= k * v4m;
+    }
+    acc.gU[4] -= g4U;
+    acc.gV[4] -= g4V;
+    acc.gW[4] -= g4W;
+    acc.gT[4] -= c.cpprandtl * ep;
+  }
+}
+
+// closed-form chain rule with the column cell (same result as block_finish, which differentiates cell_prims and
+// the flux formulas by forward AD): d(u,v,w,T,p,mu)/d(conservatives) are sparse and cheap by hand.
+BC_HD void block_finish_fast(const ColAcc& acc, const double (&wc)[5], const SchemeConsts& c, bool euler, bool needmu, double (&B)[25]) {
+  const double ro = wc[0];
+  const double r = 1.0 / ro;
+  const double U = wc[1] * r, V = wc[2] * r, Wz = wc[3] * r;
+  const double ec = 0.5 * (U * U + V * V + Wz * Wz);
+  const double eloc = (wc[4] - ec * ro) * r;
+  const double T = eloc * c.cvm1;
+  double dmu = 0.0;   // d mu / d T  (Sutherland, phys/viscosity.F; sqrt'(0) = 0 as in the reference tangent)
+  if (needmu) {
+    const double s = ::sqrt(T);
+    const double q = 1.0 / (T + c.s_suth);
+    dmu = (T == 0.0) ? 0.0 : c.betas * s * q * (1.5 - T * q);
+  }
+  const double g1 = c.gam1;
+  const double kTr = c.cvm1 * r;
+  // d p / d w = g1 (ec, -U, -V, -Wz, 1);  d T / d w = cvm1 r (ec - eloc, -U, -V, -Wz, 1)
+#pragma unroll
+  for (int e = 0; e < 5; ++e) {
+    const double gT = acc.gT[e] + dmu * acc.gMu[e];
+    const double kT = gT * kTr + acc.gP[e] * g1;
+    const double gU = acc.gU[e], gV = acc.gV[e], gW = acc.gW[e];
+    B[e * 5 + 0] = acc.dir[e][0] - r * (gU * U + gV * V + gW * Wz) + kT * ec - gT * kTr * eloc;
+    B[e * 5 + 1] = acc.dir[e][1] + r * gU - kT * U;
+    B[e * 5 + 2] = acc.dir[e][2] + r * gV - kT * V;
+    B[e * 5 + 3] = acc.dir[e][3] + r * gW - kT * Wz;
+    B[e * 5 + 4] = acc.dir[e][4] + kT;
+    B[e * 6] += acc.diag;
+  }
+  if (euler) {
+    // F_e = mn phi_e + p n_e,  mn = w1 Nx + w2 Ny,  phi = (1, U, V, Wz, H),  n = (0, Nx, Ny, 0, 0)
+    const double Nx = acc.Nx, Ny = acc.Ny;
+    const double P = g1 * ro * eloc;
+    const double H = (wc[4] + P) * r;
+    const double Vn = U * Nx + V * Ny;
+    const double dP[5] = {g1 * ec, -g1 * U, -g1 * V, -g1 * Wz, g1};
+    B[1] += Nx;
+    B[2] += Ny;
+    B[5] += -Vn * U + Nx * dP[0];
+    B[6] += U * Nx + Vn + Nx * dP[1];
+    B[7] += U * Ny + Nx * dP[2];
+    B[8] += Nx * dP[3];
+    B[9] += Nx * dP[4];
+    B[10] += -Vn * V + Ny * dP[0];
+    B[11] += V * Nx + Ny * dP[1];
+    B[12] += V * Ny + Vn + Ny * dP[2];
+    B[13] += Ny * dP[3];
+    B[14] += Ny * dP[4];
+    B[15] += -Vn * Wz;
+    B[16] += Wz * Nx;
+    B[17] += Wz * Ny;
+    B[18] += Vn;
+    B[20] += Vn * (dP[0] - H);
+    B[21] += H * Nx + Vn * dP[1];
+    B[22] += H * Ny + Vn * dP[2];
+    B[23] += Vn * dP[3];
+    B[24] += Vn * (1.0 + dP[4]);
+  }
+}
+
+// block of column slot `s` through the table
+BC_HD void block_of_rt(const JacTab& J, int s, const FaceCtx& fi0, const FaceCtx& fi1, const FaceCtx& fj0, const FaceCtx& fj1,
+                       const double (&wc)[5], const SchemeConsts& c, double (&B)[25]) {
+  ColAcc acc;
+  acc.clear();
+  face_contrib_rt(fi0, J.t[s][0], c, -1.0, acc);
+  face_contrib_rt(fi1, J.t[s][1], c, 1.0, acc);
+  face_contrib_rt(fj0, J.t[s][2], c, -1.0, acc);
+  face_contrib_rt(fj1, J.t[s][3], c, 1.0, acc);
+  block_finish_fast(acc, wc, c, J.euler[s] != 0, true, B);
+}
+
 }  // namespace bcast

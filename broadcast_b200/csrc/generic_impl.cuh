@@ -72,10 +72,10 @@ static __global__ void k_grad_ghost(GridDesc g, double* __restrict__ grad, int n
     const int i = t + 1;
     p[g.cidx(i, 0)] = 2.0 * p[g.cidx(i, 1)] - p[g.cidx(i, 2)];
     p[g.cidx(i, jm + 1)] = 2.0 * p[g.cidx(i, jm)] - p[g.cidx(i, jm - 1)];
-  } else if (t < im + jm) {  // i sides
+  } else if (t < im + jm) {  // i sides (physical ones only: a slab-internal edge holds computed gradients)
     const int j = t - im + 1;
-    p[g.cidx(0, j)] = 2.0 * p[g.cidx(1, j)] - p[g.cidx(2, j)];
-    p[g.cidx(im + 1, j)] = 2.0 * p[g.cidx(im, j)] - p[g.cidx(im - 1, j)];
+    if (!(g.edges & 1)) p[g.cidx(0, j)] = 2.0 * p[g.cidx(1, j)] - p[g.cidx(2, j)];
+    if (!(g.edges & 2)) p[g.cidx(im + 1, j)] = 2.0 * p[g.cidx(im, j)] - p[g.cidx(im - 1, j)];
   }
 }
 
@@ -142,7 +142,7 @@ cudaError_t residual_generic_t(const GridDesc& g, const SchemeArgs& a, bool wall
   if (rc.i1 < rc.i0 || rc.j1 < rc.j0) return cudaSuccess;
   // the balance of a cell reads gradients of its 4-neighbourhood (sensor) and primitives up to gh = 3
   // cells away; a gradient reads primitives 2 cells away: restrict both passes to what `rect` needs
-  const Rect rg{max(1, rc.i0 - 1), min(g.im, rc.i1 + 1), max(1, rc.j0 - 1), min(g.jm, rc.j1 + 1)};
+  const Rect rg{max(g.glo(), rc.i0 - 1), min(g.ghi(), rc.i1 + 1), max(1, rc.j0 - 1), min(g.jm, rc.j1 + 1)};
   const Rect rp{max(0, rc.i0 - 5 + g.gh), min(g.ni() - 1, rc.i1 + 3 + g.gh), max(0, rc.j0 - 5 + g.gh), min(g.nj() - 1, rc.j1 + 3 + g.gh)};  // +-4 (wall row 1 reads row 5)
   dim3 gall((rp.i1 - rp.i0 + 32) / 32, (rp.j1 - rp.j0 + 4) / 4);
   k_prims<N><<<gall, blk, 0, st>>>(g, c, rp, w, wd, prim, primd);
@@ -299,8 +299,8 @@ cudaError_t prepare_prims_grads(const GridDesc& g, const SchemeArgs& a, const do
   dim3 gall((g.ni() + 31) / 32, (g.nj() + 3) / 4);
   k_prims<0><<<gall, blk, 0, st>>>(g, c, Rect{0, g.ni() - 1, 0, g.nj() - 1}, w, nullptr, prim, nullptr);
   f = FieldPtrs{w, prim, grad, nx, ny, vol, volf, nullptr, nullptr, nullptr};
-  dim3 gint((g.im + 31) / 32, (g.jm + 3) / 4);
-  k_grads<0><<<gint, blk, 0, st>>>(g, f, Rect{1, g.im, 1, g.jm}, grad, nullptr);
+  dim3 gint((g.im + 2 + 31) / 32, (g.jm + 3) / 4);
+  k_grads<0><<<gint, blk, 0, st>>>(g, f, Rect{g.glo(), g.ghi(), 1, g.jm}, grad, nullptr);
   k_grad_ghost<<<dim3((g.im + g.jm + 127) / 128, NGRAD), 128, 0, st>>>(g, grad, NGRAD);
   return cudaGetLastError();
 }

@@ -23,6 +23,12 @@ struct GridDesc {
   int im, jm, gh;
   int ldc, ldn;
   long long sc, sn;
+  // i-slab of a larger block: global index of local cell i is i + ioff, the block has img columns;
+  // edges bit 0 / 1: the Ilo / Ihi side is a slab-internal edge whose gh halo columns hold real neighbour data
+  // (gradients are then computed there instead of extrapolated).  Whole block: ioff = 0, img = im, edges = 0.
+  int ioff, img, edges;
+  BC_HD int glo() const { return (edges & 1) ? 0 : 1; }        // first / last column with a computed gradient
+  BC_HD int ghi() const { return (edges & 2) ? im + 1 : im; }
   BC_HD long long cidx(int i, int j) const { return (long long)(i - 1 + gh) + (long long)(j - 1 + gh) * ldc; }
   BC_HD long long nidx(int i, int j) const { return (long long)(i - 1 + gh) + (long long)(j - 1 + gh) * ldn; }
   BC_HD int ni() const { return im + 2 * gh; }
@@ -38,6 +44,9 @@ inline GridDesc make_grid(int im, int jm, int gh) {
   g.ldn = im + 2 * gh + 1;
   g.sc = (long long)g.ldc * (jm + 2 * gh);
   g.sn = (long long)g.ldn * (jm + 2 * gh + 1);
+  g.ioff = 0;
+  g.img = im;
+  g.edges = 0;
   return g;
 }
 

@@ -42,12 +42,14 @@ extern "C" int bcd_jacobian_interior(double* values, const double* w, const doub
                                      double muref, double tref, double s_suth, double k2, double k4, int im, int jm,
                                      const double* coefdiag, const int32_t* rect, void* stream) {
   if (im < 1 || jm < 1 || gh != 3) return BC_ERR_ARG;
-  const GridDesc g = make_grid(im, jm, gh);
+  const GridDesc g = make_grid_ctx(im, jm, gh);
   const SchemeArgs a{cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4};
-  Rect rc{gh + 1, im - gh, gh + 1, jm - gh};
+  // regular rows: gh away from the physical sides; a slab-internal edge has real data in its halo, rows go up to it
+  const int ilo = (g.edges & 1) ? 1 : gh + 1, ihi = (g.edges & 2) ? im : im - gh;
+  Rect rc{ilo, ihi, gh + 1, jm - gh};
   if (rect) {
     rc = Rect{rect[0], rect[1], rect[2], rect[3]};
-    if (rc.i0 < gh + 1 || rc.i1 > im - gh || rc.j0 < gh + 1 || rc.j1 > jm - gh) return BC_ERR_ARG;
+    if (rc.i0 < ilo || rc.i1 > ihi || rc.j0 < gh + 1 || rc.j1 > jm - gh) return BC_ERR_ARG;
   }
   if (rc.i1 < rc.i0 || rc.j1 < rc.j0) return BC_OK;
   cudaError_t e = launch_jacobian_faces(g, a, w, nx, ny, vol, volf, rc, values, coefdiag, (cudaStream_t)stream);
@@ -60,13 +62,15 @@ extern "C" int bcd_jacobian_interior_ad(double* values, const double* w, const d
                                      const double* coefdiag, const int32_t* rect, void* stream) {
   if (im < 1 || jm < 1 || gh != 3) return BC_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const GridDesc g = make_grid(im, jm, gh);
+  const GridDesc g = make_grid_ctx(im, jm, gh);
   const SchemeArgs a{cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4};
   const SchemeConsts c = make_consts(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4);
-  Rect rc{gh + 1, im - gh, gh + 1, jm - gh};
+  // regular rows: gh away from the physical sides; a slab-internal edge has real data in its halo, rows go up to it
+  const int ilo = (g.edges & 1) ? 1 : gh + 1, ihi = (g.edges & 2) ? im : im - gh;
+  Rect rc{ilo, ihi, gh + 1, jm - gh};
   if (rect) {
     rc = Rect{rect[0], rect[1], rect[2], rect[3]};
-    if (rc.i0 < gh + 1 || rc.i1 > im - gh || rc.j0 < gh + 1 || rc.j1 > jm - gh) return BC_ERR_ARG;
+    if (rc.i0 < ilo || rc.i1 > ihi || rc.j0 < gh + 1 || rc.j1 > jm - gh) return BC_ERR_ARG;
   }
   if (rc.i1 < rc.i0 || rc.j1 < rc.j0) return BC_OK;
   FieldPtrs f;

@@ -42,11 +42,13 @@ static cudaError_t apply_bc_list(const GridDesc& g, double gam, int ndir, double
 __global__ void k_scatter5(GridDesc g, int kind, double* __restrict__ jac, int* __restrict__ ia, int* __restrict__ ja,
                            const double* __restrict__ resd5, int l, int k, const double* __restrict__ coefdiag,
                            const double* __restrict__ vol, Rect rc, int compact) {
-  const int im = g.im, jm = g.jm, gh = g.gh, s = 2 * gh + 1;
+  // i-slabs: il = local column, i = global column (see k_scatter)
+  const int iml = g.im, im = g.img, jm = g.jm, gh = g.gh, s = 2 * gh + 1;
   const int wi = rc.i1 - rc.i0 + 1, wj = rc.j1 - rc.j0 + 1;
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= 5LL * wi * wj) return;
-  const int i = (int)(t % wi) + rc.i0;
+  const int il = (int)(t % wi) + rc.i0;
+  const int i = il + g.ioff;
   const int j = (int)((t / wi) % wj) + rc.j0;
   const int e = (int)(t / ((long long)wi * wj)) + 1;
   const bool withjn = kind == SCATTER_JV_RELAXED_JN || kind == SCATTER_JV_JN;
@@ -74,10 +76,10 @@ __global__ void k_scatter5(GridDesc g, int kind, double* __restrict__ jac, int* 
     }
   }
   // reference slot order (ComputeJacobian.f90:524), over the whole grid or (compact) over the rectangle only
-  const long long n = compact ? 5LL * wi * wj : 5LL * im * jm;
-  const long long cell = compact ? (long long)(i - rc.i0) + (long long)(j - rc.j0) * wi + (long long)(e - 1) * wi * wj
-                                 : (long long)(i - 1) + (long long)(j - 1) * im + (long long)(e - 1) * im * jm;
-  const long long kc = g.cidx(i, j);
+  const long long n = compact ? 5LL * wi * wj : 5LL * iml * jm;
+  const long long cell = compact ? (long long)(il - rc.i0) + (long long)(j - rc.j0) * wi + (long long)(e - 1) * wi * wj
+                                 : (long long)(il - 1) + (long long)(j - 1) * iml + (long long)(e - 1) * iml * jm;
+  const long long kc = g.cidx(il, j);
 #pragma unroll
   for (int m = 0; m < 5; ++m) {
     const long long slot = cell + (long long)k * n + (long long)l * n * s + (long long)m * n * s * s;
@@ -90,7 +92,7 @@ __global__ void k_scatter5(GridDesc g, int kind, double* __restrict__ jac, int* 
       } else {
         val = -r;
         if ((kind == SCATTER_JV_RELAXED || kind == SCATTER_JV_RELAXED_JN || kind == SCATTER_JV_RELAXED_DBYVOL) && row == col)
-          val = -r + coefdiag[(i - 1) + (long long)(j - 1) * im];
+          val = -r + coefdiag[(il - 1) + (long long)(j - 1) * iml];
         if (kind == SCATTER_JV_DBYVOL || kind == SCATTER_JV_RELAXED_DBYVOL) val = val / vol[kc];
       }
       jac[slot] = val;
@@ -111,7 +113,7 @@ using namespace bcast;
 extern "C" int bcd_apply_bcs(double* w, const double* nx, const double* ny, double gam, int gh, int im, int jm, const bc_desc_t* bcs,
                              int nbcs, void* stream) {
   if (im < 1 || jm < 1 || gh != 3) return BC_ERR_ARG;
-  const GridDesc g = make_grid(im, jm, gh);
+  const GridDesc g = make_grid_ctx(im, jm, gh);
   cudaError_t e = apply_bc_list(g, gam, 0, w, nullptr, nx, ny, bcs, nbcs, (cudaStream_t)stream);
   return e == cudaSuccess ? BC_OK : (int)e;
 }
@@ -124,7 +126,7 @@ extern "C" int bcd_jacobian_coo(double* jac, int32_t* ia, int32_t* ja, double* w
   if (im < 1 || jm < 1 || gh != 3) return BC_ERR_ARG;
   if (scatter_kind < 0 || scatter_kind > 6) return BC_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const GridDesc g = make_grid(im, jm, gh);
+  const GridDesc g = make_grid_ctx(im, jm, gh);
   const SchemeArgs a{cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4};
   const int s = 2 * gh + 1;
   double* wd5 = scratch_doubles(20, (size_t)g.sc * 25);
@@ -134,9 +136,14 @@ extern "C" int bcd_jacobian_coo(double* jac, int32_t* ia, int32_t* ja, double* w
   if (rect) rc = Rect{rect[0], rect[1], rect[2], rect[3]};
   if (rc.i1 < rc.i0 || rc.j1 < rc.j0) return BC_OK;
   const long long nt = 5LL * (rc.i1 - rc.i0 + 1) * (rc.j1 - rc.j0 + 1);
+  // the seeds may be restricted to the window the rows of `rect` can read, unless a join copies tangents from the far
+  // side of the block (periodic cut): then every seed matters
+  bool has_join = false;
+  for (int b = 0; b < nbcs; ++b) has_join = has_join || bcs[b].kind == BC_KIND_JOIN;
+  const Rect* seed_rows = (rect && !has_join) ? &rc : nullptr;
   for (int l = 0; l < s; ++l)
     for (int k = 0; k < s; ++k) {
-      cudaError_t e = launch_testvector(g, wd5, 5, 0, l, k, nullptr, st, rect ? &rc : nullptr);
+      cudaError_t e = launch_testvector(g, wd5, 5, 0, l, k, nullptr, st, seed_rows);
       if (e != cudaSuccess) return (int)e;
       e = apply_bc_list(g, gam, 5, w, wd5, nx, ny, bcs, nbcs, st);
       if (e != cudaSuccess) return (int)e;
@@ -158,7 +165,7 @@ extern "C" int bcd_dz_coo(double* jac1, int32_t* ia1, int32_t* ja1, double* jac2
                           void* stream) {
   if (im < 1 || jm < 1 || gh != 3) return BC_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const GridDesc g = make_grid(im, jm, gh);
+  const GridDesc g = make_grid_ctx(im, jm, gh);
   const SchemeArgs a{cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, 0.0, 0.0};
   const int s = 2 * gh + 1;
   double* wd5 = scratch_doubles(20, (size_t)g.sc * 25);

@@ -23,6 +23,11 @@ std::mutex g_scratch_mu;
 std::map<std::pair<int, int>, Slot> g_scratch;  // (device, slot)
 }  // namespace
 
+SlabInfo& current_slab() {
+  static thread_local SlabInfo s{0, 0, 0};
+  return s;
+}
+
 double* scratch_doubles(int slot, size_t count) {
   int dev = 0;
   cudaGetDevice(&dev);
@@ -156,7 +161,7 @@ __global__ void k_testvector(GridDesc g, double* __restrict__ wd, int ndir, int 
   const int ii = blockIdx.x * blockDim.x + threadIdx.x + win.i0;
   const int jj = blockIdx.y * blockDim.y + threadIdx.y + win.j0;
   if (ii > win.i1 || jj > win.j1) return;
-  const int i = ii + 1 - g.gh, j = jj + 1 - g.gh;
+  const int i = ii + 1 - g.gh + g.ioff, j = jj + 1 - g.gh;   // global column index (i-slabs: seeds also fall in the halo)
   const int s = 2 * g.gh + 1;
   const bool seed = i >= is + l + 1 && i <= ie && j >= js + k + 1 && j <= je && (i - (is + l + 1)) % s == 0 && (j - (js + k + 1)) % s == 0;
   const long long kk = ii + (long long)jj * g.ldc;
@@ -178,7 +183,7 @@ cudaError_t launch_testvector(const GridDesc& g, double* wd, int ndir, int m, in
     win = Rect{max(0, rows->i0 - 5 + g.gh), min(g.ni() - 1, rows->i1 + 3 + g.gh), max(0, rows->j0 - 5 + g.gh),
                min(g.nj() - 1, rows->j1 + 3 + g.gh)};
   dim3 blk(32, 4), grd((win.i1 - win.i0 + 32) / 32, (win.j1 - win.j0 + 4) / 4);
-  int is = 0, ie = g.im, js = 0, je = g.jm;
+  int is = 0, ie = g.img, js = 0, je = g.jm;
   if (zone) {  // testvector_partial: i = istart+l+1 .. iend+1, j = jstart+k+1 .. jend+1
     is = zone[0];
     ie = zone[1] + 1;
@@ -196,12 +201,15 @@ cudaError_t launch_testvector(const GridDesc& g, double* wd, int ndir, int m, in
 __global__ void k_scatter(GridDesc g, int kind, double* __restrict__ jac, int* __restrict__ ia, int* __restrict__ ja,
                           const double* __restrict__ resd, int m, int l, int k, const double* __restrict__ coefdiag,
                           const double* __restrict__ vol) {
-  const int im = g.im, jm = g.jm, gh = g.gh, s = 2 * gh + 1;
+  // i-slabs: il = local column (addresses resd / coefdiag / the slot), i = global column (row, column numbering and the
+  // nearest-seed rules of misc/ComputeJacobian.f90, which refer to the whole block of im = g.img columns)
+  const int iml = g.im, im = g.img, jm = g.jm, gh = g.gh, s = 2 * gh + 1;
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (t >= 5LL * im * jm) return;
-  const int i = (int)(t % im) + 1;
-  const int j = (int)((t / im) % jm) + 1;
-  const int e = (int)(t / ((long long)im * jm)) + 1;
+  if (t >= 5LL * iml * jm) return;
+  const int il = (int)(t % iml) + 1;
+  const int i = il + g.ioff;
+  const int j = (int)((t / iml) % jm) + 1;
+  const int e = (int)(t / ((long long)iml * jm)) + 1;
   const bool withjn = kind == SCATTER_JV_RELAXED_JN || kind == SCATTER_JV_JN;
   const int dummy_ia = 5 * im * jm - (withjn ? 2 : 1);
   int row = e - 1 + (j - 1) * 5 + (i - 1) * jm * 5;
@@ -237,14 +245,14 @@ __global__ void k_scatter(GridDesc g, int kind, double* __restrict__ jac, int* _
   }
   if (ok) {
     col = m + valj * 5 + vali * jm * 5;
-    const double r = resd[(long long)(e - 1) * g.sc + g.cidx(i, j)];
+    const double r = resd[(long long)(e - 1) * g.sc + g.cidx(il, j)];
     if (kind == SCATTER_DZ) {
       val = r;
     } else {
       val = -r;
       if ((kind == SCATTER_JV_RELAXED || kind == SCATTER_JV_RELAXED_JN || kind == SCATTER_JV_RELAXED_DBYVOL) && row == col)
-        val = -r + coefdiag[(i - 1) + (long long)(j - 1) * im];
-      if (kind == SCATTER_JV_DBYVOL || kind == SCATTER_JV_RELAXED_DBYVOL) val = val / vol[g.cidx(i, j)];
+        val = -r + coefdiag[(il - 1) + (long long)(j - 1) * iml];
+      if (kind == SCATTER_JV_DBYVOL || kind == SCATTER_JV_RELAXED_DBYVOL) val = val / vol[g.cidx(il, j)];
     }
   } else {
     row = dummy_ia;

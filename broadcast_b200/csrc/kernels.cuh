@@ -11,6 +11,22 @@ namespace bcast {
 double* scratch_doubles(int slot, size_t count);
 void scratch_release_all();
 
+// slab descriptor of the calling thread (bcd_slab_begin / bcd_slab_end); make_grid_ctx applies it
+struct SlabInfo {
+  int ioff, img, edges;
+};
+SlabInfo& current_slab();
+inline GridDesc make_grid_ctx(int im, int jm, int gh) {
+  GridDesc g = make_grid(im, jm, gh);
+  const SlabInfo& s = current_slab();
+  if (s.img > 0) {
+    g.ioff = s.ioff;
+    g.img = s.img;
+    g.edges = s.edges;
+  }
+  return g;
+}
+
 struct SchemeArgs {
   double cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4;
 };

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(TI* TJ, 2)
   for (int idx = tid; idx < GI * GJ; idx += NT) {
     const int a = idx % GI + (H - 1), b = idx / GI + (H - 1);
     const int ci = i0 - H + a, cj = j0 - H + b;
-    if (ci >= 1 && ci <= im && cj >= 1 && cj <= jm) {
+    if (ci >= g.glo() && ci <= g.ghi() && cj >= 1 && cj <= jm) {   // slab-internal edges: real gradients in the halo column
       const Acc A = make_acc(a, b);
       const auto r = cell_gradients<0, 0>(A);
       sm[(A_G + 0) * NC + A.k] = r.u0.v;
@@ -133,8 +133,8 @@ __global__ void __launch_bounds__(TI* TJ, 2)
     const int k = a + b * PI;
     int d = 0;
     if (cj >= 1 && cj <= jm) {
-      if (ci == 0) d = 1;
-      else if (ci == im + 1) d = -1;
+      if (ci == 0 && !(g.edges & 1)) d = 1;
+      else if (ci == im + 1 && !(g.edges & 2)) d = -1;
     } else if (ci >= 1 && ci <= im) {
       if (cj == 0) d = PI;
       else if (cj == jm + 1) d = -PI;

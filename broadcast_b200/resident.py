@@ -37,10 +37,13 @@ def _interf(a) -> np.ndarray:
 
 
 class Block:
-    def __init__(self, case: Case, device="cuda:0"):
+    def __init__(self, case: Case, device="cuda:0", slab=None):
+        """``slab`` = (ioff, im_global, edges) when ``case`` is an i-slab of a larger block (broadcast_b200.sharding)."""
         if not torch.cuda.is_available():
             raise _lib.BroadcastB200Error("resident mode needs a CUDA device (no CPU fallback)")
         self.lib = _lib.lib()
+        self.slab = tuple(int(v) for v in slab) if slab is not None else None
+        self.ioff, self.im_global = (self.slab[0], self.slab[1]) if self.slab else (0, case.im)
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         self.case = case
@@ -81,6 +84,19 @@ class Block:
     def _ck(self, rc, what):
         _lib.check(rc, what)
 
+    def call(self, name, *args):
+        """one device entry point, inside this block's slab context (bcd_slab_begin / bcd_slab_end)"""
+        fn = getattr(self.lib, name)
+        if self.slab is None:
+            rc = fn(*args)
+        else:
+            _lib.check(self.lib.bcd_slab_begin(*self.slab), "bcd_slab_begin")
+            try:
+                rc = fn(*args)
+            finally:
+                self.lib.bcd_slab_end()
+        _lib.check(rc, name)
+
     def upload_state(self, w_host: np.ndarray):
         self.w.copy_(torch.from_numpy(np.ascontiguousarray(np.asfortranarray(w_host).T)))
 
@@ -114,9 +130,8 @@ class Block:
     def residual(self, generic=False, w=None, out=None):
         w = self.w if w is None else w
         out = self.res if out is None else out
-        rc = self.lib.bcd_residual(_p(out), _p(w), _p(self.nx), _p(self.ny), _p(self.vol), _p(self.volf), self.gh, *self._phys,
-                                   self.im, self.jm, self.wall, 1 if generic else 0, self._stream())
-        self._ck(rc, "bcd_residual")
+        self.call("bcd_residual", _p(out), _p(w), _p(self.nx), _p(self.ny), _p(self.vol), _p(self.volf), self.gh, *self._phys,
+                  self.im, self.jm, self.wall, 1 if generic else 0, self._stream())
         return out
 
     def tangent(self, wd, ndir, out, w=None, rect=None):
@@ -124,15 +139,16 @@ class Block:
         r = None
         if rect is not None:
             r = np.asarray(rect, dtype=np.int32)
-        rc = self.lib.bcd_tangent(_p(out), _p(w), _p(wd), ndir, _p(self.nx), _p(self.ny), _p(self.vol), _p(self.volf), self.gh,
-                                  *self._phys, self.im, self.jm, self.wall,
-                                  r.ctypes.data_as(ctypes.c_void_p) if r is not None else ctypes.c_void_p(None), self._stream())
-        self._ck(rc, "bcd_tangent")
+        self.call("bcd_tangent", _p(out), _p(w), _p(wd), ndir, _p(self.nx), _p(self.ny), _p(self.vol), _p(self.volf), self.gh,
+                  *self._phys, self.im, self.jm, self.wall,
+                  r.ctypes.data_as(ctypes.c_void_p) if r is not None else ctypes.c_void_p(None), self._stream())
         return out
 
-    def norms(self, res=None):
+    def norms(self, res=None, reduce=None):
         res = self.res if res is None else res
         self._ck(self.lib.bcd_norm_sums(_p(self.out10), _p(res), self.im, self.jm, self.gh, self._stream()), "bcd_norm_sums")
+        if reduce is not None:   # slabs: sum of squares / 10th powers over the ranks (one all-reduce of 10 doubles)
+            reduce(self.out10)
         h = self.out10.cpu().numpy()
         return np.sqrt(h[:5]), h[5:10] ** 0.1
 
@@ -148,6 +164,15 @@ class Block:
         self.step()
         res_pinned.copy_(self.res, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
+
+
+def local_halo_exchange(blocks):
+    """halo exchange between the i-slab Blocks of ONE process (rank order = list order): device-to-device copies of the
+    gh columns next to every slab-internal edge (peer copies over NVLink when the blocks live on different GPUs)."""
+    for a, b in zip(blocks[:-1], blocks[1:]):
+        gh = a.gh
+        b.w[:, :, 0:gh].copy_(a.w[:, :, a.im:a.im + gh], non_blocking=True)                    # a's last owned -> b's left halo
+        a.w[:, :, a.im + gh:a.im + 2 * gh].copy_(b.w[:, :, gh:2 * gh], non_blocking=True)      # b's first owned -> a's right halo
 
 
 # ----------------------------------------------------------------------------------------------
@@ -212,11 +237,9 @@ def jacobian_coo(blk: "Block", coefdiag=None, kind=None, rect=None, out=None, co
         coefdiag = _t(coefdiag, blk.device)
     descs, n = _bc_descs(blk)
     r = np.asarray(rect, dtype=np.int32) if rect is not None else None
-    rc = blk.lib.bcd_jacobian_coo(_p(jac), _p(ia), _p(ja), _p(blk.w), _p(blk.nx), _p(blk.ny), _p(blk.vol), _p(blk.volf), gh, *blk._phys,
-                                  im, jm, blk.wall, descs, n, SCATTER[kind], _p(coefdiag),
-                                  r.ctypes.data_as(ctypes.c_void_p) if r is not None else ctypes.c_void_p(None), 1 if compact else 0,
-                                  blk._stream())
-    _lib.check(rc, "bcd_jacobian_coo")
+    blk.call("bcd_jacobian_coo", _p(jac), _p(ia), _p(ja), _p(blk.w), _p(blk.nx), _p(blk.ny), _p(blk.vol), _p(blk.volf), gh, *blk._phys,
+             im, jm, blk.wall, descs, n, SCATTER[kind], _p(coefdiag),
+             r.ctypes.data_as(ctypes.c_void_p) if r is not None else ctypes.c_void_p(None), 1 if compact else 0, blk._stream())
     return jac, ia, ja
 
 
@@ -236,9 +259,8 @@ def dz_coo(blk: "Block", which=(1, 2)):
     descs, n = _bc_descs(blk)
     a = [(_p(t) for t in out[wh]) if wh in out else (ctypes.c_void_p(None),) * 3 for wh in (1, 2)]
     args = [x for trip in a for x in trip]
-    rc = blk.lib.bcd_dz_coo(*args, _p(blk.w), _p(blk.nx), _p(blk.ny), _p(blk.vol), _p(blk.volf), gh, *blk._phys[:9], im, jm, descs, n,
-                            blk._stream())
-    _lib.check(rc, "bcd_dz_coo")
+    blk.call("bcd_dz_coo", *args, _p(blk.w), _p(blk.nx), _p(blk.ny), _p(blk.vol), _p(blk.volf), gh, *blk._phys[:9], im, jm, descs, n,
+             blk._stream())
     return out
 
 
@@ -273,7 +295,7 @@ class HybridJacobian:
         vals, rows, cols = [], [], []
         if i1 >= i0 and j1 >= j0:
             dev = blk.device
-            I = torch.arange(i0, i1 + 1, device=dev, dtype=torch.int64)[None, :]
+            I = torch.arange(i0, i1 + 1, device=dev, dtype=torch.int64)[None, :] + blk.ioff   # global column index of the local cells
             J = torch.arange(j0, j1 + 1, device=dev, dtype=torch.int64)[:, None]
             for s, (di, dj) in enumerate(self.offsets):
                 for e in range(5):
@@ -295,7 +317,7 @@ class HybridJacobian:
     def to_scipy_csr(self, thresh=2e-16):
         import scipy.sparse as sp
         v, r, c = self.to_coo(thresh)
-        n = 5 * self.blk.im * self.blk.jm
+        n = 5 * self.blk.im_global * self.blk.jm
         return sp.csr_matrix((v.cpu().numpy(), (r.cpu().numpy(), c.cpu().numpy())), shape=(n, n))
 
 
@@ -312,14 +334,19 @@ def jacobian_hybrid(blk: "Block", coefdiag=None, kind=None, blocks=None, interio
         cd = coefdiag if isinstance(coefdiag, torch.Tensor) else _t(coefdiag, blk.device)
     elif relaxed:
         cd = torch.zeros((jm, im), dtype=torch.float64, device=blk.device)
-    region = (gh + 1, im - gh, gh + 1, jm - gh)
+    edges = blk.slab[2] if blk.slab else 0
+    ilo = 1 if edges & 1 else gh + 1          # a slab-internal edge has no irregular rows: the block kernels run up to it
+    ihi = im if edges & 2 else im - gh
+    region = (ilo, ihi, gh + 1, jm - gh)
     if blocks is None:
         blocks = torch.zeros((29, 5, 5, jm, im), dtype=torch.float64, device=blk.device)
-    fn = blk.lib.bcd_jacobian_interior if interior == "faces" else blk.lib.bcd_jacobian_interior_ad
-    rc = fn(_p(blocks), _p(blk.w), _p(blk.nx), _p(blk.ny), _p(blk.vol), _p(blk.volf), gh, *blk._phys, im, jm,
-                                       _p(cd if relaxed else None), ctypes.c_void_p(None), blk._stream())
-    _lib.check(rc, "bcd_jacobian_interior")
-    rects = [(1, im, 1, gh), (1, im, jm - gh + 1, jm), (1, gh, gh + 1, jm - gh), (im - gh + 1, im, gh + 1, jm - gh)]
+    blk.call("bcd_jacobian_interior" if interior == "faces" else "bcd_jacobian_interior_ad", _p(blocks), _p(blk.w), _p(blk.nx), _p(blk.ny),
+             _p(blk.vol), _p(blk.volf), gh, *blk._phys, im, jm, _p(cd if relaxed else None), ctypes.c_void_p(None), blk._stream())
+    rects = [(1, im, 1, gh), (1, im, jm - gh + 1, jm)]
+    if not edges & 1:
+        rects.append((1, gh, gh + 1, jm - gh))
+    if not edges & 2:
+        rects.append((im - gh + 1, im, gh + 1, jm - gh))
     strips = []
     for r in rects:
         if r[1] >= r[0] and r[3] >= r[2]:

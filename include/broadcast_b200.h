@@ -136,6 +136,14 @@ int bc_compute_norml2inf(double* norm, double* ninf, const double* rhs, int im, 
  * Device-pointer (resident) API.  Same semantics, no host transfers, asynchronous on `stream`.
  * `ndir` = 0 primal; 1 or 5 = number of tangent directions held in wd / residud as [ndir][5] planes.
  * ===================================================================================================== */
+/* i-slab context of the calling thread (multi-GPU).  Between bcd_slab_begin and bcd_slab_end the device
+ * entry points treat their (im, jm) block as columns ioff+1 .. ioff+im of a block of im_global columns: colouring seeds,
+ * row/column numbers and the nearest-seed rules of the scatter use GLOBAL column indices; `edges` bit 0 / bit 1 says the
+ * Ilo / Ihi side is a slab-internal edge whose gh halo columns hold the neighbour's cells (filled by the caller's halo
+ * exchange), so velocity gradients are computed there instead of extrapolated (rhs/gradveloingh.F applies to physical
+ * sides only) and the regular-row block kernels run up to that edge.  Arrays, rect arguments and slot layouts stay local. */
+int bcd_slab_begin(int ioff, int im_global, int edges);
+int bcd_slab_end(void);
 int bcd_residual(double* residu, const double* w, const double* nx, const double* ny, const double* vol,
                  const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
                  double muref, double tref, double s_suth, double k2, double k4, int im, int jm, int wall,

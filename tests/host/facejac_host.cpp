@@ -6,7 +6,22 @@
 
 using namespace bcast;
 
+static const JacTab kTab = fj::make_jac_tab();
+
+extern "C" int fj_host_blocks_impl(int table_driven, double* values, const double* w, const double* nx, const double* ny, const double* vol,
+                              const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
+                              double muref, double tref, double s_suth, double k2, double k4, int im, int jm);
 extern "C" int fj_host_blocks(double* values /* [29][25][im*jm] */, const double* w, const double* nx, const double* ny, const double* vol,
+                              const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
+                              double muref, double tref, double s_suth, double k2, double k4, int im, int jm) {
+  return fj_host_blocks_impl(0, values, w, nx, ny, vol, volf, gh, cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4, im, jm);
+}
+extern "C" int fj_host_blocks_table(double* values, const double* w, const double* nx, const double* ny, const double* vol,
+                              const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
+                              double muref, double tref, double s_suth, double k2, double k4, int im, int jm) {
+  return fj_host_blocks_impl(1, values, w, nx, ny, vol, volf, gh, cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4, im, jm);
+}
+extern "C" int fj_host_blocks_impl(int table_driven, double* values, const double* w, const double* nx, const double* ny, const double* vol,
                               const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
                               double muref, double tref, double s_suth, double k2, double k4, int im, int jm) {
   const GridDesc g = make_grid(im, jm, gh);
@@ -55,6 +70,15 @@ extern "C" int fj_host_blocks(double* values /* [29][25][im*jm] */, const double
     for (int i = i0; i <= i1; ++i) {
       const FaceCtx fi0 = ctx(0, i, j), fi1 = ctx(0, i + 1, j), fj0 = ctx(1, i, j), fj1 = ctx(1, i, j + 1);
       const long long cell = (long long)(i - 1) + (long long)(j - 1) * im;
+      if (table_driven) {
+        for (int s = 0; s < JAC_NSLOT; ++s) {
+          double wc[5], B[25];
+          for (int e = 0; e < 5; ++e) wc[e] = w[e * g.sc + g.cidx(i + kTab.di[s], j + kTab.dj[s])];
+          block_of_rt(kTab, s, fi0, fi1, fj0, fj1, wc, c, B);
+          for (int q = 0; q < 25; ++q) values[((long long)s * 25 + q) * ncell + cell] = B[q];
+        }
+        continue;
+      }
       int slot = 0;
 #define X(DI, DJ)                                                                                  \
   {                                                                                                \

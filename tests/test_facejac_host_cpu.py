@@ -28,8 +28,9 @@ def hostlib():
     return ctypes.CDLL(SO)
 
 
+@pytest.mark.parametrize("entry", ["fj_host_blocks", "fj_host_blocks_table"])
 @pytest.mark.parametrize("kind,im,jm", [("bl", 24, 16), ("cyl", 28, 16)])
-def test_face_linearisation_blocks_match_reference_colour_loop(ref, hostlib, kind, im, jm):
+def test_face_linearisation_blocks_match_reference_colour_loop(ref, hostlib, kind, im, jm, entry):
     c = H.make_case(kind, im, jm, ref, with_w=True)
     w, _ = H.residual_sequence(ref, c)
     jac, ia, ja = H.jacobian_sequence(ref, c, w, None, None)
@@ -39,7 +40,7 @@ def test_face_linearisation_blocks_match_reference_colour_loop(ref, hostlib, kin
     p, gh = c.phys, c.gh
     D = ctypes.c_double
     P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    rc = hostlib.fj_host_blocks(P(vals), P(w), P(c.nx), P(c.ny), P(c.vol), P(c.volf), gh, D(p["cp"]), D(p["cv"]), D(p["prandtl"]),
+    rc = getattr(hostlib, entry)(P(vals), P(w), P(c.nx), P(c.ny), P(c.vol), P(c.volf), gh, D(p["cp"]), D(p["cv"]), D(p["prandtl"]),
                                 D(p["gam"]), D(p["rgaz"]), D(p["cs"]), D(p["muref"]), D(p["tref"]), D(p["cs"]), D(c.k2), D(c.k4), im, jm)
     assert rc == 0
     scale = np.abs(A).max()
