@@ -26,6 +26,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 RES_BYTES_PER_CELL = 136.0  # 12 doubles read (w5, nx2, ny2, vol, volf2) + 5 written, SURVEY.md 8(d)
+JAC_BYTES_PER_CELL = 5904.0  # 29 blocks x 25 doubles written + 13 doubles read, SURVEY.md 8(d)
+RES_TRAFFIC_NCU = 2.269e9    # dram__bytes_read.sum + dram__bytes_write.sum of one launch at C5 (profiles/r1_b_residual_tile_full_raw.csv)
 
 
 def parse():
@@ -65,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -98,85 +100,11 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-# case construction (host) and slab sharding
+# case construction (host); slab sharding lives in broadcast_b200.sharding
 # ----------------------------------------------------------------------------------------------
 def build_global_case(im, jm, f_geom):
     from broadcast_b200 import cases
     return cases.make_bl_case(im, jm, f_geom=f_geom, name=f"bl2d_{im}x{jm}")
-
-
-def slab_of(case, rank, world):
-    """contiguous i-slab of the global case with its gh halo columns."""
-    import copy
-    from broadcast_b200.cases import Case
-    if world == 1:
-        return case, (1, case.im)
-    gh, im, jm = case.gh, case.im, case.jm
-    base, rem = divmod(im, world)
-    lo = rank * base + min(rank, rem) + 1
-    n = base + (1 if rank < rem else 0)
-    hi = lo + n - 1
-    cs = slice(lo - 1, hi + 2 * gh)          # storage columns of cells lo-gh .. hi+gh
-    ns = slice(lo - 1, hi + 2 * gh + 1)
-    first, last = rank == 0, rank == world - 1
-    F = np.asfortranarray
-    bcs = []
-    for bc in case.bcs:
-        kind = bc[0]
-        itf = np.array(bc[2], dtype=float)
-        if kind == "inflow":
-            if first:
-                bcs.append(bc)
-        elif kind == "outflow":
-            if last:
-                it = itf.copy(); it[0, 0] = n; it[1, 0] = n
-                bcs.append((kind, bc[1], F(it)))
-        elif kind == "noref":   # global i range [1-gh, im] -> local; interior slab edges include the halo columns
-            it = itf.copy()
-            it[0, 0] = 1 - gh
-            it[1, 0] = n if last else n + gh
-            g0 = lo - gh           # global cell index of local column 1-gh
-            wbd = bc[3][g0 - (1 - gh): g0 - (1 - gh) + (int(it[1, 0]) - int(it[0, 0]) + 1), :]
-            bcs.append((kind, bc[1], F(it), F(wbd)))
-        elif kind == "wall":
-            it = itf.copy(); it[0, 0] = 1 - gh; it[1, 0] = n + gh
-            bcs.append((kind, bc[1], F(it)))
-    sl = Case(name=f"{case.name}_slab{rank}of{world}", im=n, jm=jm, gh=gh, phys=case.phys, k2=case.k2, k4=case.k4,
-              x0=F(case.x0[ns]), y0=F(case.y0[ns]), nx=F(case.nx[ns]), ny=F(case.ny[ns]), xc=F(case.xc[cs]), yc=F(case.yc[cs]),
-              vol=F(case.vol[cs]), volf=F(case.volf[cs]), w=F(case.w[cs]), bcs=bcs, periodic_i=False, scheme=case.scheme)
-    return sl, (lo, hi)
-
-
-class HaloExchange:
-    """neighbour exchange of gh columns of w (interior rows) over NCCL send/recv"""
-
-    def __init__(self, blk, rank, world):
-        import torch
-        self.blk, self.rank, self.world = blk, rank, world
-        gh, jm = blk.gh, blk.jm
-        mk = lambda: torch.empty((5, jm, gh), dtype=torch.float64, device=blk.device)
-        self.send_l, self.send_r, self.recv_l, self.recv_r = mk(), mk(), mk(), mk()
-
-    def __call__(self):
-        import torch.distributed as dist
-        if self.world == 1:
-            return
-        b, gh, im, jm = self.blk, self.blk.gh, self.blk.im, self.blk.jm
-        w = b.w  # (5, nj, ni)
-        J = slice(gh, gh + jm)
-        ops = []
-        if self.rank > 0:
-            self.send_l.copy_(w[:, J, gh:2 * gh])
-            ops += [dist.P2POp(dist.isend, self.send_l, self.rank - 1), dist.P2POp(dist.irecv, self.recv_l, self.rank - 1)]
-        if self.rank < self.world - 1:
-            self.send_r.copy_(w[:, J, im:im + gh])
-            ops += [dist.P2POp(dist.isend, self.send_r, self.rank + 1), dist.P2POp(dist.irecv, self.recv_r, self.rank + 1)]
-        for r in dist.batch_isend_irecv(ops):
-            r.wait()
-        if self.rank > 0:
-            w[:, J, 0:gh].copy_(self.recv_l)
-        if self.rank < self.world - 1:
-            w[:, J, im + gh:im + 2 * gh].copy_(self.recv_r)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -255,15 +183,19 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    import ctypes
     import broadcast_b200 as bb
     from broadcast_b200 import _lib
-    from broadcast_b200.resident import Block
+    from broadcast_b200.resident import Block, _p
+
+    from broadcast_b200 import sharding
+    from broadcast_b200.resident import jacobian_hybrid
 
     peak, peak_kind = measured_peaks()
     gcase = build_global_case(a.im, a.jm, bb.f_geom)
-    case, (lo, hi) = slab_of(gcase, rank, world)
-    blk = Block(case, dev)
-    halo = HaloExchange(blk, rank, world)
+    case, slab = sharding.slab_of(gcase, rank, world)
+    blk = Block(case, dev, slab=slab if world > 1 else None)
+    halo = sharding.HaloExchange(case.gh, rank, world)
     del gcase
     cells_global = a.im * a.jm
     cells_local = case.im * case.jm
@@ -274,23 +206,23 @@ def main():
         torch.cuda.synchronize()
 
     def step():
-        halo()
+        halo(blk.w)
         blk.apply_bcs()
         blk.residual()
 
-    for _ in range(max(a.warmup, 3)):
-        step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(a.warmup, 3)):
+        step()
+    barrier()
     n0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     barrier()
     ev0.record()
     for s in range(a.steps):
-        halo()
+        halo(blk.w)
         blk.apply_bcs()
         kev[s][0].record()
         blk.residual()
@@ -306,12 +238,60 @@ def main():
     ms_total, k_ms = float(t[0]), float(t[1])
     ms_step = ms_total / a.steps
     value = cells_global / (ms_step * 1e-3)
-    clocks = sampler.stop() if rank == 0 else {}
 
     # roofline of the dominant kernel (fused residual tile kernel), per launch, per GPU
     achieved = RES_BYTES_PER_CELL * cells_local / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_residual_tile<32,8>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_kind": peak_kind, "traffic": None, "kernel_ms": k_ms, "algorithmic_bytes_per_cell": RES_BYTES_PER_CELL}
+                "peak_kind": peak_kind, "traffic": RES_TRAFFIC_NCU if (a.im, a.jm, world) == (8192, 2048, 1) else None, "kernel_ms": k_ms,
+                "algorithmic_bytes_per_cell": RES_BYTES_PER_CELL,
+                "fp64_pipe_note": "FP64-pipe bound at ~11 flop/B (ridge 5.8): see DESIGN.md section 4 and profiles/"}
+
+    # Jacobian assembly of the same state (BASELINE.json metric, second half): regular rows by face linearisation into the
+    # fixed 29-block pattern + the four boundary strips by the reference colour loop; algorithmic bytes 5904 B per cell
+    jac = None
+    if not a.no_jacobian:
+        nblk = 29 * 25 * cells_local * 8
+        free, _tot = torch.cuda.mem_get_info(dev)
+        if nblk + 40 * blk.w.numel() * 8 < 0.9 * free:
+            blocks = torch.empty((29, 5, 5, case.jm, case.im), dtype=torch.float64, device=dev)
+            cd = torch.zeros((case.jm, case.im), dtype=torch.float64, device=dev)
+            halo(blk.w)
+            blk.apply_bcs()
+            jacobian_hybrid(blk, coefdiag=cd, blocks=blocks)   # warm-up (allocations, first launches)
+            barrier()
+            nrep = 3
+            j0, j1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            j0.record()
+            for _ in range(nrep):
+                halo(blk.w)
+                blk.apply_bcs()
+                i0.record()
+                blk.call("bcd_jacobian_interior", _p(blocks), _p(blk.w), _p(blk.nx), _p(blk.ny), _p(blk.vol), _p(blk.volf), blk.gh, *blk._phys,
+                         case.im, case.jm, _p(cd), ctypes.c_void_p(None), blk._stream())
+                i1.record()
+                H = jacobian_hybrid(blk, coefdiag=cd, blocks=blocks)
+            j1.record()
+            barrier()
+            # the interior pass is timed once more inside the loop (i0..i1) to report its share; subtract it from the total
+            int_ms = i0.elapsed_time(i1)
+            tot_ms = j0.elapsed_time(j1) / nrep - int_ms
+            tt = torch.tensor([tot_ms, int_ms], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            tot_ms, int_ms = float(tt[0]), float(tt[1])
+            ach = JAC_BYTES_PER_CELL * cells_local / (tot_ms * 1e-3) / 1e9
+            jac = {"assembly_s": tot_ms * 1e-3, "cells": cells_global, "cells_per_s": cells_global / (tot_ms * 1e-3),
+                   "interior_blocks_ms": int_ms, "strips_and_fill_ms": tot_ms - int_ms,
+                   "layout": "29 fixed 5x5 blocks per cell (values[slot][25][cell]) + COO strips in the reference's slot order",
+                   "roofline": {"bound": "hbm", "kernel": "k_face_packages + k_jac_assemble_rt (+ strip colour loops)", "achieved": ach,
+                                "peak": peak, "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_cell": JAC_BYTES_PER_CELL,
+                                "interior_only_frac": JAC_BYTES_PER_CELL * cells_local / (int_ms * 1e-3) / 1e9 / peak}}
+            del blocks, H
+            torch.cuda.empty_cache()
+        else:
+            jac = {"skipped": "block values do not fit next to the state on this GPU at this size"}
+    clocks = sampler.stop() if rank == 0 else {}
 
     # end to end through the plugin-level call with pinned HOST buffers (state in, residual out, every step)
     e2e = None
@@ -321,11 +301,11 @@ def main():
         wp.copy_(blk.w.cpu())
         nst = max(3, min(a.steps, 10))
         for _ in range(2):
-            halo(); blk.step_from_host(wp, rp)
+            blk.step_from_host(wp, rp, halo)
         barrier()
         t0 = time.perf_counter()
         for _ in range(nst):
-            halo(); blk.step_from_host(wp, rp)
+            blk.step_from_host(wp, rp, halo)
         barrier()
         dt = torch.tensor([(time.perf_counter() - t0) / nst], dtype=torch.float64, device=dev)
         if world > 1:
@@ -343,7 +323,7 @@ def main():
             "config": {"workload": f"C5 synthetic 2-D boundary layer {a.im}x{a.jm}, order 5 (gh=3), i-slabs over {world} GPU(s)",
                        "step": "halo exchange (N>1) + 4 boundary fills + 1 residual (flux_num_dnc5_2d)",
                        "l2": f"inputs larger than L2 ({blk.w.numel() * 8 / 2**20:.0f} MiB state per GPU)"},
-            "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
+            "roofline": roofline, "jacobian": jac, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
         }
         if not a.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline()

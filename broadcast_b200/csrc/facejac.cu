@@ -28,13 +28,11 @@ __global__ void __launch_bounds__(128) k_face_packages(GridDesc g, SchemeConsts 
 
 template <int DIR>
 __device__ __forceinline__ FaceCtx make_ctx(const FieldPtrs& f, const GridDesc& g, const double* pkg, int i, int j) {
-  const GlobalAcc<0> a(f, g, i, j);
   FaceCtx x;
-  x.nxf = a.template NX<0, 0>(DIR);
-  x.nyf = a.template NY<0, 0>(DIR);
-  x.dn = dual_normals<DIR>(a);
   x.pk = pkg + (long long)DIR * FPK_N * g.sc + g.cidx(i, j);
   x.stride = g.sc;
+  x.vs = x.pk + (long long)FPK_VS * g.sc;
+  x.vstride = (int)g.sc;
   return x;
 }
 
@@ -68,14 +66,38 @@ __global__ void __launch_bounds__(128) k_jac_assemble(GridDesc g, SchemeConsts c
 
 __constant__ JacTab kJacTabDev = fj::make_jac_tab();
 
-// table-driven assembly: one runtime loop over the 29 column slots (see facejac.cuh)
-__global__ void __launch_bounds__(128) k_jac_assemble_rt(GridDesc g, SchemeConsts c, FieldPtrs f, Rect rc, const double* __restrict__ pkg,
-                                                         double* __restrict__ V, const double* __restrict__ coefdiag) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x + rc.i0;
-  const int j = blockIdx.y * blockDim.y + threadIdx.y + rc.j0;
+// table-driven assembly: one runtime loop over the 29 column slots (see facejac.cuh).  CTA = 32 x 4 row cells; the
+// viscous subset (14 fields) of the packages of its 33x4 i-faces and 32x5 j-faces is staged in shared memory (32 KB).
+constexpr int JT_I = 32, JT_J = 4;
+__global__ void __launch_bounds__(JT_I* JT_J, 3)
+    k_jac_assemble_rt(GridDesc g, SchemeConsts c, FieldPtrs f, Rect rc, const double* __restrict__ pkg, double* __restrict__ V,
+                      const double* __restrict__ coefdiag) {
+  __shared__ double sI[FPK_NVS * JT_J * (JT_I + 1)];
+  __shared__ double sJ[FPK_NVS * (JT_J + 1) * JT_I];
+  const int tid = threadIdx.y * JT_I + threadIdx.x;
+  const int bi0 = blockIdx.x * JT_I + rc.i0, bj0 = blockIdx.y * JT_J + rc.j0;
+  const double* pI = pkg + (long long)FPK_VS * g.sc;
+  const double* pJ = pkg + (long long)(FPK_N + FPK_VS) * g.sc;
+  for (int idx = tid; idx < FPK_NVS * JT_J * (JT_I + 1); idx += JT_I * JT_J) {
+    const int k = idx / (JT_J * (JT_I + 1)), r = idx % (JT_J * (JT_I + 1));
+    const int fi = bi0 + r % (JT_I + 1), fj = bj0 + r / (JT_I + 1);
+    if (fi <= rc.i1 + 1 && fj <= rc.j1) sI[idx] = __ldg(pI + k * g.sc + g.cidx(fi, fj));
+  }
+  for (int idx = tid; idx < FPK_NVS * (JT_J + 1) * JT_I; idx += JT_I * JT_J) {
+    const int k = idx / ((JT_J + 1) * JT_I), r = idx % ((JT_J + 1) * JT_I);
+    const int fi = bi0 + r % JT_I, fj = bj0 + r / JT_I;
+    if (fi <= rc.i1 && fj <= rc.j1 + 1) sJ[idx] = __ldg(pJ + k * g.sc + g.cidx(fi, fj));
+  }
+  __syncthreads();
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i = bi0 + tx, j = bj0 + ty;
   if (i > rc.i1 || j > rc.j1) return;
-  const FaceCtx fi0 = make_ctx<0>(f, g, pkg, i, j), fi1 = make_ctx<0>(f, g, pkg, i + 1, j);
-  const FaceCtx fj0 = make_ctx<1>(f, g, pkg, i, j), fj1 = make_ctx<1>(f, g, pkg, i, j + 1);
+  const double* pk = pkg + g.cidx(i, j);
+  const long long dj = (long long)FPK_N * g.sc;
+  const FaceCtx fi0{pk, g.sc, sI + ty * (JT_I + 1) + tx, JT_J * (JT_I + 1)};
+  const FaceCtx fi1{pk + 1, g.sc, sI + ty * (JT_I + 1) + tx + 1, JT_J * (JT_I + 1)};
+  const FaceCtx fj0{pk + dj, g.sc, sJ + ty * JT_I + tx, (JT_J + 1) * JT_I};
+  const FaceCtx fj1{pk + dj + g.ldc, g.sc, sJ + (ty + 1) * JT_I + tx, (JT_J + 1) * JT_I};
   const long long ncell = (long long)g.im * g.jm;
   const long long cell = (long long)(i - 1) + (long long)(j - 1) * g.im;
   const double cd = coefdiag ? coefdiag[cell] : 0.0;
@@ -114,7 +136,8 @@ cudaError_t launch_jacobian_faces(const GridDesc& g, const SchemeArgs& a, const 
   if (unrolled)
     k_jac_assemble<<<gr, blk, 0, st>>>(g, c, f, rc, pkg, values, coefdiag);
   else
-    k_jac_assemble_rt<<<gr, blk, 0, st>>>(g, c, f, rc, pkg, values, coefdiag);
+    k_jac_assemble_rt<<<dim3((rc.i1 - rc.i0 + JT_I) / JT_I, (rc.j1 - rc.j0 + JT_J) / JT_J), dim3(JT_I, JT_J), 0, st>>>(g, c, f, rc, pkg, values,
+                                                                                                                  coefdiag);
   count_launches(5);
   return cudaGetLastError();
 }

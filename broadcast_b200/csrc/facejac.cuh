@@ -30,7 +30,7 @@
 namespace bcast {
 
 constexpr int JAC_NSLOT = 29;
-constexpr int FPK_N = 44;
+constexpr int FPK_N = 54;
 enum {
   FPK_RSE2 = 0,   // rspec * eps2
   FPK_RSE4 = 1,   // rspec * eps4
@@ -40,9 +40,15 @@ enum {
   FPK_DEP = 22,   // [4] d eps2 / d p(s), s = -2..1
   FPK_DET = 26,   // [2] d eps2 / d T(s), s = -1, 0
   FPK_DEG = 28,   // [2][4] sensor cell s = -1, 0: coefficients of (wI, wJ) in d eps2/dU_c and in d eps2/dV_c
-  FPK_MMU = 36, FPK_UU = 37, FPK_VV = 38, FPK_WW = 39,
-  FPK_V1M = 40, FPK_V2M = 41, FPK_V3M = 42, FPK_V4M = 43,  // visc_e / mmu
+  FPK_V1M = 36, FPK_V2M = 37, FPK_V3M = 38, FPK_V4M = 39,  // visc_e / mmu
+  // "viscous subset": the 14 fields every in-stencil column cell needs (staged in shared memory by the assembly kernel)
+  FPK_VS = 40,
+  FPK_NXF = 40, FPK_NYF = 41,                              // face normal (length-scaled)
+  FPK_MMU = 42, FPK_UU = 43, FPK_VV = 44, FPK_WW = 45,
+  FPK_DNX = 46,   // [4] dual-cell normals x volm1: A+, A-, C+, C-   (x components)
+  FPK_DNY = 50,   // [4]                                               (y components)
 };
+constexpr int FPK_NVS = 14;
 
 // a single cell seen through the accessor interface (for flux_f / flux_g)
 struct OneCell {
@@ -180,6 +186,16 @@ BC_HD void face_package(const A& a, const SchemeConsts& c, OUT&& out) {
   const double v2m = (s.uy.v + s.vx.v) * nxf + TWOTHIRD * (-s.ux.v + 2.0 * s.vy.v) * nyf;
   const double v3m = s.wx.v * nxf + s.wy.v * nyf;
   const double v4m = c.cpprandtl * (s.tx.v * nxf + s.ty.v * nyf) + s.uu.v * v1m + s.vv.v * v2m + s.ww.v * v3m;
+  out(FPK_NXF, nxf);
+  out(FPK_NYF, nyf);
+  out(FPK_DNX + 0, dn.nAp_x * dn.volm1);
+  out(FPK_DNX + 1, dn.nAm_x * dn.volm1);
+  out(FPK_DNX + 2, dn.nCp_x * dn.volm1);
+  out(FPK_DNX + 3, dn.nCm_x * dn.volm1);
+  out(FPK_DNY + 0, dn.nAp_y * dn.volm1);
+  out(FPK_DNY + 1, dn.nAm_y * dn.volm1);
+  out(FPK_DNY + 2, dn.nCp_y * dn.volm1);
+  out(FPK_DNY + 3, dn.nCm_y * dn.volm1);
   out(FPK_MMU, s.mmu.v);
   out(FPK_UU, s.uu.v);
   out(FPK_VV, s.vv.v);
@@ -209,13 +225,15 @@ struct ColAcc {
   }
 };
 
-// per-face data the consumer keeps at hand
+// handle of one face's package: field f at pk[f * stride]; the viscous subset (fields FPK_VS ..) may live in a second,
+// faster array (shared memory in the assembly kernel): field FPK_VS + k at vs[k * vstride]
 struct FaceCtx {
-  double nxf, nyf;
-  DualNormals dn;
-  const double* pk;   // package of this face: field f at pk[f * stride]
+  const double* pk;
   long long stride;
+  const double* vs;
+  int vstride;
   BC_HD double operator()(int f) const { return BC_LDG(pk + f * stride); }
+  BC_HD double v(int f) const { return vs[(f - FPK_VS) * vstride]; }
 };
 
 namespace fj {
@@ -249,8 +267,8 @@ BC_HD void face_contrib(const FaceCtx& f, const SchemeConsts& c, double sgn, Col
   } else {
     if constexpr (T == 0 && S >= -3 && S <= 2) {
       constexpr double cE = euler_c(S), dd = diff_c(S), dp = pred_c(S);
-      acc.Nx += sgn * cE * f.nxf;
-      acc.Ny += sgn * cE * f.nyf;
+      acc.Nx += sgn * cE * f.v(FPK_NXF);
+      acc.Ny += sgn * cE * f.v(FPK_NYF);
       if constexpr (dd != 0.0)
         acc.diag -= sgn * (f(FPK_RSE2) * dd + f(FPK_RSE4) * dp);
       else
@@ -303,20 +321,19 @@ BC_HD void face_contrib(const FaceCtx& f, const SchemeConsts& c, double sgn, Col
     if constexpr (in_visc(S, T)) {
       constexpr double aAp = o4_Ap(S, T), aAm = o4_Am(S, T), aCp = o4_Cp(S, T), aCm = o4_Cm(S, T);
       constexpr double c0 = T == 0 ? o4_r(S) * 0.0625 : 0.0;
-      double cx = aCp * f.dn.nCp_x + aCm * f.dn.nCm_x;
-      double cy = aCp * f.dn.nCp_y + aCm * f.dn.nCm_y;
+      double cx = aCp * f.v(FPK_DNX + 2) + aCm * f.v(FPK_DNX + 3);
+      double cy = aCp * f.v(FPK_DNY + 2) + aCm * f.v(FPK_DNY + 3);
       if constexpr (aAp != 0.0) {
-        cx += aAp * f.dn.nAp_x;
-        cy += aAp * f.dn.nAp_y;
+        cx += aAp * f.v(FPK_DNX + 0);
+        cy += aAp * f.v(FPK_DNY + 0);
       }
       if constexpr (aAm != 0.0) {
-        cx += aAm * f.dn.nAm_x;
-        cy += aAm * f.dn.nAm_y;
+        cx += aAm * f.v(FPK_DNX + 1);
+        cy += aAm * f.v(FPK_DNY + 1);
       }
-      cx *= f.dn.volm1;
-      cy *= f.dn.volm1;
-      const double mmu = f(FPK_MMU), uu = f(FPK_UU), vv = f(FPK_VV), ww = f(FPK_WW);
-      const double a_ = f.nxf * cx, b_ = f.nyf * cy, c_ = f.nyf * cx, d_ = f.nxf * cy;
+      const double mmu = f.v(FPK_MMU), uu = f.v(FPK_UU), vv = f.v(FPK_VV), ww = f.v(FPK_WW);
+      const double nxf = f.v(FPK_NXF), nyf = f.v(FPK_NYF);
+      const double a_ = nxf * cx, b_ = nyf * cy, c_ = nyf * cx, d_ = nxf * cy;
       constexpr double FT = 4.0 / 3.0, TT = 2.0 / 3.0;
       const double al = sgn * mmu * (FT * a_ + b_);   // d visc_1 / dU
       const double be = sgn * mmu * (c_ - TT * d_);   // d visc_1 / dV
@@ -415,6 +432,7 @@ struct JacTab {
   FaceTab t[JAC_NSLOT][4];
   int di[JAC_NSLOT], dj[JAC_NSLOT];
   int euler[JAC_NSLOT];           // column cell on a grid axis through the row cell: Euler part present
+  int needmu[JAC_NSLOT];          // some face sees the column cell in its face-value row (mu interpolation)
 };
 
 namespace fj {
@@ -464,6 +482,7 @@ constexpr JacTab make_jac_tab() {
   J.t[s][1] = make_face_tab(0, (DI)-1, (DJ));       \
   J.t[s][2] = make_face_tab(1, (DJ), (DI));         \
   J.t[s][3] = make_face_tab(1, (DJ)-1, (DI));       \
+  J.needmu[s] = ((J.t[s][0].flags | J.t[s][1].flags | J.t[s][2].flags | J.t[s][3].flags) & FT_C0) ? 1 : 0; \
   ++s;
   BCAST_JAC_OFFSETS(X)
 #undef X
@@ -471,79 +490,84 @@ constexpr JacTab make_jac_tab() {
 }
 }  // namespace fj
 
-// runtime-table version of face_contrib
-BC_HD void face_contrib_rt(const FaceCtx& f, const FaceTab& t, const SchemeConsts& c, double sgn, ColAcc& acc) {
+// runtime-table version of face_contrib.  The viscous part is branch-free (table weights are zero for cells outside
+// the 4x5 box) so that the loads of the four faces of a slot batch up; the rarer along-line / sensor terms branch.
+BC_HD void face_contrib_rt(const FaceCtx& f, const FaceTab& t, const SchemeConsts& c, double sgn, ColAcc& acc, double (&B)[25]) {
   if (!(t.flags & FT_ANY)) return;
-  if (t.flags & FT_LINE) {
-    acc.Nx += sgn * t.cE * f.nxf;
-    acc.Ny += sgn * t.cE * f.nyf;
-    acc.diag -= sgn * (f(FPK_RSE2) * t.dd + f(FPK_RSE4) * t.dp);
-  }
-  if (t.side >= 0) {
-    double drs[5];
-#pragma unroll
-    for (int m = 0; m < 5; ++m) drs[m] = f(FPK_DRS + t.side * 5 + m);
-    const double det = f(FPK_DET + t.side);
-#pragma unroll
-    for (int e = 0; e < 5; ++e) {
-      const double sd = sgn * f(FPK_SD + e);
-#pragma unroll
-      for (int m = 0; m < 5; ++m) acc.dir[e][m] -= sd * drs[m];
-      acc.gT[e] -= sgn * f(FPK_SE + e) * det;
-    }
-  }
-  if (t.pk >= 0 || (t.flags & FT_SENS)) {
-    double eP = 0.0, eU = 0.0, eV = 0.0;
-    if (t.pk >= 0) eP = f(FPK_DEP + t.pk);
-    if (t.flags & FT_SENS) {
-      eU = f(FPK_DEG + 0) * t.wIL + f(FPK_DEG + 1) * t.wJL + f(FPK_DEG + 4) * t.wIR + f(FPK_DEG + 5) * t.wJR;
-      eV = f(FPK_DEG + 2) * t.wIL + f(FPK_DEG + 3) * t.wJL + f(FPK_DEG + 6) * t.wIR + f(FPK_DEG + 7) * t.wJR;
-    }
-#pragma unroll
-    for (int e = 0; e < 5; ++e) {
-      const double se = sgn * f(FPK_SE + e);
-      acc.gP[e] -= se * eP;
-      acc.gU[e] -= se * eU;
-      acc.gV[e] -= se * eV;
-    }
-  }
-  if (t.flags & FT_VISC) {
-    const double cx = (t.aCp * f.dn.nCp_x + t.aCm * f.dn.nCm_x + t.aAp * f.dn.nAp_x + t.aAm * f.dn.nAm_x) * f.dn.volm1;
-    const double cy = (t.aCp * f.dn.nCp_y + t.aCm * f.dn.nCm_y + t.aAp * f.dn.nAp_y + t.aAm * f.dn.nAm_y) * f.dn.volm1;
-    const double mmu = f(FPK_MMU), uu = f(FPK_UU), vv = f(FPK_VV), ww = f(FPK_WW);
-    const double a_ = f.nxf * cx, b_ = f.nyf * cy, c_ = f.nyf * cx, d_ = f.nxf * cy;
+  const double nxf = f.v(FPK_NXF), nyf = f.v(FPK_NYF);
+  {
+    const double cx = t.aCp * f.v(FPK_DNX + 2) + t.aCm * f.v(FPK_DNX + 3) + t.aAp * f.v(FPK_DNX + 0) + t.aAm * f.v(FPK_DNX + 1);
+    const double cy = t.aCp * f.v(FPK_DNY + 2) + t.aCm * f.v(FPK_DNY + 3) + t.aAp * f.v(FPK_DNY + 0) + t.aAm * f.v(FPK_DNY + 1);
+    const double mmu = sgn * f.v(FPK_MMU), uu = f.v(FPK_UU), vv = f.v(FPK_VV), ww = f.v(FPK_WW);
+    const double a_ = nxf * cx, b_ = nyf * cy, c_ = nyf * cx, d_ = nxf * cy;
     constexpr double FT = 4.0 / 3.0, TT = 2.0 / 3.0;
-    const double al = sgn * mmu * (FT * a_ + b_);
-    const double be = sgn * mmu * (c_ - TT * d_);
-    const double ga = sgn * mmu * (d_ - TT * c_);
-    const double de = sgn * mmu * (a_ + FT * b_);
-    const double ep = sgn * mmu * (a_ + b_);
+    const double al = mmu * (FT * a_ + b_);
+    const double be = mmu * (c_ - TT * d_);
+    const double ga = mmu * (d_ - TT * c_);
+    const double de = mmu * (a_ + FT * b_);
+    const double ep = mmu * (a_ + b_);
     acc.gU[1] -= al;
     acc.gV[1] -= be;
     acc.gU[2] -= ga;
     acc.gV[2] -= de;
     acc.gW[3] -= ep;
-    double g4U = uu * al + vv * ga, g4V = uu * be + vv * de, g4W = ww * ep;
-    if (t.flags & FT_C0) {
-      const double v1m = f(FPK_V1M), v2m = f(FPK_V2M), v3m = f(FPK_V3M), v4m = f(FPK_V4M);
-      const double k = sgn * t.c0;
-      g4U += k * mmu * v1m;
-      g4V += k * mmu * v2m;
-      g4W += k * mmu * v3m;
-      acc.gMu[1] -= k * v1m;
-      acc.gMu[2] -= k * v2m;
-      acc.gMu[3] -= k * v3m;
-      acc.gMu[4] -= k * v4m;
-    }
-    acc.gU[4] -= g4U;
-    acc.gV[4] -= g4V;
-    acc.gW[4] -= g4W;
+    acc.gU[4] -= uu * al + vv * ga;
+    acc.gV[4] -= uu * be + vv * de;
+    acc.gW[4] -= ww * ep;
     acc.gT[4] -= c.cpprandtl * ep;
+  }
+  if (t.flags & FT_C0) {
+    const double v1m = f(FPK_V1M), v2m = f(FPK_V2M), v3m = f(FPK_V3M), v4m = f(FPK_V4M);
+    const double k = sgn * t.c0;
+    const double km = k * f.v(FPK_MMU);
+    acc.gU[4] -= km * v1m;
+    acc.gV[4] -= km * v2m;
+    acc.gW[4] -= km * v3m;
+    acc.gMu[1] -= k * v1m;
+    acc.gMu[2] -= k * v2m;
+    acc.gMu[3] -= k * v3m;
+    acc.gMu[4] -= k * v4m;
+  }
+  if (t.flags & FT_LINE) {
+    acc.Nx += sgn * t.cE * nxf;
+    acc.Ny += sgn * t.cE * nyf;
+    acc.diag -= sgn * (f(FPK_RSE2) * t.dd + f(FPK_RSE4) * t.dp);
+  }
+  if (t.side >= 0 || t.pk >= 0 || (t.flags & FT_SENS)) {
+    double se[5];
+#pragma unroll
+    for (int e = 0; e < 5; ++e) se[e] = sgn * f(FPK_SE + e);
+    double eP = 0.0, eU = 0.0, eV = 0.0, eT = 0.0;
+    if (t.pk >= 0) eP = f(FPK_DEP + t.pk);
+    if (t.flags & FT_SENS) {
+      eU = f(FPK_DEG + 0) * t.wIL + f(FPK_DEG + 1) * t.wJL + f(FPK_DEG + 4) * t.wIR + f(FPK_DEG + 5) * t.wJR;
+      eV = f(FPK_DEG + 2) * t.wIL + f(FPK_DEG + 3) * t.wJL + f(FPK_DEG + 6) * t.wIR + f(FPK_DEG + 7) * t.wJR;
+    }
+    if (t.side >= 0) {
+      eT = f(FPK_DET + t.side);
+      double drs[5];
+#pragma unroll
+      for (int m = 0; m < 5; ++m) drs[m] = f(FPK_DRS + t.side * 5 + m);
+#pragma unroll
+      for (int e = 0; e < 5; ++e) {
+        const double sd = sgn * f(FPK_SD + e);
+#pragma unroll
+        for (int m = 0; m < 5; ++m) B[e * 5 + m] -= sd * drs[m];
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 5; ++e) {
+      acc.gP[e] -= se[e] * eP;
+      acc.gU[e] -= se[e] * eU;
+      acc.gV[e] -= se[e] * eV;
+      acc.gT[e] -= se[e] * eT;
+    }
   }
 }
 
 // closed-form chain rule with the column cell (same result as block_finish, which differentiates cell_prims and
 // the flux formulas by forward AD): d(u,v,w,T,p,mu)/d(conservatives) are sparse and cheap by hand.
+// `B` enters holding the conservative-level rank-1 terms (SD x d rspec) and leaves holding the block.
 BC_HD void block_finish_fast(const ColAcc& acc, const double (&wc)[5], const SchemeConsts& c, bool euler, bool needmu, double (&B)[25]) {
   const double ro = wc[0];
   const double r = 1.0 / ro;
@@ -565,11 +589,11 @@ BC_HD void block_finish_fast(const ColAcc& acc, const double (&wc)[5], const Sch
     const double gT = acc.gT[e] + dmu * acc.gMu[e];
     const double kT = gT * kTr + acc.gP[e] * g1;
     const double gU = acc.gU[e], gV = acc.gV[e], gW = acc.gW[e];
-    B[e * 5 + 0] = acc.dir[e][0] - r * (gU * U + gV * V + gW * Wz) + kT * ec - gT * kTr * eloc;
-    B[e * 5 + 1] = acc.dir[e][1] + r * gU - kT * U;
-    B[e * 5 + 2] = acc.dir[e][2] + r * gV - kT * V;
-    B[e * 5 + 3] = acc.dir[e][3] + r * gW - kT * Wz;
-    B[e * 5 + 4] = acc.dir[e][4] + kT;
+    B[e * 5 + 0] += -r * (gU * U + gV * V + gW * Wz) + kT * ec - gT * kTr * eloc;
+    B[e * 5 + 1] += r * gU - kT * U;
+    B[e * 5 + 2] += r * gV - kT * V;
+    B[e * 5 + 3] += r * gW - kT * Wz;
+    B[e * 5 + 4] += kT;
     B[e * 6] += acc.diag;
   }
   if (euler) {
@@ -608,11 +632,13 @@ BC_HD void block_of_rt(const JacTab& J, int s, const FaceCtx& fi0, const FaceCtx
                        const double (&wc)[5], const SchemeConsts& c, double (&B)[25]) {
   ColAcc acc;
   acc.clear();
-  face_contrib_rt(fi0, J.t[s][0], c, -1.0, acc);
-  face_contrib_rt(fi1, J.t[s][1], c, 1.0, acc);
-  face_contrib_rt(fj0, J.t[s][2], c, -1.0, acc);
-  face_contrib_rt(fj1, J.t[s][3], c, 1.0, acc);
-  block_finish_fast(acc, wc, c, J.euler[s] != 0, true, B);
+#pragma unroll
+  for (int q = 0; q < 25; ++q) B[q] = 0.0;
+  face_contrib_rt(fi0, J.t[s][0], c, -1.0, acc, B);
+  face_contrib_rt(fi1, J.t[s][1], c, 1.0, acc, B);
+  face_contrib_rt(fj0, J.t[s][2], c, -1.0, acc, B);
+  face_contrib_rt(fj1, J.t[s][3], c, 1.0, acc, B);
+  block_finish_fast(acc, wc, c, J.euler[s] != 0, J.needmu[s] != 0, B);
 }
 
 }  // namespace bcast

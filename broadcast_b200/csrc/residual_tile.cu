@@ -17,14 +17,18 @@ namespace {
 
 constexpr int H = 3;  // halo width = gh for order 5
 
+// Thread tile TI x TJ: thread (tx,ty) owns cell (i0+tx, j0+ty), evaluates that cell's LEFT i-face and BOTTOM j-face
+// (exactly two face fluxes per thread, no serial tail), and the CTA writes the (TI-1) x (TJ-1) cells whose four faces
+// it holds.  Staged cells: i0-3 .. i0+TI+1, j0-3 .. j0+TJ+1.
 template <int TI, int TJ>
 struct Tile {
-  static constexpr int PI = TI + 2 * H;
-  static constexpr int PJ = TJ + 2 * H;
+  static constexpr int OI = TI - 1, OJ = TJ - 1;  // output cells per CTA
+  static constexpr int PI = TI + 2 * H - 1;
+  static constexpr int PJ = TJ + 2 * H - 1;
   static constexpr int NC = PI * PJ;
   static constexpr int NARR = 16;  // w(5) u v wz T p mu h gu0 gu1 gv0 gv1
   static constexpr int XP = TI + 1;  // exchange pitch
-  static constexpr int NX = 5 * (TJ + 1) * XP;
+  static constexpr int NX = 5 * TJ * XP;
   static constexpr size_t SMEM = (size_t)(NARR * NC + NX) * sizeof(double);
 };
 enum { A_W = 0, A_U = 5, A_V = 6, A_WZ = 7, A_T = 8, A_P = 9, A_MU = 10, A_H = 11, A_G = 12 };
@@ -70,7 +74,7 @@ __global__ void __launch_bounds__(TI* TJ, 2)
   double* X = sm + TL::NARR * NC;
   const int tid = threadIdx.x;
   const int tx = tid % TI, ty = tid / TI;
-  const int i0 = 1 + blockIdx.x * TI, j0 = 1 + blockIdx.y * TJ;
+  const int i0 = 1 + blockIdx.x * TL::OI, j0 = 1 + blockIdx.y * TL::OJ;
   const int im = g.im, jm = g.jm;
   const SchemeConsts c = cst_;
   using Acc = SmemAcc<PI, NC>;
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(TI* TJ, 2)
   __syncthreads();
 
   // ---- stage 2: gradients on interior cells of [i0-1, i0+TI] x [j0-1, j0+TJ] ---------------------
-  constexpr int GI = TI + 2, GJ = TJ + 2;
+  constexpr int GI = TI + 1, GJ = TJ + 1;
   for (int idx = tid; idx < GI * GJ; idx += NT) {
     const int a = idx % GI + (H - 1), b = idx / GI + (H - 1);
     const int ci = i0 - H + a, cj = j0 - H + b;
@@ -148,51 +152,33 @@ __global__ void __launch_bounds__(TI* TJ, 2)
 
   double r[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
 
-  // ---- stage 3a: i-faces ---------------------------------------------------------------------
-#pragma unroll 1
-  for (int rep = 0; rep < 2; ++rep) {
-    int fa, fb;  // face position in tile coordinates (0-based inside the tile)
-    bool act;
-    if (rep == 0) {
-      fa = tx; fb = ty; act = true;
-    } else {  // right-edge faces i = i0+TI, one per row, done by the first TJ threads
-      fa = TI; fb = tid; act = tid < TJ;
-    }
-    const int fi = i0 + fa, fj = j0 + fb;
-    if (act && fi <= im + 1 && fj <= jm) {
-      const Acc A = make_acc(fa + H, fb + H);
+  // ---- stage 3a: i-faces (rows ty < TJ-1) ----------------------------------------------------------
+  {
+    const int fi = i0 + tx, fj = j0 + ty;
+    if (ty < TJ - 1 && fi <= im + 1 && fj <= jm) {
+      const Acc A = make_acc(tx + H, ty + H);
       PVar hn[5];
       if (wall && fj <= 2)
         face_flux<0, true, FACE_MAIN>(A, c, hn);
       else
         face_flux<0, false, FACE_MAIN>(A, c, hn);
 #pragma unroll
-      for (int e = 0; e < 5; ++e) X[(e * (TJ + 1) + fb) * XP + fa] = hn[e].v;
+      for (int e = 0; e < 5; ++e) X[(e * TJ + ty) * XP + tx] = hn[e].v;
     }
   }
   __syncthreads();
-  {
-    const int i = i0 + tx, j = j0 + ty;
-    if (i <= im && j <= jm) {
+  const bool mine = tx < TI - 1 && ty < TJ - 1 && i0 + tx <= im && j0 + ty <= jm;
+  if (mine) {
 #pragma unroll
-      for (int e = 0; e < 5; ++e) r[e] = -(X[(e * (TJ + 1) + ty) * XP + tx + 1] - X[(e * (TJ + 1) + ty) * XP + tx]);
-    }
+    for (int e = 0; e < 5; ++e) r[e] = -(X[(e * TJ + ty) * XP + tx + 1] - X[(e * TJ + ty) * XP + tx]);
   }
   __syncthreads();
 
-  // ---- stage 3b: j-faces ---------------------------------------------------------------------
-#pragma unroll 1
-  for (int rep = 0; rep < 2; ++rep) {
-    int fa, fb;
-    bool act;
-    if (rep == 0) {
-      fa = tx; fb = ty; act = true;
-    } else {  // top-edge faces j = j0+TJ, done by the last row of threads
-      fa = tx; fb = TJ; act = ty == TJ - 1;
-    }
-    const int fi = i0 + fa, fj = j0 + fb;
-    if (act && fi <= im && fj <= jm + 1) {
-      const Acc A = make_acc(fa + H, fb + H);
+  // ---- stage 3b: j-faces (columns tx < TI-1) -------------------------------------------------------
+  {
+    const int fi = i0 + tx, fj = j0 + ty;
+    if (tx < TI - 1 && fi <= im && fj <= jm + 1) {
+      const Acc A = make_acc(tx + H, ty + H);
       PVar hn[5];
       if (wall && fj == 1)
         face_flux<1, true, FACE_WALL>(A, c, hn);
@@ -203,19 +189,16 @@ __global__ void __launch_bounds__(TI* TJ, 2)
       else
         face_flux<1, false, FACE_MAIN>(A, c, hn);
 #pragma unroll
-      for (int e = 0; e < 5; ++e) X[(e * (TJ + 1) + fb) * XP + fa] = hn[e].v;
+      for (int e = 0; e < 5; ++e) X[(e * TJ + ty) * XP + tx] = hn[e].v;
     }
   }
   __syncthreads();
-  {
-    const int i = i0 + tx, j = j0 + ty;
-    if (i <= im && j <= jm) {
-      const long long k = g.cidx(i, j);
+  if (mine) {
+    const long long k = g.cidx(i0 + tx, j0 + ty);
 #pragma unroll
-      for (int e = 0; e < 5; ++e) {
-        const double v = r[e] - (X[(e * (TJ + 1) + ty + 1) * XP + tx] - X[(e * (TJ + 1) + ty) * XP + tx]);
-        res[e * g.sc + k] = v;
-      }
+    for (int e = 0; e < 5; ++e) {
+      const double v = r[e] - (X[(e * TJ + ty + 1) * XP + tx] - X[(e * TJ + ty) * XP + tx]);
+      res[e * g.sc + k] = v;
     }
   }
 }
@@ -234,7 +217,7 @@ cudaError_t launch_residual_tiled(const GridDesc& g, const SchemeArgs& a, bool w
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  dim3 grid((g.im + TI - 1) / TI, (g.jm + TJ - 1) / TJ);
+  dim3 grid((g.im + TL::OI - 1) / TL::OI, (g.jm + TL::OJ - 1) / TL::OJ);
   k_residual_tile<TI, TJ><<<grid, TI * TJ, TL::SMEM, st>>>(g, c, wall, w, nx, ny, vol, volf, res);
   return cudaGetLastError();
 }

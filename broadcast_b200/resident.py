@@ -157,10 +157,12 @@ class Block:
         self.apply_bcs()
         return self.residual()
 
-    def step_from_host(self, w_pinned: torch.Tensor, res_pinned: torch.Tensor):
-        """plugin-level step with HOST buffers: H2D of the state, boundary fill + residual on the
+    def step_from_host(self, w_pinned: torch.Tensor, res_pinned: torch.Tensor, halo=None):
+        """plugin-level step with HOST buffers: H2D of the state, (halo exchange,) boundary fill + residual on the
         device, D2H of the residual.  Geometry and BC tables stay resident (they belong to the mesh)."""
         self.w.copy_(w_pinned, non_blocking=True)
+        if halo is not None:
+            halo(self.w)
         self.step()
         res_pinned.copy_(self.res, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()

@@ -57,13 +57,11 @@ extern "C" int fj_host_blocks_impl(int table_driven, double* values, const doubl
     }
   const long long ncell = (long long)im * jm;
   auto ctx = [&](int dir, int i, int j) {
-    GlobalAcc<0> a(f, g, i, j);
     FaceCtx x;
-    x.nxf = a.template NX<0, 0>(dir);
-    x.nyf = a.template NY<0, 0>(dir);
-    x.dn = dir == 0 ? dual_normals<0>(a) : dual_normals<1>(a);
     x.pk = pkg.data() + (size_t)dir * FPK_N * g.sc + g.cidx(i, j);
     x.stride = g.sc;
+    x.vs = x.pk + (size_t)FPK_VS * g.sc;
+    x.vstride = (int)g.sc;
     return x;
   };
   for (int j = j0; j <= j1; ++j)

@@ -23,6 +23,11 @@ for im, jm in sizes:
     out["residual_ms"] = timed(lambda: blk.residual(), 10)
     blocks = torch.zeros((29, 5, 5, jm, im), dtype=torch.float64, device=blk.device)
     out["hybrid_ms"] = timed(lambda: jacobian_hybrid(blk, blocks=blocks), 2)
+    import ctypes
+    from broadcast_b200.resident import _p
+    out["interior_ms"] = timed(lambda: blk.call("bcd_jacobian_interior", _p(blocks), _p(blk.w), _p(blk.nx), _p(blk.ny), _p(blk.vol), _p(blk.volf),
+                                                 blk.gh, *blk._phys, im, jm, ctypes.c_void_p(None), ctypes.c_void_p(None), blk._stream()), 5)
+    out["interior_GBs_5904"] = 5904.0 * im * jm / (out["interior_ms"] * 1e-3) / 1e9
     if 25 * 49 * im * jm < 2**31 and 25 * 49 * im * jm * 16 < 60e9:
         nb = 25 * 49 * im * jm
         bufs = (torch.zeros(nb, dtype=torch.float64, device=blk.device), torch.zeros(nb, dtype=torch.int32, device=blk.device),
