@@ -129,6 +129,27 @@ def cpu_sample_worker(args):
     return im * jm * steps / dt, dt / steps
 
 
+def cpu_jacobian_colour_seconds(sample=(1024, 512), colours=2):
+    """reference colour pass (seed + 4 linearised boundary fills + tangent; the COO scatter of the reference layout does not
+    fit at this size) on one host core: seconds per colour per cell"""
+    from oracle import refmods
+    from broadcast_b200 import cases
+    R = refmods.make(fast=True)
+    im, jm = sample
+    c = cases.make_bl_case(im, jm, f_geom=R["f_geom"])
+    w = c.w.copy(order="F")
+    cases.apply_bcs(c, w, R["f_bnd"])
+    wd = c.zeros_state()
+    res, resd = c.zeros_state(), c.zeros_state()
+    t0 = time.perf_counter()
+    for n in range(colours):
+        wd *= 0.0
+        R["f_misc"].testvector(wd, n % 5, n % 7, (3 * n) % 7, c.gh, im, jm)
+        cases.apply_bcs_lin(c, w, wd, R["f_bnd"], R["f_lin"])
+        R["f_lin"].flux_num_dnc5_2d_d(res, resd, w, wd, *c.scheme_args())
+    return (time.perf_counter() - t0) / colours / (im * jm)
+
+
 def cpu_baseline(sample=(1024, 512), steps=8, warm=1):
     v, ms = cpu_sample_worker((sample[0], sample[1], steps, warm))
     return {"value": v, "unit": "cell-updates/s", "cores": 1, "kind": "reference",
@@ -300,20 +321,29 @@ def main():
         rp = torch.empty(blk.w.shape, dtype=torch.float64).pin_memory()
         wp.copy_(blk.w.cpu())
         nst = max(3, min(a.steps, 10))
+        if world == 1:
+            # one GPU: the host step is pipelined over 8 i-slabs (H2D of slab k+1 / kernels of slab k / D2H of slab k-1 overlap)
+            from broadcast_b200.resident import StreamedBlock
+            sb = StreamedBlock(case, nslab=8, device=dev)
+            run = lambda: sb.step_from_host(wp, rp)
+            h2d, d2h = sb.bytes_per_step()
+            api = "broadcast_b200.resident.StreamedBlock.step_from_host (pinned host w in, residual out, 8 pipelined i-slabs; mesh metrics resident)"
+        else:
+            run = lambda: blk.step_from_host(wp, rp, halo)
+            h2d = d2h = blk.w.numel() * 8
+            api = "broadcast_b200.resident.Block.step_from_host per rank (pinned host w in, halo exchange, residual out; mesh metrics resident)"
         for _ in range(2):
-            blk.step_from_host(wp, rp, halo)
+            run()
         barrier()
         t0 = time.perf_counter()
         for _ in range(nst):
-            blk.step_from_host(wp, rp, halo)
+            run()
         barrier()
         dt = torch.tensor([(time.perf_counter() - t0) / nst], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        nbytes = blk.w.numel() * 8
-        e2e = {"value": cells_global / float(dt[0]), "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-               "ms_per_step": float(dt[0]) * 1e3,
-               "api": "broadcast_b200.resident.Block.step_from_host (pinned host w in, residual out; mesh metrics resident)"}
+        e2e = {"value": cells_global / float(dt[0]), "unit": "cell-updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": float(dt[0]) * 1e3, "api": api}
 
     if rank == 0:
         line = {
@@ -327,6 +357,12 @@ def main():
         }
         if not a.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline()
+            if jac is not None and "assembly_s" in jac:
+                spc = cpu_jacobian_colour_seconds()
+                jac["cpu_baseline"] = {"value": 245 * spc * cells_global, "unit": "s", "cores": 1, "kind": "reference",
+                                       "sample": "2 colour passes (seed + 4 linearised boundary fills + tangent, no COO scatter) of the C5 "
+                                                 "recipe at 1024x512 on oracle/_ref, extrapolated to 245 colours x 8192x2048 cells: the "
+                                                 "reference's COO layout (329 GB, int32 slots) cannot hold C5"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

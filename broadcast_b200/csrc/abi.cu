@@ -192,6 +192,15 @@ int bcd_slab_begin(int ioff, int im_global, int edges) {
   current_slab() = SlabInfo{ioff, im_global, edges};
   return BC_OK;
 }
+// strided copy between a HOST array and a device array (columns of a Fortran-ordered block = pitched rows):
+// width bytes per row, `height` rows; kind 1 = host -> device, 2 = device -> host; asynchronous on `stream`
+int bcd_memcpy2d(void* dst, long long dpitch, const void* src, long long spitch, long long width, long long height, int kind,
+                 void* stream) {
+  if (kind != 1 && kind != 2) return fail(BC_ERR_ARG, "kind must be 1 (H2D) or 2 (D2H)");
+  cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)width, (size_t)height,
+                                    kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  return e == cudaSuccess ? BC_OK : cuda_fail(e, "bcd_memcpy2d");
+}
 int bcd_slab_end(void) {
   current_slab() = SlabInfo{0, 0, 0};
   return BC_OK;

@@ -101,12 +101,13 @@ BC_HD void face_package(const A& a, const SchemeConsts& c, OUT&& out) {
   const PVar tr = a.template T<0, 0>(), tl = a.template T<AT(-1, 0)>();
 
   // ---- spectral radius: value and gradient w.r.t. the conservative variables of the two face cells
-  const PVar rspec = spectral_radius(cst(wr[0]), cst(wr[1]), cst(wr[2]), tr, cst(wl[0]), cst(wl[1]), cst(wl[2]), tl, nxf, nyf, c);
+  const PVar ur = a.template U<0, 0>(), vr = a.template V<0, 0>(), ul = a.template U<AT(-1, 0)>(), vl = a.template V<AT(-1, 0)>();
+  const PVar rspec = spectral_radius(cst(wr[0]), ur, vr, tr, cst(wl[0]), ul, vl, tl, nxf, nyf, c);
   {
     Var<Tan<5>> q[5];
     seed_cell(wr, q);
     const CellPrims<Tan<5>> pp = cell_prims(q, c);
-    const auto rs = spectral_radius(q[0], q[1], q[2], pp.t, cst(wl[0]), cst(wl[1]), cst(wl[2]), tl, nxf, nyf, c);
+    const auto rs = spectral_radius(q[0], pp.u, pp.v, pp.t, cst(wl[0]), ul, vl, tl, nxf, nyf, c);
 #pragma unroll
     for (int m = 0; m < 5; ++m) out(FPK_DRS + 5 + m, rs.d.d[m]);
   }
@@ -114,7 +115,7 @@ BC_HD void face_package(const A& a, const SchemeConsts& c, OUT&& out) {
     Var<Tan<5>> q[5];
     seed_cell(wl, q);
     const CellPrims<Tan<5>> pp = cell_prims(q, c);
-    const auto rs = spectral_radius(cst(wr[0]), cst(wr[1]), cst(wr[2]), tr, q[0], q[1], q[2], pp.t, nxf, nyf, c);
+    const auto rs = spectral_radius(cst(wr[0]), ur, vr, tr, q[0], pp.u, pp.v, pp.t, nxf, nyf, c);
 #pragma unroll
     for (int m = 0; m < 5; ++m) out(FPK_DRS + m, rs.d.d[m]);
   }
@@ -128,18 +129,15 @@ BC_HD void face_package(const A& a, const SchemeConsts& c, OUT&& out) {
     for (int n = 0; n < 10; ++n) r.d.d[n] = (n == k) ? 1.0 : 0.0;
     return r;
   };
-  struct G10 {
-    Var<T10> u0, u1, v0, v1;
-  };
   const auto g0p = a.template GR<0, 0>();
   const auto g1p = a.template GR<AT(-1, 0)>();
   // directions: 0..3 p(-2..1), 4 T(-1), 5 T(0), 6 divu(-1), 7 vort(-1), 8 divu(0), 9 vort(0)   (vort = gv0 - gu1)
-  const G10 gr1{seed(g1p.u0.v, 6), seed(g1p.u1.v, -1), seed(g1p.v0.v, 7), seed(g1p.v1.v, -1)};
-  const G10 gr0{seed(g0p.u0.v, 8), seed(g0p.u1.v, -1), seed(g0p.v0.v, 9), seed(g0p.v1.v, -1)};
+  const auto sn1 = sens_from_divu_vort(seed((g1p.u0 + g1p.v1).v, 6), seed((g1p.v0 - g1p.u1).v, 7));
+  const auto sn0 = sens_from_divu_vort(seed((g0p.u0 + g0p.v1).v, 8), seed((g0p.v0 - g0p.u1).v, 9));
   const auto c2l = c.gam * c.rgaz * seed(tl.v, 4);
   const auto c2r = c.gam * c.rgaz * seed(tr.v, 5);
   const auto coef = sensor_coef(seed(a.template P<AT(-2, 0)>().v, 0), seed(a.template P<AT(-1, 0)>().v, 1), seed(a.template P<0, 0>().v, 2),
-                                seed(a.template P<AT(1, 0)>().v, 3), gr0, gr1, a.template VOL<0, 0>(), a.template VOL<AT(-1, 0)>(), c2r, c2l,
+                                seed(a.template P<AT(1, 0)>().v, 3), sn0, sn1, a.template VOL<0, 0>(), a.template VOL<AT(-1, 0)>(), c2r, c2l,
                                 nx2);
   const auto eps2 = c.k2 * coef;
   const auto eps4 = fmax(0.0, c.k4 - eps2 * 12.0);

@@ -8,10 +8,11 @@ namespace bcast {
 // primitives over every cell including ghosts (rhs/primvisc.F:2-9)
 // ---------------------------------------------------------------------------------------------
 template <int N>
-__global__ void k_prims(GridDesc g, SchemeConsts c, Rect rc /* storage (0-based) index window, inclusive */,
+__global__ void k_prims(GridDesc g, SchemeConsts c, RectList rl /* storage (0-based) index windows, inclusive */,
                         const double* __restrict__ w, const double* __restrict__ wd, double* __restrict__ prim,
                         double* __restrict__ primd) {
   using DT = TanOf<N>;
+  const Rect rc = rl.r[blockIdx.z];
   const int ii = blockIdx.x * blockDim.x + threadIdx.x + rc.i0;
   const int jj = blockIdx.y * blockDim.y + threadIdx.y + rc.j0;
   if (ii > rc.i1 || jj > rc.j1) return;
@@ -41,8 +42,9 @@ __global__ void k_prims(GridDesc g, SchemeConsts c, Rect rc /* storage (0-based)
 // gradients of velx, vely on interior cells (flux_num_dnc5.F90:124-137)
 // ---------------------------------------------------------------------------------------------
 template <int N>
-__global__ void k_grads(GridDesc g, FieldPtrs f, Rect rc /* interior cells, Fortran indices */, double* __restrict__ grad,
+__global__ void k_grads(GridDesc g, FieldPtrs f, RectList rl /* interior cells, Fortran indices */, double* __restrict__ grad,
                         double* __restrict__ gradd) {
+  const Rect rc = rl.r[blockIdx.z];
   const int i = blockIdx.x * blockDim.x + threadIdx.x + rc.i0;
   const int j = blockIdx.y * blockDim.y + threadIdx.y + rc.j0;
   if (i > rc.i1 || j > rc.j1) return;
@@ -145,10 +147,10 @@ cudaError_t residual_generic_t(const GridDesc& g, const SchemeArgs& a, bool wall
   const Rect rg{max(g.glo(), rc.i0 - 1), min(g.ghi(), rc.i1 + 1), max(1, rc.j0 - 1), min(g.jm, rc.j1 + 1)};
   const Rect rp{max(0, rc.i0 - 5 + g.gh), min(g.ni() - 1, rc.i1 + 3 + g.gh), max(0, rc.j0 - 5 + g.gh), min(g.nj() - 1, rc.j1 + 3 + g.gh)};  // +-4 (wall row 1 reads row 5)
   dim3 gall((rp.i1 - rp.i0 + 32) / 32, (rp.j1 - rp.j0 + 4) / 4);
-  k_prims<N><<<gall, blk, 0, st>>>(g, c, rp, w, wd, prim, primd);
+  k_prims<N><<<gall, blk, 0, st>>>(g, c, one_rect(rp), w, wd, prim, primd);
   FieldPtrs f{w, prim, grad, nx, ny, vol, volf, wd, primd, gradd};
   dim3 gint((rg.i1 - rg.i0 + 32) / 32, (rg.j1 - rg.j0 + 4) / 4);
-  k_grads<N><<<gint, blk, 0, st>>>(g, f, rg, grad, gradd);
+  k_grads<N><<<gint, blk, 0, st>>>(g, f, one_rect(rg), grad, gradd);
   {
     const int nt = g.im + g.jm;
     k_grad_ghost<<<dim3((nt + 127) / 128, NGRAD), 128, 0, st>>>(g, grad, NGRAD);
@@ -276,13 +278,83 @@ cudaError_t BCAST_CAT(dz_generic_, BCAST_N)(const GridDesc& g, const SchemeArgs&
   const Rect rp{max(0, rc.i0 - 3 + g.gh), min(g.ni() - 1, rc.i1 + 1 + g.gh), max(0, rc.j0 - 3 + g.gh), min(g.nj() - 1, rc.j1 + 1 + g.gh)};
   dim3 blk(32, 4);
   dim3 gall((rp.i1 - rp.i0 + 32) / 32, (rp.j1 - rp.j0 + 4) / 4);
-  k_prims<N><<<gall, blk, 0, st>>>(g, c, rp, w, wd, prim, primd);
+  k_prims<N><<<gall, blk, 0, st>>>(g, c, one_rect(rp), w, wd, prim, primd);
   FieldPtrs f{w, prim, nullptr, nx, ny, vol, volf, wd, primd, nullptr};
   dim3 gb((rc.i1 - rc.i0 + 32) / 32, (rc.j1 - rc.j0 + 4) / 4);
   if (which == 1)
     k_dz<N, 1><<<gb, blk, 0, st>>>(g, c, f, rc, out);
   else
     k_dz<N, 2><<<gb, blk, 0, st>>>(g, c, f, rc, out);
+  return cudaGetLastError();
+}
+#endif
+
+#if BCAST_N == 5
+// ---------------------------------------------------------------------------------------------
+// Tangent of the rows of up to four rectangles (the boundary strips of the Jacobian assembly) in ONE pass:
+// block = 32 cells x 4 faces, thread (x, z) evaluates ONE face flux of cell x in 5-direction tangent arithmetic
+// (a quarter of k_balance<5>'s per-thread work and no register spills: the strip launches are latency bound),
+// the four faces of a cell are combined through shared memory exactly as rhs/balance.F does.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_balance_faces5(GridDesc g, SchemeConsts c, FieldPtrs f, bool wall, RectList rl, double* __restrict__ out) {
+  // blockIdx.z = rect * 5 + direction: each thread differentiates ONE face in ONE direction (Tan<1>)
+  __shared__ double sh[4][5][32];
+  const int dir = blockIdx.z % 5;
+  const Rect rc = rl.r[blockIdx.z / 5];
+  const int i = blockIdx.x * 32 + threadIdx.x + rc.i0;
+  const int j = blockIdx.y + rc.j0;
+  const int face = threadIdx.z;
+  const bool act = i <= rc.i1 && j <= rc.j1;
+  // direction `dir` of the 5-direction arrays seen as a 1-direction field set
+  FieldPtrs f1 = f;
+  f1.wd = f.wd + (long long)dir * 5 * g.sc;
+  f1.primd = f.primd + (long long)dir * NPRIM * g.sc;
+  f1.gradd = f.gradd + (long long)dir * NGRAD * g.sc;
+  if (act) {
+    Var<Tan<1>> hn[5];
+    if (face == 0) face_dispatch<1, 0>(f1, g, c, wall, i, j, hn);
+    else if (face == 1) face_dispatch<1, 0>(f1, g, c, wall, i + 1, j, hn);
+    else if (face == 2) face_dispatch<1, 1>(f1, g, c, wall, i, j, hn);
+    else face_dispatch<1, 1>(f1, g, c, wall, i, j + 1, hn);
+#pragma unroll
+    for (int e = 0; e < 5; ++e) sh[face][e][threadIdx.x] = hn[e].d.d[0];
+  }
+  __syncthreads();
+  if (!act) return;
+  const long long k = g.cidx(i, j);
+  for (int e = face; e < 5; e += 4) {
+    const double r = -(sh[1][e][threadIdx.x] - sh[0][e][threadIdx.x]) - (sh[3][e][threadIdx.x] - sh[2][e][threadIdx.x]);
+    out[(long long)(dir * 5 + e) * g.sc + k] = r;
+  }
+}
+
+cudaError_t tangent_strips_5(const GridDesc& g, const SchemeArgs& a, bool wall, const RectList& rows, double* out5, const double* w,
+                             const double* wd5, const double* nx, const double* ny, const double* vol, const double* volf, cudaStream_t st) {
+  constexpr int N = 5;
+  const SchemeConsts c = make_consts(a.cp, a.cv, a.prandtl, a.gam, a.rgaz, a.cs, a.muref, a.tref, a.s_suth, a.k2, a.k4);
+  double* prim = scratch_doubles(0, (size_t)g.sc * NPRIM);
+  double* grad = scratch_doubles(1, (size_t)g.sc * NGRAD);
+  double* primd = scratch_doubles(2, (size_t)g.sc * NPRIM * N);
+  double* gradd = scratch_doubles(3, (size_t)g.sc * NGRAD * N);
+  if (!prim || !grad || !primd || !gradd) return cudaErrorMemoryAllocation;
+  RectList rg = rows, rp = rows;
+  for (int k = 0; k < rows.n; ++k) {
+    const Rect rc = rows.r[k];
+    rg.r[k] = Rect{max(g.glo(), rc.i0 - 1), min(g.ghi(), rc.i1 + 1), max(1, rc.j0 - 1), min(g.jm, rc.j1 + 1)};
+    rp.r[k] = Rect{max(0, rc.i0 - 5 + g.gh), min(g.ni() - 1, rc.i1 + 3 + g.gh), max(0, rc.j0 - 5 + g.gh), min(g.nj() - 1, rc.j1 + 3 + g.gh)};
+  }
+  dim3 blk(32, 4);
+  for_each_rect(rp, [&](const RectList& r1, int) { k_prims<N><<<grid_of(r1, 32, 4), blk, 0, st>>>(g, c, r1, w, wd5, prim, primd); });
+  FieldPtrs f{w, prim, grad, nx, ny, vol, volf, wd5, primd, gradd};
+  for_each_rect(rg, [&](const RectList& r1, int) { k_grads<N><<<grid_of(r1, 32, 4), blk, 0, st>>>(g, f, r1, grad, gradd); });
+  const int nt = g.im + g.jm;
+  k_grad_ghost<<<dim3((nt + 127) / 128, NGRAD), 128, 0, st>>>(g, grad, NGRAD);
+  k_grad_ghost<<<dim3((nt + 127) / 128, NGRAD * N), 128, 0, st>>>(g, gradd, NGRAD * N);
+  for_each_rect(rows, [&](const RectList& r1, int) {
+    dim3 gb = grid_of(r1, 32, 1);
+    gb.z = 5;
+    k_balance_faces5<<<gb, dim3(32, 1, 4), 0, st>>>(g, c, f, wall, r1, out5);
+  });
   return cudaGetLastError();
 }
 #endif
@@ -297,10 +369,10 @@ cudaError_t prepare_prims_grads(const GridDesc& g, const SchemeArgs& a, const do
   if (!prim || !grad) return cudaErrorMemoryAllocation;
   dim3 blk(32, 4);
   dim3 gall((g.ni() + 31) / 32, (g.nj() + 3) / 4);
-  k_prims<0><<<gall, blk, 0, st>>>(g, c, Rect{0, g.ni() - 1, 0, g.nj() - 1}, w, nullptr, prim, nullptr);
+  k_prims<0><<<gall, blk, 0, st>>>(g, c, one_rect(Rect{0, g.ni() - 1, 0, g.nj() - 1}), w, nullptr, prim, nullptr);
   f = FieldPtrs{w, prim, grad, nx, ny, vol, volf, nullptr, nullptr, nullptr};
   dim3 gint((g.im + 2 + 31) / 32, (g.jm + 3) / 4);
-  k_grads<0><<<gint, blk, 0, st>>>(g, f, Rect{g.glo(), g.ghi(), 1, g.jm}, grad, nullptr);
+  k_grads<0><<<gint, blk, 0, st>>>(g, f, one_rect(Rect{g.glo(), g.ghi(), 1, g.jm}), grad, nullptr);
   k_grad_ghost<<<dim3((g.im + g.jm + 127) / 128, NGRAD), 128, 0, st>>>(g, grad, NGRAD);
   return cudaGetLastError();
 }

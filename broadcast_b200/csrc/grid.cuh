@@ -111,6 +111,7 @@ struct GlobalAcc {
     struct R { Var<DT> u0, u1, v0, v1; };
     return R{GU<OI, OJ>(0), GU<OI, OJ>(1), GV<OI, OJ>(0), GV<OI, OJ>(1)};
   }
+  template <int OI, int OJ> BC_HD auto SENS() const;   // defined in scheme.cuh (needs sens_from_grad)
   template <int OI, int OJ> BC_HD double NX(int k) const { return BC_LDG(f.nx + k * sn + nk<OI, OJ>()); }
   template <int OI, int OJ> BC_HD double NY(int k) const { return BC_LDG(f.ny + k * sn + nk<OI, OJ>()); }
   template <int OI, int OJ> BC_HD double VOL() const { return BC_LDG(f.vol + ck<OI, OJ>()); }

@@ -59,6 +59,7 @@ struct PrunedAcc {
     else
       return g.template GR<OI, OJ>();
   }
+  template <int OI, int OJ> __device__ __forceinline__ auto SENS() const { return sens_from_grad(GR<OI, OJ>()); }
   template <int OI, int OJ> __device__ __forceinline__ double NX(int k) const { return g.template NX<OI, OJ>(k); }
   template <int OI, int OJ> __device__ __forceinline__ double NY(int k) const { return g.template NY<OI, OJ>(k); }
   template <int OI, int OJ> __device__ __forceinline__ double VOL() const { return g.template VOL<OI, OJ>(); }

@@ -140,7 +140,8 @@ extern "C" int bcd_jacobian_coo(double* jac, int32_t* ia, int32_t* ja, double* w
   // side of the block (periodic cut): then every seed matters
   bool has_join = false;
   for (int b = 0; b < nbcs; ++b) has_join = has_join || bcs[b].kind == BC_KIND_JOIN;
-  const Rect* seed_rows = (rect && !has_join) ? &rc : nullptr;
+  const RectList seed_list = one_rect(rc);
+  const RectList* seed_rows = (rect && !has_join) ? &seed_list : nullptr;
   for (int l = 0; l < s; ++l)
     for (int k = 0; k < s; ++k) {
       cudaError_t e = launch_testvector(g, wd5, 5, 0, l, k, nullptr, st, seed_rows);
@@ -192,6 +193,52 @@ extern "C" int bcd_dz_coo(double* jac1, int32_t* ia1, int32_t* ja1, double* jac2
         count_launches(1);
       }
       count_launches(1);
+    }
+  return BC_OK;
+}
+
+// The boundary strips of the Jacobian (rows within gh of a physical side) by the reference colour loop, all strips in
+// the SAME 49 passes: seeds (windows of the strips only) -> linearised boundary fills -> tangent of the strip rows with
+// one thread per (cell, face) -> scatter into one compact COO triple per strip (slot order of
+// misc/ComputeJacobian.f90:524 over the strip's own index space, ia/ja global).
+extern "C" int bcd_jacobian_strips(int nrect, const int32_t* rects /* [nrect][4] i0,i1,j0,j1 */, double* const* jac, int32_t* const* ia,
+                                   int32_t* const* ja, double* w, const double* nx, const double* ny, const double* vol, const double* volf,
+                                   int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs, double muref,
+                                   double tref, double s_suth, double k2, double k4, int im, int jm, int wall, const bc_desc_t* bcs,
+                                   int nbcs, int scatter_kind, const double* coefdiag, void* stream) {
+  if (im < 1 || jm < 1 || gh != 3 || nrect < 0 || nrect > 4) return BC_ERR_ARG;
+  if (scatter_kind < 0 || scatter_kind > 6) return BC_ERR_ARG;
+  if (nrect == 0) return BC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const GridDesc g = make_grid_ctx(im, jm, gh);
+  const SchemeArgs a{cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4};
+  const int s = 2 * gh + 1;
+  double* wd5 = scratch_doubles(20, (size_t)g.sc * 25);
+  double* resd5 = scratch_doubles(21, (size_t)g.sc * 25);
+  if (!wd5 || !resd5) return BC_ERR_ALLOC;
+  RectList rows;
+  rows.n = nrect;
+  for (int q = 0; q < 4; ++q) rows.r[q] = q < nrect ? Rect{rects[4 * q], rects[4 * q + 1], rects[4 * q + 2], rects[4 * q + 3]} : Rect{1, 0, 1, 0};
+  for (int q = 0; q < nrect; ++q)
+    if (rows.r[q].i1 < rows.r[q].i0 || rows.r[q].j1 < rows.r[q].j0) return BC_ERR_ARG;
+  bool has_join = false;
+  for (int b = 0; b < nbcs; ++b) has_join = has_join || bcs[b].kind == BC_KIND_JOIN;
+  for (int l = 0; l < s; ++l)
+    for (int k = 0; k < s; ++k) {
+      cudaError_t e = launch_testvector(g, wd5, 5, 0, l, k, nullptr, st, has_join ? nullptr : &rows);
+      if (e != cudaSuccess) return (int)e;
+      e = apply_bc_list(g, gam, 5, w, wd5, nx, ny, bcs, nbcs, st);
+      if (e != cudaSuccess) return (int)e;
+      e = launch_tangent_strips5(g, a, wall != 0, rows, resd5, w, wd5, nx, ny, vol, volf, st);
+      if (e != cudaSuccess) return (int)e;
+      for (int q = 0; q < nrect; ++q) {
+        const Rect rc = rows.r[q];
+        const long long nt = 5LL * (rc.i1 - rc.i0 + 1) * (rc.j1 - rc.j0 + 1);
+        k_scatter5<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(g, scatter_kind, jac[q], ia[q], ja[q], resd5, l, k, coefdiag, vol, rc, 1);
+      }
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return (int)e;
+      count_launches(6 + nrect);
     }
   return BC_OK;
 }

@@ -57,6 +57,14 @@ cudaError_t residual_generic_1(const GridDesc&, const SchemeArgs&, bool, double*
 cudaError_t residual_generic_5(const GridDesc&, const SchemeArgs&, bool, double*, const double*, const double*, const double*,
                                const double*, const double*, const double*, const Rect*, cudaStream_t);
 
+cudaError_t tangent_strips_5(const GridDesc&, const SchemeArgs&, bool, const RectList&, double*, const double*, const double*, const double*,
+                             const double*, const double*, const double*, cudaStream_t);
+cudaError_t launch_tangent_strips5(const GridDesc& g, const SchemeArgs& a, bool wall, const RectList& rows, double* out5, const double* w,
+                                   const double* wd5, const double* nx, const double* ny, const double* vol, const double* volf,
+                                   cudaStream_t st) {
+  return tangent_strips_5(g, a, wall, rows, out5, w, wd5, nx, ny, vol, volf, st);
+}
+
 cudaError_t launch_residual_generic(const GridDesc& g, const SchemeArgs& a, bool wall, int ndir, double* out, const double* w,
                                     const double* wd, const double* nx, const double* ny, const double* vol, const double* volf,
                                     const Rect* rect, cudaStream_t st) {
@@ -157,7 +165,8 @@ cudaError_t launch_jn_match(double* wr, const Window& r, const int prr[4], const
 // variable n (vector mode), m ignored.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_testvector(GridDesc g, double* __restrict__ wd, int ndir, int m, int l, int k, int is, int ie, int js, int je,
-                             Rect win /* storage index window that is written */) {
+                             RectList wins /* storage index windows that are written */) {
+  const Rect win = wins.r[blockIdx.z];
   const int ii = blockIdx.x * blockDim.x + threadIdx.x + win.i0;
   const int jj = blockIdx.y * blockDim.y + threadIdx.y + win.j0;
   if (ii > win.i1 || jj > win.j1) return;
@@ -176,13 +185,16 @@ __global__ void k_testvector(GridDesc g, double* __restrict__ wd, int ndir, int 
 }
 
 cudaError_t launch_testvector(const GridDesc& g, double* wd, int ndir, int m, int l, int k, const int* zone, cudaStream_t st,
-                              const Rect* rows) {
+                              const RectList* rows) {
   // rows (optional): only the cells a tangent restricted to these rows can read are (re)written
-  Rect win{0, g.ni() - 1, 0, g.nj() - 1};
-  if (rows)
-    win = Rect{max(0, rows->i0 - 5 + g.gh), min(g.ni() - 1, rows->i1 + 3 + g.gh), max(0, rows->j0 - 5 + g.gh),
-               min(g.nj() - 1, rows->j1 + 3 + g.gh)};
-  dim3 blk(32, 4), grd((win.i1 - win.i0 + 32) / 32, (win.j1 - win.j0 + 4) / 4);
+  RectList win = one_rect(Rect{0, g.ni() - 1, 0, g.nj() - 1});
+  if (rows) {
+    win = *rows;
+    for (int q = 0; q < rows->n; ++q)
+      win.r[q] = Rect{max(0, rows->r[q].i0 - 5 + g.gh), min(g.ni() - 1, rows->r[q].i1 + 3 + g.gh), max(0, rows->r[q].j0 - 5 + g.gh),
+                      min(g.nj() - 1, rows->r[q].j1 + 3 + g.gh)};
+  }
+  dim3 blk(32, 4);
   int is = 0, ie = g.img, js = 0, je = g.jm;
   if (zone) {  // testvector_partial: i = istart+l+1 .. iend+1, j = jstart+k+1 .. jend+1
     is = zone[0];
@@ -190,7 +202,7 @@ cudaError_t launch_testvector(const GridDesc& g, double* wd, int ndir, int m, in
     js = zone[2];
     je = zone[3] + 1;
   }
-  k_testvector<<<grd, blk, 0, st>>>(g, wd, ndir, m, l, k, is, ie, js, je, win);
+  for_each_rect(win, [&](const RectList& w1, int) { k_testvector<<<grid_of(w1, 32, 4), blk, 0, st>>>(g, wd, ndir, m, l, k, is, ie, js, je, w1); });
   return cudaGetLastError();
 }
 

@@ -35,6 +35,32 @@ struct SchemeArgs {
 struct Rect {
   int i0, i1, j0, j1;
 };
+// up to four rectangles handled by one launch (blockIdx.z selects the rectangle)
+struct RectList {
+  int n;
+  Rect r[4];
+};
+inline RectList one_rect(const Rect& r) {
+  RectList l;
+  l.n = 1;
+  l.r[0] = r;
+  l.r[1] = l.r[2] = l.r[3] = Rect{1, 0, 1, 0};
+  return l;
+}
+inline dim3 grid_of(const RectList& l, int bx, int by) {   // grid covering the largest rectangle, one z-slice per rectangle
+  int wi = 1, wj = 1;
+  for (int k = 0; k < l.n; ++k) {
+    wi = l.r[k].i1 - l.r[k].i0 + 1 > wi ? l.r[k].i1 - l.r[k].i0 + 1 : wi;
+    wj = l.r[k].j1 - l.r[k].j0 + 1 > wj ? l.r[k].j1 - l.r[k].j0 + 1 : wj;
+  }
+  return dim3((wi + bx - 1) / bx, (wj + by - 1) / by, l.n);
+}
+// Rectangles of very different shapes (the boundary strips: im x gh and gh x jm) are launched one by one instead:
+// a common grid would be (im/bx) x (jm/by) blocks, almost all of them empty.
+template <class F>
+inline void for_each_rect(const RectList& l, F&& launch) {
+  for (int k = 0; k < l.n; ++k) launch(one_rect(l.r[k]), k);
+}
 
 // Generic ("reference-shaped") residual and tangent: prims -> gradients (+ ghost-layer extrapolation)
 // -> cell-centred balance of four face fluxes.  ndir == 0: residual into `out` (5 planes, interior
@@ -62,7 +88,11 @@ cudaError_t launch_jn_match(double* wr, const Window& r, const int prr[4], const
 
 // colouring seeds and COO scatter (misc/ComputeJacobian.f90)
 cudaError_t launch_testvector(const GridDesc& g, double* wd, int ndir, int m, int l, int k, const int* zone /*null or istart,iend,jstart,jend*/,
-                              cudaStream_t st, const Rect* rows = nullptr);
+                              cudaStream_t st, const RectList* rows = nullptr);
+// tangent (5 directions) of the rows of up to four rectangles in one pass; one thread per (cell, face)
+cudaError_t launch_tangent_strips5(const GridDesc& g, const SchemeArgs& a, bool wall, const RectList& rows, double* out5, const double* w,
+                                   const double* wd5, const double* nx, const double* ny, const double* vol, const double* volf,
+                                   cudaStream_t st);
 enum ScatterKind {
   SCATTER_JV = 0,            // computejacobianfromjv            :292-355
   SCATTER_JV_RELAXED = 1,    // computejacobianfromjv_relaxed    :503-570

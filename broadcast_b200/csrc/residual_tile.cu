@@ -26,7 +26,7 @@ struct Tile {
   static constexpr int PI = TI + 2 * H - 1;
   static constexpr int PJ = TJ + 2 * H - 1;
   static constexpr int NC = PI * PJ;
-  static constexpr int NARR = 16;  // w(5) u v wz T p mu h gu0 gu1 gv0 gv1
+  static constexpr int NARR = 14;  // w(5) u v wz T p mu h divu ducros
   static constexpr int XP = TI + 1;  // exchange pitch
   static constexpr int NX = 5 * TJ * XP;
   static constexpr size_t SMEM = (size_t)(NARR * NC + NX) * sizeof(double);
@@ -51,12 +51,8 @@ struct SmemAcc {
   template <int OI, int OJ> __device__ __forceinline__ PVar P() const { return ld<OI, OJ>(A_P); }
   template <int OI, int OJ> __device__ __forceinline__ PVar Mu() const { return ld<OI, OJ>(A_MU); }
   template <int OI, int OJ> __device__ __forceinline__ PVar H() const { return ld<OI, OJ>(A_H); }
-  template <int OI, int OJ> __device__ __forceinline__ PVar GU(int cc) const { return ld<OI, OJ>(A_G + cc); }
-  template <int OI, int OJ> __device__ __forceinline__ PVar GV(int cc) const { return ld<OI, OJ>(A_G + 2 + cc); }
-  template <int OI, int OJ> __device__ __forceinline__ auto GR() const {
-    struct R { PVar u0, u1, v0, v1; };
-    return R{GU<OI, OJ>(0), GU<OI, OJ>(1), GV<OI, OJ>(0), GV<OI, OJ>(1)};
-  }
+  // per-cell sensor quantities precomputed in stage 2: dilatation and Ducros ratio
+  template <int OI, int OJ> __device__ __forceinline__ auto SENS() const { return CellSens<Zero, Zero>{ld<OI, OJ>(A_G), ld<OI, OJ>(A_G + 1)}; }
   template <int OI, int OJ> __device__ __forceinline__ double NX(int kk) const { return __ldg(nx + kk * sn + n + OI + (long long)OJ * ldn); }
   template <int OI, int OJ> __device__ __forceinline__ double NY(int kk) const { return __ldg(ny + kk * sn + n + OI + (long long)OJ * ldn); }
   template <int OI, int OJ> __device__ __forceinline__ double VOL() const { return __ldg(vol + c + OI + (long long)OJ * ldc); }
@@ -64,7 +60,7 @@ struct SmemAcc {
 };
 
 template <int TI, int TJ>
-__global__ void __launch_bounds__(TI* TJ, 2)
+__global__ void __launch_bounds__(TI* TJ, 3)
     k_residual_tile(GridDesc g, SchemeConsts cst_, bool wall, const double* __restrict__ w, const double* __restrict__ nx,
                     const double* __restrict__ ny, const double* __restrict__ vol, const double* __restrict__ volf,
                     double* __restrict__ res) {
@@ -123,10 +119,8 @@ __global__ void __launch_bounds__(TI* TJ, 2)
     if (ci >= g.glo() && ci <= g.ghi() && cj >= 1 && cj <= jm) {   // slab-internal edges: real gradients in the halo column
       const Acc A = make_acc(a, b);
       const auto r = cell_gradients<0, 0>(A);
-      sm[(A_G + 0) * NC + A.k] = r.u0.v;
-      sm[(A_G + 1) * NC + A.k] = r.u1.v;
-      sm[(A_G + 2) * NC + A.k] = r.v0.v;
-      sm[(A_G + 3) * NC + A.k] = r.v1.v;
+      sm[(A_G + 0) * NC + A.k] = (r.u0 + r.v1).v;   // dilatation
+      sm[(A_G + 1) * NC + A.k] = (r.v0 - r.u1).v;   // vorticity (replaced by the Ducros ratio below)
     }
   }
   __syncthreads();
@@ -143,10 +137,18 @@ __global__ void __launch_bounds__(TI* TJ, 2)
       if (cj == 0) d = PI;
       else if (cj == jm + 1) d = -PI;
     }
-    if (d != 0) {
+    if (d != 0) {   // divu and vort are linear in the gradients: extrapolating them = extrapolating the gradients
 #pragma unroll
-      for (int q = 0; q < 4; ++q) sm[(A_G + q) * NC + k] = 2.0 * sm[(A_G + q) * NC + k + d] - sm[(A_G + q) * NC + k + 2 * d];
+      for (int q = 0; q < 2; ++q) sm[(A_G + q) * NC + k] = 2.0 * sm[(A_G + q) * NC + k + d] - sm[(A_G + q) * NC + k + 2 * d];
     }
+  }
+  __syncthreads();
+  // Ducros ratio of every sensor cell (once per cell instead of once per face side)
+  for (int idx = tid; idx < GI * GJ; idx += NT) {
+    const int a = idx % GI + (H - 1), b = idx / GI + (H - 1);
+    const int k = a + b * PI;
+    const auto cs = sens_from_divu_vort(PVar{sm[A_G * NC + k], {}}, PVar{sm[(A_G + 1) * NC + k], {}});
+    sm[(A_G + 1) * NC + k] = cs.ducros.v;
   }
   __syncthreads();
 

@@ -15,6 +15,7 @@
 // Fortran to rounding of FMA contraction only.
 #pragma once
 #include "dual.cuh"
+#include "grid.cuh"
 
 namespace bcast {
 
@@ -247,15 +248,12 @@ BC_HD auto visc_stress(const VS& s, const SchemeConsts& c) {
   return r;
 }
 
-// Roe-averaged spectral radius of a face (spectralradius_{i,j}.F); r = right (face cell), l = left
+// Roe-averaged spectral radius of a face (spectralradius_{i,j}.F); r = right (face cell), l = left.
+// The cell velocities are taken from the primitives (w * (1/rho); the reference divides w by rho again here: 1 ulp).
 template <class R0, class R1, class R2, class TR, class L0, class L1, class L2, class TL>
-BC_HD auto spectral_radius(Var<R0> rhomr, Var<R1> w1r, Var<R2> w2r, Var<TR> tr, Var<L0> rhoml, Var<L1> w1l, Var<L2> w2l, Var<TL> tl,
+BC_HD auto spectral_radius(Var<R0> rhomr, Var<R1> ur, Var<R2> vr, Var<TR> tr, Var<L0> rhoml, Var<L1> ul, Var<L2> vl, Var<TL> tl,
                            double nxf, double nyf, const SchemeConsts& c) {
-  auto ur = w1r / rhomr;
-  auto vr = w2r / rhomr;
   auto c2r = c.gam * c.rgaz * tr;
-  auto ul = w1l / rhoml;
-  auto vl = w2l / rhoml;
   auto c2l = c.gam * c.rgaz * tl;
   auto r = sqrt(rhomr / rhoml);
   auto rr = 1.0 / (1.0 + r);
@@ -269,31 +267,45 @@ BC_HD auto spectral_radius(Var<R0> rhomr, Var<R1> w1r, Var<R2> w2r, Var<TR> tr, 
   return ab + sq;
 }
 
+// per-cell part of the sensor: dilatation and the Ducros ratio from the velocity gradients (ducrosfordnc_{i,j}.F)
+template <class DV, class DU>
+struct CellSens {
+  Var<DV> divu;
+  Var<DU> ducros;
+};
+template <class A, class B>
+BC_HD auto sens_from_divu_vort(Var<A> divu, Var<B> vort) {
+  auto divu2 = divu * divu;
+  auto vort2 = vort * vort;
+  auto ducros = divu2 / (divu2 + vort2 + 1e-15);
+  return CellSens<A, decltype(ducros.d)>{divu, ducros};
+}
+template <class G>
+BC_HD auto sens_from_grad(const G& gr) {
+  return sens_from_divu_vort(gr.u0 + gr.v1, gr.v0 - gr.u1);
+}
+
 // Jameson pressure sensor x Ducros x dilatation switch (ducrosfordnc_{i,j}.F): the factor `coef` of eps2.
-// gr0 / gr1: velocity gradients (u0,u1,v0,v1) of the face cell and of its along-neighbour -1.
-template <class P2, class P1, class P0, class PP, class G0, class G1, class C0, class C1>
-BC_HD auto sensor_coef(Var<P2> p_m2, Var<P1> p_m1, Var<P0> p_0, Var<PP> p_p1, const G0& gr0, const G1& gr1, double vol0, double vol1,
+// s0 / s1: CellSens of the face cell and of its along-neighbour -1.  The dilatation switch
+// dxm = (1 - tanh(x)) / 2 is decreasing in x, so max(dxm0, dxm1) is evaluated as ONE tanh of the smaller argument
+// (same branch rule as the reference's max: the second operand is taken iff the first is smaller).
+template <class P2, class P1, class P0, class PP, class S0, class S1, class C0, class C1>
+BC_HD auto sensor_coef(Var<P2> p_m2, Var<P1> p_m1, Var<P0> p_0, Var<PP> p_p1, const S0& s0, const S1& s1, double vol0, double vol1,
                        Var<C0> c2r, Var<C1> c2l, double nx2) {
   auto k_sensor1 = fabs(p_m1 - 2.0 * p_0 + p_p1) / fabs(p_m1 + 2.0 * p_0 + p_p1);
   auto k_sensor2 = fabs(p_m2 - 2.0 * p_m1 + p_0) / fabs(p_m2 + 2.0 * p_m1 + p_0);
-  auto sens_cell = [&](auto gr, double vol, auto c2, auto& ducros, auto& dxm) {
-    auto divu = gr.u0 + gr.v1;
-    auto divu2 = divu * divu;
-    auto vort2 = (gr.v0 - gr.u1) * (gr.v0 - gr.u1);
-    ducros = divu2 / (divu2 + vort2 + 1e-15);
-    dxm = 0.5 * (1.0 - tanh(2.5 + 10.0 * vol / (sqrt(c2 * nx2) + 1e-15) * divu));
-  };
-  using GD0 = decltype(gr0.u0.d);
-  using GD1 = decltype(gr1.u0.d);
-  using SD0 = decltype((gr0.u0 * c2r).d);
-  using SD1 = decltype((gr1.u0 * c2l).d);
-  Var<GD0> ducros1;
-  Var<SD0> dxm1;
-  Var<GD1> ducros2;
-  Var<SD1> dxm2;
-  sens_cell(gr0, vol0, c2r, ducros1, dxm1);
-  sens_cell(gr1, vol1, c2l, ducros2, dxm2);
-  return fmax(k_sensor1, k_sensor2) * fmax(ducros1, ducros2) * fmax(dxm1, dxm2);
+  auto x0 = 2.5 + 10.0 * vol0 / (sqrt(c2r * nx2) + 1e-15) * s0.divu;
+  auto x1 = 2.5 + 10.0 * vol1 / (sqrt(c2l * nx2) + 1e-15) * s1.divu;
+  const bool take1 = x0.v > x1.v;   // dxm(x0) < dxm(x1)
+  const Var<decltype(t_sel(take1, x1.d, x0.d))> xs{take1 ? x1.v : x0.v, t_sel(take1, x1.d, x0.d)};
+  auto dxm = 0.5 * (1.0 - tanh(xs));
+  return fmax(k_sensor1, k_sensor2) * fmax(s0.ducros, s1.ducros) * dxm;
+}
+
+template <int N>
+template <int OI, int OJ>
+BC_HD auto GlobalAcc<N>::SENS() const {
+  return sens_from_grad(GR<OI, OJ>());
 }
 
 enum FaceMode { FACE_MAIN = 0, FACE_NEAR5 = 1, FACE_NEAR3 = 2, FACE_WALL = 3 };
@@ -346,8 +358,8 @@ BC_HD void face_flux(const A& a, const SchemeConsts& c, Var<RD> (&hn)[5]) {
     const auto vs = visc_stress(vsc, c);
 
     // ---- scalar dissipation: Roe spectral radius (spectralradius_{i,j}.F) -------------------------
-    auto rspec = spectral_radius(a.template W<0, 0>(0), a.template W<0, 0>(1), a.template W<0, 0>(2), a.template T<0, 0>(),
-                                 a.template W<AT(-1, 0)>(0), a.template W<AT(-1, 0)>(1), a.template W<AT(-1, 0)>(2),
+    auto rspec = spectral_radius(a.template W<0, 0>(0), a.template U<0, 0>(), a.template V<0, 0>(), a.template T<0, 0>(),
+                                 a.template W<AT(-1, 0)>(0), a.template U<AT(-1, 0)>(), a.template V<AT(-1, 0)>(),
                                  a.template T<AT(-1, 0)>(), nxf, nyf, c);
     const double nx2 = nxf * nxf + nyf * nyf;
 
@@ -355,7 +367,7 @@ BC_HD void face_flux(const A& a, const SchemeConsts& c, Var<RD> (&hn)[5]) {
     auto c2r = c.gam * c.rgaz * a.template T<0, 0>();
     auto c2l = c.gam * c.rgaz * a.template T<AT(-1, 0)>();
     auto coef = sensor_coef(a.template P<AT(-2, 0)>(), a.template P<AT(-1, 0)>(), a.template P<AT(0, 0)>(), a.template P<AT(1, 0)>(),
-                            a.template GR<0, 0>(), a.template GR<AT(-1, 0)>(), a.template VOL<0, 0>(), a.template VOL<AT(-1, 0)>(),
+                            a.template SENS<0, 0>(), a.template SENS<AT(-1, 0)>(), a.template VOL<0, 0>(), a.template VOL<AT(-1, 0)>(),
                             c2r, c2l, nx2);
     auto eps2 = c.k2 * coef;
     auto eps4 = fmax(0.0, c.k4 - eps2 * 12.0);

@@ -168,6 +168,56 @@ class Block:
         torch.cuda.current_stream(self.device).synchronize()
 
 
+class StreamedBlock:
+    """Plugin-level residual step on HOST buffers, pipelined over ``nslab`` i-slabs of the block on ONE GPU: the pitched
+    host-to-device copy of slab k+1 (its columns plus gh halo columns straight from the host array) and the
+    device-to-host copy of slab k-1's residual overlap the boundary fill + residual kernels of slab k (three streams,
+    both copy engines busy).  Same results as ``Block.step_from_host`` (slab-internal edges compute their gradients)."""
+
+    def __init__(self, case: Case, nslab: int = 8, device="cuda:0"):
+        from . import sharding
+        self.case, self.device = case, torch.device(device)
+        self.gh, self.im, self.jm = case.gh, case.im, case.jm
+        self.slabs = []
+        for k in range(nslab):
+            sl, desc = sharding.slab_of(case, k, nslab)
+            lo, hi = sharding.slab_range(case.im, k, nslab)
+            self.slabs.append((Block(sl, device, slab=desc if nslab > 1 else None), lo, hi))
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(min(3, nslab))]
+        self.lib = _lib.lib()
+
+    def bytes_per_step(self):
+        nj = self.jm + 2 * self.gh
+        h2d = sum((b.im + 2 * self.gh) * nj * 5 * 8 for b, _, _ in self.slabs)
+        d2h = sum(b.im * nj * 5 * 8 for b, _, _ in self.slabs)
+        return h2d, d2h
+
+    def step_from_host(self, w_pinned: torch.Tensor, res_pinned: torch.Tensor):
+        """``w_pinned`` / ``res_pinned``: pinned host tensors (5, jm+2gh, im+2gh) = memory image of the Fortran arrays"""
+        gh, nj, ni = self.gh, self.jm + 2 * self.gh, self.im + 2 * self.gh
+        rows = 5 * nj
+        main = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            s.wait_stream(main)
+        for k, (b, lo, hi) in enumerate(self.slabs):
+            st = self.streams[k % len(self.streams)]
+            with torch.cuda.stream(st):
+                sp = ctypes.c_void_p(st.cuda_stream)
+                nl = b.im + 2 * gh
+                src = w_pinned.data_ptr() + (lo - 1) * 8                      # storage column of cell lo-gh
+                _lib.check(self.lib.bcd_memcpy2d(_p(b.w), ctypes.c_longlong(nl * 8), ctypes.c_void_p(src), ctypes.c_longlong(ni * 8),
+                                                 ctypes.c_longlong(nl * 8), ctypes.c_longlong(rows), 1, sp), "bcd_memcpy2d")
+                b.apply_bcs()
+                b.residual()
+                dst = res_pinned.data_ptr() + (lo - 1 + gh) * 8               # owned columns only
+                _lib.check(self.lib.bcd_memcpy2d(ctypes.c_void_p(dst), ctypes.c_longlong(ni * 8), ctypes.c_void_p(b.res.data_ptr() + gh * 8),
+                                                 ctypes.c_longlong(nl * 8), ctypes.c_longlong(b.im * 8), ctypes.c_longlong(rows), 2, sp),
+                           "bcd_memcpy2d")
+        for s in self.streams:
+            main.wait_stream(s)
+        main.synchronize()
+
+
 def local_halo_exchange(blocks):
     """halo exchange between the i-slab Blocks of ONE process (rank order = list order): device-to-device copies of the
     gh columns next to every slab-internal edge (peer copies over NVLink when the blocks live on different GPUs)."""
@@ -316,6 +366,19 @@ class HybridJacobian:
             cols.append(ja[keep].to(torch.int64))
         return torch.cat(vals), torch.cat(rows), torch.cat(cols)
 
+    def to_csr(self, thresh=2e-16, divide_by_vol=False):
+        """device-side CSR row block of this (slab's) rows: (indptr, indices, data) torch tensors with duplicates summed,
+        optionally divided by the row cell's volume (``Jacsurvol``, BROADCAST_npz.py:1206-1210)."""
+        from . import formats
+        blk = self.blk
+        v, r, c = self.to_coo(thresh)
+        if divide_by_vol:
+            ci = torch.div(r, 5 * blk.jm, rounding_mode="floor") - blk.ioff + blk.gh
+            cj = torch.div(r % (5 * blk.jm), 5, rounding_mode="floor") + blk.gh
+            v = v / blk.vol[cj, ci]
+        n = 5 * blk.im_global * blk.jm
+        return formats.coo_to_csr(v, r, c, 5 * blk.im * blk.jm, n, row0=5 * blk.jm * blk.ioff)
+
     def to_scipy_csr(self, thresh=2e-16):
         import scipy.sparse as sp
         v, r, c = self.to_coo(thresh)
@@ -323,7 +386,7 @@ class HybridJacobian:
         return sp.csr_matrix((v.cpu().numpy(), (r.cpu().numpy(), c.cpu().numpy())), shape=(n, n))
 
 
-def jacobian_hybrid(blk: "Block", coefdiag=None, kind=None, blocks=None, interior="faces"):
+def jacobian_hybrid(blk: "Block", coefdiag=None, kind=None, blocks=None, interior="faces", strip_buffers=None):
     """Jacobian of the current state: interior rows by the direct block kernels (one launch per
     structural column offset, no colouring), boundary strips (gh rows/columns along each side) by the
     reference colour loop restricted to those rows."""
@@ -349,8 +412,31 @@ def jacobian_hybrid(blk: "Block", coefdiag=None, kind=None, blocks=None, interio
         rects.append((1, gh, gh + 1, jm - gh))
     if not edges & 2:
         rects.append((im - gh + 1, im, gh + 1, jm - gh))
-    strips = []
-    for r in rects:
-        if r[1] >= r[0] and r[3] >= r[2]:
-            strips.append(jacobian_coo(blk, coefdiag=cd, kind=kind, rect=r, compact=True))
+    rects = [r for r in rects if r[1] >= r[0] and r[3] >= r[2]]
+    strips = jacobian_strips(blk, rects, coefdiag=cd, kind=kind, out=strip_buffers)
     return HybridJacobian(blk, blocks, jacobian_slots(blk), strips, region)
+
+
+def jacobian_strips(blk: "Block", rects, coefdiag=None, kind="jv_relaxed", out=None):
+    """reference colour loop restricted to the rows of up to four rectangles, all in the same 49 passes (bcd_jacobian_strips);
+    returns one compact COO triple (jac, ia, ja) per rectangle"""
+    gh = blk.gh
+    s = 2 * gh + 1
+    if not rects:
+        return []
+    if out is None:
+        out = []
+        for r in rects:
+            nb = 25 * s * s * (r[1] - r[0] + 1) * (r[3] - r[2] + 1)
+            out.append((torch.zeros(nb, dtype=torch.float64, device=blk.device), torch.zeros(nb, dtype=torch.int32, device=blk.device),
+                        torch.zeros(nb, dtype=torch.int32, device=blk.device)))
+    n = len(rects)
+    ra = np.asarray(rects, dtype=np.int32).reshape(-1)
+    PP = ctypes.c_void_p * n
+    jp, ip, kp = PP(*[t[0].data_ptr() for t in out]), PP(*[t[1].data_ptr() for t in out]), PP(*[t[2].data_ptr() for t in out])
+    if coefdiag is None and "relaxed" in kind:
+        coefdiag = torch.zeros((blk.jm, blk.im), dtype=torch.float64, device=blk.device)
+    descs, nb_ = _bc_descs(blk)
+    blk.call("bcd_jacobian_strips", n, ra.ctypes.data_as(ctypes.c_void_p), jp, ip, kp, _p(blk.w), _p(blk.nx), _p(blk.ny), _p(blk.vol),
+             _p(blk.volf), gh, *blk._phys, blk.im, blk.jm, blk.wall, descs, nb_, SCATTER[kind], _p(coefdiag), blk._stream())
+    return out

@@ -144,6 +144,10 @@ int bc_compute_norml2inf(double* norm, double* ninf, const double* rhs, int im, 
  * sides only) and the regular-row block kernels run up to that edge.  Arrays, rect arguments and slot layouts stay local. */
 int bcd_slab_begin(int ioff, int im_global, int edges);
 int bcd_slab_end(void);
+/* pitched copy of `height` rows of `width` BYTES between a host array and a device array (an i-slab of a Fortran-ordered
+ * block is a set of pitched rows); kind 1 = host to device, 2 = device to host; asynchronous on `stream`. */
+int bcd_memcpy2d(void* dst, long long dpitch, const void* src, long long spitch, long long width, long long height, int kind,
+                 void* stream);
 int bcd_residual(double* residu, const double* w, const double* nx, const double* ny, const double* vol,
                  const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
                  double muref, double tref, double s_suth, double k2, double k4, int im, int jm, int wall,
@@ -211,6 +215,13 @@ int bcd_jacobian_coo(double* jac, int32_t* ia, int32_t* ja, double* w, const dou
                      double rgaz, double cs, double muref, double tref, double s_suth, double k2, double k4, int im,
                      int jm, int wall, const bc_desc_t* bcs, int nbcs, int scatter_kind, const double* coefdiag,
                      const int32_t* rect, int compact, void* stream);
+/* The same colour loop restricted to the rows of up to four rectangles (the boundary strips of the hybrid assembly),
+ * all rectangles in the same 49 passes; output: one compact COO triple per rectangle (as bcd_jacobian_coo with compact). */
+int bcd_jacobian_strips(int nrect, const int32_t* rects /* [nrect][4] = i0,i1,j0,j1 */, double* const* jac, int32_t* const* ia,
+                        int32_t* const* ja, double* w, const double* nx, const double* ny, const double* vol, const double* volf,
+                        int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs, double muref, double tref,
+                        double s_suth, double k2, double k4, int im, int jm, int wall, const bc_desc_t* bcs, int nbcs,
+                        int scatter_kind, const double* coefdiag, void* stream);
 /* Colour loop of the spanwise operators (BROADCAST_npz.py:1231-1246) on the device: COO triplets of Dz (jac1, ia1, ja1)
  * and Dz2 (jac2, ia2, ja2) in the reference's slot order, scatter rule computejacobianfromdz (misc/ComputeJacobian.f90:708-779).
  * Either triplet may be null. */

@@ -334,3 +334,60 @@ def test_slab_sharded_residual_and_jacobian_match_single_block(gpu, world):
     assert JS.nnz == JG.nnz
     h = sums.cpu().numpy()
     assert np.allclose(np.sqrt(h[:5]), n2G, rtol=1e-12) and np.allclose(h[5:10] ** 0.1, ninfG, rtol=1e-12)
+
+
+def test_streamed_host_step_matches_resident_block(gpu):
+    """slab-pipelined host step (H2D / compute / D2H overlapped over i-slabs) == the single-block host step"""
+    import torch
+    from broadcast_b200.resident import Block, StreamedBlock
+    g = H.make_case("bl", 130, 40, gpu, with_w=True)
+    blk = Block(g)
+    wp = torch.empty(blk.w.shape, dtype=torch.float64).pin_memory()
+    wp.copy_(blk.w.cpu())
+    r1 = torch.zeros(blk.w.shape, dtype=torch.float64).pin_memory()
+    r2 = torch.zeros(blk.w.shape, dtype=torch.float64).pin_memory()
+    blk.step_from_host(wp, r1)
+    sb = StreamedBlock(g, nslab=4)
+    sb.step_from_host(wp, r2)
+    gh = g.gh
+    a, b = r1[:, gh:-gh, gh:-gh], r2[:, gh:-gh, gh:-gh]
+    assert (a - b).abs().max().item() <= 1e-13 * a.abs().max().item()
+    assert a.abs().max().item() > 0
+
+
+def test_csr_row_blocks_and_petsc_file(gpu, tmp_path):
+    """device-side filter + divide-by-volume + CSR == the reference's remove_zero_jac / Jacvol loop / csr_matrix on the
+    hybrid Jacobian; slab row blocks gather to the same matrix; PETSc binary AIJ round trip"""
+    import scipy.sparse as sp
+    from broadcast_b200 import sharding, formats
+    from broadcast_b200.resident import Block, jacobian_hybrid, local_halo_exchange
+    im, jm = 48, 26
+    g = H.make_case("bl", im, jm, gpu, with_w=True)
+    G = Block(g)
+    G.apply_bcs()
+    Hj = jacobian_hybrid(G)
+    v, r, c = (t.cpu().numpy() for t in Hj.to_coo())
+    gh = g.gh
+    jacvol = v / g.vol[r // (5 * jm) + gh, (r % (5 * jm)) // 5 + gh]          # BROADCAST_npz.py:1206-1209
+    n = 5 * im * jm
+    A = sp.csr_matrix((jacvol, (r, c)), shape=(n, n)); A.sort_indices()
+    ip, idx, dat = (t.cpu().numpy() for t in Hj.to_csr(divide_by_vol=True))
+    assert np.array_equal(ip, A.indptr) and np.array_equal(idx, A.indices)
+    assert np.allclose(dat, A.data, rtol=1e-15, atol=0)
+    # two slabs -> two row blocks -> host gather
+    blocks = []
+    for rk in range(2):
+        sl, desc = sharding.slab_of(g, rk, 2)
+        blocks.append(Block(sl, slab=desc))
+    local_halo_exchange(blocks)
+    parts = []
+    for b in blocks:
+        b.apply_bcs()
+        parts.append(tuple(t.cpu().numpy() for t in jacobian_hybrid(b).to_csr(divide_by_vol=True)))
+    ip2, idx2, dat2 = sharding.gather_row_blocks(parts)
+    assert np.array_equal(ip2, A.indptr) and np.array_equal(idx2, A.indices)
+    assert np.allclose(dat2, A.data, rtol=1e-14, atol=0)
+    p = str(tmp_path / "Jacsurvol")
+    formats.write_petsc_aij(p, ip2, idx2, dat2, n)
+    ip3, idx3, dat3, shape = formats.read_petsc_aij(p)
+    assert shape == (n, n) and np.array_equal(ip3, A.indptr) and np.array_equal(dat3.real, dat2)

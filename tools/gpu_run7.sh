@@ -1,0 +1,6 @@
+set -x
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/r7_pytest.log; cat gpurun_out/r7_pytest.log
+timeout 900 python tools/jac_probe.py 500x150 2048x512 4096x1024 > gpurun_out/r7_jac_probe.log 2>&1; cat gpurun_out/r7_jac_probe.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r7_jac_launches.csv python tools/jac_probe.py 4096x1024 > gpurun_out/r7_jac_launches.log 2>&1; tail -2 gpurun_out/r7_jac_launches.log
+ls -la gpurun_out
