@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 
 RES_BYTES_PER_CELL = 136.0  # 12 doubles read (w5, nx2, ny2, vol, volf2) + 5 written, SURVEY.md 8(d)
 JAC_BYTES_PER_CELL = 5904.0  # 29 blocks x 25 doubles written + 13 doubles read, SURVEY.md 8(d)
-RES_TRAFFIC_NCU = 2.269e9    # dram__bytes_read.sum + dram__bytes_write.sum of one launch at C5 (profiles/r1_b_residual_tile_full_raw.csv)
+RES_TRAFFIC_NCU = 2.265e9    # dram__bytes_read.sum + dram__bytes_write.sum of one launch at C5 (profiles/r1_d_residual_fast_full_raw.csv)
 
 
 def parse():
@@ -262,7 +262,7 @@ def main():
 
     # roofline of the dominant kernel (fused residual tile kernel), per launch, per GPU
     achieved = RES_BYTES_PER_CELL * cells_local / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_residual_tile<32,8>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "kernel": "k_residual_fast (32x8 tile, 288 threads)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_kind": peak_kind, "traffic": RES_TRAFFIC_NCU if (a.im, a.jm, world) == (8192, 2048, 1) else None, "kernel_ms": k_ms,
                 "algorithmic_bytes_per_cell": RES_BYTES_PER_CELL,
                 "fp64_pipe_note": "FP64-pipe bound at ~11 flop/B (ridge 5.8): see DESIGN.md section 4 and profiles/"}

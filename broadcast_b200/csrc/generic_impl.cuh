@@ -1,6 +1,7 @@
 // Generic residual / tangent pipeline, instantiated once per tangent width BCAST_N by
 // generic_n0.cu / generic_n1.cu / generic_n5.cu (separate translation units keep build times low).
 #include "kernels.cuh"
+#include <cstdlib>
 
 namespace bcast {
 
@@ -297,14 +298,18 @@ cudaError_t BCAST_CAT(dz_generic_, BCAST_N)(const GridDesc& g, const SchemeArgs&
 // the four faces of a cell are combined through shared memory exactly as rhs/balance.F does.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_balance_faces5(GridDesc g, SchemeConsts c, FieldPtrs f, bool wall, RectList rl, double* __restrict__ out) {
-  // blockIdx.z = rect * 5 + direction: each thread differentiates ONE face in ONE direction (Tan<1>)
+  // blockIdx.z = rect * 5 + direction: each thread differentiates ONE face in ONE direction (Tan<1>).
+  // The 32 cells of a block are consecutive cells of the rectangle in row-major order (i fastest), so that the
+  // gh-wide column strips (3 x jm cells) fill their warps just like the row strips (im x 3).
   __shared__ double sh[4][5][32];
   const int dir = blockIdx.z % 5;
   const Rect rc = rl.r[blockIdx.z / 5];
-  const int i = blockIdx.x * 32 + threadIdx.x + rc.i0;
-  const int j = blockIdx.y + rc.j0;
+  const int wi = rc.i1 - rc.i0 + 1, wj = rc.j1 - rc.j0 + 1;
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  const bool act = n < wi * wj;
+  const int i = rc.i0 + n % wi;
+  const int j = rc.j0 + n / wi;
   const int face = threadIdx.z;
-  const bool act = i <= rc.i1 && j <= rc.j1;
   // direction `dir` of the 5-direction arrays seen as a 1-direction field set
   FieldPtrs f1 = f;
   f1.wd = f.wd + (long long)dir * 5 * g.sc;
@@ -325,6 +330,93 @@ __global__ void __launch_bounds__(128) k_balance_faces5(GridDesc g, SchemeConsts
   for (int e = face; e < 5; e += 4) {
     const double r = -(sh[1][e][threadIdx.x] - sh[0][e][threadIdx.x]) - (sh[3][e][threadIdx.x] - sh[2][e][threadIdx.x]);
     out[(long long)(dir * 5 + e) * g.sc + k] = r;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Strip tangent, second version: one block = a tile of 32 x th (th <= 3) or tw x 32 (tw <= 3) cells of a boundary strip
+// and ONE direction.  Every face of the tile is evaluated ONCE (33*th + 32*(th+1) <= 227 faces on 256 threads instead of
+// 4 per cell), and only if a tangent input of its stencil is non-zero in this direction: the block first builds the
+// activity map of its cell window from wd (seeds and linearised ghost fills), a face is skipped when none of the cells
+// of its stencil is active and the tangents of its two sensor gradients are zero (with seeds 7 cells apart about half of
+// the faces of a colour pass see no seed at all).  Faces are combined per cell through shared memory as rhs/balance.F does.
+// ---------------------------------------------------------------------------------------------
+constexpr int SF_MAXF = 232;
+__global__ void __launch_bounds__(256) k_strip_faces5(GridDesc g, SchemeConsts c, FieldPtrs f, bool wall, Rect rc, int wide,
+                                                      double* __restrict__ out) {
+  __shared__ double sh[5][SF_MAXF];
+  __shared__ unsigned char flag[38 * 9];
+  const int dir = blockIdx.z;
+  const int ti0 = wide ? rc.i0 + 32 * blockIdx.x : rc.i0;
+  const int tj0 = wide ? rc.j0 : rc.j0 + 32 * blockIdx.x;
+  const int twc = min(wide ? 32 : 3, rc.i1 - ti0 + 1);
+  const int thc = min(wide ? 3 : 32, rc.j1 - tj0 + 1);
+  const int fw = twc + 6, fh = thc + 6;   // activity window: cells ti0-3 .. ti0+twc+2, tj0-3 .. tj0+thc+2
+  FieldPtrs f1 = f;
+  f1.wd = f.wd + (long long)dir * 5 * g.sc;
+  f1.primd = f.primd + (long long)dir * NPRIM * g.sc;
+  f1.gradd = f.gradd + (long long)dir * NGRAD * g.sc;
+  for (int idx = threadIdx.x; idx < fw * fh; idx += blockDim.x) {
+    const int ci = ti0 - 3 + idx % fw, cj = tj0 - 3 + idx / fw;
+    bool a = false;
+    if (ci >= 1 - g.gh && ci <= g.im + g.gh && cj >= 1 - g.gh && cj <= g.jm + g.gh) {
+      const long long k = g.cidx(ci, cj);
+#pragma unroll
+      for (int e = 0; e < 5; ++e) a = a || (f1.wd[e * g.sc + k] != 0.0);
+    }
+    flag[idx] = a ? 1 : 0;
+  }
+  __syncthreads();
+  const int nI = (twc + 1) * thc, nJ = twc * (thc + 1);
+  const int t = threadIdx.x;
+  if (t < nI + nJ) {
+    const bool isI = t < nI;
+    const int u = isI ? t : t - nI;
+    const int pw = isI ? twc + 1 : twc;
+    const int fi = ti0 + u % pw, fj = tj0 + u / pw;
+    // stencil of a regular face: along -3 .. 2 on its own row, along -2 .. 1 on the cross rows +-1, +-2; the off-centred
+    // wall flux of face j = 2 reaches j = 5 (along +3)
+    bool act = false;
+    const int bi = fi - (ti0 - 3), bj = fj - (tj0 - 3);   // window coordinates of the face cell
+    auto chk = [&](int di, int dj) -> bool {   // outside the window: assume active
+      const int x = bi + di, y = bj + dj;
+      return (x < 0 || x >= fw || y < 0 || y >= fh) ? true : flag[x + y * fw] != 0;
+    };
+    if (isI) {
+      for (int s_ = -3; s_ <= 2; ++s_) act = act || chk(s_, 0);
+      for (int t_ = -2; t_ <= 2; ++t_)
+        for (int s_ = -2; s_ <= 1; ++s_) act = act || chk(s_, t_);
+    } else {
+      const int hi = (wall && fj == 2) ? 3 : 2;
+      for (int s_ = -3; s_ <= hi; ++s_) act = act || chk(0, s_);
+      for (int t_ = -2; t_ <= 2; ++t_)
+        for (int s_ = -2; s_ <= 1; ++s_) act = act || chk(t_, s_);
+    }
+    if (!act) {   // sensor gradients of the two face cells (extrapolated ones in the first ghost layer included)
+      const long long k0 = g.cidx(fi, fj), k1 = isI ? k0 - 1 : k0 - g.ldc;
+#pragma unroll
+      for (int q = 0; q < NGRAD; ++q) act = act || (f1.gradd[q * g.sc + k0] != 0.0) || (f1.gradd[q * g.sc + k1] != 0.0);
+    }
+    double hd[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (act) {
+      Var<Tan<1>> hn[5];
+      if (isI) face_dispatch<1, 0>(f1, g, c, wall, fi, fj, hn);
+      else face_dispatch<1, 1>(f1, g, c, wall, fi, fj, hn);
+#pragma unroll
+      for (int e = 0; e < 5; ++e) hd[e] = hn[e].d.d[0];
+    }
+#pragma unroll
+    for (int e = 0; e < 5; ++e) sh[e][t] = hd[e];
+  }
+  __syncthreads();
+  const int ncell = twc * thc;
+  for (int idx = threadIdx.x; idx < 5 * ncell; idx += blockDim.x) {
+    const int e = idx / ncell, cell = idx % ncell;
+    const int cc = cell % twc, r = cell / twc;
+    const double* hI = sh[e];
+    const double* hJ = sh[e] + nI;
+    const double v = -(hI[r * (twc + 1) + cc + 1] - hI[r * (twc + 1) + cc]) - (hJ[(r + 1) * twc + cc] - hJ[r * twc + cc]);
+    out[(long long)(dir * 5 + e) * g.sc + g.cidx(ti0 + cc, tj0 + r)] = v;
   }
 }
 
@@ -351,9 +443,17 @@ cudaError_t tangent_strips_5(const GridDesc& g, const SchemeArgs& a, bool wall, 
   k_grad_ghost<<<dim3((nt + 127) / 128, NGRAD), 128, 0, st>>>(g, grad, NGRAD);
   k_grad_ghost<<<dim3((nt + 127) / 128, NGRAD * N), 128, 0, st>>>(g, gradd, NGRAD * N);
   for_each_rect(rows, [&](const RectList& r1, int) {
-    dim3 gb = grid_of(r1, 32, 1);
-    gb.z = 5;
-    k_balance_faces5<<<gb, dim3(32, 1, 4), 0, st>>>(g, c, f, wall, r1, out5);
+    const Rect& q = r1.r[0];
+    const int wi = q.i1 - q.i0 + 1, wj = q.j1 - q.j0 + 1;
+    static const bool v1 = getenv("BROADCAST_B200_STRIPS_V1") != nullptr;
+    if (!v1 && wj <= 3 && wi >= wj) {
+      k_strip_faces5<<<dim3((wi + 31) / 32, 1, 5), 256, 0, st>>>(g, c, f, wall, q, 1, out5);
+    } else if (!v1 && wi <= 3) {
+      k_strip_faces5<<<dim3((wj + 31) / 32, 1, 5), 256, 0, st>>>(g, c, f, wall, q, 0, out5);
+    } else {
+      const int ncell = wi * wj;
+      k_balance_faces5<<<dim3((ncell + 31) / 32, 1, 5), dim3(32, 1, 4), 0, st>>>(g, c, f, wall, r1, out5);
+    }
   });
   return cudaGetLastError();
 }

@@ -113,4 +113,8 @@ cudaError_t launch_norms(const GridDesc& g, const double* res, double* out10 /*d
 cudaError_t launch_residual_tiled(const GridDesc& g, const SchemeArgs& a, bool wall, double* res, const double* w, const double* nx,
                                   const double* ny, const double* vol, const double* volf, cudaStream_t st);
 
+// second-generation fused residual (residual_fast.cu): re-associated face formulas, shared normal-direction interpolations
+cudaError_t launch_residual_fast(const GridDesc& g, const SchemeArgs& a, bool wall, double* res, const double* w, const double* nx,
+                                 const double* ny, const double* vol, const double* volf, cudaStream_t st);
+
 }  // namespace bcast

@@ -1,0 +1,488 @@
+// Second-generation fused primal residual (order 5, gh = 3): the tile algorithm and its face formulas, written as
+// host+device phase functions so that the very same code runs inside k_residual_fast (residual_fast.cu) and, on a
+// machine without a GPU, inside tests/host/residual_fast_host.cpp against the oracle.
+//
+// What changed against k_residual_tile (residual_tile.cu), which evaluates the reference-shaped templates of
+// scheme.cuh face by face (ncu, profiles/r1_c_summary.md: shared-memory wavefronts 59 %, FP64 pipe 44 %, ~450 LDS.64
+// and ~1 400 FP64 instructions per cell):
+//   * convective flux as (u nx + v ny) * [rho, rho u, rho v, rho w, rho E + p] + p n, one pass over the six stencil
+//     cells shared with the 5th-difference operand (euler_o6_{i,j}.F + predictor_7p_{i,j}.F): 8 loads per cell;
+//   * the normal-direction interpolation (-1, 9, 9, -1) of u, v, w, T that the compact viscous gradients apply on five
+//     cross rows (flux_visqueux_o4_{i,j}.F) is a per-FACE quantity: it is computed once per face into shared memory
+//     and read by the four cross neighbours (84 -> ~36 loads per face, ~216 -> ~110 flops);
+//   * sqrt(rho) and the sound speed are per-cell quantities: the Roe weights become sl/(sl+sr), the sensor
+//     denominators a*|n| (spectralradius_{i,j}.F, ducrosfordnc_{i,j}.F): 5 -> 2 square roots per face;
+//   * max(k1, k2) of the Jameson sensor and min(x0, x1) of the dilatation switch are selected by cross-multiplication
+//     before dividing; (1 - tanh x)/2 = 1/(1 + exp 2x); reciprocals by MUFU seed + two Newton steps;
+//   * the face metric scalings (1/24, 1/(12*16), 1/vol_face, 1/2) are folded into the eight dual-cell normals;
+//     (fv nx/|n| + gv ny/|n|) |n| is evaluated as fv nx + gv ny (fluxnumassembly_{i,j}.F).
+// All of these are re-associations: results agree with the reference to a few ulp of the largest term (tests: 1e-12 of
+// the plane maximum).  The three wall rows (o2 viscous fluxes, off-centred fluxes, wall flux: flux_num_dnc5.F90:161-220)
+// keep the reference-shaped templates of scheme.cuh through an accessor over the same shared arrays.
+//
+// Tile: 32 x 8 output cells per CTA of 288 threads (9 warps): 8 x 33 i-faces (8 warps x 32 left faces + 8 lanes of the
+// ninth warp for the last column) and 9 x 32 j-faces (all 288 threads) -- no face is evaluated twice inside a CTA.
+#pragma once
+#include "scheme.cuh"
+
+namespace bcast {
+namespace rf {
+
+constexpr int H = 3;
+constexpr int OI = 32, OJ = 8;
+constexpr int PI = OI + 2 * H, PJ = OJ + 2 * H;  // staged cells: i0-3 .. i0+34, j0-3 .. j0+10
+constexpr int NC = PI * PJ;
+constexpr int NT = 288;
+enum { A_W = 0, A_U = 5, A_V = 6, A_WZ = 7, A_T = 8, A_P = 9, A_MU = 10, A_SR = 11, A_CS = 12, A_DV = 13, A_DU = 14, NARR = 15 };
+// normal-direction interpolations R_q (q = u, v, w, T) of the faces a CTA's viscous gradients read
+constexpr int RI_W = OI + 1, RI_H = OJ + 4;   // i-faces i0 .. i0+32, rows j0-2 .. j0+9
+constexpr int RJ_W = OI + 4, RJ_H = OJ + 1;   // j-faces columns i0-2 .. i0+33, rows j0 .. j0+8
+constexpr int RQ = RI_W * RI_H;               // 396 >= 324
+constexpr int NRB = 4 * RQ;
+constexpr int XI_P = OI + 1, XJ_P = OI;       // pitches of the face-flux exchange buffer
+constexpr int NXB = 5 * (OJ + 1) * OI;        // 1440 >= 5 * 8 * 33
+constexpr int GW = OI + 2, GH_ = OJ + 2;      // sensor cells: i0-1 .. i0+32, j0-1 .. j0+8 (scratch divu / vort alias X)
+constexpr int NSM = NARR * NC + NRB + NXB;    // doubles of shared memory per CTA (88 032 bytes)
+static_assert(2 * GW * GH_ <= NXB, "scratch aliasing");
+static_assert(RJ_W * RJ_H <= RQ, "R buffer");
+
+// reciprocal: MUFU seed (20 mantissa bits) + two Newton steps (device); plain division on the host build
+BC_HD double frcp(double x) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+#else
+  return 1.0 / x;
+#endif
+}
+
+struct TileCtx {
+  double* sm;
+  GridDesc g;
+  SchemeConsts c;
+  double sqgr;  // sqrt(gam * rgaz)
+  bool wall;
+  const double *w, *nx, *ny, *vol, *volf;
+  double* res;
+  int i0, j0;  // first output cell of the tile
+  BC_HD double* arr(int a) const { return sm + a * NC; }
+  BC_HD double* RB() const { return sm + NARR * NC; }
+  BC_HD double* X() const { return sm + NARR * NC + NRB; }
+  // does the tile hold sensor cells of the first ghost layer of a physical boundary?
+  BC_HD bool has_ghost_sensor() const {
+    return (i0 == 1 && !(g.edges & 1)) || (i0 + OI >= g.im + 1 && !(g.edges & 2)) || j0 == 1 || j0 + OJ >= g.jm + 1;
+  }
+};
+
+// accessor over the shared arrays for the reference-shaped templates of scheme.cuh (wall rows, gradients)
+struct SmemAcc2 {
+  using DT = Zero;
+  const double* s;  // sm + shared index of the base cell
+  const double *nx, *ny, *vol, *volf;
+  long long c, n;
+  int ldc, ldn;
+  long long sc, sn;
+  template <int OI_, int OJ_> BC_HD double raw(int a) const { return s[a * NC + OI_ + OJ_ * PI]; }
+  template <int OI_, int OJ_> BC_HD PVar ld(int a) const { return PVar{raw<OI_, OJ_>(a), {}}; }
+  template <int OI_, int OJ_> BC_HD PVar W(int e) const { return ld<OI_, OJ_>(A_W + e); }
+  template <int OI_, int OJ_> BC_HD PVar U() const { return ld<OI_, OJ_>(A_U); }
+  template <int OI_, int OJ_> BC_HD PVar V() const { return ld<OI_, OJ_>(A_V); }
+  template <int OI_, int OJ_> BC_HD PVar Wz() const { return ld<OI_, OJ_>(A_WZ); }
+  template <int OI_, int OJ_> BC_HD PVar T() const { return ld<OI_, OJ_>(A_T); }
+  template <int OI_, int OJ_> BC_HD PVar P() const { return ld<OI_, OJ_>(A_P); }
+  template <int OI_, int OJ_> BC_HD PVar Mu() const { return ld<OI_, OJ_>(A_MU); }
+  template <int OI_, int OJ_> BC_HD PVar H() const {
+    return PVar{(raw<OI_, OJ_>(A_W + 4) + raw<OI_, OJ_>(A_P)) * (1.0 / raw<OI_, OJ_>(A_W)), {}};
+  }
+  template <int OI_, int OJ_> BC_HD auto SENS() const {   // A_DV holds vol * divu
+    return CellSens<Zero, Zero>{PVar{raw<OI_, OJ_>(A_DV) / VOL<OI_, OJ_>(), {}}, ld<OI_, OJ_>(A_DU)};
+  }
+  template <int OI_, int OJ_> BC_HD double NX(int kk) const { return BC_LDG(nx + kk * sn + n + OI_ + (long long)OJ_ * ldn); }
+  template <int OI_, int OJ_> BC_HD double NY(int kk) const { return BC_LDG(ny + kk * sn + n + OI_ + (long long)OJ_ * ldn); }
+  template <int OI_, int OJ_> BC_HD double VOL() const { return BC_LDG(vol + c + OI_ + (long long)OJ_ * ldc); }
+  template <int OI_, int OJ_> BC_HD double VOLF(int kk) const { return BC_LDG(volf + kk * sc + c + OI_ + (long long)OJ_ * ldc); }
+};
+
+BC_HD SmemAcc2 make_acc(const TileCtx& t, int a, int b) {  // shared coordinates (a, b): cell (i0-H+a, j0-H+b)
+  SmemAcc2 A;
+  A.s = t.sm + a + b * PI;
+  A.nx = t.nx; A.ny = t.ny; A.vol = t.vol; A.volf = t.volf;
+  A.c = t.g.cidx(t.i0 - H + a, t.j0 - H + b);
+  A.n = t.g.nidx(t.i0 - H + a, t.j0 - H + b);
+  A.ldc = t.g.ldc; A.ldn = t.g.ldn; A.sc = t.g.sc; A.sn = t.g.sn;
+  return A;
+}
+
+// ---- phase 0: stage w, cell primitives (phys/Primitives.F:2-34, phys/viscosity.F:1) -------------------------------
+BC_HD void phase0(const TileCtx& t, int tid) {
+  const GridDesc& g = t.g;
+  constexpr int NIT = (NC + NT - 1) / NT;
+  double q[NIT][5];
+  // all loads of the thread first (the only HBM reads of the kernel besides the metrics), then the arithmetic
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int idx = tid + it * NT;
+    const int a = idx % PI, b = idx / PI;
+    const int gi = t.i0 - H + a, gj = t.j0 - H + b;
+    q[it][0] = 1.0; q[it][1] = 0.0; q[it][2] = 0.0; q[it][3] = 0.0; q[it][4] = 1.0;
+    if (idx < NC && gi <= g.im + g.gh && gj <= g.jm + g.gh) {
+      const double* p = t.w + g.cidx(gi, gj);
+#pragma unroll
+      for (int e = 0; e < 5; ++e) q[it][e] = BC_LDG(p + e * g.sc);
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int idx = tid + it * NT;
+    if (idx >= NC) break;
+    const double q0 = q[it][0], q1 = q[it][1], q2 = q[it][2], q3 = q[it][3], q4 = q[it][4];
+    const double rom1 = frcp(q0);
+    const double u = q1 * rom1, v = q2 * rom1, wz = q3 * rom1;
+    const double ec = 0.5 * (u * u + v * v + wz * wz);
+    const double eloc = (q4 - ec * q0) * rom1;
+    const double tl = eloc * t.c.cvm1;
+    const double p = t.c.gam1 * q0 * eloc;
+    const double sqt = ::sqrt(tl);
+    double* s = t.sm + idx;
+    s[(A_W + 0) * NC] = q0;
+    s[(A_W + 1) * NC] = q1;
+    s[(A_W + 2) * NC] = q2;
+    s[(A_W + 3) * NC] = q3;
+    s[(A_W + 4) * NC] = q4;
+    s[A_U * NC] = u;
+    s[A_V * NC] = v;
+    s[A_WZ * NC] = wz;
+    s[A_T * NC] = tl;
+    s[A_P * NC] = p;
+    s[A_MU * NC] = t.c.betas * frcp(tl + t.c.s_suth) * sqt * tl;
+    s[A_SR * NC] = ::sqrt(q0);
+    s[A_CS * NC] = t.sqgr * sqt;
+  }
+}
+
+// ---- phase 1: sensor cells (dilatation, Ducros ratio) and the R_q of the i-faces ---------------------------------
+BC_HD double ducros_ratio(double divu, double vort) {
+  const double d2 = divu * divu;
+  return d2 * frcp(d2 + vort * vort + 1e-15);
+}
+// R_q(face) = -q(-2) + 9 q(-1) + 9 q(0) - q(1) along the face normal (the 1/16 is applied by the consumer)
+BC_HD double rrow(const double* q, int stride) { return 9.0 * (q[-stride] + q[0]) - (q[-2 * stride] + q[stride]); }
+
+// Sensor cells of a tile: rows j0 .. j0+7 over columns i0-1 .. i0+32 (272 cells, one per thread) and the two rows
+// j0-1, j0+8 over columns i0 .. i0+31 (64 cells, a second round of the first two warps); the corners are never read.
+BC_HD void sensor_cell(const TileCtx& t, int ga, int gb) {   // window coordinates: cell (i0-1+ga, j0-1+gb)
+  const GridDesc& g = t.g;
+  const int a = ga + (H - 1), b = gb + (H - 1);
+  const int ci = t.i0 - H + a, cj = t.j0 - H + b;
+  if (ci >= g.glo() && ci <= g.ghi() && cj >= 1 && cj <= g.jm) {  // slab-internal edges: real gradients in the halo column
+    const SmemAcc2 A = make_acc(t, a, b);
+    const auto r = cell_gradients<0, 0>(A);
+    const double divu = r.u0.v + r.v1.v, vort = r.v0.v - r.u1.v;
+    double* S0 = t.X();
+    S0[ga + gb * GW] = divu;
+    S0[GW * GH_ + ga + gb * GW] = vort;
+    const int k = a + b * PI;
+    t.arr(A_DV)[k] = A.template VOL<0, 0>() * divu;
+    t.arr(A_DU)[k] = ducros_ratio(divu, vort);
+  }
+}
+
+BC_HD void phase1(const TileCtx& t, int tid) {
+  if (tid < GW * OJ) sensor_cell(t, tid % GW, 1 + tid / GW);
+  if (tid < 2 * OI) sensor_cell(t, 1 + (tid & (OI - 1)), tid < OI ? 0 : GH_ - 1);
+  // R_q of the i-faces: thread (fcol = tid % 36 < 33, grp = tid / 36) owns quantity grp/2 and six of the twelve face rows
+  const int fcol = tid % (RI_W + 3), grp = tid / (RI_W + 3);
+  if (fcol < RI_W) {
+    const int q = grp >> 1, frow0 = (grp & 1) * (RI_H / 2);
+    const double* src = t.arr(A_U + q) + (fcol + H) + (frow0 + 1) * PI;  // face (i0 + fcol, j0 - 2 + frow0)
+    double* dst = t.RB() + q * RQ + frow0 * RI_W + fcol;
+#pragma unroll
+    for (int n = 0; n < RI_H / 2; ++n) dst[n * RI_W] = rrow(src + n * PI, 1);
+  }
+}
+
+// first ghost layer of the sensor cells by linear extrapolation of the gradients (rhs/gradveloingh.F:1-19); divu and the
+// vorticity are linear in the gradients, so extrapolating them is extrapolating the gradients
+BC_HD void phase1b(const TileCtx& t, int tid) {
+  const GridDesc& g = t.g;
+  const double* S0 = t.X();
+  const double* S1 = S0 + GW * GH_;
+  for (int idx = tid; idx < GW * GH_; idx += NT) {
+    const int a = idx % GW + (H - 1), b = idx / GW + (H - 1);
+    const int ci = t.i0 - H + a, cj = t.j0 - H + b;
+    int d = 0;
+    if (cj >= 1 && cj <= g.jm) {
+      if (ci == 0 && !(g.edges & 1)) d = 1;
+      else if (ci == g.im + 1 && !(g.edges & 2)) d = -1;
+    } else if (ci >= 1 && ci <= g.im) {
+      if (cj == 0) d = GW;
+      else if (cj == g.jm + 1) d = -GW;
+    }
+    if (d != 0) {
+      const double divu = 2.0 * S0[idx + d] - S0[idx + 2 * d];
+      const double vort = 2.0 * S1[idx + d] - S1[idx + 2 * d];
+      const int k = a + b * PI;
+      t.arr(A_DV)[k] = BC_LDG(t.vol + g.cidx(ci, cj)) * divu;
+      t.arr(A_DU)[k] = ducros_ratio(divu, vort);
+    }
+  }
+}
+
+// R_q of the j-faces (columns i0-2 .. i0+33, rows j0 .. j0+8): thread (fcol = tid % 36, grp = tid / 36) owns quantity grp/2
+// and five (even grp) or four (odd grp) consecutive face rows, sliding along j
+BC_HD void phase_rj(const TileCtx& t, int tid) {
+  const int fcol = tid % RJ_W, grp = tid / RJ_W;
+  const int q = grp >> 1, frow0 = (grp & 1) * 5, nrow = (grp & 1) ? 4 : 5;
+  const double* src = t.arr(A_U + q) + (fcol + 1) + (frow0 + H) * PI;  // face (i0 - 2 + fcol, j0 + frow0)
+  double* dst = t.RB() + q * RQ + frow0 * RJ_W + fcol;
+  double m2 = src[-2 * PI], m1 = src[-PI], c0 = src[0];
+#pragma unroll
+  for (int n = 0; n < 5; ++n) {
+    if (n < nrow) {
+      const double p1 = src[(n + 1) * PI];
+      dst[n * RJ_W] = 9.0 * (m1 + c0) - (m2 + p1);
+      m2 = m1; m1 = c0; c0 = p1;
+    }
+  }
+}
+
+// ---- one regular face (FACE_MAIN, compact o4 viscous gradients) ---------------------------------------------------
+// s: shared pointer of the face cell (array 0); rb: R buffer entry of this face for q = 0 (quantity stride RQ, cross
+// stride RC); n / c: node- and cell-layout indices of the face cell in the global metric arrays.
+// Face metrics, loaded from global memory BEFORE the phases that precede the face evaluation so that their latency is
+// hidden: face normal and the eight dual-cell normals (flux_visqueux_o4_{i,j}.F) with the scalings folded in.
+struct FaceGeom {
+  double nxf, nyf;
+  double nApx, nAmx, nApy, nAmy, nCpx, nCmx, nCpy, nCmy;
+};
+template <int DIR>
+BC_HD FaceGeom load_geom(const TileCtx& t, int fi, int fj) {
+  const GridDesc& g = t.g;
+  const long long n = g.nidx(fi, fj), c = g.cidx(fi, fj);
+  const long long a1 = DIR == 0 ? 1 : g.ldn, c1 = DIR == 0 ? g.ldn : 1;
+  const double* nxA = t.nx + DIR * g.sn + n;
+  const double* nyA = t.ny + DIR * g.sn + n;
+  const double* nxC = t.nx + (1 - DIR) * g.sn + n;
+  const double* nyC = t.ny + (1 - DIR) * g.sn + n;
+  FaceGeom G;
+  G.nxf = BC_LDG(nxA);
+  G.nyf = BC_LDG(nyA);
+  const double volf = BC_LDG(t.volf + DIR * g.sc + c);
+  constexpr double ccross = (0.25 / 3.0) * 0.0625;
+  const double sA = (0.5 / 24.0) * volf, sC = (0.5 * ccross) * volf;
+  G.nApx = (BC_LDG(nxA + a1) + G.nxf) * sA;
+  G.nAmx = -(BC_LDG(nxA - a1) + G.nxf) * sA;
+  G.nApy = (BC_LDG(nyA + a1) + G.nyf) * sA;
+  G.nAmy = -(BC_LDG(nyA - a1) + G.nyf) * sA;
+  G.nCpx = (BC_LDG(nxC - a1 + c1) + BC_LDG(nxC + c1)) * sC;
+  G.nCmx = -(BC_LDG(nxC - a1) + BC_LDG(nxC)) * sC;
+  G.nCpy = (BC_LDG(nyC - a1 + c1) + BC_LDG(nyC + c1)) * sC;
+  G.nCmy = -(BC_LDG(nyC - a1) + BC_LDG(nyC)) * sC;
+  return G;
+}
+
+// s: shared pointer of the face cell (array 0); rb: R buffer entry of this face for q = 0 (quantity stride RQ, cross
+// stride RC)
+template <int DIR>
+BC_HD void face_fast(const TileCtx& t, const double* s, const double* rb, const FaceGeom& G, double (&hn)[5]) {
+  constexpr int SA = DIR == 0 ? 1 : PI;
+  constexpr int RC = DIR == 0 ? RI_W : 1;
+  const SchemeConsts& cs = t.c;
+#define RF_LD(A_, K_) s[(A_) * NC + (K_) * SA]
+  const double nxf = G.nxf, nyf = G.nyf;
+  const double nApx = G.nApx, nAmx = G.nAmx, nApy = G.nApy, nAmy = G.nAmy;
+  const double nCpx = G.nCpx, nCmx = G.nCmx, nCpy = G.nCpy, nCmy = G.nCmy;
+
+  // (order of the blocks chosen for register pressure: the viscous part first, its dual normals and gradients die before
+  //  the convective accumulators become live)
+  // ---- viscous flux, compact 4th order (flux_visqueux_o4_{i,j}.F) -------------------------------------------------
+  double gx[4], gy[4], fv[4];  // gradients and face values of u, v, w, T
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const double q1 = RF_LD(A_U + q, 1), q0 = RF_LD(A_U + q, 0), qm1 = RF_LD(A_U + q, -1), qm2 = RF_LD(A_U + q, -2);
+    const double Ap = 26.0 * q0 - (q1 + qm1), Am = 26.0 * qm1 - (q0 + qm2);
+    const double* r = rb + q * RQ;
+    const double rm2 = r[-2 * RC], rm1 = r[-RC], r0 = r[0], r1 = r[RC], r2 = r[2 * RC];
+    const double Cm = 7.0 * (rm1 + r0) - (rm2 + r1), Cp = 7.0 * (r0 + r1) - (rm1 + r2);
+    gx[q] = Ap * nApx + Am * nAmx + Cp * nCpx + Cm * nCmx;
+    gy[q] = Ap * nApy + Am * nAmy + Cp * nCpy + Cm * nCmy;
+    fv[q] = 0.0625 * r0;
+  }
+  const double mmu = 0.0625 * (9.0 * (RF_LD(A_MU, -1) + RF_LD(A_MU, 0)) - (RF_LD(A_MU, -2) + RF_LD(A_MU, 1)));
+  constexpr double TWOTHIRD = 2.0 / 3.0;
+  const double lambda = mmu * cs.cpprandtl;
+  const double fvrou = TWOTHIRD * mmu * (2.0 * gx[0] - gy[1]);
+  const double fvrov = mmu * (gy[0] + gx[1]);
+  const double fvrow = mmu * gx[2];
+  const double gvrov = TWOTHIRD * mmu * (2.0 * gy[1] - gx[0]);
+  const double gvrow = mmu * gy[2];
+  const double fvroe = lambda * gx[3] + fv[0] * fvrou + fv[1] * fvrov + fv[2] * fvrow;
+  const double gvroe = lambda * gy[3] + fv[0] * fvrov + fv[1] * gvrov + fv[2] * gvrow;
+  const double visc[5] = {0.0, fvrou * nxf + fvrov * nyf, fvrov * nxf + gvrov * nyf, fvrow * nxf + gvrow * nyf, fvroe * nxf + gvroe * nyf};
+
+  // ---- Roe spectral radius (spectralradius_{i,j}.F) ---------------------------------------------------------------
+  const double nx2 = nxf * nxf + nyf * nyf;
+  double rspec;
+  {
+    const double sr = RF_LD(A_SR, 0), sl = RF_LD(A_SR, -1);
+    const double inv = frcp(sl + sr);
+    const double rr = sl * inv, omrr = sr * inv;  // 1/(1+sqrt(rho_r/rho_l)) and its complement
+    const double u = RF_LD(A_U, -1) * rr + RF_LD(A_U, 0) * omrr;
+    const double v = RF_LD(A_V, -1) * rr + RF_LD(A_V, 0) * omrr;
+    const double c2x = (cs.gam * cs.rgaz) * (RF_LD(A_T, -1) * rr + RF_LD(A_T, 0) * omrr);
+    rspec = ::fabs(nxf * u + nyf * v) + ::sqrt(c2x * nx2);
+  }
+
+  // ---- Jameson x Ducros x dilatation sensor (ducrosfordnc_{i,j}.F) -------------------------------------------------
+  double eps2 = 0.0;
+  if (cs.k2 != 0.0) {
+    const double pm2 = RF_LD(A_P, -2), pm1 = RF_LD(A_P, -1), p0 = RF_LD(A_P, 0), pp1 = RF_LD(A_P, 1);
+    const double a1_ = ::fabs(pm1 - 2.0 * p0 + pp1), b1_ = ::fabs(pm1 + 2.0 * p0 + pp1);
+    const double a2_ = ::fabs(pm2 - 2.0 * pm1 + p0), b2_ = ::fabs(pm2 + 2.0 * pm1 + p0);
+    const bool second = a1_ * b2_ < a2_ * b1_;  // k1 < k2: max() takes the second operand
+    const double ks = (second ? a2_ : a1_) * frcp(second ? b2_ : b1_);
+    const double duc = ::fmax(RF_LD(A_DU, 0), RF_LD(A_DU, -1));
+    const double sn = ::sqrt(nx2);
+    const double t0 = RF_LD(A_DV, 0), t1 = RF_LD(A_DV, -1);
+    const double d0 = RF_LD(A_CS, 0) * sn + 1e-15, d1 = RF_LD(A_CS, -1) * sn + 1e-15;
+    const bool take1 = t0 * d1 > t1 * d0;  // x0 > x1: the dilatation switch is decreasing, max() is at the smaller argument
+    const double xs = 2.5 + 10.0 * (take1 ? t1 : t0) * frcp(take1 ? d1 : d0);
+    const double dxm = frcp(1.0 + ::exp(::fmin(2.0 * xs, 700.0)));  // (1 - tanh x) / 2
+    eps2 = cs.k2 * (ks * duc * dxm);
+  }
+  const double eps4 = ::fmax(0.0, cs.k4 - eps2 * 12.0);
+
+  // ---- convective flux + 5th-difference operand: one pass over cells -3 .. 2 -----------------------------------
+  constexpr double denom = 1.0 / 60.0;
+  constexpr double ck[6] = {denom, -8.0 * denom, 37.0 * denom, 37.0 * denom, -8.0 * denom, denom};
+  constexpr double dk[6] = {-denom, 5.0 * denom, -10.0 * denom, 10.0 * denom, -5.0 * denom, denom};
+  double fx[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, pr[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  double pbar = 0.0;
+#pragma unroll
+  for (int k = -3; k <= 2; ++k) {
+    const double u = RF_LD(A_U, k), v = RF_LD(A_V, k), p = RF_LD(A_P, k);
+    const double cv = ck[k + 3] * (u * nxf + v * nyf);
+    pbar += ck[k + 3] * p;
+#pragma unroll
+    for (int e = 0; e < 5; ++e) {
+      const double we = RF_LD(A_W + e, k);
+      fx[e] += cv * (e == 4 ? we + p : we);
+      pr[e] += dk[k + 3] * we;
+    }
+  }
+  fx[1] += pbar * nxf;
+  fx[2] += pbar * nyf;
+
+  // ---- assembly (dissipation_ducros_{i,j}.F, fluxnumassembly_{i,j}.F) ----------------------------------------------
+  const double e2h = 0.5 * eps2;
+#pragma unroll
+  for (int e = 0; e < 5; ++e) {
+    const double diff = RF_LD(A_W + e, 0) - RF_LD(A_W + e, -1);
+    hn[e] = fx[e] - rspec * (e2h * diff + eps4 * pr[e]) - visc[e];
+  }
+#undef RF_LD
+}
+
+// ---- phase 2: i-faces (i0 + col, j0 + row) -------------------------------------------------------------------------
+// warps 0..7: row = warp, col = lane (the left faces of the tile's cells); warp 8, lanes 0..7: the right faces of the
+// last column (col = 32, row = lane).  Both mappings are bank-conflict free on the 38-double pitch.
+struct FaceId {
+  int row, col, fi, fj;
+  bool active, generic;
+};
+BC_HD FaceId iface_of(const TileCtx& t, int tid) {
+  FaceId f;
+  if (tid < OI * OJ) { f.row = tid / OI; f.col = tid % OI; }
+  else { f.row = tid - OI * OJ; f.col = OI; }
+  f.fi = t.i0 + f.col;
+  f.fj = t.j0 + f.row;
+  f.active = f.row < OJ && f.fi <= t.g.im + 1 && f.fj <= t.g.jm;
+  f.generic = t.wall && f.fj <= 2;
+  return f;
+}
+BC_HD FaceId jface_of(const TileCtx& t, int tid) {
+  FaceId f;
+  f.row = tid / OI; f.col = tid % OI;
+  f.fi = t.i0 + f.col;
+  f.fj = t.j0 + f.row;
+  f.active = f.fi <= t.g.im && f.fj <= t.g.jm + 1;
+  f.generic = t.wall && f.fj <= 3;
+  return f;
+}
+BC_HD FaceGeom prefetch_iface(const TileCtx& t, int tid) {
+  const FaceId f = iface_of(t, tid);
+  if (f.active && !f.generic) return load_geom<0>(t, f.fi, f.fj);
+  return FaceGeom{};
+}
+BC_HD FaceGeom prefetch_jface(const TileCtx& t, int tid) {
+  const FaceId f = jface_of(t, tid);
+  if (f.active && !f.generic) return load_geom<1>(t, f.fi, f.fj);
+  return FaceGeom{};
+}
+
+BC_HD void phase2(const TileCtx& t, int tid, const FaceGeom& G) {
+  const FaceId f = iface_of(t, tid);
+  if (!f.active) return;
+  double hn[5];
+  const int a = f.col + H, b = f.row + H;
+  if (f.generic) {
+    PVar h[5];
+    face_flux<0, true, FACE_MAIN>(make_acc(t, a, b), t.c, h);
+#pragma unroll
+    for (int e = 0; e < 5; ++e) hn[e] = h[e].v;
+  } else {
+    face_fast<0>(t, t.sm + a + b * PI, t.RB() + (f.row + 2) * RI_W + f.col, G, hn);
+  }
+  double* X = t.X();
+#pragma unroll
+  for (int e = 0; e < 5; ++e) X[(e * OJ + f.row) * XI_P + f.col] = hn[e];
+}
+
+// ---- phase 3: j-faces ----------------------------------------------------------------------------------------------
+BC_HD void phase3(const TileCtx& t, int tid, const FaceGeom& G) {
+  const FaceId f = jface_of(t, tid);
+  if (!f.active) return;
+  double hn[5];
+  const int a = f.col + H, b = f.row + H;
+  if (f.generic) {
+    PVar h[5];
+    const SmemAcc2 A = make_acc(t, a, b);
+    if (f.fj == 1) face_flux<1, true, FACE_WALL>(A, t.c, h);
+    else if (f.fj == 2) face_flux<1, true, FACE_NEAR3>(A, t.c, h);
+    else face_flux<1, false, FACE_NEAR5>(A, t.c, h);
+#pragma unroll
+    for (int e = 0; e < 5; ++e) hn[e] = h[e].v;
+  } else {
+    face_fast<1>(t, t.sm + a + b * PI, t.RB() + f.row * RJ_W + f.col + 2, G, hn);
+  }
+  double* X = t.X();
+#pragma unroll
+  for (int e = 0; e < 5; ++e) X[(e * (OJ + 1) + f.row) * XJ_P + f.col] = hn[e];
+}
+
+// ---- balance (rhs/balance.F:2-15) ------------------------------------------------------------------------------------
+BC_HD bool owns_cell(const TileCtx& t, int tid) { return tid < OI * OJ && t.i0 + tid % OI <= t.g.im && t.j0 + tid / OI <= t.g.jm; }
+BC_HD void balance_i(const TileCtx& t, int tid, double (&r)[5]) {
+  if (!owns_cell(t, tid)) return;
+  const int cx = tid % OI, cy = tid / OI;
+  const double* X = t.X();
+#pragma unroll
+  for (int e = 0; e < 5; ++e) r[e] = -(X[(e * OJ + cy) * XI_P + cx + 1] - X[(e * OJ + cy) * XI_P + cx]);
+}
+BC_HD void balance_j_store(const TileCtx& t, int tid, const double (&r)[5]) {
+  if (!owns_cell(t, tid)) return;
+  const int cx = tid % OI, cy = tid / OI;
+  const double* X = t.X();
+  const long long k = t.g.cidx(t.i0 + cx, t.j0 + cy);
+#pragma unroll
+  for (int e = 0; e < 5; ++e)
+    t.res[e * t.g.sc + k] = r[e] - (X[(e * (OJ + 1) + cy + 1) * XJ_P + cx] - X[(e * (OJ + 1) + cy) * XJ_P + cx]);
+}
+
+}  // namespace rf
+}  // namespace bcast

@@ -10,6 +10,7 @@
 // prims/gradient arrays (HBM traffic ~ the algorithmic 136 B per cell plus halo re-reads from L2).
 // Reference: srcfv/rhs/flux_num_dnc5.F90:7-226.
 #include "kernels.cuh"
+#include <cstdlib>
 
 namespace bcast {
 
@@ -210,6 +211,9 @@ __global__ void __launch_bounds__(TI* TJ, 3)
 cudaError_t launch_residual_tiled(const GridDesc& g, const SchemeArgs& a, bool wall, double* res, const double* w, const double* nx,
                                   const double* ny, const double* vol, const double* volf, cudaStream_t st) {
   if (g.im < 4 || g.jm < 6) return launch_residual_generic(g, a, wall, 0, res, w, nullptr, nx, ny, vol, volf, nullptr, st);
+  // second-generation kernel (residual_fast.cu) unless the first one is asked for as a cross-check
+  static const bool v1 = getenv("BROADCAST_B200_RESIDUAL_V1") != nullptr;
+  if (!v1) return launch_residual_fast(g, a, wall, res, w, nx, ny, vol, volf, st);
   constexpr int TI = 32, TJ = 8;
   using TL = Tile<TI, TJ>;
   const SchemeConsts c = make_consts(a.cp, a.cv, a.prandtl, a.gam, a.rgaz, a.cs, a.muref, a.tref, a.s_suth, a.k2, a.k4);

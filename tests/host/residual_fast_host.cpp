@@ -1,0 +1,51 @@
+// Host build of the product's fused residual tile algorithm (broadcast_b200/csrc/residual_fast.cuh is host+device code):
+// TEST INFRASTRUCTURE so that the tile indexing and the re-associated face formulas can be checked against the oracle
+// on a machine without a GPU.  The CTA is emulated phase by phase (a loop over the 288 thread ids per phase, barriers
+// = loop boundaries).  Not part of the product; the product runs the same phase functions inside k_residual_fast.
+#include <vector>
+#include "../../broadcast_b200/csrc/residual_fast.cuh"
+
+using namespace bcast;
+
+extern "C" int rf_host_residual(double* res, const double* w, const double* nx, const double* ny, const double* vol, const double* volf,
+                                int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs, double muref,
+                                double tref, double s_suth, double k2, double k4, int im, int jm, int wall, int ioff, int img, int edges) {
+  if (gh != rf::H) return 1;
+  GridDesc g = make_grid(im, jm, gh);
+  if (img > 0) {
+    g.ioff = ioff;
+    g.img = img;
+    g.edges = edges;
+  }
+  std::vector<double> sm(rf::NSM);
+  std::vector<double> r((size_t)rf::NT * 5);
+  rf::TileCtx t;
+  t.sm = sm.data();
+  t.g = g;
+  t.c = make_consts(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4);
+  t.sqgr = std::sqrt(gam * rgaz);
+  t.wall = wall != 0;
+  t.w = w; t.nx = nx; t.ny = ny; t.vol = vol; t.volf = volf; t.res = res;
+  for (int by = 0; by < (jm + rf::OJ - 1) / rf::OJ; ++by)
+    for (int bx = 0; bx < (im + rf::OI - 1) / rf::OI; ++bx) {
+      t.i0 = 1 + bx * rf::OI;
+      t.j0 = 1 + by * rf::OJ;
+      std::fill(sm.begin(), sm.end(), std::nan(""));   // reading an unwritten shared entry must show up
+      for (int tid = 0; tid < rf::NT; ++tid) rf::phase0(t, tid);
+      for (int tid = 0; tid < rf::NT; ++tid) rf::phase1(t, tid);
+      if (t.has_ghost_sensor())
+        for (int tid = 0; tid < rf::NT; ++tid) rf::phase1b(t, tid);
+      for (int tid = 0; tid < rf::NT; ++tid) rf::phase2(t, tid, rf::prefetch_iface(t, tid));
+      for (int tid = 0; tid < rf::NT; ++tid) {
+        double (&rr)[5] = *reinterpret_cast<double(*)[5]>(&r[(size_t)tid * 5]);
+        rf::balance_i(t, tid, rr);
+        rf::phase_rj(t, tid);
+      }
+      for (int tid = 0; tid < rf::NT; ++tid) rf::phase3(t, tid, rf::prefetch_jface(t, tid));
+      for (int tid = 0; tid < rf::NT; ++tid) {
+        const double (&rr)[5] = *reinterpret_cast<double(*)[5]>(&r[(size_t)tid * 5]);
+        rf::balance_j_store(t, tid, rr);
+      }
+    }
+  return 0;
+}

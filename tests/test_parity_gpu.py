@@ -38,7 +38,8 @@ def test_boundary_fill_and_residual(gpu, ref, kind, im, jm):
     finally:
         del os.environ['BROADCAST_B200_GENERIC']
     assert np.all(H.rel_err(rg, rb) < TOL), H.rel_err(rg, rb)
-    assert np.all(H.rel_err(rg, ra) < 1e-13), H.rel_err(rg, ra)
+    # (the fused kernel evaluates re-associated face formulas, residual_fast.cuh: same bound, not tighter)
+    assert np.all(H.rel_err(rg, ra) < TOL), H.rel_err(rg, ra)
     # ghosts of the residual are never written
     gh = a.gh
     assert np.all(ra[:gh] == 0) and np.all(ra[:, :gh] == 0)

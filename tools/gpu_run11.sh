@@ -1,0 +1,8 @@
+set -x
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/r11_pytest.log; cat gpurun_out/r11_pytest.log
+timeout 600 python tools/res_probe.py 2048x512 8192x2048 > gpurun_out/r11_res_probe.log 2>&1; cat gpurun_out/r11_res_probe.log
+timeout 900 python tools/jac_probe.py 2048x512 4096x1024 > gpurun_out/r11_jac_probe.log 2>&1; cat gpurun_out/r11_jac_probe.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_residual_fast -s 3 -c 1 -o gpurun_out/r11_residual_full python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-jacobian > gpurun_out/r11_ncu_res.log 2>&1; tail -n 3 gpurun_out/r11_ncu_res.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_jac_assemble_rt|k_balance_faces5|k_face_packages" -s 3 -c 6 -o gpurun_out/r11_jac_full python tools/jac_probe.py 2048x512 > gpurun_out/r11_ncu_jac.log 2>&1; tail -n 3 gpurun_out/r11_ncu_jac.log
+ls -la gpurun_out

@@ -1,0 +1,7 @@
+set -x
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/r12_pytest.log; cat gpurun_out/r12_pytest.log
+timeout 600 python tools/res_probe.py 2048x512 8192x2048 > gpurun_out/r12_res_probe.log 2>&1; cat gpurun_out/r12_res_probe.log
+timeout 900 python tools/jac_probe.py 2048x512 4096x1024 > gpurun_out/r12_jac_probe.log 2>&1; cat gpurun_out/r12_jac_probe.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_residual_fast -s 3 -c 1 -o gpurun_out/r12_residual_full python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-jacobian > gpurun_out/r12_ncu_res.log 2>&1; tail -n 3 gpurun_out/r12_ncu_res.log
+ls -la gpurun_out
