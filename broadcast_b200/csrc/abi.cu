@@ -234,11 +234,11 @@ int bcd_residual(double* residu, const double* w, const double* nx, const double
   const GridDesc g = make_grid_ctx(im, jm, gh);
   const SchemeArgs a = sargs(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4);
   cudaError_t e;
-  if (use_generic) {
+  if (use_generic == RES_GENERIC) {
     e = launch_residual_generic(g, a, wall != 0, 0, residu, w, nullptr, nx, ny, vol, volf, nullptr, (cudaStream_t)stream);
     g_launches += 4;
   } else {
-    e = launch_residual_tiled(g, a, wall != 0, residu, w, nx, ny, vol, volf, (cudaStream_t)stream);
+    e = launch_residual_tiled(g, a, wall != 0, residu, w, nx, ny, vol, volf, (cudaStream_t)stream, use_generic);
     g_launches += 1;
   }
   if (e != cudaSuccess) return cuda_fail(e, "bcd_residual");

@@ -33,7 +33,9 @@ constexpr int OI = 32, OJ = 8;
 constexpr int PI = OI + 2 * H, PJ = OJ + 2 * H;  // staged cells: i0-3 .. i0+34, j0-3 .. j0+10
 constexpr int NC = PI * PJ;
 constexpr int NT = 288;
-enum { A_W = 0, A_U = 5, A_V = 6, A_WZ = 7, A_T = 8, A_P = 9, A_MU = 10, A_SR = 11, A_CS = 12, A_DV = 13, A_DU = 14, NARR = 15 };
+// derived per-cell arrays (the five planes of w live in their own buffer so that TMA can deliver them, double buffered)
+enum { A_U = 0, A_V = 1, A_WZ = 2, A_T = 3, A_P = 4, A_MU = 5, A_SR = 6, A_CS = 7, A_DV = 8, A_DU = 9, NARR = 10 };
+constexpr int WBUF = 2672;                    // doubles per w buffer: 5 * NC = 2660 rounded up to a multiple of 128 bytes
 // normal-direction interpolations R_q (q = u, v, w, T) of the faces a CTA's viscous gradients read
 constexpr int RI_W = OI + 1, RI_H = OJ + 4;   // i-faces i0 .. i0+32, rows j0-2 .. j0+9
 constexpr int RJ_W = OI + 4, RJ_H = OJ + 1;   // j-faces columns i0-2 .. i0+33, rows j0 .. j0+8
@@ -42,7 +44,10 @@ constexpr int NRB = 4 * RQ;
 constexpr int XI_P = OI + 1, XJ_P = OI;       // pitches of the face-flux exchange buffer
 constexpr int NXB = 5 * (OJ + 1) * OI;        // 1440 >= 5 * 8 * 33
 constexpr int GW = OI + 2, GH_ = OJ + 2;      // sensor cells: i0-1 .. i0+32, j0-1 .. j0+8 (scratch divu / vort alias X)
-constexpr int NSM = NARR * NC + NRB + NXB;    // doubles of shared memory per CTA (88 032 bytes)
+constexpr int NSM_REST = NARR * NC + NRB + NXB;
+constexpr int NSM = WBUF + NSM_REST;          // doubles of shared memory per CTA, one w buffer (88 128 bytes)
+constexpr int NSM_TMA = 2 * WBUF + NSM_REST + 2;   // two w buffers + two mbarriers (109 520 bytes)
+static_assert(5 * NC <= WBUF, "w buffer");
 static_assert(2 * GW * GH_ <= NXB, "scratch aliasing");
 static_assert(RJ_W * RJ_H <= RQ, "R buffer");
 
@@ -62,14 +67,16 @@ BC_HD double frcp(double x) {
 }
 
 struct TileCtx {
-  double* sm;
-  GridDesc g;
-  SchemeConsts c;
+  double* wsm;  // the five planes of w of the tile, [e][b][a]  (exactly the box a 3-D TMA load of w delivers)
+  double* sm;   // derived arrays, R buffer, exchange buffer
+  const GridDesc& g;      // (references: in the kernels these are the kernel parameters, read from the constant bank)
+  const SchemeConsts& c;
   double sqgr;  // sqrt(gam * rgaz)
   bool wall;
   const double *w, *nx, *ny, *vol, *volf;
   double* res;
   int i0, j0;  // first output cell of the tile
+  BC_HD TileCtx(const GridDesc& g_, const SchemeConsts& c_) : g(g_), c(c_) {}
   BC_HD double* arr(int a) const { return sm + a * NC; }
   BC_HD double* RB() const { return sm + NARR * NC; }
   BC_HD double* X() const { return sm + NARR * NC + NRB; }
@@ -82,14 +89,16 @@ struct TileCtx {
 // accessor over the shared arrays for the reference-shaped templates of scheme.cuh (wall rows, gradients)
 struct SmemAcc2 {
   using DT = Zero;
-  const double* s;  // sm + shared index of the base cell
+  const double* s;   // sm + shared index of the base cell
+  const double* sw;  // wsm + shared index of the base cell
   const double *nx, *ny, *vol, *volf;
   long long c, n;
   int ldc, ldn;
   long long sc, sn;
   template <int OI_, int OJ_> BC_HD double raw(int a) const { return s[a * NC + OI_ + OJ_ * PI]; }
   template <int OI_, int OJ_> BC_HD PVar ld(int a) const { return PVar{raw<OI_, OJ_>(a), {}}; }
-  template <int OI_, int OJ_> BC_HD PVar W(int e) const { return ld<OI_, OJ_>(A_W + e); }
+  template <int OI_, int OJ_> BC_HD double rawW(int e) const { return sw[e * NC + OI_ + OJ_ * PI]; }
+  template <int OI_, int OJ_> BC_HD PVar W(int e) const { return PVar{rawW<OI_, OJ_>(e), {}}; }
   template <int OI_, int OJ_> BC_HD PVar U() const { return ld<OI_, OJ_>(A_U); }
   template <int OI_, int OJ_> BC_HD PVar V() const { return ld<OI_, OJ_>(A_V); }
   template <int OI_, int OJ_> BC_HD PVar Wz() const { return ld<OI_, OJ_>(A_WZ); }
@@ -97,7 +106,7 @@ struct SmemAcc2 {
   template <int OI_, int OJ_> BC_HD PVar P() const { return ld<OI_, OJ_>(A_P); }
   template <int OI_, int OJ_> BC_HD PVar Mu() const { return ld<OI_, OJ_>(A_MU); }
   template <int OI_, int OJ_> BC_HD PVar H() const {
-    return PVar{(raw<OI_, OJ_>(A_W + 4) + raw<OI_, OJ_>(A_P)) * (1.0 / raw<OI_, OJ_>(A_W)), {}};
+    return PVar{(rawW<OI_, OJ_>(4) + raw<OI_, OJ_>(A_P)) * (1.0 / rawW<OI_, OJ_>(0)), {}};
   }
   template <int OI_, int OJ_> BC_HD auto SENS() const {   // A_DV holds vol * divu
     return CellSens<Zero, Zero>{PVar{raw<OI_, OJ_>(A_DV) / VOL<OI_, OJ_>(), {}}, ld<OI_, OJ_>(A_DU)};
@@ -111,6 +120,7 @@ struct SmemAcc2 {
 BC_HD SmemAcc2 make_acc(const TileCtx& t, int a, int b) {  // shared coordinates (a, b): cell (i0-H+a, j0-H+b)
   SmemAcc2 A;
   A.s = t.sm + a + b * PI;
+  A.sw = t.wsm + a + b * PI;
   A.nx = t.nx; A.ny = t.ny; A.vol = t.vol; A.volf = t.volf;
   A.c = t.g.cidx(t.i0 - H + a, t.j0 - H + b);
   A.n = t.g.nidx(t.i0 - H + a, t.j0 - H + b);
@@ -119,6 +129,8 @@ BC_HD SmemAcc2 make_acc(const TileCtx& t, int a, int b) {  // shared coordinates
 }
 
 // ---- phase 0: stage w, cell primitives (phys/Primitives.F:2-34, phys/viscosity.F:1) -------------------------------
+// STAGED: the five planes of w are already in t.wsm (TMA); otherwise they are loaded from global memory here.
+template <bool STAGED>
 BC_HD void phase0(const TileCtx& t, int tid) {
   const GridDesc& g = t.g;
   constexpr int NIT = (NC + NT - 1) / NT;
@@ -130,10 +142,15 @@ BC_HD void phase0(const TileCtx& t, int tid) {
     const int a = idx % PI, b = idx / PI;
     const int gi = t.i0 - H + a, gj = t.j0 - H + b;
     q[it][0] = 1.0; q[it][1] = 0.0; q[it][2] = 0.0; q[it][3] = 0.0; q[it][4] = 1.0;
-    if (idx < NC && gi <= g.im + g.gh && gj <= g.jm + g.gh) {
-      const double* p = t.w + g.cidx(gi, gj);
+    if (idx < NC && gi <= g.im + g.gh && gj <= g.jm + g.gh) {   // cells beyond the padded array (TMA: zero fill) get a sane state
+      if constexpr (STAGED) {
 #pragma unroll
-      for (int e = 0; e < 5; ++e) q[it][e] = BC_LDG(p + e * g.sc);
+        for (int e = 0; e < 5; ++e) q[it][e] = t.wsm[e * NC + idx];
+      } else {
+        const double* p = t.w + g.cidx(gi, gj);
+#pragma unroll
+        for (int e = 0; e < 5; ++e) q[it][e] = BC_LDG(p + e * g.sc);
+      }
     }
   }
 #pragma unroll
@@ -148,12 +165,11 @@ BC_HD void phase0(const TileCtx& t, int tid) {
     const double tl = eloc * t.c.cvm1;
     const double p = t.c.gam1 * q0 * eloc;
     const double sqt = ::sqrt(tl);
+    if constexpr (!STAGED) {
+      double* sw = t.wsm + idx;
+      sw[0] = q0; sw[NC] = q1; sw[2 * NC] = q2; sw[3 * NC] = q3; sw[4 * NC] = q4;
+    }
     double* s = t.sm + idx;
-    s[(A_W + 0) * NC] = q0;
-    s[(A_W + 1) * NC] = q1;
-    s[(A_W + 2) * NC] = q2;
-    s[(A_W + 3) * NC] = q3;
-    s[(A_W + 4) * NC] = q4;
     s[A_U * NC] = u;
     s[A_V * NC] = v;
     s[A_WZ * NC] = wz;
@@ -252,7 +268,7 @@ BC_HD void phase_rj(const TileCtx& t, int tid) {
 }
 
 // ---- one regular face (FACE_MAIN, compact o4 viscous gradients) ---------------------------------------------------
-// s: shared pointer of the face cell (array 0); rb: R buffer entry of this face for q = 0 (quantity stride RQ, cross
+// s / sw: shared pointers of the face cell in the derived arrays / the w planes; rb: R buffer entry of this face for q = 0 (quantity stride RQ, cross
 // stride RC); n / c: node- and cell-layout indices of the face cell in the global metric arrays.
 // Face metrics, loaded from global memory BEFORE the phases that precede the face evaluation so that their latency is
 // hidden: face normal and the eight dual-cell normals (flux_visqueux_o4_{i,j}.F) with the scalings folded in.
@@ -286,14 +302,15 @@ BC_HD FaceGeom load_geom(const TileCtx& t, int fi, int fj) {
   return G;
 }
 
-// s: shared pointer of the face cell (array 0); rb: R buffer entry of this face for q = 0 (quantity stride RQ, cross
+// s / sw: shared pointers of the face cell in the derived arrays / the w planes; rb: R buffer entry of this face for q = 0 (quantity stride RQ, cross
 // stride RC)
 template <int DIR>
-BC_HD void face_fast(const TileCtx& t, const double* s, const double* rb, const FaceGeom& G, double (&hn)[5]) {
+BC_HD void face_fast(const TileCtx& t, const double* s, const double* sw, const double* rb, const FaceGeom& G, double (&hn)[5]) {
   constexpr int SA = DIR == 0 ? 1 : PI;
   constexpr int RC = DIR == 0 ? RI_W : 1;
   const SchemeConsts& cs = t.c;
 #define RF_LD(A_, K_) s[(A_) * NC + (K_) * SA]
+#define RF_LW(E_, K_) sw[(E_) * NC + (K_) * SA]
   const double nxf = G.nxf, nyf = G.nyf;
   const double nApx = G.nApx, nAmx = G.nAmx, nApy = G.nApy, nAmy = G.nAmy;
   const double nCpx = G.nCpx, nCmx = G.nCmx, nCpy = G.nCpy, nCmy = G.nCmy;
@@ -370,7 +387,7 @@ BC_HD void face_fast(const TileCtx& t, const double* s, const double* rb, const 
     pbar += ck[k + 3] * p;
 #pragma unroll
     for (int e = 0; e < 5; ++e) {
-      const double we = RF_LD(A_W + e, k);
+      const double we = RF_LW(e, k);
       fx[e] += cv * (e == 4 ? we + p : we);
       pr[e] += dk[k + 3] * we;
     }
@@ -382,10 +399,11 @@ BC_HD void face_fast(const TileCtx& t, const double* s, const double* rb, const 
   const double e2h = 0.5 * eps2;
 #pragma unroll
   for (int e = 0; e < 5; ++e) {
-    const double diff = RF_LD(A_W + e, 0) - RF_LD(A_W + e, -1);
+    const double diff = RF_LW(e, 0) - RF_LW(e, -1);
     hn[e] = fx[e] - rspec * (e2h * diff + eps4 * pr[e]) - visc[e];
   }
 #undef RF_LD
+#undef RF_LW
 }
 
 // ---- phase 2: i-faces (i0 + col, j0 + row) -------------------------------------------------------------------------
@@ -436,7 +454,7 @@ BC_HD void phase2(const TileCtx& t, int tid, const FaceGeom& G) {
 #pragma unroll
     for (int e = 0; e < 5; ++e) hn[e] = h[e].v;
   } else {
-    face_fast<0>(t, t.sm + a + b * PI, t.RB() + (f.row + 2) * RI_W + f.col, G, hn);
+    face_fast<0>(t, t.sm + a + b * PI, t.wsm + a + b * PI, t.RB() + (f.row + 2) * RI_W + f.col, G, hn);
   }
   double* X = t.X();
 #pragma unroll
@@ -458,7 +476,7 @@ BC_HD void phase3(const TileCtx& t, int tid, const FaceGeom& G) {
 #pragma unroll
     for (int e = 0; e < 5; ++e) hn[e] = h[e].v;
   } else {
-    face_fast<1>(t, t.sm + a + b * PI, t.RB() + f.row * RJ_W + f.col + 2, G, hn);
+    face_fast<1>(t, t.sm + a + b * PI, t.wsm + a + b * PI, t.RB() + f.row * RJ_W + f.col + 2, G, hn);
   }
   double* X = t.X();
 #pragma unroll

@@ -127,11 +127,13 @@ class Block:
                         self._ck(L.bcd_jn_match(_p(t), I(prr), gh, gh, gh, gh, im, jm, _p(t), I(prd), gh, gh, gh, gh, im, jm, I(tr), em,
                                                 st), "bcd_jn_match")
 
-    def residual(self, generic=False, w=None, out=None):
+    def residual(self, generic=False, w=None, out=None, variant=None):
+        """variant: 0 default fused kernel, 1 generic four-kernel pipeline, 2 fused + TMA/persistent, 3 first-generation fused"""
         w = self.w if w is None else w
         out = self.res if out is None else out
+        v = int(variant) if variant is not None else (1 if generic else 0)
         self.call("bcd_residual", _p(out), _p(w), _p(self.nx), _p(self.ny), _p(self.vol), _p(self.volf), self.gh, *self._phys,
-                  self.im, self.jm, self.wall, 1 if generic else 0, self._stream())
+                  self.im, self.jm, self.wall, v, self._stream())
         return out
 
     def tangent(self, wd, ndir, out, w=None, rect=None):

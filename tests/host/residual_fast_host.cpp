@@ -9,7 +9,7 @@ using namespace bcast;
 
 extern "C" int rf_host_residual(double* res, const double* w, const double* nx, const double* ny, const double* vol, const double* volf,
                                 int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs, double muref,
-                                double tref, double s_suth, double k2, double k4, int im, int jm, int wall, int ioff, int img, int edges) {
+                                double tref, double s_suth, double k2, double k4, int im, int jm, int wall, int ioff, int img, int edges, int staged) {
   if (gh != rf::H) return 1;
   GridDesc g = make_grid(im, jm, gh);
   if (img > 0) {
@@ -19,10 +19,10 @@ extern "C" int rf_host_residual(double* res, const double* w, const double* nx, 
   }
   std::vector<double> sm(rf::NSM);
   std::vector<double> r((size_t)rf::NT * 5);
-  rf::TileCtx t;
-  t.sm = sm.data();
-  t.g = g;
-  t.c = make_consts(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4);
+  const SchemeConsts sc = make_consts(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4);
+  rf::TileCtx t(g, sc);
+  t.wsm = sm.data();
+  t.sm = sm.data() + rf::WBUF;
   t.sqgr = std::sqrt(gam * rgaz);
   t.wall = wall != 0;
   t.w = w; t.nx = nx; t.ny = ny; t.vol = vol; t.volf = volf; t.res = res;
@@ -31,7 +31,17 @@ extern "C" int rf_host_residual(double* res, const double* w, const double* nx, 
       t.i0 = 1 + bx * rf::OI;
       t.j0 = 1 + by * rf::OJ;
       std::fill(sm.begin(), sm.end(), std::nan(""));   // reading an unwritten shared entry must show up
-      for (int tid = 0; tid < rf::NT; ++tid) rf::phase0(t, tid);
+      if (staged) {   // what the TMA load of k_residual_fast_tma delivers: the (PI, PJ, 5) box of w, zero fill outside the array
+        for (int e = 0; e < 5; ++e)
+          for (int b = 0; b < rf::PJ; ++b)
+            for (int a = 0; a < rf::PI; ++a) {
+              const int si = t.i0 - 1 + a, sj = t.j0 - 1 + b;   // storage coordinates of cell (i0-3+a, j0-3+b)
+              t.wsm[e * rf::NC + a + b * rf::PI] = (si < g.ni() && sj < g.nj()) ? w[e * g.sc + si + (long long)sj * g.ldc] : 0.0;
+            }
+        for (int tid = 0; tid < rf::NT; ++tid) rf::phase0<true>(t, tid);
+      } else {
+        for (int tid = 0; tid < rf::NT; ++tid) rf::phase0<false>(t, tid);
+      }
       for (int tid = 0; tid < rf::NT; ++tid) rf::phase1(t, tid);
       if (t.has_ghost_sensor())
         for (int tid = 0; tid < rf::NT; ++tid) rf::phase1b(t, tid);
