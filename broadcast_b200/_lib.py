@@ -53,7 +53,7 @@ def _conv(a):
 # arguments that are 64-bit integers in the header
 _INT64_ARGS = {
     "computejacobianfromjv": (10,), "computejacobianfromjv_relaxed": (10,), "computejacobianfromjv_relaxed_withjn": (10,),
-    "computejacobianfromjv_withjn": (10,), "computejacobianfromdz": (10,),
+    "computejacobianfromjv_withjn": (10,), "computejacobianfromdz": (10,), "computejacobianfromjv_relaxed_withjnandcheck": (10,),
 }
 
 

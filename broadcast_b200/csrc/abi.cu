@@ -496,6 +496,39 @@ int bc_computejacobianfromjv_relaxed_withjn(double* jac, int32_t* ia, int32_t* j
   if (!coefdiag) return fail(BC_ERR_ARG, "coefdiag is null");
   return scatter_host(SCATTER_JV_RELAXED_JN, jac, ia, ja, resd, m, l, k, gh, im, jm, nbentry, coefdiag, nullptr);
 }
+int bc_computejacobianfromjv_relaxed_withjnandcheck(double* jac, int32_t* ia, int32_t* ja, const double* resd, int m, int l, int k,
+                                                    int gh, int im, int jm, int64_t nbentry, const double* coefdiag, double mini,
+                                                    int n) {
+  if (!coefdiag) return fail(BC_ERR_ARG, "coefdiag is null");
+  if (int rc = check_device()) return rc;
+  if (int rc = check_dims(im, jm, gh)) return rc;
+  const int s = 2 * gh + 1;
+  if (m < 0 || m > 4 || l < 0 || l >= s || k < 0 || k >= s || n < 0 || n > 1) return fail(BC_ERR_ARG, "colour / zone indices out of range");
+  const GridDesc g = make_grid(im, jm, gh);
+  const long long nn = 5LL * im * jm;
+  const long long base = (long long)k * nn + (long long)l * nn * s + (long long)m * nn * s * s + (long long)n * nn * 5 * s * s;
+  if (base + nn > nbentry) return fail(BC_ERR_ARG, "jac/ia/ja too short for this colour and zone");
+  double* dres = dbuf<double>(S_RES, g.sc * 5);
+  double* dseg = dbuf<double>(S_SEG, nn);
+  int* dia = dbuf<int>(S_IA, nn);
+  int* dja = dbuf<int>(S_JA, nn);
+  double* dcoef = dbuf<double>(S_AUX, (size_t)im * jm);
+  if (!dres || !dseg || !dia || !dja || !dcoef) return fail(BC_ERR_ALLOC, "device allocation failed");
+  CK(cudaMemcpyAsync(dres, resd, sizeof(double) * g.sc * 5, cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpyAsync(dcoef, coefdiag, sizeof(double) * im * jm, cudaMemcpyHostToDevice, 0));
+  // the routine is read-modify-write on its slot segment
+  CK(cudaMemcpyAsync(dseg, jac + base, sizeof(double) * nn, cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpyAsync(dia, ia + base, sizeof(int) * nn, cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpyAsync(dja, ja + base, sizeof(int) * nn, cudaMemcpyHostToDevice, 0));
+  cudaError_t e = launch_scatter_check(g, dseg, dia, dja, dres, m, l, k, dcoef, mini, n, 0);
+  g_launches += 1;
+  if (e != cudaSuccess) return cuda_fail(e, "computejacobianfromjv_relaxed_withjnandcheck");
+  CK(cudaMemcpyAsync(jac + base, dseg, sizeof(double) * nn, cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(ia + base, dia, sizeof(int) * nn, cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(ja + base, dja, sizeof(int) * nn, cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  return BC_OK;
+}
 int bc_computejacobianfromjv_withjn(double* jac, int32_t* ia, int32_t* ja, const double* resd, int m, int l, int k, int gh, int im,
                                     int jm, int64_t nbentry) {
   return scatter_host(SCATTER_JV_JN, jac, ia, ja, resd, m, l, k, gh, im, jm, nbentry, nullptr, nullptr);

@@ -67,26 +67,59 @@ __global__ void __launch_bounds__(128) k_jac_assemble(GridDesc g, SchemeConsts c
 __constant__ JacTab kJacTabDev = fj::make_jac_tab();
 
 // table-driven assembly: one runtime loop over the 29 column slots (see facejac.cuh).  CTA = 32 x 4 row cells; the
-// viscous subset (14 fields) of the packages of its 33x4 i-faces and 32x5 j-faces is staged in shared memory (32 KB).
+// staged subset (27 of the 54 fields: everything that more than two column cells of a face read) of the packages of its
+// 33x4 i-faces and 32x5 j-faces lives in shared memory (62.8 KB); ncu of the 14-field version: 1 160 package LDGs per cell
+// at 14 % L1 hit rate, long_scoreboard 6.6 per issue (profiles/r1_d_summary.md).
 constexpr int JT_I = 32, JT_J = 4;
 __global__ void __launch_bounds__(JT_I* JT_J, 3)
     k_jac_assemble_rt(GridDesc g, SchemeConsts c, FieldPtrs f, Rect rc, const double* __restrict__ pkg, double* __restrict__ V,
                       const double* __restrict__ coefdiag) {
-  __shared__ double sI[FPK_NVS * JT_J * (JT_I + 1)];
-  __shared__ double sJ[FPK_NVS * (JT_J + 1) * JT_I];
+  extern __shared__ double jsm[];   // 62.8 KB: three CTAs per SM
+  double* sI = jsm;
+  double* sJ = jsm + FPK_NVS * JT_J * (JT_I + 1);
   const int tid = threadIdx.y * JT_I + threadIdx.x;
   const int bi0 = blockIdx.x * JT_I + rc.i0, bj0 = blockIdx.y * JT_J + rc.j0;
   const double* pI = pkg + (long long)FPK_VS * g.sc;
   const double* pJ = pkg + (long long)(FPK_N + FPK_VS) * g.sc;
-  for (int idx = tid; idx < FPK_NVS * JT_J * (JT_I + 1); idx += JT_I * JT_J) {
-    const int k = idx / (JT_J * (JT_I + 1)), r = idx % (JT_J * (JT_I + 1));
-    const int fi = bi0 + r % (JT_I + 1), fj = bj0 + r / (JT_I + 1);
-    if (fi <= rc.i1 + 1 && fj <= rc.j1) sI[idx] = __ldg(pI + k * g.sc + g.cidx(fi, fj));
+  // staging: eight loads in flight per thread before the first store (the loop was load -> store, one latency per element)
+  constexpr int NTH = JT_I * JT_J, UNR = 8;
+  {
+    constexpr int NI = FPK_NVS * JT_J * (JT_I + 1);
+    for (int base = tid; base < NI; base += NTH * UNR) {
+      double v[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int idx = base + u * NTH;
+        v[u] = 0.0;
+        if (idx < NI) {
+          const int k = idx / (JT_J * (JT_I + 1)), r = idx % (JT_J * (JT_I + 1));
+          const int fi = bi0 + r % (JT_I + 1), fj = bj0 + r / (JT_I + 1);
+          if (fi <= rc.i1 + 1 && fj <= rc.j1) v[u] = __ldg(pI + k * g.sc + g.cidx(fi, fj));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+        if (base + u * NTH < NI) sI[base + u * NTH] = v[u];
+    }
   }
-  for (int idx = tid; idx < FPK_NVS * (JT_J + 1) * JT_I; idx += JT_I * JT_J) {
-    const int k = idx / ((JT_J + 1) * JT_I), r = idx % ((JT_J + 1) * JT_I);
-    const int fi = bi0 + r % JT_I, fj = bj0 + r / JT_I;
-    if (fi <= rc.i1 && fj <= rc.j1 + 1) sJ[idx] = __ldg(pJ + k * g.sc + g.cidx(fi, fj));
+  {
+    constexpr int NJ = FPK_NVS * (JT_J + 1) * JT_I;
+    for (int base = tid; base < NJ; base += NTH * UNR) {
+      double v[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int idx = base + u * NTH;
+        v[u] = 0.0;
+        if (idx < NJ) {
+          const int k = idx / ((JT_J + 1) * JT_I), r = idx % ((JT_J + 1) * JT_I);
+          const int fi = bi0 + r % JT_I, fj = bj0 + r / JT_I;
+          if (fi <= rc.i1 && fj <= rc.j1 + 1) v[u] = __ldg(pJ + k * g.sc + g.cidx(fi, fj));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+        if (base + u * NTH < NJ) sJ[base + u * NTH] = v[u];
+    }
   }
   __syncthreads();
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -101,12 +134,22 @@ __global__ void __launch_bounds__(JT_I* JT_J, 3)
   const long long ncell = (long long)g.im * g.jm;
   const long long cell = (long long)(i - 1) + (long long)(j - 1) * g.im;
   const double cd = coefdiag ? coefdiag[cell] : 0.0;
+  double wn[5];   // state of the next slot's column cell: loaded one slot ahead
+  {
+    const long long kc = g.cidx(i + kJacTabDev.di[0], j + kJacTabDev.dj[0]);
+#pragma unroll
+    for (int e = 0; e < 5; ++e) wn[e] = __ldg(f.w + e * g.sc + kc);
+  }
 #pragma unroll 1
   for (int s = 0; s < JAC_NSLOT; ++s) {
     double wc[5], B[25];
-    const long long kc = g.cidx(i + kJacTabDev.di[s], j + kJacTabDev.dj[s]);
 #pragma unroll
-    for (int e = 0; e < 5; ++e) wc[e] = __ldg(f.w + e * g.sc + kc);
+    for (int e = 0; e < 5; ++e) wc[e] = wn[e];
+    if (s + 1 < JAC_NSLOT) {
+      const long long kc = g.cidx(i + kJacTabDev.di[s + 1], j + kJacTabDev.dj[s + 1]);
+#pragma unroll
+      for (int e = 0; e < 5; ++e) wn[e] = __ldg(f.w + e * g.sc + kc);
+    }
     block_of_rt(kJacTabDev, s, fi0, fi1, fj0, fj1, wc, c, B);
     if (kJacTabDev.di[s] == 0 && kJacTabDev.dj[s] == 0) {
 #pragma unroll
@@ -136,8 +179,19 @@ cudaError_t launch_jacobian_faces(const GridDesc& g, const SchemeArgs& a, const 
   if (unrolled)
     k_jac_assemble<<<gr, blk, 0, st>>>(g, c, f, rc, pkg, values, coefdiag);
   else
-    k_jac_assemble_rt<<<dim3((rc.i1 - rc.i0 + JT_I) / JT_I, (rc.j1 - rc.j0 + JT_J) / JT_J), dim3(JT_I, JT_J), 0, st>>>(g, c, f, rc, pkg, values,
-                                                                                                                  coefdiag);
+  {
+    constexpr size_t SMEM = (size_t)FPK_NVS * (JT_J * (JT_I + 1) + (JT_J + 1) * JT_I) * sizeof(double);
+    static bool attr = false;
+    if (!attr) {
+      e = cudaFuncSetAttribute(k_jac_assemble_rt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(k_jac_assemble_rt, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return e;
+      attr = true;
+    }
+    k_jac_assemble_rt<<<dim3((rc.i1 - rc.i0 + JT_I) / JT_I, (rc.j1 - rc.j0 + JT_J) / JT_J), dim3(JT_I, JT_J), SMEM, st>>>(g, c, f, rc, pkg,
+                                                                                                                     values, coefdiag);
+  }
   count_launches(5);
   return cudaGetLastError();
 }

@@ -35,20 +35,21 @@ enum {
   FPK_RSE2 = 0,   // rspec * eps2
   FPK_RSE4 = 1,   // rspec * eps4
   FPK_SD = 2,     // [5] eps2 diff_e + eps4 pred_e              (x d rspec)
-  FPK_SE = 7,     // [5] rspec (diff_e - 12 chi pred_e)          (x d eps2),  chi = [eps4 > 0]
-  FPK_DRS = 12,   // [2][5] d rspec / d w_m of along-cells -1, 0
-  FPK_DEP = 22,   // [4] d eps2 / d p(s), s = -2..1
-  FPK_DET = 26,   // [2] d eps2 / d T(s), s = -1, 0
-  FPK_DEG = 28,   // [2][4] sensor cell s = -1, 0: coefficients of (wI, wJ) in d eps2/dU_c and in d eps2/dV_c
-  FPK_V1M = 36, FPK_V2M = 37, FPK_V3M = 38, FPK_V4M = 39,  // visc_e / mmu
-  // "viscous subset": the 14 fields every in-stencil column cell needs (staged in shared memory by the assembly kernel)
-  FPK_VS = 40,
+  FPK_DRS = 7,    // [2][5] d rspec / d w_m of along-cells -1, 0
+  FPK_DEP = 17,   // [4] d eps2 / d p(s), s = -2..1
+  FPK_DET = 21,   // [2] d eps2 / d T(s), s = -1, 0
+  FPK_V1M = 23, FPK_V2M = 24, FPK_V3M = 25, FPK_V4M = 26,  // visc_e / mmu
+  // "staged subset": the 27 fields that many column cells of a face's stencil read (14 of its 22 cells read SE and DEG, all
+  // 20 cells of the viscous box read the last 14); the assembly kernel stages them in shared memory
+  FPK_VS = 27,
+  FPK_SE = 27,    // [5] rspec (diff_e - 12 chi pred_e)          (x d eps2),  chi = [eps4 > 0]
+  FPK_DEG = 32,   // [2][4] sensor cell s = -1, 0: coefficients of (wI, wJ) in d eps2/dU_c and in d eps2/dV_c
   FPK_NXF = 40, FPK_NYF = 41,                              // face normal (length-scaled)
   FPK_MMU = 42, FPK_UU = 43, FPK_VV = 44, FPK_WW = 45,
   FPK_DNX = 46,   // [4] dual-cell normals x volm1: A+, A-, C+, C-   (x components)
   FPK_DNY = 50,   // [4]                                               (y components)
 };
-constexpr int FPK_NVS = 14;
+constexpr int FPK_NVS = 27;
 
 // a single cell seen through the accessor interface (for flux_f / flux_g)
 struct OneCell {
@@ -223,7 +224,7 @@ struct ColAcc {
   }
 };
 
-// handle of one face's package: field f at pk[f * stride]; the viscous subset (fields FPK_VS ..) may live in a second,
+// handle of one face's package: field f at pk[f * stride]; the staged subset (fields FPK_VS ..) may live in a second,
 // faster array (shared memory in the assembly kernel): field FPK_VS + k at vs[k * vstride]
 struct FaceCtx {
   const double* pk;
@@ -282,13 +283,13 @@ BC_HD void face_contrib(const FaceCtx& f, const SchemeConsts& c, double sgn, Col
         const double sd = sgn * f(FPK_SD + e);
 #pragma unroll
         for (int m = 0; m < 5; ++m) acc.dir[e][m] -= sd * drs[m];
-        acc.gT[e] -= sgn * f(FPK_SE + e) * det;
+        acc.gT[e] -= sgn * f.v(FPK_SE + e) * det;
       }
     }
     if constexpr (T == 0 && S >= -2 && S <= 1) {
       const double dep = f(FPK_DEP + (S + 2));
 #pragma unroll
-      for (int e = 0; e < 5; ++e) acc.gP[e] -= sgn * f(FPK_SE + e) * dep;
+      for (int e = 0; e < 5; ++e) acc.gP[e] -= sgn * f.v(FPK_SE + e) * dep;
     }
     // sensor: velocity gradients of the along-cells -1 and 0 (5-point crosses in GRID directions)
     {
@@ -301,16 +302,16 @@ BC_HD void face_contrib(const FaceCtx& f, const SchemeConsts& c, double sgn, Col
       if constexpr (anyL || anyR) {
         double eU = 0.0, eV = 0.0;
         if constexpr (anyL) {
-          eU += f(FPK_DEG + 0) * wIL + f(FPK_DEG + 1) * wJL;
-          eV += f(FPK_DEG + 2) * wIL + f(FPK_DEG + 3) * wJL;
+          eU += f.v(FPK_DEG + 0) * wIL + f.v(FPK_DEG + 1) * wJL;
+          eV += f.v(FPK_DEG + 2) * wIL + f.v(FPK_DEG + 3) * wJL;
         }
         if constexpr (anyR) {
-          eU += f(FPK_DEG + 4) * wIR + f(FPK_DEG + 5) * wJR;
-          eV += f(FPK_DEG + 6) * wIR + f(FPK_DEG + 7) * wJR;
+          eU += f.v(FPK_DEG + 4) * wIR + f.v(FPK_DEG + 5) * wJR;
+          eV += f.v(FPK_DEG + 6) * wIR + f.v(FPK_DEG + 7) * wJR;
         }
 #pragma unroll
         for (int e = 0; e < 5; ++e) {
-          const double se = sgn * f(FPK_SE + e);
+          const double se = sgn * f.v(FPK_SE + e);
           acc.gU[e] -= se * eU;
           acc.gV[e] -= se * eV;
         }
@@ -534,12 +535,12 @@ BC_HD void face_contrib_rt(const FaceCtx& f, const FaceTab& t, const SchemeConst
   if (t.side >= 0 || t.pk >= 0 || (t.flags & FT_SENS)) {
     double se[5];
 #pragma unroll
-    for (int e = 0; e < 5; ++e) se[e] = sgn * f(FPK_SE + e);
+    for (int e = 0; e < 5; ++e) se[e] = sgn * f.v(FPK_SE + e);
     double eP = 0.0, eU = 0.0, eV = 0.0, eT = 0.0;
     if (t.pk >= 0) eP = f(FPK_DEP + t.pk);
     if (t.flags & FT_SENS) {
-      eU = f(FPK_DEG + 0) * t.wIL + f(FPK_DEG + 1) * t.wJL + f(FPK_DEG + 4) * t.wIR + f(FPK_DEG + 5) * t.wJR;
-      eV = f(FPK_DEG + 2) * t.wIL + f(FPK_DEG + 3) * t.wJL + f(FPK_DEG + 6) * t.wIR + f(FPK_DEG + 7) * t.wJR;
+      eU = f.v(FPK_DEG + 0) * t.wIL + f.v(FPK_DEG + 1) * t.wJL + f.v(FPK_DEG + 4) * t.wIR + f.v(FPK_DEG + 5) * t.wJR;
+      eV = f.v(FPK_DEG + 2) * t.wIL + f.v(FPK_DEG + 3) * t.wJL + f.v(FPK_DEG + 6) * t.wIR + f.v(FPK_DEG + 7) * t.wJR;
     }
     if (t.side >= 0) {
       eT = f(FPK_DET + t.side);

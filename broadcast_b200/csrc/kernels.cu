@@ -276,6 +276,69 @@ __global__ void k_scatter(GridDesc g, int kind, double* __restrict__ jac, int* _
   ja[t] = col;
 }
 
+// computejacobianfromjv_relaxed_withjnandcheck (misc/ComputeJacobian.f90:1095-1204): two zones joined in i; zone n writes
+// the slot range shifted by n * 25 s^2 im jm and only where the slot is still empty (|jac| < mini) -- the slot arrays are
+// read-modify-write.  Integer rules restated statement by statement (dummy row 5 im jm - 2).
+__global__ void k_scatter_check(GridDesc g, double* __restrict__ jac, int* __restrict__ ia, int* __restrict__ ja,
+                                const double* __restrict__ resd, int m, int l, int k, const double* __restrict__ coefdiag, double mini,
+                                int zone) {
+  const int im = g.im, jm = g.jm, gh = g.gh, s = 2 * gh + 1;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= 5LL * im * jm) return;
+  const int i = (int)(t % im) + 1;
+  const int j = (int)((t / im) % jm) + 1;
+  const int e = (int)(t / ((long long)im * jm)) + 1;
+  const int dummy = 5 * im * jm - 2;
+  const int row = e - 1 + (j - 1) * 5 + (i - 1) * jm * 5;
+  ia[t] = row;
+  const int valj = (j <= k + 1 + gh) ? k : (j - gh - (k + 1) + 2 * gh) / s * s + k;
+  if (valj >= jm) {
+    ia[t] = dummy;
+    ja[t] = 0;
+    jac[t] = 0.0;
+    return;
+  }
+  int vali;
+  if (l <= gh)
+    vali = (i <= l + 1 + gh) ? l : (i - (l + 1) + gh) / s * s + l;
+  else
+    vali = (i <= l - gh) ? l : (i - (l + 1) + gh) / s * s + l;
+  bool clear_if_taken;   // what happens when the slot already holds an entry
+  if (zone == 0) {
+    if (vali >= im - 2 * gh) {
+      vali = l;
+      clear_if_taken = true;
+    } else {
+      clear_if_taken = false;
+    }
+  } else {
+    if (vali <= 2 * gh) {
+      vali = im - im % s + l;
+      if (vali > im - 1) vali -= s;
+      clear_if_taken = false;
+    } else {
+      clear_if_taken = true;
+    }
+  }
+  if (::fabs(jac[t]) < mini) {
+    const int col = m + valj * 5 + vali * jm * 5;
+    const double r = resd[(long long)(e - 1) * g.sc + g.cidx(i, j)];
+    ja[t] = col;
+    jac[t] = (row == col) ? coefdiag[(i - 1) + (long long)(j - 1) * im] - r : -r;
+  } else if (clear_if_taken) {
+    ia[t] = dummy;
+    ja[t] = 0;
+    jac[t] = 0.0;
+  }
+}
+
+cudaError_t launch_scatter_check(const GridDesc& g, double* seg_jac, int* seg_ia, int* seg_ja, const double* resd, int m, int l, int k,
+                                 const double* coefdiag, double mini, int zone, cudaStream_t st) {
+  const long long n = 5LL * g.im * g.jm;
+  k_scatter_check<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, seg_jac, seg_ia, seg_ja, resd, m, l, k, coefdiag, mini, zone);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_scatter(const GridDesc& g, int kind, double* seg_jac, int* seg_ia, int* seg_ja, const double* resd, int m, int l,
                            int k, const double* coefdiag, const double* vol, cudaStream_t st) {
   const long long n = 5LL * g.im * g.jm;

@@ -106,6 +106,10 @@ enum ScatterKind {
 cudaError_t launch_scatter(const GridDesc& g, int kind, double* seg_jac, int* seg_ia, int* seg_ja, const double* resd, int m, int l,
                            int k, const double* coefdiag /*im x jm or null*/, const double* vol /*cell layout or null*/, cudaStream_t st);
 
+// two-zone variant computejacobianfromjv_relaxed_withjnandcheck (:1095-1204): read-modify-write of the slot segment of zone `zone`
+cudaError_t launch_scatter_check(const GridDesc& g, double* seg_jac, int* seg_ia, int* seg_ja, const double* resd, int m, int l, int k,
+                                 const double* coefdiag, double mini, int zone, cudaStream_t st);
+
 // norms (srcfv/norm.F90)
 cudaError_t launch_norms(const GridDesc& g, const double* res, double* out10 /*device: sum r^2 [5], sum r^10 [5]*/, cudaStream_t st);
 

@@ -240,6 +240,15 @@ def build(backend):
         f.__name__ = name
         return f
 
+    def computejacobianfromjv_relaxed_withjnandcheck(jac, ia, ja, resd, m, l, k, gh, coefdiag, mini, n, im=None, jm=None, nbentry=None):
+        nb = _coo(jac, ia, ja)
+        coefdiag = _in(coefdiag)
+        gh = int(gh)
+        im = int(im) if im is not None else coefdiag.shape[0]
+        jm = int(jm) if jm is not None else coefdiag.shape[1]
+        B("computejacobianfromjv_relaxed_withjnandcheck", jac, ia, ja, _in(resd), int(m), int(l), int(k), gh, im, jm,
+          nb if nbentry is None else int(nbentry), coefdiag, float(mini), int(n))
+
     def computejacobianfromjv_withjn(jac, ia, ja, resd, m, l, k, gh, im, jm, nbentry=None):
         n = _coo(jac, ia, ja)
         gh, im, jm = _dims_from(resd, gh, im, jm)
@@ -255,6 +264,7 @@ def build(backend):
         testvector=testvector, testvector_partial=testvector_partial, computejacobianfromjv=computejacobianfromjv,
         computejacobianfromjv_relaxed=_relaxed("computejacobianfromjv_relaxed"),
         computejacobianfromjv_relaxed_withjn=_relaxed("computejacobianfromjv_relaxed_withjn"),
+        computejacobianfromjv_relaxed_withjnandcheck=computejacobianfromjv_relaxed_withjnandcheck,
         computejacobianfromjv_withjn=computejacobianfromjv_withjn, computejacobianfromdz=computejacobianfromdz)
 
     # ------------------------------------------------------------------ f_dz (spanwise operator rows)

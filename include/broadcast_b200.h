@@ -107,6 +107,12 @@ int bc_computejacobianfromjv_relaxed(double* jac, int32_t* ia, int32_t* ja, cons
                                      int gh, int im, int jm, int64_t nbentry, const double* coefdiag);
 int bc_computejacobianfromjv_relaxed_withjn(double* jac, int32_t* ia, int32_t* ja, const double* resd, int m, int l,
                                             int k, int gh, int im, int jm, int64_t nbentry, const double* coefdiag);
+/* misc/ComputeJacobian.f90:1095-1204 -- two zones joined in i (cylinder.py:1159): zone n (0 or 1) uses the slot range shifted
+ * by n * 25 (2gh+1)^2 im jm, writes only slots whose |jac| < mini and clears the others where the reference does; jac, ia,
+ * ja are read AND written. */
+int bc_computejacobianfromjv_relaxed_withjnandcheck(double* jac, int32_t* ia, int32_t* ja, const double* resd, int m, int l,
+                                                    int k, int gh, int im, int jm, int64_t nbentry, const double* coefdiag,
+                                                    double mini, int n);
 int bc_computejacobianfromjv_withjn(double* jac, int32_t* ia, int32_t* ja, const double* resd, int m, int l, int k,
                                     int gh, int im, int jm, int64_t nbentry);
 int bc_computejacobianfromdz(double* jac, int32_t* ia, int32_t* ja, const double* dz, int m, int l, int k, int gh,

@@ -175,6 +175,32 @@ def test_scatter_variants_integer_exact(gpu, ref):
         assert np.array_equal(out[0][0], out[1][0]), name
 
 
+def test_two_zone_scatter_with_check_integer_exact(gpu, ref):
+    """computejacobianfromjv_relaxed_withjnandcheck (misc/ComputeJacobian.f90:1095-1204, cylinder.py:1159): read-modify-write
+    of the slot arrays, zone 0 then zone 1 over the same colours, partially pre-filled slots"""
+    im, jm, gh = 37, 24, 3
+    s = 2 * gh + 1
+    rng = np.random.default_rng(5)
+    coef = np.asfortranarray(rng.uniform(0.5, 1.5, size=(im, jm)))
+    nb = 2 * 25 * s * s * im * jm
+    colours = [(0, 0, 0), (2, 3, 3), (4, 6, 5), (1, 4, 0), (3, 0, 6), (4, 6, 6), (2, 5, 2)]
+    resds = [np.asfortranarray(rng.standard_normal((im + 2 * gh, jm + 2 * gh, 5))) for _ in range(2 * len(colours))]
+    pre = rng.standard_normal(nb) * (rng.uniform(size=nb) < 0.3)          # 30 % of the slots already taken
+    out = []
+    for mods in (gpu, ref):
+        jac, ia, ja = pre.copy(), np.full(nb, 7, np.int32), np.full(nb, 11, np.int32)
+        q = 0
+        for n in (0, 1):
+            for (m, l, k) in colours:
+                mods["f_misc"].computejacobianfromjv_relaxed_withjnandcheck(jac, ia, ja, resds[q], m, l, k, gh, coef, 1e-14, n)
+                q += 1
+        out.append((jac, ia, ja))
+    assert np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[0][2], out[1][2])
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.count_nonzero(out[0][0] != pre) > 0
+
+
 def test_testvector(gpu, ref):
     im, jm, gh = 30, 22, 3
     for (m, l, k) in [(0, 0, 0), (4, 6, 6), (2, 3, 1)]:
