@@ -192,6 +192,15 @@ def main():
     if a.impl == "reference":
         run_reference(a)
         return
+    # rank 0 prints exactly ONE line on stdout: anything a library writes to fd 1 on the way (NCCL prints its version there when
+    # NCCL_DEBUG is set) goes to stderr instead, and the JSON line is written to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(real_stdout, (line + "\n").encode())
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -262,7 +271,7 @@ def main():
 
     # roofline of the dominant kernel (fused residual tile kernel), per launch, per GPU
     achieved = RES_BYTES_PER_CELL * cells_local / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_residual_fast (32x8 tile, 288 threads)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "kernel": "k_residual_fast (32x9 tile, 320 threads)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_kind": peak_kind, "traffic": RES_TRAFFIC_NCU if (a.im, a.jm, world) == (8192, 2048, 1) else None, "kernel_ms": k_ms,
                 "algorithmic_bytes_per_cell": RES_BYTES_PER_CELL,
                 "fp64_pipe_note": "FP64-pipe bound at ~11 flop/B (ridge 5.8): see DESIGN.md section 4 and profiles/"}
@@ -363,7 +372,7 @@ def main():
                                        "sample": "2 colour passes (seed + 4 linearised boundary fills + tangent, no COO scatter) of the C5 "
                                                  "recipe at 1024x512 on oracle/_ref, extrapolated to 245 colours x 8192x2048 cells: the "
                                                  "reference's COO layout (329 GB, int32 slots) cannot hold C5"}
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

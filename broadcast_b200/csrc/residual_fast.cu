@@ -1,16 +1,17 @@
-// The fused primal residual of residual_fast.cuh as CUDA kernels for sm_100a (32 x 8 tile, 288 threads, two CTAs per SM).
+// The fused primal residual of residual_fast.cuh as CUDA kernels for sm_100a.
 //
-//   k_residual_fast_tma   variant RES_FAST_TMA / BROADCAST_B200_RESIDUAL_TMA=1: PERSISTENT CTAs (2 per SM) walk the tiles; the five planes of w of the NEXT tile
-//                         (38 x 14 x 5 box, halo included, zero fill outside the padded array) are delivered into the
-//                         second shared-memory buffer by ONE TMA load (cp.async.bulk.tensor.3d + mbarrier) while the
-//                         faces of the current tile are evaluated; the face metrics are prefetched into registers one phase
-//                         ahead of their use.
-//   k_residual_fast       DEFAULT: one CTA per tile, w loaded with LDG (all loads of a thread issued before its arithmetic).
-//                         Also the fallback of the TMA variant when TMA cannot describe the array (odd leading dimension:
-//                         global strides must be multiples of 16 bytes).
-// Measured on B200 at C5 (profiles/r1_e_summary.md): LDG variant 2.51 ms, TMA variant 2.75 ms -- staging w by TMA removes the
-// HBM wait of phase 0 but the metric loads of phases 1-3 stay exposed and the persistent loop costs more than it hides, so the
-// LDG kernel stays the default.
+//   k_residual_fast       DEFAULT (this file): one CTA of 320 threads per 32 x 9 tile, two CTAs per SM (5 warps on every SM
+//                         sub-partition, what 96 registers allow); w loaded with LDG, all loads of a thread issued before its
+//                         arithmetic; face metrics prefetched into registers one phase ahead of their use.
+//   k_residual_fast_tma   variant RES_FAST_TMA / BROADCAST_B200_RESIDUAL_TMA=1 (residual_fast_tma.cu, 32 x 8 tile): PERSISTENT CTAs
+//                         (2 per SM) walk the tiles; the five planes of w of the NEXT tile (38 x 14 x 5 box, halo included, zero
+//                         fill outside the padded array) are delivered into a second shared-memory buffer by ONE TMA load
+//                         (cp.async.bulk.tensor.3d + mbarrier) while the faces of the current tile are evaluated.  Falls back to
+//                         k_residual_fast when TMA cannot describe the array (odd leading dimension: global strides must be
+//                         multiples of 16 bytes).
+// Measured on B200 at C5 (profiles/r1_e_summary.md): LDG kernel 2.51 ms (32 x 8) / 2.35 ms (32 x 9), TMA kernel 2.75 ms -- staging
+// w by TMA removes the HBM wait of phase 0 but the metric loads of phases 1-3 stay exposed and the persistent loop costs more
+// than it hides, so the LDG kernel stays the default.
 //
 // Phases and their barriers (both kernels):
 //   0  (wait for the TMA) primitives         | 1  sensor cells + R_q of the i-faces | (1b ghost sensor cells, boundary tiles)
@@ -18,8 +19,6 @@
 //   3  j-face fluxes -> exchange buffer      | 3b balance, coalesced store of residu
 // Reference: srcfv/rhs/flux_num_dnc5.F90:7-226.  Selected by launch_residual_tiled (residual_tile.cu keeps the first
 // generation, BROADCAST_B200_RESIDUAL_V1=1, as a cross-check).
-#include <cuda.h>
-#include <cstdint>
 #include <cstdlib>
 #include "kernels.cuh"
 #include "residual_fast.cuh"
@@ -27,33 +26,6 @@
 namespace bcast {
 
 namespace {
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  }
-}
-// one 3-D tiled TMA load: box (PI, PJ, 5) of w at storage coordinates (x, y, 0) -> dst, completion on bar
-__device__ __forceinline__ void tma_load_w(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
-      "l"(map), "r"(x), "r"(y), "r"(0), "r"(smem_u32(bar))
-      : "memory");
-}
 
 __device__ __forceinline__ rf::TileCtx make_ctx(double* sm, const GridDesc& g, const SchemeConsts& c, double sqgr, bool wall, const double* w,
                                                 const double* nx, const double* ny, const double* vol, const double* volf, double* res) {
@@ -96,92 +68,6 @@ __global__ void __launch_bounds__(rf::NT, 2)
   rf::balance_j_store(t, tid, r);
 }
 
-__global__ void __launch_bounds__(rf::NT, 2)
-    k_residual_fast_tma(const __grid_constant__ CUtensorMap wmap, GridDesc g, SchemeConsts c, double sqgr, bool wall,
-                        const double* __restrict__ w, const double* __restrict__ nx, const double* __restrict__ ny,
-                        const double* __restrict__ vol, const double* __restrict__ volf, double* __restrict__ res, int ntx, int ntiles) {
-  extern __shared__ __align__(128) double sm[];
-  // layout: [w buffer 0][w buffer 1][derived arrays, R buffer, exchange buffer][two mbarriers]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 2 * rf::WBUF + rf::NSM_REST);
-  rf::TileCtx t = make_ctx(sm, g, c, sqgr, wall, w, nx, ny, vol, volf, res);
-  t.sm = sm + 2 * rf::WBUF;
-  const int tid = threadIdx.x;
-  constexpr uint32_t BYTES = 5u * rf::NC * sizeof(double);
-  int tile = blockIdx.x;
-  if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (tile >= ntiles) return;
-  if (tid == 0) {
-    mbar_expect_tx(&bar[0], BYTES);
-    tma_load_w(sm, &wmap, (tile % ntx) * rf::OI, (tile / ntx) * rf::OJ, &bar[0]);   // storage coordinates of cell (i0-3, j0-3)
-  }
-  uint32_t parity = 0u;   // bit b: phase parity of mbarrier b
-  int b = 0;
-  for (; tile < ntiles; tile += gridDim.x) {
-    const int next = tile + gridDim.x;
-    // buffer b^1 was read last by the faces of the previous tile; every thread has passed the barrier that follows them
-    if (tid == 0 && next < ntiles) {
-      mbar_expect_tx(&bar[b ^ 1], BYTES);
-      tma_load_w(sm + (b ^ 1) * rf::WBUF, &wmap, (next % ntx) * rf::OI, (next / ntx) * rf::OJ, &bar[b ^ 1]);
-    }
-    t.i0 = 1 + (tile % ntx) * rf::OI;
-    t.j0 = 1 + (tile / ntx) * rf::OJ;
-    t.wsm = sm + b * rf::WBUF;
-    const rf::FaceGeom gi = rf::prefetch_iface(t, tid);   // metric loads in flight across phases 0 and 1
-    mbar_wait(&bar[b], (parity >> b) & 1u);
-    parity ^= 1u << b;
-    rf::phase0<true>(t, tid);
-    __syncthreads();
-    rf::phase1(t, tid);
-    __syncthreads();
-    if (t.has_ghost_sensor()) {  // CTA-uniform
-      rf::phase1b(t, tid);
-      __syncthreads();
-    }
-    rf::phase2(t, tid, gi);
-    const rf::FaceGeom gj = rf::prefetch_jface(t, tid);
-    __syncthreads();
-    double r[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    rf::balance_i(t, tid, r);
-    rf::phase_rj(t, tid);
-    __syncthreads();
-    rf::phase3(t, tid, gj);
-    __syncthreads();
-    rf::balance_j_store(t, tid, r);
-    b ^= 1;
-  }
-}
-
-// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links cudart only)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(p);
-  }();
-  return fn;
-}
-
-// tensor map of w seen as (ni, nj, 5) doubles, box (PI, PJ, 5); false if TMA cannot describe it
-bool make_w_map(const GridDesc& g, const double* w, CUtensorMap* map) {
-  EncodeTiledFn enc = encode_tiled_fn();
-  if (!enc) return false;
-  if ((reinterpret_cast<uintptr_t>(w) & 15) || (g.ldc & 1)) return false;   // base and strides: multiples of 16 bytes
-  const cuuint64_t dims[3] = {(cuuint64_t)g.ni(), (cuuint64_t)g.nj(), 5};
-  const cuuint64_t strides[2] = {(cuuint64_t)g.ldc * sizeof(double), (cuuint64_t)g.sc * sizeof(double)};
-  const cuuint32_t box[3] = {rf::PI, rf::PJ, 5};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 template <class K>
 cudaError_t prepare_kernel(K kernel, size_t smem) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -192,29 +78,19 @@ cudaError_t prepare_kernel(K kernel, size_t smem) {
 
 }  // namespace
 
+cudaError_t launch_residual_fast_tma(const GridDesc& g, const SchemeConsts& c, double sqgr, bool wall, double* res, const double* w,
+                                     const double* nx, const double* ny, const double* vol, const double* volf, cudaStream_t st, bool* done);
+
 cudaError_t launch_residual_fast(const GridDesc& g, const SchemeArgs& a, bool wall, double* res, const double* w, const double* nx,
                                  const double* ny, const double* vol, const double* volf, cudaStream_t st, bool tma) {
   const SchemeConsts c = make_consts(a.cp, a.cv, a.prandtl, a.gam, a.rgaz, a.cs, a.muref, a.tref, a.s_suth, a.k2, a.k4);
   const double sqgr = ::sqrt(a.gam * a.rgaz);
-  const int ntx = (g.im + rf::OI - 1) / rf::OI, nty = (g.jm + rf::OJ - 1) / rf::OJ;
-  CUtensorMap map;
-  if (tma && make_w_map(g, w, &map)) {
-    constexpr size_t SMEM = (size_t)rf::NSM_TMA * sizeof(double);
-    static bool ready = false;
-    static int nsm = 0;
-    if (!ready) {
-      cudaError_t e = prepare_kernel(k_residual_fast_tma, SMEM);
-      if (e != cudaSuccess) return e;
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-      ready = true;
-    }
-    const int ntiles = ntx * nty;
-    const int grid = ntiles < 2 * nsm ? ntiles : 2 * nsm;
-    k_residual_fast_tma<<<grid, rf::NT, SMEM, st>>>(map, g, c, sqgr, wall, w, nx, ny, vol, volf, res, ntx, ntiles);
-    return cudaGetLastError();
+  if (tma) {
+    bool done = false;
+    cudaError_t e = launch_residual_fast_tma(g, c, sqgr, wall, res, w, nx, ny, vol, volf, st, &done);
+    if (done || e != cudaSuccess) return e;
   }
+  const int ntx = (g.im + rf::OI - 1) / rf::OI, nty = (g.jm + rf::OJ - 1) / rf::OJ;
   constexpr size_t SMEM = (size_t)rf::NSM * sizeof(double);
   static bool ready = false;
   if (!ready) {

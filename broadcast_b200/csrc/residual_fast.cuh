@@ -20,34 +20,46 @@
 // the plane maximum).  The three wall rows (o2 viscous fluxes, off-centred fluxes, wall flux: flux_num_dnc5.F90:161-220)
 // keep the reference-shaped templates of scheme.cuh through an accessor over the same shared arrays.
 //
-// Tile: 32 x 8 output cells per CTA of 288 threads (9 warps): 8 x 33 i-faces (8 warps x 32 left faces + 8 lanes of the
-// ninth warp for the last column) and 9 x 32 j-faces (all 288 threads) -- no face is evaluated twice inside a CTA.
+// Tile: 32 x OJ output cells per CTA of 32 (OJ + 1) threads: OJ x 33 i-faces (OJ warps x 32 left faces + OJ lanes of the
+// last warp for the last column) and (OJ + 1) x 32 j-faces (all threads) -- no face is evaluated twice inside a CTA.
+// OJ = 9 (320 threads, 10 warps): two CTAs put 5 warps on every SM sub-partition, the most that 96 registers allow.
 #pragma once
 #include "scheme.cuh"
 
+// The tile height is a compile-time constant; a translation unit that wants another one (residual_fast_tma.cu: OJ = 8, so that
+// two w buffers still leave room for two CTAs per SM) defines BCAST_RF_OJ and its own namespace name BCAST_RF_NS.
+#ifndef BCAST_RF_NS
+#define BCAST_RF_NS rf
+#endif
+
 namespace bcast {
-namespace rf {
+namespace BCAST_RF_NS {
 
 constexpr int H = 3;
-constexpr int OI = 32, OJ = 8;
-constexpr int PI = OI + 2 * H, PJ = OJ + 2 * H;  // staged cells: i0-3 .. i0+34, j0-3 .. j0+10
+#ifndef BCAST_RF_OJ
+#define BCAST_RF_OJ 9
+#endif
+constexpr int OI = 32, OJ = BCAST_RF_OJ;
+constexpr int PI = OI + 2 * H, PJ = OJ + 2 * H;  // staged cells: i0-3 .. i0+34, j0-3 .. j0+OJ+2
 constexpr int NC = PI * PJ;
-constexpr int NT = 288;
+constexpr int NT = OI * (OJ + 1);                // one thread per j-face; OJ rows of i-faces + OJ lanes for the last column
 // derived per-cell arrays (the five planes of w live in their own buffer so that TMA can deliver them, double buffered)
 enum { A_U = 0, A_V = 1, A_WZ = 2, A_T = 3, A_P = 4, A_MU = 5, A_SR = 6, A_CS = 7, A_DV = 8, A_DU = 9, NARR = 10 };
-constexpr int WBUF = 2672;                    // doubles per w buffer: 5 * NC = 2660 rounded up to a multiple of 128 bytes
+constexpr int WBUF = (5 * NC + 15) / 16 * 16;    // doubles per w buffer: 5 * NC rounded up to a multiple of 128 bytes
 // normal-direction interpolations R_q (q = u, v, w, T) of the faces a CTA's viscous gradients read
 constexpr int RI_W = OI + 1, RI_H = OJ + 4;   // i-faces i0 .. i0+32, rows j0-2 .. j0+9
 constexpr int RJ_W = OI + 4, RJ_H = OJ + 1;   // j-faces columns i0-2 .. i0+33, rows j0 .. j0+8
 constexpr int RQ = RI_W * RI_H;               // 396 >= 324
 constexpr int NRB = 4 * RQ;
 constexpr int XI_P = OI + 1, XJ_P = OI;       // pitches of the face-flux exchange buffer
-constexpr int NXB = 5 * (OJ + 1) * OI;        // 1440 >= 5 * 8 * 33
+constexpr int NXB = 5 * (OJ + 1) * OI;        // >= 5 * OJ * (OI + 1)
 constexpr int GW = OI + 2, GH_ = OJ + 2;      // sensor cells: i0-1 .. i0+32, j0-1 .. j0+8 (scratch divu / vort alias X)
 constexpr int NSM_REST = NARR * NC + NRB + NXB;
 constexpr int NSM = WBUF + NSM_REST;          // doubles of shared memory per CTA, one w buffer (88 128 bytes)
 constexpr int NSM_TMA = 2 * WBUF + NSM_REST + 2;   // two w buffers + two mbarriers (109 520 bytes)
 static_assert(5 * NC <= WBUF, "w buffer");
+static_assert(5 * OJ * XI_P <= NXB, "exchange buffer");
+static_assert(OJ <= 32 && GW * OJ <= NT + 0 && 8 * (RI_W + 3) <= NT && 8 * RJ_W <= NT, "thread mappings");
 static_assert(2 * GW * GH_ <= NXB, "scratch aliasing");
 static_assert(RJ_W * RJ_H <= RQ, "R buffer");
 
@@ -189,8 +201,8 @@ BC_HD double ducros_ratio(double divu, double vort) {
 // R_q(face) = -q(-2) + 9 q(-1) + 9 q(0) - q(1) along the face normal (the 1/16 is applied by the consumer)
 BC_HD double rrow(const double* q, int stride) { return 9.0 * (q[-stride] + q[0]) - (q[-2 * stride] + q[stride]); }
 
-// Sensor cells of a tile: rows j0 .. j0+7 over columns i0-1 .. i0+32 (272 cells, one per thread) and the two rows
-// j0-1, j0+8 over columns i0 .. i0+31 (64 cells, a second round of the first two warps); the corners are never read.
+// Sensor cells of a tile: rows j0 .. j0+OJ-1 over columns i0-1 .. i0+32 (34 OJ cells, one per thread) and the two rows
+// j0-1, j0+OJ over columns i0 .. i0+31 (64 cells, a second round of the first two warps); the corners are never read.
 BC_HD void sensor_cell(const TileCtx& t, int ga, int gb) {   // window coordinates: cell (i0-1+ga, j0-1+gb)
   const GridDesc& g = t.g;
   const int a = ga + (H - 1), b = gb + (H - 1);
@@ -211,14 +223,16 @@ BC_HD void sensor_cell(const TileCtx& t, int ga, int gb) {   // window coordinat
 BC_HD void phase1(const TileCtx& t, int tid) {
   if (tid < GW * OJ) sensor_cell(t, tid % GW, 1 + tid / GW);
   if (tid < 2 * OI) sensor_cell(t, 1 + (tid & (OI - 1)), tid < OI ? 0 : GH_ - 1);
-  // R_q of the i-faces: thread (fcol = tid % 36 < 33, grp = tid / 36) owns quantity grp/2 and six of the twelve face rows
+  // R_q of the i-faces: thread (fcol = tid % 36 < 33, grp = tid / 36 < 8) owns quantity grp/2 and one half of the face rows
   const int fcol = tid % (RI_W + 3), grp = tid / (RI_W + 3);
-  if (fcol < RI_W) {
-    const int q = grp >> 1, frow0 = (grp & 1) * (RI_H / 2);
+  if (fcol < RI_W && grp < 8) {
+    constexpr int HALF = (RI_H + 1) / 2;
+    const int q = grp >> 1, frow0 = (grp & 1) * HALF, nrow = (grp & 1) ? RI_H - HALF : HALF;
     const double* src = t.arr(A_U + q) + (fcol + H) + (frow0 + 1) * PI;  // face (i0 + fcol, j0 - 2 + frow0)
     double* dst = t.RB() + q * RQ + frow0 * RI_W + fcol;
 #pragma unroll
-    for (int n = 0; n < RI_H / 2; ++n) dst[n * RI_W] = rrow(src + n * PI, 1);
+    for (int n = 0; n < HALF; ++n)
+      if (n < nrow) dst[n * RI_W] = rrow(src + n * PI, 1);
   }
 }
 
@@ -253,12 +267,14 @@ BC_HD void phase1b(const TileCtx& t, int tid) {
 // and five (even grp) or four (odd grp) consecutive face rows, sliding along j
 BC_HD void phase_rj(const TileCtx& t, int tid) {
   const int fcol = tid % RJ_W, grp = tid / RJ_W;
-  const int q = grp >> 1, frow0 = (grp & 1) * 5, nrow = (grp & 1) ? 4 : 5;
+  if (grp >= 8) return;
+  constexpr int HALF = (RJ_H + 1) / 2;
+  const int q = grp >> 1, frow0 = (grp & 1) * HALF, nrow = (grp & 1) ? RJ_H - HALF : HALF;
   const double* src = t.arr(A_U + q) + (fcol + 1) + (frow0 + H) * PI;  // face (i0 - 2 + fcol, j0 + frow0)
   double* dst = t.RB() + q * RQ + frow0 * RJ_W + fcol;
   double m2 = src[-2 * PI], m1 = src[-PI], c0 = src[0];
 #pragma unroll
-  for (int n = 0; n < 5; ++n) {
+  for (int n = 0; n < HALF; ++n) {
     if (n < nrow) {
       const double p1 = src[(n + 1) * PI];
       dst[n * RJ_W] = 9.0 * (m1 + c0) - (m2 + p1);
@@ -502,5 +518,5 @@ BC_HD void balance_j_store(const TileCtx& t, int tid, const double (&r)[5]) {
     t.res[e * t.g.sc + k] = r[e] - (X[(e * (OJ + 1) + cy + 1) * XJ_P + cx] - X[(e * (OJ + 1) + cy) * XJ_P + cx]);
 }
 
-}  // namespace rf
+}  // namespace BCAST_RF_NS
 }  // namespace bcast
