@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 
 RES_BYTES_PER_CELL = 136.0  # 12 doubles read (w5, nx2, ny2, vol, volf2) + 5 written, SURVEY.md 8(d)
 JAC_BYTES_PER_CELL = 5904.0  # 29 blocks x 25 doubles written + 13 doubles read, SURVEY.md 8(d)
-RES_TRAFFIC_NCU = 2.265e9    # dram__bytes_read.sum + dram__bytes_write.sum of one launch at C5 (profiles/r1_d_residual_fast_full_raw.csv)
+RES_TRAFFIC_NCU = 2.268e9    # dram__bytes_read.sum + dram__bytes_write.sum of one launch at C5 (profiles/r1_e_residual_fast_full_raw.csv)
 
 
 def parse():
@@ -333,10 +333,11 @@ def main():
         if world == 1:
             # one GPU: the host step is pipelined over 8 i-slabs (H2D of slab k+1 / kernels of slab k / D2H of slab k-1 overlap)
             from broadcast_b200.resident import StreamedBlock
-            sb = StreamedBlock(case, nslab=8, device=dev)
+            nslab = int(os.environ.get("BROADCAST_B200_E2E_SLABS", "8"))
+            sb = StreamedBlock(case, nslab=nslab, device=dev)
             run = lambda: sb.step_from_host(wp, rp)
             h2d, d2h = sb.bytes_per_step()
-            api = "broadcast_b200.resident.StreamedBlock.step_from_host (pinned host w in, residual out, 8 pipelined i-slabs; mesh metrics resident)"
+            api = "broadcast_b200.resident.StreamedBlock.step_from_host (pinned host w in, residual out, " + str(nslab) + " pipelined i-slabs; mesh metrics resident)"
         else:
             run = lambda: blk.step_from_host(wp, rp, halo)
             h2d = d2h = blk.w.numel() * 8

@@ -38,8 +38,31 @@ __device__ __forceinline__ rf::TileCtx make_ctx(double* sm, const GridDesc& g, c
   return t;
 }
 
+// L2 prefetch of everything a LATER tile reads (w with halo, nx, ny, vol, volf rows): CTAs start in blockIdx order, so the CTA
+// that will run `dist` tiles after this one finds its first loads in L2 instead of HBM (ncu r1_e: 18 % of all stall samples
+// were the long-scoreboard wait at the top of each CTA).  One 128-byte line per thread and instruction, no register results.
+__device__ __forceinline__ void prefetch_tile_l2(const GridDesc& g, const double* w, const double* nx, const double* ny, const double* vol,
+                                                 const double* volf, int i0, int j0, int tid) {
+  constexpr int LINES = (rf::PI * 8 + 127) / 128 + 1;   // lines per staged row (unaligned start)
+  constexpr int ROWS = rf::PJ;
+  const int jmax = g.jm + g.gh, imax = g.im + g.gh;
+  for (int u = tid; u < 12 * ROWS * LINES; u += rf::NT) {
+    const int plane = u / (ROWS * LINES), r = (u / LINES) % ROWS, l = u % LINES;
+    const int gj = j0 - rf::H + r;
+    const int gi = i0 - rf::H + l * 16;
+    if (gj > jmax || gi > imax) continue;
+    const double* p;
+    if (plane < 5) p = w + plane * g.sc + g.cidx(gi, gj);
+    else if (plane < 7) p = nx + (plane - 5) * g.sn + g.nidx(gi, gj);
+    else if (plane < 9) p = ny + (plane - 7) * g.sn + g.nidx(gi, gj);
+    else if (plane < 10) p = vol + g.cidx(gi, gj);
+    else p = volf + (plane - 10) * g.sc + g.cidx(gi, gj);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  }
+}
+
 __global__ void __launch_bounds__(rf::NT, 2)
-    k_residual_fast(GridDesc g, SchemeConsts c, double sqgr, bool wall, const double* __restrict__ w, const double* __restrict__ nx,
+    k_residual_fast(int l2dist, GridDesc g, SchemeConsts c, double sqgr, bool wall, const double* __restrict__ w, const double* __restrict__ nx,
                     const double* __restrict__ ny, const double* __restrict__ vol, const double* __restrict__ volf,
                     double* __restrict__ res) {
   extern __shared__ __align__(128) double sm[];
@@ -47,10 +70,16 @@ __global__ void __launch_bounds__(rf::NT, 2)
   t.i0 = 1 + blockIdx.x * rf::OI;
   t.j0 = 1 + blockIdx.y * rf::OJ;
   const int tid = threadIdx.x;
+  if (l2dist > 0) {
+    const int L = blockIdx.y * gridDim.x + blockIdx.x + l2dist;
+    const int bx = L % gridDim.x, by = L / gridDim.x;
+    if (by < gridDim.y) prefetch_tile_l2(g, w, nx, ny, vol, volf, 1 + bx * rf::OI, 1 + by * rf::OJ, tid);
+  }
   const rf::FaceGeom gi = rf::prefetch_iface(t, tid);   // metric loads in flight across phases 0 and 1
+  const rf::SensGeom sg0 = rf::prefetch_sensor(t, tid, 0), sg1 = rf::prefetch_sensor(t, tid, 1);   // ... across phase 0
   rf::phase0<false>(t, tid);
   __syncthreads();
-  rf::phase1(t, tid);
+  rf::phase1(t, tid, sg0, sg1);
   __syncthreads();
   if (t.has_ghost_sensor()) {  // CTA-uniform
     rf::phase1b(t, tid);
@@ -98,7 +127,8 @@ cudaError_t launch_residual_fast(const GridDesc& g, const SchemeArgs& a, bool wa
     if (e != cudaSuccess) return e;
     ready = true;
   }
-  k_residual_fast<<<dim3(ntx, nty), rf::NT, SMEM, st>>>(g, c, sqgr, wall, w, nx, ny, vol, volf, res);
+  static const int l2dist = getenv("BROADCAST_B200_RESIDUAL_L2DIST") ? atoi(getenv("BROADCAST_B200_RESIDUAL_L2DIST")) : 592;
+  k_residual_fast<<<dim3(ntx, nty), rf::NT, SMEM, st>>>(l2dist, g, c, sqgr, wall, w, nx, ny, vol, volf, res);
   return cudaGetLastError();
 }
 

@@ -202,27 +202,71 @@ BC_HD double ducros_ratio(double divu, double vort) {
 BC_HD double rrow(const double* q, int stride) { return 9.0 * (q[-stride] + q[0]) - (q[-2 * stride] + q[stride]); }
 
 // Sensor cells of a tile: rows j0 .. j0+OJ-1 over columns i0-1 .. i0+32 (34 OJ cells, one per thread) and the two rows
-// j0-1, j0+OJ over columns i0 .. i0+31 (64 cells, a second round of the first two warps); the corners are never read.
-BC_HD void sensor_cell(const TileCtx& t, int ga, int gb) {   // window coordinates: cell (i0-1+ga, j0-1+gb)
-  const GridDesc& g = t.g;
-  const int a = ga + (H - 1), b = gb + (H - 1);
-  const int ci = t.i0 - H + a, cj = t.j0 - H + b;
-  if (ci >= g.glo() && ci <= g.ghi() && cj >= 1 && cj <= g.jm) {  // slab-internal edges: real gradients in the halo column
-    const SmemAcc2 A = make_acc(t, a, b);
-    const auto r = cell_gradients<0, 0>(A);
-    const double divu = r.u0.v + r.v1.v, vort = r.v0.v - r.u1.v;
-    double* S0 = t.X();
-    S0[ga + gb * GW] = divu;
-    S0[GW * GH_ + ga + gb * GW] = vort;
-    const int k = a + b * PI;
-    t.arr(A_DV)[k] = A.template VOL<0, 0>() * divu;
-    t.arr(A_DU)[k] = ducros_ratio(divu, vort);
+// j0-1, j0+OJ over columns i0 .. i0+31 (64 cells, a second round of the last two warps); the corners are never read.
+// cell metrics of the 5-point gradient (geom/dxdy.F:1-6), loaded before phase 0 so that their latency is hidden
+struct SensGeom {
+  double dxm1, dxm2, dym1, dym2, vol;
+  bool valid;
+};
+BC_HD bool sensor_of(const TileCtx& t, int tid, int round, int& ga, int& gb) {   // window coordinates of the thread's sensor cell
+  if (round == 0) {
+    if (tid >= GW * OJ) return false;
+    ga = tid % GW;
+    gb = 1 + tid / GW;
+  } else {   // the two rows j0-1 and j0+OJ, columns i0 .. i0+31: the last two warps (the lightest ones in this phase)
+    const int u = tid - (NT - 2 * OI);
+    if (u < 0) return false;
+    ga = 1 + (u & (OI - 1));
+    gb = u < OI ? 0 : GH_ - 1;
   }
+  const GridDesc& g = t.g;
+  const int ci = t.i0 - 1 + ga, cj = t.j0 - 1 + gb;
+  return ci >= g.glo() && ci <= g.ghi() && cj >= 1 && cj <= g.jm;   // slab-internal edges: real gradients in the halo column
+}
+BC_HD SensGeom prefetch_sensor(const TileCtx& t, int tid, int round) {
+  SensGeom G{};
+  int ga, gb;
+  G.valid = sensor_of(t, tid, round, ga, gb);
+  if (G.valid) {
+    const GridDesc& g = t.g;
+    const int ci = t.i0 - 1 + ga, cj = t.j0 - 1 + gb;
+    const long long n = g.nidx(ci, cj);
+    G.vol = BC_LDG(t.vol + g.cidx(ci, cj));
+    const double volm1 = 1.0 / G.vol;
+    G.dxm1 = 0.5 * (BC_LDG(t.nx + n) + BC_LDG(t.nx + n + 1)) * volm1;
+    G.dxm2 = 0.5 * (BC_LDG(t.nx + g.sn + n) + BC_LDG(t.nx + g.sn + n + g.ldn)) * volm1;
+    G.dym1 = 0.5 * (BC_LDG(t.ny + n) + BC_LDG(t.ny + n + 1)) * volm1;
+    G.dym2 = 0.5 * (BC_LDG(t.ny + g.sn + n) + BC_LDG(t.ny + g.sn + n + g.ldn)) * volm1;
+  }
+  return G;
+}
+// dilatation, vorticity and Ducros ratio of one sensor cell (gradop_5pi.F, gradop_5pj.F, gradient.F: same operation order
+// as cell_gradients() of scheme.cuh)
+BC_HD void sensor_cell(const TileCtx& t, int tid, int round, const SensGeom& G) {
+  if (!G.valid) return;
+  int ga, gb;
+  sensor_of(t, tid, round, ga, gb);
+  const int k = (ga + H - 1) + (gb + H - 1) * PI;
+  const double* U = t.arr(A_U) + k;
+  const double* V = t.arr(A_V) + k;
+  constexpr double b1 = 8.0 * (1.0 / 12.0), b2 = -(1.0 / 12.0);
+  const double gui = b1 * (U[1] - U[-1]) + b2 * (U[2] - U[-2]);
+  const double gvi = b1 * (V[1] - V[-1]) + b2 * (V[2] - V[-2]);
+  const double guj = b1 * (U[PI] - U[-PI]) + b2 * (U[2 * PI] - U[-2 * PI]);
+  const double gvj = b1 * (V[PI] - V[-PI]) + b2 * (V[2 * PI] - V[-2 * PI]);
+  const double gu0 = G.dxm1 * gui + G.dxm2 * guj, gv0 = G.dxm1 * gvi + G.dxm2 * gvj;
+  const double gu1 = G.dym1 * gui + G.dym2 * guj, gv1 = G.dym1 * gvi + G.dym2 * gvj;
+  const double divu = gu0 + gv1, vort = gv0 - gu1;
+  double* S0 = t.X();
+  S0[ga + gb * GW] = divu;
+  S0[GW * GH_ + ga + gb * GW] = vort;
+  t.arr(A_DV)[k] = G.vol * divu;
+  t.arr(A_DU)[k] = ducros_ratio(divu, vort);
 }
 
-BC_HD void phase1(const TileCtx& t, int tid) {
-  if (tid < GW * OJ) sensor_cell(t, tid % GW, 1 + tid / GW);
-  if (tid < 2 * OI) sensor_cell(t, 1 + (tid & (OI - 1)), tid < OI ? 0 : GH_ - 1);
+BC_HD void phase1(const TileCtx& t, int tid, const SensGeom& G0, const SensGeom& G1) {
+  sensor_cell(t, tid, 0, G0);
+  sensor_cell(t, tid, 1, G1);
   // R_q of the i-faces: thread (fcol = tid % 36 < 33, grp = tid / 36 < 8) owns quantity grp/2 and one half of the face rows
   const int fcol = tid % (RI_W + 3), grp = tid / (RI_W + 3);
   if (fcol < RI_W && grp < 8) {

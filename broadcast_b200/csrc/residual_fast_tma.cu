@@ -88,11 +88,12 @@ __global__ void __launch_bounds__(rf::NT, 2)
     t.j0 = 1 + (tile / ntx) * rf::OJ;
     t.wsm = sm + b * rf::WBUF;
     const rf::FaceGeom gi = rf::prefetch_iface(t, tid);   // metric loads in flight across phases 0 and 1
+    const rf::SensGeom sg0 = rf::prefetch_sensor(t, tid, 0), sg1 = rf::prefetch_sensor(t, tid, 1);
     mbar_wait(&bar[b], (parity >> b) & 1u);
     parity ^= 1u << b;
     rf::phase0<true>(t, tid);
     __syncthreads();
-    rf::phase1(t, tid);
+    rf::phase1(t, tid, sg0, sg1);
     __syncthreads();
     if (t.has_ghost_sensor()) {  // CTA-uniform
       rf::phase1b(t, tid);

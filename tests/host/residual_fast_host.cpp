@@ -42,7 +42,7 @@ extern "C" int rf_host_residual(double* res, const double* w, const double* nx, 
       } else {
         for (int tid = 0; tid < rf::NT; ++tid) rf::phase0<false>(t, tid);
       }
-      for (int tid = 0; tid < rf::NT; ++tid) rf::phase1(t, tid);
+      for (int tid = 0; tid < rf::NT; ++tid) rf::phase1(t, tid, rf::prefetch_sensor(t, tid, 0), rf::prefetch_sensor(t, tid, 1));
       if (t.has_ghost_sensor())
         for (int tid = 0; tid < rf::NT; ++tid) rf::phase1b(t, tid);
       for (int tid = 0; tid < rf::NT; ++tid) rf::phase2(t, tid, rf::prefetch_iface(t, tid));
