@@ -201,6 +201,13 @@ int bcd_memcpy2d(void* dst, long long dpitch, const void* src, long long spitch,
                                     kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream);
   return e == cudaSuccess ? BC_OK : cuda_fail(e, "bcd_memcpy2d");
 }
+// colour sharding: the colour loops of this thread (bcd_jacobian_coo, bcd_jacobian_strips, bcd_dz_coo) visit only the passes
+// c0 <= l * (2gh+1) + k < c1; c1 <= c0 restores all colours.  Slots of the other colours keep their content.
+int bcd_colour_range(int c0, int c1) {
+  if (c0 < 0 || c1 < 0) return fail(BC_ERR_ARG, "bad colour range");
+  current_colours() = ColourRange{c0, c1};
+  return BC_OK;
+}
 int bcd_slab_end(void) {
   current_slab() = SlabInfo{0, 0, 0};
   return BC_OK;

@@ -341,16 +341,20 @@ __global__ void __launch_bounds__(128) k_balance_faces5(GridDesc g, SchemeConsts
 // of its stencil is active and the tangents of its two sensor gradients are zero (with seeds 7 cells apart about half of
 // the faces of a colour pass see no seed at all).  Faces are combined per cell through shared memory as rhs/balance.F does.
 // ---------------------------------------------------------------------------------------------
-constexpr int SF_MAXF = 232;
-__global__ void __launch_bounds__(256) k_strip_faces5(GridDesc g, SchemeConsts c, FieldPtrs f, bool wall, Rect rc, int wide,
-                                                      double* __restrict__ out) {
+// TL = cells of a tile along the strip (32: 227 faces on 256 threads; 16: 115 faces on 128 threads), MINB = CTAs per SM the
+// register allocation aims at (the face flux in tangent arithmetic wants ~254 registers: 8 warps per SM; fewer registers =
+// more warps to hide the dependent FP64 latency, at the price of spills)
+template <int TL, int MINB>
+__global__ void __launch_bounds__(TL * 8, MINB) k_strip_faces5(GridDesc g, SchemeConsts c, FieldPtrs f, bool wall, Rect rc, int wide,
+                                                               double* __restrict__ out) {
+  constexpr int SF_MAXF = (TL + 1) * 3 + TL * 4;
   __shared__ double sh[5][SF_MAXF];
-  __shared__ unsigned char flag[38 * 9];
+  __shared__ unsigned char flag[(TL + 6) * 9];
   const int dir = blockIdx.z;
-  const int ti0 = wide ? rc.i0 + 32 * blockIdx.x : rc.i0;
-  const int tj0 = wide ? rc.j0 : rc.j0 + 32 * blockIdx.x;
-  const int twc = min(wide ? 32 : 3, rc.i1 - ti0 + 1);
-  const int thc = min(wide ? 3 : 32, rc.j1 - tj0 + 1);
+  const int ti0 = wide ? rc.i0 + TL * blockIdx.x : rc.i0;
+  const int tj0 = wide ? rc.j0 : rc.j0 + TL * blockIdx.x;
+  const int twc = min(wide ? TL : 3, rc.i1 - ti0 + 1);
+  const int thc = min(wide ? 3 : TL, rc.j1 - tj0 + 1);
   const int fw = twc + 6, fh = thc + 6;   // activity window: cells ti0-3 .. ti0+twc+2, tj0-3 .. tj0+thc+2
   FieldPtrs f1 = f;
   f1.wd = f.wd + (long long)dir * 5 * g.sc;
@@ -436,23 +440,34 @@ cudaError_t tangent_strips_5(const GridDesc& g, const SchemeArgs& a, bool wall, 
     rp.r[k] = Rect{max(0, rc.i0 - 5 + g.gh), min(g.ni() - 1, rc.i1 + 3 + g.gh), max(0, rc.j0 - 5 + g.gh), min(g.nj() - 1, rc.j1 + 3 + g.gh)};
   }
   dim3 blk(32, 4);
-  for_each_rect(rp, [&](const RectList& r1, int) { k_prims<N><<<grid_of(r1, 32, 4), blk, 0, st>>>(g, c, r1, w, wd5, prim, primd); });
+  for_each_rect(rp, st, [&](const RectList& r1, int, cudaStream_t s1) { k_prims<N><<<grid_of(r1, 32, 4), blk, 0, s1>>>(g, c, r1, w, wd5, prim, primd); });
   FieldPtrs f{w, prim, grad, nx, ny, vol, volf, wd5, primd, gradd};
-  for_each_rect(rg, [&](const RectList& r1, int) { k_grads<N><<<grid_of(r1, 32, 4), blk, 0, st>>>(g, f, r1, grad, gradd); });
+  for_each_rect(rg, st, [&](const RectList& r1, int, cudaStream_t s1) { k_grads<N><<<grid_of(r1, 32, 4), blk, 0, s1>>>(g, f, r1, grad, gradd); });
   const int nt = g.im + g.jm;
   k_grad_ghost<<<dim3((nt + 127) / 128, NGRAD), 128, 0, st>>>(g, grad, NGRAD);
   k_grad_ghost<<<dim3((nt + 127) / 128, NGRAD * N), 128, 0, st>>>(g, gradd, NGRAD * N);
-  for_each_rect(rows, [&](const RectList& r1, int) {
+  for_each_rect(rows, st, [&](const RectList& r1, int, cudaStream_t s1) {
     const Rect& q = r1.r[0];
     const int wi = q.i1 - q.i0 + 1, wj = q.j1 - q.j0 + 1;
     static const bool v1 = getenv("BROADCAST_B200_STRIPS_V1") != nullptr;
-    if (!v1 && wj <= 3 && wi >= wj) {
-      k_strip_faces5<<<dim3((wi + 31) / 32, 1, 5), 256, 0, st>>>(g, c, f, wall, q, 1, out5);
-    } else if (!v1 && wi <= 3) {
-      k_strip_faces5<<<dim3((wj + 31) / 32, 1, 5), 256, 0, st>>>(g, c, f, wall, q, 0, out5);
+    static const int cfg_env = getenv("BROADCAST_B200_STRIPS_CFG") ? atoi(getenv("BROADCAST_B200_STRIPS_CFG")) : -1;
+    const int wide = (wj <= 3 && wi >= wj) ? 1 : 0;
+    if (!v1 && (wide || wi <= 3)) {
+      const int len = wide ? wi : wj;
+      // measured on B200 (profiles/r1_f_summary.md): 16-cell tiles at 168 registers (12 warps per SM, 552 B of spills) win on long
+      // strips (4096x1024: 22.2 -> 19.8 ms), 32-cell tiles at 254 registers on short ones
+      const int cfg = cfg_env >= 0 ? cfg_env : (len >= 1024 ? 2 : 0);
+      if (cfg == 1)
+        k_strip_faces5<32, 2><<<dim3((len + 31) / 32, 1, 5), 256, 0, s1>>>(g, c, f, wall, q, wide, out5);
+      else if (cfg == 2)
+        k_strip_faces5<16, 3><<<dim3((len + 15) / 16, 1, 5), 128, 0, s1>>>(g, c, f, wall, q, wide, out5);
+      else if (cfg == 3)
+        k_strip_faces5<16, 4><<<dim3((len + 15) / 16, 1, 5), 128, 0, s1>>>(g, c, f, wall, q, wide, out5);
+      else
+        k_strip_faces5<32, 1><<<dim3((len + 31) / 32, 1, 5), 256, 0, s1>>>(g, c, f, wall, q, wide, out5);
     } else {
       const int ncell = wi * wj;
-      k_balance_faces5<<<dim3((ncell + 31) / 32, 1, 5), dim3(32, 1, 4), 0, st>>>(g, c, f, wall, r1, out5);
+      k_balance_faces5<<<dim3((ncell + 31) / 32, 1, 5), dim3(32, 1, 4), 0, s1>>>(g, c, f, wall, r1, out5);
     }
   });
   return cudaGetLastError();

@@ -1,6 +1,10 @@
 // Device-resident colour loop: the reference algorithm (seed -> linearised boundary fills -> tangent
 // -> scatter; BROADCAST_npz.py:1068-1127, misc/ComputeJacobian.f90) with the five variables of a
 // colour (l,k) carried together as five tangent directions, so 49 passes instead of 245.
+#include <cstdlib>
+#include <cstring>
+#include <list>
+#include <string>
 #include <vector>
 #include "../../include/broadcast_b200.h"
 #include "kernels.cuh"
@@ -144,6 +148,7 @@ extern "C" int bcd_jacobian_coo(double* jac, int32_t* ia, int32_t* ja, double* w
   const RectList* seed_rows = (rect && !has_join) ? &seed_list : nullptr;
   for (int l = 0; l < s; ++l)
     for (int k = 0; k < s; ++k) {
+      if (!current_colours().has(l * s + k)) continue;   // colour sharding: this rank's passes only
       cudaError_t e = launch_testvector(g, wd5, 5, 0, l, k, nullptr, st, seed_rows);
       if (e != cudaSuccess) return (int)e;
       e = apply_bc_list(g, gam, 5, w, wd5, nx, ny, bcs, nbcs, st);
@@ -176,6 +181,7 @@ extern "C" int bcd_dz_coo(double* jac1, int32_t* ia1, int32_t* ja1, double* jac2
   const long long nt = 5LL * im * jm;
   for (int l = 0; l < s; ++l)
     for (int k = 0; k < s; ++k) {
+      if (!current_colours().has(l * s + k)) continue;   // colour sharding: this rank's passes only
       cudaError_t e = launch_testvector(g, wd5, 5, 0, l, k, nullptr, st);
       if (e != cudaSuccess) return (int)e;
       e = apply_bc_list(g, gam, 5, w, wd5, nx, ny, bcs, nbcs, st);
@@ -223,22 +229,93 @@ extern "C" int bcd_jacobian_strips(int nrect, const int32_t* rects /* [nrect][4]
     if (rows.r[q].i1 < rows.r[q].i0 || rows.r[q].j1 < rows.r[q].j0) return BC_ERR_ARG;
   bool has_join = false;
   for (int b = 0; b < nbcs; ++b) has_join = has_join || bcs[b].kind == BC_KIND_JOIN;
-  for (int l = 0; l < s; ++l)
-    for (int k = 0; k < s; ++k) {
-      cudaError_t e = launch_testvector(g, wd5, 5, 0, l, k, nullptr, st, has_join ? nullptr : &rows);
-      if (e != cudaSuccess) return (int)e;
-      e = apply_bc_list(g, gam, 5, w, wd5, nx, ny, bcs, nbcs, st);
-      if (e != cudaSuccess) return (int)e;
-      e = launch_tangent_strips5(g, a, wall != 0, rows, resd5, w, wd5, nx, ny, vol, volf, st);
-      if (e != cudaSuccess) return (int)e;
-      for (int q = 0; q < nrect; ++q) {
-        const Rect rc = rows.r[q];
-        const long long nt = 5LL * (rc.i1 - rc.i0 + 1) * (rc.j1 - rc.j0 + 1);
-        k_scatter5<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(g, scatter_kind, jac[q], ia[q], ja[q], resd5, l, k, coefdiag, vol, rc, 1);
+  int nlaunch = 0;
+  // the 49 passes (~26 small launches each): launch-latency bound on the reference's own grids (500 x 150: 206 us per pass)
+  auto run = [&](cudaStream_t s_) -> cudaError_t {
+    for (int l = 0; l < s; ++l)
+      for (int k = 0; k < s; ++k) {
+        if (!current_colours().has(l * s + k)) continue;   // colour sharding: this rank's passes only
+        cudaError_t e = launch_testvector(g, wd5, 5, 0, l, k, nullptr, s_, has_join ? nullptr : &rows);
+        if (e != cudaSuccess) return e;
+        e = apply_bc_list(g, gam, 5, w, wd5, nx, ny, bcs, nbcs, s_);
+        if (e != cudaSuccess) return e;
+        e = launch_tangent_strips5(g, a, wall != 0, rows, resd5, w, wd5, nx, ny, vol, volf, s_);
+        if (e != cudaSuccess) return e;
+        for_each_rect(rows, s_, [&](const RectList& r1, int q, cudaStream_t s1) {
+          const Rect rc = r1.r[0];
+          const long long nt = 5LL * (rc.i1 - rc.i0 + 1) * (rc.j1 - rc.j0 + 1);
+          k_scatter5<<<(unsigned)((nt + 255) / 256), 256, 0, s1>>>(g, scatter_kind, jac[q], ia[q], ja[q], resd5, l, k, coefdiag, vol, rc, 1);
+        });
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        nlaunch += 6 + nrect;
       }
-      e = cudaGetLastError();
-      if (e != cudaSuccess) return (int)e;
-      count_launches(6 + nrect);
+    return cudaSuccess;
+  };
+  // CUDA graph of the whole loop, cached on everything a launch depends on (pointers, sizes, scalars, slab and colour context,
+  // scratch arena addresses).  BROADCAST_B200_NO_GRAPH=1 launches kernel by kernel.
+  static const bool no_graph = getenv("BROADCAST_B200_NO_GRAPH") != nullptr;
+  if (no_graph) {
+    cudaError_t e = run(st);
+    count_launches(nlaunch);
+    return e == cudaSuccess ? BC_OK : (int)e;
+  }
+  // every scratch slot the loop touches must exist before capture (allocation is not capturable)
+  double* sc_[4] = {scratch_doubles(0, (size_t)g.sc * NPRIM), scratch_doubles(1, (size_t)g.sc * NGRAD),
+                    scratch_doubles(2, (size_t)g.sc * NPRIM * 5), scratch_doubles(3, (size_t)g.sc * NGRAD * 5)};
+  for (double* p : sc_)
+    if (!p) return BC_ERR_ALLOC;
+  std::string key;
+  auto put = [&](const void* p, size_t n) { key.append(reinterpret_cast<const char*>(p), n); };
+  int dev = 0;
+  cudaGetDevice(&dev);
+  put(&dev, sizeof dev); put(&g, sizeof g); put(&a, sizeof a); put(&rows, sizeof rows); put(&wall, sizeof wall);
+  put(&scatter_kind, sizeof scatter_kind); put(&nbcs, sizeof nbcs); put(&gam, sizeof gam);
+  for (int b = 0; b < nbcs; ++b) put(&bcs[b], sizeof(bc_desc_t));
+  for (int q = 0; q < nrect; ++q) { put(&jac[q], sizeof(void*)); put(&ia[q], sizeof(void*)); put(&ja[q], sizeof(void*)); }
+  const void* ptrs[] = {w, nx, ny, vol, volf, coefdiag, wd5, resd5, sc_[0], sc_[1], sc_[2], sc_[3]};
+  put(ptrs, sizeof ptrs);
+  const ColourRange cr = current_colours();
+  put(&cr, sizeof cr);
+  struct Entry { std::string key; cudaGraphExec_t exec; int nlaunch; };
+  static thread_local std::list<Entry> cache;
+  // graphs cannot be captured on the legacy default stream: use a blocking side stream, which the legacy stream orders with
+  static thread_local cudaStream_t side = nullptr;
+  cudaStream_t gs = st;
+  if (st == nullptr || st == cudaStreamLegacy) {
+    if (!side && cudaStreamCreate(&side) != cudaSuccess) return BC_ERR_ALLOC;
+    gs = side;
+  }
+  for (auto it = cache.begin(); it != cache.end(); ++it)
+    if (it->key == key) {
+      cudaError_t e = cudaGraphLaunch(it->exec, gs);
+      count_launches(it->nlaunch);
+      cache.splice(cache.begin(), cache, it);
+      return e == cudaSuccess ? BC_OK : (int)e;
     }
-  return BC_OK;
+  static const bool no_fork = getenv("BROADCAST_B200_NO_GRAPH_FORK") != nullptr;
+  rect_fork().ready();   // side streams and events exist before the capture starts
+  cudaError_t e = cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) return (int)e;
+  rect_fork().on = !no_fork;   // per-rectangle launches become parallel branches of the graph
+  const cudaError_t er = run(gs);
+  rect_fork().on = false;
+  cudaGraph_t graph = nullptr;
+  e = cudaStreamEndCapture(gs, &graph);
+  if (er != cudaSuccess || e != cudaSuccess) {
+    if (graph) cudaGraphDestroy(graph);
+    return (int)(er != cudaSuccess ? er : e);
+  }
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return (int)e;
+  cache.push_front(Entry{key, exec, nlaunch});
+  if (cache.size() > 8) {
+    cudaGraphExecDestroy(cache.back().exec);
+    cache.pop_back();
+  }
+  e = cudaGraphLaunch(exec, gs);
+  count_launches(nlaunch);
+  return e == cudaSuccess ? BC_OK : (int)e;
 }

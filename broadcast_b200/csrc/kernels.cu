@@ -28,6 +28,24 @@ SlabInfo& current_slab() {
   return s;
 }
 
+RectFork& rect_fork() {
+  static thread_local RectFork f;
+  return f;
+}
+bool RectFork::ready() {
+  if (fork) return true;
+  for (int k = 0; k < 4; ++k) {
+    if (cudaStreamCreateWithFlags(&side[k], cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&join[k], cudaEventDisableTiming) != cudaSuccess) return false;
+  }
+  return cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess;
+}
+
+ColourRange& current_colours() {
+  static thread_local ColourRange c{0, 0};
+  return c;
+}
+
 double* scratch_doubles(int slot, size_t count) {
   int dev = 0;
   cudaGetDevice(&dev);
@@ -202,7 +220,9 @@ cudaError_t launch_testvector(const GridDesc& g, double* wd, int ndir, int m, in
     js = zone[2];
     je = zone[3] + 1;
   }
-  for_each_rect(win, [&](const RectList& w1, int) { k_testvector<<<grid_of(w1, 32, 4), blk, 0, st>>>(g, wd, ndir, m, l, k, is, ie, js, je, w1); });
+  for_each_rect(win, st, [&](const RectList& w1, int, cudaStream_t s1) {
+    k_testvector<<<grid_of(w1, 32, 4), blk, 0, s1>>>(g, wd, ndir, m, l, k, is, ie, js, je, w1);
+  });
   return cudaGetLastError();
 }
 

@@ -27,6 +27,14 @@ inline GridDesc make_grid_ctx(int im, int jm, int gh) {
   return g;
 }
 
+// colour range of the calling thread (bcd_colour_range): the colour loops visit only the (l,k) passes with
+// c0 <= l * (2gh+1) + k < c1 -- colour sharding over GPUs for grids too small for i-slabs
+struct ColourRange {
+  int c0, c1;
+  bool has(int c) const { return c1 <= c0 || (c >= c0 && c < c1); }   // empty range = all colours
+};
+ColourRange& current_colours();
+
 struct SchemeArgs {
   double cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4;
 };
@@ -56,10 +64,31 @@ inline dim3 grid_of(const RectList& l, int bx, int by) {   // grid covering the 
   return dim3((wi + bx - 1) / bx, (wj + by - 1) / by, l.n);
 }
 // Rectangles of very different shapes (the boundary strips: im x gh and gh x jm) are launched one by one instead:
-// a common grid would be (im/bx) x (jm/by) blocks, almost all of them empty.
+// a common grid would be (im/bx) x (jm/by) blocks, almost all of them empty.  The launches of one call are independent of
+// each other; when the calling thread has switched its fork context on (bcd_jacobian_strips while it captures its CUDA graph)
+// each rectangle goes to its own side stream between a fork and a join event, so that the graph holds parallel branches
+// instead of a chain (the strip passes are latency bound: ~8 us per dependent kernel on the reference's own grids).
+struct RectFork {
+  bool on = false;
+  cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool ready();   // creates streams and events on first use
+};
+RectFork& rect_fork();
 template <class F>
-inline void for_each_rect(const RectList& l, F&& launch) {
-  for (int k = 0; k < l.n; ++k) launch(one_rect(l.r[k]), k);
+inline void for_each_rect(const RectList& l, cudaStream_t st, F&& launch) {   // launch(one-rect list, index, stream)
+  RectFork& rf_ = rect_fork();
+  if (!rf_.on || l.n < 2 || !rf_.ready()) {
+    for (int k = 0; k < l.n; ++k) launch(one_rect(l.r[k]), k, st);
+    return;
+  }
+  cudaEventRecord(rf_.fork, st);
+  for (int k = 0; k < l.n; ++k) {
+    cudaStreamWaitEvent(rf_.side[k], rf_.fork, 0);
+    launch(one_rect(l.r[k]), k, rf_.side[k]);
+    cudaEventRecord(rf_.join[k], rf_.side[k]);
+    cudaStreamWaitEvent(st, rf_.join[k], 0);
+  }
 }
 
 // Generic ("reference-shaped") residual and tangent: prims -> gradients (+ ghost-layer extrapolation)

@@ -266,10 +266,12 @@ def _bc_descs(blk: "Block"):
     return arr, len(out)
 
 
-def jacobian_coo(blk: "Block", coefdiag=None, kind=None, rect=None, out=None, compact=False):
+def jacobian_coo(blk: "Block", coefdiag=None, kind=None, rect=None, out=None, compact=False, colours=None):
     """The reference's COO lists (Jac, IA, JA; slot order of misc/ComputeJacobian.f90:524) assembled
     on the device by the colour loop of BROADCAST_npz.py:1068-1127 with 5 directions per pass.
-    ``blk.w`` must hold the state with its ghosts filled (``blk.apply_bcs()``)."""
+    ``blk.w`` must hold the state with its ghosts filled (``blk.apply_bcs()``).
+    ``colours`` = (c0, c1): colour sharding, only the passes c0 <= l*(2gh+1)+k < c1 (sharding.colour_range); the slots
+    of the other colours stay zero."""
     im, jm, gh = blk.im, blk.jm, blk.gh
     s = 2 * gh + 1
     nb = 25 * s * s * im * jm
@@ -291,9 +293,15 @@ def jacobian_coo(blk: "Block", coefdiag=None, kind=None, rect=None, out=None, co
         coefdiag = _t(coefdiag, blk.device)
     descs, n = _bc_descs(blk)
     r = np.asarray(rect, dtype=np.int32) if rect is not None else None
-    blk.call("bcd_jacobian_coo", _p(jac), _p(ia), _p(ja), _p(blk.w), _p(blk.nx), _p(blk.ny), _p(blk.vol), _p(blk.volf), gh, *blk._phys,
-             im, jm, blk.wall, descs, n, SCATTER[kind], _p(coefdiag),
-             r.ctypes.data_as(ctypes.c_void_p) if r is not None else ctypes.c_void_p(None), 1 if compact else 0, blk._stream())
+    if colours is not None:
+        _lib.check(_lib.lib().bcd_colour_range(int(colours[0]), int(colours[1])), "bcd_colour_range")
+    try:
+        blk.call("bcd_jacobian_coo", _p(jac), _p(ia), _p(ja), _p(blk.w), _p(blk.nx), _p(blk.ny), _p(blk.vol), _p(blk.volf), gh, *blk._phys,
+                 im, jm, blk.wall, descs, n, SCATTER[kind], _p(coefdiag),
+                 r.ctypes.data_as(ctypes.c_void_p) if r is not None else ctypes.c_void_p(None), 1 if compact else 0, blk._stream())
+    finally:
+        if colours is not None:
+            _lib.lib().bcd_colour_range(0, 0)
     return jac, ia, ja
 
 
@@ -391,7 +399,10 @@ class HybridJacobian:
 def jacobian_hybrid(blk: "Block", coefdiag=None, kind=None, blocks=None, interior="faces", strip_buffers=None):
     """Jacobian of the current state: interior rows by the direct block kernels (one launch per
     structural column offset, no colouring), boundary strips (gh rows/columns along each side) by the
-    reference colour loop restricted to those rows."""
+    reference colour loop restricted to those rows.
+    The strip COO buffers (and the zero ``coefdiag`` used when none is given) belong to the block and are REUSED by its next
+    assembly (every slot is rewritten by every assembly): the strip colour loop is replayed as a CUDA graph keyed on its
+    pointers, fresh buffers would mean a new capture per call.  Pass ``strip_buffers="fresh"`` to get buffers of your own."""
     im, jm, gh = blk.im, blk.jm, blk.gh
     if kind is None:
         kind = "jv_relaxed_withjn" if blk.case.periodic_i else "jv_relaxed"
@@ -400,7 +411,9 @@ def jacobian_hybrid(blk: "Block", coefdiag=None, kind=None, blocks=None, interio
     if coefdiag is not None:
         cd = coefdiag if isinstance(coefdiag, torch.Tensor) else _t(coefdiag, blk.device)
     elif relaxed:
-        cd = torch.zeros((jm, im), dtype=torch.float64, device=blk.device)
+        cd = getattr(blk, "_zero_coefdiag", None)
+        if cd is None:
+            cd = blk._zero_coefdiag = torch.zeros((jm, im), dtype=torch.float64, device=blk.device)
     edges = blk.slab[2] if blk.slab else 0
     ilo = 1 if edges & 1 else gh + 1          # a slab-internal edge has no irregular rows: the block kernels run up to it
     ihi = im if edges & 2 else im - gh
@@ -415,6 +428,18 @@ def jacobian_hybrid(blk: "Block", coefdiag=None, kind=None, blocks=None, interio
     if not edges & 2:
         rects.append((im - gh + 1, im, gh + 1, jm - gh))
     rects = [r for r in rects if r[1] >= r[0] and r[3] >= r[2]]
+    if strip_buffers == "fresh":
+        strip_buffers = None
+    elif strip_buffers is None:
+        cache = blk.__dict__.setdefault("_strip_buffers", {})
+        key = tuple(rects)
+        if key not in cache:
+            s_ = 2 * gh + 1
+            cache[key] = [(torch.zeros(25 * s_ * s_ * (r[1] - r[0] + 1) * (r[3] - r[2] + 1), dtype=torch.float64, device=blk.device),
+                           torch.zeros(25 * s_ * s_ * (r[1] - r[0] + 1) * (r[3] - r[2] + 1), dtype=torch.int32, device=blk.device),
+                           torch.zeros(25 * s_ * s_ * (r[1] - r[0] + 1) * (r[3] - r[2] + 1), dtype=torch.int32, device=blk.device))
+                          for r in rects]
+        strip_buffers = cache[key]
     strips = jacobian_strips(blk, rects, coefdiag=cd, kind=kind, out=strip_buffers)
     return HybridJacobian(blk, blocks, jacobian_slots(blk), strips, region)
 

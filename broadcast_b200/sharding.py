@@ -116,6 +116,27 @@ class HaloExchange:
             w[:, :, im + gh:im + 2 * gh].copy_(self._buf["rr"])
 
 
+def colour_range(ncolours: int, rank: int, world: int):
+    """[c0, c1) of the ``ncolours`` = (2gh+1)^2 colour passes owned by ``rank``: colour sharding for grids too small for
+    i-slabs and for the i-periodic O-mesh.  Every rank holds the whole state and evaluates its passes on the
+    full grid; nothing is exchanged, the COO entries of different ranks are disjoint column subsets."""
+    base, rem = divmod(ncolours, world)
+    c0 = rank * base + min(rank, rem)
+    return c0, c0 + base + (1 if rank < rem else 0)
+
+
+def merge_colour_shards(parts, n, thresh=2e-16):
+    """host merge of per-rank COO triples (jac, ia, ja) produced under colour sharding into one scipy CSR matrix of order n:
+    zero filter of BROADCAST_npz.py:129-135 on each part, then duplicate summation (scipy csr semantics, as the reference)"""
+    import scipy.sparse as sp
+    js, rs, cs = [], [], []
+    for jac, ia, ja in parts:
+        jac, ia, ja = np.asarray(jac), np.asarray(ia), np.asarray(ja)
+        keep = np.abs(jac) > thresh
+        js.append(jac[keep]); rs.append(ia[keep]); cs.append(ja[keep])
+    return sp.csr_matrix((np.concatenate(js), (np.concatenate(rs), np.concatenate(cs))), shape=(n, n))
+
+
 def gather_row_blocks(parts):
     """host gather of per-rank CSR row blocks [(indptr, indices, data), ...] (rank order = row order) into one CSR triple"""
     indptr = [np.asarray(parts[0][0], dtype=np.int64)]

@@ -150,6 +150,10 @@ int bc_compute_norml2inf(double* norm, double* ninf, const double* rhs, int im, 
  * sides only) and the regular-row block kernels run up to that edge.  Arrays, rect arguments and slot layouts stay local. */
 int bcd_slab_begin(int ioff, int im_global, int edges);
 int bcd_slab_end(void);
+/* Colour sharding (grids too small for i-slabs and the i-periodic O-mesh): the device colour loops called by this
+ * thread visit only the (l,k) passes with c0 <= l*(2gh+1)+k < c1 (49 passes in all for gh = 3); c1 <= c0 = all colours.  Every
+ * rank holds the whole state; the COO slots of a colour belong to exactly one rank, the host merges the filtered lists. */
+int bcd_colour_range(int c0, int c1);
 /* pitched copy of `height` rows of `width` BYTES between a host array and a device array (an i-slab of a Fortran-ordered
  * block is a set of pitched rows); kind 1 = host to device, 2 = device to host; asynchronous on `stream`. */
 int bcd_memcpy2d(void* dst, long long dpitch, const void* src, long long spitch, long long width, long long height, int kind,

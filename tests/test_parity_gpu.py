@@ -175,6 +175,39 @@ def test_scatter_variants_integer_exact(gpu, ref):
         assert np.array_equal(out[0][0], out[1][0]), name
 
 
+def test_colour_sharded_device_loop_merges_to_the_full_jacobian(gpu):
+    """colour sharding (bcd_colour_range): three 'ranks' on one device each run their range of the 49 passes of the device colour
+    loop on the i-periodic O-mesh; the merged COO lists equal the unsharded loop exactly, slot by slot"""
+    import torch
+    from broadcast_b200 import sharding
+    from broadcast_b200.resident import Block, jacobian_coo
+    c = H.make_case("cyl", 42, 30, gpu, with_w=True)
+    blk = Block(c)
+    blk.apply_bcs()
+    full = [t.clone() for t in jacobian_coo(blk)]
+    s = 2 * c.gh + 1
+    world = 3
+    acc = None
+    seen = torch.zeros_like(full[0], dtype=torch.bool)
+    for r in range(world):
+        c0, c1 = sharding.colour_range(s * s, r, world)
+        jac, ia, ja = jacobian_coo(blk, colours=(c0, c1))
+        mine = (ia != 0) | (ja != 0) | (jac != 0)
+        assert not bool((mine & seen).any())                  # disjoint slots
+        seen |= mine
+        acc = [jac.clone(), ia.clone(), ja.clone()] if acc is None else [acc[0] + jac, acc[1] + ia, acc[2] + ja]
+    assert torch.equal(acc[0], full[0]) and torch.equal(acc[1], full[1]) and torch.equal(acc[2], full[2])
+    n = 5 * c.im * c.jm
+    parts = []
+    for r in range(world):
+        c0, c1 = sharding.colour_range(s * s, r, world)
+        parts.append(tuple(t.cpu().numpy() for t in jacobian_coo(blk, colours=(c0, c1))))
+    A = sharding.merge_colour_shards(parts, n)
+    B = H.coo_to_dict(*(t.cpu().numpy() for t in full))
+    B.resize((n, n))
+    assert A.nnz == B.nnz and (A - B).nnz == 0
+
+
 def test_two_zone_scatter_with_check_integer_exact(gpu, ref):
     """computejacobianfromjv_relaxed_withjnandcheck (misc/ComputeJacobian.f90:1095-1204, cylinder.py:1159): read-modify-write
     of the slot arrays, zone 0 then zone 1 over the same colours, partially pre-filled slots"""

@@ -94,3 +94,60 @@ def test_slab_partition_and_row_gather():
     ip, idx, dat = sharding.gather_row_blocks(parts)
     C = sp.csr_matrix((dat, idx, ip), shape=A.shape)
     assert (C != A).nnz == 0
+
+
+# ---- colour sharding (small grids and the i-periodic O-mesh) ------------------------------------------------
+def test_colour_ranges_partition_the_passes():
+    for world in (1, 2, 3, 4, 8, 49, 60):
+        got = []
+        for r in range(world):
+            c0, c1 = sharding.colour_range(49, r, world)
+            assert 0 <= c0 <= c1 <= 49
+            got += list(range(c0, c1))
+        assert got == list(range(49))
+        sizes = [sharding.colour_range(49, r, world)[1] - sharding.colour_range(49, r, world)[0] for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _colour_worker(rank, world, port, im, jm, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import refmods
+        R = refmods.make()
+        c = H.make_case("cyl", im, jm, R, with_w=True)          # periodic in i: cannot be slab-sharded
+        w, _ = H.residual_sequence(R, c)
+        s = 2 * c.gh + 1
+        c0, c1 = sharding.colour_range(s * s, rank, world)
+        mine = [(m, l, k) for m in range(5) for l in range(s) for k in range(s) if c0 <= l * s + k < c1]
+        jac, ia, ja = H.jacobian_sequence(R, c, w, mine, None)   # the checker computes this rank's passes
+        parts = [None] * world
+        dist.all_gather_object(parts, (jac, ia, ja))
+        if rank == 0:
+            n = 5 * im * jm
+            A = sharding.merge_colour_shards(parts, n)
+            jf, iaf, jaf = H.jacobian_sequence(R, c, w, None, None)
+            B = H.coo_to_dict(jf, iaf, jaf)
+            B.resize((n, n))
+            D = (A - B).tocoo()
+            out.put((A.nnz, B.nnz, float(np.abs(D.data).max()) if D.nnz else 0.0))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_colour_sharded_jacobian_merges_to_the_full_one_gloo(world):
+    """every rank runs a contiguous range of the 49 colour passes on the whole (i-periodic) grid; rank 0 merges the filtered
+    COO lists: identical to the single-process colour loop (each matrix entry comes from exactly one colour)"""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_colour_worker, args=(r, world, port, 21, 14, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+        assert p.exitcode == 0
+    nnzA, nnzB, err = out.get(timeout=10)
+    assert nnzA == nnzB and err == 0.0

@@ -1,0 +1,4 @@
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/r27_pytest.log; cat gpurun_out/r27_pytest.log
+timeout 300 python tools/jac_probe.py 500x150 630x300 2048x512 4096x1024 > gpurun_out/r27_jac_probe.log 2>&1; cat gpurun_out/r27_jac_probe.log
