@@ -70,11 +70,17 @@ __constant__ JacTab kJacTabDev = fj::make_jac_tab();
 // staged subset (27 of the 54 fields: everything that more than two column cells of a face read) of the packages of its
 // 33x4 i-faces and 32x5 j-faces lives in shared memory (62.8 KB); ncu of the 14-field version: 1 160 package LDGs per cell
 // at 14 % L1 hit rate, long_scoreboard 6.6 per issue (profiles/r1_d_summary.md).
+// ST = first staged field (27: DEG + SE + viscous = 27 fields, 62.8 KB; 35: SE + viscous = 19 fields, 44.2 KB; 40: viscous only),
+// MINB = CTAs per SM the register allocation aims at.
 constexpr int JT_I = 32, JT_J = 4;
-__global__ void __launch_bounds__(JT_I* JT_J, 3)
+template <int ST, int MINB>
+__global__ void __launch_bounds__(JT_I* JT_J, MINB)
     k_jac_assemble_rt(GridDesc g, SchemeConsts c, FieldPtrs f, Rect rc, const double* __restrict__ pkg, double* __restrict__ V,
                       const double* __restrict__ coefdiag) {
-  extern __shared__ double jsm[];   // 62.8 KB: three CTAs per SM
+  constexpr int FPK_NVS = FPK_N - ST;
+  constexpr int FPK_VS = ST;
+  using FaceCtx = FaceCtxT<ST>;
+  extern __shared__ double jsm[];
   double* sI = jsm;
   double* sJ = jsm + FPK_NVS * JT_J * (JT_I + 1);
   const int tid = threadIdx.y * JT_I + threadIdx.x;
@@ -180,17 +186,23 @@ cudaError_t launch_jacobian_faces(const GridDesc& g, const SchemeArgs& a, const 
     k_jac_assemble<<<gr, blk, 0, st>>>(g, c, f, rc, pkg, values, coefdiag);
   else
   {
-    constexpr size_t SMEM = (size_t)FPK_NVS * (JT_J * (JT_I + 1) + (JT_J + 1) * JT_I) * sizeof(double);
-    static bool attr = false;
-    if (!attr) {
-      e = cudaFuncSetAttribute(k_jac_assemble_rt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
-      if (e != cudaSuccess) return e;
-      e = cudaFuncSetAttribute(k_jac_assemble_rt, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-      if (e != cudaSuccess) return e;
-      attr = true;
-    }
-    k_jac_assemble_rt<<<dim3((rc.i1 - rc.i0 + JT_I) / JT_I, (rc.j1 - rc.j0 + JT_J) / JT_J), dim3(JT_I, JT_J), SMEM, st>>>(g, c, f, rc, pkg,
-                                                                                                                     values, coefdiag);
+    static const int cfg = getenv("BROADCAST_B200_JAC_CFG") ? atoi(getenv("BROADCAST_B200_JAC_CFG")) : 0;
+    const dim3 grd((rc.i1 - rc.i0 + JT_I) / JT_I, (rc.j1 - rc.j0 + JT_J) / JT_J), blk2(JT_I, JT_J);
+    auto go = [&](auto kern, int st_field) -> cudaError_t {
+      const size_t smem = (size_t)(FPK_N - st_field) * (JT_J * (JT_I + 1) + (JT_J + 1) * JT_I) * sizeof(double);
+      cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e2 != cudaSuccess) return e2;
+      e2 = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+      if (e2 != cudaSuccess) return e2;
+      kern<<<grd, blk2, smem, st>>>(g, c, f, rc, pkg, values, coefdiag);
+      return cudaGetLastError();
+    };
+    if (cfg == 1) e = go(k_jac_assemble_rt<35, 4>, 35);        // 19 staged fields, 128 registers, 16 warps per SM
+    else if (cfg == 2) e = go(k_jac_assemble_rt<40, 4>, 40);   // 14 staged fields, 128 registers
+    else if (cfg == 3) e = go(k_jac_assemble_rt<40, 5>, 40);   // 14 staged fields, 96 registers, 20 warps per SM
+    else if (cfg == 4) e = go(k_jac_assemble_rt<35, 3>, 35);   // 19 staged fields, 168 registers
+    else e = go(k_jac_assemble_rt<27, 3>, 27);                 // 27 staged fields, 168 registers, 12 warps per SM
+    if (e != cudaSuccess) return e;
   }
   count_launches(5);
   return cudaGetLastError();

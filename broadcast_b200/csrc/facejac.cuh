@@ -42,8 +42,8 @@ enum {
   // "staged subset": the 27 fields that many column cells of a face's stencil read (14 of its 22 cells read SE and DEG, all
   // 20 cells of the viscous box read the last 14); the assembly kernel stages them in shared memory
   FPK_VS = 27,
-  FPK_SE = 27,    // [5] rspec (diff_e - 12 chi pred_e)          (x d eps2),  chi = [eps4 > 0]
-  FPK_DEG = 32,   // [2][4] sensor cell s = -1, 0: coefficients of (wI, wJ) in d eps2/dU_c and in d eps2/dV_c
+  FPK_DEG = 27,   // [2][4] sensor cell s = -1, 0: coefficients of (wI, wJ) in d eps2/dU_c and in d eps2/dV_c
+  FPK_SE = 35,    // [5] rspec (diff_e - 12 chi pred_e)          (x d eps2),  chi = [eps4 > 0]
   FPK_NXF = 40, FPK_NYF = 41,                              // face normal (length-scaled)
   FPK_MMU = 42, FPK_UU = 43, FPK_VV = 44, FPK_WW = 45,
   FPK_DNX = 46,   // [4] dual-cell normals x volm1: A+, A-, C+, C-   (x components)
@@ -226,14 +226,17 @@ struct ColAcc {
 
 // handle of one face's package: field f at pk[f * stride]; the staged subset (fields FPK_VS ..) may live in a second,
 // faster array (shared memory in the assembly kernel): field FPK_VS + k at vs[k * vstride]
-struct FaceCtx {
+// ST = first staged field: fields >= ST are read from vs (field ST + k at vs[k * vstride]), the others from global memory
+template <int ST>
+struct FaceCtxT {
   const double* pk;
   long long stride;
   const double* vs;
   int vstride;
   BC_HD double operator()(int f) const { return BC_LDG(pk + f * stride); }
-  BC_HD double v(int f) const { return vs[(f - FPK_VS) * vstride]; }
+  BC_HD double v(int f) const { return f >= ST ? vs[(f - ST) * vstride] : BC_LDG(pk + f * stride); }
 };
+using FaceCtx = FaceCtxT<FPK_VS>;
 
 namespace fj {
 constexpr double kDen = 1.0 / 60.0;
@@ -258,8 +261,8 @@ constexpr bool in_face(int s, int t) { return (t == 0 && s >= -3 && s <= 2) || i
 
 // contribution of one face (direction DIR, sign sgn in the row balance) to the column cell at
 // (along, cross) = (S, T) from the face cell
-template <int DIR, int S, int T>
-BC_HD void face_contrib(const FaceCtx& f, const SchemeConsts& c, double sgn, ColAcc& acc) {
+template <int DIR, int S, int T, class FC>
+BC_HD void face_contrib(const FC& f, const SchemeConsts& c, double sgn, ColAcc& acc) {
   using namespace fj;
   if constexpr (!in_face(S, T)) {
     return;
@@ -399,8 +402,8 @@ BC_HD void block_finish(const ColAcc& acc, const double (&wc)[5], const SchemeCo
 }
 
 // whole block of row cell (i,j), column offset (DI,DJ).  fi0/fi1/fj0/fj1: contexts of faces i, i+1, j, j+1.
-template <int DI, int DJ>
-BC_HD void block_of(const FaceCtx& fi0, const FaceCtx& fi1, const FaceCtx& fj0, const FaceCtx& fj1, const double (&wc)[5],
+template <int DI, int DJ, class FC>
+BC_HD void block_of(const FC& fi0, const FC& fi1, const FC& fj0, const FC& fj1, const double (&wc)[5],
                     const SchemeConsts& c, double (&B)[25]) {
   ColAcc acc;
   acc.clear();
@@ -491,7 +494,8 @@ constexpr JacTab make_jac_tab() {
 
 // runtime-table version of face_contrib.  The viscous part is branch-free (table weights are zero for cells outside
 // the 4x5 box) so that the loads of the four faces of a slot batch up; the rarer along-line / sensor terms branch.
-BC_HD void face_contrib_rt(const FaceCtx& f, const FaceTab& t, const SchemeConsts& c, double sgn, ColAcc& acc, double (&B)[25]) {
+template <class FC>
+BC_HD void face_contrib_rt(const FC& f, const FaceTab& t, const SchemeConsts& c, double sgn, ColAcc& acc, double (&B)[25]) {
   if (!(t.flags & FT_ANY)) return;
   const double nxf = f.v(FPK_NXF), nyf = f.v(FPK_NYF);
   {
@@ -627,7 +631,8 @@ BC_HD void block_finish_fast(const ColAcc& acc, const double (&wc)[5], const Sch
 }
 
 // block of column slot `s` through the table
-BC_HD void block_of_rt(const JacTab& J, int s, const FaceCtx& fi0, const FaceCtx& fi1, const FaceCtx& fj0, const FaceCtx& fj1,
+template <class FC>
+BC_HD void block_of_rt(const JacTab& J, int s, const FC& fi0, const FC& fi1, const FC& fj0, const FC& fj1,
                        const double (&wc)[5], const SchemeConsts& c, double (&B)[25]) {
   ColAcc acc;
   acc.clear();
