@@ -235,10 +235,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # BROADCAST_B200_OVERLAP=1: halo exchange + boundary fills on a side stream while the inner tiles of the residual run
+    # (Block.step_overlapped).  Measured on B200 (profiles/r1_g_summary.md): no gain -- N = 1: 2.40 vs 2.35 ms, N = 8: 0.378 vs 0.375 ms
+    # per step (the one-wave ring launch and the stream joins cost what the overlap hides) -- so the plain sequence is the default.
+    overlap = os.environ.get("BROADCAST_B200_OVERLAP", "0") == "1"
+
     def step():
-        halo(blk.w)
-        blk.apply_bcs()
-        blk.residual()
+        if overlap:
+            blk.step_overlapped(halo if world > 1 else None)
+        else:
+            halo(blk.w)
+            blk.apply_bcs()
+            blk.residual()
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -252,11 +260,16 @@ def main():
     barrier()
     ev0.record()
     for s in range(a.steps):
-        halo(blk.w)
-        blk.apply_bcs()
-        kev[s][0].record()
-        blk.residual()
-        kev[s][1].record()
+        if overlap:
+            kev[s][0].record()
+            step()
+            kev[s][1].record()
+        else:
+            halo(blk.w)
+            blk.apply_bcs()
+            kev[s][0].record()
+            blk.residual()
+            kev[s][1].record()
     ev1.record()
     barrier()
     launches = _lib.launch_count() - n0
@@ -271,7 +284,7 @@ def main():
 
     # roofline of the dominant kernel (fused residual tile kernel), per launch, per GPU
     achieved = RES_BYTES_PER_CELL * cells_local / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_residual_fast (32x9 tile, 320 threads)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "kernel": "k_residual_fast (32x9 tile, 320 threads)" + ("; inner tiles + ring of tiles = 2 launches per step overlapping the halo exchange and boundary fills, timed first launch to end of last" if overlap else ""), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_kind": peak_kind, "traffic": RES_TRAFFIC_NCU if (a.im, a.jm, world) == (8192, 2048, 1) else None, "kernel_ms": k_ms,
                 "algorithmic_bytes_per_cell": RES_BYTES_PER_CELL,
                 "fp64_pipe_note": "FP64-pipe bound at ~11 flop/B (ridge 5.8): see DESIGN.md section 4 and profiles/"}
@@ -361,7 +374,7 @@ def main():
             "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"C5 synthetic 2-D boundary layer {a.im}x{a.jm}, order 5 (gh=3), i-slabs over {world} GPU(s)",
-                       "step": "halo exchange (N>1) + 4 boundary fills + 1 residual (flux_num_dnc5_2d)",
+                       "step": "halo exchange (N>1) + 4 boundary fills + 1 residual (flux_num_dnc5_2d)" + (", fills and exchange overlapped with the inner tiles" if overlap else ""),
                        "l2": f"inputs larger than L2 ({blk.w.numel() * 8 / 2**20:.0f} MiB state per GPU)"},
             "roofline": roofline, "jacobian": jac, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
         }

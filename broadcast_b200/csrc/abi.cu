@@ -252,6 +252,19 @@ int bcd_residual(double* residu, const double* w, const double* nx, const double
   return BC_OK;
 }
 
+int bcd_residual_part(double* residu, const double* w, const double* nx, const double* ny, const double* vol, const double* volf, int gh,
+                      double cp, double cv, double prandtl, double gam, double rgaz, double cs, double muref, double tref, double s_suth,
+                      double k2, double k4, int im, int jm, int wall, int part, void* stream) {
+  if (int rc = check_dims(im, jm, gh)) return rc;
+  if (part < 0 || part > 2) return fail(BC_ERR_ARG, "part must be 0 (all), 1 (inner tiles) or 2 (ring of tiles)");
+  const GridDesc g = make_grid_ctx(im, jm, gh);
+  const SchemeArgs a = sargs(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4);
+  cudaError_t e = launch_residual_tiled(g, a, wall != 0, residu, w, nx, ny, vol, volf, (cudaStream_t)stream, RES_DEFAULT, part);
+  g_launches += 1;
+  if (e != cudaSuccess) return cuda_fail(e, "bcd_residual_part");
+  return BC_OK;
+}
+
 int bcd_tangent(double* residud, const double* w, const double* wd, int ndir, const double* nx, const double* ny, const double* vol,
                 const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs, double muref,
                 double tref, double s_suth, double k2, double k4, int im, int jm, int wall, const int32_t* rect, void* stream) {

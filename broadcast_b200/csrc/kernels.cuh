@@ -146,10 +146,11 @@ cudaError_t launch_norms(const GridDesc& g, const double* res, double* out10 /*d
 // variant: RES_DEFAULT (= k_residual_fast), RES_FAST_TMA (persistent CTAs + TMA staging of w), RES_TILE_V1 (first generation)
 enum ResidualVariant { RES_DEFAULT = 0, RES_GENERIC = 1, RES_FAST_TMA = 2, RES_TILE_V1 = 3 };
 cudaError_t launch_residual_tiled(const GridDesc& g, const SchemeArgs& a, bool wall, double* res, const double* w, const double* nx,
-                                  const double* ny, const double* vol, const double* volf, cudaStream_t st, int variant = RES_DEFAULT);
+                                  const double* ny, const double* vol, const double* volf, cudaStream_t st, int variant = RES_DEFAULT,
+                                  int part = 0);
 
 // second-generation fused residual (residual_fast.cu): re-associated face formulas, shared normal-direction interpolations
 cudaError_t launch_residual_fast(const GridDesc& g, const SchemeArgs& a, bool wall, double* res, const double* w, const double* nx,
-                                 const double* ny, const double* vol, const double* volf, cudaStream_t st, bool tma);
+                                 const double* ny, const double* vol, const double* volf, cudaStream_t st, bool tma, int part = 0);
 
 }  // namespace bcast

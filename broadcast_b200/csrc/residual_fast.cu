@@ -62,18 +62,31 @@ __device__ __forceinline__ void prefetch_tile_l2(const GridDesc& g, const double
 }
 
 __global__ void __launch_bounds__(rf::NT, 2)
-    k_residual_fast(int l2dist, GridDesc g, SchemeConsts c, double sqgr, bool wall, const double* __restrict__ w, const double* __restrict__ nx,
+    k_residual_fast(int l2dist, int ox, int oy, int ntx, int nty, GridDesc g, SchemeConsts c, double sqgr, bool wall, const double* __restrict__ w, const double* __restrict__ nx,
                     const double* __restrict__ ny, const double* __restrict__ vol, const double* __restrict__ volf,
                     double* __restrict__ res) {
   extern __shared__ __align__(128) double sm[];
   rf::TileCtx t = make_ctx(sm, g, c, sqgr, wall, w, nx, ny, vol, volf, res);
-  t.i0 = 1 + blockIdx.x * rf::OI;
-  t.j0 = 1 + blockIdx.y * rf::OJ;
+  // (ox, oy): first tile of this launch in the ntx x nty tile grid of the block (launches over a part of the tiles).
+  // l2dist < 0: ring launch, a 1-D grid over the tiles outside the inner rectangle [1, ox] x [1, oy] (= bx1, by1):
+  // first tile row, last tile rows, first tile column, last tile columns.
+  int bx_ = blockIdx.x + ox, by_ = blockIdx.y + oy;
+  if (l2dist < 0) {
+    const int bx1 = ox, by1 = oy;
+    int u = blockIdx.x;
+    const int nA = ntx, nB = ntx * (nty - by1 - 1), nC = by1;
+    if (u < nA) { bx_ = u; by_ = 0; }
+    else if ((u -= nA) < nB) { bx_ = u % ntx; by_ = by1 + 1 + u / ntx; }
+    else if ((u -= nB) < nC) { bx_ = 0; by_ = 1 + u; }
+    else { u -= nC; const int wr = ntx - bx1 - 1; bx_ = bx1 + 1 + u % wr; by_ = 1 + u / wr; }
+  }
+  t.i0 = 1 + bx_ * rf::OI;
+  t.j0 = 1 + by_ * rf::OJ;
   const int tid = threadIdx.x;
   if (l2dist > 0) {
-    const int L = blockIdx.y * gridDim.x + blockIdx.x + l2dist;
-    const int bx = L % gridDim.x, by = L / gridDim.x;
-    if (by < gridDim.y) prefetch_tile_l2(g, w, nx, ny, vol, volf, 1 + bx * rf::OI, 1 + by * rf::OJ, tid);
+    const int L = by_ * ntx + bx_ + l2dist;
+    const int bx = L % ntx, by = L / ntx;
+    if (by < nty) prefetch_tile_l2(g, w, nx, ny, vol, volf, 1 + bx * rf::OI, 1 + by * rf::OJ, tid);
   }
   const rf::FaceGeom gi = rf::prefetch_iface(t, tid);   // metric loads in flight across phases 0 and 1
   const rf::SensGeom sg0 = rf::prefetch_sensor(t, tid, 0), sg1 = rf::prefetch_sensor(t, tid, 1);   // ... across phase 0
@@ -110,11 +123,14 @@ cudaError_t prepare_kernel(K kernel, size_t smem) {
 cudaError_t launch_residual_fast_tma(const GridDesc& g, const SchemeConsts& c, double sqgr, bool wall, double* res, const double* w,
                                      const double* nx, const double* ny, const double* vol, const double* volf, cudaStream_t st, bool* done);
 
+// part: 0 = every tile; 1 = the tiles that touch neither the first / last tile column nor the first / last tile row (they read no
+// ghost cell and no slab halo column: they can run while the halo exchange and the boundary fills are still in flight);
+// 2 = the remaining ring of tiles.  1 followed by 2 writes exactly what 0 writes.
 cudaError_t launch_residual_fast(const GridDesc& g, const SchemeArgs& a, bool wall, double* res, const double* w, const double* nx,
-                                 const double* ny, const double* vol, const double* volf, cudaStream_t st, bool tma) {
+                                 const double* ny, const double* vol, const double* volf, cudaStream_t st, bool tma, int part) {
   const SchemeConsts c = make_consts(a.cp, a.cv, a.prandtl, a.gam, a.rgaz, a.cs, a.muref, a.tref, a.s_suth, a.k2, a.k4);
   const double sqgr = ::sqrt(a.gam * a.rgaz);
-  if (tma) {
+  if (tma && part == 0) {
     bool done = false;
     cudaError_t e = launch_residual_fast_tma(g, c, sqgr, wall, res, w, nx, ny, vol, volf, st, &done);
     if (done || e != cudaSuccess) return e;
@@ -128,7 +144,20 @@ cudaError_t launch_residual_fast(const GridDesc& g, const SchemeArgs& a, bool wa
     ready = true;
   }
   static const int l2dist = getenv("BROADCAST_B200_RESIDUAL_L2DIST") ? atoi(getenv("BROADCAST_B200_RESIDUAL_L2DIST")) : 592;
-  k_residual_fast<<<dim3(ntx, nty), rf::NT, SMEM, st>>>(l2dist, g, c, sqgr, wall, w, nx, ny, vol, volf, res);
+  auto go = [&](int ox, int oy, int cx, int cy, int dist) {
+    if (cx > 0 && cy > 0) k_residual_fast<<<dim3(cx, cy), rf::NT, SMEM, st>>>(dist, ox, oy, ntx, nty, g, c, sqgr, wall, w, nx, ny, vol, volf, res);
+  };
+  // inner tiles: bx in [1, bx1], by in [1, by1] -- every cell they read (tile + gh halo) is an interior cell
+  const int bx1 = (g.im - rf::OI - 3) / rf::OI, by1 = (g.jm - rf::OJ - 3) / rf::OJ;
+  const bool has_inner = bx1 >= 1 && by1 >= 1;
+  if (part == 0 || (part == 2 && !has_inner)) {
+    go(0, 0, ntx, nty, l2dist);
+  } else if (part == 1) {
+    if (has_inner) go(1, 1, bx1, by1, l2dist);
+  } else {   // the ring in ONE launch (1-D grid, tile found from the block index)
+    const int nring = ntx + ntx * (nty - by1 - 1) + by1 + (ntx - bx1 - 1) * by1;
+    k_residual_fast<<<nring, rf::NT, SMEM, st>>>(-1, bx1, by1, ntx, nty, g, c, sqgr, wall, w, nx, ny, vol, volf, res);
+  }
   return cudaGetLastError();
 }
 

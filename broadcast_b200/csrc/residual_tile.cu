@@ -209,13 +209,17 @@ __global__ void __launch_bounds__(TI* TJ, 3)
 }  // namespace
 
 cudaError_t launch_residual_tiled(const GridDesc& g, const SchemeArgs& a, bool wall, double* res, const double* w, const double* nx,
-                                  const double* ny, const double* vol, const double* volf, cudaStream_t st, int variant) {
-  if (g.im < 4 || g.jm < 6) return launch_residual_generic(g, a, wall, 0, res, w, nullptr, nx, ny, vol, volf, nullptr, st);
+                                  const double* ny, const double* vol, const double* volf, cudaStream_t st, int variant, int part) {
+  if (g.im < 4 || g.jm < 6 || (part != 0 && (variant == RES_TILE_V1 || variant == RES_FAST_TMA))) {
+    if (part == 1) return cudaSuccess;   // kernels without a tile split do everything in the "ring" call
+    if (g.im < 4 || g.jm < 6) return launch_residual_generic(g, a, wall, 0, res, w, nullptr, nx, ny, vol, volf, nullptr, st);
+    part = 0;
+  }
   // second-generation kernel (residual_fast.cu) unless the first one is asked for as a cross-check
   static const bool v1 = getenv("BROADCAST_B200_RESIDUAL_V1") != nullptr;
   static const bool tma = getenv("BROADCAST_B200_RESIDUAL_TMA") != nullptr;
   if (variant != RES_TILE_V1 && !(variant == RES_DEFAULT && v1))
-    return launch_residual_fast(g, a, wall, res, w, nx, ny, vol, volf, st, variant == RES_FAST_TMA || (variant == RES_DEFAULT && tma));
+    return launch_residual_fast(g, a, wall, res, w, nx, ny, vol, volf, st, variant == RES_FAST_TMA || (variant == RES_DEFAULT && tma), part);
   constexpr int TI = 32, TJ = 8;
   using TL = Tile<TI, TJ>;
   const SchemeConsts c = make_consts(a.cp, a.cv, a.prandtl, a.gam, a.rgaz, a.cs, a.muref, a.tref, a.s_suth, a.k2, a.k4);

@@ -136,6 +136,27 @@ class Block:
                   self.im, self.jm, self.wall, v, self._stream())
         return out
 
+    def residual_part(self, part, stream=None):
+        """part 1 = inner tiles (no ghost / halo reads), part 2 = the outer ring of tiles, 0 = all (bcd_residual_part)"""
+        st = ctypes.c_void_p(stream.cuda_stream) if stream is not None else self._stream()
+        self.call("bcd_residual_part", _p(self.res), _p(self.w), _p(self.nx), _p(self.ny), _p(self.vol), _p(self.volf), self.gh,
+                  *self._phys, self.im, self.jm, self.wall, int(part), st)
+        return self.res
+
+    def step_overlapped(self, halo=None):
+        """halo exchange + boundary fills on a side stream WHILE the inner tiles of the residual run; the ring of tiles that
+        reads ghosts / halo columns follows both.  Same result as halo(); step(), bit for bit."""
+        main = torch.cuda.current_stream(self.device)
+        side = self.__dict__.setdefault("_side_stream", torch.cuda.Stream(device=self.device))
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if halo is not None:
+                halo(self.w)
+            self.apply_bcs()
+        self.residual_part(1)
+        main.wait_stream(side)
+        return self.residual_part(2)
+
     def tangent(self, wd, ndir, out, w=None, rect=None):
         w = self.w if w is None else w
         r = None

@@ -158,6 +158,13 @@ int bcd_colour_range(int c0, int c1);
  * block is a set of pitched rows); kind 1 = host to device, 2 = device to host; asynchronous on `stream`. */
 int bcd_memcpy2d(void* dst, long long dpitch, const void* src, long long spitch, long long width, long long height, int kind,
                  void* stream);
+/* The residual in two parts for overlap with the halo exchange / boundary fills: part 1 = the tiles of the fused kernel that read
+ * neither ghost cells nor slab halo columns (everything but the outermost ring of 32 x 9 tiles), part 2 = that ring, part 0 = all.
+ * Part 1 may run while the ghosts are still being written; part 2 must follow the fills.  1 then 2 == 0, bit for bit. */
+int bcd_residual_part(double* residu, const double* w, const double* nx, const double* ny, const double* vol,
+                      const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
+                      double muref, double tref, double s_suth, double k2, double k4, int im, int jm, int wall, int part,
+                      void* stream);
 /* use_generic selects the kernel: 0 = default fused tile kernel (k_residual_fast), 1 = reference-shaped four-kernel
  * pipeline, 2 = fused kernel with persistent CTAs and TMA staging of w, 3 = first-generation fused kernel. All variants
  * compute the same residual (tests: 1e-12 of the plane maximum). */

@@ -67,6 +67,32 @@ def test_residual_kernel_variants_agree(gpu, ref, kind, im, jm):
     assert torch.equal(outs[0], outs[2])
 
 
+@pytest.mark.parametrize("im,jm", [(200, 64), (97, 33), (64, 18), (40, 12)])
+def test_residual_in_two_parts_equals_the_whole(gpu, im, jm):
+    """inner tiles + ring of tiles (bcd_residual_part 1, 2) == one launch, bit for bit; the inner part must not depend on any
+    ghost cell (poisoned while it runs); Block.step_overlapped == apply_bcs + residual"""
+    import torch
+    from broadcast_b200.resident import Block
+    c = H.make_case("bl", im, jm, gpu, with_w=True)
+    blk = Block(c)
+    blk.apply_bcs()
+    whole = blk.residual().clone()
+    gh = c.gh
+    w_ok = blk.w.clone()
+    blk.res.zero_()
+    blk.w[:, :gh] = float("nan"); blk.w[:, -gh:] = float("nan"); blk.w[:, :, :gh] = float("nan"); blk.w[:, :, -gh:] = float("nan")
+    blk.residual_part(1)
+    assert not torch.isnan(blk.res).any()
+    blk.w.copy_(w_ok)
+    blk.residual_part(2)
+    assert torch.equal(blk.res, whole)
+    blk.upload_state(c.w)
+    blk.res.zero_()
+    blk.step_overlapped()
+    torch.cuda.synchronize()
+    assert torch.equal(blk.res, whole)
+
+
 def test_residual_full_size_properties(gpu):
     """C5 (8192 x 2048, BASELINE.json's bench configuration): the oracle cannot run there in seconds, so size-independent
     properties: (1) the fused kernels agree with the reference-shaped pipeline to TOL-level noise (the reference's own
