@@ -13,17 +13,21 @@ void count_launches(int n);
 cudaError_t prepare_prims_grads(const GridDesc& g, const SchemeArgs& a, const double* w, const double* nx, const double* ny,
                                 const double* vol, const double* volf, FieldPtrs& f, cudaStream_t st);
 
+// blockIdx.z = face direction: one face package per thread (half the work per thread of the both-faces version, twice the threads)
 __global__ void __launch_bounds__(128) k_face_packages(GridDesc g, SchemeConsts c, FieldPtrs f, Rect rc, double* __restrict__ pkg) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + rc.i0;
   const int j = blockIdx.y * blockDim.y + threadIdx.y + rc.j0;
   if (i > rc.i1 || j > rc.j1) return;
   const GlobalAcc<0> a(f, g, i, j);
   const long long k = g.cidx(i, j);
-  double* p0 = pkg + k;
-  double* p1 = pkg + (long long)FPK_N * g.sc + k;
   const long long sc = g.sc;
-  face_package<0>(a, c, [&](int fld, double v) { p0[fld * sc] = v; });
-  face_package<1>(a, c, [&](int fld, double v) { p1[fld * sc] = v; });
+  if (blockIdx.z == 0) {
+    double* p0 = pkg + k;
+    face_package<0>(a, c, [&](int fld, double v) { p0[fld * sc] = v; });
+  } else {
+    double* p1 = pkg + (long long)FPK_N * g.sc + k;
+    face_package<1>(a, c, [&](int fld, double v) { p1[fld * sc] = v; });
+  }
 }
 
 template <int DIR>
@@ -178,7 +182,7 @@ cudaError_t launch_jacobian_faces(const GridDesc& g, const SchemeArgs& a, const 
   if (!pkg) return cudaErrorMemoryAllocation;
   const Rect rf{rc.i0, rc.i1 + 1, rc.j0, rc.j1 + 1};
   dim3 blk(32, 4);
-  dim3 gf((rf.i1 - rf.i0 + 32) / 32, (rf.j1 - rf.j0 + 4) / 4);
+  dim3 gf((rf.i1 - rf.i0 + 32) / 32, (rf.j1 - rf.j0 + 4) / 4, 2);
   k_face_packages<<<gf, blk, 0, st>>>(g, c, f, rf, pkg);
   dim3 gr((rc.i1 - rc.i0 + 32) / 32, (rc.j1 - rc.j0 + 4) / 4);
   static const bool unrolled = getenv("BROADCAST_B200_JAC_UNROLLED") != nullptr;   // template-unrolled variant (cross-check)

@@ -67,6 +67,22 @@ def test_residual_kernel_variants_agree(gpu, ref, kind, im, jm):
     assert torch.equal(outs[0], outs[2])
 
 
+@pytest.mark.parametrize("kind,im,jm", [("bl", 7, 7), ("bl", 8, 8), ("bl", 33, 7), ("bl", 9, 10), ("cyl", 14, 9), ("bl", 3, 12), ("bl", 12, 5)])
+def test_smallest_grids(gpu, ref, kind, im, jm):
+    """grids of one tile or less (a stencil wide, fewer rows than the wall scheme's special rows + 1 fall back to the generic
+    pipeline inside the same entry point): boundary fills, residual, one tangent direction vs the oracle"""
+    a = H.make_case(kind, im, jm, gpu, with_w=True)
+    b = H.make_case(kind, im, jm, ref, with_w=True)
+    wa, ra = H.residual_sequence(gpu, a)
+    wb, rb = H.residual_sequence(ref, b)
+    assert np.all(H.rel_err(wa, wb) < TOL), H.rel_err(wa, wb)
+    assert np.all(H.rel_err(ra, rb) < TOL), H.rel_err(ra, rb)
+    wd = np.asfortranarray(np.random.default_rng(1).standard_normal(wa.shape))
+    _, da = H.tangent_sequence(gpu, a, wa, wd)
+    _, db = H.tangent_sequence(ref, b, wb, wd)
+    assert np.all(H.rel_err(da, db) < TOL), H.rel_err(da, db)
+
+
 @pytest.mark.parametrize("im,jm", [(200, 64), (97, 33), (64, 18), (40, 12)])
 def test_residual_in_two_parts_equals_the_whole(gpu, im, jm):
     """inner tiles + ring of tiles (bcd_residual_part 1, 2) == one launch, bit for bit; the inner part must not depend on any
