@@ -103,8 +103,15 @@ class Block:
     def apply_bcs(self, w=None, wd=None, ndir=0):
         """ghost fill in driver order; with ``wd`` ([ndir,5,nj,ni]) the linearised fills (w and wd ghosts)."""
         L, st = self.lib, self._stream()
-        w = self.w if w is None else w
         im, jm, gh = self.im, self.jm, self.gh
+        if w is None and wd is None:
+            # primal fill of the block's own state: the whole list in ONE call (bcd_apply_bcs), descriptors built once
+            d = self.__dict__.get("_bc_desc_cache")
+            if d is None:
+                d = self._bc_desc_cache = _bc_descs(self)
+            self.call("bcd_apply_bcs", _p(self.w), _p(self.nx), _p(self.ny), ctypes.c_double(self.gam), gh, im, jm, d[0], d[1], st)
+            return
+        w = self.w if w is None else w
         I = lambda a: a.ctypes.data_as(ctypes.c_void_p)
         for bc in self.bcs:
             kind = bc[0]
@@ -233,13 +240,15 @@ class StreamedBlock:
             _lib.check(self.lib.bcd_memcpy2d(_p(b.w), LL(nl * 8), VP(src), LL(ni * 8), LL(nl * 8), LL(rows), 1, VP(self.s_in.cuda_stream)),
                        "bcd_memcpy2d")
             self.ev_in[k].record(self.s_in)
-        for k, (b, lo, hi) in enumerate(self.slabs):      # kernels of slab k as soon as its state has landed
+        for k, (b, lo, hi) in enumerate(self.slabs):
+            # kernels of slab k as soon as its state has landed ...
             self.s_k.wait_event(self.ev_in[k])
             with torch.cuda.stream(self.s_k):
                 b.apply_bcs()
                 b.residual()
             self.ev_k[k].record(self.s_k)
-        for k, (b, lo, hi) in enumerate(self.slabs):      # residual of slab k back as soon as it exists
+            # ... and its residual back as soon as it exists (issued right away: the host needs ~0.2 ms per slab to issue the
+            # kernels, a device-to-host copy issued after ALL kernels would start milliseconds late)
             nl = b.im + 2 * gh
             self.s_out.wait_event(self.ev_k[k])
             dst = res_pinned.data_ptr() + (lo - 1 + gh) * 8                   # owned columns only

@@ -36,4 +36,21 @@ for nslab in (4, 8, 16):
                 lib.bcd_memcpy2d(ctypes.c_void_p(d_in.data_ptr() + k * w * 5 * nj * 8), ctypes.c_longlong(w * 8), ctypes.c_void_p(h_in.data_ptr() + k * w * 8),
                                  ctypes.c_longlong(ni * 8), ctypes.c_longlong(w * 8), ctypes.c_longlong(5 * nj), 1, sp)
     out[f"h2d_pitched_{nslab}slabs_GBs"] = nslab * w * 5 * nj * 8 / timeit(pitched) / 1e9
+for nslab in (8,):
+    w = ni // nslab
+    def d2h_pitched():
+        for k in range(nslab):
+            st = (s1, s2)[k % 2]
+            with torch.cuda.stream(st):
+                sp = ctypes.c_void_p(st.cuda_stream)
+                lib.bcd_memcpy2d(ctypes.c_void_p(h_out.data_ptr() + k * w * 8), ctypes.c_longlong(ni * 8), ctypes.c_void_p(d_out.data_ptr() + k * w * 5 * nj * 8),
+                                 ctypes.c_longlong(w * 8), ctypes.c_longlong(w * 8), ctypes.c_longlong(5 * nj), 2, sp)
+    out[f"d2h_pitched_{nslab}slabs_GBs"] = nslab * w * 5 * nj * 8 / timeit(d2h_pitched) / 1e9
+    def duplex_pitched():
+        for k in range(nslab):
+            lib.bcd_memcpy2d(ctypes.c_void_p(d_in.data_ptr() + k * w * 5 * nj * 8), ctypes.c_longlong(w * 8), ctypes.c_void_p(h_in.data_ptr() + k * w * 8),
+                             ctypes.c_longlong(ni * 8), ctypes.c_longlong(w * 8), ctypes.c_longlong(5 * nj), 1, ctypes.c_void_p(s1.cuda_stream))
+            lib.bcd_memcpy2d(ctypes.c_void_p(h_out.data_ptr() + k * w * 8), ctypes.c_longlong(ni * 8), ctypes.c_void_p(d_out.data_ptr() + k * w * 5 * nj * 8),
+                             ctypes.c_longlong(w * 8), ctypes.c_longlong(w * 8), ctypes.c_longlong(5 * nj), 2, ctypes.c_void_p(s2.cuda_stream))
+    t = timeit(duplex_pitched); out["duplex_pitched_ms"] = t * 1e3
 print(json.dumps(out))
