@@ -330,6 +330,28 @@ def main():
                    "roofline": {"bound": "hbm", "kernel": "k_face_packages + k_jac_assemble_rt (+ strip colour loops)", "achieved": ach,
                                 "peak": peak, "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_cell": JAC_BYTES_PER_CELL,
                                 "interior_only_frac": JAC_BYTES_PER_CELL * cells_local / (int_ms * 1e-3) / 1e9 / peak}}
+            # CSR row block of this rank (zero filter, reference numbering, columns ascending: csrc/csr.cu) where it fits next
+            # to the block values (C5 on one GPU: 97 GB of blocks + ~75 GB of CSR do not)
+            free, _tot = torch.cuda.mem_get_info(dev)
+            if 110.0 * 5 * cells_local * 12 < 0.8 * free:
+                H.to_csr()
+                barrier()
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record()
+                ip, _idx, _dat = H.to_csr()
+                c1.record()
+                barrier()
+                cm = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
+                nz = torch.tensor([float(ip[-1].item())], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(cm, op=dist.ReduceOp.MAX)
+                    dist.all_reduce(nz, op=dist.ReduceOp.SUM)
+                jac["csr_ms"] = float(cm[0])
+                jac["csr_nnz"] = int(nz[0])
+                del ip, _idx, _dat
+            else:
+                jac["csr_ms"] = None
+                jac["csr_note"] = "CSR row block does not fit next to the block values on this GPU at this size"
             del blocks, H
             torch.cuda.empty_cache()
         else:

@@ -1,0 +1,309 @@
+// Hybrid block Jacobian -> CSR on the device: the last step of the assembly path, what the reference does on the host with
+// remove_zero_jac (BROADCAST_npz.py:129-135: keep |v| > 2e-16), scipy's csr_matrix((Jac,(IA,JA))) (misc/PETSc_func.py:85) and the
+// interpreted "divide by the cell volume" loop (BROADCAST_npz.py:1206-1209).
+//
+// Input: the 29 fixed 5x5 blocks per regular row cell (values[slot][e*5+m][cell], bcd_jacobian_interior) and the compact COO
+// lists of the boundary strips (bcd_jacobian_strips).  Output: indptr (int64), indices (int32, ascending inside a row), data of
+// the rows of this block (local row = e + 5 (j-1) + 5 jm (i-1), the reference's numbering; columns are global).
+//   1. k_csr_count_interior / k_csr_count_strip   kept entries per row (the sparsity pattern is value dependent, as in the reference)
+//   2. k_scan_*                                   exclusive scan of the counts: warp shuffles inside a warp, shared memory across the
+//                                                 warps of a block, a second level over the block sums
+//   3. k_csr_fill_interior                        one WARP per row cell: the 145 candidates of each of its five rows are read in
+//                                                 column order, kept ones compacted with ballot + popc and written as contiguous
+//                                                 runs (slot order is column order: no sort)
+//      k_csr_fill_strip + k_csr_sort_strip_rows   strip entries are appended with one atomic per entry, then every strip row
+//                                                 (<= 245 entries) is put in column order by a warp-wide rank sort in shared memory
+#include <cstdint>
+#include "../../include/broadcast_b200.h"
+#include "facejac.cuh"
+#include "kernels.cuh"
+
+namespace bcast {
+void count_launches(int n);
+
+namespace {
+
+__constant__ int kSlotDi[JAC_NSLOT] = {
+#define X(a, b) a,
+    BCAST_JAC_OFFSETS(X)
+#undef X
+};
+__constant__ int kSlotDj[JAC_NSLOT] = {
+#define X(a, b) b,
+    BCAST_JAC_OFFSETS(X)
+#undef X
+};
+
+constexpr int NCAND = JAC_NSLOT * 5;  // candidates of one row: 29 column cells x 5 variables
+
+// ---- 1. counts ---------------------------------------------------------------------------------------------------------
+// thread per cell of the region (i fastest: every plane is read coalesced), five row counters in registers
+__global__ void __launch_bounds__(128) k_csr_count_interior(GridDesc g, Rect rc, const double* __restrict__ V, double thresh,
+                                                            int* __restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + rc.i0;
+  const int j = blockIdx.y + rc.j0;
+  if (i > rc.i1) return;
+  const long long ncell = (long long)g.im * g.jm;
+  const long long cell = (long long)(i - 1) + (long long)(j - 1) * g.im;
+  int cnt[5] = {0, 0, 0, 0, 0};
+  for (int s = 0; s < JAC_NSLOT; ++s) {
+#pragma unroll
+    for (int q = 0; q < 25; ++q) cnt[q / 5] += ::fabs(__ldg(V + ((long long)s * 25 + q) * ncell + cell)) > thresh ? 1 : 0;
+  }
+  const long long row = 5LL * (j - 1) + 5LL * g.jm * (i - 1);
+#pragma unroll
+  for (int e = 0; e < 5; ++e) counts[row + e] = cnt[e];
+}
+
+__global__ void k_csr_count_strip(const double* __restrict__ jac, const int* __restrict__ ia, long long n, double thresh, long long row0,
+                                  int* __restrict__ counts) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  if (::fabs(jac[t]) > thresh) atomicAdd(&counts[ia[t] - row0], 1);
+}
+
+// ---- 2. exclusive scan int32 -> int64 ---------------------------------------------------------------------------------
+constexpr int SCAN_T = 256, SCAN_ITEMS = 8, SCAN_CHUNK = SCAN_T * SCAN_ITEMS;
+
+__device__ __forceinline__ long long warp_incl_scan(long long v) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long u = __shfl_up_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) >= o) v += u;
+  }
+  return v;
+}
+// inclusive scan over the threads of a block (blockDim.x <= 1024); *total = block sum
+__device__ __forceinline__ long long block_incl_scan(long long v, long long* total) {
+  __shared__ long long wsum[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_incl_scan(v);
+  if (lane == 31) wsum[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    long long s = lane < nw ? wsum[lane] : 0;
+    s = warp_incl_scan(s);
+    wsum[lane] = s;
+  }
+  __syncthreads();
+  if (wid > 0) v += wsum[wid - 1];
+  *total = wsum[nw - 1];
+  __syncthreads();
+  return v;
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_scan_reduce(const int* __restrict__ counts, long long n, long long* __restrict__ bsum) {
+  const long long base = (long long)blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
+  long long s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k)
+    if (base + k < n) s += counts[base + k];
+  long long tot;
+  block_incl_scan(s, &tot);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+// one block: exclusive scan of the block sums in place (tiles of blockDim.x with a running carry)
+__global__ void __launch_bounds__(1024) k_scan_blocks(long long* __restrict__ bsum, int nb) {
+  long long carry = 0;
+  for (int t0 = 0; t0 < nb; t0 += blockDim.x) {
+    const int idx = t0 + threadIdx.x;
+    const long long v = idx < nb ? bsum[idx] : 0;
+    long long tot;
+    const long long inc = block_incl_scan(v, &tot);
+    if (idx < nb) bsum[idx] = carry + inc - v;
+    carry += tot;
+  }
+}
+__global__ void __launch_bounds__(SCAN_T) k_scan_final(const int* __restrict__ counts, long long n, const long long* __restrict__ bsum,
+                                                       long long* __restrict__ indptr) {
+  const long long base = (long long)blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
+  int c[SCAN_ITEMS];
+  long long s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    c[k] = base + k < n ? counts[base + k] : 0;
+    s += c[k];
+  }
+  long long tot;
+  const long long inc = block_incl_scan(s, &tot);
+  long long run = bsum[blockIdx.x] + inc - s;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    if (base + k < n) indptr[base + k] = run;
+    run += c[k];
+  }
+  if (base <= n - 1 && n - 1 < base + SCAN_ITEMS) indptr[n] = run;   // the thread that holds the last count
+}
+
+// ---- 3. fill --------------------------------------------------------------------------------------------------------
+// one warp per cell of the region: for each of its five rows the 145 candidates are visited in column order, 32 at a time;
+// kept entries get their position from ballot / popc and leave as one contiguous run per 32 candidates
+// The eight warps of a block own eight consecutive cells in i (one row j): every 64-byte piece of a block plane they touch is used
+// completely (a lane reads ONE value of a plane; the other seven come from the neighbouring warps through L1).
+__global__ void __launch_bounds__(256) k_csr_fill_interior(GridDesc g, Rect rc, const double* __restrict__ V, double thresh,
+                                                           const double* __restrict__ vol, const long long* __restrict__ indptr,
+                                                           int* __restrict__ indices, double* __restrict__ data) {
+  const int lane = threadIdx.x & 31;
+  const int i = rc.i0 + blockIdx.x * 8 + (threadIdx.x >> 5), j = rc.j0 + blockIdx.y;
+  if (i > rc.i1) return;
+  const long long ncell = (long long)g.im * g.jm;
+  const long long cell = (long long)(i - 1) + (long long)(j - 1) * g.im;
+  const double volc = vol ? vol[g.cidx(i, j)] : 1.0;
+  const long long row0 = 5LL * (j - 1) + 5LL * g.jm * (i - 1);
+  const int ig = i + g.ioff;
+#pragma unroll 1
+  for (int e = 0; e < 5; ++e) {
+    long long pos = indptr[row0 + e];
+#pragma unroll 1
+    for (int c0 = 0; c0 < NCAND; c0 += 32) {
+      const int c = c0 + lane;
+      double v = 0.0;
+      int col = 0;
+      if (c < NCAND) {
+        const int s = c / 5, m = c % 5;
+        v = __ldg(V + ((long long)s * 25 + e * 5 + m) * ncell + cell);
+        col = m + 5 * (j + kSlotDj[s] - 1) + 5 * g.jm * (ig + kSlotDi[s] - 1);
+      }
+      const bool keep = c < NCAND && ::fabs(v) > thresh;
+      const unsigned mask = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const long long p = pos + __popc(mask & ((1u << lane) - 1u));
+        data[p] = vol ? v / volc : v;   // true division, as the reference's Jacvol loop
+        indices[p] = col;
+      }
+      pos += __popc(mask);
+    }
+  }
+}
+
+__global__ void k_csr_fill_strip(const double* __restrict__ jac, const int* __restrict__ ia, const int* __restrict__ ja, long long n,
+                                 double thresh, long long row0, const long long* __restrict__ indptr, int* __restrict__ cursor,
+                                 int* __restrict__ indices, double* __restrict__ data) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const double v = jac[t];
+  if (::fabs(v) > thresh) {
+    const long long r = ia[t] - row0;
+    const long long p = indptr[r] + atomicAdd(&cursor[r], 1);
+    data[p] = v;
+    indices[p] = ja[t];
+  }
+}
+
+// one warp per strip row: rank sort by column in shared memory (columns of a row are distinct: each (row, column) pair has
+// exactly one slot in the reference's colouring), then the optional division by the row cell's volume
+constexpr int SORT_MAX = 256;
+__global__ void __launch_bounds__(128) k_csr_sort_strip_rows(GridDesc g, RectList rl, const double* __restrict__ vol,
+                                                             const long long* __restrict__ indptr, int* __restrict__ indices,
+                                                             double* __restrict__ data, int* __restrict__ overflow) {
+  __shared__ int scol[4][SORT_MAX];
+  __shared__ double sval[4][SORT_MAX];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  long long wrow = (long long)blockIdx.x * 4 + w;   // index among the strip rows: rect by rect, cells i fastest, 5 rows per cell
+  int q = 0;
+  for (; q < rl.n; ++q) {
+    const long long nr = 5LL * (rl.r[q].i1 - rl.r[q].i0 + 1) * (rl.r[q].j1 - rl.r[q].j0 + 1);
+    if (wrow < nr) break;
+    wrow -= nr;
+  }
+  if (q == rl.n) return;
+  const Rect rc = rl.r[q];
+  const int e = (int)(wrow % 5);
+  const long long cellq = wrow / 5;
+  const int wi = rc.i1 - rc.i0 + 1;
+  const int i = rc.i0 + (int)(cellq % wi), j = rc.j0 + (int)(cellq / wi);
+  const long long row = e + 5LL * (j - 1) + 5LL * g.jm * (i - 1);
+  const long long p0 = indptr[row];
+  const int n = (int)(indptr[row + 1] - p0);
+  if (n > SORT_MAX) {
+    if (lane == 0) atomicAdd(overflow, 1);
+    return;
+  }
+  for (int k = lane; k < n; k += 32) {
+    scol[w][k] = indices[p0 + k];
+    sval[w][k] = data[p0 + k];
+  }
+  __syncwarp();
+  const double volc = vol ? vol[g.cidx(i, j)] : 1.0;
+  for (int k = lane; k < n; k += 32) {
+    const int ck = scol[w][k];
+    int rank = 0;
+    for (int u = 0; u < n; ++u) rank += (scol[w][u] < ck || (scol[w][u] == ck && u < k)) ? 1 : 0;
+    indices[p0 + rank] = ck;
+    data[p0 + rank] = vol ? sval[w][k] / volc : sval[w][k];
+  }
+}
+
+}  // namespace
+}  // namespace bcast
+
+using namespace bcast;
+
+// Step 1 + 2: indptr[0 .. 5 im jm] (int64, device) of the CSR row block; counts / bsum are device work arrays of
+// 5 im jm + 1 ints and ceil(5 im jm / 2048) + 1 int64.  The caller reads indptr[5 im jm] (= nnz) and allocates indices / data.
+extern "C" int bcd_hybrid_csr_indptr(long long* indptr, int32_t* counts, long long* bsum, const double* values, const int32_t* region,
+                                     int nstrip, const double* const* sjac, const int32_t* const* sia, const long long* slen, double thresh,
+                                     int gh, int im, int jm, void* stream) {
+  if (im < 1 || jm < 1 || gh != 3 || nstrip < 0 || nstrip > 4) return BC_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const GridDesc g = make_grid_ctx(im, jm, gh);
+  const long long n = 5LL * im * jm;
+  const long long row0 = 5LL * jm * g.ioff;
+  cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int) * (n + 1), st);
+  if (e != cudaSuccess) return (int)e;
+  const Rect rc{region[0], region[1], region[2], region[3]};
+  if (rc.i1 >= rc.i0 && rc.j1 >= rc.j0 && values)
+    k_csr_count_interior<<<dim3((rc.i1 - rc.i0 + 128) / 128, rc.j1 - rc.j0 + 1), 128, 0, st>>>(g, rc, values, thresh, counts);
+  for (int q = 0; q < nstrip; ++q)
+    if (slen[q] > 0) k_csr_count_strip<<<(unsigned)((slen[q] + 255) / 256), 256, 0, st>>>(sjac[q], sia[q], slen[q], thresh, row0, counts);
+  const int nb = (int)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
+  k_scan_reduce<<<nb, SCAN_T, 0, st>>>(counts, n, bsum);
+  k_scan_blocks<<<1, 1024, 0, st>>>(bsum, nb);
+  k_scan_final<<<nb, SCAN_T, 0, st>>>(counts, n, bsum, indptr);
+  count_launches(4 + nstrip);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? BC_OK : (int)e;
+}
+
+// Step 3: indices (int32) and data of the rows, columns ascending inside a row; vol (cell layout, or null) divides every row by
+// the volume of its cell; cursor = 5 im jm ints of work space.  Returns BC_ERR_UNSUPPORTED if a strip row holds more than 256
+// entries (cannot happen with the reference's colouring: 245 slots per row).
+extern "C" int bcd_hybrid_csr_fill(int32_t* indices, double* data, int32_t* cursor, const long long* indptr, const double* values,
+                                   const int32_t* region, int nstrip, const int32_t* srect /* [nstrip][4] */, const double* const* sjac,
+                                   const int32_t* const* sia, const int32_t* const* sja, const long long* slen, double thresh,
+                                   const double* vol, int gh, int im, int jm, void* stream) {
+  if (im < 1 || jm < 1 || gh != 3 || nstrip < 0 || nstrip > 4) return BC_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const GridDesc g = make_grid_ctx(im, jm, gh);
+  const long long n = 5LL * im * jm;
+  const long long row0 = 5LL * jm * g.ioff;
+  const Rect rc{region[0], region[1], region[2], region[3]};
+  if (rc.i1 >= rc.i0 && rc.j1 >= rc.j0 && values) {
+    k_csr_fill_interior<<<dim3((rc.i1 - rc.i0 + 8) / 8, rc.j1 - rc.j0 + 1), 256, 0, st>>>(g, rc, values, thresh, vol, indptr, indices, data);
+  }
+  if (nstrip > 0) {
+    cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(int) * (n + 1), st);
+    if (e != cudaSuccess) return (int)e;
+    RectList rl;
+    rl.n = nstrip;
+    long long nrows = 0;
+    for (int q = 0; q < 4; ++q) {
+      rl.r[q] = q < nstrip ? Rect{srect[4 * q], srect[4 * q + 1], srect[4 * q + 2], srect[4 * q + 3]} : Rect{1, 0, 1, 0};
+      if (q < nstrip) nrows += 5LL * (rl.r[q].i1 - rl.r[q].i0 + 1) * (rl.r[q].j1 - rl.r[q].j0 + 1);
+    }
+    for (int q = 0; q < nstrip; ++q)
+      if (slen[q] > 0)
+        k_csr_fill_strip<<<(unsigned)((slen[q] + 255) / 256), 256, 0, st>>>(sjac[q], sia[q], sja[q], slen[q], thresh, row0, indptr, cursor,
+                                                                           indices, data);
+    // cursor[n] doubles as the overflow flag of the sort (zeroed by the memset above)
+    k_csr_sort_strip_rows<<<(unsigned)((nrows + 3) / 4), 128, 0, st>>>(g, rl, vol, indptr, indices, data, cursor + n);
+    int ovf = 0;
+    e = cudaMemcpyAsync(&ovf, cursor + n, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return (int)e;
+    if (ovf) return BC_ERR_UNSUPPORTED;
+  }
+  count_launches(2 + nstrip);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? BC_OK : (int)e;
+}

@@ -384,8 +384,9 @@ class HybridJacobian:
     (gh+1..im-gh x gh+1..jm-gh; other rows of ``blocks`` are unused) and reference-ordered COO lists for
     the four boundary strips."""
 
-    def __init__(self, blk, blocks, offsets, strips, region):
+    def __init__(self, blk, blocks, offsets, strips, region, strip_rects=()):
         self.blk, self.blocks, self.offsets, self.strips, self.region = blk, blocks, offsets, strips, region
+        self.strip_rects = list(strip_rects)
 
     def to_coo(self, thresh=2e-16):
         """filtered COO (remove_zero_jac semantics) on the device, reference numbering of rows/columns"""
@@ -415,8 +416,13 @@ class HybridJacobian:
         return torch.cat(vals), torch.cat(rows), torch.cat(cols)
 
     def to_csr(self, thresh=2e-16, divide_by_vol=False):
-        """device-side CSR row block of this (slab's) rows: (indptr, indices, data) torch tensors with duplicates summed,
-        optionally divided by the row cell's volume (``Jacsurvol``, BROADCAST_npz.py:1206-1210)."""
+        """device-side CSR row block of this (slab's) rows: (indptr, indices, data) torch tensors, columns ascending in a row,
+        optionally divided by the row cell's volume (``Jacsurvol``, BROADCAST_npz.py:1206-1210).  Hand-written kernels
+        (``to_csr_device``); ``to_csr_torch`` is the same result by torch ops (the cross-check, ~150x slower at C1)."""
+        return self.to_csr_device(thresh, divide_by_vol)
+
+    def to_csr_torch(self, thresh=2e-16, divide_by_vol=False):
+        """``to_csr`` by torch ops (masked selects per block plane, sort-based COO -> CSR): cross-check of the kernels"""
         from . import formats
         blk = self.blk
         v, r, c = self.to_coo(thresh)
@@ -426,6 +432,35 @@ class HybridJacobian:
             v = v / blk.vol[cj, ci]
         n = 5 * blk.im_global * blk.jm
         return formats.coo_to_csr(v, r, c, 5 * blk.im * blk.jm, n, row0=5 * blk.jm * blk.ioff)
+
+    def to_csr_device(self, thresh=2e-16, divide_by_vol=False):
+        """the same CSR row block as ``to_csr`` by hand-written kernels (csrc/csr.cu): per-row counts, warp-shuffle scan, ballot-
+        compacted fill in column order, warp rank sort of the strip rows -- no sort of the whole matrix, no Python loop over the
+        725 block planes.  Returns (indptr int64, indices int32, data float64) device tensors."""
+        blk = self.blk
+        dev = blk.device
+        n = 5 * blk.im * blk.jm
+        indptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        counts = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        bsum = torch.empty(n // 2048 + 2, dtype=torch.int64, device=dev)
+        region = np.asarray(self.region, dtype=np.int32)
+        ns = len(self.strips)
+        PP = ctypes.c_void_p * max(ns, 1)
+        sj = PP(*[t[0].data_ptr() for t in self.strips])
+        si = PP(*[t[1].data_ptr() for t in self.strips])
+        sk = PP(*[t[2].data_ptr() for t in self.strips])
+        slen = (ctypes.c_longlong * max(ns, 1))(*[t[0].numel() for t in self.strips])
+        srect = np.asarray(self.strip_rects, dtype=np.int32).reshape(-1) if ns else np.zeros(4, dtype=np.int32)
+        VP = ctypes.c_void_p
+        blk.call("bcd_hybrid_csr_indptr", _p(indptr), _p(counts), _p(bsum), _p(self.blocks), region.ctypes.data_as(VP), ns, sj, si, slen,
+                 ctypes.c_double(thresh), blk.gh, blk.im, blk.jm, blk._stream())
+        nnz = int(indptr[-1].item())
+        indices = torch.empty(nnz, dtype=torch.int32, device=dev)
+        data = torch.empty(nnz, dtype=torch.float64, device=dev)
+        blk.call("bcd_hybrid_csr_fill", _p(indices), _p(data), _p(counts), _p(indptr), _p(self.blocks), region.ctypes.data_as(VP), ns,
+                 srect.ctypes.data_as(VP), sj, si, sk, slen, ctypes.c_double(thresh), _p(blk.vol if divide_by_vol else None), blk.gh,
+                 blk.im, blk.jm, blk._stream())
+        return indptr, indices, data
 
     def to_scipy_csr(self, thresh=2e-16):
         import scipy.sparse as sp
@@ -479,7 +514,7 @@ def jacobian_hybrid(blk: "Block", coefdiag=None, kind=None, blocks=None, interio
                           for r in rects]
         strip_buffers = cache[key]
     strips = jacobian_strips(blk, rects, coefdiag=cd, kind=kind, out=strip_buffers)
-    return HybridJacobian(blk, blocks, jacobian_slots(blk), strips, region)
+    return HybridJacobian(blk, blocks, jacobian_slots(blk), strips, region, strip_rects=rects)
 
 
 def jacobian_strips(blk: "Block", rects, coefdiag=None, kind="jv_relaxed", out=None):

@@ -266,6 +266,20 @@ int bcd_jacobian_interior_ad(double* values, const double* w, const double* nx, 
                              const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz,
                              double cs, double muref, double tref, double s_suth, double k2, double k4, int im, int jm,
                              const double* coefdiag, const int32_t* rect, void* stream);
+/* Hybrid block Jacobian -> CSR row block on the device (what the reference does on the host: remove_zero_jac, BROADCAST_npz.py:129-135;
+ * csr_matrix((Jac,(IA,JA))), misc/PETSc_func.py:85; the division by the cell volume, BROADCAST_npz.py:1206-1209).
+ * values = the 29-block array of bcd_jacobian_interior (region = i0,i1,j0,j1 of its valid rows), sjac/sia/sja/slen = the compact COO
+ * lists of bcd_jacobian_strips, srect their rectangles.  Local row = e + 5 (j-1) + 5 jm (i-1); columns global, ascending in a row.
+ * Step 1 (…_indptr): kept entries per row (|v| > thresh) and their exclusive scan; indptr has 5 im jm + 1 int64 entries, the last
+ * one is nnz.  counts: 5 im jm + 1 ints, bsum: 5 im jm / 2048 + 2 int64 of device work space.
+ * Step 2 (…_fill): indices / data of nnz entries; vol != null divides each row by the volume of its cell; cursor: 5 im jm + 1 ints. */
+int bcd_hybrid_csr_indptr(long long* indptr, int32_t* counts, long long* bsum, const double* values, const int32_t* region,
+                          int nstrip, const double* const* sjac, const int32_t* const* sia, const long long* slen, double thresh,
+                          int gh, int im, int jm, void* stream);
+int bcd_hybrid_csr_fill(int32_t* indices, double* data, int32_t* cursor, const long long* indptr, const double* values,
+                        const int32_t* region, int nstrip, const int32_t* srect, const double* const* sjac,
+                        const int32_t* const* sia, const int32_t* const* sja, const long long* slen, double thresh,
+                        const double* vol, int gh, int im, int jm, void* stream);
 /* primal boundary fill of a whole list */
 int bcd_apply_bcs(double* w, const double* nx, const double* ny, double gam, int gh, int im, int jm,
                   const bc_desc_t* bcs, int nbcs, void* stream);

@@ -535,6 +535,8 @@ def test_csr_row_blocks_and_petsc_file(gpu, tmp_path):
     ip, idx, dat = (t.cpu().numpy() for t in Hj.to_csr(divide_by_vol=True))
     assert np.array_equal(ip, A.indptr) and np.array_equal(idx, A.indices)
     assert np.allclose(dat, A.data, rtol=1e-15, atol=0)
+    ipt, idxt, datt = (t.cpu().numpy() for t in Hj.to_csr_torch(divide_by_vol=True))      # torch-op cross-check of the kernels
+    assert np.array_equal(ipt, ip) and np.array_equal(idxt, idx) and np.array_equal(datt, dat)
     # two slabs -> two row blocks -> host gather
     blocks = []
     for rk in range(2):
@@ -552,3 +554,45 @@ def test_csr_row_blocks_and_petsc_file(gpu, tmp_path):
     formats.write_petsc_aij(p, ip2, idx2, dat2, n)
     ip3, idx3, dat3, shape = formats.read_petsc_aij(p)
     assert shape == (n, n) and np.array_equal(ip3, A.indptr) and np.array_equal(dat3.real, dat2)
+
+
+@pytest.mark.parametrize("kind,im,jm", [("bl", 48, 26), ("cyl", 42, 30), ("bl", 97, 33)])
+def test_csr_kernels_match_scipy_semantics(gpu, kind, im, jm):
+    """hand-written CSR conversion (csrc/csr.cu: counts, warp-shuffle scan, ballot-compacted fill, warp rank sort of the strip
+    rows) == remove_zero_jac + csr_matrix((Jac,(IA,JA))) (+ the divide-by-volume loop) of the reference drivers: indptr, column
+    order and values bit for bit; also on the two row blocks of an i-slab split"""
+    import scipy.sparse as sp
+    from broadcast_b200 import sharding
+    from broadcast_b200.resident import Block, jacobian_hybrid, local_halo_exchange
+    g = H.make_case(kind, im, jm, gpu, with_w=True)
+    G = Block(g)
+    G.apply_bcs()
+    coef = np.asfortranarray(np.random.default_rng(2).uniform(0.5, 1.5, size=(im, jm)))
+    Hj = jacobian_hybrid(G, coefdiag=coef)
+    n = 5 * im * jm
+    gh = g.gh
+    v, r, c = (t.cpu().numpy() for t in Hj.to_coo())
+    for dbv in (False, True):
+        vv = v / g.vol[r // (5 * jm) + gh, (r % (5 * jm)) // 5 + gh] if dbv else v
+        A = sp.csr_matrix((vv, (r, c)), shape=(n, n))
+        A.sort_indices()
+        ip, idx, dat = (t.cpu().numpy() for t in Hj.to_csr_device(divide_by_vol=dbv))
+        assert ip[-1] == A.nnz == len(v)                      # no duplicate (row, column) pair in the reference's slot scheme
+        assert np.array_equal(ip, A.indptr) and np.array_equal(idx, A.indices)
+        assert np.array_equal(dat, A.data)
+    if kind == "bl":
+        blocks = []
+        for rk in range(2):
+            sl, desc = sharding.slab_of(g, rk, 2)
+            blocks.append(Block(sl, slab=desc))
+        local_halo_exchange(blocks)
+        parts = []
+        for rk, b in enumerate(blocks):
+            b.apply_bcs()
+            lo, hi = sharding.slab_range(im, rk, 2)
+            parts.append(tuple(t.cpu().numpy() for t in jacobian_hybrid(b, coefdiag=np.asfortranarray(coef[lo - 1:hi])).to_csr_device()))
+        ip2, idx2, dat2 = sharding.gather_row_blocks(parts)
+        A = sp.csr_matrix((v, (r, c)), shape=(n, n))
+        A.sort_indices()
+        assert np.array_equal(ip2, A.indptr) and np.array_equal(idx2, A.indices)
+        assert np.abs(dat2 - A.data).max() <= 1e-12 * np.abs(A.data).max()
