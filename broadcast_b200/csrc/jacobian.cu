@@ -269,14 +269,24 @@ extern "C" int bcd_jacobian_strips(int nrect, const int32_t* rects /* [nrect][4]
   auto put = [&](const void* p, size_t n) { key.append(reinterpret_cast<const char*>(p), n); };
   int dev = 0;
   cudaGetDevice(&dev);
-  put(&dev, sizeof dev); put(&g, sizeof g); put(&a, sizeof a); put(&rows, sizeof rows); put(&wall, sizeof wall);
+  // (field by field: raw struct bytes would drag uninitialised padding into the key and miss the cache at random)
+  const long long gk[] = {g.im, g.jm, g.gh, g.ldc, g.ldn, g.sc, g.sn, g.ioff, g.img, g.edges};
+  put(&dev, sizeof dev); put(gk, sizeof gk); put(&a, sizeof a); put(&wall, sizeof wall);
+  for (int q = 0; q < 4; ++q) {
+    const int rk[] = {rows.n, rows.r[q].i0, rows.r[q].i1, rows.r[q].j0, rows.r[q].j1};
+    put(rk, sizeof rk);
+  }
   put(&scatter_kind, sizeof scatter_kind); put(&nbcs, sizeof nbcs); put(&gam, sizeof gam);
-  for (int b = 0; b < nbcs; ++b) put(&bcs[b], sizeof(bc_desc_t));
+  for (int b = 0; b < nbcs; ++b) {
+    const bc_desc_t& d = bcs[b];
+    put(&d.kind, sizeof d.kind); put(d.loc, 3); put(d.window, sizeof d.window); put(d.prd, sizeof d.prd); put(d.tr, sizeof d.tr);
+    put(&d.lm, sizeof d.lm); put(&d.table, sizeof d.table);
+  }
   for (int q = 0; q < nrect; ++q) { put(&jac[q], sizeof(void*)); put(&ia[q], sizeof(void*)); put(&ja[q], sizeof(void*)); }
   const void* ptrs[] = {w, nx, ny, vol, volf, coefdiag, wd5, resd5, sc_[0], sc_[1], sc_[2], sc_[3]};
   put(ptrs, sizeof ptrs);
-  const ColourRange cr = current_colours();
-  put(&cr, sizeof cr);
+  const int crk[] = {current_colours().c0, current_colours().c1};
+  put(crk, sizeof crk);
   struct Entry { std::string key; cudaGraphExec_t exec; int nlaunch; };
   static thread_local std::list<Entry> cache;
   // graphs cannot be captured on the legacy default stream: use a blocking side stream, which the legacy stream orders with

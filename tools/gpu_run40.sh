@@ -1,0 +1,2 @@
+mkdir -p gpurun_out
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/r40_bench_n2.json 2> gpurun_out/r40_bench_n2.err; wc -l gpurun_out/r40_bench_n2.json; tail -n 4 gpurun_out/r40_bench_n2.err | cut -c1-300
