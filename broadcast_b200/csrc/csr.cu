@@ -8,9 +8,10 @@
 //   1. k_csr_count_interior / k_csr_count_strip   kept entries per row (the sparsity pattern is value dependent, as in the reference)
 //   2. k_scan_*                                   exclusive scan of the counts: warp shuffles inside a warp, shared memory across the
 //                                                 warps of a block, a second level over the block sums
-//   3. k_csr_fill_interior                        one WARP per row cell: the 145 candidates of each of its five rows are read in
-//                                                 column order, kept ones compacted with ballot + popc and written as contiguous
-//                                                 runs (slot order is column order: no sort)
+//   3. k_csr_fill_interior                        32 cells per block: the 145 candidate planes of an equation row staged in shared
+//                                                 memory by coalesced loads, then one WARP per cell row: candidates in column
+//                                                 order, kept ones compacted with ballot + popc and written as contiguous runs
+//                                                 (slot order is column order: no sort)
 //      k_csr_fill_strip + k_csr_sort_strip_rows   strip entries are appended with one atomic per entry, then every strip row
 //                                                 (<= 245 entries) is put in column order by a warp-wide rank sort in shared memory
 #include <cstdint>
@@ -138,40 +139,51 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_final(const int* __restrict__ c
 // ---- 3. fill --------------------------------------------------------------------------------------------------------
 // one warp per cell of the region: for each of its five rows the 145 candidates are visited in column order, 32 at a time;
 // kept entries get their position from ballot / popc and leave as one contiguous run per 32 candidates
-// The eight warps of a block own eight consecutive cells in i (one row j): every 64-byte piece of a block plane they touch is used
-// completely (a lane reads ONE value of a plane; the other seven come from the neighbouring warps through L1).
+// Block = 32 consecutive cells in i (one row j), 8 warps.  Per equation row e the 145 candidate planes are first staged into shared
+// memory with COALESCED loads (one plane = 32 consecutive cells = one 256-byte warp load), then every warp compacts the rows of
+// four cells: lane = candidate (column order), ballot + popc give the position, the kept run leaves contiguously.
+constexpr int FILL_CELLS = 32, FILL_PITCH = FILL_CELLS + 1;   // +1: lanes walk a column of the staged tile, conflict free
 __global__ void __launch_bounds__(256) k_csr_fill_interior(GridDesc g, Rect rc, const double* __restrict__ V, double thresh,
                                                            const double* __restrict__ vol, const long long* __restrict__ indptr,
                                                            int* __restrict__ indices, double* __restrict__ data) {
-  const int lane = threadIdx.x & 31;
-  const int i = rc.i0 + blockIdx.x * 8 + (threadIdx.x >> 5), j = rc.j0 + blockIdx.y;
-  if (i > rc.i1) return;
+  __shared__ double sv[NCAND * FILL_PITCH];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int ib = rc.i0 + blockIdx.x * FILL_CELLS, j = rc.j0 + blockIdx.y;
+  const int nc = min(FILL_CELLS, rc.i1 - ib + 1);
   const long long ncell = (long long)g.im * g.jm;
-  const long long cell = (long long)(i - 1) + (long long)(j - 1) * g.im;
-  const double volc = vol ? vol[g.cidx(i, j)] : 1.0;
-  const long long row0 = 5LL * (j - 1) + 5LL * g.jm * (i - 1);
-  const int ig = i + g.ioff;
+  const long long cell0 = (long long)(ib - 1) + (long long)(j - 1) * g.im;
 #pragma unroll 1
   for (int e = 0; e < 5; ++e) {
-    long long pos = indptr[row0 + e];
+    __syncthreads();
+    for (int c = w; c < NCAND; c += 8) {   // candidate c = (slot c / 5, variable c % 5): plane slot * 25 + e * 5 + m
+      const long long plane = (long long)(c / 5) * 25 + e * 5 + c % 5;
+      sv[c * FILL_PITCH + lane] = lane < nc ? __ldg(V + plane * ncell + cell0 + lane) : 0.0;
+    }
+    __syncthreads();
+    for (int q = w; q < nc; q += 8) {
+      const int i = ib + q;
+      const double volc = vol ? vol[g.cidx(i, j)] : 1.0;
+      const int ig = i + g.ioff;
+      long long pos = indptr[e + 5LL * (j - 1) + 5LL * g.jm * (i - 1)];
 #pragma unroll 1
-    for (int c0 = 0; c0 < NCAND; c0 += 32) {
-      const int c = c0 + lane;
-      double v = 0.0;
-      int col = 0;
-      if (c < NCAND) {
-        const int s = c / 5, m = c % 5;
-        v = __ldg(V + ((long long)s * 25 + e * 5 + m) * ncell + cell);
-        col = m + 5 * (j + kSlotDj[s] - 1) + 5 * g.jm * (ig + kSlotDi[s] - 1);
+      for (int c0 = 0; c0 < NCAND; c0 += 32) {
+        const int c = c0 + lane;
+        double v = 0.0;
+        int col = 0;
+        if (c < NCAND) {
+          const int s = c / 5, m = c % 5;
+          v = sv[c * FILL_PITCH + q];
+          col = m + 5 * (j + kSlotDj[s] - 1) + 5 * g.jm * (ig + kSlotDi[s] - 1);
+        }
+        const bool keep = c < NCAND && ::fabs(v) > thresh;
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+          const long long p = pos + __popc(mask & ((1u << lane) - 1u));
+          data[p] = vol ? v / volc : v;   // true division, as the reference's Jacvol loop
+          indices[p] = col;
+        }
+        pos += __popc(mask);
       }
-      const bool keep = c < NCAND && ::fabs(v) > thresh;
-      const unsigned mask = __ballot_sync(0xffffffffu, keep);
-      if (keep) {
-        const long long p = pos + __popc(mask & ((1u << lane) - 1u));
-        data[p] = vol ? v / volc : v;   // true division, as the reference's Jacvol loop
-        indices[p] = col;
-      }
-      pos += __popc(mask);
     }
   }
 }
@@ -279,7 +291,8 @@ extern "C" int bcd_hybrid_csr_fill(int32_t* indices, double* data, int32_t* curs
   const long long row0 = 5LL * jm * g.ioff;
   const Rect rc{region[0], region[1], region[2], region[3]};
   if (rc.i1 >= rc.i0 && rc.j1 >= rc.j0 && values) {
-    k_csr_fill_interior<<<dim3((rc.i1 - rc.i0 + 8) / 8, rc.j1 - rc.j0 + 1), 256, 0, st>>>(g, rc, values, thresh, vol, indptr, indices, data);
+    k_csr_fill_interior<<<dim3((rc.i1 - rc.i0 + FILL_CELLS) / FILL_CELLS, rc.j1 - rc.j0 + 1), 256, 0, st>>>(g, rc, values, thresh, vol, indptr,
+                                                                                                      indices, data);
   }
   if (nstrip > 0) {
     cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(int) * (n + 1), st);

@@ -190,7 +190,7 @@ cudaError_t launch_jacobian_faces(const GridDesc& g, const SchemeArgs& a, const 
     k_jac_assemble<<<gr, blk, 0, st>>>(g, c, f, rc, pkg, values, coefdiag);
   else
   {
-    static const int cfg = getenv("BROADCAST_B200_JAC_CFG") ? atoi(getenv("BROADCAST_B200_JAC_CFG")) : 0;
+    static const int cfg = getenv("BROADCAST_B200_JAC_CFG") ? atoi(getenv("BROADCAST_B200_JAC_CFG")) : 5;
     const dim3 grd((rc.i1 - rc.i0 + JT_I) / JT_I, (rc.j1 - rc.j0 + JT_J) / JT_J), blk2(JT_I, JT_J);
     auto go = [&](auto kern, int st_field) -> cudaError_t {
       const size_t smem = (size_t)(FPK_N - st_field) * (JT_J * (JT_I + 1) + (JT_J + 1) * JT_I) * sizeof(double);
@@ -205,7 +205,9 @@ cudaError_t launch_jacobian_faces(const GridDesc& g, const SchemeArgs& a, const 
     else if (cfg == 2) e = go(k_jac_assemble_rt<40, 4>, 40);   // 14 staged fields, 128 registers
     else if (cfg == 3) e = go(k_jac_assemble_rt<40, 5>, 40);   // 14 staged fields, 96 registers, 20 warps per SM
     else if (cfg == 4) e = go(k_jac_assemble_rt<35, 3>, 35);   // 19 staged fields, 168 registers
-    else e = go(k_jac_assemble_rt<27, 3>, 27);                 // 27 staged fields, 168 registers, 12 warps per SM
+    else if (cfg == 0) e = go(k_jac_assemble_rt<27, 3>, 27);   // 27 staged fields, 168 registers, 12 warps per SM
+    else e = go(k_jac_assemble_rt<27, 2>, 27);                 // DEFAULT: 27 staged fields, 255 registers (no spills), 8 warps per SM
+    // measured at 4096x1024 (profiles/r1_g_summary.md, r1_h): 12.17 ms (168 registers) vs 11.43 ms (255 registers)
     if (e != cudaSuccess) return e;
   }
   count_launches(5);
