@@ -335,7 +335,8 @@ __global__ void __launch_bounds__(128) k_balance_faces5(GridDesc g, SchemeConsts
 
 // ---------------------------------------------------------------------------------------------
 // Strip tangent, second version: one block = a tile of 32 x th (th <= 3) or tw x 32 (tw <= 3) cells of a boundary strip
-// and ONE direction.  Every face of the tile is evaluated ONCE (33*th + 32*(th+1) <= 227 faces on 256 threads instead of
+// and ONE direction (rectangles thicker than a strip are cut into bands of three rows, blockIdx.y: the full colour loop of
+// bcd_jacobian_coo uses the same kernel).  Every face of the tile is evaluated ONCE (33*th + 32*(th+1) <= 227 faces on 256 threads instead of
 // 4 per cell), and only if a tangent input of its stencil is non-zero in this direction: the block first builds the
 // activity map of its cell window from wd (seeds and linearised ghost fills), a face is skipped when none of the cells
 // of its stencil is active and the tangents of its two sensor gradients are zero (with seeds 7 cells apart about half of
@@ -351,8 +352,9 @@ __global__ void __launch_bounds__(TL * 8, MINB) k_strip_faces5(GridDesc g, Schem
   __shared__ double sh[5][SF_MAXF];
   __shared__ unsigned char flag[(TL + 6) * 9];
   const int dir = blockIdx.z;
-  const int ti0 = wide ? rc.i0 + TL * blockIdx.x : rc.i0;
-  const int tj0 = wide ? rc.j0 : rc.j0 + TL * blockIdx.x;
+  // blockIdx.y: band of three rows (wide) / three columns (tall) of a rectangle thicker than a strip
+  const int ti0 = wide ? rc.i0 + TL * blockIdx.x : rc.i0 + 3 * blockIdx.y;
+  const int tj0 = wide ? rc.j0 + 3 * blockIdx.y : rc.j0 + TL * blockIdx.x;
   const int twc = min(wide ? TL : 3, rc.i1 - ti0 + 1);
   const int thc = min(wide ? 3 : TL, rc.j1 - tj0 + 1);
   const int fw = twc + 6, fh = thc + 6;   // activity window: cells ti0-3 .. ti0+twc+2, tj0-3 .. tj0+thc+2
@@ -451,20 +453,21 @@ cudaError_t tangent_strips_5(const GridDesc& g, const SchemeArgs& a, bool wall, 
     const int wi = q.i1 - q.i0 + 1, wj = q.j1 - q.j0 + 1;
     static const bool v1 = getenv("BROADCAST_B200_STRIPS_V1") != nullptr;
     static const int cfg_env = getenv("BROADCAST_B200_STRIPS_CFG") ? atoi(getenv("BROADCAST_B200_STRIPS_CFG")) : -1;
-    const int wide = (wj <= 3 && wi >= wj) ? 1 : 0;
-    if (!v1 && (wide || wi <= 3)) {
+    const int wide = wi >= wj || wi > 3 ? 1 : 0;   // thin column strips run along j, everything else in bands of three rows
+    if (!v1) {
       const int len = wide ? wi : wj;
+      const int nband = wide ? (wj + 2) / 3 : (wi + 2) / 3;
       // measured on B200 (profiles/r1_f_summary.md): 16-cell tiles at 168 registers (12 warps per SM, 552 B of spills) win on long
       // strips (4096x1024: 22.2 -> 19.8 ms), 32-cell tiles at 254 registers on short ones
       const int cfg = cfg_env >= 0 ? cfg_env : (len >= 1024 ? 2 : 0);
       if (cfg == 1)
-        k_strip_faces5<32, 2><<<dim3((len + 31) / 32, 1, 5), 256, 0, s1>>>(g, c, f, wall, q, wide, out5);
+        k_strip_faces5<32, 2><<<dim3((len + 31) / 32, nband, 5), 256, 0, s1>>>(g, c, f, wall, q, wide, out5);
       else if (cfg == 2)
-        k_strip_faces5<16, 3><<<dim3((len + 15) / 16, 1, 5), 128, 0, s1>>>(g, c, f, wall, q, wide, out5);
+        k_strip_faces5<16, 3><<<dim3((len + 15) / 16, nband, 5), 128, 0, s1>>>(g, c, f, wall, q, wide, out5);
       else if (cfg == 3)
-        k_strip_faces5<16, 4><<<dim3((len + 15) / 16, 1, 5), 128, 0, s1>>>(g, c, f, wall, q, wide, out5);
+        k_strip_faces5<16, 4><<<dim3((len + 15) / 16, nband, 5), 128, 0, s1>>>(g, c, f, wall, q, wide, out5);
       else
-        k_strip_faces5<32, 1><<<dim3((len + 31) / 32, 1, 5), 256, 0, s1>>>(g, c, f, wall, q, wide, out5);
+        k_strip_faces5<32, 1><<<dim3((len + 31) / 32, nband, 5), 256, 0, s1>>>(g, c, f, wall, q, wide, out5);
     } else {
       const int ncell = wi * wj;
       k_balance_faces5<<<dim3((ncell + 31) / 32, 1, 5), dim3(32, 1, 4), 0, s1>>>(g, c, f, wall, r1, out5);

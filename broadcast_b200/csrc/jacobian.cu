@@ -153,7 +153,11 @@ extern "C" int bcd_jacobian_coo(double* jac, int32_t* ia, int32_t* ja, double* w
       if (e != cudaSuccess) return (int)e;
       e = apply_bc_list(g, gam, 5, w, wd5, nx, ny, bcs, nbcs, st);
       if (e != cudaSuccess) return (int)e;
-      e = launch_residual_generic(g, a, wall != 0, 5, resd5, w, wd5, nx, ny, vol, volf, &rc, st);
+      // tangent of the rows of rc, five directions: one face per thread, every face once, faces without a tangent input skipped
+      // (k_strip_faces5 over bands of three rows); BROADCAST_B200_COO_GENERIC=1: the cell-centred k_balance<5>
+      static const bool coo_generic = getenv("BROADCAST_B200_COO_GENERIC") != nullptr;
+      if (coo_generic) e = launch_residual_generic(g, a, wall != 0, 5, resd5, w, wd5, nx, ny, vol, volf, &rc, st);
+      else e = launch_tangent_strips5(g, a, wall != 0, one_rect(rc), resd5, w, wd5, nx, ny, vol, volf, st);
       if (e != cudaSuccess) return (int)e;
       k_scatter5<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(g, scatter_kind, jac, ia, ja, resd5, l, k, coefdiag, vol, rc, (rect && compact) ? 1 : 0);
       e = cudaGetLastError();
