@@ -259,6 +259,8 @@ extern "C" int bcd_hybrid_csr_indptr(long long* indptr, int32_t* counts, long lo
   if (im < 1 || jm < 1 || gh != 3 || nstrip < 0 || nstrip > 4) return BC_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const GridDesc g = make_grid_ctx(im, jm, gh);
+  // limits of this layout: one grid row per j (65 535), 32-bit column indices (5 * im_global * jm < 2^31)
+  if (jm > 65535 || 5LL * g.img * jm >= (1LL << 31)) return BC_ERR_UNSUPPORTED;
   const long long n = 5LL * im * jm;
   const long long row0 = 5LL * jm * g.ioff;
   cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int) * (n + 1), st);
