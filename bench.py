@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 
 RES_BYTES_PER_CELL = 136.0  # 12 doubles read (w5, nx2, ny2, vol, volf2) + 5 written, SURVEY.md 8(d)
 JAC_BYTES_PER_CELL = 5904.0  # 29 blocks x 25 doubles written + 13 doubles read, SURVEY.md 8(d)
-RES_TRAFFIC_NCU = 2.268e9    # dram__bytes_read.sum + dram__bytes_write.sum of one launch at C5 (profiles/r1_e_residual_fast_full_raw.csv)
+RES_TRAFFIC_NCU = 2.278e9    # dram__bytes_read.sum + dram__bytes_write.sum of one launch at C5 (profiles/r1_i_residual_fast_full_raw.csv)
 
 
 def parse():
