@@ -62,7 +62,7 @@ __device__ __forceinline__ void prefetch_tile_l2(const GridDesc& g, const double
 }
 
 __global__ void __launch_bounds__(rf::NT, 2)
-    k_residual_fast(int l2dist, int ox, int oy, int ntx, int nty, GridDesc g, SchemeConsts c, double sqgr, bool wall, const double* __restrict__ w, const double* __restrict__ nx,
+    k_residual_fast(int l2dist, int early, int ox, int oy, int ntx, int nty, GridDesc g, SchemeConsts c, double sqgr, bool wall, const double* __restrict__ w, const double* __restrict__ nx,
                     const double* __restrict__ ny, const double* __restrict__ vol, const double* __restrict__ volf,
                     double* __restrict__ res) {
   extern __shared__ __align__(128) double sm[];
@@ -89,9 +89,18 @@ __global__ void __launch_bounds__(rf::NT, 2)
     if (by < nty) prefetch_tile_l2(g, w, nx, ny, vol, volf, 1 + bx * rf::OI, 1 + by * rf::OJ, tid);
   }
   const rf::FaceGeom gi = rf::prefetch_iface(t, tid);   // metric loads in flight across phases 0 and 1
-  const rf::SensGeom sg0 = rf::prefetch_sensor(t, tid, 0), sg1 = rf::prefetch_sensor(t, tid, 1);   // ... across phase 0
+  // sensor-cell metrics: before phase 0 (early != 0) or at their use in phase 1 (with the L2 prefetch they are L2 hits there)
+  rf::SensGeom sg0{}, sg1{};
+  if (early) {
+    sg0 = rf::prefetch_sensor(t, tid, 0);
+    sg1 = rf::prefetch_sensor(t, tid, 1);
+  }
   rf::phase0<false>(t, tid);
   __syncthreads();
+  if (!early) {
+    sg0 = rf::prefetch_sensor(t, tid, 0);
+    sg1 = rf::prefetch_sensor(t, tid, 1);
+  }
   rf::phase1(t, tid, sg0, sg1);
   __syncthreads();
   if (t.has_ghost_sensor()) {  // CTA-uniform
@@ -144,8 +153,9 @@ cudaError_t launch_residual_fast(const GridDesc& g, const SchemeArgs& a, bool wa
     ready = true;
   }
   static const int l2dist = getenv("BROADCAST_B200_RESIDUAL_L2DIST") ? atoi(getenv("BROADCAST_B200_RESIDUAL_L2DIST")) : 592;
+  static const int early = getenv("BROADCAST_B200_RESIDUAL_EARLY_SENSOR") ? atoi(getenv("BROADCAST_B200_RESIDUAL_EARLY_SENSOR")) : 1;
   auto go = [&](int ox, int oy, int cx, int cy, int dist) {
-    if (cx > 0 && cy > 0) k_residual_fast<<<dim3(cx, cy), rf::NT, SMEM, st>>>(dist, ox, oy, ntx, nty, g, c, sqgr, wall, w, nx, ny, vol, volf, res);
+    if (cx > 0 && cy > 0) k_residual_fast<<<dim3(cx, cy), rf::NT, SMEM, st>>>(dist, early, ox, oy, ntx, nty, g, c, sqgr, wall, w, nx, ny, vol, volf, res);
   };
   // inner tiles: bx in [1, bx1], by in [1, by1] -- every cell they read (tile + gh halo) is an interior cell
   const int bx1 = (g.im - rf::OI - 3) / rf::OI, by1 = (g.jm - rf::OJ - 3) / rf::OJ;
@@ -156,7 +166,7 @@ cudaError_t launch_residual_fast(const GridDesc& g, const SchemeArgs& a, bool wa
     if (has_inner) go(1, 1, bx1, by1, l2dist);
   } else {   // the ring in ONE launch (1-D grid, tile found from the block index)
     const int nring = ntx + ntx * (nty - by1 - 1) + by1 + (ntx - bx1 - 1) * by1;
-    k_residual_fast<<<nring, rf::NT, SMEM, st>>>(-1, bx1, by1, ntx, nty, g, c, sqgr, wall, w, nx, ny, vol, volf, res);
+    k_residual_fast<<<nring, rf::NT, SMEM, st>>>(-1, early, bx1, by1, ntx, nty, g, c, sqgr, wall, w, nx, ny, vol, volf, res);
   }
   return cudaGetLastError();
 }
