@@ -334,6 +334,10 @@ __global__ void __launch_bounds__(128) k_balance_faces5(GridDesc g, SchemeConsts
 }
 
 // ---------------------------------------------------------------------------------------------
+cudaError_t launch_tangent_tile5(const GridDesc& g, const SchemeArgs& a, bool wall, const Rect& rc, double* out5, const double* w,
+                                 const double* wd5, const double* nx, const double* ny, const double* vol, const double* volf,
+                                 cudaStream_t st);
+
 // Strip tangent, second version: one block = a tile of 32 x th (th <= 3) or tw x 32 (tw <= 3) cells of a boundary strip
 // and ONE direction (rectangles thicker than a strip are cut into bands of three rows, blockIdx.y: the full colour loop of
 // bcd_jacobian_coo uses the same kernel).  Every face of the tile is evaluated ONCE (33*th + 32*(th+1) <= 227 faces on 256 threads instead of
@@ -426,8 +430,30 @@ __global__ void __launch_bounds__(TL * 8, MINB) k_strip_faces5(GridDesc g, Schem
   }
 }
 
-cudaError_t tangent_strips_5(const GridDesc& g, const SchemeArgs& a, bool wall, const RectList& rows, double* out5, const double* w,
+cudaError_t tangent_strips_5(const GridDesc& g, const SchemeArgs& a, bool wall, const RectList& rows_in, double* out5, const double* w,
                              const double* wd5, const double* nx, const double* ny, const double* vol, const double* volf, cudaStream_t st) {
+  // Row-shaped rectangles (the Jlo / Jhi strips, the whole grid of the colour loop) go to the fused dual-number tile kernel
+  // (residual_tangent.cu: no global primitive / gradient arrays); thin column strips keep the chain below.
+  static const bool use_tile = getenv("BROADCAST_B200_TANGENT_TILE") == nullptr || atoi(getenv("BROADCAST_B200_TANGENT_TILE")) != 0;
+  RectList tiled, rest;
+  tiled.n = rest.n = 0;
+  for (int k = 0; k < 4; ++k) tiled.r[k] = rest.r[k] = Rect{1, 0, 1, 0};
+  for (int k = 0; k < rows_in.n; ++k) {
+    const Rect& q = rows_in.r[k];
+    const int wi = q.i1 - q.i0 + 1, wj = q.j1 - q.j0 + 1;
+    if (use_tile && (wi >= wj || wi > 3)) tiled.r[tiled.n++] = q;
+    else rest.r[rest.n++] = q;
+  }
+  if (tiled.n > 0) {
+    cudaError_t et = cudaSuccess;
+    for_each_rect(tiled, st, [&](const RectList& r1, int, cudaStream_t s1) {
+      const cudaError_t e1 = launch_tangent_tile5(g, a, wall, r1.r[0], out5, w, wd5, nx, ny, vol, volf, s1);
+      if (e1 != cudaSuccess) et = e1;
+    });
+    if (et != cudaSuccess) return et;
+  }
+  if (rest.n == 0) return cudaGetLastError();
+  const RectList& rows = rest;
   constexpr int N = 5;
   const SchemeConsts c = make_consts(a.cp, a.cv, a.prandtl, a.gam, a.rgaz, a.cs, a.muref, a.tref, a.s_suth, a.k2, a.k4);
   double* prim = scratch_doubles(0, (size_t)g.sc * NPRIM);

@@ -32,8 +32,69 @@
 #define BCAST_RF_NS rf
 #endif
 
+// A translation unit that defines BCAST_RF_DUAL gets the same algorithm in forward-mode tangent arithmetic (value + ONE tangent
+// direction per scalar: residual_tangent.cu, the strip / colour-loop tangent kernel): `real` is then a dual number, every state-
+// dependent scalar below is a `real`, the mesh metrics stay double.  Non-smooth intrinsics follow the conventions of the
+// reference's Tapenade tangent (dual.cuh): abs' by the sign of x (x >= 0 -> +), max takes the second operand iff the first is
+// smaller, sqrt'(0) = 0.
 namespace bcast {
 namespace BCAST_RF_NS {
+
+#ifdef BCAST_RF_DUAL
+struct Dual {
+  double v, d;
+};
+using real = Dual;
+BC_HD Dual operator+(Dual a, Dual b) { return {a.v + b.v, a.d + b.d}; }
+BC_HD Dual operator+(Dual a, double b) { return {a.v + b, a.d}; }
+BC_HD Dual operator+(double a, Dual b) { return {a + b.v, b.d}; }
+BC_HD Dual operator-(Dual a, Dual b) { return {a.v - b.v, a.d - b.d}; }
+BC_HD Dual operator-(Dual a, double b) { return {a.v - b, a.d}; }
+BC_HD Dual operator-(double a, Dual b) { return {a - b.v, -b.d}; }
+BC_HD Dual operator-(Dual a) { return {-a.v, -a.d}; }
+BC_HD Dual operator*(Dual a, Dual b) { return {a.v * b.v, a.d * b.v + a.v * b.d}; }
+BC_HD Dual operator*(Dual a, double b) { return {a.v * b, a.d * b}; }
+BC_HD Dual operator*(double a, Dual b) { return {a * b.v, a * b.d}; }
+BC_HD Dual operator/(Dual a, double b) { return {a.v / b, a.d / b}; }
+BC_HD Dual& operator+=(Dual& a, Dual b) { a.v += b.v; a.d += b.d; return a; }
+BC_HD double rf_val(Dual x) { return x.v; }
+BC_HD double rf_out(Dual x) { return x.d; }   // what a tangent kernel stores
+BC_HD Dual rf_const(double x) { return {x, 0.0}; }
+BC_HD Dual rf_sqrt(Dual x) {
+  const double s = ::sqrt(x.v);
+  return {s, x.v == 0.0 ? 0.0 : x.d / (2.0 * s)};
+}
+BC_HD Dual rf_abs(Dual x) { return {::fabs(x.v), x.v >= 0.0 ? x.d : -x.d}; }
+BC_HD Dual rf_max(Dual a, Dual b) { return a.v < b.v ? b : a; }
+BC_HD Dual rf_max(double a, Dual b) { return a < b.v ? b : Dual{a, 0.0}; }
+BC_HD Dual rf_min(Dual a, double b) { return a.v < b ? a : Dual{b, 0.0}; }
+BC_HD Dual rf_exp(Dual x) {
+  const double e = ::exp(x.v);
+  return {e, e * x.d};
+}
+using RfDT = Tan<1>;
+BC_HD Var<Tan<1>> rf_to_var(Dual x) {
+  Var<Tan<1>> r;
+  r.v = x.v;
+  r.d.d[0] = x.d;
+  return r;
+}
+BC_HD Dual rf_from_var(const Var<Tan<1>>& x) { return {x.v, x.d.d[0]}; }
+BC_HD Dual rf_from_var(const Var<Zero>& x) { return {x.v, 0.0}; }
+#else
+using real = double;
+BC_HD double rf_val(double x) { return x; }
+BC_HD double rf_out(double x) { return x; }
+BC_HD double rf_const(double x) { return x; }
+BC_HD double rf_sqrt(double x) { return ::sqrt(x); }
+BC_HD double rf_abs(double x) { return ::fabs(x); }
+BC_HD double rf_max(double a, double b) { return ::fmax(a, b); }
+BC_HD double rf_min(double a, double b) { return ::fmin(a, b); }
+BC_HD double rf_exp(double x) { return ::exp(x); }
+using RfDT = Zero;
+BC_HD PVar rf_to_var(double x) { return PVar{x, {}}; }
+BC_HD double rf_from_var(const PVar& x) { return x.v; }
+#endif
 
 constexpr int H = 3;
 #ifndef BCAST_RF_OJ
@@ -59,7 +120,7 @@ constexpr int NSM = WBUF + NSM_REST;          // doubles of shared memory per CT
 constexpr int NSM_TMA = 2 * WBUF + NSM_REST + 2;   // two w buffers + two mbarriers (109 520 bytes)
 static_assert(5 * NC <= WBUF, "w buffer");
 static_assert(5 * OJ * XI_P <= NXB, "exchange buffer");
-static_assert(OJ <= 32 && GW * OJ <= NT + 0 && 8 * (RI_W + 3) <= NT && 8 * RJ_W <= NT, "thread mappings");
+static_assert(OJ <= 32 && GW * OJ <= NT + 0 && (RI_W + 3) <= NT && RJ_W <= NT && 2 * OI <= NT, "thread mappings");
 static_assert(2 * GW * GH_ <= NXB, "scratch aliasing");
 static_assert(RJ_W * RJ_H <= RQ, "R buffer");
 
@@ -78,20 +139,32 @@ BC_HD double frcp(double x) {
 #endif
 }
 
+BC_HD real rf_rcp(real x) {
+#ifdef BCAST_RF_DUAL
+  const double r = frcp(x.v);
+  return {r, -r * r * x.d};
+#else
+  return frcp(x);
+#endif
+}
+
 struct TileCtx {
-  double* wsm;  // the five planes of w of the tile, [e][b][a]  (exactly the box a 3-D TMA load of w delivers)
-  double* sm;   // derived arrays, R buffer, exchange buffer
+  real* wsm;  // the five planes of w of the tile, [e][b][a]  (exactly the box a 3-D TMA load of w delivers)
+  real* sm;   // derived arrays, R buffer, exchange buffer
   const GridDesc& g;      // (references: in the kernels these are the kernel parameters, read from the constant bank)
   const SchemeConsts& c;
   double sqgr;  // sqrt(gam * rgaz)
   bool wall;
   const double *w, *nx, *ny, *vol, *volf;
+  const double* wd = nullptr;   // tangent build: the five planes of the direction at hand
   double* res;
   int i0, j0;  // first output cell of the tile
+  int i1 = 1 << 30, j1 = 1 << 30;   // last cell the tile may write (tangent build: the rows of a rectangle)
+  unsigned char* flags = nullptr;   // tangent build: per staged cell, 1 if any of its five tangents is non-zero (face skipping)
   BC_HD TileCtx(const GridDesc& g_, const SchemeConsts& c_) : g(g_), c(c_) {}
-  BC_HD double* arr(int a) const { return sm + a * NC; }
-  BC_HD double* RB() const { return sm + NARR * NC; }
-  BC_HD double* X() const { return sm + NARR * NC + NRB; }
+  BC_HD real* arr(int a) const { return sm + a * NC; }
+  BC_HD real* RB() const { return sm + NARR * NC; }
+  BC_HD real* X() const { return sm + NARR * NC + NRB; }
   // does the tile hold sensor cells of the first ghost layer of a physical boundary?
   BC_HD bool has_ghost_sensor() const {
     return (i0 == 1 && !(g.edges & 1)) || (i0 + OI >= g.im + 1 && !(g.edges & 2)) || j0 == 1 || j0 + OJ >= g.jm + 1;
@@ -100,28 +173,27 @@ struct TileCtx {
 
 // accessor over the shared arrays for the reference-shaped templates of scheme.cuh (wall rows, gradients)
 struct SmemAcc2 {
-  using DT = Zero;
-  const double* s;   // sm + shared index of the base cell
-  const double* sw;  // wsm + shared index of the base cell
+  using DT = RfDT;
+  const real* s;   // sm + shared index of the base cell
+  const real* sw;  // wsm + shared index of the base cell
   const double *nx, *ny, *vol, *volf;
   long long c, n;
   int ldc, ldn;
   long long sc, sn;
-  template <int OI_, int OJ_> BC_HD double raw(int a) const { return s[a * NC + OI_ + OJ_ * PI]; }
-  template <int OI_, int OJ_> BC_HD PVar ld(int a) const { return PVar{raw<OI_, OJ_>(a), {}}; }
-  template <int OI_, int OJ_> BC_HD double rawW(int e) const { return sw[e * NC + OI_ + OJ_ * PI]; }
-  template <int OI_, int OJ_> BC_HD PVar W(int e) const { return PVar{rawW<OI_, OJ_>(e), {}}; }
-  template <int OI_, int OJ_> BC_HD PVar U() const { return ld<OI_, OJ_>(A_U); }
-  template <int OI_, int OJ_> BC_HD PVar V() const { return ld<OI_, OJ_>(A_V); }
-  template <int OI_, int OJ_> BC_HD PVar Wz() const { return ld<OI_, OJ_>(A_WZ); }
-  template <int OI_, int OJ_> BC_HD PVar T() const { return ld<OI_, OJ_>(A_T); }
-  template <int OI_, int OJ_> BC_HD PVar P() const { return ld<OI_, OJ_>(A_P); }
-  template <int OI_, int OJ_> BC_HD PVar Mu() const { return ld<OI_, OJ_>(A_MU); }
-  template <int OI_, int OJ_> BC_HD PVar H() const {
-    return PVar{(rawW<OI_, OJ_>(4) + raw<OI_, OJ_>(A_P)) * (1.0 / rawW<OI_, OJ_>(0)), {}};
-  }
+  using VT = Var<RfDT>;
+  template <int OI_, int OJ_> BC_HD real raw(int a) const { return s[a * NC + OI_ + OJ_ * PI]; }
+  template <int OI_, int OJ_> BC_HD VT ld(int a) const { return rf_to_var(raw<OI_, OJ_>(a)); }
+  template <int OI_, int OJ_> BC_HD real rawW(int e) const { return sw[e * NC + OI_ + OJ_ * PI]; }
+  template <int OI_, int OJ_> BC_HD VT W(int e) const { return rf_to_var(rawW<OI_, OJ_>(e)); }
+  template <int OI_, int OJ_> BC_HD VT U() const { return ld<OI_, OJ_>(A_U); }
+  template <int OI_, int OJ_> BC_HD VT V() const { return ld<OI_, OJ_>(A_V); }
+  template <int OI_, int OJ_> BC_HD VT Wz() const { return ld<OI_, OJ_>(A_WZ); }
+  template <int OI_, int OJ_> BC_HD VT T() const { return ld<OI_, OJ_>(A_T); }
+  template <int OI_, int OJ_> BC_HD VT P() const { return ld<OI_, OJ_>(A_P); }
+  template <int OI_, int OJ_> BC_HD VT Mu() const { return ld<OI_, OJ_>(A_MU); }
+  template <int OI_, int OJ_> BC_HD VT H() const { return (W<OI_, OJ_>(4) + P<OI_, OJ_>()) * (1.0 / W<OI_, OJ_>(0)); }
   template <int OI_, int OJ_> BC_HD auto SENS() const {   // A_DV holds vol * divu
-    return CellSens<Zero, Zero>{PVar{raw<OI_, OJ_>(A_DV) / VOL<OI_, OJ_>(), {}}, ld<OI_, OJ_>(A_DU)};
+    return CellSens<RfDT, RfDT>{ld<OI_, OJ_>(A_DV) / VOL<OI_, OJ_>(), ld<OI_, OJ_>(A_DU)};
   }
   template <int OI_, int OJ_> BC_HD double NX(int kk) const { return BC_LDG(nx + kk * sn + n + OI_ + (long long)OJ_ * ldn); }
   template <int OI_, int OJ_> BC_HD double NY(int kk) const { return BC_LDG(ny + kk * sn + n + OI_ + (long long)OJ_ * ldn); }
@@ -146,15 +218,20 @@ template <bool STAGED>
 BC_HD void phase0(const TileCtx& t, int tid) {
   const GridDesc& g = t.g;
   constexpr int NIT = (NC + NT - 1) / NT;
-  double q[NIT][5];
+  real q[NIT][5];
   // all loads of the thread first (the only HBM reads of the kernel besides the metrics), then the arithmetic
 #pragma unroll
   for (int it = 0; it < NIT; ++it) {
     const int idx = tid + it * NT;
     const int a = idx % PI, b = idx / PI;
     const int gi = t.i0 - H + a, gj = t.j0 - H + b;
-    q[it][0] = 1.0; q[it][1] = 0.0; q[it][2] = 0.0; q[it][3] = 0.0; q[it][4] = 1.0;
+    q[it][0] = rf_const(1.0); q[it][1] = rf_const(0.0); q[it][2] = rf_const(0.0); q[it][3] = rf_const(0.0); q[it][4] = rf_const(1.0);
     if (idx < NC && gi <= g.im + g.gh && gj <= g.jm + g.gh) {   // cells beyond the padded array (TMA: zero fill) get a sane state
+#ifdef BCAST_RF_DUAL
+      const long long k = g.cidx(gi, gj);
+#pragma unroll
+      for (int e = 0; e < 5; ++e) q[it][e] = Dual{BC_LDG(t.w + e * g.sc + k), BC_LDG(t.wd + e * g.sc + k)};
+#else
       if constexpr (STAGED) {
 #pragma unroll
         for (int e = 0; e < 5; ++e) q[it][e] = t.wsm[e * NC + idx];
@@ -163,43 +240,47 @@ BC_HD void phase0(const TileCtx& t, int tid) {
 #pragma unroll
         for (int e = 0; e < 5; ++e) q[it][e] = BC_LDG(p + e * g.sc);
       }
+#endif
     }
   }
 #pragma unroll
   for (int it = 0; it < NIT; ++it) {
     const int idx = tid + it * NT;
     if (idx >= NC) break;
-    const double q0 = q[it][0], q1 = q[it][1], q2 = q[it][2], q3 = q[it][3], q4 = q[it][4];
-    const double rom1 = frcp(q0);
-    const double u = q1 * rom1, v = q2 * rom1, wz = q3 * rom1;
-    const double ec = 0.5 * (u * u + v * v + wz * wz);
-    const double eloc = (q4 - ec * q0) * rom1;
-    const double tl = eloc * t.c.cvm1;
-    const double p = t.c.gam1 * q0 * eloc;
-    const double sqt = ::sqrt(tl);
+    const real q0 = q[it][0], q1 = q[it][1], q2 = q[it][2], q3 = q[it][3], q4 = q[it][4];
+#ifdef BCAST_RF_DUAL
+    if (t.flags) t.flags[idx] = (q0.d != 0.0 || q1.d != 0.0 || q2.d != 0.0 || q3.d != 0.0 || q4.d != 0.0) ? 1 : 0;
+#endif
+    const real rom1 = rf_rcp(q0);
+    const real u = q1 * rom1, v = q2 * rom1, wz = q3 * rom1;
+    const real ec = 0.5 * (u * u + v * v + wz * wz);
+    const real eloc = (q4 - ec * q0) * rom1;
+    const real tl = eloc * t.c.cvm1;
+    const real p = t.c.gam1 * q0 * eloc;
+    const real sqt = rf_sqrt(tl);
     if constexpr (!STAGED) {
-      double* sw = t.wsm + idx;
+      real* sw = t.wsm + idx;
       sw[0] = q0; sw[NC] = q1; sw[2 * NC] = q2; sw[3 * NC] = q3; sw[4 * NC] = q4;
     }
-    double* s = t.sm + idx;
+    real* s = t.sm + idx;
     s[A_U * NC] = u;
     s[A_V * NC] = v;
     s[A_WZ * NC] = wz;
     s[A_T * NC] = tl;
     s[A_P * NC] = p;
-    s[A_MU * NC] = t.c.betas * frcp(tl + t.c.s_suth) * sqt * tl;
-    s[A_SR * NC] = ::sqrt(q0);
+    s[A_MU * NC] = t.c.betas * rf_rcp(tl + t.c.s_suth) * sqt * tl;
+    s[A_SR * NC] = rf_sqrt(q0);
     s[A_CS * NC] = t.sqgr * sqt;
   }
 }
 
 // ---- phase 1: sensor cells (dilatation, Ducros ratio) and the R_q of the i-faces ---------------------------------
-BC_HD double ducros_ratio(double divu, double vort) {
-  const double d2 = divu * divu;
-  return d2 * frcp(d2 + vort * vort + 1e-15);
+BC_HD real ducros_ratio(real divu, real vort) {
+  const real d2 = divu * divu;
+  return d2 * rf_rcp(d2 + vort * vort + 1e-15);
 }
 // R_q(face) = -q(-2) + 9 q(-1) + 9 q(0) - q(1) along the face normal (the 1/16 is applied by the consumer)
-BC_HD double rrow(const double* q, int stride) { return 9.0 * (q[-stride] + q[0]) - (q[-2 * stride] + q[stride]); }
+BC_HD real rrow(const real* q, int stride) { return 9.0 * (q[-stride] + q[0]) - (q[-2 * stride] + q[stride]); }
 
 // Sensor cells of a tile: rows j0 .. j0+OJ-1 over columns i0-1 .. i0+32 (34 OJ cells, one per thread) and the two rows
 // j0-1, j0+OJ over columns i0 .. i0+31 (64 cells, a second round of the last two warps); the corners are never read.
@@ -247,17 +328,17 @@ BC_HD void sensor_cell(const TileCtx& t, int tid, int round, const SensGeom& G) 
   int ga, gb;
   sensor_of(t, tid, round, ga, gb);
   const int k = (ga + H - 1) + (gb + H - 1) * PI;
-  const double* U = t.arr(A_U) + k;
-  const double* V = t.arr(A_V) + k;
+  const real* U = t.arr(A_U) + k;
+  const real* V = t.arr(A_V) + k;
   constexpr double b1 = 8.0 * (1.0 / 12.0), b2 = -(1.0 / 12.0);
-  const double gui = b1 * (U[1] - U[-1]) + b2 * (U[2] - U[-2]);
-  const double gvi = b1 * (V[1] - V[-1]) + b2 * (V[2] - V[-2]);
-  const double guj = b1 * (U[PI] - U[-PI]) + b2 * (U[2 * PI] - U[-2 * PI]);
-  const double gvj = b1 * (V[PI] - V[-PI]) + b2 * (V[2 * PI] - V[-2 * PI]);
-  const double gu0 = G.dxm1 * gui + G.dxm2 * guj, gv0 = G.dxm1 * gvi + G.dxm2 * gvj;
-  const double gu1 = G.dym1 * gui + G.dym2 * guj, gv1 = G.dym1 * gvi + G.dym2 * gvj;
-  const double divu = gu0 + gv1, vort = gv0 - gu1;
-  double* S0 = t.X();
+  const real gui = b1 * (U[1] - U[-1]) + b2 * (U[2] - U[-2]);
+  const real gvi = b1 * (V[1] - V[-1]) + b2 * (V[2] - V[-2]);
+  const real guj = b1 * (U[PI] - U[-PI]) + b2 * (U[2 * PI] - U[-2 * PI]);
+  const real gvj = b1 * (V[PI] - V[-PI]) + b2 * (V[2 * PI] - V[-2 * PI]);
+  const real gu0 = G.dxm1 * gui + G.dxm2 * guj, gv0 = G.dxm1 * gvi + G.dxm2 * gvj;
+  const real gu1 = G.dym1 * gui + G.dym2 * guj, gv1 = G.dym1 * gvi + G.dym2 * gvj;
+  const real divu = gu0 + gv1, vort = gv0 - gu1;
+  real* S0 = t.X();
   S0[ga + gb * GW] = divu;
   S0[GW * GH_ + ga + gb * GW] = vort;
   t.arr(A_DV)[k] = G.vol * divu;
@@ -267,16 +348,19 @@ BC_HD void sensor_cell(const TileCtx& t, int tid, int round, const SensGeom& G) 
 BC_HD void phase1(const TileCtx& t, int tid, const SensGeom& G0, const SensGeom& G1) {
   sensor_cell(t, tid, 0, G0);
   sensor_cell(t, tid, 1, G1);
-  // R_q of the i-faces: thread (fcol = tid % 36 < 33, grp = tid / 36 < 8) owns quantity grp/2 and one half of the face rows
-  const int fcol = tid % (RI_W + 3), grp = tid / (RI_W + 3);
-  if (fcol < RI_W && grp < 8) {
+  // R_q of the i-faces: eight tasks (quantity q, half of the face rows) spread over the NT / 36 thread groups of 36 (33 active)
+  const int fcol = tid % (RI_W + 3);
+  constexpr int NG = NT / (RI_W + 3) < 8 ? NT / (RI_W + 3) : 8;
+  if (fcol < RI_W) {
     constexpr int HALF = (RI_H + 1) / 2;
-    const int q = grp >> 1, frow0 = (grp & 1) * HALF, nrow = (grp & 1) ? RI_H - HALF : HALF;
-    const double* src = t.arr(A_U + q) + (fcol + H) + (frow0 + 1) * PI;  // face (i0 + fcol, j0 - 2 + frow0)
-    double* dst = t.RB() + q * RQ + frow0 * RI_W + fcol;
+    for (int grp = tid / (RI_W + 3); grp < 8; grp += NG) {
+      const int q = grp >> 1, frow0 = (grp & 1) * HALF, nrow = (grp & 1) ? RI_H - HALF : HALF;
+      const real* src = t.arr(A_U + q) + (fcol + H) + (frow0 + 1) * PI;  // face (i0 + fcol, j0 - 2 + frow0)
+      real* dst = t.RB() + q * RQ + frow0 * RI_W + fcol;
 #pragma unroll
-    for (int n = 0; n < HALF; ++n)
-      if (n < nrow) dst[n * RI_W] = rrow(src + n * PI, 1);
+      for (int n = 0; n < HALF; ++n)
+        if (n < nrow) dst[n * RI_W] = rrow(src + n * PI, 1);
+    }
   }
 }
 
@@ -284,8 +368,8 @@ BC_HD void phase1(const TileCtx& t, int tid, const SensGeom& G0, const SensGeom&
 // vorticity are linear in the gradients, so extrapolating them is extrapolating the gradients
 BC_HD void phase1b(const TileCtx& t, int tid) {
   const GridDesc& g = t.g;
-  const double* S0 = t.X();
-  const double* S1 = S0 + GW * GH_;
+  const real* S0 = t.X();
+  const real* S1 = S0 + GW * GH_;
   for (int idx = tid; idx < GW * GH_; idx += NT) {
     const int a = idx % GW + (H - 1), b = idx / GW + (H - 1);
     const int ci = t.i0 - H + a, cj = t.j0 - H + b;
@@ -298,8 +382,8 @@ BC_HD void phase1b(const TileCtx& t, int tid) {
       else if (cj == g.jm + 1) d = -GW;
     }
     if (d != 0) {
-      const double divu = 2.0 * S0[idx + d] - S0[idx + 2 * d];
-      const double vort = 2.0 * S1[idx + d] - S1[idx + 2 * d];
+      const real divu = 2.0 * S0[idx + d] - S0[idx + 2 * d];
+      const real vort = 2.0 * S1[idx + d] - S1[idx + 2 * d];
       const int k = a + b * PI;
       t.arr(A_DV)[k] = BC_LDG(t.vol + g.cidx(ci, cj)) * divu;
       t.arr(A_DU)[k] = ducros_ratio(divu, vort);
@@ -310,19 +394,22 @@ BC_HD void phase1b(const TileCtx& t, int tid) {
 // R_q of the j-faces (columns i0-2 .. i0+33, rows j0 .. j0+8): thread (fcol = tid % 36, grp = tid / 36) owns quantity grp/2
 // and five (even grp) or four (odd grp) consecutive face rows, sliding along j
 BC_HD void phase_rj(const TileCtx& t, int tid) {
-  const int fcol = tid % RJ_W, grp = tid / RJ_W;
-  if (grp >= 8) return;
+  const int fcol = tid % RJ_W;
+  constexpr int NG = NT / RJ_W < 8 ? NT / RJ_W : 8;
   constexpr int HALF = (RJ_H + 1) / 2;
-  const int q = grp >> 1, frow0 = (grp & 1) * HALF, nrow = (grp & 1) ? RJ_H - HALF : HALF;
-  const double* src = t.arr(A_U + q) + (fcol + 1) + (frow0 + H) * PI;  // face (i0 - 2 + fcol, j0 + frow0)
-  double* dst = t.RB() + q * RQ + frow0 * RJ_W + fcol;
-  double m2 = src[-2 * PI], m1 = src[-PI], c0 = src[0];
+  if (tid / RJ_W >= NG) return;
+  for (int grp = tid / RJ_W; grp < 8; grp += NG) {
+    const int q = grp >> 1, frow0 = (grp & 1) * HALF, nrow = (grp & 1) ? RJ_H - HALF : HALF;
+    const real* src = t.arr(A_U + q) + (fcol + 1) + (frow0 + H) * PI;  // face (i0 - 2 + fcol, j0 + frow0)
+    real* dst = t.RB() + q * RQ + frow0 * RJ_W + fcol;
+    real m2 = src[-2 * PI], m1 = src[-PI], c0 = src[0];
 #pragma unroll
-  for (int n = 0; n < HALF; ++n) {
-    if (n < nrow) {
-      const double p1 = src[(n + 1) * PI];
-      dst[n * RJ_W] = 9.0 * (m1 + c0) - (m2 + p1);
-      m2 = m1; m1 = c0; c0 = p1;
+    for (int n = 0; n < HALF; ++n) {
+      if (n < nrow) {
+        const real p1 = src[(n + 1) * PI];
+        dst[n * RJ_W] = 9.0 * (m1 + c0) - (m2 + p1);
+        m2 = m1; m1 = c0; c0 = p1;
+      }
     }
   }
 }
@@ -365,7 +452,7 @@ BC_HD FaceGeom load_geom(const TileCtx& t, int fi, int fj) {
 // s / sw: shared pointers of the face cell in the derived arrays / the w planes; rb: R buffer entry of this face for q = 0 (quantity stride RQ, cross
 // stride RC)
 template <int DIR>
-BC_HD void face_fast(const TileCtx& t, const double* s, const double* sw, const double* rb, const FaceGeom& G, double (&hn)[5]) {
+BC_HD void face_fast(const TileCtx& t, const real* s, const real* sw, const real* rb, const FaceGeom& G, real (&hn)[5]) {
   constexpr int SA = DIR == 0 ? 1 : PI;
   constexpr int RC = DIR == 0 ? RI_W : 1;
   const SchemeConsts& cs = t.c;
@@ -378,76 +465,80 @@ BC_HD void face_fast(const TileCtx& t, const double* s, const double* sw, const 
   // (order of the blocks chosen for register pressure: the viscous part first, its dual normals and gradients die before
   //  the convective accumulators become live)
   // ---- viscous flux, compact 4th order (flux_visqueux_o4_{i,j}.F) -------------------------------------------------
-  double gx[4], gy[4], fv[4];  // gradients and face values of u, v, w, T
+  real gx[4], gy[4], fv[4];  // gradients and face values of u, v, w, T
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const double q1 = RF_LD(A_U + q, 1), q0 = RF_LD(A_U + q, 0), qm1 = RF_LD(A_U + q, -1), qm2 = RF_LD(A_U + q, -2);
-    const double Ap = 26.0 * q0 - (q1 + qm1), Am = 26.0 * qm1 - (q0 + qm2);
-    const double* r = rb + q * RQ;
-    const double rm2 = r[-2 * RC], rm1 = r[-RC], r0 = r[0], r1 = r[RC], r2 = r[2 * RC];
-    const double Cm = 7.0 * (rm1 + r0) - (rm2 + r1), Cp = 7.0 * (r0 + r1) - (rm1 + r2);
+    const real q1 = RF_LD(A_U + q, 1), q0 = RF_LD(A_U + q, 0), qm1 = RF_LD(A_U + q, -1), qm2 = RF_LD(A_U + q, -2);
+    const real Ap = 26.0 * q0 - (q1 + qm1), Am = 26.0 * qm1 - (q0 + qm2);
+    const real* r = rb + q * RQ;
+    const real rm2 = r[-2 * RC], rm1 = r[-RC], r0 = r[0], r1 = r[RC], r2 = r[2 * RC];
+    const real Cm = 7.0 * (rm1 + r0) - (rm2 + r1), Cp = 7.0 * (r0 + r1) - (rm1 + r2);
     gx[q] = Ap * nApx + Am * nAmx + Cp * nCpx + Cm * nCmx;
     gy[q] = Ap * nApy + Am * nAmy + Cp * nCpy + Cm * nCmy;
     fv[q] = 0.0625 * r0;
   }
-  const double mmu = 0.0625 * (9.0 * (RF_LD(A_MU, -1) + RF_LD(A_MU, 0)) - (RF_LD(A_MU, -2) + RF_LD(A_MU, 1)));
+  const real mmu = 0.0625 * (9.0 * (RF_LD(A_MU, -1) + RF_LD(A_MU, 0)) - (RF_LD(A_MU, -2) + RF_LD(A_MU, 1)));
   constexpr double TWOTHIRD = 2.0 / 3.0;
-  const double lambda = mmu * cs.cpprandtl;
-  const double fvrou = TWOTHIRD * mmu * (2.0 * gx[0] - gy[1]);
-  const double fvrov = mmu * (gy[0] + gx[1]);
-  const double fvrow = mmu * gx[2];
-  const double gvrov = TWOTHIRD * mmu * (2.0 * gy[1] - gx[0]);
-  const double gvrow = mmu * gy[2];
-  const double fvroe = lambda * gx[3] + fv[0] * fvrou + fv[1] * fvrov + fv[2] * fvrow;
-  const double gvroe = lambda * gy[3] + fv[0] * fvrov + fv[1] * gvrov + fv[2] * gvrow;
-  const double visc[5] = {0.0, fvrou * nxf + fvrov * nyf, fvrov * nxf + gvrov * nyf, fvrow * nxf + gvrow * nyf, fvroe * nxf + gvroe * nyf};
+  const real lambda = mmu * cs.cpprandtl;
+  const real fvrou = TWOTHIRD * mmu * (2.0 * gx[0] - gy[1]);
+  const real fvrov = mmu * (gy[0] + gx[1]);
+  const real fvrow = mmu * gx[2];
+  const real gvrov = TWOTHIRD * mmu * (2.0 * gy[1] - gx[0]);
+  const real gvrow = mmu * gy[2];
+  const real fvroe = lambda * gx[3] + fv[0] * fvrou + fv[1] * fvrov + fv[2] * fvrow;
+  const real gvroe = lambda * gy[3] + fv[0] * fvrov + fv[1] * gvrov + fv[2] * gvrow;
+  const real visc[5] = {rf_const(0.0), fvrou * nxf + fvrov * nyf, fvrov * nxf + gvrov * nyf, fvrow * nxf + gvrow * nyf,
+                        fvroe * nxf + gvroe * nyf};
 
   // ---- Roe spectral radius (spectralradius_{i,j}.F) ---------------------------------------------------------------
   const double nx2 = nxf * nxf + nyf * nyf;
-  double rspec;
+  real rspec;
   {
-    const double sr = RF_LD(A_SR, 0), sl = RF_LD(A_SR, -1);
-    const double inv = frcp(sl + sr);
-    const double rr = sl * inv, omrr = sr * inv;  // 1/(1+sqrt(rho_r/rho_l)) and its complement
-    const double u = RF_LD(A_U, -1) * rr + RF_LD(A_U, 0) * omrr;
-    const double v = RF_LD(A_V, -1) * rr + RF_LD(A_V, 0) * omrr;
-    const double c2x = (cs.gam * cs.rgaz) * (RF_LD(A_T, -1) * rr + RF_LD(A_T, 0) * omrr);
-    rspec = ::fabs(nxf * u + nyf * v) + ::sqrt(c2x * nx2);
+    const real sr = RF_LD(A_SR, 0), sl = RF_LD(A_SR, -1);
+    const real inv = rf_rcp(sl + sr);
+    const real rr = sl * inv, omrr = sr * inv;  // 1/(1+sqrt(rho_r/rho_l)) and its complement
+    const real u = RF_LD(A_U, -1) * rr + RF_LD(A_U, 0) * omrr;
+    const real v = RF_LD(A_V, -1) * rr + RF_LD(A_V, 0) * omrr;
+    const real c2x = (cs.gam * cs.rgaz) * (RF_LD(A_T, -1) * rr + RF_LD(A_T, 0) * omrr);
+    rspec = rf_abs(nxf * u + nyf * v) + rf_sqrt(c2x * nx2);
   }
 
   // ---- Jameson x Ducros x dilatation sensor (ducrosfordnc_{i,j}.F) -------------------------------------------------
-  double eps2 = 0.0;
+  real eps2 = rf_const(0.0);
   if (cs.k2 != 0.0) {
-    const double pm2 = RF_LD(A_P, -2), pm1 = RF_LD(A_P, -1), p0 = RF_LD(A_P, 0), pp1 = RF_LD(A_P, 1);
-    const double a1_ = ::fabs(pm1 - 2.0 * p0 + pp1), b1_ = ::fabs(pm1 + 2.0 * p0 + pp1);
-    const double a2_ = ::fabs(pm2 - 2.0 * pm1 + p0), b2_ = ::fabs(pm2 + 2.0 * pm1 + p0);
-    const bool second = a1_ * b2_ < a2_ * b1_;  // k1 < k2: max() takes the second operand
-    const double ks = (second ? a2_ : a1_) * frcp(second ? b2_ : b1_);
-    const double duc = ::fmax(RF_LD(A_DU, 0), RF_LD(A_DU, -1));
+    const real pm2 = RF_LD(A_P, -2), pm1 = RF_LD(A_P, -1), p0 = RF_LD(A_P, 0), pp1 = RF_LD(A_P, 1);
+    const real a1_ = rf_abs(pm1 - 2.0 * p0 + pp1), b1_ = rf_abs(pm1 + 2.0 * p0 + pp1);
+    const real a2_ = rf_abs(pm2 - 2.0 * pm1 + p0), b2_ = rf_abs(pm2 + 2.0 * pm1 + p0);
+    const bool second = rf_val(a1_) * rf_val(b2_) < rf_val(a2_) * rf_val(b1_);  // k1 < k2: max() takes the second operand
+    const real ks = (second ? a2_ : a1_) * rf_rcp(second ? b2_ : b1_);
+    const real duc = rf_max(RF_LD(A_DU, 0), RF_LD(A_DU, -1));
     const double sn = ::sqrt(nx2);
-    const double t0 = RF_LD(A_DV, 0), t1 = RF_LD(A_DV, -1);
-    const double d0 = RF_LD(A_CS, 0) * sn + 1e-15, d1 = RF_LD(A_CS, -1) * sn + 1e-15;
-    const bool take1 = t0 * d1 > t1 * d0;  // x0 > x1: the dilatation switch is decreasing, max() is at the smaller argument
-    const double xs = 2.5 + 10.0 * (take1 ? t1 : t0) * frcp(take1 ? d1 : d0);
-    const double dxm = frcp(1.0 + ::exp(::fmin(2.0 * xs, 700.0)));  // (1 - tanh x) / 2
+    const real t0 = RF_LD(A_DV, 0), t1 = RF_LD(A_DV, -1);
+    const real d0 = RF_LD(A_CS, 0) * sn + 1e-15, d1 = RF_LD(A_CS, -1) * sn + 1e-15;
+    // x0 > x1: the dilatation switch is decreasing, max() is at the smaller argument
+    const bool take1 = rf_val(t0) * rf_val(d1) > rf_val(t1) * rf_val(d0);
+    const real xs = 2.5 + 10.0 * (take1 ? t1 : t0) * rf_rcp(take1 ? d1 : d0);
+    const real dxm = rf_rcp(1.0 + rf_exp(rf_min(2.0 * xs, 700.0)));  // (1 - tanh x) / 2
     eps2 = cs.k2 * (ks * duc * dxm);
   }
-  const double eps4 = ::fmax(0.0, cs.k4 - eps2 * 12.0);
+  const real eps4 = rf_max(0.0, cs.k4 - eps2 * 12.0);
 
   // ---- convective flux + 5th-difference operand: one pass over cells -3 .. 2 -----------------------------------
   constexpr double denom = 1.0 / 60.0;
   constexpr double ck[6] = {denom, -8.0 * denom, 37.0 * denom, 37.0 * denom, -8.0 * denom, denom};
   constexpr double dk[6] = {-denom, 5.0 * denom, -10.0 * denom, 10.0 * denom, -5.0 * denom, denom};
-  double fx[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, pr[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  double pbar = 0.0;
+  real fx[5], pr[5];
+#pragma unroll
+  for (int e = 0; e < 5; ++e) fx[e] = pr[e] = rf_const(0.0);
+  real pbar = rf_const(0.0);
 #pragma unroll
   for (int k = -3; k <= 2; ++k) {
-    const double u = RF_LD(A_U, k), v = RF_LD(A_V, k), p = RF_LD(A_P, k);
-    const double cv = ck[k + 3] * (u * nxf + v * nyf);
+    const real u = RF_LD(A_U, k), v = RF_LD(A_V, k), p = RF_LD(A_P, k);
+    const real cv = ck[k + 3] * (u * nxf + v * nyf);
     pbar += ck[k + 3] * p;
 #pragma unroll
     for (int e = 0; e < 5; ++e) {
-      const double we = RF_LW(e, k);
+      const real we = RF_LW(e, k);
       fx[e] += cv * (e == 4 ? we + p : we);
       pr[e] += dk[k + 3] * we;
     }
@@ -456,10 +547,10 @@ BC_HD void face_fast(const TileCtx& t, const double* s, const double* sw, const 
   fx[2] += pbar * nyf;
 
   // ---- assembly (dissipation_ducros_{i,j}.F, fluxnumassembly_{i,j}.F) ----------------------------------------------
-  const double e2h = 0.5 * eps2;
+  const real e2h = 0.5 * eps2;
 #pragma unroll
   for (int e = 0; e < 5; ++e) {
-    const double diff = RF_LW(e, 0) - RF_LW(e, -1);
+    const real diff = RF_LW(e, 0) - RF_LW(e, -1);
     hn[e] = fx[e] - rspec * (e2h * diff + eps4 * pr[e]) - visc[e];
   }
 #undef RF_LD
@@ -503,20 +594,44 @@ BC_HD FaceGeom prefetch_jface(const TileCtx& t, int tid) {
   return FaceGeom{};
 }
 
+// tangent build: does any cell of the face's stencil carry a tangent?  (along -3 .. 2 on its own row -- up to +3 for the
+// off-centred wall flux of face j = 2 --, along -2 .. 1 on the cross rows +-1, +-2; the tangents of the two sensor cells cover
+// the extrapolated gradients of the first ghost layer)
+template <int DIR>
+BC_HD bool face_has_tangent(const TileCtx& t, int a, int b, int hi) {
+#ifdef BCAST_RF_DUAL
+  if (!t.flags) return true;
+  constexpr int SA = DIR == 0 ? 1 : PI, SC = DIR == 0 ? PI : 1;
+  const unsigned char* f = t.flags + a + b * PI;
+  bool act = false;
+  for (int s_ = -3; s_ <= hi; ++s_) act = act || f[s_ * SA] != 0;
+  for (int t_ = -2; t_ <= 2; ++t_)
+    for (int s_ = -2; s_ <= 1; ++s_) act = act || f[s_ * SA + t_ * SC] != 0;
+  const int k = a + b * PI;
+  act = act || t.arr(A_DV)[k].d != 0.0 || t.arr(A_DU)[k].d != 0.0 || t.arr(A_DV)[k - SA].d != 0.0 || t.arr(A_DU)[k - SA].d != 0.0;
+  return act;
+#else
+  return true;
+#endif
+}
+
 BC_HD void phase2(const TileCtx& t, int tid, const FaceGeom& G) {
   const FaceId f = iface_of(t, tid);
   if (!f.active) return;
-  double hn[5];
+  real hn[5];
   const int a = f.col + H, b = f.row + H;
-  if (f.generic) {
-    PVar h[5];
+  if (!face_has_tangent<0>(t, a, b, 2)) {
+#pragma unroll
+    for (int e = 0; e < 5; ++e) hn[e] = rf_const(0.0);
+  } else if (f.generic) {
+    Var<RfDT> h[5];
     face_flux<0, true, FACE_MAIN>(make_acc(t, a, b), t.c, h);
 #pragma unroll
-    for (int e = 0; e < 5; ++e) hn[e] = h[e].v;
+    for (int e = 0; e < 5; ++e) hn[e] = rf_from_var(h[e]);
   } else {
     face_fast<0>(t, t.sm + a + b * PI, t.wsm + a + b * PI, t.RB() + (f.row + 2) * RI_W + f.col, G, hn);
   }
-  double* X = t.X();
+  real* X = t.X();
 #pragma unroll
   for (int e = 0; e < 5; ++e) X[(e * OJ + f.row) * XI_P + f.col] = hn[e];
 }
@@ -525,41 +640,47 @@ BC_HD void phase2(const TileCtx& t, int tid, const FaceGeom& G) {
 BC_HD void phase3(const TileCtx& t, int tid, const FaceGeom& G) {
   const FaceId f = jface_of(t, tid);
   if (!f.active) return;
-  double hn[5];
+  real hn[5];
   const int a = f.col + H, b = f.row + H;
-  if (f.generic) {
-    PVar h[5];
+  if (!face_has_tangent<1>(t, a, b, (t.wall && f.fj == 2) ? 3 : 2)) {
+#pragma unroll
+    for (int e = 0; e < 5; ++e) hn[e] = rf_const(0.0);
+  } else if (f.generic) {
+    Var<RfDT> h[5];
     const SmemAcc2 A = make_acc(t, a, b);
     if (f.fj == 1) face_flux<1, true, FACE_WALL>(A, t.c, h);
     else if (f.fj == 2) face_flux<1, true, FACE_NEAR3>(A, t.c, h);
     else face_flux<1, false, FACE_NEAR5>(A, t.c, h);
 #pragma unroll
-    for (int e = 0; e < 5; ++e) hn[e] = h[e].v;
+    for (int e = 0; e < 5; ++e) hn[e] = rf_from_var(h[e]);
   } else {
     face_fast<1>(t, t.sm + a + b * PI, t.wsm + a + b * PI, t.RB() + f.row * RJ_W + f.col + 2, G, hn);
   }
-  double* X = t.X();
+  real* X = t.X();
 #pragma unroll
   for (int e = 0; e < 5; ++e) X[(e * (OJ + 1) + f.row) * XJ_P + f.col] = hn[e];
 }
 
 // ---- balance (rhs/balance.F:2-15) ------------------------------------------------------------------------------------
-BC_HD bool owns_cell(const TileCtx& t, int tid) { return tid < OI * OJ && t.i0 + tid % OI <= t.g.im && t.j0 + tid / OI <= t.g.jm; }
-BC_HD void balance_i(const TileCtx& t, int tid, double (&r)[5]) {
+BC_HD bool owns_cell(const TileCtx& t, int tid) {
+  const int i = t.i0 + tid % OI, j = t.j0 + tid / OI;
+  return tid < OI * OJ && i <= t.g.im && j <= t.g.jm && i <= t.i1 && j <= t.j1;
+}
+BC_HD void balance_i(const TileCtx& t, int tid, real (&r)[5]) {
   if (!owns_cell(t, tid)) return;
   const int cx = tid % OI, cy = tid / OI;
-  const double* X = t.X();
+  const real* X = t.X();
 #pragma unroll
   for (int e = 0; e < 5; ++e) r[e] = -(X[(e * OJ + cy) * XI_P + cx + 1] - X[(e * OJ + cy) * XI_P + cx]);
 }
-BC_HD void balance_j_store(const TileCtx& t, int tid, const double (&r)[5]) {
+BC_HD void balance_j_store(const TileCtx& t, int tid, const real (&r)[5]) {
   if (!owns_cell(t, tid)) return;
   const int cx = tid % OI, cy = tid / OI;
-  const double* X = t.X();
+  const real* X = t.X();
   const long long k = t.g.cidx(t.i0 + cx, t.j0 + cy);
 #pragma unroll
   for (int e = 0; e < 5; ++e)
-    t.res[e * t.g.sc + k] = r[e] - (X[(e * (OJ + 1) + cy + 1) * XJ_P + cx] - X[(e * (OJ + 1) + cy) * XJ_P + cx]);
+    t.res[e * t.g.sc + k] = rf_out(r[e] - (X[(e * (OJ + 1) + cy + 1) * XJ_P + cx] - X[(e * (OJ + 1) + cy) * XJ_P + cx]));
 }
 
 }  // namespace BCAST_RF_NS
