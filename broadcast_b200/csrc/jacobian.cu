@@ -41,6 +41,29 @@ static cudaError_t apply_bc_list(const GridDesc& g, double gam, int ndir, double
   return cudaSuccess;
 }
 
+// Linearised boundary fills a colour (l,k) can skip: the tangent a fill writes into the ghosts of a boundary line depends on wd
+// of the first three interior cells of the SAME line only (bc.cuh: wall mirror / pressure extrapolation, o2 extrapolation,
+// characteristic updates from the first interior cell and the ghosts already written), and the seeds of a colour sit on the rows
+// j = k+1 (mod 7), columns i = l+1 (mod 7): a side whose three first interior rows (columns) hold no seed row (column) of this
+// colour receives zero tangents, which is what the seeding kernel has already written there.  Joins are always applied.
+static int active_bcs(const GridDesc& g, const bc_desc_t* bcs, int nbcs, int l, int k, bc_desc_t* out) {
+  const int s = 2 * g.gh + 1;
+  auto near_lo = [&](int c) { return c <= g.gh - 1; };                                   // a seed line among lines 1 .. gh
+  auto near_hi = [&](int c, int n) { return n >= c + 1 && (n - (c + 1)) % s <= g.gh - 1; };   // ... among n-gh+1 .. n
+  int m = 0;
+  for (int b = 0; b < nbcs; ++b) {
+    const bc_desc_t& d = bcs[b];
+    bool keep = true;
+    if (d.kind != BC_KIND_JOIN) {
+      const bool lo = d.loc[1] == 'l' || d.loc[1] == 'L';
+      if (d.loc[0] == 'I' || d.loc[0] == 'i') keep = lo ? near_lo(l) : near_hi(l, g.img);
+      else keep = lo ? near_lo(k) : near_hi(k, g.jm);
+    }
+    if (keep) out[m++] = d;
+  }
+  return m;
+}
+
 // scatter of the five directions of colour (l,k): same integer rules as k_scatter, writing straight
 // into the reference's slot order for m = 0..4
 __global__ void k_scatter5(GridDesc g, int kind, double* __restrict__ jac, int* __restrict__ ia, int* __restrict__ ja,
@@ -151,7 +174,10 @@ extern "C" int bcd_jacobian_coo(double* jac, int32_t* ia, int32_t* ja, double* w
       if (!current_colours().has(l * s + k)) continue;   // colour sharding: this rank's passes only
       cudaError_t e = launch_testvector(g, wd5, 5, 0, l, k, nullptr, st, seed_rows);
       if (e != cudaSuccess) return (int)e;
-      e = apply_bc_list(g, gam, 5, w, wd5, nx, ny, bcs, nbcs, st);
+      static const bool skip_bcs = getenv("BROADCAST_B200_NO_BC_SKIP") == nullptr;
+      bc_desc_t act[16];
+      const int nact = (skip_bcs && nbcs <= 16) ? active_bcs(g, bcs, nbcs, l, k, act) : -1;
+      e = nact >= 0 ? apply_bc_list(g, gam, 5, w, wd5, nx, ny, act, nact, st) : apply_bc_list(g, gam, 5, w, wd5, nx, ny, bcs, nbcs, st);
       if (e != cudaSuccess) return (int)e;
       // tangent of the rows of rc, five directions: one face per thread, every face once, faces without a tangent input skipped
       // (k_strip_faces5 over bands of three rows); BROADCAST_B200_COO_GENERIC=1: the cell-centred k_balance<5>
@@ -234,6 +260,7 @@ extern "C" int bcd_jacobian_strips(int nrect, const int32_t* rects /* [nrect][4]
   bool has_join = false;
   for (int b = 0; b < nbcs; ++b) has_join = has_join || bcs[b].kind == BC_KIND_JOIN;
   int nlaunch = 0;
+  static const bool skip_bcs = getenv("BROADCAST_B200_NO_BC_SKIP") == nullptr;
   // the 49 passes (~26 small launches each): launch-latency bound on the reference's own grids (500 x 150: 206 us per pass)
   auto run = [&](cudaStream_t s_) -> cudaError_t {
     for (int l = 0; l < s; ++l)
@@ -241,7 +268,9 @@ extern "C" int bcd_jacobian_strips(int nrect, const int32_t* rects /* [nrect][4]
         if (!current_colours().has(l * s + k)) continue;   // colour sharding: this rank's passes only
         cudaError_t e = launch_testvector(g, wd5, 5, 0, l, k, nullptr, s_, has_join ? nullptr : &rows);
         if (e != cudaSuccess) return e;
-        e = apply_bc_list(g, gam, 5, w, wd5, nx, ny, bcs, nbcs, s_);
+        bc_desc_t act[16];
+        const int nact = (skip_bcs && nbcs <= 16) ? active_bcs(g, bcs, nbcs, l, k, act) : -1;
+        e = nact >= 0 ? apply_bc_list(g, gam, 5, w, wd5, nx, ny, act, nact, s_) : apply_bc_list(g, gam, 5, w, wd5, nx, ny, bcs, nbcs, s_);
         if (e != cudaSuccess) return e;
         e = launch_tangent_strips5(g, a, wall != 0, rows, resd5, w, wd5, nx, ny, vol, volf, s_);
         if (e != cudaSuccess) return e;
