@@ -249,9 +249,27 @@ extern "C" int bcd_jacobian_strips(int nrect, const int32_t* rects /* [nrect][4]
   const GridDesc g = make_grid_ctx(im, jm, gh);
   const SchemeArgs a{cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4};
   const int s = 2 * gh + 1;
-  double* wd5 = scratch_doubles(20, (size_t)g.sc * 25);
-  double* resd5 = scratch_doubles(21, (size_t)g.sc * 25);
-  if (!wd5 || !resd5) return BC_ERR_ALLOC;
+  // colour chains: up to four colours of the loop run at a time inside the graph (each chain has its own wd / tangent / primitive
+  // scratch and side streams): on the reference's own grid sizes a pass is a chain of ~10 dependent small kernels, latency bound
+  static const int chains_env = getenv("BROADCAST_B200_STRIP_CHAINS") ? atoi(getenv("BROADCAST_B200_STRIP_CHAINS")) : 0;
+  static const bool no_graph = getenv("BROADCAST_B200_NO_GRAPH") != nullptr;
+  int K = chains_env > 0 ? chains_env : ((long long)im * jm <= 2200000LL ? 4 : 1);
+  if (K > 4) K = 4;
+  if (no_graph) K = 1;
+  double* wd5c[4] = {nullptr, nullptr, nullptr, nullptr};
+  double* resd5c[4] = {nullptr, nullptr, nullptr, nullptr};
+  double* sc_[4][4];
+  for (int c = 0; c < K; ++c) {   // every scratch slot the loop touches must exist before capture (allocation is not capturable)
+    scratch_chain() = c;
+    wd5c[c] = scratch_doubles(20, (size_t)g.sc * 25);
+    resd5c[c] = scratch_doubles(21, (size_t)g.sc * 25);
+    sc_[c][0] = scratch_doubles(0, (size_t)g.sc * NPRIM);
+    sc_[c][1] = scratch_doubles(1, (size_t)g.sc * NGRAD);
+    sc_[c][2] = scratch_doubles(2, (size_t)g.sc * NPRIM * 5);
+    sc_[c][3] = scratch_doubles(3, (size_t)g.sc * NGRAD * 5);
+    scratch_chain() = 0;
+    if (!wd5c[c] || !resd5c[c] || !sc_[c][0] || !sc_[c][1] || !sc_[c][2] || !sc_[c][3]) return BC_ERR_ALLOC;
+  }
   RectList rows;
   rows.n = nrect;
   for (int q = 0; q < 4; ++q) rows.r[q] = q < nrect ? Rect{rects[4 * q], rects[4 * q + 1], rects[4 * q + 2], rects[4 * q + 3]} : Rect{1, 0, 1, 0};
@@ -261,43 +279,69 @@ extern "C" int bcd_jacobian_strips(int nrect, const int32_t* rects /* [nrect][4]
   for (int b = 0; b < nbcs; ++b) has_join = has_join || bcs[b].kind == BC_KIND_JOIN;
   int nlaunch = 0;
   static const bool skip_bcs = getenv("BROADCAST_B200_NO_BC_SKIP") == nullptr;
-  // the 49 passes (~26 small launches each): launch-latency bound on the reference's own grids (500 x 150: 206 us per pass)
-  auto run = [&](cudaStream_t s_) -> cudaError_t {
-    for (int l = 0; l < s; ++l)
-      for (int k = 0; k < s; ++k) {
+  // one pass = one colour (l,k) on stream s_, with the buffers of chain c
+  auto pass = [&](int l, int k, int c, cudaStream_t s_) -> cudaError_t {
+    double* wd5 = wd5c[c];
+    double* resd5 = resd5c[c];
+    scratch_chain() = c;
+    cudaError_t e = launch_testvector(g, wd5, 5, 0, l, k, nullptr, s_, has_join ? nullptr : &rows);
+    if (e == cudaSuccess) {
+      bc_desc_t act[16];
+      const int nact = (skip_bcs && nbcs <= 16) ? active_bcs(g, bcs, nbcs, l, k, act) : -1;
+      e = nact >= 0 ? apply_bc_list(g, gam, 5, w, wd5, nx, ny, act, nact, s_) : apply_bc_list(g, gam, 5, w, wd5, nx, ny, bcs, nbcs, s_);
+    }
+    if (e == cudaSuccess) e = launch_tangent_strips5(g, a, wall != 0, rows, resd5, w, wd5, nx, ny, vol, volf, s_);
+    if (e == cudaSuccess) {
+      for_each_rect(rows, s_, [&](const RectList& r1, int q, cudaStream_t s1) {
+        const Rect rc = r1.r[0];
+        const long long nt = 5LL * (rc.i1 - rc.i0 + 1) * (rc.j1 - rc.j0 + 1);
+        k_scatter5<<<(unsigned)((nt + 255) / 256), 256, 0, s1>>>(g, scatter_kind, jac[q], ia[q], ja[q], resd5, l, k, coefdiag, vol, rc, 1);
+      });
+      e = cudaGetLastError();
+    }
+    scratch_chain() = 0;
+    nlaunch += 6 + nrect;
+    return e;
+  };
+  // the 49 passes on one stream (K = 1) or dealt round-robin to K chain streams forked from s_ and joined at the end
+  auto run = [&](cudaStream_t s_, cudaStream_t* cs, cudaEvent_t fork, cudaEvent_t* join) -> cudaError_t {
+    if (K > 1) {
+      cudaEventRecord(fork, s_);
+      for (int c = 0; c < K; ++c) cudaStreamWaitEvent(cs[c], fork, 0);
+    }
+    int n = 0;
+    cudaError_t err = cudaSuccess;
+    for (int l = 0; l < s && err == cudaSuccess; ++l)
+      for (int k = 0; k < s && err == cudaSuccess; ++k) {
         if (!current_colours().has(l * s + k)) continue;   // colour sharding: this rank's passes only
-        cudaError_t e = launch_testvector(g, wd5, 5, 0, l, k, nullptr, s_, has_join ? nullptr : &rows);
-        if (e != cudaSuccess) return e;
-        bc_desc_t act[16];
-        const int nact = (skip_bcs && nbcs <= 16) ? active_bcs(g, bcs, nbcs, l, k, act) : -1;
-        e = nact >= 0 ? apply_bc_list(g, gam, 5, w, wd5, nx, ny, act, nact, s_) : apply_bc_list(g, gam, 5, w, wd5, nx, ny, bcs, nbcs, s_);
-        if (e != cudaSuccess) return e;
-        e = launch_tangent_strips5(g, a, wall != 0, rows, resd5, w, wd5, nx, ny, vol, volf, s_);
-        if (e != cudaSuccess) return e;
-        for_each_rect(rows, s_, [&](const RectList& r1, int q, cudaStream_t s1) {
-          const Rect rc = r1.r[0];
-          const long long nt = 5LL * (rc.i1 - rc.i0 + 1) * (rc.j1 - rc.j0 + 1);
-          k_scatter5<<<(unsigned)((nt + 255) / 256), 256, 0, s1>>>(g, scatter_kind, jac[q], ia[q], ja[q], resd5, l, k, coefdiag, vol, rc, 1);
-        });
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        nlaunch += 6 + nrect;
+        const int c = K > 1 ? n % K : 0;
+        err = pass(l, k, c, K > 1 ? cs[c] : s_);
+        ++n;
       }
-    return cudaSuccess;
+    if (K > 1)
+      for (int c = 0; c < K; ++c) {
+        cudaEventRecord(join[c], cs[c]);
+        cudaStreamWaitEvent(s_, join[c], 0);
+      }
+    return err;
   };
   // CUDA graph of the whole loop, cached on everything a launch depends on (pointers, sizes, scalars, slab and colour context,
   // scratch arena addresses).  BROADCAST_B200_NO_GRAPH=1 launches kernel by kernel.
-  static const bool no_graph = getenv("BROADCAST_B200_NO_GRAPH") != nullptr;
   if (no_graph) {
-    cudaError_t e = run(st);
+    cudaError_t e = run(st, nullptr, nullptr, nullptr);
     count_launches(nlaunch);
     return e == cudaSuccess ? BC_OK : (int)e;
   }
-  // every scratch slot the loop touches must exist before capture (allocation is not capturable)
-  double* sc_[4] = {scratch_doubles(0, (size_t)g.sc * NPRIM), scratch_doubles(1, (size_t)g.sc * NGRAD),
-                    scratch_doubles(2, (size_t)g.sc * NPRIM * 5), scratch_doubles(3, (size_t)g.sc * NGRAD * 5)};
-  for (double* p : sc_)
-    if (!p) return BC_ERR_ALLOC;
+  static thread_local cudaStream_t chain_st[4] = {nullptr, nullptr, nullptr, nullptr};
+  static thread_local cudaEvent_t chain_join[4] = {nullptr, nullptr, nullptr, nullptr};
+  static thread_local cudaEvent_t chain_fork = nullptr;
+  if (K > 1 && !chain_fork) {
+    for (int c = 0; c < 4; ++c) {
+      if (cudaStreamCreateWithFlags(&chain_st[c], cudaStreamNonBlocking) != cudaSuccess) return BC_ERR_ALLOC;
+      if (cudaEventCreateWithFlags(&chain_join[c], cudaEventDisableTiming) != cudaSuccess) return BC_ERR_ALLOC;
+    }
+    if (cudaEventCreateWithFlags(&chain_fork, cudaEventDisableTiming) != cudaSuccess) return BC_ERR_ALLOC;
+  }
   std::string key;
   auto put = [&](const void* p, size_t n) { key.append(reinterpret_cast<const char*>(p), n); };
   int dev = 0;
@@ -316,8 +360,13 @@ extern "C" int bcd_jacobian_strips(int nrect, const int32_t* rects /* [nrect][4]
     put(&d.lm, sizeof d.lm); put(&d.table, sizeof d.table);
   }
   for (int q = 0; q < nrect; ++q) { put(&jac[q], sizeof(void*)); put(&ia[q], sizeof(void*)); put(&ja[q], sizeof(void*)); }
-  const void* ptrs[] = {w, nx, ny, vol, volf, coefdiag, wd5, resd5, sc_[0], sc_[1], sc_[2], sc_[3]};
+  const void* ptrs[] = {w, nx, ny, vol, volf, coefdiag};
   put(ptrs, sizeof ptrs);
+  put(&K, sizeof K);
+  for (int c = 0; c < K; ++c) {
+    const void* pc[] = {wd5c[c], resd5c[c], sc_[c][0], sc_[c][1], sc_[c][2], sc_[c][3]};
+    put(pc, sizeof pc);
+  }
   const int crk[] = {current_colours().c0, current_colours().c1};
   put(crk, sizeof crk);
   struct Entry { std::string key; cudaGraphExec_t exec; int nlaunch; };
@@ -337,12 +386,24 @@ extern "C" int bcd_jacobian_strips(int nrect, const int32_t* rects /* [nrect][4]
       return e == cudaSuccess ? BC_OK : (int)e;
     }
   static const bool no_fork = getenv("BROADCAST_B200_NO_GRAPH_FORK") != nullptr;
-  rect_fork().ready();   // side streams and events exist before the capture starts
+  for (int c = 0; c < K; ++c) {   // side streams and events exist before the capture starts
+    scratch_chain() = c;
+    rect_fork().ready();
+  }
+  scratch_chain() = 0;
   cudaError_t e = cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal);
   if (e != cudaSuccess) return (int)e;
-  rect_fork().on = !no_fork;   // per-rectangle launches become parallel branches of the graph
-  const cudaError_t er = run(gs);
-  rect_fork().on = false;
+  for (int c = 0; c < K; ++c) {   // per-rectangle launches become parallel branches of the graph
+    scratch_chain() = c;
+    rect_fork().on = !no_fork;
+  }
+  scratch_chain() = 0;
+  const cudaError_t er = run(gs, chain_st, chain_fork, chain_join);
+  for (int c = 0; c < K; ++c) {
+    scratch_chain() = c;
+    rect_fork().on = false;
+  }
+  scratch_chain() = 0;
   cudaGraph_t graph = nullptr;
   e = cudaStreamEndCapture(gs, &graph);
   if (er != cudaSuccess || e != cudaSuccess) {

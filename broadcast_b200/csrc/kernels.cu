@@ -28,9 +28,13 @@ SlabInfo& current_slab() {
   return s;
 }
 
+int& scratch_chain() {
+  static thread_local int c = 0;
+  return c;
+}
 RectFork& rect_fork() {
-  static thread_local RectFork f;
-  return f;
+  static thread_local RectFork f[4];
+  return f[scratch_chain() & 3];
 }
 bool RectFork::ready() {
   if (fork) return true;
@@ -50,7 +54,7 @@ double* scratch_doubles(int slot, size_t count) {
   int dev = 0;
   cudaGetDevice(&dev);
   std::lock_guard<std::mutex> lk(g_scratch_mu);
-  Slot& s = g_scratch[{dev, slot}];
+  Slot& s = g_scratch[{dev, slot + 1000 * scratch_chain()}];
   if (s.n < count) {
     if (s.p) cudaFree(s.p);
     s.p = nullptr;

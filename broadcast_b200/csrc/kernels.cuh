@@ -74,7 +74,10 @@ struct RectFork {
   cudaEvent_t fork = nullptr, join[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ready();   // creates streams and events on first use
 };
-RectFork& rect_fork();
+RectFork& rect_fork();   // the fork context of the calling thread's current chain (scratch_chain())
+// Colour chains: the strip colour loop runs up to four colours at a time inside its CUDA graph, each chain with its own scratch
+// buffers and side streams.  scratch_doubles(slot, n) resolves to slot + 1000 * scratch_chain().
+int& scratch_chain();
 template <class F>
 inline void for_each_rect(const RectList& l, cudaStream_t st, F&& launch) {   // launch(one-rect list, index, stream)
   RectFork& rf_ = rect_fork();
