@@ -253,7 +253,9 @@ extern "C" int bcd_jacobian_strips(int nrect, const int32_t* rects /* [nrect][4]
   // scratch and side streams): on the reference's own grid sizes a pass is a chain of ~10 dependent small kernels, latency bound
   static const int chains_env = getenv("BROADCAST_B200_STRIP_CHAINS") ? atoi(getenv("BROADCAST_B200_STRIP_CHAINS")) : 0;
   static const bool no_graph = getenv("BROADCAST_B200_NO_GRAPH") != nullptr;
-  int K = chains_env > 0 ? chains_env : ((long long)im * jm <= 2200000LL ? 4 : 1);
+  // each chain holds 116 full-grid planes of scratch (0.93 KB per cell): four chains up to 4.5 M cells, two up to 9 M, one beyond
+  const long long ncells_ = (long long)im * jm;
+  int K = chains_env > 0 ? chains_env : (ncells_ <= 4500000LL ? 4 : (ncells_ <= 9000000LL ? 2 : 1));
   if (K > 4) K = 4;
   if (no_graph) K = 1;
   double* wd5c[4] = {nullptr, nullptr, nullptr, nullptr};
