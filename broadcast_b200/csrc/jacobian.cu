@@ -214,7 +214,10 @@ extern "C" int bcd_dz_coo(double* jac1, int32_t* ia1, int32_t* ja1, double* jac2
       if (!current_colours().has(l * s + k)) continue;   // colour sharding: this rank's passes only
       cudaError_t e = launch_testvector(g, wd5, 5, 0, l, k, nullptr, st);
       if (e != cudaSuccess) return (int)e;
-      e = apply_bc_list(g, gam, 5, w, wd5, nx, ny, bcs, nbcs, st);
+      static const bool skip_bcs = getenv("BROADCAST_B200_NO_BC_SKIP") == nullptr;
+      bc_desc_t act[16];
+      const int nact = (skip_bcs && nbcs <= 16) ? active_bcs(g, bcs, nbcs, l, k, act) : -1;
+      e = nact >= 0 ? apply_bc_list(g, gam, 5, w, wd5, nx, ny, act, nact, st) : apply_bc_list(g, gam, 5, w, wd5, nx, ny, bcs, nbcs, st);
       if (e != cudaSuccess) return (int)e;
       for (int which = 1; which <= 2; ++which) {
         double* jac = which == 1 ? jac1 : jac2;
