@@ -185,3 +185,43 @@ def test_seed_and_scatter_integer_semantics(ref):
                             assert (ci, cj) == near[0] and len(near) == 1
                     else:
                         assert not near and ia[slot] == 5 * im * jm - 1 and ja[slot] == 0
+
+
+def test_fill_skipping_rule_of_the_colour_loops(ref):
+    """The device colour loops skip the linearised boundary fill of a side for the colours that have no seed row / column
+    among the first three interior lines of that side (csrc/jacobian.cu, active_bcs).  Checked on the reference itself: for
+    every colour the ghost tangents the reference's linearised fills write on such a side are exactly zero."""
+    import helpers as H
+    from broadcast_b200 import cases
+    for kind, im, jm in (("bl", 23, 17), ("cyl", 28, 16)):
+        c = H.make_case(kind, im, jm, ref, with_w=True)
+        w, _ = H.residual_sequence(ref, c)
+        gh = c.gh
+        s = 2 * gh + 1
+        near_lo = lambda q: q <= gh - 1
+        near_hi = lambda q, n: n >= q + 1 and (n - (q + 1)) % s <= gh - 1
+        skipped = 0
+        for l in range(s):
+            for k in range(s):
+                for m in (0, 4):
+                    wd = c.zeros_state()
+                    ref["f_misc"].testvector(wd, m, l, k, gh, im, jm)
+                    ww = w.copy(order="F")
+                    cases.apply_bcs_lin(c, ww, wd, ref["f_bnd"], ref["f_lin"])
+                    ghosts = {"Ilo": wd[:gh], "Ihi": wd[-gh:], "Jlo": wd[:, :gh], "Jhi": wd[:, -gh:]}
+                    active = {"Ilo": near_lo(l), "Ihi": near_hi(l, im), "Jlo": near_lo(k), "Jhi": near_hi(k, jm)}
+                    for side, a in active.items():
+                        if kind == "cyl" and side in ("Ilo", "Ihi"):
+                            continue      # periodic cut: the join copies interior tangents, always applied
+                        if not a:
+                            # the whole ghost strip of the side, corners included (a corner is filled by the LATER of its two
+                            # sides from the ghosts of the earlier one, which are zero as well)
+                            other = ("Jlo", "Jhi") if side[0] == "I" else ("Ilo", "Ihi")
+                            g_ = ghosts[side]
+                            if kind == "cyl" and side[0] == "J":
+                                g_ = g_[gh:-gh]       # the cut's ghost columns are copies of interior cells of the far side
+                            assert not np.any(g_[gh:-gh] if side[0] == "J" else g_[:, gh:-gh]), (kind, side, l, k, m)
+                            if not any(active[o] for o in other):
+                                assert not np.any(g_), (kind, side, l, k, m, "corners")
+                            skipped += 1
+        assert skipped > 0
