@@ -7,7 +7,7 @@ optional trailing arguments; the wrappers below reproduce exactly that surface (
 8(b)) and forward the FULL Fortran argument list, in Fortran order, to ``backend(name, *args)``.
 
 ``build(backend)`` returns a dict of module-like namespaces
-``{'f_sch', 'f_lin', 'f_bnd', 'f_geom', 'f_norm', 'f_misc', 'f_init', 'f_dz'}``.
+``{'f_sch', 'f_lin', 'f_bnd', 'f_geom', 'f_norm', 'f_misc', 'f_init', 'f_dz', 'f_lindz'}``.
 """
 from __future__ import annotations
 
@@ -285,6 +285,29 @@ def build(backend):
 
     f_dz = types.SimpleNamespace(coeffs_5p_dz=_dz("coeffs_5p_dz"), coeffs_5p_dz2=_dz("coeffs_5p_dz2"))
 
+    # ------------------------------------------------------------------ f_lindz (tangent of the operator rows w.r.t. the base flow)
+    # srcfv/tangentdz/coeffs_5p_dz_d.f90, coeffs_5p_dz2_d.f90; call sites BROADCAST_npz_sens.py:1768-1797, 2157-2185:
+    #   f_lindz.coeffs_5p_dz_d(resd, dzr, w, wd, wmoder, x0, ..., im, jm)  ->  Fortran (dz_out, dz_outd, w, wd0, wd, ...)
+    # dz_out is left untouched (Tapenade sliced its assignments), the WHOLE of dz_outd is written (ghost frame = 0).
+    def _dz_d(name):
+        def f(dz, dzd, w, wd0, wd, x0, y0, nx, ny, xc, yc, vol, volf, gh, cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth,
+              im=None, jm=None):
+            gh = int(gh)
+            im = int(im) if im is not None else w.shape[0] - 2 * gh
+            jm = int(jm) if jm is not None else w.shape[1] - 2 * gh
+            _check_cells(_state(dz, "dz_out"), im, jm, gh, "dz_out")
+            _check_cells(_state(dzd, "dz_outd"), im, jm, gh, "dz_outd")
+            w, wd0, wd = _in(w), _in(wd0), _in(wd)
+            _check_cells(w, im, jm, gh, "w")
+            _check_cells(wd0, im, jm, gh, "wd0")
+            _check_cells(wd, im, jm, gh, "wd")
+            B(name, dz, dzd, w, wd0, wd, _in(x0), _in(y0), _in(nx), _in(ny), _in(xc), _in(yc), _in(vol), _in(volf), gh, cp, cv,
+              prandtl, gam, rgaz, cs, muref, tref, s_suth, im, jm)
+        f.__name__ = name
+        return f
+
+    f_lindz = types.SimpleNamespace(coeffs_5p_dz_d=_dz_d("coeffs_5p_dz_d"), coeffs_5p_dz2_d=_dz_d("coeffs_5p_dz2_d"))
+
     # ------------------------------------------------------------------ f_init (boundary tables from the initial field)
     def set_bndbl_2d(w, field, wbd, im, jm=None, gh=None):
         w = _in(w)
@@ -296,4 +319,4 @@ def build(backend):
 
     f_init = types.SimpleNamespace(set_bndbl_2d=set_bndbl_2d)
 
-    return dict(f_sch=f_sch, f_lin=f_lin, f_bnd=f_bnd, f_geom=f_geom, f_norm=f_norm, f_misc=f_misc, f_dz=f_dz, f_init=f_init)
+    return dict(f_sch=f_sch, f_lin=f_lin, f_bnd=f_bnd, f_geom=f_geom, f_norm=f_norm, f_misc=f_misc, f_dz=f_dz, f_lindz=f_lindz, f_init=f_init)

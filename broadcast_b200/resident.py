@@ -174,6 +174,17 @@ class Block:
                   r.ctypes.data_as(ctypes.c_void_p) if r is not None else ctypes.c_void_p(None), self._stream())
         return out
 
+    def dz_tangent(self, wd0, wd, out1=None, out2=None, w=None, rect=None):
+        """tangent of the Dz (out1) and Dz2 (out2) operator rows w.r.t. the base flow, both in ONE pass over device arrays
+        (f_lindz.coeffs_5p_dz_d / coeffs_5p_dz2_d, BROADCAST_npz_sens.py:1768-1769); wd0 = base-flow variation, wd = mode"""
+        w = self.w if w is None else w
+        r = np.asarray(rect, dtype=np.int32) if rect is not None else None
+        null = ctypes.c_void_p(None)
+        self.call("bcd_dz_tangent", _p(out1) if out1 is not None else null, _p(out2) if out2 is not None else null, _p(w), _p(wd0),
+                  _p(wd), _p(self.nx), _p(self.ny), _p(self.vol), self.gh, *self._phys[:9], self.im, self.jm,
+                  r.ctypes.data_as(ctypes.c_void_p) if r is not None else null, self._stream())
+        return out1, out2
+
     def norms(self, res=None, reduce=None):
         res = self.res if res is None else res
         self._ck(self.lib.bcd_norm_sums(_p(self.out10), _p(res), self.im, self.jm, self.gh, self._stream()), "bcd_norm_sums")

@@ -129,6 +129,19 @@ int bc_coeffs_5p_dz2(double* dz_out, const double* w, const double* wd, const do
                      double cv, double prandtl, double gam, double rgaz, double cs, double muref, double tref, double s_suth, int im,
                      int jm);
 
+/* ---- tangent of the spanwise operator rows w.r.t. the base flow: srcfv/tangentdz/coeffs_5p_dz_d.f90 (COEFFS_5P_DZ_D),
+ *      srcfv/tangentdz/coeffs_5p_dz2_d.f90 (COEFFS_5P_DZ2_D) = f_lindz.coeffs_5p_dz_d / coeffs_5p_dz2_d of the sensitivity driver
+ *      (BROADCAST_npz_sens.py:1768-1797, 2157-2185).  wd0 = variation of the base flow, wd = the mode.  As in the reference, dz_out
+ *      is never assigned and the WHOLE of dz_outd is written (interior rows, ghost frame = 0). */
+int bc_coeffs_5p_dz_d(double* dz_out, double* dz_outd, const double* w, const double* wd0, const double* wd, const double* x0,
+                      const double* y0, const double* nx, const double* ny, const double* xc, const double* yc, const double* vol,
+                      const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
+                      double muref, double tref, double s_suth, int im, int jm);
+int bc_coeffs_5p_dz2_d(double* dz2_out, double* dz2_outd, const double* w, const double* wd0, const double* wd, const double* x0,
+                       const double* y0, const double* nx, const double* ny, const double* xc, const double* yc, const double* vol,
+                       const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
+                       double muref, double tref, double s_suth, int im, int jm);
+
 /* ---- boundary tables from the initial field: set_bnd.f90:2-24 (f_init.set_bndbl_2d).  A host-side copy
  *      (field(j,depth,:) = w(1-depth,j,:), wbd(i,:) = w(i-gh,jm,:)); set-up, not on the device path. */
 int bc_set_bndbl_2d(const double* w, double* field, double* wbd, int im, int jm, int gh);
@@ -197,6 +210,11 @@ int bcd_scatter(int kind, double* seg_jac, int32_t* seg_ia, int32_t* seg_ja, con
 int bcd_dz(double* dz_out, const double* w, const double* wd, int ndir, int which, const double* nx, const double* ny,
            const double* vol, const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
            double muref, double tref, double s_suth, int im, int jm, const int32_t* rect, void* stream);
+/* tangent of both operator rows w.r.t. the base flow in ONE pass over device arrays (either output may be NULL); interior cells of
+ * `rect` (NULL = all) are written, nothing else */
+int bcd_dz_tangent(double* dz_outd, double* dz2_outd, const double* w, const double* wd0, const double* wd, const double* nx,
+                   const double* ny, const double* vol, int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
+                   double muref, double tref, double s_suth, int im, int jm, const int32_t* rect, void* stream);
 /* out10 (device): sum r^2 per equation [5], sum r^10 per equation [5] */
 int bcd_norm_sums(double* out10, const double* rhs, int im, int jm, int gh, void* stream);
 

@@ -53,6 +53,9 @@ FILES = [
     # expand the authoritative srcfv/dz/*.F90 here exactly as srcfv/compile_dz.py does (fpp -I srcfv -P)
     ("cpp:srcfv/dz/coeffs_5p_dz.F90", None),
     ("cpp:srcfv/dz/coeffs_5p_dz2.F90", None),
+    # tangent of the spanwise operator rows w.r.t. the base flow (f_lindz of the sensitivity driver, BROADCAST_npz_sens.py:1768-1797)
+    ("srcfv/tangentdz/coeffs_5p_dz_d.f90", None),
+    ("srcfv/tangentdz/coeffs_5p_dz2_d.f90", None),
     ("srcfv/norm.F90", None),
     ("set_bnd.f90", None),
     ("initialisation.f90", None),

@@ -67,6 +67,24 @@ def make(kind, im, jm, R):
     return out
 
 
+def make_dz_tangent(kind, im, jm, R):
+    """outputs of the reference's srcfv/tangentdz/coeffs_5p_dz_d.f90 / coeffs_5p_dz2_d.f90 (f_lindz, BROADCAST_npz_sens.py:1768-1769)
+    on the filled state of the fixture, a seeded base-flow variation wd0 and a seeded mode wd (both stored)"""
+    c = H.make_case(kind, im, jm, R, with_w=True)
+    w, _ = H.residual_sequence(R, c)
+    rng = np.random.default_rng(21)
+    wd = np.asfortranarray(rng.standard_normal(w.shape))
+    wd0 = np.asfortranarray(rng.standard_normal(w.shape) * np.abs(w).max(axis=(0, 1)))
+    a = c.scheme_args()
+    dzargs = a[:18] + a[20:]
+    out = dict(kind=kind, im=im, jm=jm, gh=c.gh, wd=wd, wd0=wd0)
+    for name, key in (("coeffs_5p_dz_d", "dzd"), ("coeffs_5p_dz2_d", "dz2d")):
+        z, zd = c.zeros_state(), c.zeros_state()
+        getattr(R["f_lindz"], name)(z, zd, w, wd0, wd, *dzargs)
+        out[key] = zd
+    return out
+
+
 def main():
     if not refmods.available():
         sys.path.insert(0, HERE)
@@ -75,7 +93,15 @@ def main():
             raise SystemExit("oracle/_ref is not built and /root/reference is absent")
     R = refmods.make()
     os.makedirs(OUT, exist_ok=True)
+    only_dz_tangent = "--dz-tangent" in sys.argv   # add the f_lindz fixtures without rewriting the others
     for kind, im, jm in FIXTURES:
+        d = make_dz_tangent(kind, im, jm, R)
+        p = os.path.join(OUT, "lindz", f"{kind}_{im}x{jm}.npz")
+        os.makedirs(os.path.dirname(p), exist_ok=True)
+        np.savez_compressed(p, **d)
+        print(p, os.path.getsize(p) // 1024, "KiB")
+        if only_dz_tangent:
+            continue
         d = make(kind, im, jm, R)
         p = os.path.join(OUT, f"{kind}_{im}x{jm}.npz")
         np.savez_compressed(p, **d)

@@ -32,4 +32,4 @@ def gpu():
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
     import broadcast_b200 as bb
     assert bb._lib.device_count() > 0
-    return dict(f_sch=bb.f_sch, f_lin=bb.f_lin, f_bnd=bb.f_bnd, f_geom=bb.f_geom, f_norm=bb.f_norm, f_misc=bb.f_misc, f_dz=bb.f_dz, f_init=bb.f_init)
+    return dict(f_sch=bb.f_sch, f_lin=bb.f_lin, f_bnd=bb.f_bnd, f_geom=bb.f_geom, f_norm=bb.f_norm, f_misc=bb.f_misc, f_dz=bb.f_dz, f_lindz=bb.f_lindz, f_init=bb.f_init)

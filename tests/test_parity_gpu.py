@@ -596,3 +596,130 @@ def test_csr_kernels_match_scipy_semantics(gpu, kind, im, jm):
         A.sort_indices()
         assert np.array_equal(ip2, A.indptr) and np.array_equal(idx2, A.indices)
         assert np.abs(dat2 - A.data).max() <= 1e-12 * np.abs(A.data).max()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# tangent of the spanwise operator rows w.r.t. the base flow (f_lindz of BROADCAST_npz_sens.py:1768-1797)
+# ---------------------------------------------------------------------------------------------------------------------
+def _dz_tangent_dirs(mods, c, w, seed):
+    rng = np.random.default_rng(seed)
+    wd = np.asfortranarray(rng.standard_normal(w.shape))
+    wd0 = np.asfortranarray(rng.standard_normal(w.shape) * np.abs(w).max(axis=(0, 1)))
+    ws = c.zeros_state()
+    mods["f_misc"].testvector(ws, 2, 3, 1, c.gh, c.im, c.jm)
+    return wd, wd0, ws
+
+
+@pytest.mark.parametrize("kind,im,jm", CASES + [("bl", 5, 3)])
+def test_dz_tangent_rows(gpu, ref, kind, im, jm):
+    """f_lindz.coeffs_5p_dz_d / coeffs_5p_dz2_d vs the reference's Tapenade code (srcfv/tangentdz) on dense directions and a
+    colour seed; dz_out untouched, the whole of dz_outd written (ghost frame = 0)"""
+    a = H.make_case(kind, im, jm, gpu, with_w=True)
+    b = H.make_case(kind, im, jm, ref, with_w=True)
+    wa, _ = H.residual_sequence(gpu, a)
+    wb, _ = H.residual_sequence(ref, b)
+    wd, wd0, ws = _dz_tangent_dirs(ref, b, wb, 12)
+    g = a.gh
+    for d0, d in ((wd0, wd), (ws, wd), (wd0, ws)):
+        for name in ("coeffs_5p_dz_d", "coeffs_5p_dz2_d"):
+            za, zb = (np.asfortranarray(np.full(wa.shape, 7.0)) for _ in range(2))
+            zda, zdb = (np.asfortranarray(np.full(wa.shape, 5.0)) for _ in range(2))
+            getattr(gpu["f_lindz"], name)(za, zda, wa, d0, d, *_dz_args(a))
+            getattr(ref["f_lindz"], name)(zb, zdb, wb, d0, d, *_dz_args(b))
+            assert np.all(za == 7.0) and np.all(zb == 7.0)
+            assert np.all(zda[:g] == 0.0) and np.all(zda[:, :g] == 0.0) and np.all(zda[-g:] == 0.0) and np.all(zda[:, -g:] == 0.0)
+            assert np.abs(zdb).max() > 0
+            assert np.all(H.rel_err(zda, zdb) < TOL), (name, H.rel_err(zda, zdb))
+
+
+def test_dz_tangent_device_fused_pass(gpu):
+    """Block.dz_tangent: both operators in ONE pass equal the two single-operator passes bit for bit; a rectangle writes only its
+    cells and its values do not depend on where the tiles start"""
+    import torch
+    from broadcast_b200.resident import Block, _t
+    im, jm = 97, 33
+    a = H.make_case("bl", im, jm, gpu, with_w=True)
+    blk = Block(a)
+    blk.apply_bcs()
+    w = np.asfortranarray(blk.w.cpu().numpy().T)
+    wd, wd0, _ = _dz_tangent_dirs(gpu, a, w, 5)
+    dwd, dwd0 = _t(wd, blk.device), _t(wd0, blk.device)
+    o1, o2, s1, s2 = (torch.zeros_like(blk.w) for _ in range(4))
+    blk.dz_tangent(dwd0, dwd, o1, o2)
+    blk.dz_tangent(dwd0, dwd, s1, None)
+    blk.dz_tangent(dwd0, dwd, None, s2)
+    assert torch.equal(o1, s1) and torch.equal(o2, s2) and float(o1.abs().max()) > 0 and float(o2.abs().max()) > 0
+    gh = a.gh
+    r1, r2 = (torch.full_like(blk.w, 3.0) for _ in range(2))
+    rect = (12, 70, 4, 29)
+    blk.dz_tangent(dwd0, dwd, r1, r2, rect=rect)
+    sl = (slice(None), slice(gh + rect[2] - 1, gh + rect[3]), slice(gh + rect[0] - 1, gh + rect[1]))
+    assert torch.equal(r1[sl], o1[sl]) and torch.equal(r2[sl], o2[sl])
+    r1[sl] = 3.0
+    r2[sl] = 3.0
+    assert bool((r1 == 3.0).all()) and bool((r2 == 3.0).all())
+
+
+def test_dz_tangent_full_size_properties(gpu):
+    """C5 (8192 x 2048): size-independent properties of the fused pass -- no NaN, ghost frame untouched, exact homogeneity in both
+    directions (powers of two), additivity in the base-flow variation to rounding, tiling invariance on a shifted rectangle --
+    and its device time against the algorithmic traffic (240 B per cell for both operators)."""
+    import json
+    import os
+    import torch
+    import broadcast_b200 as bb
+    from broadcast_b200.resident import Block
+    im, jm = 8192, 2048
+    c = cases.make_bl_case(im, jm, f_geom=bb.f_geom, with_w=True)
+    blk = Block(c)
+    blk.apply_bcs()
+    gh = c.gh
+    gen = torch.Generator(device=blk.device).manual_seed(4)
+    wd = torch.randn(blk.w.shape, dtype=torch.float64, device=blk.device, generator=gen)
+    wd0 = torch.randn(blk.w.shape, dtype=torch.float64, device=blk.device, generator=gen) * blk.w.abs().amax(dim=(1, 2), keepdim=True)
+    wd1 = torch.randn(blk.w.shape, dtype=torch.float64, device=blk.device, generator=gen) * blk.w.abs().amax(dim=(1, 2), keepdim=True)
+    o1, o2, p1, p2 = (torch.zeros_like(blk.w) for _ in range(4))
+    blk.dz_tangent(wd0, wd, o1, o2)
+    assert not torch.isnan(o1).any() and not torch.isnan(o2).any()
+    assert float(o1[:, :gh].abs().max()) == 0.0 and float(o1[:, :, :gh].abs().max()) == 0.0
+    blk.dz_tangent(wd0 * 4.0, wd * 0.5, p1, p2)
+    assert torch.equal(p1, o1 * 2.0) and torch.equal(p2, o2 * 2.0)
+    blk.dz_tangent(wd0 + wd1, wd, p1, p2)
+    q1, q2 = (torch.zeros_like(blk.w) for _ in range(2))
+    blk.dz_tangent(wd1, wd, q1, q2)
+    for s, a, b in ((p1, o1, q1), (p2, o2, q2)):
+        scale = s.abs().amax(dim=(1, 2))
+        err = (s - a - b).abs().amax(dim=(1, 2))
+        assert bool(((err <= 1e-12 * scale) | (scale == 0)).all()), (err / scale).tolist()
+    rect = (12, 5000, 3, 1999)
+    blk.dz_tangent(wd0, wd, q1, q2, rect=rect)
+    sl = (slice(None), slice(gh + rect[2] - 1, gh + rect[3]), slice(gh + rect[0] - 1, gh + rect[1]))
+    assert torch.equal(q1[sl], o1[sl]) and torch.equal(q2[sl], o2[sl])
+    # device time (CUDA events on the launching stream, after warm-up)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        blk.dz_tangent(wd0, wd, o1, o2)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    line = {"kernel": "k_dz_tangent", "grid": [im, jm], "ms": ms, "algorithmic_bytes_per_cell": 240, "GBps": 240.0 * im * jm / ms / 1e6}
+    print("DZ_TANGENT", json.dumps(line))
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/dz_tangent_c5.json", "w") as fh:
+        fh.write(json.dumps(line) + "\n")
+
+
+@pytest.mark.parametrize("name", ["bl_24x16", "cyl_28x16"])
+def test_dz_tangent_golden(gpu, name):
+    """product vs the committed outputs of the reference's tangentdz code (tests/golden/lindz, oracle/make_golden.py --dz-tangent)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lindz", name + ".npz"))
+    a = H.make_case(str(g["kind"]), int(g["im"]), int(g["jm"]), gpu, with_w=True)
+    wa, _ = H.residual_sequence(gpu, a)
+    wd0, wd = np.asfortranarray(g["wd0"]), np.asfortranarray(g["wd"])
+    for fn, key in (("coeffs_5p_dz_d", "dzd"), ("coeffs_5p_dz2_d", "dz2d")):
+        z, zd = a.zeros_state(), a.zeros_state()
+        getattr(gpu["f_lindz"], fn)(z, zd, wa, wd0, wd, *_dz_args(a))
+        assert np.all(H.rel_err(zd, g[key]) < TOL), (fn, H.rel_err(zd, g[key]))
