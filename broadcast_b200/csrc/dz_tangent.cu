@@ -4,11 +4,14 @@
 #include "../../include/broadcast_b200.h"
 #include "kernels.cuh"
 #include "dz_tangent.cuh"
+#include <cstdlib>
 
 namespace bcast {
 void count_launches(int n);
 
-__global__ void __launch_bounds__(dzt::NT, 2) k_dz_tangent(dzt::Tile t, Rect rc) {
+// MINB = CTAs per SM the register budget is cut for: 2 (118 registers, no spills) or 3 (80 registers, 34 spilled doubles, 24 warps per SM)
+template <int MINB>
+__global__ void __launch_bounds__(dzt::NT, MINB) k_dz_tangent(dzt::Tile t, Rect rc) {
   extern __shared__ double dzt_sm[];
   t.sm = dzt_sm;
   t.i0 = rc.i0 + blockIdx.x * dzt::TI;
@@ -16,22 +19,30 @@ __global__ void __launch_bounds__(dzt::NT, 2) k_dz_tangent(dzt::Tile t, Rect rc)
   t.i1 = rc.i1;
   t.j1 = rc.j1;
   const int tid = threadIdx.x;
-  const dzt::Cell c = dzt::phase_a(t, tid);
-  if (!t.out1) return;   // d2/dz2 rows only: cell-local, finished in phase A (uniform over the grid)
-  dzt::phase_b(t, tid);
+  long long ka, kb = 0;
+  const int sa = dzt::own_cell(t, tid, &ka);
+  const int sb = t.out1 ? dzt::halo_cell(t, tid, &kb) : -1;   // d2/dz2 rows only: cell-local, no halo (uniform over the grid)
+  const dzt::Raw ra = dzt::load_raw(t, sa >= 0, ka), rb = dzt::load_raw(t, sb >= 0, kb);
+  const dzt::Met m = dzt::load_metrics(t, tid);
+  dzt::phase_b(t, sb, rb);
+  const dzt::Carry c = dzt::carry_of(dzt::phase_a(t, tid, ra, ka));
+  if (!t.out1) return;
   __syncthreads();
-  dzt::phase_c(t, tid, c);
+  dzt::phase_c(t, tid, c, m);
 }
 
 cudaError_t launch_dz_tangent(const GridDesc& g, const dzt::Consts& c, double* out1, double* out2, const double* w, const double* wd0,
                               const double* wd, const double* nx, const double* ny, const double* vol, const Rect& rc, cudaStream_t st) {
   if (rc.i1 < rc.i0 || rc.j1 < rc.j0 || (!out1 && !out2)) return cudaSuccess;
-  static bool attr_set = false;
+  static int minb = 0;   // BCAST_DZT_MINB = 2 | 3 selects the register budget (A/B in profiles/r1_l_summary.md)
   constexpr int smem = dzt::NSM * (int)sizeof(double);
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_dz_tangent, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (!minb) {
+    const char* env = getenv("BCAST_DZT_MINB");
+    const int want = env && env[0] == '3' ? 3 : 2;
+    cudaError_t e = cudaFuncSetAttribute(k_dz_tangent<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_dz_tangent<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    minb = want;
   }
   dzt::Tile t{};
   t.g = g;
@@ -46,7 +57,10 @@ cudaError_t launch_dz_tangent(const GridDesc& g, const dzt::Consts& c, double* o
   t.out2 = out2;
   const dim3 grid((rc.i1 - rc.i0 + dzt::TI) / dzt::TI, (rc.j1 - rc.j0 + dzt::TJ) / dzt::TJ);
   count_launches(1);
-  k_dz_tangent<<<grid, dzt::NT, smem, st>>>(t, rc);
+  if (minb == 3)
+    k_dz_tangent<3><<<grid, dzt::NT, smem, st>>>(t, rc);
+  else
+    k_dz_tangent<2><<<grid, dzt::NT, smem, st>>>(t, rc);
   return cudaGetLastError();
 }
 }  // namespace bcast

@@ -83,10 +83,28 @@ struct Cell {
   HD q[5], u, v, wz, t, p, mu;
 };
 
-BC_HD Cell cell_prims(const Tile& t, long long k) {
+// the 15 doubles of one cell (w, wd, wd0): loaded first, for the own cell AND the halo cell of a thread, so that both sets of loads
+// are in flight before any arithmetic starts (the pass is latency bound on them at 16 warps per SM)
+struct Raw {
+  double w[5], a[5], b[5];
+  bool ok;
+};
+BC_HD Raw load_raw(const Tile& t, bool ok, long long k) {
+  Raw r;
+  r.ok = ok;
+#pragma unroll
+  for (int e = 0; e < 5; ++e) {
+    r.w[e] = ok ? BC_LDG(t.w + e * t.g.sc + k) : 1.0;
+    r.a[e] = ok ? BC_LDG(t.wa + e * t.g.sc + k) : 0.0;
+    r.b[e] = ok ? BC_LDG(t.wb + e * t.g.sc + k) : 0.0;
+  }
+  return r;
+}
+
+BC_HD Cell cell_prims(const Tile& t, const Raw& in) {
   Cell r;
 #pragma unroll
-  for (int e = 0; e < 5; ++e) r.q[e] = HD{BC_LDG(t.w + e * t.g.sc + k), BC_LDG(t.wa + e * t.g.sc + k), BC_LDG(t.wb + e * t.g.sc + k), 0.0};
+  for (int e = 0; e < 5; ++e) r.q[e] = HD{in.w[e], in.a[e], in.b[e], 0.0};
   const HD rom1 = recip(r.q[0]);
   r.u = r.q[1] * rom1;
   r.v = r.q[2] * rom1;
@@ -135,12 +153,15 @@ BC_HD void row_dz2(const Tile& t, const Cell& c, double (&r)[5]) {
 }
 
 // Phase A: own cell -> primitives; u, v, w, mu to shared memory; d2/dz2 row finished here.
-BC_HD Cell phase_a(const Tile& t, int tid) {
+BC_HD int own_cell(const Tile& t, int tid, long long* k) {   // staged index of the thread's own cell, -1 if outside the padded array
   const int tx = tid % TI, ty = tid / TI;
-  long long k;
+  return staged_in_array(t, tx + HALO, ty + HALO, k) ? (ty + HALO) * SI + tx + HALO : -1;
+}
+BC_HD Cell phase_a(const Tile& t, int tid, const Raw& in, long long k) {
+  const int tx = tid % TI, ty = tid / TI;
   Cell c{};
-  if (!staged_in_array(t, tx + HALO, ty + HALO, &k)) return c;
-  c = cell_prims(t, k);
+  if (!in.ok) return c;
+  c = cell_prims(t, in);
   sm_put_cell(t, (ty + HALO) * SI + tx + HALO, c);
   if (t.out2 && t.i0 + tx <= t.i1 && t.j0 + ty <= t.j1) {
     double r[5];
@@ -152,8 +173,8 @@ BC_HD Cell phase_a(const Tile& t, int tid) {
 }
 
 // Phase B: the cross-shaped halo (threads 0..159)
-BC_HD void phase_b(const Tile& t, int tid) {
-  if (tid >= NHALO) return;
+BC_HD int halo_cell(const Tile& t, int tid, long long* k) {   // staged index of the thread's halo cell, -1 if none
+  if (tid >= NHALO) return -1;
   int sx, sy;
   if (tid < 2 * HALO * TI) {
     const int row = tid / TI;
@@ -164,25 +185,38 @@ BC_HD void phase_b(const Tile& t, int tid) {
     sy = HALO + r / (2 * HALO);
     sx = col < HALO ? col : TI + col;
   }
-  long long k;
-  if (!staged_in_array(t, sx, sy, &k)) return;
-  sm_put_cell(t, sy * SI + sx, cell_prims(t, k));
+  return staged_in_array(t, sx, sy, k) ? sy * SI + sx : -1;
+}
+BC_HD void phase_b(const Tile& t, int s, const Raw& in) {
+  if (in.ok) sm_put_cell(t, s, cell_prims(t, in));
 }
 
 // Phase C: d/dz row (srcfv/tangentdz/coeffs_5p_dz_d.f90; tables dz/coeffs_dz.F, matrix_dz/function_dz.F, gradients rhs/gradop_5pi.F,
 // gradop_5pj.F, gradient.F with geom/dxdy.F)
-BC_HD void phase_c(const Tile& t, int tid, const Cell& c) {
+struct Carry {   // what a thread keeps in registers across the barrier
+  HD q1, q2, q3, q4, p;
+};
+BC_HD Carry carry_of(const Cell& c) { return Carry{c.q[1], c.q[2], c.q[3], c.q[4], c.p}; }
+// metric factors of the 5-point gradient (geom/dxdy.F); loaded with the state, before the barrier
+struct Met {
+  double dxm1, dxm2, dym1, dym2;
+};
+BC_HD Met load_metrics(const Tile& t, int tid) {
+  const int i = t.i0 + tid % TI, j = t.j0 + tid / TI;
+  if (!t.out1 || i > t.i1 || j > t.j1) return Met{0.0, 0.0, 0.0, 0.0};
+  const long long k = t.g.cidx(i, j), n = t.g.nidx(i, j);
+  const double volm1 = 1.0 / BC_LDG(t.vol + k);
+  return Met{0.5 * (BC_LDG(t.nx + n) + BC_LDG(t.nx + n + 1)) * volm1, 0.5 * (BC_LDG(t.nx + t.g.sn + n) + BC_LDG(t.nx + t.g.sn + n + t.g.ldn)) * volm1,
+             0.5 * (BC_LDG(t.ny + n) + BC_LDG(t.ny + n + 1)) * volm1, 0.5 * (BC_LDG(t.ny + t.g.sn + n) + BC_LDG(t.ny + t.g.sn + n + t.g.ldn)) * volm1};
+}
+BC_HD void phase_c(const Tile& t, int tid, const Carry& c, const Met& m) {
   const int tx = tid % TI, ty = tid / TI;
   const int i = t.i0 + tx, j = t.j0 + ty;
   if (!t.out1 || i > t.i1 || j > t.j1) return;
-  const long long k = t.g.cidx(i, j), n = t.g.nidx(i, j);
+  const long long k = t.g.cidx(i, j);
   const int s = (ty + HALO) * SI + tx + HALO;
   constexpr double b1 = 8.0 * (1.0 / 12.0), b2 = -(1.0 / 12.0), TT = 2.0 / 3.0;
-  const double volm1 = 1.0 / BC_LDG(t.vol + k);
-  const double dxm1 = 0.5 * (BC_LDG(t.nx + n) + BC_LDG(t.nx + n + 1)) * volm1;
-  const double dxm2 = 0.5 * (BC_LDG(t.nx + t.g.sn + n) + BC_LDG(t.nx + t.g.sn + n + t.g.ldn)) * volm1;
-  const double dym1 = 0.5 * (BC_LDG(t.ny + n) + BC_LDG(t.ny + n + 1)) * volm1;
-  const double dym2 = 0.5 * (BC_LDG(t.ny + t.g.sn + n) + BC_LDG(t.ny + t.g.sn + n + t.g.ldn)) * volm1;
+  const double dxm1 = m.dxm1, dxm2 = m.dxm2, dym1 = m.dym1, dym2 = m.dym2;
   HD gx[NQ], gy[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
@@ -193,15 +227,15 @@ BC_HD void phase_c(const Tile& t, int tid, const Cell& c) {
   }
   const HD gu0 = gx[Q_U], gv1 = gy[Q_V], gw0 = gx[Q_W], gw1 = gy[Q_W], gm0 = gx[Q_MU], gm1 = gy[Q_MU];
   const HD divu = gu0 + gv1;
-  const HD &u = c.u, &v = c.v, &wz = c.wz, &mu = c.mu;
+  const HD u = sm_get(t, Q_U, s), v = sm_get(t, Q_V, s), wz = sm_get(t, Q_W, s), mu = sm_get(t, Q_MU, s);
   const HD mgw0 = mu * gw0, mgw1 = mu * gw1, muwz = mu * wz;
   double r[5];
   // coefficient ONE: the function's own mixed derivative
-  r[0] = c.q[3].ab;
-  r[1] = (c.q[1] * wz - mgw0).ab + term(TT * gm0, wz) + term(TT * mu, gw0);
-  r[2] = (c.q[2] * wz - mgw1).ab + term(TT * gm1, wz) + term(TT * mu, gw1);
-  r[3] = (c.q[3] * wz + c.p + TT * (mu * divu)).ab + term(-gm0, u) + term(-gm1, v) + term(-mu, divu);
-  r[4] = ((c.q[4] + c.p) * wz).ab                           //
+  r[0] = c.q3.ab;
+  r[1] = (c.q1 * wz - mgw0).ab + term(TT * gm0, wz) + term(TT * mu, gw0);
+  r[2] = (c.q2 * wz - mgw1).ab + term(TT * gm1, wz) + term(TT * mu, gw1);
+  r[3] = (c.q3 * wz + c.p + TT * (mu * divu)).ab + term(-gm0, u) + term(-gm1, v) + term(-mu, divu);
+  r[4] = ((c.q4 + c.p) * wz).ab                           //
          + term(TT * (gm0 * u + mu * gu0), wz)              // coeffs(5,2)  func1
          + term(TT * (mu * u), gw0)                         // coeffs(5,3)  func2
          + term(-(gm0 * wz + mgw0), u)                      // coeffs(5,4)  func3

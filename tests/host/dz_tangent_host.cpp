@@ -16,16 +16,21 @@ extern "C" int dzt_host(double* out1, double* out2, const double* w, const doubl
   t.c = dzt::make_dz_consts(cp, cv, prandtl, gam, cs, muref, tref, s_suth);
   t.w = w; t.wa = wd; t.wb = wd0; t.nx = nx; t.ny = ny; t.vol = vol; t.out1 = out1; t.out2 = out2;
   std::vector<double> sm(dzt::NSM);
-  std::vector<dzt::Cell> cells(dzt::NT);
+  std::vector<dzt::Carry> cells(dzt::NT);
   t.sm = sm.data();
   t.i1 = im; t.j1 = jm;
   for (int j0 = 1; j0 <= jm; j0 += dzt::TJ)
     for (int i0 = 1; i0 <= im; i0 += dzt::TI) {
       t.i0 = i0; t.j0 = j0;
       for (auto& x : sm) x = std::nan("");   // a read of an unstaged cell must show
-      for (int tid = 0; tid < dzt::NT; ++tid) cells[tid] = dzt::phase_a(t, tid);
-      for (int tid = 0; tid < dzt::NT; ++tid) dzt::phase_b(t, tid);
-      for (int tid = 0; tid < dzt::NT; ++tid) dzt::phase_c(t, tid, cells[tid]);
+      for (int tid = 0; tid < dzt::NT; ++tid) {   // the kernel's order: both loads, halo cell, own cell
+        long long ka, kb;
+        const int sa = dzt::own_cell(t, tid, &ka), sb = dzt::halo_cell(t, tid, &kb);
+        const dzt::Raw ra = dzt::load_raw(t, sa >= 0, ka), rb = dzt::load_raw(t, sb >= 0, kb);
+        dzt::phase_b(t, sb, rb);
+        cells[tid] = dzt::carry_of(dzt::phase_a(t, tid, ra, ka));
+      }
+      for (int tid = 0; tid < dzt::NT; ++tid) dzt::phase_c(t, tid, cells[tid], dzt::load_metrics(t, tid));
     }
   return 0;
 }
