@@ -295,6 +295,21 @@ int bcd_bc_wall_viscous_adia(double* w, double* wd, int ndir, const char* loc, d
   g_launches += 1;
   return e == cudaSuccess ? BC_OK : cuda_fail(e, "bcd_bc_wall_viscous_adia");
 }
+int bcd_bc_wall_viscous_iso(double* w, double* wd, int ndir, double twall, const char* loc, double gam, double rgaz, const int32_t* interf,
+                            int gh, int im, int jm, void* stream) {
+  BCD_PROLOGUE();
+  cudaError_t e = launch_bc_wall_iso(g, b, twall, gam, rgaz, ndir, w, wd, (cudaStream_t)stream);
+  g_launches += 1;
+  return e == cudaSuccess ? BC_OK : cuda_fail(e, "bcd_bc_wall_viscous_iso");
+}
+int bcd_bc_symmetry(double* w, double* wd, int ndir, const char* loc, const int32_t* interf, const double* nx, const double* ny, int gh,
+                    int im, int jm, void* stream) {
+  BCD_PROLOGUE();
+  if (!nx || !ny) return fail(BC_ERR_ARG, "nx / ny is null");
+  cudaError_t e = launch_bc_symmetry(g, b, ndir, w, wd, nx, ny, (cudaStream_t)stream);
+  g_launches += 1;
+  return e == cudaSuccess ? BC_OK : cuda_fail(e, "bcd_bc_symmetry");
+}
 int bcd_bc_no_reflexion(double* w, double* wd, int ndir, const double* wbd, const char* loc, const int32_t* interf, const double* nx,
                         const double* ny, double gam, int gh, int im, int jm, int lm, void* stream) {
   BCD_PROLOGUE();
@@ -392,6 +407,40 @@ int bc_bc_wall_viscous_adia_2d_d(double* w, double* wd, const char* loc, double 
   if (!wd) return fail(BC_ERR_ARG, "wd is null");
   return bc_host(w, wd, gh, im, jm,
                  [&](const GridDesc&, double* dw, double* dwd) { return bcd_bc_wall_viscous_adia(dw, dwd, 1, loc, gam, interf, gh, im, jm, nullptr); });
+}
+
+int bc_bc_wall_viscous_iso_2d(double* w, double twall, const char* loc, double gam, double rgaz, const int32_t* interf, int gh, int im,
+                              int jm) {
+  return bc_host(w, nullptr, gh, im, jm, [&](const GridDesc&, double* dw, double*) {
+    return bcd_bc_wall_viscous_iso(dw, nullptr, 0, twall, loc, gam, rgaz, interf, gh, im, jm, nullptr);
+  });
+}
+int bc_bc_wall_viscous_iso_2d_d(double* w, double* wd, double twall, const char* loc, double gam, double rgaz, const int32_t* interf, int gh,
+                                int im, int jm) {
+  if (!wd) return fail(BC_ERR_ARG, "wd is null");
+  return bc_host(w, wd, gh, im, jm, [&](const GridDesc&, double* dw, double* dwd) {
+    return bcd_bc_wall_viscous_iso(dw, dwd, 1, twall, loc, gam, rgaz, interf, gh, im, jm, nullptr);
+  });
+}
+
+static int symmetry_host(double* w, double* wd, const char* loc, const int32_t* interf, const double* nx, const double* ny, int gh, int im,
+                         int jm) {
+  return bc_host(w, wd, gh, im, jm, [&](const GridDesc& g, double* dw, double* dwd) -> int {
+    double* dnx = dbuf<double>(S_NX, g.sn * 2);
+    double* dny = dbuf<double>(S_NY, g.sn * 2);
+    if (!dnx || !dny) return fail(BC_ERR_ALLOC, "device allocation failed");
+    CK(cudaMemcpyAsync(dnx, nx, sizeof(double) * g.sn * 2, cudaMemcpyHostToDevice, 0));
+    CK(cudaMemcpyAsync(dny, ny, sizeof(double) * g.sn * 2, cudaMemcpyHostToDevice, 0));
+    return bcd_bc_symmetry(dw, dwd, wd ? 1 : 0, loc, interf, dnx, dny, gh, im, jm, nullptr);
+  });
+}
+int bc_bc_symmetry_2d(double* w, const char* loc, const int32_t* interf, const double* nx, const double* ny, int gh, int im, int jm) {
+  return symmetry_host(w, nullptr, loc, interf, nx, ny, gh, im, jm);
+}
+int bc_bc_symmetry_2d_d(double* w, double* wd, const char* loc, const int32_t* interf, const double* nx, const double* ny, int gh, int im,
+                        int jm) {
+  if (!wd) return fail(BC_ERR_ARG, "wd is null");
+  return symmetry_host(w, wd, loc, interf, nx, ny, gh, im, jm);
 }
 
 static int noref_host(double* w, double* wd, const double* wbd, const char* loc, const int32_t* interf, const double* nx, const double* ny,

@@ -3,7 +3,8 @@
 //
 // Reference (restated): srcfv/borders/init_2d.F:1-44 (interface decoding),
 //   bc_wall_viscous.F90:2-99, bc_no_reflexion.F90:8-152, bc_supandsubinlet.F90:2-171,
-//   bc_extrapolate.F90:39-71, jn_match.F90:3-66 and their Tapenade tangents in srcfv/tangent/.
+//   bc_extrapolate.F90:39-71, jn_match.F90:3-66, bc_wall_viscous_iso.F90:1-108, bc_symmetry.F90:1-79 (the last two: SURVEY.md 8(f3),
+//   the sensitivity driver's walls / half-domain cards) and their Tapenade tangents in srcfv/tangent/.
 // The tangent routines of the reference update BOTH w and wd ghosts, except the extrapolation whose
 // tangent writes wd only (tangent/bc_extrapolateo2_d.f90:63-65).
 #pragma once
@@ -115,6 +116,93 @@ __device__ void bc_wall_viscous_adia_line(const StateRW<N>& s, const BcLine& b, 
     ui = -u1;
     vi = -v1;
     wi = -w1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// isothermal viscous wall (bc_wall_viscous_iso.F90:37-105; tangent/bc_wall_viscous_iso_d.f90): wall pressure as for the adiabatic
+// wall, first ghost density from the wall temperature (roi = 2 pw / (rgaz twall) - roe), deeper ghost densities by linear
+// extrapolation of the two previous layers, velocities mirrored, ghost internal energy pi / (gam - 1) for every layer
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__device__ void bc_wall_viscous_iso_line(const StateRW<N>& s, const BcLine& b, double twall, double gam, double rgaz, int l /*0-based*/) {
+  using DT = TanOf<N>;
+  using VT = Var<DT>;
+  const int i = b.imin + l * b.j0 * b.j0;
+  const int j = b.jmin + l * b.i0 * b.i0;
+  const int i0 = b.i0, j0 = b.j0, gh = s.g.gh;
+  const double gam1 = gam - 1.0;
+  const double THIRD = 1.0 / 3.0;
+
+  VT roe = s.get(i, j, 0);
+  VT roem1 = 1.0 / roe;
+  VT ue = s.get(i, j, 1) * roem1;
+  VT ve = s.get(i, j, 2) * roem1;
+  VT we = s.get(i, j, 3) * roem1;
+  VT ve2 = ue * ue + ve * ve + we * we;
+  VT pe = gam1 * (s.get(i, j, 4) - 0.5 * roe * ve2);
+
+  VT roe1 = s.get(i + i0, j + j0, 0);
+  VT roe1m1 = 1.0 / roe1;
+  VT ue1 = s.get(i + i0, j + j0, 1) * roe1m1;
+  VT ve1 = s.get(i + i0, j + j0, 2) * roe1m1;
+  VT we1 = s.get(i + i0, j + j0, 3) * roe1m1;
+  VT ve21 = ue1 * ue1 + ve1 * ve1 + we1 * we1;
+  VT pe1 = gam1 * (s.get(i + i0, j + j0, 4) - 0.5 * roe1 * ve21);
+
+  VT pw = 1.125 * pe + (-0.125) * pe1;
+  VT roi = 2.0 * pw / (rgaz * twall) - roe;
+  VT pi = THIRD * (4.0 * pw - pe);
+  VT roiei = pi / gam1;
+  VT ui = -ue, vi = -ve, wi = -we;
+  VT prev = roe;   // density one layer towards the interior of the ghost being written (da = de - 1)
+
+  for (int de = 1; de <= gh; ++de) {
+    s.set(i - de * i0, j - de * j0, 0, roi);
+    s.set(i - de * i0, j - de * j0, 1, roi * ui);
+    s.set(i - de * i0, j - de * j0, 2, roi * vi);
+    s.set(i - de * i0, j - de * j0, 3, roi * wi);
+    s.set(i - de * i0, j - de * j0, 4, roiei + 0.5 * roi * (ui * ui + vi * vi + wi * wi));
+    VT next = 2.0 * roi - prev;
+    prev = roi;
+    roi = next;
+    VT rm1 = 1.0 / s.get(i + de * i0, j + de * j0, 0);
+    ui = -(s.get(i + de * i0, j + de * j0, 1) * rm1);
+    vi = -(s.get(i + de * i0, j + de * j0, 2) * rm1);
+    wi = -(s.get(i + de * i0, j + de * j0, 3) * rm1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// symmetry plane (bc_symmetry.F90:36-76; tangent/bc_symmetry_d.f90): ghost de mirrors interior layer de - 1, the velocity reflected
+// about the boundary-face normal, total energy corrected by the change of in-plane kinetic energy; rho w (plane 4) is NOT written
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__device__ void bc_symmetry_line(const StateRW<N>& s, const BcLine& b, const double* __restrict__ nx, const double* __restrict__ ny, int l) {
+  using DT = TanOf<N>;
+  using VT = Var<DT>;
+  const int i1 = b.i0 * b.i0, j1 = b.j0 * b.j0;
+  const int i = b.imin + l * j1;
+  const int j = b.jmin + l * i1;
+  const int i0 = b.i0, j0 = b.j0, gh = s.g.gh;
+  const double sens = (double)(i0 + j0);
+  const long long kn = s.g.nidx(i + b.high * i1, j + b.high * j1) + (long long)(b.kdir - 1) * s.g.sn;
+  const double nxloc = nx[kn], nyloc = ny[kn];
+  const double nsumi = 1.0 / ::sqrt(nxloc * nxloc + nyloc * nyloc);
+  const double nxnorm = nxloc * nsumi * sens, nynorm = nyloc * nsumi * sens;
+  for (int de = 1; de <= gh; ++de) {
+    const int da = de - 1;
+    const VT rho = s.get(i + da * i0, j + da * j0, 0), m1 = s.get(i + da * i0, j + da * j0, 1), m2 = s.get(i + da * i0, j + da * j0, 2);
+    const VT rhoinv = 1.0 / rho;
+    VT velx = m1 * rhoinv, vely = m2 * rhoinv;
+    const VT veln = velx * nxnorm + vely * nynorm;
+    velx = velx - 2.0 * veln * nxnorm;
+    vely = vely - 2.0 * veln * nynorm;
+    const VT g1 = rho * velx, g2 = rho * vely;
+    s.set(i - de * i0, j - de * j0, 0, rho);
+    s.set(i - de * i0, j - de * j0, 1, g1);
+    s.set(i - de * i0, j - de * j0, 2, g2);
+    s.set(i - de * i0, j - de * j0, 4, s.get(i + da * i0, j + da * j0, 4) - 0.5 * ((m1 * m1 + m2 * m2) / rho) + 0.5 * ((g1 * g1 + g2 * g2) / rho));
   }
 }
 

@@ -162,7 +162,7 @@ BC_HD Cell phase_a(const Tile& t, int tid, const Raw& in, long long k) {
   Cell c{};
   if (!in.ok) return c;
   c = cell_prims(t, in);
-  sm_put_cell(t, (ty + HALO) * SI + tx + HALO, c);
+  if (t.out1) sm_put_cell(t, (ty + HALO) * SI + tx + HALO, c);   // the d2/dz2 rows alone are cell-local
   if (t.out2 && t.i0 + tx <= t.i1 && t.j0 + ty <= t.j1) {
     double r[5];
     row_dz2(t, c, r);

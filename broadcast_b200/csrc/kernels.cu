@@ -122,6 +122,17 @@ __global__ void k_bc_extrap(StateRW<N> s, BcLine b) {
   if (l < b.lmax) bc_extrapolate_o2_line<N>(s, b, l);
 }
 
+template <int N>
+__global__ void k_bc_wall_iso(StateRW<N> s, BcLine b, double twall, double gam, double rgaz) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < b.lmax) bc_wall_viscous_iso_line<N>(s, b, twall, gam, rgaz, l);
+}
+template <int N>
+__global__ void k_bc_symmetry(StateRW<N> s, BcLine b, const double* nx, const double* ny) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < b.lmax) bc_symmetry_line<N>(s, b, nx, ny, l);
+}
+
 #define BC_DISPATCH(KERNEL, ...)                                                     \
   do {                                                                               \
     if (b.lmax <= 0) return cudaSuccess;                                             \
@@ -145,6 +156,14 @@ cudaError_t launch_bc_noref(const GridDesc& g, const BcLine& b, double gam, int 
 cudaError_t launch_bc_inlet(const GridDesc& g, const BcLine& b, double gam, int ndir, double* w, double* wd, const double* field, int lm,
                             const double* nx, const double* ny, cudaStream_t st) {
   BC_DISPATCH(k_bc_inlet, field, lm, nx, ny, gam);
+}
+cudaError_t launch_bc_wall_iso(const GridDesc& g, const BcLine& b, double twall, double gam, double rgaz, int ndir, double* w, double* wd,
+                               cudaStream_t st) {
+  BC_DISPATCH(k_bc_wall_iso, twall, gam, rgaz);
+}
+cudaError_t launch_bc_symmetry(const GridDesc& g, const BcLine& b, int ndir, double* w, double* wd, const double* nx, const double* ny,
+                               cudaStream_t st) {
+  BC_DISPATCH(k_bc_symmetry, nx, ny);
 }
 cudaError_t launch_bc_extrap(const GridDesc& g, const BcLine& b, int ndir, double* w, double* wd, cudaStream_t st) {
   BC_DISPATCH(k_bc_extrap);

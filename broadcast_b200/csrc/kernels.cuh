@@ -108,6 +108,10 @@ cudaError_t launch_bc_noref(const GridDesc& g, const BcLine& b, double gam, int 
 cudaError_t launch_bc_inlet(const GridDesc& g, const BcLine& b, double gam, int ndir, double* w, double* wd, const double* field, int lm,
                             const double* nx, const double* ny, cudaStream_t st);
 cudaError_t launch_bc_extrap(const GridDesc& g, const BcLine& b, int ndir, double* w, double* wd, cudaStream_t st);
+cudaError_t launch_bc_wall_iso(const GridDesc& g, const BcLine& b, double twall, double gam, double rgaz, int ndir, double* w, double* wd,
+                               cudaStream_t st);
+cudaError_t launch_bc_symmetry(const GridDesc& g, const BcLine& b, int ndir, double* w, double* wd, const double* nx, const double* ny,
+                               cudaStream_t st);
 
 // rectangular window copy (jn_match): arrays described by (ld, plane stride, origin offsets)
 struct Window {

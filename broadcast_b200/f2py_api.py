@@ -99,6 +99,16 @@ def build(backend):
         _check_cells(_state(w, "w"), im, jm, gh, "w")
         B("bc_wall_viscous_adia_2d", w, _loc(loc), gam, _interf(interf), int(gh), int(im), int(jm))
 
+    def bc_wall_viscous_iso_2d(w, twall, loc, gam, rgaz, interf, gh, im, jm):
+        """srcfv/borders/bc_wall_viscous_iso.F90:1 (w, twall, loc, gam, rgaz, interf, gh, im, jm)"""
+        _check_cells(_state(w, "w"), im, jm, gh, "w")
+        B("bc_wall_viscous_iso_2d", w, float(twall), _loc(loc), gam, rgaz, _interf(interf), int(gh), int(im), int(jm))
+
+    def bc_symmetry_2d(w, loc, interf, nx, ny, gh, im, jm):
+        """srcfv/borders/bc_symmetry.F90:1; call site handleBC.py:231 fsym(w, loc, interf, nx, ny, gh, im, jm)"""
+        _check_cells(_state(w, "w"), im, jm, gh, "w")
+        B("bc_symmetry_2d", w, _loc(loc), _interf(interf), _in(nx), _in(ny), int(gh), int(im), int(jm))
+
     def bc_no_reflexion_2d(w, wbd, loc, interf, nx, ny, gam, gh, im, jm, lm=None):
         _check_cells(_state(w, "w"), im, jm, gh, "w")
         wbd = _in(wbd)
@@ -137,6 +147,7 @@ def build(backend):
 
     f_bnd = types.SimpleNamespace(
         bc_wall_viscous_adia_2d=bc_wall_viscous_adia_2d, bc_no_reflexion_2d=bc_no_reflexion_2d,
+        bc_wall_viscous_iso_2d=bc_wall_viscous_iso_2d, bc_symmetry_2d=bc_symmetry_2d,
         bc_supandsubinlet_2d=bc_supandsubinlet_2d, bc_extrapolate_o2_2d=bc_extrapolate_o2_2d,
         jn_match_2d=jn_match_2d, jn_match_geom_2d=jn_match_geom_2d)
 
@@ -145,6 +156,18 @@ def build(backend):
         _check_cells(_state(w, "w"), im, jm, gh, "w")
         _check_cells(_state(wd, "wd"), im, jm, gh, "wd")
         B("bc_wall_viscous_adia_2d_d", w, wd, _loc(loc), gam, _interf(interf), int(gh), int(im), int(jm))
+
+    def bc_wall_viscous_iso_2d_d(w, wd, twall, loc, gam, rgaz, interf, gh, im, jm):
+        """srcfv/tangent/bc_wall_viscous_iso_d.f90 (w, wd, twall, loc, gam, rgaz, interf, gh, im, jm)"""
+        _check_cells(_state(w, "w"), im, jm, gh, "w")
+        _check_cells(_state(wd, "wd"), im, jm, gh, "wd")
+        B("bc_wall_viscous_iso_2d_d", w, wd, float(twall), _loc(loc), gam, rgaz, _interf(interf), int(gh), int(im), int(jm))
+
+    def bc_symmetry_2d_d(w, wd, loc, interf, nx, ny, gh, im, jm):
+        """srcfv/tangent/bc_symmetry_d.f90; call site handleBC.py:230 flinsym(w, wd, loc, interf, nx, ny, gh, im, jm)"""
+        _check_cells(_state(w, "w"), im, jm, gh, "w")
+        _check_cells(_state(wd, "wd"), im, jm, gh, "wd")
+        B("bc_symmetry_2d_d", w, wd, _loc(loc), _interf(interf), _in(nx), _in(ny), int(gh), int(im), int(jm))
 
     def bc_no_reflexion_2d_d(w, wd, wbd, loc, interf, nx, ny, gam, gh, im, jm, lm=None):
         _check_cells(_state(w, "w"), im, jm, gh, "w")
@@ -174,6 +197,7 @@ def build(backend):
         flux_num_dnc5_2d_d=_scheme_d("flux_num_dnc5_2d_d"),
         flux_num_dnc5_nowall_2d_d=_scheme_d("flux_num_dnc5_nowall_2d_d"),
         bc_wall_viscous_adia_2d_d=bc_wall_viscous_adia_2d_d, bc_no_reflexion_2d_d=bc_no_reflexion_2d_d,
+        bc_wall_viscous_iso_2d_d=bc_wall_viscous_iso_2d_d, bc_symmetry_2d_d=bc_symmetry_2d_d,
         bc_supandsubinlet_2d_d=bc_supandsubinlet_2d_d, bc_extrapolate_o2_2d_d=bc_extrapolate_o2_2d_d)
 
     # ------------------------------------------------------------------ f_geom

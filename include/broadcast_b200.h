@@ -83,6 +83,17 @@ int bc_bc_supandsubinlet_2d_d(double* w, double* wd, const char* loc, const int3
 int bc_bc_extrapolate_o2_2d(double* w, const char* loc, const int32_t* interf, int im, int jm, int gh, int em);
 int bc_bc_extrapolate_o2_2d_d(double* w, double* wd, const char* loc, const int32_t* interf, int im, int jm, int gh,
                               int em);
+/* isothermal wall and symmetry plane (the sensitivity driver's walls, half-domain cards card_cyl2d.py:105):
+ * srcfv/borders/bc_wall_viscous_iso.F90:1-108 + srcfv/tangent/bc_wall_viscous_iso_d.f90; srcfv/borders/bc_symmetry.F90:1-79 +
+ * srcfv/tangent/bc_symmetry_d.f90 (call site handleBC.py:228-231: fsym(w, loc, interf, nx, ny, gh, im, jm)) */
+int bc_bc_wall_viscous_iso_2d(double* w, double twall, const char* loc, double gam, double rgaz, const int32_t* interf, int gh,
+                              int im, int jm);
+int bc_bc_wall_viscous_iso_2d_d(double* w, double* wd, double twall, const char* loc, double gam, double rgaz,
+                                const int32_t* interf, int gh, int im, int jm);
+int bc_bc_symmetry_2d(double* w, const char* loc, const int32_t* interf, const double* nx, const double* ny, int gh, int im,
+                      int jm);
+int bc_bc_symmetry_2d_d(double* w, double* wd, const char* loc, const int32_t* interf, const double* nx, const double* ny,
+                        int gh, int im, int jm);
 /* srcfv/borders/jn_match.F90:3-66 (3-D arrays, em planes) and jn_match_geom.F90:7-69 (2-D arrays) */
 int bc_jn_match_2d(double* wr, const int32_t* prr, int gh1r, int gh2r, int gh3r, int gh4r, int imr, int jmr,
                    const double* wd, const int32_t* prd, int gh1d, int gh2d, int gh3d, int gh4d, int imd, int jmd,
@@ -198,6 +209,10 @@ int bcd_bc_supandsubinlet(double* w, double* wd, int ndir, const char* loc, cons
                           int gh, void* stream);
 int bcd_bc_extrapolate_o2(double* w, double* wd, int ndir, const char* loc, const int32_t* interf, int im, int jm,
                           int gh, void* stream);
+int bcd_bc_wall_viscous_iso(double* w, double* wd, int ndir, double twall, const char* loc, double gam, double rgaz,
+                            const int32_t* interf, int gh, int im, int jm, void* stream);
+int bcd_bc_symmetry(double* w, double* wd, int ndir, const char* loc, const int32_t* interf, const double* nx,
+                    const double* ny, int gh, int im, int jm, void* stream);
 int bcd_jn_match(double* wr, const int32_t* prr, int gh1r, int gh2r, int gh3r, int gh4r, int imr, int jmr,
                  const double* wd, const int32_t* prd, int gh1d, int gh2d, int gh3d, int gh4d, int imd, int jmd,
                  const int32_t* tr, int em, void* stream);

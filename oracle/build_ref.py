@@ -37,6 +37,10 @@ FILES = [
     ("srcfv/prepro/bc_general.f90", ["bc_general_2d"]),
     ("srcfv/prepro/jn_match.f90", ["jn_match_2d"]),
     ("srcfv/prepro/jn_match_geom.f90", ["jn_match_geom_2d"]),
+    ("srcfv/prepro/bc_wall_viscous_iso.f90", ["bc_wall_viscous_iso_2d"]),
+    ("srcfv/prepro/bc_symmetry.f90", ["bc_symmetry_2d"]),
+    ("srcfv/tangent/bc_wall_viscous_iso_d.f90", None),
+    ("srcfv/tangent/bc_symmetry_d.f90", None),
     ("srcfv/tangent/bc_wall_viscous_d.f90", None),
     ("srcfv/tangent/bc_no_reflexion_d.f90", None),
     ("srcfv/tangent/bc_supandsubinlet_d.f90", None),

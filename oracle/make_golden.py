@@ -85,6 +85,24 @@ def make_dz_tangent(kind, im, jm, R):
     return out
 
 
+def make_bcs(kind, im, jm, R):
+    """outputs of the reference's isothermal-wall and symmetry fills and their tangents (srcfv/prepro/bc_wall_viscous_iso.f90,
+    bc_symmetry.f90, srcfv/tangent/bc_wall_viscous_iso_d.f90, bc_symmetry_d.f90) on each side of the fixture's filled state"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_extra_bcs_cpu as T
+    c = H.make_case(kind, im, jm, R, with_w=True)
+    w0, _ = H.residual_sequence(R, c)
+    rng = np.random.default_rng(31)
+    d = np.asfortranarray(rng.standard_normal(w0.shape))
+    out = dict(kind=kind, im=im, jm=jm, gh=c.gh, seed=31, twall=T.TWALL)   # wd_in = default_rng(seed).standard_normal(w.shape)
+    for name in ("iso", "sym"):
+        for loc, interf in T.sides(c):
+            w, wd = w0.copy(order="F"), d.copy(order="F")
+            T.fill(R, name, c, w, loc, interf, wd)
+            out[f"{name}_{loc}_w"], out[f"{name}_{loc}_wd"] = T.strip(w, loc, c.gh).copy(), T.strip(wd, loc, c.gh).copy()
+    return out
+
+
 def main():
     if not refmods.available():
         sys.path.insert(0, HERE)
@@ -94,7 +112,15 @@ def main():
     R = refmods.make()
     os.makedirs(OUT, exist_ok=True)
     only_dz_tangent = "--dz-tangent" in sys.argv   # add the f_lindz fixtures without rewriting the others
+    only_bcs = "--bcs" in sys.argv                 # same for the isothermal-wall / symmetry fixtures
     for kind, im, jm in FIXTURES:
+        d = make_bcs(kind, im, jm, R)
+        p = os.path.join(OUT, "bcs", f"{kind}_{im}x{jm}.npz")
+        os.makedirs(os.path.dirname(p), exist_ok=True)
+        np.savez_compressed(p, **d)
+        print(p, os.path.getsize(p) // 1024, "KiB")
+        if only_bcs:
+            continue
         d = make_dz_tangent(kind, im, jm, R)
         p = os.path.join(OUT, "lindz", f"{kind}_{im}x{jm}.npz")
         os.makedirs(os.path.dirname(p), exist_ok=True)

@@ -1,0 +1,112 @@
+"""Pins the checker for the boundary fills of SURVEY.md 8(f3) (isothermal wall, symmetry plane): oracle/_ref =
+srcfv/prepro/bc_wall_viscous_iso.f90, bc_symmetry.f90 and their Tapenade tangents.  The reference ships no vectors for them, so:
+the tangent routine against central differences of the primal one, the defining invariants of each fill (mirror density / reflected
+velocity / wall temperature), and the committed golden outputs (tests/golden/bcs, oracle/make_golden.py --bcs) that the GPU tests
+compare the product with."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = sorted(glob.glob(os.path.join(HERE, "golden", "bcs", "*.npz")))
+TWALL = 1.3
+
+
+def sides(c):
+    """(loc, interf) of the four sides of the block, corner ownership as BROADCAST_npz.py:706-731"""
+    im, jm = c.im, c.jm
+    return [("Ilo", np.array([[1, 1], [1, jm]])), ("Ihi", np.array([[im, 1], [im, jm]])),
+            ("Jlo", np.array([[1, 1], [im, 1]])), ("Jhi", np.array([[1, jm], [im, jm]]))]
+
+
+def strip(a, loc, gh):
+    """the ghost layers a fill at `loc` may write (the fixtures store these only; everything else must stay as it was)"""
+    return {"Ilo": a[:gh], "Ihi": a[-gh:], "Jlo": a[:, :gh], "Jhi": a[:, -gh:]}[loc]
+
+
+def check_against_golden(g, name, loc, gh, w, wd, w_in, wd_in, tol):
+    assert np.all(H.rel_err(strip(w, loc, gh), g[f"{name}_{loc}_w"]) < tol), (name, loc)
+    assert np.all(H.rel_err(strip(wd, loc, gh), g[f"{name}_{loc}_wd"]) < tol), (name, loc)
+    for a, b in ((w, w_in), (wd, wd_in)):          # nothing outside the ghost strip of that side is touched
+        a, b = a.copy(), b.copy()
+        strip(a, loc, gh)[...] = 0.0
+        strip(b, loc, gh)[...] = 0.0
+        assert np.array_equal(a, b), (name, loc)
+
+
+def fill(mods, name, c, w, loc, interf, wd=None):
+    p = c.phys
+    if name == "iso":
+        if wd is None:
+            mods["f_bnd"].bc_wall_viscous_iso_2d(w, TWALL, loc, p["gam"], p["rgaz"], interf, c.gh, c.im, c.jm)
+        else:
+            mods["f_lin"].bc_wall_viscous_iso_2d_d(w, wd, TWALL, loc, p["gam"], p["rgaz"], interf, c.gh, c.im, c.jm)
+    else:
+        if wd is None:
+            mods["f_bnd"].bc_symmetry_2d(w, loc, interf, c.nx, c.ny, c.gh, c.im, c.jm)
+        else:
+            mods["f_lin"].bc_symmetry_2d_d(w, wd, loc, interf, c.nx, c.ny, c.gh, c.im, c.jm)
+
+
+@pytest.mark.parametrize("name", ["iso", "sym"])
+@pytest.mark.parametrize("kind,im,jm", [("bl", 20, 12), ("cyl", 24, 12)])
+def test_tangent_fill_is_the_derivative_of_the_primal_fill(ref, name, kind, im, jm):
+    c = H.make_case(kind, im, jm, ref, with_w=True)
+    w0, _ = H.residual_sequence(ref, c)
+    rng = np.random.default_rng(2)
+    d = np.asfortranarray(rng.standard_normal(w0.shape) * 1e-2 * np.abs(w0).max(axis=(0, 1)))
+    for loc, interf in sides(c):
+        w, wd = w0.copy(order="F"), d.copy(order="F")
+        fill(ref, name, c, w, loc, interf, wd)
+        wp, wm = np.asfortranarray(w0 + 1e-5 * d), np.asfortranarray(w0 - 1e-5 * d)
+        fill(ref, name, c, wp, loc, interf)
+        fill(ref, name, c, wm, loc, interf)
+        fd = (wp - wm) / 2e-5
+        assert np.all(H.rel_err(fd, wd) < 1e-7), (name, loc, H.rel_err(fd, wd))
+        w1 = w0.copy(order="F")
+        fill(ref, name, c, w1, loc, interf)
+        assert np.array_equal(w1, w)          # the tangent routine also writes the primal ghosts, identically
+
+
+def test_fill_invariants(ref):
+    c = H.make_case("bl", 20, 12, ref, with_w=True)
+    w0, _ = H.residual_sequence(ref, c)
+    g, p = c.gh, c.phys
+    # symmetry at Jlo: ghost de mirrors row de-1; density equal, wall-normal momentum reversed (the wall is y = 0: normal = e_y)
+    w = w0.copy(order="F")
+    fill(ref, "sym", c, w, "Jlo", sides(c)[2][1])
+    for de in range(1, g + 1):
+        gi, ii = g - de, g + de - 1
+        assert np.array_equal(w[g:-g, gi, 0], w[g:-g, ii, 0])
+        assert np.allclose(w[g:-g, gi, 2], -w[g:-g, ii, 2], rtol=1e-13, atol=0)
+        assert np.allclose(w[g:-g, gi, 1], w[g:-g, ii, 1], rtol=1e-13, atol=1e-300)
+        assert np.array_equal(w[g:-g, gi, 3], w0[g:-g, gi, 3])        # rho w is not written
+    # isothermal wall at Jlo: mean of the first ghost and first interior density is pw / (rgaz twall)
+    w = w0.copy(order="F")
+    fill(ref, "iso", c, w, "Jlo", sides(c)[2][1])
+    def pres(q):
+        return (p["gam"] - 1.0) * (q[..., 4] - 0.5 * (q[..., 1] ** 2 + q[..., 2] ** 2 + q[..., 3] ** 2) / q[..., 0])
+    pw = 1.125 * pres(w0[g:-g, g]) - 0.125 * pres(w0[g:-g, g + 1])
+    assert np.allclose(0.5 * (w[g:-g, g - 1, 0] + w0[g:-g, g, 0]), pw / (p["rgaz"] * TWALL), rtol=1e-13)
+    assert np.allclose(w[g:-g, g - 1, 1] / w[g:-g, g - 1, 0], -w0[g:-g, g, 1] / w0[g:-g, g, 0], rtol=1e-13, atol=1e-300)
+
+
+def test_bc_golden_present():
+    assert len(GOLD) >= 2
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_ref_reproduces_the_bc_golden(ref, path):
+    g = np.load(path)
+    c = H.make_case(str(g["kind"]), int(g["im"]), int(g["jm"]), ref, with_w=True)
+    w0, _ = H.residual_sequence(ref, c)
+    for name in ("iso", "sym"):
+        for loc, interf in sides(c):
+            d = np.asfortranarray(np.random.default_rng(int(g["seed"])).standard_normal(w0.shape))
+            w, wd = w0.copy(order="F"), d.copy(order="F")
+            fill(ref, name, c, w, loc, interf, wd)
+            check_against_golden(g, name, loc, c.gh, w, wd, w0, d, 1e-13)

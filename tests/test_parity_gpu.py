@@ -723,3 +723,43 @@ def test_dz_tangent_golden(gpu, name):
         z, zd = a.zeros_state(), a.zeros_state()
         getattr(gpu["f_lindz"], fn)(z, zd, wa, wd0, wd, *_dz_args(a))
         assert np.all(H.rel_err(zd, g[key]) < TOL), (fn, H.rel_err(zd, g[key]))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# boundary fills of SURVEY.md 8(f3): isothermal wall, symmetry plane (primal and tangent), every side of the block
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["iso", "sym"])
+@pytest.mark.parametrize("kind,im,jm", [("bl", 60, 40), ("cyl", 70, 40), ("bl", 7, 7)])
+def test_isothermal_wall_and_symmetry_fills(gpu, ref, name, kind, im, jm):
+    import test_extra_bcs_cpu as T
+    a = H.make_case(kind, im, jm, gpu, with_w=True)
+    b = H.make_case(kind, im, jm, ref, with_w=True)
+    wa0, _ = H.residual_sequence(gpu, a)
+    wb0, _ = H.residual_sequence(ref, b)
+    d = np.asfortranarray(np.random.default_rng(9).standard_normal(wa0.shape))
+    for loc, interf in T.sides(a):
+        wa, wb = wa0.copy(order="F"), wb0.copy(order="F")
+        T.fill(gpu, name, a, wa, loc, interf)
+        T.fill(ref, name, b, wb, loc, interf)
+        assert np.all(H.rel_err(wa, wb) < TOL), (loc, H.rel_err(wa, wb))
+        assert not np.array_equal(wa, wa0)
+        wa, wb, da, db = wa0.copy(order="F"), wb0.copy(order="F"), d.copy(order="F"), d.copy(order="F")
+        T.fill(gpu, name, a, wa, loc, interf, da)
+        T.fill(ref, name, b, wb, loc, interf, db)
+        assert np.all(H.rel_err(wa, wb) < TOL) and np.all(H.rel_err(da, db) < TOL), (loc, H.rel_err(da, db))
+
+
+@pytest.mark.parametrize("fixture", ["bl_24x16", "cyl_28x16"])
+def test_isothermal_wall_and_symmetry_golden(gpu, fixture):
+    """product vs the committed outputs of the reference's routines (tests/golden/bcs, oracle/make_golden.py --bcs)"""
+    import os
+    import test_extra_bcs_cpu as T
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "bcs", fixture + ".npz"))
+    a = H.make_case(str(g["kind"]), int(g["im"]), int(g["jm"]), gpu, with_w=True)
+    w0, _ = H.residual_sequence(gpu, a)
+    d = np.asfortranarray(np.random.default_rng(int(g["seed"])).standard_normal(w0.shape))
+    for name in ("iso", "sym"):
+        for loc, interf in T.sides(a):
+            w, wd = w0.copy(order="F"), d.copy(order="F")
+            T.fill(gpu, name, a, w, loc, interf, wd)
+            T.check_against_golden(g, name, loc, a.gh, w, wd, w0, d, TOL)
