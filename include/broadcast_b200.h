@@ -317,6 +317,31 @@ int bcd_hybrid_csr_fill(int32_t* indices, double* data, int32_t* cursor, const l
 int bcd_apply_bcs(double* w, const double* nx, const double* ny, double gam, int gh, int im, int jm,
                   const bc_desc_t* bcs, int nbcs, void* stream);
 
+/* =====================================================================================================
+ * Resident-mode context for hosts without a device-memory library of their own (C, Fortran via ISO_C_BINDING; INTEGRATION.md
+ * section 3): one block stays on the device between calls.  All array arguments are HOST arrays in the layout of the bc_* entry
+ * points (bc_desc_t.table included: field(lm,gh,5) / wbd(lm,5) Fortran arrays, copied at set time).  Sequence of the reference
+ * drivers: create -> set_geometry (after f_geom.computegeom_2d) -> set_bcs -> upload_state -> residual [-> norms / download_residual]
+ * (BROADCAST_npz.py:1018-1035) -> jacobian_csr -> download_csr (BROADCAST_npz.py:1068-1127, 129-135, 1206-1209;
+ * misc/PETSc_func.py:71-95).  Every number comes from the bcd_* entry points above.
+ * ===================================================================================================== */
+typedef struct bcast_ctx bcast_ctx_t;
+int bcast_ctx_create(bcast_ctx_t** ctx, int im, int jm, int gh, double cp, double cv, double prandtl, double gam, double rgaz,
+                     double cs, double muref, double tref, double s_suth, double k2, double k4, int wall);
+int bcast_ctx_destroy(bcast_ctx_t* ctx);
+int bcast_ctx_set_geometry(bcast_ctx_t* ctx, const double* nx, const double* ny, const double* vol, const double* volf);
+int bcast_ctx_set_bcs(bcast_ctx_t* ctx, const bc_desc_t* bcs, int nbcs);
+int bcast_ctx_upload_state(bcast_ctx_t* ctx, const double* w);
+int bcast_ctx_download_state(bcast_ctx_t* ctx, double* w);
+int bcast_ctx_apply_bcs(bcast_ctx_t* ctx);
+int bcast_ctx_residual(bcast_ctx_t* ctx);
+int bcast_ctx_download_residual(bcast_ctx_t* ctx, double* res);
+int bcast_ctx_norms(bcast_ctx_t* ctx, double* norm5, double* ninf5);
+/* coefdiag: host (im,jm) array or NULL; scatter_kind 1 = jv_relaxed, 3 = jv_relaxed_withjn, -1 = by the boundary list */
+int bcast_ctx_jacobian_csr(bcast_ctx_t* ctx, const double* coefdiag, int divide_by_vol, double thresh, int scatter_kind,
+                           long long* nnz);
+int bcast_ctx_download_csr(bcast_ctx_t* ctx, long long* indptr, int32_t* indices, double* data);
+
 #ifdef __cplusplus
 }
 #endif

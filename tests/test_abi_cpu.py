@@ -73,3 +73,16 @@ print("ok")
 '''
     out = subprocess.run([sys.executable, "-c", code, os.path.join(root, "broadcast_b200", "dropin")], capture_output=True, text=True, cwd="/tmp")
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def test_context_api_fails_loudly_without_a_device():
+    """no CPU fallback: bcast_ctx_create reports BC_ERR_NODEV (-2) when there is no GPU (skipped on a GPU box)"""
+    import ctypes
+    from broadcast_b200 import _lib
+    if _lib.device_count() > 0:
+        import pytest
+        pytest.skip("a CUDA device is present")
+    h = ctypes.c_void_p()
+    D = ctypes.c_double
+    rc = _lib.lib().bcast_ctx_create(ctypes.byref(h), 10, 10, 3, *[D(1.0)] * 11, 1)
+    assert rc == -2 and not h.value

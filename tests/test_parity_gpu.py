@@ -763,3 +763,58 @@ def test_isothermal_wall_and_symmetry_golden(gpu, fixture):
             w, wd = w0.copy(order="F"), d.copy(order="F")
             T.fill(gpu, name, a, w, loc, interf, wd)
             T.check_against_golden(g, name, loc, a.gh, w, wd, w0, d, TOL)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# resident C-ABI context (bcast_ctx_*): what a C / Fortran host binds; host arrays in and out, no torch memory
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,im,jm", [("bl", 60, 40), ("cyl", 70, 40)])
+def test_c_abi_context_residual_and_norms(gpu, ref, kind, im, jm):
+    from broadcast_b200.cabi_ctx import Context
+    a = H.make_case(kind, im, jm, gpu, with_w=True)
+    b = H.make_case(kind, im, jm, ref, with_w=True)
+    wb, rb = H.residual_sequence(ref, b)
+    ctx = Context(a)
+    ctx.upload_state(a.w)
+    ra = ctx.residual()
+    wa = ctx.state()
+    assert np.all(H.rel_err(wa, wb) < TOL) and np.all(H.rel_err(ra, rb) < TOL), H.rel_err(ra, rb)
+    _, rp = H.residual_sequence(gpu, a)          # f2py-shaped path of the product: same kernels, same bits
+    assert np.array_equal(ra, rp)
+    n2, ninf = ctx.norms()
+    m2, minf = ref["f_norm"].compute_norml2inf(rb, im, jm, b.gh)
+    assert np.allclose(n2, m2, rtol=1e-12) and np.allclose(ninf, minf, rtol=1e-12)
+    ctx.close()
+
+
+@pytest.mark.parametrize("kind,im,jm", [("bl", 48, 26), ("cyl", 42, 30)])
+def test_c_abi_context_jacobian_csr(gpu, ref, kind, im, jm):
+    """bcast_ctx_jacobian_csr = the Python resident path (jacobian_hybrid + to_csr_device) array for array, and the reference's
+    colour loop + remove_zero_jac + csr_matrix + division by the volume to TOL"""
+    import scipy.sparse as sp
+    from broadcast_b200.cabi_ctx import Context
+    from broadcast_b200.resident import Block, jacobian_hybrid
+    a = H.make_case(kind, im, jm, gpu, with_w=True)
+    coef = np.asfortranarray(np.random.default_rng(3).uniform(0.5, 1.5, size=(im, jm)))
+    ctx = Context(a)
+    ctx.upload_state(a.w)
+    indptr, indices, data = ctx.jacobian_csr(coefdiag=coef, divide_by_vol=True)
+    blk = Block(a)
+    blk.apply_bcs()
+    hj = jacobian_hybrid(blk, coefdiag=coef)
+    p2, i2, d2 = (t.cpu().numpy() for t in hj.to_csr_device(divide_by_vol=True))
+    assert np.array_equal(indptr, p2) and np.array_equal(indices, i2) and np.array_equal(data, d2)
+    # against the reference loop on the CPU
+    b = H.make_case(kind, im, jm, ref, with_w=True)
+    wb, _ = H.residual_sequence(ref, b)
+    jac, ia, ja = H.jacobian_sequence(ref, b, wb, None, coef)
+    keep = np.abs(jac) > 2e-16
+    n = 5 * im * jm
+    A = sp.csr_matrix((jac[keep], (ia[keep], ja[keep])), shape=(n, n))
+    vol = b.vol[b.gh:-b.gh, b.gh:-b.gh]
+    rowvol = np.repeat(vol.reshape(-1), 5)      # row = e + 5 (j-1) + 5 jm (i-1): C-order ravel of (i, j), 5 equations each
+    A = sp.diags(1.0 / rowvol) @ A
+    B = sp.csr_matrix((data, indices, indptr), shape=(n, n))
+    diff = abs(A - B)
+    assert diff.max() <= TOL * abs(A).max(), diff.max() / abs(A).max()
+    ctx.close()
