@@ -68,7 +68,7 @@ int bc_flux_num_dnc5_nowall_2d_d(double* residu, double* residud, const double* 
                                  double prandtl, double gam, double rgaz, double cs, double muref, double tref,
                                  double s_suth, double k2, double k4, int im, int jm);
 
-/* ---- boundary fills (f_bnd.*) and their tangents (f_lin.*_d): srcfv/borders/*.F90, srcfv/tangent/bc_*_d.f90 */
+/* ---- boundary fills (f_bnd.*) and their tangents (f_lin.*_d): srcfv/borders/ (.F90), srcfv/tangent/bc_*_d.f90 */
 int bc_bc_wall_viscous_adia_2d(double* w, const char* loc, double gam, const int32_t* interf, int gh, int im, int jm);
 int bc_bc_wall_viscous_adia_2d_d(double* w, double* wd, const char* loc, double gam, const int32_t* interf, int gh,
                                  int im, int jm);
