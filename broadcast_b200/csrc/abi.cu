@@ -303,12 +303,20 @@ int bcd_bc_wall_viscous_iso(double* w, double* wd, int ndir, double twall, const
   return e == cudaSuccess ? BC_OK : cuda_fail(e, "bcd_bc_wall_viscous_iso");
 }
 int bcd_bc_symmetry(double* w, double* wd, int ndir, const char* loc, const int32_t* interf, const double* nx, const double* ny, int gh,
-                    int im, int jm, void* stream) {
+                    int im, int jm, int anti, void* stream) {
   BCD_PROLOGUE();
   if (!nx || !ny) return fail(BC_ERR_ARG, "nx / ny is null");
-  cudaError_t e = launch_bc_symmetry(g, b, ndir, w, wd, nx, ny, (cudaStream_t)stream);
+  cudaError_t e = launch_bc_symmetry(g, b, ndir, w, wd, nx, ny, anti != 0, (cudaStream_t)stream);
   g_launches += 1;
   return e == cudaSuccess ? BC_OK : cuda_fail(e, "bcd_bc_symmetry");
+}
+int bcd_bc_pressure(double* w, double* wd, int ndir, const char* loc, const int32_t* interf, double pext, int noref, double gam,
+                    const double* nx, const double* ny, int im, int jm, int gh, void* stream) {
+  BCD_PROLOGUE();
+  if (!nx || !ny) return fail(BC_ERR_ARG, "nx / ny is null");
+  cudaError_t e = launch_bc_pressure(g, b, pext, noref != 0, gam, ndir, w, wd, nx, ny, (cudaStream_t)stream);
+  g_launches += 1;
+  return e == cudaSuccess ? BC_OK : cuda_fail(e, "bcd_bc_pressure");
 }
 int bcd_bc_no_reflexion(double* w, double* wd, int ndir, const double* wbd, const char* loc, const int32_t* interf, const double* nx,
                         const double* ny, double gam, int gh, int im, int jm, int lm, void* stream) {
@@ -424,15 +432,44 @@ int bc_bc_wall_viscous_iso_2d_d(double* w, double* wd, double twall, const char*
 }
 
 static int symmetry_host(double* w, double* wd, const char* loc, const int32_t* interf, const double* nx, const double* ny, int gh, int im,
-                         int jm) {
+                         int jm, int anti = 0) {
   return bc_host(w, wd, gh, im, jm, [&](const GridDesc& g, double* dw, double* dwd) -> int {
     double* dnx = dbuf<double>(S_NX, g.sn * 2);
     double* dny = dbuf<double>(S_NY, g.sn * 2);
     if (!dnx || !dny) return fail(BC_ERR_ALLOC, "device allocation failed");
     CK(cudaMemcpyAsync(dnx, nx, sizeof(double) * g.sn * 2, cudaMemcpyHostToDevice, 0));
     CK(cudaMemcpyAsync(dny, ny, sizeof(double) * g.sn * 2, cudaMemcpyHostToDevice, 0));
-    return bcd_bc_symmetry(dw, dwd, wd ? 1 : 0, loc, interf, dnx, dny, gh, im, jm, nullptr);
+    return bcd_bc_symmetry(dw, dwd, wd ? 1 : 0, loc, interf, dnx, dny, gh, im, jm, anti, nullptr);
   });
+}
+int bc_bc_antisymmetry_2d(double* w, const char* loc, const int32_t* interf, const double* nx, const double* ny, int gh, int im, int jm) {
+  return symmetry_host(w, nullptr, loc, interf, nx, ny, gh, im, jm, 1);
+}
+int bc_bc_antisymmetry_2d_d(double* w, double* wd, const char* loc, const int32_t* interf, const double* nx, const double* ny, int gh,
+                            int im, int jm) {
+  if (!wd) return fail(BC_ERR_ARG, "wd is null");
+  return symmetry_host(w, wd, loc, interf, nx, ny, gh, im, jm, 1);
+}
+static int pressure_host(double* w, double* wd, const char* loc, const int32_t* interf, double pext, int noref, double gam, const double* nx,
+                         const double* ny, int im, int jm, int gh, int em) {
+  if (em != 5) return fail(BC_ERR_UNSUPPORTED, "bc_pressure_2d: em must be 5 (no transported scalars on this path)");
+  return bc_host(w, wd, gh, im, jm, [&](const GridDesc& g, double* dw, double* dwd) -> int {
+    double* dnx = dbuf<double>(S_NX, g.sn * 2);
+    double* dny = dbuf<double>(S_NY, g.sn * 2);
+    if (!dnx || !dny) return fail(BC_ERR_ALLOC, "device allocation failed");
+    CK(cudaMemcpyAsync(dnx, nx, sizeof(double) * g.sn * 2, cudaMemcpyHostToDevice, 0));
+    CK(cudaMemcpyAsync(dny, ny, sizeof(double) * g.sn * 2, cudaMemcpyHostToDevice, 0));
+    return bcd_bc_pressure(dw, dwd, wd ? 1 : 0, loc, interf, pext, noref, gam, dnx, dny, im, jm, gh, nullptr);
+  });
+}
+int bc_bc_pressure_2d(double* w, const char* loc, const int32_t* interf, double pext, int noref, double gam, const double* nx,
+                      const double* ny, int im, int jm, int gh, int em) {
+  return pressure_host(w, nullptr, loc, interf, pext, noref, gam, nx, ny, im, jm, gh, em);
+}
+int bc_bc_pressure_2d_d(double* w, double* wd, const char* loc, const int32_t* interf, double pext, int noref, double gam, const double* nx,
+                        const double* ny, int im, int jm, int gh, int em) {
+  if (!wd) return fail(BC_ERR_ARG, "wd is null");
+  return pressure_host(w, wd, loc, interf, pext, noref, gam, nx, ny, im, jm, gh, em);
 }
 int bc_bc_symmetry_2d(double* w, const char* loc, const int32_t* interf, const double* nx, const double* ny, int gh, int im, int jm) {
   return symmetry_host(w, nullptr, loc, interf, nx, ny, gh, im, jm);

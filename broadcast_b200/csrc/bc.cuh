@@ -175,9 +175,10 @@ __device__ void bc_wall_viscous_iso_line(const StateRW<N>& s, const BcLine& b, d
 
 // ---------------------------------------------------------------------------------------------
 // symmetry plane (bc_symmetry.F90:36-76; tangent/bc_symmetry_d.f90): ghost de mirrors interior layer de - 1, the velocity reflected
-// about the boundary-face normal, total energy corrected by the change of in-plane kinetic energy; rho w (plane 4) is NOT written
+// about the boundary-face normal, total energy corrected by the change of in-plane kinetic energy; rho w (plane 4) is NOT written.
+// ANTI: bc_antisymmetry.F90:40-49 (tangent/bc_antisymmetry_d.f90) -- same reflection, ghost = (-rho, -(rho u'), rho v', -(E'))
 // ---------------------------------------------------------------------------------------------
-template <int N>
+template <int N, bool ANTI = false>
 __device__ void bc_symmetry_line(const StateRW<N>& s, const BcLine& b, const double* __restrict__ nx, const double* __restrict__ ny, int l) {
   using DT = TanOf<N>;
   using VT = Var<DT>;
@@ -198,11 +199,94 @@ __device__ void bc_symmetry_line(const StateRW<N>& s, const BcLine& b, const dou
     const VT veln = velx * nxnorm + vely * nynorm;
     velx = velx - 2.0 * veln * nxnorm;
     vely = vely - 2.0 * veln * nynorm;
-    const VT g1 = rho * velx, g2 = rho * vely;
-    s.set(i - de * i0, j - de * j0, 0, rho);
-    s.set(i - de * i0, j - de * j0, 1, g1);
-    s.set(i - de * i0, j - de * j0, 2, g2);
-    s.set(i - de * i0, j - de * j0, 4, s.get(i + da * i0, j + da * j0, 4) - 0.5 * ((m1 * m1 + m2 * m2) / rho) + 0.5 * ((g1 * g1 + g2 * g2) / rho));
+    if constexpr (!ANTI) {
+      const VT g1 = rho * velx, g2 = rho * vely;
+      s.set(i - de * i0, j - de * j0, 0, rho);
+      s.set(i - de * i0, j - de * j0, 1, g1);
+      s.set(i - de * i0, j - de * j0, 2, g2);
+      s.set(i - de * i0, j - de * j0, 4, s.get(i + da * i0, j + da * j0, 4) - 0.5 * ((m1 * m1 + m2 * m2) / rho) + 0.5 * ((g1 * g1 + g2 * g2) / rho));
+    } else {
+      const VT g0 = -rho, g1 = -(rho * velx), g2 = rho * vely;
+      s.set(i - de * i0, j - de * j0, 0, g0);
+      s.set(i - de * i0, j - de * j0, 1, g1);
+      s.set(i - de * i0, j - de * j0, 2, g2);
+      s.set(i - de * i0, j - de * j0, 4, -(s.get(i + da * i0, j + da * j0, 4) - 0.5 * ((m1 * m1 + m2 * m2) / rho) + 0.5 * ((g1 * g1 + g2 * g2) / g0)));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pressure outlet (bc_pressure.F90:30-112; tangent/bc_pressure_d.f90): exterior state from the imposed pressure pext along the
+// outgoing characteristics of the boundary cell; with noref the characteristic blend of bc_no_reflexion between the cell state and
+// that exterior state (switches piecewise constant, not differentiated); every ghost layer gets the same state
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__device__ void bc_pressure_line(const StateRW<N>& s, const BcLine& b, double pext, bool noref, double gam, const double* __restrict__ nx,
+                                 const double* __restrict__ ny, int l) {
+  using DT = TanOf<N>;
+  using VT = Var<DT>;
+  const int i1 = b.i0 * b.i0, j1 = b.j0 * b.j0;
+  const int i = b.imin + l * j1;
+  const int j = b.jmin + l * i1;
+  const int i0 = b.i0, j0 = b.j0, gh = s.g.gh;
+  const double gam1 = gam - 1.0;
+  const double sens = (double)(i0 + j0);
+  const long long kn = s.g.nidx(i + b.high * i1, j + b.high * j1) + (long long)(b.kdir - 1) * s.g.sn;
+  const double nxloc = nx[kn], nyloc = ny[kn];
+  const double nsumi = 1.0 / ::sqrt(nxloc * nxloc + nyloc * nyloc);
+  const double nxnorm = nxloc * nsumi * sens, nynorm = nyloc * nsumi * sens;
+
+  const VT ro0 = s.get(i, j, 0), w2 = s.get(i, j, 1), w3 = s.get(i, j, 2), w4 = s.get(i, j, 3), w5 = s.get(i, j, 4);
+  const VT ro0m1 = 1.0 / ro0;
+  const VT uu = w2 * ro0m1, vv = w3 * ro0m1, ww = w4 * ro0m1;
+  const VT p0 = gam1 * (w5 - 0.5 * ro0 * (uu * uu + vv * vv + ww * ww));
+  const VT c20 = gam * p0 * ro0m1;
+  const VT c20m1 = 1.0 / c20;
+  const VT roc0 = ro0 * sqrt(c20);
+  const VT roc0m1 = 1.0 / roc0;
+  const VT ros = ro0, us = uu, vs = vv, ws = ww;
+  const VT ps = gam1 * (w5 - ros * 0.5 * (us * us + vs * vs + ws * ws));
+  const VT vns = us * nxnorm + vs * nynorm;
+  const VT uts = us - vns * nxnorm, vts = vs - vns * nynorm;
+  const VT dp = pext - ps;
+  const VT rod = ros + dp * c20m1;
+  const VT vnd = vns + dp * roc0m1;
+  const VT ud = uts + vnd * nxnorm, vd = vts + vnd * nynorm;
+  VT ro, rou, rov, row, roe;
+  if (noref) {
+    const VT rovn0 = w2 * nxnorm + w3 * nynorm;
+    const double epsm = 0.5 + fsign(0.5, roc0.v - rovn0.v);
+    const double eps0 = 0.5 + fsign(0.5, -rovn0.v);
+    const double epsp = 0.5 + fsign(0.5, -roc0.v - rovn0.v);
+    const VT ut = eps0 * uts + (1.0 - eps0) * uts;
+    const VT vt = eps0 * vts + (1.0 - eps0) * vts;
+    const VT wt = eps0 * ws + (1.0 - eps0) * ws;
+    const VT am = epsm * (ps - roc0 * vns) + (1.0 - epsm) * (pext - roc0 * vnd);
+    const VT ap = epsp * (ps + roc0 * vns) + (1.0 - epsp) * (pext + roc0 * vnd);
+    const VT vn = (ap - am) * 0.5 * roc0m1;
+    const VT p = (ap + am) * 0.5;
+    const VT bs = (p - ps) * ro0 * ro0 * roc0m1 * roc0m1 + ros;
+    const VT b0 = (p - pext) * ro0 * ro0 * roc0m1 * roc0m1 + rod;
+    ro = eps0 * bs + (1.0 - eps0) * b0;
+    roe = p / gam1;
+    rou = ro * (ut + vn * nxnorm);
+    rov = ro * (vt + vn * nynorm);
+    row = ro * wt;
+  } else {
+    ro = rod;
+    rou = ro * ud;
+    rov = ro * vd;
+    row = ro * ws;
+    roe = VT{pext / gam1, DT{}};
+  }
+  const VT rom1 = 1.0 / ro;
+  const VT etot = roe + 0.5 * rom1 * (rou * rou + rov * rov + row * row);
+  for (int de = 1; de <= gh; ++de) {
+    s.set(i - de * i0, j - de * j0, 0, ro);
+    s.set(i - de * i0, j - de * j0, 1, rou);
+    s.set(i - de * i0, j - de * j0, 2, rov);
+    s.set(i - de * i0, j - de * j0, 3, row);
+    s.set(i - de * i0, j - de * j0, 4, etot);
   }
 }
 

@@ -128,9 +128,18 @@ __global__ void k_bc_wall_iso(StateRW<N> s, BcLine b, double twall, double gam, 
   if (l < b.lmax) bc_wall_viscous_iso_line<N>(s, b, twall, gam, rgaz, l);
 }
 template <int N>
-__global__ void k_bc_symmetry(StateRW<N> s, BcLine b, const double* nx, const double* ny) {
+__global__ void k_bc_symmetry(StateRW<N> s, BcLine b, const double* nx, const double* ny, bool anti) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l < b.lmax) bc_symmetry_line<N>(s, b, nx, ny, l);
+  if (l >= b.lmax) return;
+  if (anti)
+    bc_symmetry_line<N, true>(s, b, nx, ny, l);
+  else
+    bc_symmetry_line<N, false>(s, b, nx, ny, l);
+}
+template <int N>
+__global__ void k_bc_pressure(StateRW<N> s, BcLine b, double pext, bool noref, double gam, const double* nx, const double* ny) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < b.lmax) bc_pressure_line<N>(s, b, pext, noref, gam, nx, ny, l);
 }
 
 #define BC_DISPATCH(KERNEL, ...)                                                     \
@@ -162,8 +171,12 @@ cudaError_t launch_bc_wall_iso(const GridDesc& g, const BcLine& b, double twall,
   BC_DISPATCH(k_bc_wall_iso, twall, gam, rgaz);
 }
 cudaError_t launch_bc_symmetry(const GridDesc& g, const BcLine& b, int ndir, double* w, double* wd, const double* nx, const double* ny,
-                               cudaStream_t st) {
-  BC_DISPATCH(k_bc_symmetry, nx, ny);
+                               bool anti, cudaStream_t st) {
+  BC_DISPATCH(k_bc_symmetry, nx, ny, anti);
+}
+cudaError_t launch_bc_pressure(const GridDesc& g, const BcLine& b, double pext, bool noref, double gam, int ndir, double* w, double* wd,
+                               const double* nx, const double* ny, cudaStream_t st) {
+  BC_DISPATCH(k_bc_pressure, pext, noref, gam, nx, ny);
 }
 cudaError_t launch_bc_extrap(const GridDesc& g, const BcLine& b, int ndir, double* w, double* wd, cudaStream_t st) {
   BC_DISPATCH(k_bc_extrap);

@@ -111,7 +111,9 @@ cudaError_t launch_bc_extrap(const GridDesc& g, const BcLine& b, int ndir, doubl
 cudaError_t launch_bc_wall_iso(const GridDesc& g, const BcLine& b, double twall, double gam, double rgaz, int ndir, double* w, double* wd,
                                cudaStream_t st);
 cudaError_t launch_bc_symmetry(const GridDesc& g, const BcLine& b, int ndir, double* w, double* wd, const double* nx, const double* ny,
-                               cudaStream_t st);
+                               bool anti, cudaStream_t st);
+cudaError_t launch_bc_pressure(const GridDesc& g, const BcLine& b, double pext, bool noref, double gam, int ndir, double* w, double* wd,
+                               const double* nx, const double* ny, cudaStream_t st);
 
 // rectangular window copy (jn_match): arrays described by (ld, plane stride, origin offsets)
 struct Window {

@@ -109,6 +109,17 @@ def build(backend):
         _check_cells(_state(w, "w"), im, jm, gh, "w")
         B("bc_symmetry_2d", w, _loc(loc), _interf(interf), _in(nx), _in(ny), int(gh), int(im), int(jm))
 
+    def bc_antisymmetry_2d(w, loc, interf, nx, ny, gh, im, jm):
+        """srcfv/borders/bc_antisymmetry.F90:1"""
+        _check_cells(_state(w, "w"), im, jm, gh, "w")
+        B("bc_antisymmetry_2d", w, _loc(loc), _interf(interf), _in(nx), _in(ny), int(gh), int(im), int(jm))
+
+    def bc_pressure_2d(w, loc, interf, pext, noref, gam, nx, ny, im, jm, gh, em=None):
+        """srcfv/borders/bc_pressure.F90:1 (w, loc, interf, pext, noref, gam, nx, ny, im, jm, gh[, em])"""
+        _check_cells(_state(w, "w"), im, jm, gh, "w")
+        B("bc_pressure_2d", w, _loc(loc), _interf(interf), float(pext), int(bool(noref)), gam, _in(nx), _in(ny), int(im), int(jm), int(gh),
+          int(em) if em is not None else w.shape[2])
+
     def bc_no_reflexion_2d(w, wbd, loc, interf, nx, ny, gam, gh, im, jm, lm=None):
         _check_cells(_state(w, "w"), im, jm, gh, "w")
         wbd = _in(wbd)
@@ -147,7 +158,8 @@ def build(backend):
 
     f_bnd = types.SimpleNamespace(
         bc_wall_viscous_adia_2d=bc_wall_viscous_adia_2d, bc_no_reflexion_2d=bc_no_reflexion_2d,
-        bc_wall_viscous_iso_2d=bc_wall_viscous_iso_2d, bc_symmetry_2d=bc_symmetry_2d,
+        bc_wall_viscous_iso_2d=bc_wall_viscous_iso_2d, bc_symmetry_2d=bc_symmetry_2d, bc_antisymmetry_2d=bc_antisymmetry_2d,
+        bc_pressure_2d=bc_pressure_2d,
         bc_supandsubinlet_2d=bc_supandsubinlet_2d, bc_extrapolate_o2_2d=bc_extrapolate_o2_2d,
         jn_match_2d=jn_match_2d, jn_match_geom_2d=jn_match_geom_2d)
 
@@ -168,6 +180,19 @@ def build(backend):
         _check_cells(_state(w, "w"), im, jm, gh, "w")
         _check_cells(_state(wd, "wd"), im, jm, gh, "wd")
         B("bc_symmetry_2d_d", w, wd, _loc(loc), _interf(interf), _in(nx), _in(ny), int(gh), int(im), int(jm))
+
+    def bc_antisymmetry_2d_d(w, wd, loc, interf, nx, ny, gh, im, jm):
+        """srcfv/tangent/bc_antisymmetry_d.f90"""
+        _check_cells(_state(w, "w"), im, jm, gh, "w")
+        _check_cells(_state(wd, "wd"), im, jm, gh, "wd")
+        B("bc_antisymmetry_2d_d", w, wd, _loc(loc), _interf(interf), _in(nx), _in(ny), int(gh), int(im), int(jm))
+
+    def bc_pressure_2d_d(w, wd, loc, interf, pext, noref, gam, nx, ny, im, jm, gh, em=None):
+        """srcfv/tangent/bc_pressure_d.f90 (w, wd0, loc, interf, pext, noref, gam, nx, ny, im, jm, gh[, em])"""
+        _check_cells(_state(w, "w"), im, jm, gh, "w")
+        _check_cells(_state(wd, "wd"), im, jm, gh, "wd")
+        B("bc_pressure_2d_d", w, wd, _loc(loc), _interf(interf), float(pext), int(bool(noref)), gam, _in(nx), _in(ny), int(im), int(jm),
+          int(gh), int(em) if em is not None else w.shape[2])
 
     def bc_no_reflexion_2d_d(w, wd, wbd, loc, interf, nx, ny, gam, gh, im, jm, lm=None):
         _check_cells(_state(w, "w"), im, jm, gh, "w")
@@ -198,6 +223,7 @@ def build(backend):
         flux_num_dnc5_nowall_2d_d=_scheme_d("flux_num_dnc5_nowall_2d_d"),
         bc_wall_viscous_adia_2d_d=bc_wall_viscous_adia_2d_d, bc_no_reflexion_2d_d=bc_no_reflexion_2d_d,
         bc_wall_viscous_iso_2d_d=bc_wall_viscous_iso_2d_d, bc_symmetry_2d_d=bc_symmetry_2d_d,
+        bc_antisymmetry_2d_d=bc_antisymmetry_2d_d, bc_pressure_2d_d=bc_pressure_2d_d,
         bc_supandsubinlet_2d_d=bc_supandsubinlet_2d_d, bc_extrapolate_o2_2d_d=bc_extrapolate_o2_2d_d)
 
     # ------------------------------------------------------------------ f_geom

@@ -94,6 +94,17 @@ int bc_bc_symmetry_2d(double* w, const char* loc, const int32_t* interf, const d
                       int jm);
 int bc_bc_symmetry_2d_d(double* w, double* wd, const char* loc, const int32_t* interf, const double* nx, const double* ny,
                         int gh, int im, int jm);
+/* antisymmetry plane and pressure outlet (card_bl2d_fv_cgns.py:102 routineout = 'bc_pressure_2d'):
+ * srcfv/borders/bc_antisymmetry.F90:1-79 + srcfv/tangent/bc_antisymmetry_d.f90; srcfv/borders/bc_pressure.F90:1-149 +
+ * srcfv/tangent/bc_pressure_d.f90 (noref: Fortran logical as int; em must be 5) */
+int bc_bc_antisymmetry_2d(double* w, const char* loc, const int32_t* interf, const double* nx, const double* ny, int gh, int im,
+                          int jm);
+int bc_bc_antisymmetry_2d_d(double* w, double* wd, const char* loc, const int32_t* interf, const double* nx, const double* ny,
+                            int gh, int im, int jm);
+int bc_bc_pressure_2d(double* w, const char* loc, const int32_t* interf, double pext, int noref, double gam, const double* nx,
+                      const double* ny, int im, int jm, int gh, int em);
+int bc_bc_pressure_2d_d(double* w, double* wd, const char* loc, const int32_t* interf, double pext, int noref, double gam,
+                        const double* nx, const double* ny, int im, int jm, int gh, int em);
 /* srcfv/borders/jn_match.F90:3-66 (3-D arrays, em planes) and jn_match_geom.F90:7-69 (2-D arrays) */
 int bc_jn_match_2d(double* wr, const int32_t* prr, int gh1r, int gh2r, int gh3r, int gh4r, int imr, int jmr,
                    const double* wd, const int32_t* prd, int gh1d, int gh2d, int gh3d, int gh4d, int imd, int jmd,
@@ -212,7 +223,9 @@ int bcd_bc_extrapolate_o2(double* w, double* wd, int ndir, const char* loc, cons
 int bcd_bc_wall_viscous_iso(double* w, double* wd, int ndir, double twall, const char* loc, double gam, double rgaz,
                             const int32_t* interf, int gh, int im, int jm, void* stream);
 int bcd_bc_symmetry(double* w, double* wd, int ndir, const char* loc, const int32_t* interf, const double* nx,
-                    const double* ny, int gh, int im, int jm, void* stream);
+                    const double* ny, int gh, int im, int jm, int anti /* 1 = bc_antisymmetry_2d */, void* stream);
+int bcd_bc_pressure(double* w, double* wd, int ndir, const char* loc, const int32_t* interf, double pext, int noref,
+                    double gam, const double* nx, const double* ny, int im, int jm, int gh, void* stream);
 int bcd_jn_match(double* wr, const int32_t* prr, int gh1r, int gh2r, int gh3r, int gh4r, int imr, int jmr,
                  const double* wd, const int32_t* prd, int gh1d, int gh2d, int gh3d, int gh4d, int imd, int jmd,
                  const int32_t* tr, int em, void* stream);

@@ -39,6 +39,10 @@ FILES = [
     ("srcfv/prepro/jn_match_geom.f90", ["jn_match_geom_2d"]),
     ("srcfv/prepro/bc_wall_viscous_iso.f90", ["bc_wall_viscous_iso_2d"]),
     ("srcfv/prepro/bc_symmetry.f90", ["bc_symmetry_2d"]),
+    ("srcfv/prepro/bc_antisymmetry.f90", ["bc_antisymmetry_2d"]),
+    ("srcfv/prepro/bc_pressure.f90", ["bc_pressure_2d"]),
+    ("srcfv/tangent/bc_antisymmetry_d.f90", None),
+    ("srcfv/tangent/bc_pressure_d.f90", None),
     ("srcfv/tangent/bc_wall_viscous_iso_d.f90", None),
     ("srcfv/tangent/bc_symmetry_d.f90", None),
     ("srcfv/tangent/bc_wall_viscous_d.f90", None),

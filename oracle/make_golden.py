@@ -95,7 +95,7 @@ def make_bcs(kind, im, jm, R):
     rng = np.random.default_rng(31)
     d = np.asfortranarray(rng.standard_normal(w0.shape))
     out = dict(kind=kind, im=im, jm=jm, gh=c.gh, seed=31, twall=T.TWALL)   # wd_in = default_rng(seed).standard_normal(w.shape)
-    for name in ("iso", "sym"):
+    for name in T.NAMES:
         for loc, interf in T.sides(c):
             w, wd = w0.copy(order="F"), d.copy(order="F")
             T.fill(R, name, c, w, loc, interf, wd)

@@ -14,6 +14,7 @@ import helpers as H
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = sorted(glob.glob(os.path.join(HERE, "golden", "bcs", "*.npz")))
 TWALL = 1.3
+NAMES = ["iso", "sym", "anti", "pres", "presnr"]
 
 
 def sides(c):
@@ -45,14 +46,24 @@ def fill(mods, name, c, w, loc, interf, wd=None):
             mods["f_bnd"].bc_wall_viscous_iso_2d(w, TWALL, loc, p["gam"], p["rgaz"], interf, c.gh, c.im, c.jm)
         else:
             mods["f_lin"].bc_wall_viscous_iso_2d_d(w, wd, TWALL, loc, p["gam"], p["rgaz"], interf, c.gh, c.im, c.jm)
-    else:
+    elif name in ("sym", "anti"):
+        rt = "bc_symmetry_2d" if name == "sym" else "bc_antisymmetry_2d"
         if wd is None:
-            mods["f_bnd"].bc_symmetry_2d(w, loc, interf, c.nx, c.ny, c.gh, c.im, c.jm)
+            getattr(mods["f_bnd"], rt)(w, loc, interf, c.nx, c.ny, c.gh, c.im, c.jm)
         else:
-            mods["f_lin"].bc_symmetry_2d_d(w, wd, loc, interf, c.nx, c.ny, c.gh, c.im, c.jm)
+            getattr(mods["f_lin"], rt + "_d")(w, wd, loc, interf, c.nx, c.ny, c.gh, c.im, c.jm)
+    else:   # pressure outlet, plain ("pres") or with the characteristic blend ("presnr")
+        g = c.gh
+        q = c.w[g, g]
+        pext = 0.97 * (p["gam"] - 1.0) * (q[4] - 0.5 * (q[1] ** 2 + q[2] ** 2 + q[3] ** 2) / q[0])
+        noref = name == "presnr"
+        if wd is None:
+            mods["f_bnd"].bc_pressure_2d(w, loc, interf, pext, noref, p["gam"], c.nx, c.ny, c.im, c.jm, c.gh)
+        else:
+            mods["f_lin"].bc_pressure_2d_d(w, wd, loc, interf, pext, noref, p["gam"], c.nx, c.ny, c.im, c.jm, c.gh)
 
 
-@pytest.mark.parametrize("name", ["iso", "sym"])
+@pytest.mark.parametrize("name", NAMES)
 @pytest.mark.parametrize("kind,im,jm", [("bl", 20, 12), ("cyl", 24, 12)])
 def test_tangent_fill_is_the_derivative_of_the_primal_fill(ref, name, kind, im, jm):
     c = H.make_case(kind, im, jm, ref, with_w=True)
@@ -60,6 +71,8 @@ def test_tangent_fill_is_the_derivative_of_the_primal_fill(ref, name, kind, im, 
     rng = np.random.default_rng(2)
     d = np.asfortranarray(rng.standard_normal(w0.shape) * 1e-2 * np.abs(w0).max(axis=(0, 1)))
     for loc, interf in sides(c):
+        if name == "presnr" and (kind, loc) != ("bl", "Ihi"):
+            continue      # the wave-direction switches are piecewise constant: differences only where no switch is near its jump
         w, wd = w0.copy(order="F"), d.copy(order="F")
         fill(ref, name, c, w, loc, interf, wd)
         wp, wm = np.asfortranarray(w0 + 1e-5 * d), np.asfortranarray(w0 - 1e-5 * d)
@@ -104,7 +117,7 @@ def test_ref_reproduces_the_bc_golden(ref, path):
     g = np.load(path)
     c = H.make_case(str(g["kind"]), int(g["im"]), int(g["jm"]), ref, with_w=True)
     w0, _ = H.residual_sequence(ref, c)
-    for name in ("iso", "sym"):
+    for name in NAMES:
         for loc, interf in sides(c):
             d = np.asfortranarray(np.random.default_rng(int(g["seed"])).standard_normal(w0.shape))
             w, wd = w0.copy(order="F"), d.copy(order="F")

@@ -728,7 +728,7 @@ def test_dz_tangent_golden(gpu, name):
 # ---------------------------------------------------------------------------------------------------------------------
 # boundary fills of SURVEY.md 8(f3): isothermal wall, symmetry plane (primal and tangent), every side of the block
 # ---------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["iso", "sym"])
+@pytest.mark.parametrize("name", ["iso", "sym", "anti", "pres", "presnr"])
 @pytest.mark.parametrize("kind,im,jm", [("bl", 60, 40), ("cyl", 70, 40), ("bl", 7, 7)])
 def test_isothermal_wall_and_symmetry_fills(gpu, ref, name, kind, im, jm):
     import test_extra_bcs_cpu as T
@@ -758,7 +758,7 @@ def test_isothermal_wall_and_symmetry_golden(gpu, fixture):
     a = H.make_case(str(g["kind"]), int(g["im"]), int(g["jm"]), gpu, with_w=True)
     w0, _ = H.residual_sequence(gpu, a)
     d = np.asfortranarray(np.random.default_rng(int(g["seed"])).standard_normal(w0.shape))
-    for name in ("iso", "sym"):
+    for name in T.NAMES:
         for loc, interf in T.sides(a):
             w, wd = w0.copy(order="F"), d.copy(order="F")
             T.fill(gpu, name, a, w, loc, interf, wd)
