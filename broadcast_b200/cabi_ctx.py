@@ -52,6 +52,8 @@ class Context:
                     self._keep.append(t)
                     d.table = t.ctypes.data
                     d.lm = int(t.shape[0])
+                elif kind in ("wall_iso", "pressure"):
+                    d.param[:] = [float(bc[3]), float(bc[4])]
                 descs.append(d)
         arr = (_BcDesc * max(len(descs), 1))(*descs)
         _lib.check(self.lib.bcast_ctx_set_bcs(self.h, arr, len(descs)), "bcast_ctx_set_bcs")

@@ -333,11 +333,37 @@ def apply_bcs(case: Case, w, f_bnd):
             f_bnd.bc_extrapolate_o2_2d(w, bc[1], bc[2], im, jm, gh)
         elif kind == "wall":
             f_bnd.bc_wall_viscous_adia_2d(w, bc[1], gam, bc[2], gh, im, jm)
+        elif kind in _EXTRA_BCS:
+            _extra_bc(case, kind, bc, w, None, f_bnd, None)
         elif kind == "jn":
             for prr, prd, tr in bc[1:]:
                 f_bnd.jn_match_2d(w, prr, gh, gh, gh, gh, im, jm, w, prd, gh, gh, gh, gh, im, jm, tr)
         else:
             raise ValueError(kind)
+
+
+# boundary fills of SURVEY.md 8(f3): ("wall_iso", loc, interf, twall, rgaz), ("symmetry" | "antisymmetry", loc, interf),
+# ("pressure", loc, interf, pext, noref)
+_EXTRA_BCS = ("wall_iso", "symmetry", "antisymmetry", "pressure")
+
+
+def _extra_bc(case, kind, bc, w, wd, f_bnd, f_lin):
+    im, jm, gh, gam = case.im, case.jm, case.gh, case.phys["gam"]
+    if kind == "wall_iso":
+        if wd is None:
+            f_bnd.bc_wall_viscous_iso_2d(w, bc[3], bc[1], gam, bc[4], bc[2], gh, im, jm)
+        else:
+            f_lin.bc_wall_viscous_iso_2d_d(w, wd, bc[3], bc[1], gam, bc[4], bc[2], gh, im, jm)
+    elif kind in ("symmetry", "antisymmetry"):
+        if wd is None:
+            getattr(f_bnd, "bc_%s_2d" % kind)(w, bc[1], bc[2], case.nx, case.ny, gh, im, jm)
+        else:
+            getattr(f_lin, "bc_%s_2d_d" % kind)(w, wd, bc[1], bc[2], case.nx, case.ny, gh, im, jm)
+    else:
+        if wd is None:
+            f_bnd.bc_pressure_2d(w, bc[1], bc[2], bc[3], bool(bc[4]), gam, case.nx, case.ny, im, jm, gh)
+        else:
+            f_lin.bc_pressure_2d_d(w, wd, bc[1], bc[2], bc[3], bool(bc[4]), gam, case.nx, case.ny, im, jm, gh)
 
 
 def apply_bcs_lin(case: Case, w, wd, f_bnd, f_lin, *, zero_frame: bool = None):
@@ -373,6 +399,10 @@ def apply_bcs_lin(case: Case, w, wd, f_bnd, f_lin, *, zero_frame: bool = None):
             f_lin.bc_wall_viscous_adia_2d_d(w, wd, bc[1], gam, bc[2], gh, im, jm)
             if handle_bc_style:
                 f_bnd.bc_wall_viscous_adia_2d(w, bc[1], gam, bc[2], gh, im, jm)
+        elif kind in _EXTRA_BCS:
+            _extra_bc(case, kind, bc, w, wd, f_bnd, f_lin)
+            if handle_bc_style:
+                _extra_bc(case, kind, bc, w, None, f_bnd, None)
         elif kind == "jn":
             for prr, prd, tr in bc[1:]:
                 f_bnd.jn_match_2d(wd, prr, gh, gh, gh, gh, im, jm, wd, prd, gh, gh, gh, gh, im, jm, tr)

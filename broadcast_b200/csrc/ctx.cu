@@ -132,7 +132,7 @@ extern "C" int bcast_ctx_set_bcs(bcast_ctx_t* c, const bc_desc_t* bcs, int nbcs)
     if (d.kind == BC_KIND_INLET) n = (size_t)d.lm * c->gh * 5;
     else if (d.kind == BC_KIND_NOREF) n = (size_t)d.lm * 5;
     else if (d.kind == BC_KIND_JOIN) c->has_join = true;
-    else if (d.kind != BC_KIND_EXTRAP && d.kind != BC_KIND_WALL) return BC_ERR_ARG;
+    else if (d.kind != BC_KIND_EXTRAP && d.kind != BC_KIND_WALL && (d.kind < BC_KIND_WALL_ISO || d.kind > BC_KIND_PRESSURE)) return BC_ERR_ARG;
     if (n) {
       if (!d.table || d.lm < 1) return BC_ERR_ARG;
       double* t = nullptr;

@@ -32,6 +32,10 @@ static cudaError_t apply_bc_list(const GridDesc& g, double gam, int ndir, double
         case BC_KIND_NOREF: e = launch_bc_noref(g, line, gam, ndir, w, wd, d.table, d.lm, nx, ny, st); break;
         case BC_KIND_EXTRAP: e = launch_bc_extrap(g, line, ndir, w, wd, st); break;
         case BC_KIND_WALL: e = launch_bc_wall(g, line, gam, ndir, w, wd, st); break;
+        case BC_KIND_WALL_ISO: e = launch_bc_wall_iso(g, line, d.param[0], gam, d.param[1], ndir, w, wd, st); break;
+        case BC_KIND_SYMMETRY: e = launch_bc_symmetry(g, line, ndir, w, wd, nx, ny, false, st); break;
+        case BC_KIND_ANTISYMMETRY: e = launch_bc_symmetry(g, line, ndir, w, wd, nx, ny, true, st); break;
+        case BC_KIND_PRESSURE: e = launch_bc_pressure(g, line, d.param[0], d.param[1] != 0.0, gam, ndir, w, wd, nx, ny, st); break;
         default: return cudaErrorInvalidValue;
       }
       count_launches(1);
@@ -43,7 +47,8 @@ static cudaError_t apply_bc_list(const GridDesc& g, double gam, int ndir, double
 
 // Linearised boundary fills a colour (l,k) can skip: the tangent a fill writes into the ghosts of a boundary line depends on wd
 // of the first three interior cells of the SAME line only (bc.cuh: wall mirror / pressure extrapolation, o2 extrapolation,
-// characteristic updates from the first interior cell and the ghosts already written), and the seeds of a colour sit on the rows
+// characteristic updates from the first interior cell and the ghosts already written; the isothermal wall, the (anti)symmetry mirror
+// of layers 0 .. gh-1 and the pressure outlet read the same cells), and the seeds of a colour sit on the rows
 // j = k+1 (mod 7), columns i = l+1 (mod 7): a side whose three first interior rows (columns) hold no seed row (column) of this
 // colour receives zero tangents, which is what the seeding kernel has already written there.  Joins are always applied.
 static int active_bcs(const GridDesc& g, const bc_desc_t* bcs, int nbcs, int l, int k, bc_desc_t* out) {

@@ -70,8 +70,10 @@ class Block:
                 wbd = np.asfortranarray(bc[3])
                 self.bcs.append(("noref", bc[1].encode(), _interf(bc[2]), torch.from_numpy(np.ascontiguousarray(wbd.T)).to(device),
                                  wbd.shape[0]))
-            elif kind in ("outflow", "wall"):
+            elif kind in ("outflow", "wall", "symmetry", "antisymmetry"):
                 self.bcs.append((kind, bc[1].encode(), _interf(bc[2])))
+            elif kind in ("wall_iso", "pressure"):     # (kind, loc, interf, twall, rgaz) / (kind, loc, interf, pext, noref)
+                self.bcs.append((kind, bc[1].encode(), _interf(bc[2]), float(bc[3]), float(bc[4])))
             elif kind == "jn":
                 self.bcs.append(("jn", [(_interf(prr), _interf(prd), np.asarray(tr, dtype=np.int32)) for prr, prd, tr in bc[1:]]))
             else:
@@ -126,6 +128,15 @@ class Block:
             elif kind == "wall":
                 self._ck(L.bcd_bc_wall_viscous_adia(_p(w), _p(wd), ndir, bc[1], ctypes.c_double(self.gam), I(bc[2]), gh, im, jm, st),
                          "bcd_bc_wall_viscous_adia")
+            elif kind == "wall_iso":
+                self._ck(L.bcd_bc_wall_viscous_iso(_p(w), _p(wd), ndir, ctypes.c_double(bc[3]), bc[1], ctypes.c_double(self.gam),
+                                                   ctypes.c_double(bc[4]), I(bc[2]), gh, im, jm, st), "bcd_bc_wall_viscous_iso")
+            elif kind in ("symmetry", "antisymmetry"):
+                self._ck(L.bcd_bc_symmetry(_p(w), _p(wd), ndir, bc[1], I(bc[2]), _p(self.nx), _p(self.ny), gh, im, jm,
+                                           int(kind == "antisymmetry"), st), "bcd_bc_symmetry")
+            elif kind == "pressure":
+                self._ck(L.bcd_bc_pressure(_p(w), _p(wd), ndir, bc[1], I(bc[2]), ctypes.c_double(bc[3]), int(bc[4] != 0.0),
+                                           ctypes.c_double(self.gam), _p(self.nx), _p(self.ny), im, jm, gh, st), "bcd_bc_pressure")
             elif kind == "jn":
                 targets = [w] if wd is None else [wd, w]
                 for t in targets:
@@ -283,10 +294,10 @@ def local_halo_exchange(blocks):
 # ----------------------------------------------------------------------------------------------
 class _BcDesc(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int32), ("loc", ctypes.c_char * 4), ("window", ctypes.c_int32 * 4), ("prd", ctypes.c_int32 * 4),
-                ("tr", ctypes.c_int32 * 2), ("lm", ctypes.c_int32), ("table", ctypes.c_void_p)]
+                ("tr", ctypes.c_int32 * 2), ("lm", ctypes.c_int32), ("table", ctypes.c_void_p), ("param", ctypes.c_double * 2)]
 
 
-_KIND = {"inflow": 1, "noref": 2, "outflow": 3, "wall": 4, "jn": 5}
+_KIND = {"inflow": 1, "noref": 2, "outflow": 3, "wall": 4, "jn": 5, "wall_iso": 6, "symmetry": 7, "antisymmetry": 8, "pressure": 9}
 SCATTER = {"jv": 0, "jv_relaxed": 1, "dz": 2, "jv_relaxed_withjn": 3, "jv_withjn": 4, "jv_dbyvol": 5, "jv_relaxed_dbyvol": 6}
 
 
@@ -310,6 +321,8 @@ def _bc_descs(blk: "Block"):
             if kind in ("inflow", "noref"):
                 d.table = bc[3].data_ptr()
                 d.lm = int(bc[4])
+            elif kind in ("wall_iso", "pressure"):
+                d.param[:] = [bc[3], bc[4]]
             out.append(d)
     arr = (_BcDesc * len(out))(*out)
     return arr, len(out)

@@ -257,14 +257,19 @@ int bcd_norm_sums(double* out10, const double* rhs, int im, int jm, int gh, void
 #define BC_KIND_EXTRAP 3  /* bc_extrapolate_o2_2d                          */
 #define BC_KIND_WALL 4    /* bc_wall_viscous_adia_2d                       */
 #define BC_KIND_JOIN 5    /* jn_match_2d of the block onto itself: window = receiver, prd = donor */
+#define BC_KIND_WALL_ISO 6      /* bc_wall_viscous_iso_2d   param = {twall, rgaz}          */
+#define BC_KIND_SYMMETRY 7      /* bc_symmetry_2d                                          */
+#define BC_KIND_ANTISYMMETRY 8  /* bc_antisymmetry_2d                                      */
+#define BC_KIND_PRESSURE 9      /* bc_pressure_2d           param = {pext, noref (0 / 1)}  */
 typedef struct {
   int32_t kind;
   char loc[4];
-  int32_t window[4]; /* interf (kinds 1-4) or prr (kind 5): imin, jmin, imax, jmax */
+  int32_t window[4]; /* interf (kinds 1-4, 6-9) or prr (kind 5): imin, jmin, imax, jmax */
   int32_t prd[4];    /* kind 5 only */
   int32_t tr[2];     /* kind 5 only */
   int32_t lm;
   const double* table;
+  double param[2];   /* scalar arguments of kinds 6 and 9 */
 } bc_desc_t;
 
 /* Reference colour loop (BROADCAST_npz.py:1068-1127 / cylinder.py:941-978) entirely on the device:

@@ -34,6 +34,7 @@ int main(int argc, char** argv) {
     memcpy(bcs[k].prd, rec + 9, 16);
     memcpy(bcs[k].tr, rec + 13, 8);
     bcs[k].lm = rec[15];
+    RD(bcs[k].param, 2);
     size_t n = bcs[k].kind == BC_KIND_INLET ? (size_t)rec[15] * gh * 5 : bcs[k].kind == BC_KIND_NOREF ? (size_t)rec[15] * 5 : 0;
     if (n) {
       double* t = malloc(n * 8);

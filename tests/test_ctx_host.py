@@ -53,6 +53,7 @@ def write_case(path, c, coef):
             fh.write(np.asfortranarray(a, dtype=np.float64).tobytes(order="F"))
         for r, t in zip(recs, tables):
             np.array(r, dtype=np.int32).tofile(fh)
+            np.zeros(2).tofile(fh)              # bc_desc_t.param (kinds 6 and 9 only)
             if t is not None:
                 fh.write(t.tobytes(order="F"))
 

@@ -818,3 +818,53 @@ def test_c_abi_context_jacobian_csr(gpu, ref, kind, im, jm):
     diff = abs(A - B)
     assert diff.max() <= TOL * abs(A).max(), diff.max() / abs(A).max()
     ctx.close()
+
+
+def _bl_case_with_extra_bcs(mods, im, jm):
+    """boundary layer with an ISOTHERMAL wall at Jlo and a PRESSURE outlet (characteristic blend) at Ihi instead of the adiabatic
+    wall / extrapolation of card_bl2d_fv_npz.py -- the variants card_bl2d_fv.py:110 and card_bl2d_fv_cgns.py:102 select"""
+    c = H.make_case("bl", im, jm, mods, with_w=True)
+    p, g = c.phys, c.gh
+    q = c.w[g, g]
+    pr = (p["gam"] - 1.0) * (q[4] - 0.5 * (q[1] ** 2 + q[2] ** 2 + q[3] ** 2) / q[0])
+    bcs = []
+    for bc in c.bcs:
+        if bc[0] == "wall":
+            bcs.append(("wall_iso", bc[1], bc[2], 1.05 * pr / (q[0] * p["rgaz"]), p["rgaz"]))
+        elif bc[0] == "outflow":
+            bcs.append(("pressure", bc[1], bc[2], 0.97 * pr, 1.0))
+        else:
+            bcs.append(bc)
+    c.bcs = bcs
+    return c
+
+
+def test_jacobian_with_isothermal_wall_and_pressure_outlet(gpu, ref):
+    """the new boundary kinds inside the device colour loops: residual step, hybrid Jacobian (interior blocks + strip loop with the
+    linearised isothermal-wall / pressure fills) and the C-ABI context, against the reference loop on the CPU"""
+    import scipy.sparse as sp
+    from broadcast_b200.cabi_ctx import Context
+    from broadcast_b200.resident import Block, jacobian_hybrid
+    im, jm = 44, 28
+    a, b = _bl_case_with_extra_bcs(gpu, im, jm), _bl_case_with_extra_bcs(ref, im, jm)
+    wa, ra = H.residual_sequence(gpu, a)
+    wb, rb = H.residual_sequence(ref, b)
+    assert np.all(H.rel_err(wa, wb) < TOL) and np.all(H.rel_err(ra, rb) < TOL)
+    coef = np.asfortranarray(np.random.default_rng(6).uniform(0.5, 1.5, size=(im, jm)))
+    blk = Block(a)
+    blk.apply_bcs()
+    assert np.array_equal(np.ascontiguousarray(blk.w.cpu().numpy().transpose(2, 1, 0)), wa)    # bcd_apply_bcs == the f2py-shaped fills
+    hj = jacobian_hybrid(blk, coefdiag=coef)
+    A = hj.to_scipy_csr()
+    jb, ib, jbb = H.jacobian_sequence(ref, b, wb, None, coef)
+    keep = np.abs(jb) > 2e-16
+    n = 5 * im * jm
+    B = sp.csr_matrix((jb[keep], (ib[keep], jbb[keep])), shape=(n, n))
+    assert abs(A - B).max() < TOL * abs(B).max(), abs(A - B).max() / abs(B).max()
+    ctx = Context(a)
+    ctx.upload_state(a.w)
+    assert np.array_equal(ctx.residual(), ra)
+    indptr, indices, data = ctx.jacobian_csr(coefdiag=coef, divide_by_vol=False)
+    p2, i2, d2 = (t.cpu().numpy() for t in hj.to_csr_device(divide_by_vol=False))
+    assert np.array_equal(indptr, p2) and np.array_equal(indices, i2) and np.array_equal(data, d2)
+    ctx.close()
