@@ -34,15 +34,21 @@ __global__ void __launch_bounds__(dzt::NT, MINB) k_dz_tangent(dzt::Tile t, Rect 
 cudaError_t launch_dz_tangent(const GridDesc& g, const dzt::Consts& c, double* out1, double* out2, const double* w, const double* wd0,
                               const double* wd, const double* nx, const double* ny, const double* vol, const Rect& rc, cudaStream_t st) {
   if (rc.i1 < rc.i0 || rc.j1 < rc.j0 || (!out1 && !out2)) return cudaSuccess;
-  static int minb = 0;   // BCAST_DZT_MINB = 2 | 3 selects the register budget (A/B in profiles/r1_l_summary.md)
+  // BCAST_DZT_MINB = 2 | 3 selects the register budget (A/B in profiles/r1_l_summary.md); the shared-memory opt-in is per device
+  static int minb = 0;
+  static bool attr_set[64] = {};
   constexpr int smem = dzt::NSM * (int)sizeof(double);
   if (!minb) {
     const char* env = getenv("BCAST_DZT_MINB");
-    const int want = env && env[0] == '3' ? 3 : 2;
+    minb = env && env[0] == '3' ? 3 : 2;
+  }
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(k_dz_tangent<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_dz_tangent<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    minb = want;
+    attr_set[dev] = true;
   }
   dzt::Tile t{};
   t.g = g;
