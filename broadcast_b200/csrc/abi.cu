@@ -310,6 +310,15 @@ int bcd_bc_symmetry(double* w, double* wd, int ndir, const char* loc, const int3
   g_launches += 1;
   return e == cudaSuccess ? BC_OK : cuda_fail(e, "bcd_bc_symmetry");
 }
+int bcd_bc_wall_profile(double* w, double* wd, int ndir, int blow, const double* prof, const double* profd, const char* loc, double gam,
+                        double gamd, double rgaz, double rgazd, const int32_t* interf, int gh, int im, int jm, int lm, void* stream) {
+  BCD_PROLOGUE();
+  if (!prof) return fail(BC_ERR_ARG, "profile is null");
+  if (lm < b.lmax) return fail(BC_ERR_ARG, "profile shorter than the boundary line");
+  cudaError_t e = launch_bc_wall_profile(g, b, blow != 0, prof, profd, gam, gamd, rgaz, rgazd, ndir, w, wd, (cudaStream_t)stream);
+  g_launches += 1;
+  return e == cudaSuccess ? BC_OK : cuda_fail(e, "bcd_bc_wall_profile");
+}
 int bcd_bc_pressure(double* w, double* wd, int ndir, const char* loc, const int32_t* interf, double pext, int noref, double gam,
                     const double* nx, const double* ny, int im, int jm, int gh, void* stream) {
   BCD_PROLOGUE();
@@ -449,6 +458,37 @@ int bc_bc_antisymmetry_2d_d(double* w, double* wd, const char* loc, const int32_
                             int im, int jm) {
   if (!wd) return fail(BC_ERR_ARG, "wd is null");
   return symmetry_host(w, wd, loc, interf, nx, ny, gh, im, jm, 1);
+}
+static int wall_profile_host(int blow, double* w, double* wd, const double* prof, const double* profd, const char* loc, double gam,
+                             double gamd, double rgaz, double rgazd, const int32_t* interf, int gh, int im, int jm, int lm) {
+  if (lm < 1 || !prof) return fail(BC_ERR_ARG, "profile / lm");
+  return bc_host(w, wd, gh, im, jm, [&](const GridDesc&, double* dw, double* dwd) -> int {
+    double* dprof = dbuf<double>(S_AUX, (size_t)lm * 2);
+    if (!dprof) return fail(BC_ERR_ALLOC, "device allocation failed");
+    CK(cudaMemcpyAsync(dprof, prof, sizeof(double) * lm, cudaMemcpyHostToDevice, 0));
+    if (profd) CK(cudaMemcpyAsync(dprof + lm, profd, sizeof(double) * lm, cudaMemcpyHostToDevice, 0));
+    return bcd_bc_wall_profile(dw, dwd, wd ? 1 : 0, blow, dprof, profd ? dprof + lm : nullptr, loc, gam, gamd, rgaz, rgazd, interf, gh, im, jm,
+                               lm, nullptr);
+  });
+}
+int bc_bc_wall_blow_profile_2d(double* w, const double* velprof, const char* loc, double gam, const int32_t* interf, int gh, int im, int jm,
+                               int lm) {
+  return wall_profile_host(1, w, nullptr, velprof, nullptr, loc, gam, 0.0, 1.0, 0.0, interf, gh, im, jm, lm);
+}
+int bc_bc_wall_blow_profile_2d_d(double* w, double* wd, const double* velprof, const double* velprofd, const char* loc, double gam,
+                                 double gamd, const int32_t* interf, int gh, int im, int jm, int lm) {
+  if (!wd || !velprofd) return fail(BC_ERR_ARG, "wd / velprofd is null");
+  return wall_profile_host(1, w, wd, velprof, velprofd, loc, gam, gamd, 1.0, 0.0, interf, gh, im, jm, lm);
+}
+int bc_bc_wall_viscous_iso_profile_2d(double* w, const double* twallprof, const char* loc, double gam, double rgaz, const int32_t* interf,
+                                      int gh, int im, int jm, int lm) {
+  return wall_profile_host(0, w, nullptr, twallprof, nullptr, loc, gam, 0.0, rgaz, 0.0, interf, gh, im, jm, lm);
+}
+int bc_bc_wall_viscous_iso_profile_2d_d(double* w, double* wd, const double* twallprof, const double* twallprofd, const char* loc,
+                                        double gam, double gamd, double rgaz, double rgazd, const int32_t* interf, int gh, int im, int jm,
+                                        int lm) {
+  if (!wd || !twallprofd) return fail(BC_ERR_ARG, "wd / twallprofd is null");
+  return wall_profile_host(0, w, wd, twallprof, twallprofd, loc, gam, gamd, rgaz, rgazd, interf, gh, im, jm, lm);
 }
 static int pressure_host(double* w, double* wd, const char* loc, const int32_t* interf, double pext, int noref, double gam, const double* nx,
                          const double* ny, int im, int jm, int gh, int em) {

@@ -174,6 +174,70 @@ __device__ void bc_wall_viscous_iso_line(const StateRW<N>& s, const BcLine& b, d
 }
 
 // ---------------------------------------------------------------------------------------------
+// profile walls of the sensitivity driver (BROADCAST_npz_sens.py:1763; card_bl2d_fv_npz_sens.py:105).  `prof` (lm values along the line)
+// and the gas constants are ACTIVE inputs of the shipped tangents (tangent/bc_wall_blow_profile_d.f90: velprofd, gamd;
+// tangent/bc_wall_viscous_iso_profile_d.f90: twallprofd, gamd, rgazd): profd / gamd / rgazd are their tangents along direction 0
+// (null / 0 = passive); further directions of a vector-mode pass see them as passive.
+//   BLOW = true : bc_wall_blow_profile.F90:36-95      wall-normal blowing velocity profile, isentropic ghost density, all layers alike
+//   BLOW = false: bc_wall_viscous_iso_profile.F90     isothermal wall with a wall-temperature profile (as bc_wall_viscous_iso_line)
+// ---------------------------------------------------------------------------------------------
+template <int N, bool BLOW>
+__device__ void bc_wall_profile_line(const StateRW<N>& s, const BcLine& b, const double* __restrict__ prof, const double* __restrict__ profd,
+                                     double gam_, double gamd, double rgaz_, double rgazd, int l) {
+  using DT = TanOf<N>;
+  using VT = Var<DT>;
+  const int i = b.imin + l * b.j0 * b.j0;
+  const int j = b.jmin + l * b.i0 * b.i0;
+  const int i0 = b.i0, j0 = b.j0, gh = s.g.gh;
+  auto active = [](double v, double d) {
+    VT r{v, DT{}};
+    if constexpr (N > 0) r.d.d[0] = d;
+    return r;
+  };
+  const VT gam = active(gam_, gamd), rgaz = active(rgaz_, rgazd), pr = active(prof[l], profd ? profd[l] : 0.0);
+  const VT gam1 = gam - 1.0, gami = 1.0 / gam;
+  const double THIRD = 1.0 / 3.0;
+
+  const VT roe = s.get(i, j, 0);
+  const VT roem1 = 1.0 / roe;
+  const VT ue = s.get(i, j, 1) * roem1, ve = s.get(i, j, 2) * roem1, we = s.get(i, j, 3) * roem1;
+  const VT pe = gam1 * (s.get(i, j, 4) - 0.5 * roe * (ue * ue + ve * ve + we * we));
+  const VT roe1 = s.get(i + i0, j + j0, 0);
+  const VT roe1m1 = 1.0 / roe1;
+  const VT ue1 = s.get(i + i0, j + j0, 1) * roe1m1, ve1 = s.get(i + i0, j + j0, 2) * roe1m1, we1 = s.get(i + i0, j + j0, 3) * roe1m1;
+  const VT pe1 = gam1 * (s.get(i + i0, j + j0, 4) - 0.5 * roe1 * (ue1 * ue1 + ve1 * ve1 + we1 * we1));
+  const VT pw = 1.125 * pe + (-0.125) * pe1;
+  const VT pi = THIRD * (4.0 * pw - pe);
+  const VT roiei = pi / gam1;
+  VT roi, ui = -ue, vi, wi = -we;
+  if constexpr (BLOW) {
+    roi = pow(pi * pow(roe, gam) / pe, gami);
+    vi = 2.0 * pr - ve;
+  } else {
+    roi = 2.0 * pw / (rgaz * pr) - roe;
+    vi = -ve;
+  }
+  VT prev = roe;
+  for (int de = 1; de <= gh; ++de) {
+    s.set(i - de * i0, j - de * j0, 0, roi);
+    s.set(i - de * i0, j - de * j0, 1, roi * ui);
+    s.set(i - de * i0, j - de * j0, 2, roi * vi);
+    s.set(i - de * i0, j - de * j0, 3, roi * wi);
+    s.set(i - de * i0, j - de * j0, 4, roiei + 0.5 * roi * (ui * ui + vi * vi + wi * wi));
+    if constexpr (!BLOW) {
+      const VT next = 2.0 * roi - prev;
+      prev = roi;
+      roi = next;
+    }
+    const VT rm1 = 1.0 / s.get(i + de * i0, j + de * j0, 0);
+    ui = -(s.get(i + de * i0, j + de * j0, 1) * rm1);
+    const VT vn = s.get(i + de * i0, j + de * j0, 2) * rm1;
+    if constexpr (BLOW) vi = 2.0 * pr - vn; else vi = -vn;
+    wi = -(s.get(i + de * i0, j + de * j0, 3) * rm1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // symmetry plane (bc_symmetry.F90:36-76; tangent/bc_symmetry_d.f90): ghost de mirrors interior layer de - 1, the velocity reflected
 // about the boundary-face normal, total energy corrected by the change of in-plane kinetic energy; rho w (plane 4) is NOT written.
 // ANTI: bc_antisymmetry.F90:40-49 (tangent/bc_antisymmetry_d.f90) -- same reflection, ghost = (-rho, -(rho u'), rho v', -(E'))

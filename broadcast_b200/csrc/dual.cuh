@@ -186,6 +186,18 @@ template <class A> BC_HD Var<A> pow(Var<A> x, double y) {
     fac = y * ::pow(x.v, y - 1.0);
   return Var<A>{p, t_scale(fac, x.d)};
 }
+// x**y with BOTH active (Tapenade, e.g. tangent/bc_wall_blow_profile_d.f90:139-147): the exponent contributes x^y log(x) yd for x > 0 only
+template <class A> BC_HD Var<A> pow(Var<A> x, Var<A> y) {
+  const double p = ::pow(x.v, y.v);
+  double fac;
+  if (x.v <= 0.0 && (y.v == 0.0 || y.v != (double)(int)y.v))
+    fac = 0.0;
+  else
+    fac = y.v * ::pow(x.v, y.v - 1.0);
+  Var<A> r{p, t_scale(fac, x.d)};
+  if (x.v > 0.0) r.d = t_add(r.d, t_scale(p * ::log(x.v), y.d));
+  return r;
+}
 // Fortran SIGN(a,b) with passive result
 BC_HD double fsign(double a, double b) { return ::copysign(::fabs(a), b); }
 

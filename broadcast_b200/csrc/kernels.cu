@@ -142,6 +142,17 @@ __global__ void k_bc_pressure(StateRW<N> s, BcLine b, double pext, bool noref, d
   if (l < b.lmax) bc_pressure_line<N>(s, b, pext, noref, gam, nx, ny, l);
 }
 
+template <int N>
+__global__ void k_bc_wall_profile(StateRW<N> s, BcLine b, const double* prof, const double* profd, double gam, double gamd, double rgaz,
+                                  double rgazd, bool blow) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= b.lmax) return;
+  if (blow)
+    bc_wall_profile_line<N, true>(s, b, prof, profd, gam, gamd, rgaz, rgazd, l);
+  else
+    bc_wall_profile_line<N, false>(s, b, prof, profd, gam, gamd, rgaz, rgazd, l);
+}
+
 #define BC_DISPATCH(KERNEL, ...)                                                     \
   do {                                                                               \
     if (b.lmax <= 0) return cudaSuccess;                                             \
@@ -177,6 +188,10 @@ cudaError_t launch_bc_symmetry(const GridDesc& g, const BcLine& b, int ndir, dou
 cudaError_t launch_bc_pressure(const GridDesc& g, const BcLine& b, double pext, bool noref, double gam, int ndir, double* w, double* wd,
                                const double* nx, const double* ny, cudaStream_t st) {
   BC_DISPATCH(k_bc_pressure, pext, noref, gam, nx, ny);
+}
+cudaError_t launch_bc_wall_profile(const GridDesc& g, const BcLine& b, bool blow, const double* prof, const double* profd, double gam,
+                                   double gamd, double rgaz, double rgazd, int ndir, double* w, double* wd, cudaStream_t st) {
+  BC_DISPATCH(k_bc_wall_profile, prof, profd, gam, gamd, rgaz, rgazd, blow);
 }
 cudaError_t launch_bc_extrap(const GridDesc& g, const BcLine& b, int ndir, double* w, double* wd, cudaStream_t st) {
   BC_DISPATCH(k_bc_extrap);

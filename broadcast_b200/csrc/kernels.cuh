@@ -110,6 +110,8 @@ cudaError_t launch_bc_inlet(const GridDesc& g, const BcLine& b, double gam, int 
 cudaError_t launch_bc_extrap(const GridDesc& g, const BcLine& b, int ndir, double* w, double* wd, cudaStream_t st);
 cudaError_t launch_bc_wall_iso(const GridDesc& g, const BcLine& b, double twall, double gam, double rgaz, int ndir, double* w, double* wd,
                                cudaStream_t st);
+cudaError_t launch_bc_wall_profile(const GridDesc& g, const BcLine& b, bool blow, const double* prof, const double* profd, double gam,
+                                   double gamd, double rgaz, double rgazd, int ndir, double* w, double* wd, cudaStream_t st);
 cudaError_t launch_bc_symmetry(const GridDesc& g, const BcLine& b, int ndir, double* w, double* wd, const double* nx, const double* ny,
                                bool anti, cudaStream_t st);
 cudaError_t launch_bc_pressure(const GridDesc& g, const BcLine& b, double pext, bool noref, double gam, int ndir, double* w, double* wd,

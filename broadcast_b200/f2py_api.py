@@ -120,6 +120,25 @@ def build(backend):
         B("bc_pressure_2d", w, _loc(loc), _interf(interf), float(pext), int(bool(noref)), gam, _in(nx), _in(ny), int(im), int(jm), int(gh),
           int(em) if em is not None else w.shape[2])
 
+    def _prof(a, name):
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel())
+        if a.size < 1:
+            raise ValueError(f"{name}: empty profile")
+        return a
+
+    def bc_wall_blow_profile_2d(w, velprof, loc, gam, interf, gh, im, jm, lm=None):
+        """srcfv/borders/bc_wall_blow_profile.F90:1 (w, velprof, loc, gam, interf, gh, im, jm[, lm])"""
+        _check_cells(_state(w, "w"), im, jm, gh, "w")
+        vp = _prof(velprof, "velprof")
+        B("bc_wall_blow_profile_2d", w, vp, _loc(loc), gam, _interf(interf), int(gh), int(im), int(jm), int(lm) if lm is not None else vp.size)
+
+    def bc_wall_viscous_iso_profile_2d(w, twallprof, loc, gam, rgaz, interf, gh, im, jm, lm=None):
+        """srcfv/borders/bc_wall_viscous_iso_profile.F90:1 (w, twallprof, loc, gam, rgaz, interf, gh, im, jm[, lm])"""
+        _check_cells(_state(w, "w"), im, jm, gh, "w")
+        tp = _prof(twallprof, "twallprof")
+        B("bc_wall_viscous_iso_profile_2d", w, tp, _loc(loc), gam, rgaz, _interf(interf), int(gh), int(im), int(jm),
+          int(lm) if lm is not None else tp.size)
+
     def bc_no_reflexion_2d(w, wbd, loc, interf, nx, ny, gam, gh, im, jm, lm=None):
         _check_cells(_state(w, "w"), im, jm, gh, "w")
         wbd = _in(wbd)
@@ -159,7 +178,8 @@ def build(backend):
     f_bnd = types.SimpleNamespace(
         bc_wall_viscous_adia_2d=bc_wall_viscous_adia_2d, bc_no_reflexion_2d=bc_no_reflexion_2d,
         bc_wall_viscous_iso_2d=bc_wall_viscous_iso_2d, bc_symmetry_2d=bc_symmetry_2d, bc_antisymmetry_2d=bc_antisymmetry_2d,
-        bc_pressure_2d=bc_pressure_2d,
+        bc_pressure_2d=bc_pressure_2d, bc_wall_blow_profile_2d=bc_wall_blow_profile_2d,
+        bc_wall_viscous_iso_profile_2d=bc_wall_viscous_iso_profile_2d,
         bc_supandsubinlet_2d=bc_supandsubinlet_2d, bc_extrapolate_o2_2d=bc_extrapolate_o2_2d,
         jn_match_2d=jn_match_2d, jn_match_geom_2d=jn_match_geom_2d)
 
@@ -194,6 +214,34 @@ def build(backend):
         B("bc_pressure_2d_d", w, wd, _loc(loc), _interf(interf), float(pext), int(bool(noref)), gam, _in(nx), _in(ny), int(im), int(jm),
           int(gh), int(em) if em is not None else w.shape[2])
 
+    def bc_wall_blow_profile_2d_d(w, wd, velprof, velprofd, loc, gam, *rest):
+        """srcfv/tangent/bc_wall_blow_profile_d.f90 (w, wd, velprof, velprofd, loc, gam, gamd, interf, gh, im, jm[, lm]); the sensitivity
+        driver calls it WITHOUT gamd (BROADCAST_npz_sens.py:1763: ..., 'Jlo', gam, interf3, gh, im, jm): both arities are accepted,
+        a missing gamd is 0"""
+        gamd, rest = (0.0, rest) if np.ndim(rest[0]) > 0 else (float(rest[0]), rest[1:])
+        interf, gh, im, jm = rest[:4]
+        lm = rest[4] if len(rest) > 4 else None
+        _check_cells(_state(w, "w"), im, jm, gh, "w")
+        _check_cells(_state(wd, "wd"), im, jm, gh, "wd")
+        vp, vpd = _prof(velprof, "velprof"), _prof(velprofd, "velprofd")
+        B("bc_wall_blow_profile_2d_d", w, wd, vp, vpd, _loc(loc), gam, gamd, _interf(interf), int(gh), int(im), int(jm),
+          int(lm) if lm is not None else vp.size)
+
+    def bc_wall_viscous_iso_profile_2d_d(w, wd, twallprof, twallprofd, loc, gam, *rest):
+        """srcfv/tangent/bc_wall_viscous_iso_profile_d.f90 (w, wd, twallprof, twallprofd, loc, gam, gamd, rgaz, rgazd, interf, gh, im,
+        jm[, lm]); the driver-style call without gamd / rgazd (..., loc, gam, rgaz, interf, gh, im, jm) is accepted too"""
+        if np.ndim(rest[1]) > 0:
+            gamd, rgaz, rgazd, rest = 0.0, float(rest[0]), 0.0, rest[1:]
+        else:
+            gamd, rgaz, rgazd, rest = float(rest[0]), float(rest[1]), float(rest[2]), rest[3:]
+        interf, gh, im, jm = rest[:4]
+        lm = rest[4] if len(rest) > 4 else None
+        _check_cells(_state(w, "w"), im, jm, gh, "w")
+        _check_cells(_state(wd, "wd"), im, jm, gh, "wd")
+        tp, tpd = _prof(twallprof, "twallprof"), _prof(twallprofd, "twallprofd")
+        B("bc_wall_viscous_iso_profile_2d_d", w, wd, tp, tpd, _loc(loc), gam, gamd, rgaz, rgazd, _interf(interf), int(gh), int(im), int(jm),
+          int(lm) if lm is not None else tp.size)
+
     def bc_no_reflexion_2d_d(w, wd, wbd, loc, interf, nx, ny, gam, gh, im, jm, lm=None):
         _check_cells(_state(w, "w"), im, jm, gh, "w")
         _check_cells(_state(wd, "wd"), im, jm, gh, "wd")
@@ -224,6 +272,7 @@ def build(backend):
         bc_wall_viscous_adia_2d_d=bc_wall_viscous_adia_2d_d, bc_no_reflexion_2d_d=bc_no_reflexion_2d_d,
         bc_wall_viscous_iso_2d_d=bc_wall_viscous_iso_2d_d, bc_symmetry_2d_d=bc_symmetry_2d_d,
         bc_antisymmetry_2d_d=bc_antisymmetry_2d_d, bc_pressure_2d_d=bc_pressure_2d_d,
+        bc_wall_blow_profile_2d_d=bc_wall_blow_profile_2d_d, bc_wall_viscous_iso_profile_2d_d=bc_wall_viscous_iso_profile_2d_d,
         bc_supandsubinlet_2d_d=bc_supandsubinlet_2d_d, bc_extrapolate_o2_2d_d=bc_extrapolate_o2_2d_d)
 
     # ------------------------------------------------------------------ f_geom

@@ -105,6 +105,19 @@ int bc_bc_pressure_2d(double* w, const char* loc, const int32_t* interf, double 
                       const double* ny, int im, int jm, int gh, int em);
 int bc_bc_pressure_2d_d(double* w, double* wd, const char* loc, const int32_t* interf, double pext, int noref, double gam,
                         const double* nx, const double* ny, int im, int jm, int gh, int em);
+/* profile walls of the sensitivity driver (BROADCAST_npz_sens.py:1763 flinwall(w, wd, velprof, velprofd, 'Jlo', gam, interf, gh, im, jm);
+ * card_bl2d_fv_npz_sens.py:105): srcfv/borders/bc_wall_blow_profile.F90:1-97 + srcfv/tangent/bc_wall_blow_profile_d.f90,
+ * srcfv/borders/bc_wall_viscous_iso_profile.F90:1-107 + srcfv/tangent/bc_wall_viscous_iso_profile_d.f90.  The shipped tangents treat
+ * the profile, gam and rgaz as active: velprofd / twallprofd (lm values), gamd, rgazd are their tangents. */
+int bc_bc_wall_blow_profile_2d(double* w, const double* velprof, const char* loc, double gam, const int32_t* interf, int gh, int im,
+                               int jm, int lm);
+int bc_bc_wall_blow_profile_2d_d(double* w, double* wd, const double* velprof, const double* velprofd, const char* loc, double gam,
+                                 double gamd, const int32_t* interf, int gh, int im, int jm, int lm);
+int bc_bc_wall_viscous_iso_profile_2d(double* w, const double* twallprof, const char* loc, double gam, double rgaz,
+                                      const int32_t* interf, int gh, int im, int jm, int lm);
+int bc_bc_wall_viscous_iso_profile_2d_d(double* w, double* wd, const double* twallprof, const double* twallprofd, const char* loc,
+                                        double gam, double gamd, double rgaz, double rgazd, const int32_t* interf, int gh, int im,
+                                        int jm, int lm);
 /* srcfv/borders/jn_match.F90:3-66 (3-D arrays, em planes) and jn_match_geom.F90:7-69 (2-D arrays) */
 int bc_jn_match_2d(double* wr, const int32_t* prr, int gh1r, int gh2r, int gh3r, int gh4r, int imr, int jmr,
                    const double* wd, const int32_t* prd, int gh1d, int gh2d, int gh3d, int gh4d, int imd, int jmd,
@@ -224,6 +237,10 @@ int bcd_bc_wall_viscous_iso(double* w, double* wd, int ndir, double twall, const
                             const int32_t* interf, int gh, int im, int jm, void* stream);
 int bcd_bc_symmetry(double* w, double* wd, int ndir, const char* loc, const int32_t* interf, const double* nx,
                     const double* ny, int gh, int im, int jm, int anti /* 1 = bc_antisymmetry_2d */, void* stream);
+/* blow = 1: bc_wall_blow_profile_2d, 0: bc_wall_viscous_iso_profile_2d; prof / profd: device arrays of lm values (profd may be NULL) */
+int bcd_bc_wall_profile(double* w, double* wd, int ndir, int blow, const double* prof, const double* profd, const char* loc,
+                        double gam, double gamd, double rgaz, double rgazd, const int32_t* interf, int gh, int im, int jm, int lm,
+                        void* stream);
 int bcd_bc_pressure(double* w, double* wd, int ndir, const char* loc, const int32_t* interf, double pext, int noref,
                     double gam, const double* nx, const double* ny, int im, int jm, int gh, void* stream);
 int bcd_jn_match(double* wr, const int32_t* prr, int gh1r, int gh2r, int gh3r, int gh4r, int imr, int jmr,

@@ -41,6 +41,10 @@ FILES = [
     ("srcfv/prepro/bc_symmetry.f90", ["bc_symmetry_2d"]),
     ("srcfv/prepro/bc_antisymmetry.f90", ["bc_antisymmetry_2d"]),
     ("srcfv/prepro/bc_pressure.f90", ["bc_pressure_2d"]),
+    ("srcfv/prepro/bc_wall_blow_profile.f90", ["bc_wall_blow_profile_2d"]),
+    ("srcfv/prepro/bc_wall_viscous_iso_profile.f90", ["bc_wall_viscous_iso_profile_2d"]),
+    ("srcfv/tangent/bc_wall_blow_profile_d.f90", None),
+    ("srcfv/tangent/bc_wall_viscous_iso_profile_d.f90", None),
     ("srcfv/tangent/bc_antisymmetry_d.f90", None),
     ("srcfv/tangent/bc_pressure_d.f90", None),
     ("srcfv/tangent/bc_wall_viscous_iso_d.f90", None),

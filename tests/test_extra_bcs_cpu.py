@@ -14,7 +14,16 @@ import helpers as H
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = sorted(glob.glob(os.path.join(HERE, "golden", "bcs", "*.npz")))
 TWALL = 1.3
-NAMES = ["iso", "sym", "anti", "pres", "presnr"]
+NAMES = ["iso", "sym", "anti", "pres", "presnr", "blow", "isoprof"]
+GAMD, RGAZD = 0.3, -0.2      # tangents of the gas constants handed to the profile-wall routines (their shipped tangents are active in them)
+
+
+def profiles(c, name, loc, interf):
+    """seeded wall profile along the line (blowing velocity / wall temperature) and its tangent"""
+    n = int(interf[1, 1] - interf[0, 1] + 1) if loc[0] == "I" else int(interf[1, 0] - interf[0, 0] + 1)
+    rng = np.random.default_rng(17)
+    x = rng.uniform(0.5, 1.5, n)
+    return (1e-2 * (x - 1.0), rng.standard_normal(n) * 1e-2) if name == "blow" else (TWALL * x, rng.standard_normal(n))
 
 
 def sides(c):
@@ -39,13 +48,35 @@ def check_against_golden(g, name, loc, gh, w, wd, w_in, wd_in, tol):
         assert np.array_equal(a, b), (name, loc)
 
 
-def fill(mods, name, c, w, loc, interf, wd=None):
+def fill(mods, name, c, w, loc, interf, wd=None, gas=(0.0, 0.0), prof_shift=0.0):
+    """one fill (primal, or tangent when wd is given); gas / prof_shift displace gam, rgaz and the wall profile of the PRIMAL
+    profile-wall routines (for the finite-difference check of their active scalar inputs)"""
     p = c.phys
+    if prof_shift:
+        pr, prd = profiles(c, name, loc, interf)
+        pr = pr + prof_shift * prd
+        if name == "blow":
+            mods["f_bnd"].bc_wall_blow_profile_2d(w, pr, loc, p["gam"] + gas[0], interf, c.gh, c.im, c.jm)
+        else:
+            mods["f_bnd"].bc_wall_viscous_iso_profile_2d(w, pr, loc, p["gam"] + gas[0], p["rgaz"] + gas[1], interf, c.gh, c.im, c.jm)
+        return
     if name == "iso":
         if wd is None:
             mods["f_bnd"].bc_wall_viscous_iso_2d(w, TWALL, loc, p["gam"], p["rgaz"], interf, c.gh, c.im, c.jm)
         else:
             mods["f_lin"].bc_wall_viscous_iso_2d_d(w, wd, TWALL, loc, p["gam"], p["rgaz"], interf, c.gh, c.im, c.jm)
+    elif name == "blow":
+        pr, prd = profiles(c, name, loc, interf)
+        if wd is None:
+            mods["f_bnd"].bc_wall_blow_profile_2d(w, pr, loc, p["gam"] + gas[0], interf, c.gh, c.im, c.jm)
+        else:
+            mods["f_lin"].bc_wall_blow_profile_2d_d(w, wd, pr, prd, loc, p["gam"], GAMD, interf, c.gh, c.im, c.jm)
+    elif name == "isoprof":
+        pr, prd = profiles(c, name, loc, interf)
+        if wd is None:
+            mods["f_bnd"].bc_wall_viscous_iso_profile_2d(w, pr, loc, p["gam"] + gas[0], p["rgaz"] + gas[1], interf, c.gh, c.im, c.jm)
+        else:
+            mods["f_lin"].bc_wall_viscous_iso_profile_2d_d(w, wd, pr, prd, loc, p["gam"], GAMD, p["rgaz"], RGAZD, interf, c.gh, c.im, c.jm)
     elif name in ("sym", "anti"):
         rt = "bc_symmetry_2d" if name == "sym" else "bc_antisymmetry_2d"
         if wd is None:
@@ -76,8 +107,12 @@ def test_tangent_fill_is_the_derivative_of_the_primal_fill(ref, name, kind, im, 
         w, wd = w0.copy(order="F"), d.copy(order="F")
         fill(ref, name, c, w, loc, interf, wd)
         wp, wm = np.asfortranarray(w0 + 1e-5 * d), np.asfortranarray(w0 - 1e-5 * d)
-        fill(ref, name, c, wp, loc, interf)
-        fill(ref, name, c, wm, loc, interf)
+        if name in ("blow", "isoprof"):      # the profile, gam and rgaz move along with w
+            fill(ref, name, c, wp, loc, interf, gas=(1e-5 * GAMD, 1e-5 * RGAZD), prof_shift=1e-5)
+            fill(ref, name, c, wm, loc, interf, gas=(-1e-5 * GAMD, -1e-5 * RGAZD), prof_shift=-1e-5)
+        else:
+            fill(ref, name, c, wp, loc, interf)
+            fill(ref, name, c, wm, loc, interf)
         fd = (wp - wm) / 2e-5
         assert np.all(H.rel_err(fd, wd) < 1e-7), (name, loc, H.rel_err(fd, wd))
         w1 = w0.copy(order="F")

@@ -728,7 +728,7 @@ def test_dz_tangent_golden(gpu, name):
 # ---------------------------------------------------------------------------------------------------------------------
 # boundary fills of SURVEY.md 8(f3): isothermal wall, symmetry plane (primal and tangent), every side of the block
 # ---------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["iso", "sym", "anti", "pres", "presnr"])
+@pytest.mark.parametrize("name", ["iso", "sym", "anti", "pres", "presnr", "blow", "isoprof"])
 @pytest.mark.parametrize("kind,im,jm", [("bl", 60, 40), ("cyl", 70, 40), ("bl", 7, 7)])
 def test_isothermal_wall_and_symmetry_fills(gpu, ref, name, kind, im, jm):
     import test_extra_bcs_cpu as T
