@@ -69,6 +69,12 @@ cudaError_t launch_dz_tangent(const GridDesc& g, const dzt::Consts& c, double* o
     k_dz_tangent<2><<<grid, dzt::NT, smem, st>>>(t, rc);
   return cudaGetLastError();
 }
+// for the colour loop in jacobian.cu (keeps dz_tangent.cuh out of that translation unit)
+cudaError_t launch_dz_tangent_raw(const GridDesc& g, double cp, double cv, double prandtl, double gam, double cs, double muref, double tref,
+                                  double s_suth, double* out1, double* out2, const double* w, const double* wd0, const double* wd,
+                                  const double* nx, const double* ny, const double* vol, const Rect& rc, cudaStream_t st) {
+  return launch_dz_tangent(g, dzt::make_dz_consts(cp, cv, prandtl, gam, cs, muref, tref, s_suth), out1, out2, w, wd0, wd, nx, ny, vol, rc, st);
+}
 }  // namespace bcast
 
 using namespace bcast;

@@ -241,6 +241,65 @@ extern "C" int bcd_dz_coo(double* jac1, int32_t* ia1, int32_t* ja1, double* jac2
   return BC_OK;
 }
 
+// Colour loop of the sensitivity driver (BROADCAST_npz_sens.py:1741-1800) on the device: derivative of the Dz / Dz2 operator rows applied
+// to a mode (real part wmoder, imaginary part wmodei or null) with respect to the base flow, column by column.  Per colour (l,k): the
+// five seeds at once, the linearised boundary fills of the list, then for every seed m the fused pass k_dz_tangent (both operators,
+// wd0 = seed m, wd = mode) and the scatter rule computejacobianfromdz (misc/ComputeJacobian.f90:708-779).  ia / ja are shared by the
+// real and imaginary value lists, as in the driver (IAdz, JAdz).  Any of the four value lists may be null.
+namespace bcast {
+cudaError_t launch_dz_tangent_raw(const GridDesc& g, double cp, double cv, double prandtl, double gam, double cs, double muref, double tref,
+                                  double s_suth, double* out1, double* out2, const double* w, const double* wd0, const double* wd,
+                                  const double* nx, const double* ny, const double* vol, const Rect& rc, cudaStream_t st);
+}
+
+extern "C" int bcd_dz_tangent_coo(double* jac1r, double* jac1i, int32_t* ia1, int32_t* ja1, double* jac2r, double* jac2i, int32_t* ia2,
+                                  int32_t* ja2, double* w, const double* wmoder, const double* wmodei, const double* nx, const double* ny,
+                                  const double* vol, int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
+                                  double muref, double tref, double s_suth, int im, int jm, const bc_desc_t* bcs, int nbcs, void* stream) {
+  (void)rgaz;
+  if (im < 1 || jm < 1 || gh != 3 || !wmoder) return BC_ERR_ARG;
+  if (((jac1r || jac1i) && (!ia1 || !ja1)) || ((jac2r || jac2i) && (!ia2 || !ja2))) return BC_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const GridDesc g = make_grid_ctx(im, jm, gh);
+  const int s = 2 * gh + 1;
+  double* wd5 = scratch_doubles(20, (size_t)g.sc * 25);
+  double* out5a = scratch_doubles(21, (size_t)g.sc * 25);
+  double* out5b = scratch_doubles(22, (size_t)g.sc * 25);
+  if (!wd5 || !out5a || !out5b) return BC_ERR_ALLOC;
+  const Rect rc{1, im, 1, jm};
+  const long long nt = 5LL * im * jm;
+  const bool want1 = jac1r || jac1i, want2 = jac2r || jac2i;
+  for (int l = 0; l < s; ++l)
+    for (int k = 0; k < s; ++k) {
+      if (!current_colours().has(l * s + k)) continue;
+      cudaError_t e = launch_testvector(g, wd5, 5, 0, l, k, nullptr, st);
+      if (e != cudaSuccess) return (int)e;
+      bc_desc_t act[16];
+      const int nact = nbcs <= 16 ? active_bcs(g, bcs, nbcs, l, k, act) : -1;
+      e = nact >= 0 ? apply_bc_list(g, gam, 5, w, wd5, nx, ny, act, nact, st) : apply_bc_list(g, gam, 5, w, wd5, nx, ny, bcs, nbcs, st);
+      if (e != cudaSuccess) return (int)e;
+      count_launches(1);
+      for (int part = 0; part < 2; ++part) {
+        const double* mode = part == 0 ? wmoder : wmodei;
+        double* j1 = part == 0 ? jac1r : jac1i;
+        double* j2 = part == 0 ? jac2r : jac2i;
+        if (!mode || (!j1 && !j2)) continue;
+        for (int m = 0; m < 5; ++m) {
+          e = launch_dz_tangent_raw(g, cp, cv, prandtl, gam, cs, muref, tref, s_suth, j1 ? out5a + (size_t)m * 5 * g.sc : nullptr,
+                                    j2 ? out5b + (size_t)m * 5 * g.sc : nullptr, w, wd5 + (size_t)m * 5 * g.sc, mode, nx, ny, vol, rc, st);
+          if (e != cudaSuccess) return (int)e;
+        }
+        if (j1) k_scatter5<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(g, SCATTER_DZ, j1, ia1, ja1, out5a, l, k, nullptr, vol, rc, 0);
+        if (j2) k_scatter5<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(g, SCATTER_DZ, j2, ia2, ja2, out5b, l, k, nullptr, vol, rc, 0);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+        count_launches((j1 ? 1 : 0) + (j2 ? 1 : 0));
+      }
+    }
+  (void)want1; (void)want2;
+  return BC_OK;
+}
+
 // The boundary strips of the Jacobian (rows within gh of a physical side) by the reference colour loop, all strips in
 // the SAME 49 passes: seeds (windows of the strips only) -> linearised boundary fills -> tangent of the strip rows with
 // one thread per (cell, face) -> scatter into one compact COO triple per strip (slot order of

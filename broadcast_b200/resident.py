@@ -388,6 +388,31 @@ def dz_coo(blk: "Block", which=(1, 2)):
     return out
 
 
+def dz_tangent_coo(blk: "Block", wmoder, wmodei=None, which=(1, 2)):
+    """COO lists of d/dw [Dz(w) mode] (which 1) and d/dw [Dz2(w) mode] (which 2) by the colour loop of the sensitivity driver
+    (BROADCAST_npz_sens.py:1741-1800) on the device.  Returns {1: (jac_r, jac_i or None, ia, ja), 2: ...}."""
+    im, jm, gh = blk.im, blk.jm, blk.gh
+    s = 2 * gh + 1
+    nb = 25 * s * s * im * jm
+    if nb >= 2 ** 31:
+        raise _lib.BroadcastB200Error("the reference COO layout overflows 32-bit slots at this size")
+    null = ctypes.c_void_p(None)
+    out, args = {}, []
+    for wh in (1, 2):
+        if wh in which:
+            jr = torch.zeros(nb, dtype=torch.float64, device=blk.device)
+            ji = torch.zeros(nb, dtype=torch.float64, device=blk.device) if wmodei is not None else None
+            ia, ja = (torch.zeros(nb, dtype=torch.int32, device=blk.device) for _ in range(2))
+            out[wh] = (jr, ji, ia, ja)
+            args += [_p(jr), _p(ji) if ji is not None else null, _p(ia), _p(ja)]
+        else:
+            args += [null] * 4
+    descs, n = _bc_descs(blk)
+    blk.call("bcd_dz_tangent_coo", *args, _p(blk.w), _p(wmoder), _p(wmodei) if wmodei is not None else null, _p(blk.nx), _p(blk.ny),
+             _p(blk.vol), gh, *blk._phys[:9], im, jm, descs, n, blk._stream())
+    return out
+
+
 def remove_zero_jac(jac, ia, ja, thresh=2e-16):
     """BROADCAST_npz.py:129-135 on the device"""
     keep = jac.abs() > thresh

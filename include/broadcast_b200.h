@@ -317,6 +317,15 @@ int bcd_dz_coo(double* jac1, int32_t* ia1, int32_t* ja1, double* jac2, int32_t* 
                const double* ny, const double* vol, const double* volf, int gh, double cp, double cv, double prandtl, double gam,
                double rgaz, double cs, double muref, double tref, double s_suth, int im, int jm, const bc_desc_t* bcs, int nbcs,
                void* stream);
+/* Colour loop of the sensitivity driver (BROADCAST_npz_sens.py:1741-1800) on the device: d/dw [Dz(w) mode] and d/dw [Dz2(w) mode], column by
+ * column (seeds, linearised boundary fills of the list, f_lindz.coeffs_5p_dz_d / coeffs_5p_dz2_d with wd0 = seed and wd = mode,
+ * computejacobianfromdz).  wmoder / wmodei: real and imaginary part of the mode (wmodei may be NULL); jac1r, jac1i share ia1 / ja1 and
+ * jac2r, jac2i share ia2 / ja2 (the driver's IAdz, JAdz, IAdz2, JAdz2); lists of 25 (2gh+1)^2 im jm entries in the reference's slot
+ * order; any value list may be NULL. */
+int bcd_dz_tangent_coo(double* jac1r, double* jac1i, int32_t* ia1, int32_t* ja1, double* jac2r, double* jac2i, int32_t* ia2,
+                       int32_t* ja2, double* w, const double* wmoder, const double* wmodei, const double* nx, const double* ny,
+                       const double* vol, int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
+                       double muref, double tref, double s_suth, int im, int jm, const bc_desc_t* bcs, int nbcs, void* stream);
 /* Direct block-Jacobian of the regular interior rows (rows whose stencil touches neither ghost cells nor
  * the wall rows: gh+1 <= i <= im-gh, gh+1 <= j <= jm-gh) into the fixed 29-slot pattern, without colouring:
  * values[slot][e][m][cell], cell = (i-1) + (j-1)*im, slot s <-> column-cell offset given by

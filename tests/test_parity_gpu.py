@@ -868,3 +868,48 @@ def test_jacobian_with_isothermal_wall_and_pressure_outlet(gpu, ref):
     p2, i2, d2 = (t.cpu().numpy() for t in hj.to_csr_device(divide_by_vol=False))
     assert np.array_equal(indptr, p2) and np.array_equal(indices, i2) and np.array_equal(data, d2)
     ctx.close()
+
+
+def test_dz_tangent_colour_loop_device(gpu, ref):
+    """device colour loop of the sensitivity matrices d/dw [Dz(w) mode], d/dw [Dz2(w) mode] (bcd_dz_tangent_coo) vs the loop of
+    BROADCAST_npz_sens.py:1741-1800 run on the oracle: seeds, linearised boundary fills, f_lindz.coeffs_5p_dz_d / dz2_d on the real
+    and the imaginary part of a mode, computejacobianfromdz; indices slot-exact, values to TOL"""
+    import torch
+    from broadcast_b200.resident import Block, dz_tangent_coo, _t
+    im, jm = 30, 22
+    a = H.make_case("bl", im, jm, gpu, with_w=True)
+    b = H.make_case("bl", im, jm, ref, with_w=True)
+    rng = np.random.default_rng(14)
+    mr, mi = (np.asfortranarray(rng.standard_normal(a.w.shape)) for _ in range(2))
+    blk = Block(a)
+    blk.apply_bcs()
+    out = dz_tangent_coo(blk, _t(mr, blk.device), _t(mi, blk.device))
+    torch.cuda.synchronize()
+    wb, _ = H.residual_sequence(ref, b)
+    gh = b.gh
+    s = 2 * gh + 1
+    nb = 25 * s * s * im * jm
+    J = {k: np.zeros(nb) for k in ("1r", "1i", "2r", "2i")}
+    I1, K1, I2, K2 = (np.zeros(nb, np.int32) for _ in range(4))
+    dz = b.zeros_state()
+    for m in range(5):
+        for l in range(s):
+            for k in range(s):
+                wd = b.zeros_state()
+                ref["f_misc"].testvector(wd, m, l, k, gh, im, jm)
+                ww = wb.copy(order="F")
+                cases.apply_bcs_lin(b, ww, wd, ref["f_bnd"], ref["f_lin"])
+                for part, mode in (("r", mr), ("i", mi)):
+                    zd = b.zeros_state()
+                    ref["f_lindz"].coeffs_5p_dz_d(dz, zd, ww, wd, mode, *_dz_args(b))
+                    ref["f_misc"].computejacobianfromdz(J["1" + part], I1, K1, zd, m, l, k, gh, im, jm)
+                    zd = b.zeros_state()
+                    ref["f_lindz"].coeffs_5p_dz2_d(dz, zd, ww, wd, mode, *_dz_args(b))
+                    ref["f_misc"].computejacobianfromdz(J["2" + part], I2, K2, zd, m, l, k, gh, im, jm)
+    for wh, Ir, Kr in ((1, I1, K1), (2, I2, K2)):
+        jr, ji, ia, ja = (t.cpu().numpy() for t in out[wh])
+        assert np.array_equal(ia, Ir) and np.array_equal(ja, Kr)
+        for got, key in ((jr, f"{wh}r"), (ji, f"{wh}i")):
+            want = J[key]
+            assert np.abs(want).max() > 0
+            assert np.abs(got - want).max() < TOL * np.abs(want).max(), (key, np.abs(got - want).max() / np.abs(want).max())
