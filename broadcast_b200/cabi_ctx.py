@@ -54,6 +54,12 @@ class Context:
                     d.lm = int(t.shape[0])
                 elif kind in ("wall_iso", "pressure"):
                     d.param[:] = [float(bc[3]), float(bc[4])]
+                elif kind in ("wall_blow_profile", "wall_iso_profile"):
+                    t = np.ascontiguousarray(np.asarray(bc[3], dtype=np.float64).ravel())
+                    self._keep.append(t)
+                    d.table = t.ctypes.data
+                    d.lm = int(t.size)
+                    d.param[:] = [0.0, float(bc[4]) if len(bc) > 4 else 0.0]
                 descs.append(d)
         arr = (_BcDesc * max(len(descs), 1))(*descs)
         _lib.check(self.lib.bcast_ctx_set_bcs(self.h, arr, len(descs)), "bcast_ctx_set_bcs")

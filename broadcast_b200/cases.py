@@ -344,7 +344,8 @@ def apply_bcs(case: Case, w, f_bnd):
 
 # boundary fills of SURVEY.md 8(f3): ("wall_iso", loc, interf, twall, rgaz), ("symmetry" | "antisymmetry", loc, interf),
 # ("pressure", loc, interf, pext, noref)
-_EXTRA_BCS = ("wall_iso", "symmetry", "antisymmetry", "pressure")
+# ("wall_blow_profile", loc, interf, velprof), ("wall_iso_profile", loc, interf, twallprof, rgaz): profile passive in the tangent
+_EXTRA_BCS = ("wall_iso", "symmetry", "antisymmetry", "pressure", "wall_blow_profile", "wall_iso_profile")
 
 
 def _extra_bc(case, kind, bc, w, wd, f_bnd, f_lin):
@@ -354,6 +355,17 @@ def _extra_bc(case, kind, bc, w, wd, f_bnd, f_lin):
             f_bnd.bc_wall_viscous_iso_2d(w, bc[3], bc[1], gam, bc[4], bc[2], gh, im, jm)
         else:
             f_lin.bc_wall_viscous_iso_2d_d(w, wd, bc[3], bc[1], gam, bc[4], bc[2], gh, im, jm)
+    elif kind == "wall_blow_profile":
+        if wd is None:
+            f_bnd.bc_wall_blow_profile_2d(w, bc[3], bc[1], gam, bc[2], gh, im, jm)
+        else:
+            f_lin.bc_wall_blow_profile_2d_d(w, wd, bc[3], np.zeros_like(np.asarray(bc[3], dtype=float)), bc[1], gam, 0.0, bc[2], gh, im, jm)
+    elif kind == "wall_iso_profile":
+        if wd is None:
+            f_bnd.bc_wall_viscous_iso_profile_2d(w, bc[3], bc[1], gam, bc[4], bc[2], gh, im, jm)
+        else:
+            f_lin.bc_wall_viscous_iso_profile_2d_d(w, wd, bc[3], np.zeros_like(np.asarray(bc[3], dtype=float)), bc[1], gam, 0.0, bc[4], 0.0,
+                                                   bc[2], gh, im, jm)
     elif kind in ("symmetry", "antisymmetry"):
         if wd is None:
             getattr(f_bnd, "bc_%s_2d" % kind)(w, bc[1], bc[2], case.nx, case.ny, gh, im, jm)

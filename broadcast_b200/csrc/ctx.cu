@@ -131,8 +131,9 @@ extern "C" int bcast_ctx_set_bcs(bcast_ctx_t* c, const bc_desc_t* bcs, int nbcs)
     size_t n = 0;
     if (d.kind == BC_KIND_INLET) n = (size_t)d.lm * c->gh * 5;
     else if (d.kind == BC_KIND_NOREF) n = (size_t)d.lm * 5;
+    else if (d.kind == BC_KIND_WALL_BLOW_PROFILE || d.kind == BC_KIND_WALL_ISO_PROFILE) n = (size_t)d.lm;
     else if (d.kind == BC_KIND_JOIN) c->has_join = true;
-    else if (d.kind != BC_KIND_EXTRAP && d.kind != BC_KIND_WALL && (d.kind < BC_KIND_WALL_ISO || d.kind > BC_KIND_PRESSURE)) return BC_ERR_ARG;
+    else if (d.kind != BC_KIND_EXTRAP && d.kind != BC_KIND_WALL && (d.kind < BC_KIND_WALL_ISO || d.kind > BC_KIND_WALL_ISO_PROFILE)) return BC_ERR_ARG;
     if (n) {
       if (!d.table || d.lm < 1) return BC_ERR_ARG;
       double* t = nullptr;

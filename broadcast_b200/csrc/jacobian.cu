@@ -36,6 +36,11 @@ static cudaError_t apply_bc_list(const GridDesc& g, double gam, int ndir, double
         case BC_KIND_SYMMETRY: e = launch_bc_symmetry(g, line, ndir, w, wd, nx, ny, false, st); break;
         case BC_KIND_ANTISYMMETRY: e = launch_bc_symmetry(g, line, ndir, w, wd, nx, ny, true, st); break;
         case BC_KIND_PRESSURE: e = launch_bc_pressure(g, line, d.param[0], d.param[1] != 0.0, gam, ndir, w, wd, nx, ny, st); break;
+        case BC_KIND_WALL_BLOW_PROFILE:
+        case BC_KIND_WALL_ISO_PROFILE:
+          if (!d.table || d.lm < line.lmax) return cudaErrorInvalidValue;
+          e = launch_bc_wall_profile(g, line, d.kind == BC_KIND_WALL_BLOW_PROFILE, d.table, nullptr, gam, 0.0, d.param[1], 0.0, ndir, w, wd, st);
+          break;
         default: return cudaErrorInvalidValue;
       }
       count_launches(1);

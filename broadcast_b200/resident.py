@@ -72,6 +72,10 @@ class Block:
                                  wbd.shape[0]))
             elif kind in ("outflow", "wall", "symmetry", "antisymmetry"):
                 self.bcs.append((kind, bc[1].encode(), _interf(bc[2])))
+            elif kind in ("wall_blow_profile", "wall_iso_profile"):   # (kind, loc, interf, profile[, rgaz]); profile passive
+                prof = np.ascontiguousarray(np.asarray(bc[3], dtype=np.float64).ravel())
+                self.bcs.append((kind, bc[1].encode(), _interf(bc[2]), torch.from_numpy(prof).to(device), prof.size,
+                                 float(bc[4]) if len(bc) > 4 else 0.0))
             elif kind in ("wall_iso", "pressure"):     # (kind, loc, interf, twall, rgaz) / (kind, loc, interf, pext, noref)
                 self.bcs.append((kind, bc[1].encode(), _interf(bc[2]), float(bc[3]), float(bc[4])))
             elif kind == "jn":
@@ -134,6 +138,10 @@ class Block:
             elif kind in ("symmetry", "antisymmetry"):
                 self._ck(L.bcd_bc_symmetry(_p(w), _p(wd), ndir, bc[1], I(bc[2]), _p(self.nx), _p(self.ny), gh, im, jm,
                                            int(kind == "antisymmetry"), st), "bcd_bc_symmetry")
+            elif kind in ("wall_blow_profile", "wall_iso_profile"):
+                self._ck(L.bcd_bc_wall_profile(_p(w), _p(wd), ndir, int(kind == "wall_blow_profile"), _p(bc[3]), ctypes.c_void_p(None), bc[1],
+                                               ctypes.c_double(self.gam), ctypes.c_double(0.0), ctypes.c_double(bc[5]), ctypes.c_double(0.0),
+                                               I(bc[2]), gh, im, jm, bc[4], st), "bcd_bc_wall_profile")
             elif kind == "pressure":
                 self._ck(L.bcd_bc_pressure(_p(w), _p(wd), ndir, bc[1], I(bc[2]), ctypes.c_double(bc[3]), int(bc[4] != 0.0),
                                            ctypes.c_double(self.gam), _p(self.nx), _p(self.ny), im, jm, gh, st), "bcd_bc_pressure")
@@ -297,7 +305,8 @@ class _BcDesc(ctypes.Structure):
                 ("tr", ctypes.c_int32 * 2), ("lm", ctypes.c_int32), ("table", ctypes.c_void_p), ("param", ctypes.c_double * 2)]
 
 
-_KIND = {"inflow": 1, "noref": 2, "outflow": 3, "wall": 4, "jn": 5, "wall_iso": 6, "symmetry": 7, "antisymmetry": 8, "pressure": 9}
+_KIND = {"inflow": 1, "noref": 2, "outflow": 3, "wall": 4, "jn": 5, "wall_iso": 6, "symmetry": 7, "antisymmetry": 8, "pressure": 9, "wall_blow_profile": 10,
+         "wall_iso_profile": 11}
 SCATTER = {"jv": 0, "jv_relaxed": 1, "dz": 2, "jv_relaxed_withjn": 3, "jv_withjn": 4, "jv_dbyvol": 5, "jv_relaxed_dbyvol": 6}
 
 
@@ -323,6 +332,10 @@ def _bc_descs(blk: "Block"):
                 d.lm = int(bc[4])
             elif kind in ("wall_iso", "pressure"):
                 d.param[:] = [bc[3], bc[4]]
+            elif kind in ("wall_blow_profile", "wall_iso_profile"):
+                d.table = bc[3].data_ptr()
+                d.lm = int(bc[4])
+                d.param[:] = [0.0, bc[5]]
             out.append(d)
     arr = (_BcDesc * len(out))(*out)
     return arr, len(out)

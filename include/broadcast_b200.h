@@ -278,6 +278,8 @@ int bcd_norm_sums(double* out10, const double* rhs, int im, int jm, int gh, void
 #define BC_KIND_SYMMETRY 7      /* bc_symmetry_2d                                          */
 #define BC_KIND_ANTISYMMETRY 8  /* bc_antisymmetry_2d                                      */
 #define BC_KIND_PRESSURE 9      /* bc_pressure_2d           param = {pext, noref (0 / 1)}  */
+#define BC_KIND_WALL_BLOW_PROFILE 10  /* bc_wall_blow_profile_2d        table = velprof(lm)   (passive in the colour loops) */
+#define BC_KIND_WALL_ISO_PROFILE 11   /* bc_wall_viscous_iso_profile_2d table = twallprof(lm), param = {unused, rgaz}       */
 typedef struct {
   int32_t kind;
   char loc[4];
@@ -286,7 +288,7 @@ typedef struct {
   int32_t tr[2];     /* kind 5 only */
   int32_t lm;
   const double* table;
-  double param[2];   /* scalar arguments of kinds 6 and 9 */
+  double param[2];   /* scalar arguments of kinds 6, 9 and 11 */
 } bc_desc_t;
 
 /* Reference colour loop (BROADCAST_npz.py:1068-1127 / cylinder.py:941-978) entirely on the device:

@@ -35,7 +35,8 @@ int main(int argc, char** argv) {
     memcpy(bcs[k].tr, rec + 13, 8);
     bcs[k].lm = rec[15];
     RD(bcs[k].param, 2);
-    size_t n = bcs[k].kind == BC_KIND_INLET ? (size_t)rec[15] * gh * 5 : bcs[k].kind == BC_KIND_NOREF ? (size_t)rec[15] * 5 : 0;
+    size_t n = bcs[k].kind == BC_KIND_INLET ? (size_t)rec[15] * gh * 5 : bcs[k].kind == BC_KIND_NOREF ? (size_t)rec[15] * 5
+               : bcs[k].kind >= BC_KIND_WALL_BLOW_PROFILE ? (size_t)rec[15] : 0;
     if (n) {
       double* t = malloc(n * 8);
       RD(t, n);

@@ -820,7 +820,7 @@ def test_c_abi_context_jacobian_csr(gpu, ref, kind, im, jm):
     ctx.close()
 
 
-def _bl_case_with_extra_bcs(mods, im, jm):
+def _bl_case_with_extra_bcs(mods, im, jm, variant="iso+pressure"):
     """boundary layer with an ISOTHERMAL wall at Jlo and a PRESSURE outlet (characteristic blend) at Ihi instead of the adiabatic
     wall / extrapolation of card_bl2d_fv_npz.py -- the variants card_bl2d_fv.py:110 and card_bl2d_fv_cgns.py:102 select"""
     c = H.make_case("bl", im, jm, mods, with_w=True)
@@ -829,9 +829,14 @@ def _bl_case_with_extra_bcs(mods, im, jm):
     pr = (p["gam"] - 1.0) * (q[4] - 0.5 * (q[1] ** 2 + q[2] ** 2 + q[3] ** 2) / q[0])
     bcs = []
     for bc in c.bcs:
-        if bc[0] == "wall":
+        x = np.random.default_rng(23).uniform(0.5, 1.5, im + 2 * g)        # the wall line of this case spans 1-gh .. im+gh
+        if bc[0] == "wall" and variant == "iso+pressure":
             bcs.append(("wall_iso", bc[1], bc[2], 1.05 * pr / (q[0] * p["rgaz"]), p["rgaz"]))
-        elif bc[0] == "outflow":
+        elif bc[0] == "wall" and variant == "blow_profile":      # the sensitivity driver's wall (BROADCAST_npz_sens.py:1763)
+            bcs.append(("wall_blow_profile", bc[1], bc[2], 1e-3 * (x - 1.0)))
+        elif bc[0] == "wall" and variant == "iso_profile":
+            bcs.append(("wall_iso_profile", bc[1], bc[2], 1.05 * pr / (q[0] * p["rgaz"]) * x, p["rgaz"]))
+        elif bc[0] == "outflow" and variant == "iso+pressure":
             bcs.append(("pressure", bc[1], bc[2], 0.97 * pr, 1.0))
         else:
             bcs.append(bc)
@@ -839,14 +844,15 @@ def _bl_case_with_extra_bcs(mods, im, jm):
     return c
 
 
-def test_jacobian_with_isothermal_wall_and_pressure_outlet(gpu, ref):
+@pytest.mark.parametrize("variant", ["iso+pressure", "blow_profile", "iso_profile"])
+def test_jacobian_with_isothermal_wall_and_pressure_outlet(gpu, ref, variant):
     """the new boundary kinds inside the device colour loops: residual step, hybrid Jacobian (interior blocks + strip loop with the
     linearised isothermal-wall / pressure fills) and the C-ABI context, against the reference loop on the CPU"""
     import scipy.sparse as sp
     from broadcast_b200.cabi_ctx import Context
     from broadcast_b200.resident import Block, jacobian_hybrid
     im, jm = 44, 28
-    a, b = _bl_case_with_extra_bcs(gpu, im, jm), _bl_case_with_extra_bcs(ref, im, jm)
+    a, b = _bl_case_with_extra_bcs(gpu, im, jm, variant), _bl_case_with_extra_bcs(ref, im, jm, variant)
     wa, ra = H.residual_sequence(gpu, a)
     wb, rb = H.residual_sequence(ref, b)
     assert np.all(H.rel_err(wa, wb) < TOL) and np.all(H.rel_err(ra, rb) < TOL)
