@@ -158,3 +158,27 @@ def test_ref_reproduces_the_bc_golden(ref, path):
             w, wd = w0.copy(order="F"), d.copy(order="F")
             fill(ref, name, c, w, loc, interf, wd)
             check_against_golden(g, name, loc, c.gh, w, wd, w0, d, 1e-13)
+
+
+def test_profile_wall_tangents_accept_the_driver_arity(ref):
+    """BROADCAST_npz_sens.py:1763 calls flinwall(w, wd, velprof, velprofd, 'Jlo', gam, interf, gh, im, jm): no gamd, although the shipped
+    Tapenade routine has one.  The signature layer (shared by the product and the oracle) takes both; a missing gamd / rgazd is 0."""
+    c = H.make_case("bl", 20, 12, ref, with_w=True)
+    w0, _ = H.residual_sequence(ref, c)
+    p = c.phys
+    loc, interf = sides(c)[2]
+    d = np.asfortranarray(np.random.default_rng(1).standard_normal(w0.shape))
+    for name in ("blow", "isoprof"):
+        pr, prd = profiles(c, name, loc, interf)
+        outs = []
+        for driver_style in (True, False):
+            w, wd = w0.copy(order="F"), d.copy(order="F")
+            if name == "blow":
+                args = (p["gam"],) if driver_style else (p["gam"], 0.0)
+                ref["f_lin"].bc_wall_blow_profile_2d_d(w, wd, pr, prd, loc, *args, interf, c.gh, c.im, c.jm)
+            else:
+                args = (p["gam"], p["rgaz"]) if driver_style else (p["gam"], 0.0, p["rgaz"], 0.0)
+                ref["f_lin"].bc_wall_viscous_iso_profile_2d_d(w, wd, pr, prd, loc, *args, interf, c.gh, c.im, c.jm)
+            outs.append((w, wd))
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+        assert not np.array_equal(outs[0][1], d)
