@@ -125,27 +125,38 @@ extern "C" int bcast_ctx_set_geometry(bcast_ctx_t* c, const double* nx, const do
 // the driver's ordered boundary list; here the tables are HOST Fortran arrays (field(lm,gh,5), wbd(lm,5)): copied to the device
 extern "C" int bcast_ctx_set_bcs(bcast_ctx_t* c, const bc_desc_t* bcs, int nbcs) {
   if (!c || nbcs < 0 || (nbcs && !bcs)) return BC_ERR_ARG;
-  free_tables(c);
+  // the new list is built aside and swapped in only when every entry was accepted: an error leaves the installed list untouched
+  std::vector<bc_desc_t> list;
+  std::vector<double*> tabs;
+  bool join = false;
+  auto fail = [&](int code) {
+    for (double* t : tabs) cudaFree(t);
+    return code;
+  };
   for (int k = 0; k < nbcs; ++k) {
     bc_desc_t d = bcs[k];
     size_t n = 0;
     if (d.kind == BC_KIND_INLET) n = (size_t)d.lm * c->gh * 5;
     else if (d.kind == BC_KIND_NOREF) n = (size_t)d.lm * 5;
     else if (d.kind == BC_KIND_WALL_BLOW_PROFILE || d.kind == BC_KIND_WALL_ISO_PROFILE) n = (size_t)d.lm;
-    else if (d.kind == BC_KIND_JOIN) c->has_join = true;
-    else if (d.kind != BC_KIND_EXTRAP && d.kind != BC_KIND_WALL && (d.kind < BC_KIND_WALL_ISO || d.kind > BC_KIND_WALL_ISO_PROFILE)) return BC_ERR_ARG;
+    else if (d.kind == BC_KIND_JOIN) join = true;
+    else if (d.kind != BC_KIND_EXTRAP && d.kind != BC_KIND_WALL && (d.kind < BC_KIND_WALL_ISO || d.kind > BC_KIND_WALL_ISO_PROFILE)) return fail(BC_ERR_ARG);
     if (n) {
-      if (!d.table || d.lm < 1) return BC_ERR_ARG;
+      if (!d.table || d.lm < 1) return fail(BC_ERR_ARG);
       double* t = nullptr;
-      if (cudaMalloc((void**)&t, n * sizeof(double)) != cudaSuccess) return BC_ERR_ALLOC;
-      c->tables.push_back(t);
-      CTX_CK(cudaMemcpy(t, d.table, n * sizeof(double), cudaMemcpyHostToDevice));
+      if (cudaMalloc((void**)&t, n * sizeof(double)) != cudaSuccess) return fail(BC_ERR_ALLOC);
+      tabs.push_back(t);
+      if (cudaMemcpy(t, d.table, n * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) return fail(BC_ERR_ALLOC);
       d.table = t;
     } else {
       d.table = nullptr;
     }
-    c->bcs.push_back(d);
+    list.push_back(d);
   }
+  free_tables(c);
+  c->bcs.swap(list);
+  c->tables.swap(tabs);
+  c->has_join = join;
   return BC_OK;
 }
 

@@ -179,6 +179,12 @@ extern "C" int bcd_jacobian_coo(double* jac, int32_t* ia, int32_t* ja, double* w
   for (int b = 0; b < nbcs; ++b) has_join = has_join || bcs[b].kind == BC_KIND_JOIN;
   const RectList seed_list = one_rect(rc);
   const RectList* seed_rows = (rect && !has_join) ? &seed_list : nullptr;
+  // every ghost of w holds the value of this list before the passes start (they refresh only the sides their seeds reach)
+  {
+    cudaError_t e0 = apply_bc_list(g, gam, 0, w, nullptr, nx, ny, bcs, nbcs, st);
+    if (e0 != cudaSuccess) return (int)e0;
+    count_launches(nbcs);
+  }
   for (int l = 0; l < s; ++l)
     for (int k = 0; k < s; ++k) {
       if (!current_colours().has(l * s + k)) continue;   // colour sharding: this rank's passes only
@@ -219,6 +225,12 @@ extern "C" int bcd_dz_coo(double* jac1, int32_t* ia1, int32_t* ja1, double* jac2
   if (!wd5 || !out5) return BC_ERR_ALLOC;
   const Rect rc{1, im, 1, jm};
   const long long nt = 5LL * im * jm;
+  // every ghost of w holds the value of this list before the passes start (they refresh only the sides their seeds reach)
+  {
+    cudaError_t e0 = apply_bc_list(g, gam, 0, w, nullptr, nx, ny, bcs, nbcs, st);
+    if (e0 != cudaSuccess) return (int)e0;
+    count_launches(nbcs);
+  }
   for (int l = 0; l < s; ++l)
     for (int k = 0; k < s; ++k) {
       if (!current_colours().has(l * s + k)) continue;   // colour sharding: this rank's passes only
@@ -274,6 +286,12 @@ extern "C" int bcd_dz_tangent_coo(double* jac1r, double* jac1i, int32_t* ia1, in
   const Rect rc{1, im, 1, jm};
   const long long nt = 5LL * im * jm;
   const bool want1 = jac1r || jac1i, want2 = jac2r || jac2i;
+  // every ghost of w holds the value of this list before the passes start (they refresh only the sides their seeds reach)
+  {
+    cudaError_t e0 = apply_bc_list(g, gam, 0, w, nullptr, nx, ny, bcs, nbcs, st);
+    if (e0 != cudaSuccess) return (int)e0;
+    count_launches(nbcs);
+  }
   for (int l = 0; l < s; ++l)
     for (int k = 0; k < s; ++k) {
       if (!current_colours().has(l * s + k)) continue;
@@ -379,6 +397,15 @@ extern "C" int bcd_jacobian_strips(int nrect, const int32_t* rects /* [nrect][4]
   };
   // the 49 passes on one stream (K = 1) or dealt round-robin to K chain streams forked from s_ and joined at the end
   auto run = [&](cudaStream_t s_, cudaStream_t* cs, cudaEvent_t fork, cudaEvent_t* join) -> cudaError_t {
+    // The passes below apply the combined primal + tangent fills only on the sides their seeds can reach (active_bcs), and with
+    // K > 1 several colours write w's ghosts while other chains read them: both are correct only if every ghost of w already
+    // holds the value of the SAME list (the reference loop refreshes all of them in every colour, BROADCAST_npz.py:1079-1082).
+    // Establish that here, once, before the fork -- the caller does not have to.
+    {
+      cudaError_t e0 = apply_bc_list(g, gam, 0, w, nullptr, nx, ny, bcs, nbcs, s_);
+      if (e0 != cudaSuccess) return e0;
+      nlaunch += nbcs;
+    }
     if (K > 1) {
       cudaEventRecord(fork, s_);
       for (int c = 0; c < K; ++c) cudaStreamWaitEvent(cs[c], fork, 0);
@@ -431,7 +458,7 @@ extern "C" int bcd_jacobian_strips(int nrect, const int32_t* rects /* [nrect][4]
   for (int b = 0; b < nbcs; ++b) {
     const bc_desc_t& d = bcs[b];
     put(&d.kind, sizeof d.kind); put(d.loc, 3); put(d.window, sizeof d.window); put(d.prd, sizeof d.prd); put(d.tr, sizeof d.tr);
-    put(&d.lm, sizeof d.lm); put(&d.table, sizeof d.table);
+    put(&d.lm, sizeof d.lm); put(&d.table, sizeof d.table); put(d.param, sizeof d.param);   // param: baked into the captured arguments
   }
   for (int q = 0; q < nrect; ++q) { put(&jac[q], sizeof(void*)); put(&ia[q], sizeof(void*)); put(&ja[q], sizeof(void*)); }
   const void* ptrs[] = {w, nx, ny, vol, volf, coefdiag};

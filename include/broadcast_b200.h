@@ -295,8 +295,8 @@ typedef struct {
  * for every colour (l,k): seeds for the 5 variables at once (vector tangent mode), linearised boundary
  * fills in list order, tangent of the residual, scatter.  Output = the reference's own COO arrays
  * (jac, ia, ja of length 25*(2gh+1)^2*im*jm, slot order of misc/ComputeJacobian.f90:524), on the device.
- * scatter_kind as in bcd_scatter.  handle_bc_style != 0 reproduces handleBC.applyBC(mode 1): the primal
- * fill is re-applied after each linearised one (cylinder driver).  rect (or null) restricts the rows
+ * scatter_kind as in bcd_scatter.  The primal list is applied to w once before the first colour (handleBC.applyBC(mode 1) of the
+ * cylinder driver re-applies it in every colour: same ghosts, they depend on interior cells only).  rect (or null) restricts the rows
  * that are evaluated to cells i0..i1 x j0..j1 (others keep their previous content); with compact != 0 the
  * outputs have 25*(2gh+1)^2*wi*wj entries, slot order as above over the rectangle's own (wi x wj) index space
  * (ia/ja stay global). */
