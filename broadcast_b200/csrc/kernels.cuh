@@ -155,7 +155,9 @@ cudaError_t launch_norms(const GridDesc& g, const double* res, double* out10 /*d
 
 // fused, shared-memory tiled primal residual (residual_tile.cu)
 // variant: RES_DEFAULT (= k_residual_fast), RES_FAST_TMA (persistent CTAs + TMA staging of w), RES_TILE_V1 (first generation)
-enum ResidualVariant { RES_DEFAULT = 0, RES_GENERIC = 1, RES_FAST_TMA = 2, RES_TILE_V1 = 3 };
+//          RES_DEFAULT = k_residual_march (j-marching persistent kernel, TMA + LDGSTS fed rings; residual_march.cu) with
+//          k_residual_fast as its fallback; RES_FAST_TILE = k_residual_fast (the 32 x 9 tile kernel, default of round 1)
+enum ResidualVariant { RES_DEFAULT = 0, RES_GENERIC = 1, RES_FAST_TMA = 2, RES_TILE_V1 = 3, RES_FAST_TILE = 4 };
 cudaError_t launch_residual_tiled(const GridDesc& g, const SchemeArgs& a, bool wall, double* res, const double* w, const double* nx,
                                   const double* ny, const double* vol, const double* volf, cudaStream_t st, int variant = RES_DEFAULT,
                                   int part = 0);
@@ -163,5 +165,9 @@ cudaError_t launch_residual_tiled(const GridDesc& g, const SchemeArgs& a, bool w
 // second-generation fused residual (residual_fast.cu): re-associated face formulas, shared normal-direction interpolations
 cudaError_t launch_residual_fast(const GridDesc& g, const SchemeArgs& a, bool wall, double* res, const double* w, const double* nx,
                                  const double* ny, const double* vol, const double* volf, cudaStream_t st, bool tma, int part = 0);
+
+// third-generation fused residual (residual_march.cu): persistent j-marching CTAs; *done = false -> caller falls back
+cudaError_t launch_residual_march(const GridDesc& g, const SchemeConsts& c, double sqgr, bool wall, double* res, const double* w,
+                                  const double* nx, const double* ny, const double* vol, const double* volf, cudaStream_t st, bool* done);
 
 }  // namespace bcast

@@ -218,6 +218,13 @@ cudaError_t launch_residual_tiled(const GridDesc& g, const SchemeArgs& a, bool w
   // second-generation kernel (residual_fast.cu) unless the first one is asked for as a cross-check
   static const bool v1 = getenv("BROADCAST_B200_RESIDUAL_V1") != nullptr;
   static const bool tma = getenv("BROADCAST_B200_RESIDUAL_TMA") != nullptr;
+  static const bool no_march = getenv("BROADCAST_B200_RESIDUAL_TILE") != nullptr;
+  if (variant == RES_DEFAULT && part == 0 && !v1 && !tma && !no_march) {   // the marching kernel; falls through when TMA cannot describe the arrays
+    const SchemeConsts c = make_consts(a.cp, a.cv, a.prandtl, a.gam, a.rgaz, a.cs, a.muref, a.tref, a.s_suth, a.k2, a.k4);
+    bool done = false;
+    cudaError_t e = launch_residual_march(g, c, ::sqrt(a.gam * a.rgaz), wall, res, w, nx, ny, vol, volf, st, &done);
+    if (done || e != cudaSuccess) return e;
+  }
   if (variant != RES_TILE_V1 && !(variant == RES_DEFAULT && v1))
     return launch_residual_fast(g, a, wall, res, w, nx, ny, vol, volf, st, variant == RES_FAST_TMA || (variant == RES_DEFAULT && tma), part);
   constexpr int TI = 32, TJ = 8;

@@ -47,24 +47,28 @@ def test_boundary_fill_and_residual(gpu, ref, kind, im, jm):
 
 @pytest.mark.parametrize("kind,im,jm", [("bl", 60, 40), ("bl", 97, 33), ("cyl", 70, 40), ("bl", 300, 70)])
 def test_residual_kernel_variants_agree(gpu, ref, kind, im, jm):
-    """default fused kernel, reference-shaped pipeline, fused + TMA/persistent (even leading dimension: TMA; odd: its LDG
-    fallback) and the first-generation fused kernel: each within TOL of the oracle; the TMA variant runs the same phase
-    functions as the default one on the same operands, so those two agree bit for bit"""
+    """default j-marching kernel (0), reference-shaped pipeline (1), tile kernel + TMA/persistent (2; odd leading dimension: its LDG
+    fallback), first-generation tile kernel (3) and the 32 x 9 tile kernel (4): each within the parity bound of the oracle.  Variants
+    2 and 4 run the same phase functions on the same operands and agree bit for bit; the marching kernel evaluates the same face
+    formulas from another instruction stream (the compiler contracts other multiply-adds): it agrees with 4 to a few ulp of the
+    face fluxes."""
     import torch
     from broadcast_b200.resident import Block
     a = H.make_case(kind, im, jm, gpu, with_w=True)
     b = H.make_case(kind, im, jm, ref, with_w=True)
-    _, rb = H.residual_sequence(ref, b)
+    wb, rb = H.residual_sequence(ref, b)
+    floor = H.fma_floor(b)
     blk = Block(a)
     blk.apply_bcs()
     gh = a.gh
-    outs = {}
-    for v in (0, 1, 2, 3):
+    outs, np_outs = {}, {}
+    for v in (0, 1, 2, 3, 4):
         r = blk.residual(variant=v).clone()
         outs[v] = r
-        rn = np.ascontiguousarray(r.cpu().numpy().transpose(2, 1, 0))     # (planes, j, i) image -> (i, j, planes)
-        assert np.all(H.rel_err(rn[gh:-gh, gh:-gh], rb[gh:-gh, gh:-gh]) < TOL), (v, H.rel_err(rn[gh:-gh, gh:-gh], rb[gh:-gh, gh:-gh]))
-    assert torch.equal(outs[0], outs[2])
+        np_outs[v] = np.asfortranarray(r.cpu().numpy().transpose(2, 1, 0))     # (planes, j, i) image -> (i, j, planes)
+        H.assert_residual_parity(np_outs[v], rb, b, wb, floor=floor, what=("variant", v))
+    assert torch.equal(outs[4], outs[2])
+    assert np.all(H.backward_err(np_outs[0], np_outs[4], b, wb) < 1e-14)
 
 
 @pytest.mark.parametrize("kind,im,jm", [("bl", 7, 7), ("bl", 8, 8), ("bl", 33, 7), ("bl", 9, 10), ("cyl", 14, 9), ("bl", 3, 12), ("bl", 12, 5)])
@@ -92,7 +96,7 @@ def test_residual_in_two_parts_equals_the_whole(gpu, im, jm):
     c = H.make_case("bl", im, jm, gpu, with_w=True)
     blk = Block(c)
     blk.apply_bcs()
-    whole = blk.residual().clone()
+    whole = blk.residual(variant=4).clone()     # the tile kernel in one launch (the split launches are tile-kernel launches)
     gh = c.gh
     w_ok = blk.w.clone()
     blk.res.zero_()
@@ -113,7 +117,7 @@ def test_residual_full_size_properties(gpu):
     """C5 (8192 x 2048, BASELINE.json's bench configuration): the oracle cannot run there in seconds, so size-independent
     properties: (1) the fused kernels agree with the reference-shaped pipeline to TOL-level noise (the reference's own
     FMA / no-FMA builds differ by 1e-12 of the plane maximum at 126 x 60 already, profiles/r1_d_summary.md; bound 5e-12),
-    (2) no NaN, ghost frame untouched, (3) the TMA variant equals the default bit for bit, (4) translation invariance of the
+    (2) no NaN, ghost frame untouched, (3) the TMA tile variant equals the tile kernel bit for bit, (4) translation invariance of the
     tiling: the residual of an i-window of the grid computed as its own block equals the same cells of the full grid away from
     the window's edges bit for bit (each cell's result must not depend on which tile it falls in)."""
     import torch
@@ -127,23 +131,30 @@ def test_residual_full_size_properties(gpu):
     r0 = blk.residual(variant=0).clone()
     rg = blk.residual(variant=1).clone()
     r2 = blk.residual(variant=2).clone()
+    r4 = blk.residual(variant=4).clone()
     assert not torch.isnan(r0).any()
-    assert torch.equal(r0, r2)
+    assert torch.equal(r4, r2)
     inner = (slice(None), slice(gh, -gh), slice(gh, -gh))
     scale = rg[inner].abs().amax(dim=(1, 2))
-    err = (r0[inner] - rg[inner]).abs().amax(dim=(1, 2))
-    ok = (err <= 5e-12 * scale) | (scale == 0)
-    assert bool(ok.all()), (err / scale).tolist()
+    for r in (r0, r4):
+        err = (r[inner] - rg[inner]).abs().amax(dim=(1, 2))
+        ok = (err <= 5e-12 * scale) | (scale == 0)
+        assert bool(ok.all()), (err / scale).tolist()
     assert float(r0[:, :gh].abs().max()) == 0.0 and float(r0[:, :, :gh].abs().max()) == 0.0
-    # tiling invariance: the middle third of the columns as an i-slab with two internal edges (tile origin shifted by 11 cells)
+    assert float(r0[:, -gh:].abs().max()) == 0.0 and float(r0[:, :, -gh:].abs().max()) == 0.0
+    # tiling invariance: an i-window of the grid as an i-slab with two internal edges whose first column is not a multiple of 32
+    # away from the full grid's tiles / strips.  Window (1 of 3) has an odd width (the marching kernel needs an even leading
+    # dimension for its tensor maps and falls back to the tile kernel): tile kernel; window (2 of 5) has an even width: marching.
     from broadcast_b200 import sharding
-    case_w, desc = sharding.slab_of(c, 1, 3)
-    lo, hi = sharding.slab_range(im, 1, 3)
-    assert (lo - 1) % 32 != 0
-    wb = Block(case_w, slab=desc)
-    wb.w.copy_(blk.w[:, :, lo - 1:hi + 2 * gh])      # the full block's state, boundary fills included
-    rw = wb.residual(variant=0)
-    assert torch.equal(rw[:, gh:-gh, gh:-gh], r0[:, gh:-gh, gh + lo - 1:gh + hi])
+    for (rank, world, variant, full) in ((1, 3, 4, r4), (2, 5, 0, r0)):
+        case_w, desc = sharding.slab_of(c, rank, world)
+        lo, hi = sharding.slab_range(im, rank, world)
+        assert (lo - 1) % 32 != 0 and (variant != 0 or case_w.im % 2 == 0)
+        wb = Block(case_w, slab=desc)
+        wb.w.copy_(blk.w[:, :, lo - 1:hi + 2 * gh])      # the full block's state, boundary fills included
+        rw = wb.residual(variant=variant)
+        assert torch.equal(rw[:, gh:-gh, gh:-gh], full[:, gh:-gh, gh + lo - 1:gh + hi])
+        del wb
 
 
 @pytest.mark.parametrize("kind,im,jm", CASES[:2])
