@@ -155,9 +155,11 @@ cudaError_t launch_norms(const GridDesc& g, const double* res, double* out10 /*d
 
 // fused, shared-memory tiled primal residual (residual_tile.cu)
 // variant: RES_DEFAULT (= k_residual_fast), RES_FAST_TMA (persistent CTAs + TMA staging of w), RES_TILE_V1 (first generation)
-//          RES_DEFAULT = k_residual_march (j-marching persistent kernel, TMA + LDGSTS fed rings; residual_march.cu) with
-//          k_residual_fast as its fallback; RES_FAST_TILE = k_residual_fast (the 32 x 9 tile kernel, default of round 1)
-enum ResidualVariant { RES_DEFAULT = 0, RES_GENERIC = 1, RES_FAST_TMA = 2, RES_TILE_V1 = 3, RES_FAST_TILE = 4 };
+//          RES_DEFAULT = k_residual_fast (32 x 9 tile kernel); RES_MARCH = k_residual_march (j-marching persistent kernel, rings fed by
+//          TMA / bulk copies, residual_march.cu; falls back to the tile kernel when TMA cannot describe the arrays).  Measured at C5
+//          (profiles/r2_a_summary.md): tile 2.385 ms, march 2.478 ms -- the faster one is the default, BROADCAST_B200_RESIDUAL_MARCH=1
+//          swaps them.  RES_FAST_TILE always names the tile kernel.
+enum ResidualVariant { RES_DEFAULT = 0, RES_GENERIC = 1, RES_FAST_TMA = 2, RES_TILE_V1 = 3, RES_FAST_TILE = 4, RES_MARCH = 5 };
 cudaError_t launch_residual_tiled(const GridDesc& g, const SchemeArgs& a, bool wall, double* res, const double* w, const double* nx,
                                   const double* ny, const double* vol, const double* volf, cudaStream_t st, int variant = RES_DEFAULT,
                                   int part = 0);

@@ -1,5 +1,5 @@
-// k_residual_march: the j-marching fused residual of residual_march.cuh as a persistent kernel for sm_100a (DEFAULT residual
-// kernel since round 2).  Two CTAs of 320 threads (nine compute warps + one copy-issuing warp) per SM; a CTA walks work items (strip of 32 columns x segment of rows), keeps
+// k_residual_march: the j-marching fused residual of residual_march.cuh as a persistent kernel for sm_100a (variant RES_MARCH /
+// BROADCAST_B200_RESIDUAL_MARCH=1; measured 4 % behind the tile kernel at C5, see kernels.cuh and profiles/r2_a_summary.md).  Two CTAs of 320 threads (nine compute warps + one copy-issuing warp) per SM; a CTA walks work items (strip of 32 columns x segment of rows), keeps
 // its rows in shared-memory rings and receives the rows of the next step while it evaluates the faces of the current one:
 //   * w (5 planes), vol, volf: TMA, one cp.async.bulk.tensor box (38 x 1 x planes) per row, completion on two alternating mbarriers;
 //   * nx, ny (node layout, odd leading dimension: no tensor map possible): LDGSTS (cp.async 8 bytes) by all threads.
@@ -58,21 +58,25 @@ struct Maps {
 
 // One generation of copies (rows [cq0, cq0+cn) of the cell ring, [mq0, mq0+mn) of the metric ring), issued by ONE warp: every lane
 // builds and starts its own operations; lane 0 first posts the byte total of the whole generation on the mbarrier.
+__device__ __forceinline__ void start_copy(const rm::MCtx& t, const Maps& mp, uint64_t* bar, const rm::CopyOp& o) {
+  double* dst = t.sm + o.dst;
+  if (o.kind == 0) tma_load_3d(dst, &mp.w, o.x, o.y, bar);
+  else if (o.kind == 1) tma_load_2d(dst, &mp.vol, o.x, o.y, bar);
+  else if (o.kind == 2) tma_load_3d(dst, &mp.volf, o.x, o.y, bar);
+  else if (o.kind == 3) bulk_load_1d(dst, o.src, (uint32_t)o.bytes, bar);
+}
 __device__ __forceinline__ void issue_rows(const rm::MCtx& t, const Maps& mp, uint64_t* bar, int lane, int cq0, int cn, int mq0, int mn) {
   const int nops = rm::copy_count(cn, mn);
-  uint32_t bytes = 0;
-  for (int op = lane; op < nops; op += 32) bytes += (uint32_t)rm::copy_op(t, op, cq0, cn, mq0, mn).bytes;
+  // a step has 28 operations: one per lane, built once; the prologue's 52 take a second round
+  rm::CopyOp o0 = rm::copy_op(t, lane < nops ? lane : nops - 1, cq0, cn, mq0, mn);
+  if (lane >= nops) { o0.kind = -1; o0.bytes = 0; }
+  uint32_t bytes = (uint32_t)o0.bytes;
+  for (int op = lane + 32; op < nops; op += 32) bytes += (uint32_t)rm::copy_op(t, op, cq0, cn, mq0, mn).bytes;
   bytes = __reduce_add_sync(0xffffffffu, bytes);
   if (lane == 0) mbar_expect_tx(bar, bytes);
   __syncwarp();
-  for (int op = lane; op < nops; op += 32) {
-    const rm::CopyOp o = rm::copy_op(t, op, cq0, cn, mq0, mn);
-    double* dst = t.sm + o.dst;
-    if (o.kind == 0) tma_load_3d(dst, &mp.w, o.x, o.y, bar);
-    else if (o.kind == 1) tma_load_2d(dst, &mp.vol, o.x, o.y, bar);
-    else if (o.kind == 2) tma_load_3d(dst, &mp.volf, o.x, o.y, bar);
-    else if (o.kind == 3) bulk_load_1d(dst, o.src, (uint32_t)o.bytes, bar);
-  }
+  start_copy(t, mp, bar, o0);
+  for (int op = lane + 32; op < nops; op += 32) start_copy(t, mp, bar, rm::copy_op(t, op, cq0, cn, mq0, mn));
 }
 
 __global__ void __launch_bounds__(rm::NT_LAUNCH, 2)

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(TI* TJ, 3)
 
 cudaError_t launch_residual_tiled(const GridDesc& g, const SchemeArgs& a, bool wall, double* res, const double* w, const double* nx,
                                   const double* ny, const double* vol, const double* volf, cudaStream_t st, int variant, int part) {
-  if (g.im < 4 || g.jm < 6 || (part != 0 && (variant == RES_TILE_V1 || variant == RES_FAST_TMA))) {
+  if (g.im < 4 || g.jm < 6 || (part != 0 && (variant == RES_TILE_V1 || variant == RES_FAST_TMA || variant == RES_MARCH))) {
     if (part == 1) return cudaSuccess;   // kernels without a tile split do everything in the "ring" call
     if (g.im < 4 || g.jm < 6) return launch_residual_generic(g, a, wall, 0, res, w, nullptr, nx, ny, vol, volf, nullptr, st);
     part = 0;
@@ -218,8 +218,9 @@ cudaError_t launch_residual_tiled(const GridDesc& g, const SchemeArgs& a, bool w
   // second-generation kernel (residual_fast.cu) unless the first one is asked for as a cross-check
   static const bool v1 = getenv("BROADCAST_B200_RESIDUAL_V1") != nullptr;
   static const bool tma = getenv("BROADCAST_B200_RESIDUAL_TMA") != nullptr;
-  static const bool no_march = getenv("BROADCAST_B200_RESIDUAL_TILE") != nullptr;
-  if (variant == RES_DEFAULT && part == 0 && !v1 && !tma && !no_march) {   // the marching kernel; falls through when TMA cannot describe the arrays
+  static const bool march_default = getenv("BROADCAST_B200_RESIDUAL_MARCH") != nullptr;
+  if ((variant == RES_MARCH || (variant == RES_DEFAULT && march_default && !v1 && !tma)) && part == 0) {
+    // the marching kernel; falls through to the tile kernel when TMA cannot describe the arrays
     const SchemeConsts c = make_consts(a.cp, a.cv, a.prandtl, a.gam, a.rgaz, a.cs, a.muref, a.tref, a.s_suth, a.k2, a.k4);
     bool done = false;
     cudaError_t e = launch_residual_march(g, c, ::sqrt(a.gam * a.rgaz), wall, res, w, nx, ny, vol, volf, st, &done);

@@ -154,8 +154,8 @@ class Block:
                                                 st), "bcd_jn_match")
 
     def residual(self, generic=False, w=None, out=None, variant=None):
-        """variant: 0 default (j-marching persistent kernel k_residual_march), 1 generic four-kernel pipeline, 2 tile kernel + TMA/persistent,
-        3 first-generation tile kernel, 4 the 32 x 9 tile kernel k_residual_fast (default of round 1)"""
+        """variant: 0 default (the 32 x 9 tile kernel k_residual_fast), 1 generic four-kernel pipeline, 2 tile kernel + TMA/persistent,
+        3 first-generation tile kernel, 4 = 0 by name, 5 j-marching persistent kernel k_residual_march (rings fed by TMA / bulk copies)"""
         w = self.w if w is None else w
         out = self.res if out is None else out
         v = int(variant) if variant is not None else (1 if generic else 0)

@@ -47,11 +47,10 @@ def test_boundary_fill_and_residual(gpu, ref, kind, im, jm):
 
 @pytest.mark.parametrize("kind,im,jm", [("bl", 60, 40), ("bl", 97, 33), ("cyl", 70, 40), ("bl", 300, 70)])
 def test_residual_kernel_variants_agree(gpu, ref, kind, im, jm):
-    """default j-marching kernel (0), reference-shaped pipeline (1), tile kernel + TMA/persistent (2; odd leading dimension: its LDG
-    fallback), first-generation tile kernel (3) and the 32 x 9 tile kernel (4): each within the parity bound of the oracle.  Variants
-    2 and 4 run the same phase functions on the same operands and agree bit for bit; the marching kernel evaluates the same face
-    formulas from another instruction stream (the compiler contracts other multiply-adds): it agrees with 4 to a few ulp of the
-    face fluxes."""
+    """default 32 x 9 tile kernel (0 = 4), reference-shaped pipeline (1), tile kernel + TMA/persistent (2; odd leading dimension: its
+    LDG fallback), first-generation tile kernel (3) and the j-marching kernel (5): each within the parity bound of the oracle.
+    Variants 0 and 2 run the same phase functions on the same operands and agree bit for bit; the marching kernel evaluates the
+    same face formulas from another instruction stream: it agrees with 0 to a few ulp of the face fluxes (measured: bit for bit)."""
     import torch
     from broadcast_b200.resident import Block
     a = H.make_case(kind, im, jm, gpu, with_w=True)
@@ -62,13 +61,13 @@ def test_residual_kernel_variants_agree(gpu, ref, kind, im, jm):
     blk.apply_bcs()
     gh = a.gh
     outs, np_outs = {}, {}
-    for v in (0, 1, 2, 3, 4):
+    for v in (0, 1, 2, 3, 4, 5):
         r = blk.residual(variant=v).clone()
         outs[v] = r
         np_outs[v] = np.asfortranarray(r.cpu().numpy().transpose(2, 1, 0))     # (planes, j, i) image -> (i, j, planes)
         H.assert_residual_parity(np_outs[v], rb, b, wb, floor=floor, what=("variant", v))
-    assert torch.equal(outs[4], outs[2])
-    assert np.all(H.backward_err(np_outs[0], np_outs[4], b, wb) < 1e-14)
+    assert torch.equal(outs[0], outs[2]) and torch.equal(outs[0], outs[4])
+    assert np.all(H.backward_err(np_outs[5], np_outs[0], b, wb) < 1e-14)
 
 
 @pytest.mark.parametrize("kind,im,jm", [("bl", 7, 7), ("bl", 8, 8), ("bl", 33, 7), ("bl", 9, 10), ("cyl", 14, 9), ("bl", 3, 12), ("bl", 12, 5)])
@@ -96,7 +95,7 @@ def test_residual_in_two_parts_equals_the_whole(gpu, im, jm):
     c = H.make_case("bl", im, jm, gpu, with_w=True)
     blk = Block(c)
     blk.apply_bcs()
-    whole = blk.residual(variant=4).clone()     # the tile kernel in one launch (the split launches are tile-kernel launches)
+    whole = blk.residual().clone()
     gh = c.gh
     w_ok = blk.w.clone()
     blk.res.zero_()
@@ -128,10 +127,10 @@ def test_residual_full_size_properties(gpu):
     blk = Block(c)
     blk.apply_bcs()
     gh = c.gh
-    r0 = blk.residual(variant=0).clone()
+    r0 = blk.residual(variant=5).clone()     # marching kernel
     rg = blk.residual(variant=1).clone()
     r2 = blk.residual(variant=2).clone()
-    r4 = blk.residual(variant=4).clone()
+    r4 = blk.residual(variant=0).clone()     # tile kernel (default)
     assert not torch.isnan(r0).any()
     assert torch.equal(r4, r2)
     inner = (slice(None), slice(gh, -gh), slice(gh, -gh))
@@ -146,10 +145,10 @@ def test_residual_full_size_properties(gpu):
     # away from the full grid's tiles / strips.  Window (1 of 3) has an odd width (the marching kernel needs an even leading
     # dimension for its tensor maps and falls back to the tile kernel): tile kernel; window (2 of 5) has an even width: marching.
     from broadcast_b200 import sharding
-    for (rank, world, variant, full) in ((1, 3, 4, r4), (2, 5, 0, r0)):
+    for (rank, world, variant, full) in ((1, 3, 0, r4), (2, 5, 5, r0)):
         case_w, desc = sharding.slab_of(c, rank, world)
         lo, hi = sharding.slab_range(im, rank, world)
-        assert (lo - 1) % 32 != 0 and (variant != 0 or case_w.im % 2 == 0)
+        assert (lo - 1) % 32 != 0 and (variant != 5 or case_w.im % 2 == 0)
         wb = Block(case_w, slab=desc)
         wb.w.copy_(blk.w[:, :, lo - 1:hi + 2 * gh])      # the full block's state, boundary fills included
         rw = wb.residual(variant=variant)

@@ -28,7 +28,7 @@ for im, jm in sizes:
     out = {"im": im, "jm": jm, "fused_ms": timed(lambda: blk.residual()), "generic_ms": timed(lambda: blk.residual(generic=True), 3),
            "rel_diff_fused_vs_generic": err, "nan": bool(torch.isnan(ai).any().item())}
     out["GBs_136"] = 136.0 * im * jm / (out["fused_ms"] * 1e-3) / 1e9
-    for name, v in (("fast_tile_ms", 4), ("tma_ms", 2), ("tile_v1_ms", 3)):
+    for name, v in (("march_ms", 5), ("tma_ms", 2), ("tile_v1_ms", 3)):
         c2 = blk.residual(variant=v).clone()
         out[name] = timed(lambda: blk.residual(variant=v))
         out[name + "_maxdiff_vs_default"] = float(((c2 - a)[:, gh:-gh, gh:-gh].abs().amax(dim=(1, 2)) / scale).max().item())
