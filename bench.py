@@ -27,7 +27,32 @@ sys.path.insert(0, ROOT)
 
 RES_BYTES_PER_CELL = 136.0  # 12 doubles read (w5, nx2, ny2, vol, volf2) + 5 written, SURVEY.md 8(d)
 JAC_BYTES_PER_CELL = 5904.0  # 29 blocks x 25 doubles written + 13 doubles read, SURVEY.md 8(d)
-RES_TRAFFIC_NCU = 2.278e9    # dram__bytes_read.sum + dram__bytes_write.sum of one launch at C5 (profiles/r1_i_residual_fast_full_raw.csv)
+
+
+def kernel_source_hash():
+    """sha256 over the sources of the default residual kernel: the key that ties an ncu capture to the code that ran"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("residual_fast.cuh", "residual_fast.cu", "scheme.cuh", "grid.cuh"):
+        h.update(open(os.path.join(ROOT, "broadcast_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(im, jm, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the default residual kernel, from the sidecar that
+    tools/ncu_traffic.py writes next to the round's `ncu --set full` capture (profiles/residual_traffic.json).  Only reported when
+    the capture was taken at this grid size AND from the kernel sources that are running now; otherwise null (a stale number is
+    not a measurement)."""
+    p = os.path.join(ROOT, "profiles", "residual_traffic.json")
+    if world != 1 or not os.path.exists(p):
+        return None, None
+    try:
+        d = json.load(open(p))
+        if d.get("grid") == [im, jm] and d.get("source_hash") == kernel_source_hash():
+            return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]), d.get("capture")
+    except Exception:
+        pass
+    return None, None
 
 
 def parse():
@@ -158,30 +183,40 @@ def cpu_baseline(sample=(1024, 512), steps=8, warm=1):
 
 
 def run_reference(a):
+    """The reference's own CPU path (oracle/_ref: its Fortran machine-translated to C, gcc -O3 -march=x86-64-v3) on the SAME
+    config as the CUDA arm: ONE replica of the full a.im x a.jm grid (the reference is serial code: one block = one core),
+    min(steps, 2) timed steps of [4 boundary fills + residual].  The all-core figure (one bounded replica per host core, what a
+    user with many independent cases could extract from the box) is kept next to it as cpu_baseline.all_cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    sample = (1024, 512)
-    steps = max(1, min(a.steps, 6))
+    steps = max(1, min(a.steps, 2))
     warm = 1 if a.warmup > 0 else 0
     t0 = time.perf_counter()
+    value, sec = cpu_sample_worker((a.im, a.jm, steps, warm))
+    wall_full = time.perf_counter() - t0
+    sample = (1024, 512)
+    t0 = time.perf_counter()
     with mp.get_context("spawn").Pool(cores) as pool:
-        outs = pool.map(cpu_sample_worker, [(sample[0], sample[1], steps, warm)] * cores)
-    wall = time.perf_counter() - t0
-    value = float(sum(o[0] for o in outs))
-    ms = float(np.mean([o[1] for o in outs])) * 1e3
+        outs = pool.map(cpu_sample_worker, [(sample[0], sample[1], 4, 1)] * cores)
+    wall_all = time.perf_counter() - t0
+    allc = float(sum(o[0] for o in outs))
     line = {
-        "impl": "reference", "metric": "fp64_residual_cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": a.gpus,
-        "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "impl": "reference", "metric": "fp64_residual_cell_updates_per_s", "value": float(value), "unit": "cell-updates/s", "n_gpus": a.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C5 synthetic 2-D boundary layer {a.im}x{a.jm}, gh=3 (bounded sample {sample[0]}x{sample[1]} per replica)",
-                   "step": "4 boundary fills + 1 residual", "l2": "n/a (CPU)"},
-        "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": cores, "kind": "reference",
-                         "sample": f"{cores} independent replicas (the reference is serial Fortran; one replica per host core), each {steps} steps at "
-                                   f"{sample[0]}x{sample[1]} cells; reference Fortran machine-translated to C (oracle/_ref, gcc -O3); wall {wall:.1f} s"},
-        "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": f"C5 synthetic 2-D boundary layer {a.im}x{a.jm}, order 5 (gh=3), i-slabs over {a.gpus} GPU(s)",
+                   "step": "halo exchange (N>1) + 4 boundary fills + 1 residual (flux_num_dnc5_2d)", "l2": "n/a (CPU)",
+                   "note": "full grid, one replica: the reference is serial Fortran (no OpenMP / MPI inside a block)"},
+        "cpu_baseline": {"value": float(value), "unit": "cell-updates/s", "cores": 1, "kind": "reference",
+                         "sample": f"{steps} steps (4 boundary fills + residual) on the full {a.im}x{a.jm} grid, reference Fortran machine-translated "
+                                   f"to C (oracle/_ref, gcc -O3 -march=x86-64-v3), 1 thread as the reference is serial; wall {wall_full:.1f} s",
+                         "all_cores": {"value": allc, "cores": cores,
+                                       "sample": f"{cores} independent replicas, one per host core, each 4 steps at {sample[0]}x{sample[1]} cells "
+                                                 f"(cache-sized: favours the CPU); wall {wall_all:.1f} s"}},
+        "e2e": {"value": float(value), "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
@@ -225,8 +260,23 @@ def main():
     gcase = build_global_case(a.im, a.jm, bb.f_geom)
     case, slab = sharding.slab_of(gcase, rank, world)
     blk = Block(case, dev, slab=slab if world > 1 else None)
-    halo = sharding.HaloExchange(case.gh, rank, world)
+    gcase_holder = [gcase]
     del gcase
+    # halo exchange: peer stores over NVLink (csrc/halo.cu, two launches, no NCCL / torch op on the data path); NCCL send/recv
+    # (sharding.HaloExchange) only if the mailboxes cannot be mapped (BROADCAST_B200_HALO=nccl forces it)
+    halo_kind = "none"
+    halo = lambda w: None
+    if world > 1:
+        halo_kind = "peer-store kernels over NVLink (csrc/halo.cu)"
+        try:
+            if os.environ.get("BROADCAST_B200_HALO", "peer") != "peer":
+                raise RuntimeError("forced")
+            halo = sharding.PeerHalo(case.gh, rank, world, blk.w)
+        except Exception as e:   # noqa: BLE001
+            halo = sharding.HaloExchange(case.gh, rank, world)
+            halo_kind = f"NCCL send/recv (peer mailboxes unavailable: {e})"
+    gcase_e2e = gcase_holder[0] if not a.no_e2e else None
+    del gcase_holder[:]
     cells_global = a.im * a.jm
     cells_local = case.im * case.jm
 
@@ -239,9 +289,17 @@ def main():
     # (Block.step_overlapped).  Measured on B200 (profiles/r1_g_summary.md): no gain -- N = 1: 2.40 vs 2.35 ms, N = 8: 0.378 vs 0.375 ms
     # per step (the one-wave ring launch and the stream joins cost what the overlap hides) -- so the plain sequence is the default.
     overlap = os.environ.get("BROADCAST_B200_OVERLAP", "0") == "1"
+    # the step [exchange, fills, residual] as ONE captured CUDA graph (sharding.StepGraph): at N = 8 the kernel takes 0.3 ms and
+    # the Python-issued launches were a fixed ~70 us per step; BROADCAST_B200_STEP_GRAPH=0 issues the calls one by one
+    # (one GPU: the 2.4 ms kernel hides every launch; the calls stay separate so that CUDA events bracket the kernel inside the
+    # timed region)
+    use_graph = os.environ.get("BROADCAST_B200_STEP_GRAPH", "1" if world > 1 else "0") == "1" and not overlap
+    sgraph = sharding.StepGraph(blk, halo if world > 1 else None) if use_graph else None
 
     def step():
-        if overlap:
+        if sgraph is not None:
+            sgraph()
+        elif overlap:
             blk.step_overlapped(halo if world > 1 else None)
         else:
             halo(blk.w)
@@ -260,7 +318,9 @@ def main():
     barrier()
     ev0.record()
     for s in range(a.steps):
-        if overlap:
+        if sgraph is not None:
+            step()
+        elif overlap:
             kev[s][0].record()
             step()
             kev[s][1].record()
@@ -274,6 +334,15 @@ def main():
     barrier()
     launches = _lib.launch_count() - n0
     ms_total = ev0.elapsed_time(ev1)
+    kernel_timing = "CUDA events around the kernel launch of every timed step"
+    if sgraph is not None:
+        # the graph has no place for events around its kernel node: the same kernel on the same state, K launches right after
+        for s in range(a.steps):
+            kev[s][0].record()
+            blk.residual()
+            kev[s][1].record()
+        barrier()
+        kernel_timing = "K launches of the kernel alone right after the K timed graph replays (same state)"
     k_ms = float(np.mean([x.elapsed_time(y) for x, y in kev]))
     t = torch.tensor([ms_total, k_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -282,10 +351,25 @@ def main():
     ms_step = ms_total / a.steps
     value = cells_global / (ms_step * 1e-3)
 
+    # checksum of the step's result over the OWNED cells of all ranks: wrap-around int64 sum of the bit patterns of the residual
+    # (order independent, so identical for every N iff the sharded residual equals the single-GPU one bit for bit) + L2 norms
+    gh_ = case.gh
+    own = blk.res[:, gh_:gh_ + case.jm, gh_:gh_ + case.im].contiguous()
+    bits = own.view(torch.int64).sum().reshape(1)
+    sq = (own * own).sum(dim=(1, 2))
+    if world > 1:
+        dist.all_reduce(bits, op=dist.ReduceOp.SUM)
+        dist.all_reduce(sq, op=dist.ReduceOp.SUM)
+    checksum = {"res_bits_sum_i64": int(bits.item()), "res_l2": [float(x) for x in sq.sqrt().cpu()],
+                "note": "wrap-around int64 sum of the residual's bit patterns over the owned cells of all ranks (order independent): "
+                        "equal across N = 1/2/4/8 iff the slab-sharded residual is bit-identical to the single-block one"}
+    del own, bits, sq
+
     # roofline of the dominant kernel (fused residual tile kernel), per launch, per GPU
     achieved = RES_BYTES_PER_CELL * cells_local / (k_ms * 1e-3) / 1e9
+    traffic, traffic_src = measured_traffic(a.im, a.jm, world)
     roofline = {"bound": "hbm", "kernel": "k_residual_fast (32x9 tile, 320 threads)" + ("; inner tiles + ring of tiles = 2 launches per step overlapping the halo exchange and boundary fills, timed first launch to end of last" if overlap else ""), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_kind": peak_kind, "traffic": RES_TRAFFIC_NCU if (a.im, a.jm, world) == (8192, 2048, 1) else None, "kernel_ms": k_ms,
+                "peak_kind": peak_kind, "kernel_timing": kernel_timing, "traffic": traffic, "traffic_capture": traffic_src, "kernel_ms": k_ms,
                 "algorithmic_bytes_per_cell": RES_BYTES_PER_CELL,
                 "fp64_pipe_note": "FP64-pipe bound at ~11 flop/B (ridge 5.8): see DESIGN.md section 4 and profiles/"}
 
@@ -365,18 +449,16 @@ def main():
         rp = torch.empty(blk.w.shape, dtype=torch.float64).pin_memory()
         wp.copy_(blk.w.cpu())
         nst = max(3, min(a.steps, 10))
-        if world == 1:
-            # one GPU: the host step is pipelined over 8 i-slabs (H2D of slab k+1 / kernels of slab k / D2H of slab k-1 overlap)
-            from broadcast_b200.resident import StreamedBlock
-            nslab = int(os.environ.get("BROADCAST_B200_E2E_SLABS", "8"))
-            sb = StreamedBlock(case, nslab=nslab, device=dev)
-            run = lambda: sb.step_from_host(wp, rp)
-            h2d, d2h = sb.bytes_per_step()
-            api = "broadcast_b200.resident.StreamedBlock.step_from_host (pinned host w in, residual out, " + str(nslab) + " pipelined i-slabs; mesh metrics resident)"
-        else:
-            run = lambda: blk.step_from_host(wp, rp, halo)
-            h2d = d2h = blk.w.numel() * 8
-            api = "broadcast_b200.resident.Block.step_from_host per rank (pinned host w in, halo exchange, residual out; mesh metrics resident)"
+        # the host step is pipelined over i-slabs of the rank's part of the block (H2D of slab k+1 / kernels of slab k / D2H of
+        # slab k-1 overlap on three streams).  Every slab's gh halo columns come straight from the HOST array (which holds the
+        # rank's columns plus its halo columns, as a rank of the reference's host would hold them), so no device exchange is needed.
+        from broadcast_b200.resident import StreamedBlock
+        nslab = int(os.environ.get("BROADCAST_B200_E2E_SLABS", "8" if world == 1 else "4"))
+        sb = StreamedBlock(gcase_e2e, nslab=nslab * world, device=dev, first=rank * nslab, count=nslab)
+        run = lambda: sb.step_from_host(wp, rp)
+        h2d, d2h = sb.bytes_per_step()
+        api = ("broadcast_b200.resident.StreamedBlock.step_from_host per rank (pinned host w in, residual out, " + str(nslab) +
+               " pipelined i-slabs per GPU; mesh metrics resident)")
         for _ in range(2):
             run()
         barrier()
@@ -397,8 +479,9 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"C5 synthetic 2-D boundary layer {a.im}x{a.jm}, order 5 (gh=3), i-slabs over {world} GPU(s)",
                        "step": "halo exchange (N>1) + 4 boundary fills + 1 residual (flux_num_dnc5_2d)" + (", fills and exchange overlapped with the inner tiles" if overlap else ""),
+                       "halo": halo_kind, "step_issue": "one CUDA-graph replay per step" if sgraph is not None else "separate launches",
                        "l2": f"inputs larger than L2 ({blk.w.numel() * 8 / 2**20:.0f} MiB state per GPU)"},
-            "roofline": roofline, "jacobian": jac, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
+            "roofline": roofline, "jacobian": jac, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "checksum": checksum,
         }
         if not a.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline()

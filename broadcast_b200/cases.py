@@ -128,6 +128,9 @@ class Case:
     bcs: List[Tuple[Any, ...]] = dc_field(default_factory=list)
     periodic_i: bool = False
     scheme: str = "flux_num_dnc5_2d"
+    # i-slab of an i-periodic block (sharding.slab_of): the join across the cut has become a halo exchange between the first
+    # and the last slab, which (like the join, cylinder.py:499-527: all rows, ghost rows included) must FOLLOW the fills
+    slab_periodic: bool = False
 
     def scheme_args(self):
         """Trailing arguments of f_sch.flux_num_dnc5_2d after (res, w): BROADCAST_npz.py:1031.

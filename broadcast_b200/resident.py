@@ -235,15 +235,20 @@ class StreamedBlock:
     device-to-host copy of slab k-1's residual overlap the boundary fill + residual kernels of slab k (three streams,
     both copy engines busy).  Same results as ``Block.step_from_host`` (slab-internal edges compute their gradients)."""
 
-    def __init__(self, case: Case, nslab: int = 8, device="cuda:0"):
+    def __init__(self, case: Case, nslab: int = 8, device="cuda:0", first: int = 0, count: int = None):
+        """``first`` / ``count``: this object drives only the slabs first .. first+count-1 of the ``nslab`` slabs of ``case`` (one
+        rank of a multi-GPU run pipelining ITS part of the block: the host arrays then hold the columns of those slabs plus gh
+        halo columns on each side, i.e. the rank's own slab image)."""
         from . import sharding
         self.case, self.device = case, torch.device(device)
         self.gh, self.im, self.jm = case.gh, case.im, case.jm
+        count = nslab - first if count is None else count
+        self.col0 = sharding.slab_range(case.im, first, nslab)[0] - 1     # storage column of the host arrays' first column
         self.slabs = []
-        for k in range(nslab):
+        for k in range(first, first + count):
             sl, desc = sharding.slab_of(case, k, nslab)
             lo, hi = sharding.slab_range(case.im, k, nslab)
-            self.slabs.append((Block(sl, device, slab=desc if nslab > 1 else None), lo, hi))
+            self.slabs.append((Block(sl, device, slab=desc if nslab > 1 else None), lo - self.col0, hi - self.col0))
         # one stream per ROLE (host-to-device copies, kernels, device-to-host copies) and one event pair per slab: the H2D queue
         # never waits behind a D2H copy, both copy engines stay busy for the whole step (measured: 45.9 GB/s each way at once)
         self.s_in, self.s_k, self.s_out = (torch.cuda.Stream(device=self.device) for _ in range(3))
@@ -259,7 +264,7 @@ class StreamedBlock:
 
     def step_from_host(self, w_pinned: torch.Tensor, res_pinned: torch.Tensor):
         """``w_pinned`` / ``res_pinned``: pinned host tensors (5, jm+2gh, im+2gh) = memory image of the Fortran arrays"""
-        gh, nj, ni = self.gh, self.jm + 2 * self.gh, self.im + 2 * self.gh
+        gh, nj, ni = self.gh, self.jm + 2 * self.gh, int(w_pinned.shape[2])
         rows = 5 * nj
         main = torch.cuda.current_stream(self.device)
         for s in (self.s_in, self.s_k, self.s_out):

@@ -29,9 +29,9 @@ def slab_of(case: Case, rank: int, world: int):
     slab descriptor (ioff, im_global, edges) the device entry points need (include/broadcast_b200.h, bcd_slab_begin)."""
     if world == 1:
         return case, (0, case.im, 0)
-    if case.periodic_i:
-        raise NotImplementedError("i-slabs of an i-periodic block (O-mesh): shard over colours instead (SURVEY.md 8(e))")
     gh, im, jm = case.gh, case.im, case.jm
+    if case.periodic_i:
+        return _periodic_slab_of(case, rank, world)
     lo, hi = slab_range(im, rank, world)
     n = hi - lo + 1
     if n < 2 * gh + 1:
@@ -70,13 +70,53 @@ def slab_of(case: Case, rank: int, world: int):
     return sl, (lo - 1, im, edges)
 
 
+def _periodic_slab_of(case: Case, rank: int, world: int):
+    """i-slab of an i-periodic block (O-mesh, card_cyl2d.py): the join across the cut (jn_match_2d, cylinder.py:499-527) becomes
+    the halo exchange between the LAST and the FIRST slab, so every slab has two slab-internal edges (edges = 3) and no join.
+    The j-side fills keep their window over the slab's own columns; the exchange follows them (``slab_periodic``), because the
+    join they replace copies the ghost rows too.  The metric halo columns are slices of the global arrays, whose ghost columns
+    already hold the periodic copies (cases.make_cyl_case)."""
+    gh, im, jm = case.gh, case.im, case.jm
+    lo, hi = slab_range(im, rank, world)
+    n = hi - lo + 1
+    if n < 2 * gh + 1:
+        raise ValueError(f"slab of {n} columns is narrower than the stencil ({2 * gh + 1}): use fewer ranks")
+    cs = slice(lo - 1, hi + 2 * gh)
+    ns = slice(lo - 1, hi + 2 * gh + 1)
+    F = np.asfortranarray
+    bcs = []
+    for bc in case.bcs:
+        kind = bc[0]
+        if kind == "jn":
+            continue
+        itf = np.array(bc[2], dtype=float)
+        if int(itf[0, 0]) != 1 or int(itf[1, 0]) != im or bc[1] not in ("Jlo", "Jhi"):
+            raise NotImplementedError("periodic i-slabs: j-side fills over the columns 1 .. im only")
+        it = itf.copy(); it[0, 0] = 1; it[1, 0] = n
+        if kind == "noref":
+            bcs.append((kind, bc[1], F(it), F(bc[3][lo - 1:hi, :])))
+        elif kind in ("wall", "symmetry", "antisymmetry"):
+            bcs.append((kind, bc[1], F(it)))
+        elif kind in ("wall_iso", "pressure"):
+            bcs.append((kind, bc[1], F(it)) + tuple(bc[3:]))
+        else:
+            raise NotImplementedError(kind)
+    sl = Case(name=f"{case.name}_slab{rank}of{world}", im=n, jm=jm, gh=gh, phys=case.phys, k2=case.k2, k4=case.k4,
+              x0=F(case.x0[ns]), y0=F(case.y0[ns]), nx=F(case.nx[ns]), ny=F(case.ny[ns]), xc=F(case.xc[cs]), yc=F(case.yc[cs]),
+              vol=F(case.vol[cs]), volf=F(case.volf[cs]), w=F(case.w[cs]), bcs=bcs, periodic_i=False, scheme=case.scheme,
+              slab_periodic=True)
+    return sl, (lo - 1, im, 3)
+
+
 class HaloExchange:
     """neighbour exchange of the gh halo columns of a state held as a torch tensor of shape (planes, jm+2gh, im+2gh)
     (the memory image of the Fortran array (im+2gh, jm+2gh, planes)): NCCL send/recv over NVLink on the GPUs, gloo on CPU.
     All rows (ghost rows included) are exchanged, so corner ghosts of a slab are its neighbour's boundary ghosts."""
 
-    def __init__(self, gh: int, rank: int, world: int, group=None):
+    def __init__(self, gh: int, rank: int, world: int, group=None, periodic: bool = False):
         self.gh, self.rank, self.world, self.group = gh, rank, world, group
+        self.left = rank - 1 if rank > 0 else (world - 1 if periodic and world > 1 else None)
+        self.right = rank + 1 if rank < world - 1 else (0 if periodic and world > 1 else None)
         self._buf = {}
 
     def _b(self, key, like, shape):
@@ -88,7 +128,7 @@ class HaloExchange:
         return b
 
     def bytes_per_exchange(self, w) -> int:
-        sides = (1 if self.rank > 0 else 0) + (1 if self.rank < self.world - 1 else 0)
+        sides = (1 if self.left is not None else 0) + (1 if self.right is not None else 0)
         return sides * w.shape[0] * w.shape[1] * self.gh * w.element_size()
 
     def __call__(self, w):
@@ -99,21 +139,163 @@ class HaloExchange:
         ni = w.shape[2]
         im = ni - 2 * gh
         shape = (w.shape[0], w.shape[1], gh)
-        ops = []
-        if self.rank > 0:
+        sends, recvs = [], []
+        if self.left is not None:
             sl, rl = self._b("sl", w, shape), self._b("rl", w, shape)
             sl.copy_(w[:, :, gh:2 * gh])                 # my first owned columns -> left neighbour's right halo
-            ops += [dist.P2POp(dist.isend, sl, self.rank - 1, self.group), dist.P2POp(dist.irecv, rl, self.rank - 1, self.group)]
-        if self.rank < self.world - 1:
+            sends.append((sl, self.left, 0)); recvs.append((rl, self.left, 1))
+        if self.right is not None:
             sr, rr = self._b("sr", w, shape), self._b("rr", w, shape)
             sr.copy_(w[:, :, im:im + gh])                # my last owned columns -> right neighbour's left halo
-            ops += [dist.P2POp(dist.isend, sr, self.rank + 1, self.group), dist.P2POp(dist.irecv, rr, self.rank + 1, self.group)]
+            sends.append((sr, self.right, 1)); recvs.append((rr, self.right, 0))
+        # tags tell the two messages of a pair of ranks apart when the same neighbour sits on both sides (two periodic slabs):
+        # a message sent "to the left" (tag 0) is received by its target as coming "from the right" (tag 0)
+        # (NCCL ignores tags and matches the messages of a pair in issue order: receive in the order the neighbour sends)
+        if self.left is not None and self.left == self.right:
+            recvs.reverse()
+        ops = [dist.P2POp(dist.isend, b, peer, self.group, tag) for b, peer, tag in sends]
+        ops += [dist.P2POp(dist.irecv, b, peer, self.group, tag) for b, peer, tag in recvs]
         for r in dist.batch_isend_irecv(ops):
             r.wait()
-        if self.rank > 0:
+        if self.left is not None:
             w[:, :, 0:gh].copy_(self._buf["rl"])
-        if self.rank < self.world - 1:
+        if self.right is not None:
             w[:, :, im + gh:im + 2 * gh].copy_(self._buf["rr"])
+
+
+class PeerHalo:
+    """Halo exchange by PEER STORES over NVLink (csrc/halo.cu): every rank's push kernel writes its gh edge columns straight into
+    its neighbours' mailboxes and releases a flag; the unpack kernel waits for its own flags and fills the halo columns of ``w``.
+    No NCCL call, no torch op and no host synchronisation on the data path -- two launches per exchange, capturable in a CUDA
+    graph (``StepGraph``).  ``torch.distributed`` is used once, at construction, to hand the 64-byte IPC handles around.
+    ``periodic``: the first and the last slab are neighbours too (i-periodic O-mesh, cylinder.py:499-527)."""
+
+    def __init__(self, gh: int, rank: int, world: int, w, group=None, periodic: bool = False):
+        import ctypes
+        import torch.distributed as dist
+        from . import _lib
+        self.gh, self.rank, self.world = gh, rank, world
+        self.lib = _lib.lib()
+        self.lib.bcd_halo_mailbox.restype = ctypes.c_void_p
+        self.rows = int(w.shape[0] * w.shape[1])
+        self.ni = int(w.shape[2])
+        self.handle = ctypes.c_void_p(None)
+        self.left = rank - 1 if rank > 0 else (world - 1 if periodic and world > 1 else None)
+        self.right = rank + 1 if rank < world - 1 else (0 if periodic and world > 1 else None)
+        if world == 1:
+            return
+        mine = (ctypes.c_ubyte * 64)()
+        _lib.check(self.lib.bcd_halo_create(ctypes.byref(self.handle), gh, ctypes.c_longlong(self.rows), mine), "bcd_halo_create")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(mine), group=group)
+        self.lib.bcd_halo_peer.restype = ctypes.c_void_p
+        for side, nb in ((0, self.left), (1, self.right)):
+            if nb is None:
+                continue
+            if side == 1 and nb == self.left:      # two slabs of a periodic block: the same neighbour on both sides, mapped once
+                import torch
+                _lib.check(self.lib.bcd_halo_connect(self.handle, 1, None, ctypes.c_void_p(self.lib.bcd_halo_peer(self.handle, 0)),
+                                                     torch.cuda.current_device()), "bcd_halo_connect")
+                continue
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(handles[nb])
+            _lib.check(self.lib.bcd_halo_connect(self.handle, side, buf, ctypes.c_void_p(None), -1), "bcd_halo_connect")
+        dist.barrier(group=group)      # every mailbox is mapped before the first push
+
+    @classmethod
+    def local(cls, ws, gh: int, periodic: bool = False):
+        """the halos of several slabs held by ONE process (tensors ``ws`` in slab order, on one or several devices), connected
+        through plain device pointers instead of IPC handles.  The exchanges of the slabs must be issued on DIFFERENT streams
+        (an unpack spins until its neighbours' pushes have run)."""
+        import ctypes
+        import torch
+        from . import _lib
+        L = _lib.lib()
+        L.bcd_halo_mailbox.restype = ctypes.c_void_p
+        L.bcd_halo_peer.restype = ctypes.c_void_p
+        n = len(ws)
+        hs = []
+        for r, w in enumerate(ws):
+            h = cls.__new__(cls)
+            h.gh, h.rank, h.world, h.lib = gh, r, n, L
+            h.rows, h.ni = int(w.shape[0] * w.shape[1]), int(w.shape[2])
+            h.left = r - 1 if r > 0 else (n - 1 if periodic and n > 1 else None)
+            h.right = r + 1 if r < n - 1 else (0 if periodic and n > 1 else None)
+            h.handle = ctypes.c_void_p(None)
+            with torch.cuda.device(w.device):
+                _lib.check(L.bcd_halo_create(ctypes.byref(h.handle), gh, ctypes.c_longlong(h.rows), None), "bcd_halo_create")
+            hs.append(h)
+        for r, (h, w) in enumerate(zip(hs, ws)):
+            with torch.cuda.device(w.device):
+                for side, nb in ((0, h.left), (1, h.right)):
+                    if nb is not None:
+                        _lib.check(L.bcd_halo_connect(h.handle, side, None, ctypes.c_void_p(L.bcd_halo_mailbox(hs[nb].handle)),
+                                                      ws[nb].device.index), "bcd_halo_connect")
+        return hs
+
+    def bytes_per_exchange(self, w) -> int:
+        sides = (1 if self.left is not None else 0) + (1 if self.right is not None else 0)
+        return sides * self.rows * self.gh * w.element_size()
+
+    def __call__(self, w):
+        if self.world == 1:
+            return
+        import ctypes
+        import torch
+        from . import _lib
+        assert w.shape[0] * w.shape[1] == self.rows and w.shape[2] == self.ni and w.is_contiguous()
+        st = ctypes.c_void_p(torch.cuda.current_stream(w.device).cuda_stream)
+        _lib.check(self.lib.bcd_halo_exchange(self.handle, ctypes.c_void_p(w.data_ptr()), ctypes.c_longlong(self.rows), self.ni, self.gh, st),
+                   "bcd_halo_exchange")
+
+    def error(self) -> int:
+        return int(self.lib.bcd_halo_error(self.handle)) if self.world > 1 else 0
+
+    def close(self):
+        if self.handle:
+            self.lib.bcd_halo_destroy(self.handle)
+            self.handle = None
+
+
+class StepGraph:
+    """The per-step sequence [halo exchange, boundary fills, residual] of one Block captured ONCE into a CUDA graph
+    (bcd_graph_begin / _end) and replayed with one host call per step: at 8 GPUs the step is bounded by launch latency, not by
+    device time (72 us of Python-issued copies and launches on a 315 us kernel)."""
+
+    def __init__(self, blk, halo=None):
+        import ctypes
+        import torch
+        from . import _lib
+        self.blk, self.halo, self.lib = blk, halo, _lib.lib()
+        self.exec = ctypes.c_void_p(None)
+
+        after = bool(getattr(blk.case, "slab_periodic", False))   # periodic slabs: the exchange replaces the join, which follows the fills
+
+        def seq():
+            if halo is not None and not after:
+                halo(blk.w)
+            blk.apply_bcs()
+            if halo is not None and after:
+                halo(blk.w)
+            blk.residual()
+        self._seq = seq
+        seq()                                   # scratch buffers, kernel attributes, descriptor caches: not capturable
+        torch.cuda.current_stream(blk.device).synchronize()
+        st = blk._stream()
+        _lib.check(self.lib.bcd_graph_begin(st), "bcd_graph_begin")
+        try:
+            seq()
+        finally:
+            rc = self.lib.bcd_graph_end(st, ctypes.byref(self.exec))
+        _lib.check(rc, "bcd_graph_end")
+
+    def __call__(self):
+        from . import _lib
+        _lib.check(self.lib.bcd_graph_launch(self.exec, self.blk._stream()), "bcd_graph_launch")
+
+    def close(self):
+        if self.exec:
+            self.lib.bcd_graph_destroy(self.exec)
+            self.exec = None
 
 
 def colour_range(ncolours: int, rank: int, world: int):

@@ -363,6 +363,28 @@ int bcd_hybrid_csr_fill(int32_t* indices, double* data, int32_t* cursor, const l
 int bcd_apply_bcs(double* w, const double* nx, const double* ny, double gam, int gh, int im, int jm,
                   const bc_desc_t* bcs, int nbcs, void* stream);
 
+/* ---- halo exchange of the i-slabs by peer stores over NVLink (csrc/halo.cu; the periodic cut of an O-mesh is the
+ *      same exchange between the first and the last slab, cylinder.py:499-527).  One process per GPU: every rank creates a mailbox
+ *      (`rows` = planes * (jm + 2 gh) rows of gh doubles per side), hands its 64-byte IPC handle to its neighbours (any host
+ *      transport: the Python layer uses torch.distributed.all_gather_object) and connects theirs: side 0 = left neighbour
+ *      (fills my Ilo halo), side 1 = right neighbour.  bcd_halo_exchange = two launches on `stream` (push into the neighbours'
+ *      mailboxes + release flag; wait for my own flags + unpack into the halo columns of w); step numbers live on the device, so
+ *      the pair can be captured in a CUDA graph.  bcd_halo_error: 1 after an unpack that saw no delivery for ~2 s. */
+int bcd_halo_create(void** handle, int gh, long long rows, unsigned char* ipc_handle_out64);
+int bcd_halo_connect(void* handle, int side, const unsigned char* ipc_handle64, void* same_process_mailbox, int peer_device);
+void* bcd_halo_mailbox(void* handle);
+void* bcd_halo_peer(void* handle, int side);
+int bcd_halo_exchange(void* handle, double* w, long long rows, int ni, int gh, void* stream);
+int bcd_halo_error(void* handle);
+int bcd_halo_destroy(void* handle);
+/* ---- capture of a sequence of bcd_* calls issued on `stream` between begin and end into a CUDA graph (thread-local capture mode),
+ *      replayed by bcd_graph_launch: the per-step sequence exchange + boundary fills + residual as ONE host call.  Every entry
+ *      point used inside must have run once before (scratch allocations and kernel attributes are not capturable). */
+int bcd_graph_begin(void* stream);
+int bcd_graph_end(void* stream, void** exec_out);
+int bcd_graph_launch(void* exec, void* stream);
+int bcd_graph_destroy(void* exec);
+
 /* =====================================================================================================
  * Resident-mode context for hosts without a device-memory library of their own (C, Fortran via ISO_C_BINDING; INTEGRATION.md
  * section 3): one block stays on the device between calls.  All array arguments are HOST arrays in the layout of the bc_* entry

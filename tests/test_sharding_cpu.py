@@ -151,3 +151,47 @@ def test_colour_sharded_jacobian_merges_to_the_full_one_gloo(world):
         assert p.exitcode == 0
     nnzA, nnzB, err = out.get(timeout=10)
     assert nnzA == nnzB and err == 0.0
+
+
+# ---- i-slabs of the i-periodic O-mesh: the join across the cut becomes the exchange between the last and the first slab ----------
+def _periodic_worker(rank, world, port, im, jm, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import refmods
+        R = refmods.make()
+        g = H.make_case("cyl", im, jm, R, with_w=True)
+        wg, rg = H.residual_sequence(R, g)                 # single block: fills (noref, wall, join twice) + residual
+        sl, (ioff, img, edges) = sharding.slab_of(g, rank, world)
+        gh = g.gh
+        lo, hi = sharding.slab_range(im, rank, world)
+        assert edges == 3 and sl.slab_periodic and not sl.periodic_i and all(b[0] != "jn" for b in sl.bcs)
+        w = sl.w.copy(order="F")
+        w[:gh] = np.nan
+        w[-gh:] = np.nan
+        cases.apply_bcs(sl, w, R["f_bnd"])                 # j-side fills of the slab's own columns first ...
+        t = torch.from_numpy(np.ascontiguousarray(w.T))
+        sharding.HaloExchange(gh, rank, world, periodic=True)(t)   # ... then the exchange (all rows, ghost rows included)
+        w = np.asfortranarray(t.numpy().T)
+        assert not np.isnan(w).any()
+        # the slab's padded state is the window of the single block's filled state (the cut included)
+        ref = np.concatenate([wg[-2 * gh:-gh], wg[gh:-gh], wg[gh:2 * gh]], axis=0)[lo - 1:hi + 2 * gh]
+        assert np.array_equal(w, ref), np.abs(w - ref).max()
+        res = sl.zeros_state()
+        R["f_sch"].flux_num_dnc5_2d(res, w, *sl.scheme_args())
+        a, b = gh + 1, sl.im - (gh + 1)                    # away from the slab edges (the checker extrapolates gradients there)
+        err = np.abs(res[gh + a:gh + b, gh:-gh] - rg[lo - 1 + gh + a:lo - 1 + gh + b, gh:-gh]).max() / np.abs(rg).max()
+        out[rank] = float(err)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_periodic_slabs_and_exchange_gloo(world, ref):
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_periodic_worker, args=(world, _free_port(), 42, 16, out), nprocs=world, join=True)
+    assert len(out) == world
+    for r in range(world):
+        assert out[r] < 1e-13, (r, out[r])
