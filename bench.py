@@ -127,6 +127,33 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # case construction (host); slab sharding lives in broadcast_b200.sharding
 # ----------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local):
+    """pin this process (and so the first-touch placement of the pinned host buffers it allocates next) to the CPUs of the NUMA node
+    the GPU hangs off: with one process per GPU the host copies of every rank otherwise come out of whatever node the launcher
+    started on and share its memory controllers.  Best effort: returns the node or None."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def build_global_case(im, jm, f_geom):
     from broadcast_b200 import cases
     return cases.make_bl_case(im, jm, f_geom=f_geom, name=f"bl2d_{im}x{jm}")
@@ -262,6 +289,10 @@ def main():
     blk = Block(case, dev, slab=slab if world > 1 else None)
     gcase_holder = [gcase]
     del gcase
+    # everything below runs on a stream of its own: a CUDA graph cannot be captured on (or replayed into) the legacy default
+    # stream without extra cross-stream waits
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     # halo exchange: peer stores over NVLink (csrc/halo.cu, two launches, no NCCL / torch op on the data path); NCCL send/recv
     # (sharding.HaloExchange) only if the mailboxes cannot be mapped (BROADCAST_B200_HALO=nccl forces it)
     halo_kind = "none"
@@ -445,6 +476,7 @@ def main():
     # end to end through the plugin-level call with pinned HOST buffers (state in, residual out, every step)
     e2e = None
     if not a.no_e2e:
+        numa = bind_to_gpu_numa_node(local)
         wp = torch.empty(blk.w.shape, dtype=torch.float64).pin_memory()
         rp = torch.empty(blk.w.shape, dtype=torch.float64).pin_memory()
         wp.copy_(blk.w.cpu())
@@ -470,7 +502,7 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": cells_global / float(dt[0]), "unit": "cell-updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": float(dt[0]) * 1e3, "api": api}
+               "ms_per_step": float(dt[0]) * 1e3, "api": api, "host_numa_node": numa}
 
     if rank == 0:
         line = {

@@ -159,7 +159,9 @@ cudaError_t launch_norms(const GridDesc& g, const double* res, double* out10 /*d
 //          TMA / bulk copies, residual_march.cu; falls back to the tile kernel when TMA cannot describe the arrays).  Measured at C5
 //          (profiles/r2_a_summary.md): tile 2.385 ms, march 2.478 ms -- the faster one is the default, BROADCAST_B200_RESIDUAL_MARCH=1
 //          swaps them.  RES_FAST_TILE always names the tile kernel.
-enum ResidualVariant { RES_DEFAULT = 0, RES_GENERIC = 1, RES_FAST_TMA = 2, RES_TILE_V1 = 3, RES_FAST_TILE = 4, RES_MARCH = 5 };
+//          RES_FAST_BULK = k_residual_fast_bulk (residual_bulk.cu): the tile kernel with w, vol, volf and the node rows of nx / ny delivered
+//          by TMA / bulk copies on one mbarrier, metrics read from shared memory; bit-identical to the tile kernel.
+enum ResidualVariant { RES_DEFAULT = 0, RES_GENERIC = 1, RES_FAST_TMA = 2, RES_TILE_V1 = 3, RES_FAST_TILE = 4, RES_MARCH = 5, RES_FAST_BULK = 6 };
 cudaError_t launch_residual_tiled(const GridDesc& g, const SchemeArgs& a, bool wall, double* res, const double* w, const double* nx,
                                   const double* ny, const double* vol, const double* volf, cudaStream_t st, int variant = RES_DEFAULT,
                                   int part = 0);
@@ -167,6 +169,10 @@ cudaError_t launch_residual_tiled(const GridDesc& g, const SchemeArgs& a, bool w
 // second-generation fused residual (residual_fast.cu): re-associated face formulas, shared normal-direction interpolations
 cudaError_t launch_residual_fast(const GridDesc& g, const SchemeArgs& a, bool wall, double* res, const double* w, const double* nx,
                                  const double* ny, const double* vol, const double* volf, cudaStream_t st, bool tma, int part = 0);
+
+// bulk-staged tile kernel (residual_bulk.cu); *done = false -> caller falls back to the LDG tile kernel
+cudaError_t launch_residual_fast_bulk(const GridDesc& g, const SchemeConsts& c, double sqgr, bool wall, double* res, const double* w,
+                                      const double* nx, const double* ny, const double* vol, const double* volf, cudaStream_t st, bool* done);
 
 // third-generation fused residual (residual_march.cu): persistent j-marching CTAs; *done = false -> caller falls back
 cudaError_t launch_residual_march(const GridDesc& g, const SchemeConsts& c, double sqgr, bool wall, double* res, const double* w,

@@ -118,6 +118,21 @@ constexpr int GW = OI + 2, GH_ = OJ + 2;      // sensor cells: i0-1 .. i0+32, j0
 constexpr int NSM_REST = NARR * NC + NRB + NXB;
 constexpr int NSM = WBUF + NSM_REST;          // doubles of shared memory per CTA, one w buffer (88 128 bytes)
 constexpr int NSM_TMA = 2 * WBUF + NSM_REST + 2;   // two w buffers + two mbarriers (109 520 bytes)
+// ---- bulk-staged variant (k_residual_fast_bulk): the mesh metrics of the tile in shared memory too ---------------------------------
+//   vol   box (OI+2) x (OJ+2)      cells i0-1 .. i0+32, j0-1 .. j0+OJ          (sensor cells)            TMA 2-D box
+//   volf  box (OI+2) x (OJ+1) x 2  cells i0 .. i0+33,  j0 .. j0+OJ             (faces)                   TMA 3-D box
+//   node  4 planes (nx0, nx1, ny0, ny1) x (OJ+3) rows j0-1 .. j0+OJ+1, columns i0-1 .. i0+34: one 1-D bulk copy per plane and
+//         row (node planes have an odd leading dimension on even grids: no tensor map), started at the 16-byte aligned element at
+//         or below the row's first element, so a row sits shifted by `nshift` in {0, 1} entries in its slot of MN_SLOT doubles.
+constexpr int MV_W = OI + 2, MV_H = OJ + 2;
+constexpr int MF_W = OI + 2, MF_H = OJ + 1;
+constexpr int MN_ROWS = OJ + 3, MN_SLOT = 40, MN_COPY = 38;
+constexpr int up16(int n) { return (n + 15) / 16 * 16; }
+constexpr int M_VOL = 0, M_VOLF = up16(MV_W * MV_H), M_NODE = M_VOLF + up16(2 * MF_W * MF_H), NMET = M_NODE + 4 * MN_ROWS * MN_SLOT;
+constexpr int O_MET = up16(NSM);                 // metric region behind the arrays of the LDG kernel (128-byte aligned)
+constexpr int NSM_BULK = O_MET + NMET + 2;       // + one mbarrier
+static_assert((MV_W * 8) % 16 == 0 && (MF_W * 8) % 16 == 0 && (MN_SLOT * 8) % 16 == 0 && (MN_COPY * 8) % 16 == 0, "bulk copy sizes");
+static_assert(OI + 4 + 1 <= MN_COPY && MN_COPY <= MN_SLOT, "node row window");
 static_assert(5 * NC <= WBUF, "w buffer");
 static_assert(5 * OJ * XI_P <= NXB, "exchange buffer");
 static_assert(OJ <= 32 && GW * OJ <= NT + 0 && (RI_W + 3) <= NT && RJ_W <= NT && 2 * OI <= NT, "thread mappings");
@@ -161,6 +176,7 @@ struct TileCtx {
   int i0, j0;  // first output cell of the tile
   int i1 = 1 << 30, j1 = 1 << 30;   // last cell the tile may write (tangent build: the rows of a rectangle)
   unsigned char* flags = nullptr;   // tangent build: per staged cell, 1 if any of its five tangents is non-zero (face skipping)
+  const double* met = nullptr;      // bulk-staged variant: the metric region (vol / volf boxes, node rows)
   BC_HD TileCtx(const GridDesc& g_, const SchemeConsts& c_) : g(g_), c(c_) {}
   BC_HD real* arr(int a) const { return sm + a * NC; }
   BC_HD real* RB() const { return sm + NARR * NC; }
@@ -557,6 +573,102 @@ BC_HD void face_fast(const TileCtx& t, const real* s, const real* sw, const real
 #undef RF_LW
 }
 
+// ---- bulk-staged variant: metrics from shared memory ---------------------------------------------------------------------------
+// The copies of one tile as a flat list of operations (one per lane and round of the issuing warp; the host emulation executes the
+// same list): op 0 = w box, 1 = vol box, 2 = volf box, 3 + (pl * MN_ROWS + r) = node row r of plane pl (0 nx0, 1 nx1, 2 ny0, 3 ny1).
+struct BulkOp {
+  int kind;            // 0 w (3-D box PI x PJ x 5), 1 vol (2-D box), 2 volf (3-D box), 3 node row (1-D copy), -1 nothing
+  int dst;             // offset in doubles: kind 0 into wsm, kinds 1-3 into met
+  int x, y;            // tensor coordinates (storage indices) of the box origin (kinds 0-2)
+  const double* src;   // kind 3
+  int bytes;
+};
+constexpr int NBULK = 3 + 4 * MN_ROWS;
+BC_HD int node_first_par(const GridDesc& g, int i0, int j0, int k, int r) {   // parity of the element index of node (i0-1, j0-1+r) of plane k
+  return (int)(((long long)(i0 + 1) + (long long)(j0 + 1 + r) * g.ldn + (long long)k * g.sn) & 1);
+}
+BC_HD BulkOp bulk_op(const GridDesc& g, const double* nx, const double* ny, int i0, int j0, int op) {
+  BulkOp o;
+  o.kind = -1; o.dst = 0; o.x = 0; o.y = 0; o.src = nullptr; o.bytes = 0;
+  if (op == 0) { o.kind = 0; o.x = i0 - 1; o.y = j0 - 1; o.bytes = 5 * NC * 8; }
+  else if (op == 1) { o.kind = 1; o.dst = M_VOL; o.x = i0 + 1; o.y = j0 + 1; o.bytes = MV_W * MV_H * 8; }
+  else if (op == 2) { o.kind = 2; o.dst = M_VOLF; o.x = i0 + 2; o.y = j0 + 2; o.bytes = 2 * MF_W * MF_H * 8; }
+  else if (op < NBULK) {
+    const int pl = (op - 3) / MN_ROWS, r = (op - 3) - pl * MN_ROWS, k = pl & 1;
+    const int srow = j0 + 1 + r;                                   // storage row of node row j0-1+r
+    if (srow > g.jm + 2 * g.gh || i0 + 1 > g.im + 2 * g.gh) return o;   // beyond the array: never read by an active face
+    const long long first = (long long)(i0 + 1) + (long long)srow * g.ldn + (long long)k * g.sn, lo = first & ~1LL;
+    long long cnt = MN_COPY;
+    const long long total = 2 * g.sn;
+    if (lo + cnt > total) cnt = total - lo;                        // last row of the array (total and lo are even)
+    o.kind = 3; o.src = ((pl & 2) ? ny : nx) + lo; o.dst = M_NODE + (pl * MN_ROWS + r) * MN_SLOT; o.bytes = (int)cnt * 8;
+  }
+  return o;
+}
+// value of node plane (isy ? ny : nx)[k] at window coordinates (a, r) = node (i0-1+a, j0-1+r)
+struct NodeView {
+  const double* m;   // met + M_NODE
+  int sb0, sb1, odd; // parity of the first element of row 0 of planes k = 0 / 1; ldn & 1
+  BC_HD int sh(int k, int r) const { return ((k ? sb1 : sb0) + (r & odd)) & 1; }
+  BC_HD const double* row(int isy, int k, int r) const { return m + ((2 * isy + k) * MN_ROWS + r) * MN_SLOT + sh(k, r); }
+};
+BC_HD NodeView node_view(const TileCtx& t) {
+  NodeView v;
+  v.m = t.met + M_NODE;
+  v.sb0 = node_first_par(t.g, t.i0, t.j0, 0, 0);
+  v.sb1 = node_first_par(t.g, t.i0, t.j0, 1, 0);
+  v.odd = t.g.ldn & 1;
+  return v;
+}
+template <int DIR>
+BC_HD FaceGeom load_geom_sm(const TileCtx& t, int fi, int fj) {
+  const NodeView nv = node_view(t);
+  const int a = fi - (t.i0 - 1), r = fj - (t.j0 - 1);
+  const double volf = t.met[M_VOLF + DIR * MF_W * MF_H + (fi - t.i0) + (fj - t.j0) * MF_W];
+  constexpr double ccross = (0.25 / 3.0) * 0.0625;
+  const double sA = (0.5 / 24.0) * volf, sC = (0.5 * ccross) * volf;
+  FaceGeom G;
+  if (DIR == 0) {
+    const double* ax = nv.row(0, 0, r) + a;
+    const double* ay = nv.row(1, 0, r) + a;
+    const double *cx0 = nv.row(0, 1, r) + a, *cx1 = nv.row(0, 1, r + 1) + a;
+    const double *cy0 = nv.row(1, 1, r) + a, *cy1 = nv.row(1, 1, r + 1) + a;
+    G.nxf = ax[0]; G.nyf = ay[0];
+    G.nApx = (ax[1] + G.nxf) * sA; G.nAmx = -(ax[-1] + G.nxf) * sA;
+    G.nApy = (ay[1] + G.nyf) * sA; G.nAmy = -(ay[-1] + G.nyf) * sA;
+    G.nCpx = (cx1[-1] + cx1[0]) * sC; G.nCmx = -(cx0[-1] + cx0[0]) * sC;
+    G.nCpy = (cy1[-1] + cy1[0]) * sC; G.nCmy = -(cy0[-1] + cy0[0]) * sC;
+  } else {
+    const double *axm = nv.row(0, 1, r - 1) + a, *ax0 = nv.row(0, 1, r) + a, *axp = nv.row(0, 1, r + 1) + a;
+    const double *aym = nv.row(1, 1, r - 1) + a, *ay0 = nv.row(1, 1, r) + a, *ayp = nv.row(1, 1, r + 1) + a;
+    const double *cxm = nv.row(0, 0, r - 1) + a, *cx0 = nv.row(0, 0, r) + a;
+    const double *cym = nv.row(1, 0, r - 1) + a, *cy0 = nv.row(1, 0, r) + a;
+    G.nxf = ax0[0]; G.nyf = ay0[0];
+    G.nApx = (axp[0] + G.nxf) * sA; G.nAmx = -(axm[0] + G.nxf) * sA;
+    G.nApy = (ayp[0] + G.nyf) * sA; G.nAmy = -(aym[0] + G.nyf) * sA;
+    G.nCpx = (cxm[1] + cx0[1]) * sC; G.nCmx = -(cxm[0] + cx0[0]) * sC;
+    G.nCpy = (cym[1] + cy0[1]) * sC; G.nCmy = -(cym[0] + cy0[0]) * sC;
+  }
+  return G;
+}
+BC_HD SensGeom sensor_geom_sm(const TileCtx& t, int tid, int round) {
+  SensGeom G{};
+  int ga, gb;
+  G.valid = sensor_of(t, tid, round, ga, gb);
+  if (G.valid) {   // window coordinates of the sensor window = those of the vol box and of the node rows
+    const NodeView nv = node_view(t);
+    G.vol = t.met[M_VOL + ga + gb * MV_W];
+    const double volm1 = 1.0 / G.vol;
+    const double* x0 = nv.row(0, 0, gb) + ga;
+    const double* y0 = nv.row(1, 0, gb) + ga;
+    G.dxm1 = 0.5 * (x0[0] + x0[1]) * volm1;
+    G.dxm2 = 0.5 * (nv.row(0, 1, gb)[ga] + nv.row(0, 1, gb + 1)[ga]) * volm1;
+    G.dym1 = 0.5 * (y0[0] + y0[1]) * volm1;
+    G.dym2 = 0.5 * (nv.row(1, 1, gb)[ga] + nv.row(1, 1, gb + 1)[ga]) * volm1;
+  }
+  return G;
+}
+
 // ---- phase 2: i-faces (i0 + col, j0 + row) -------------------------------------------------------------------------
 // warps 0..7: row = warp, col = lane (the left faces of the tile's cells); warp 8, lanes 0..7: the right faces of the
 // last column (col = 32, row = lane).  Both mappings are bank-conflict free on the 38-double pitch.
@@ -591,6 +703,17 @@ BC_HD FaceGeom prefetch_iface(const TileCtx& t, int tid) {
 BC_HD FaceGeom prefetch_jface(const TileCtx& t, int tid) {
   const FaceId f = jface_of(t, tid);
   if (f.active && !f.generic) return load_geom<1>(t, f.fi, f.fj);
+  return FaceGeom{};
+}
+
+BC_HD FaceGeom geom_iface_sm(const TileCtx& t, int tid) {
+  const FaceId f = iface_of(t, tid);
+  if (f.active && !f.generic) return load_geom_sm<0>(t, f.fi, f.fj);
+  return FaceGeom{};
+}
+BC_HD FaceGeom geom_jface_sm(const TileCtx& t, int tid) {
+  const FaceId f = jface_of(t, tid);
+  if (f.active && !f.generic) return load_geom_sm<1>(t, f.fi, f.fj);
   return FaceGeom{};
 }
 

@@ -280,17 +280,32 @@ class StepGraph:
         self._seq = seq
         seq()                                   # scratch buffers, kernel attributes, descriptor caches: not capturable
         torch.cuda.current_stream(blk.device).synchronize()
-        st = blk._stream()
-        _lib.check(self.lib.bcd_graph_begin(st), "bcd_graph_begin")
-        try:
-            seq()
-        finally:
-            rc = self.lib.bcd_graph_end(st, ctypes.byref(self.exec))
-        _lib.check(rc, "bcd_graph_end")
+        # a capture cannot run on the legacy default stream: the graph is captured (and replayed) on the caller's current stream
+        # when that is a real stream, else on a stream of its own that is ordered with the default stream around every replay
+        cur = torch.cuda.current_stream(blk.device)
+        self.own = torch.cuda.Stream(device=blk.device) if cur.cuda_stream == 0 else None
+        with torch.cuda.stream(self.own if self.own is not None else cur):
+            st = blk._stream()
+            _lib.check(self.lib.bcd_graph_begin(st), "bcd_graph_begin")
+            try:
+                seq()
+            finally:
+                rc = self.lib.bcd_graph_end(st, ctypes.byref(self.exec))
+            _lib.check(rc, "bcd_graph_end")
 
     def __call__(self):
+        import ctypes
+        import torch
         from . import _lib
-        _lib.check(self.lib.bcd_graph_launch(self.exec, self.blk._stream()), "bcd_graph_launch")
+        cur = torch.cuda.current_stream(self.blk.device)
+        if cur.cuda_stream == 0:
+            if self.own is None:
+                self.own = torch.cuda.Stream(device=self.blk.device)
+            self.own.wait_stream(cur)
+            _lib.check(self.lib.bcd_graph_launch(self.exec, ctypes.c_void_p(self.own.cuda_stream)), "bcd_graph_launch")
+            cur.wait_stream(self.own)
+        else:
+            _lib.check(self.lib.bcd_graph_launch(self.exec, ctypes.c_void_p(cur.cuda_stream)), "bcd_graph_launch")
 
     def close(self):
         if self.exec:

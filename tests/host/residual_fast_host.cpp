@@ -2,6 +2,7 @@
 // TEST INFRASTRUCTURE so that the tile indexing and the re-associated face formulas can be checked against the oracle
 // on a machine without a GPU.  The CTA is emulated phase by phase (a loop over the 288 thread ids per phase, barriers
 // = loop boundaries).  Not part of the product; the product runs the same phase functions inside k_residual_fast.
+#include <cstdint>
 #include <vector>
 #include "../../broadcast_b200/csrc/residual_fast.cuh"
 
@@ -17,7 +18,7 @@ extern "C" int rf_host_residual(double* res, const double* w, const double* nx, 
     g.img = img;
     g.edges = edges;
   }
-  std::vector<double> sm(rf::NSM);
+  std::vector<double> sm(rf::NSM_BULK);
   std::vector<double> r((size_t)rf::NT * 5);
   const SchemeConsts sc = make_consts(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4);
   rf::TileCtx t(g, sc);
@@ -31,6 +32,53 @@ extern "C" int rf_host_residual(double* res, const double* w, const double* nx, 
       t.i0 = 1 + bx * rf::OI;
       t.j0 = 1 + by * rf::OJ;
       std::fill(sm.begin(), sm.end(), std::nan(""));   // reading an unwritten shared entry must show up
+      if (staged == 2) {   // k_residual_fast_bulk: w box, vol / volf boxes and the node rows by the op list of rf::bulk_op
+        t.met = sm.data() + rf::O_MET;
+        double* met = sm.data() + rf::O_MET;
+        for (int op = 0; op < rf::NBULK; ++op) {
+          const rf::BulkOp o = rf::bulk_op(g, nx, ny, t.i0, t.j0, op);
+          if (o.kind == 0) {
+            for (int e = 0; e < 5; ++e)
+              for (int b = 0; b < rf::PJ; ++b)
+                for (int a = 0; a < rf::PI; ++a) {
+                  const int si = o.x + a, sj = o.y + b;
+                  t.wsm[e * rf::NC + a + b * rf::PI] = (si < g.ni() && sj < g.nj()) ? w[e * g.sc + si + (long long)sj * g.ldc] : 0.0;
+                }
+          } else if (o.kind == 1) {
+            for (int b = 0; b < rf::MV_H; ++b)
+              for (int a = 0; a < rf::MV_W; ++a) {
+                const int si = o.x + a, sj = o.y + b;
+                met[o.dst + a + b * rf::MV_W] = (si < g.ni() && sj < g.nj()) ? vol[si + (long long)sj * g.ldc] : 0.0;
+              }
+          } else if (o.kind == 2) {
+            for (int e = 0; e < 2; ++e)
+              for (int b = 0; b < rf::MF_H; ++b)
+                for (int a = 0; a < rf::MF_W; ++a) {
+                  const int si = o.x + a, sj = o.y + b;
+                  met[o.dst + (e * rf::MF_H + b) * rf::MF_W + a] = (si < g.ni() && sj < g.nj()) ? volf[e * g.sc + si + (long long)sj * g.ldc] : 0.0;
+                }
+          } else if (o.kind == 3) {
+            if (o.bytes % 16 != 0 || (reinterpret_cast<uintptr_t>(o.src) - reinterpret_cast<uintptr_t>((op - 3) / rf::MN_ROWS >= 2 ? ny : nx)) % 16 != 0) return 7;
+            for (int q = 0; q < o.bytes / 8; ++q) met[o.dst + q] = o.src[q];
+          }
+        }
+        for (int tid = 0; tid < rf::NT; ++tid) rf::phase0<true>(t, tid);
+        for (int tid = 0; tid < rf::NT; ++tid) rf::phase1(t, tid, rf::sensor_geom_sm(t, tid, 0), rf::sensor_geom_sm(t, tid, 1));
+        if (t.has_ghost_sensor())
+          for (int tid = 0; tid < rf::NT; ++tid) rf::phase1b(t, tid);
+        for (int tid = 0; tid < rf::NT; ++tid) rf::phase2(t, tid, rf::geom_iface_sm(t, tid));
+        for (int tid = 0; tid < rf::NT; ++tid) {
+          double (&rr)[5] = *reinterpret_cast<double(*)[5]>(&r[(size_t)tid * 5]);
+          rf::balance_i(t, tid, rr);
+          rf::phase_rj(t, tid);
+        }
+        for (int tid = 0; tid < rf::NT; ++tid) rf::phase3(t, tid, rf::geom_jface_sm(t, tid));
+        for (int tid = 0; tid < rf::NT; ++tid) {
+          const double (&rr)[5] = *reinterpret_cast<double(*)[5]>(&r[(size_t)tid * 5]);
+          rf::balance_j_store(t, tid, rr);
+        }
+        continue;
+      }
       if (staged) {   // what the TMA load of k_residual_fast_tma delivers: the (PI, PJ, 5) box of w, zero fill outside the array
         for (int e = 0; e < 5; ++e)
           for (int b = 0; b < rf::PJ; ++b)

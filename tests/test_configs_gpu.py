@@ -62,12 +62,16 @@ def test_residual_at_named_config(gpu, ref, cfg):
     blk = Block(a)
     blk.apply_bcs()
     outs = {}
-    for v, name in ((5, "march"), (0, "tile"), (1, "generic")):
+    for v, name in ((5, "march"), (4, "tile"), (6, "bulk"), (0, "default"), (1, "generic")):
         outs[v] = _block_residual(blk, v)
         rec["variants"][name] = H.assert_residual_parity(outs[v], rb, b, wb, floor=floor, what=(cfg, name))
     # the two fused kernels evaluate the same formulas on the same operands: they differ at most by FMA contraction choices
-    rec["march_vs_tile"] = H.residual_errors(outs[5], outs[0], b, wb)
+    rec["march_vs_tile"] = H.residual_errors(outs[5], outs[4], b, wb)
     assert np.all(rec["march_vs_tile"]["backward"] < 1e-14), rec["march_vs_tile"]
+    # the bulk-staged tile kernel (TMA / bulk copies of w and of every metric) runs the phase functions of the LDG tile kernel on
+    # shared-memory images of the same numbers: bit for bit the same residual; the default is one of the two
+    assert np.array_equal(outs[6], outs[4]), np.abs(outs[6] - outs[4]).max()
+    assert np.array_equal(outs[0], outs[4])
     gh = a.gh
     assert not np.any(outs[0][:gh]) and not np.any(outs[0][:, :gh]) and not np.any(outs[0][-gh:]) and not np.any(outs[0][:, -gh:])
     _log(rec)

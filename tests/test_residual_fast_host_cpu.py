@@ -48,6 +48,8 @@ def test_fast_tile_residual_matches_reference(ref, hostlib, kind, im, jm):
     assert not np.any(res[:c.gh]) and not np.any(res[:, :c.gh])   # ghost frame of residu untouched
     # w planes delivered as the TMA box (zero fill outside the padded array) instead of loaded cell by cell: same bits
     assert np.array_equal(host_residual(hostlib, c, w, staged=1), res)
+    # k_residual_fast_bulk: metrics from the shared-memory images of the vol / volf boxes and the (shifted) node rows: same bits
+    assert np.array_equal(host_residual(hostlib, c, w, staged=2), res)
 
 
 def test_fast_tile_residual_nowall_spanwise_and_k2_zero(ref, hostlib):
