@@ -463,12 +463,61 @@ def main():
                     dist.all_reduce(nz, op=dist.ReduceOp.SUM)
                 jac["csr_ms"] = float(cm[0])
                 jac["csr_nnz"] = int(nz[0])
+                jac["assembly_plus_csr_s"] = jac["assembly_s"] + float(cm[0]) * 1e-3
+                if world > 1:
+                    # the per-GPU row blocks gathered on the host for the reference's PETSc path (north_star): device-to-host copy of
+                    # this rank's (indptr, indices, data) through a reused pinned staging buffer of 1 GiB, max over ranks
+                    stage = torch.empty(1 << 27, dtype=torch.float64).pin_memory()
+                    nbytes = 0
+                    barrier()
+                    t0 = time.perf_counter()
+                    for t_ in (ip, _idx, _dat):
+                        flat = t_.view(torch.uint8).view(-1)
+                        sb_ = stage.view(torch.uint8)
+                        for a0 in range(0, flat.numel(), sb_.numel()):
+                            n_ = min(sb_.numel(), flat.numel() - a0)
+                            sb_[:n_].copy_(flat[a0:a0 + n_], non_blocking=True)
+                            torch.cuda.current_stream().synchronize()
+                        nbytes += flat.numel()
+                    gs = torch.tensor([time.perf_counter() - t0, float(nbytes)], dtype=torch.float64, device=dev)
+                    gmax = gs.clone()
+                    dist.all_reduce(gmax, op=dist.ReduceOp.MAX)
+                    dist.all_reduce(gs, op=dist.ReduceOp.SUM)
+                    jac["gather_s"] = float(gmax[0])
+                    jac["gather_bytes"] = int(gs[1])
+                    del stage
                 del ip, _idx, _dat
+                del blocks, H
+                torch.cuda.empty_cache()
             else:
+                # C5 on one GPU: 97 GB of block values + 73 GB of CSR do not fit together.  The contract output (CSR / vol, what
+                # misc/PETSc_func.py:71-95 consumes) comes from the banded assembly: i-bands through ONE reused band buffer of
+                # block values, the zero filter and the CSR conversion per band (resident.BandedAssembly); timed as a whole.
+                del blocks, H
+                torch.cuda.empty_cache()
                 jac["csr_ms"] = None
-                jac["csr_note"] = "CSR row block does not fit next to the block values on this GPU at this size"
-            del blocks, H
-            torch.cuda.empty_cache()
+                if world == 1:
+                    from broadcast_b200.resident import BandedAssembly
+                    nband = int(os.environ.get("BROADCAST_B200_JAC_BANDS", "8"))
+                    ba = BandedAssembly(case, nband, dev)
+                    parts = ba.assemble_csr(blk.w)           # warm-up: allocations, graph captures
+                    nnz = int(sum(int(p_[0][-1].item()) for p_ in parts))
+                    del parts
+                    torch.cuda.empty_cache()
+                    barrier()
+                    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    b0.record()
+                    parts = ba.assemble_csr(blk.w)
+                    b1.record()
+                    barrier()
+                    jac["assembly_plus_csr_s"] = b0.elapsed_time(b1) * 1e-3
+                    jac["csr_nnz"] = nnz
+                    jac["csr_bands"] = nband
+                    jac["csr_note"] = (f"banded: {nband} i-bands through one reused band buffer of block values ({ba._buf.numel() * 8 / 2**30:.1f} GiB); "
+                                       "Jacobian -> zero filter -> CSR / vol, row blocks in row order")
+                    jac["roofline"]["assembly_plus_csr_frac"] = JAC_BYTES_PER_CELL * cells_local / jac["assembly_plus_csr_s"] / 1e9 / peak
+                    del parts, ba
+                    torch.cuda.empty_cache()
         else:
             jac = {"skipped": "block values do not fit next to the state on this GPU at this size"}
     clocks = sampler.stop() if rank == 0 else {}

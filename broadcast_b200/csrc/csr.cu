@@ -246,6 +246,58 @@ __global__ void __launch_bounds__(128) k_csr_sort_strip_rows(GridDesc g, RectLis
   }
 }
 
+
+// ---- transpose (adjoint operator): CSR of A^T from the CSR of A ------------------------------------------------------------
+// The adjoint baseflow / optimal-forcing drivers take the transpose of the assembled Jacobian (cylinder.py:1090-1177,
+// misc/PETSc_func.py: createTranspose): column counts by atomics, the int32 -> int64 scan above, a fill with one atomic cursor
+// per transposed row, then a warp-wide rank sort of every transposed row (a row of A^T holds <= 245 entries: the columns of A a
+// cell's variable appears in), so the result has ascending column indices like scipy's csr(A.T) and is deterministic.
+__global__ void k_tr_count(const int* __restrict__ indices, long long nnz, int* __restrict__ counts) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t < nnz) atomicAdd(&counts[indices[t]], 1);
+}
+// one warp per row of A: lanes stride over the row's entries
+__global__ void __launch_bounds__(256) k_tr_fill(const long long* __restrict__ indptr, const int* __restrict__ indices,
+                                                 const double* __restrict__ data, long long nrows, long long row0,
+                                                 const long long* __restrict__ tptr, int* __restrict__ cursor, int* __restrict__ tind,
+                                                 double* __restrict__ tdat) {
+  const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= nrows) return;
+  const long long p0 = indptr[r], p1 = indptr[r + 1];
+  for (long long p = p0 + lane; p < p1; p += 32) {
+    const int c = indices[p];
+    const int k = atomicAdd(&cursor[c], 1);
+    tind[tptr[c] + k] = (int)(r + row0);
+    tdat[tptr[c] + k] = data[p];
+  }
+}
+__global__ void __launch_bounds__(128) k_tr_sort_rows(long long n, const long long* __restrict__ tptr, int* __restrict__ tind,
+                                                      double* __restrict__ tdat, int* __restrict__ overflow) {
+  __shared__ int scol[4][SORT_MAX];
+  __shared__ double sval[4][SORT_MAX];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long row = (long long)blockIdx.x * 4 + w;
+  if (row >= n) return;
+  const long long p0 = tptr[row];
+  const int m = (int)(tptr[row + 1] - p0);
+  if (m > SORT_MAX) {
+    if (lane == 0) atomicAdd(overflow, 1);
+    return;
+  }
+  for (int k = lane; k < m; k += 32) {
+    scol[w][k] = tind[p0 + k];
+    sval[w][k] = tdat[p0 + k];
+  }
+  __syncwarp();
+  for (int k = lane; k < m; k += 32) {
+    const int ck = scol[w][k];
+    int rank = 0;
+    for (int u = 0; u < m; ++u) rank += scol[w][u] < ck ? 1 : 0;   // (row, column) pairs of a CSR matrix are distinct
+    tind[p0 + rank] = ck;
+    tdat[p0 + rank] = sval[w][k];
+  }
+}
 }  // namespace
 }  // namespace bcast
 
@@ -321,4 +373,39 @@ extern "C" int bcd_hybrid_csr_fill(int32_t* indices, double* data, int32_t* curs
   count_launches(2 + nstrip);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? BC_OK : (int)e;
+}
+
+// Transpose of a CSR row block (rows row0 .. row0 + nrows - 1 of a matrix with ncols columns; row0 = 0 and nrows = ncols for a whole
+// matrix): step 1 fills tptr[0 .. ncols] (int64), the caller reads tptr[ncols] (= nnz) and allocates tind / tdat; step 2 fills
+// them, columns (= rows of A) ascending.  counts / cursor: ncols + 1 ints of work space each, bsum: ceil(ncols / 2048) + 1 int64.
+extern "C" int bcd_csr_transpose_indptr(long long* tptr, int32_t* counts, long long* bsum, const int32_t* indices, long long nnz,
+                                        long long ncols, void* stream) {
+  if (ncols < 1 || nnz < 0) return BC_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int) * (ncols + 1), st);
+  if (e != cudaSuccess) return (int)e;
+  if (nnz > 0) k_tr_count<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(indices, nnz, counts);
+  const int nb = (int)((ncols + SCAN_CHUNK - 1) / SCAN_CHUNK);
+  k_scan_reduce<<<nb, SCAN_T, 0, st>>>(counts, ncols, bsum);
+  k_scan_blocks<<<1, 1024, 0, st>>>(bsum, nb);
+  k_scan_final<<<nb, SCAN_T, 0, st>>>(counts, ncols, bsum, tptr);
+  count_launches(4);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? BC_OK : (int)e;
+}
+extern "C" int bcd_csr_transpose_fill(int32_t* tind, double* tdat, int32_t* cursor, const long long* tptr, const long long* indptr,
+                                      const int32_t* indices, const double* data, long long nrows, long long row0, long long ncols,
+                                      void* stream) {
+  if (ncols < 1 || nrows < 0 || row0 < 0 || row0 + nrows >= (1LL << 31)) return BC_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(int) * (ncols + 1), st);
+  if (e != cudaSuccess) return (int)e;
+  if (nrows > 0) k_tr_fill<<<(unsigned)((nrows * 32 + 255) / 256), 256, 0, st>>>(indptr, indices, data, nrows, row0, tptr, cursor, tind, tdat);
+  k_tr_sort_rows<<<(unsigned)((ncols + 3) / 4), 128, 0, st>>>(ncols, tptr, tind, tdat, cursor + ncols);
+  int ovf = 0;
+  e = cudaMemcpyAsync(&ovf, cursor + ncols, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return (int)e;
+  count_launches(2);
+  return ovf ? BC_ERR_UNSUPPORTED : BC_OK;
 }

@@ -27,6 +27,10 @@ struct GridDesc {
   // edges bit 0 / 1: the Ilo / Ihi side is a slab-internal edge whose gh halo columns hold real neighbour data
   // (gradients are then computed there instead of extrapolated).  Whole block: ioff = 0, img = im, edges = 0.
   int ioff, img, edges;
+  // window of a larger block in j as well (the boundary-strip sub-blocks of the Jacobian assembly, jacobian.cu): global row of
+  // local row j is j + joff, the block has jmg rows.  Only the colouring seeds and the row / column numbers of the COO scatter use
+  // global indices; a j-cut has no special treatment in the kernels (the sub-blocks keep a margin wider than the stencil).
+  int joff, jmg;
   BC_HD int glo() const { return (edges & 1) ? 0 : 1; }        // first / last column with a computed gradient
   BC_HD int ghi() const { return (edges & 2) ? im + 1 : im; }
   BC_HD long long cidx(int i, int j) const { return (long long)(i - 1 + gh) + (long long)(j - 1 + gh) * ldc; }
@@ -47,6 +51,8 @@ inline GridDesc make_grid(int im, int jm, int gh) {
   g.ioff = 0;
   g.img = im;
   g.edges = 0;
+  g.joff = 0;
+  g.jmg = jm;
   return g;
 }
 

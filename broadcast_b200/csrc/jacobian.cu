@@ -67,7 +67,7 @@ static int active_bcs(const GridDesc& g, const bc_desc_t* bcs, int nbcs, int l, 
     if (d.kind != BC_KIND_JOIN) {
       const bool lo = d.loc[1] == 'l' || d.loc[1] == 'L';
       if (d.loc[0] == 'I' || d.loc[0] == 'i') keep = lo ? near_lo(l) : near_hi(l, g.img);
-      else keep = lo ? near_lo(k) : near_hi(k, g.jm);
+      else keep = lo ? near_lo(k) : near_hi(k, g.jmg);
     }
     if (keep) out[m++] = d;
   }
@@ -79,14 +79,15 @@ static int active_bcs(const GridDesc& g, const bc_desc_t* bcs, int nbcs, int l, 
 __global__ void k_scatter5(GridDesc g, int kind, double* __restrict__ jac, int* __restrict__ ia, int* __restrict__ ja,
                            const double* __restrict__ resd5, int l, int k, const double* __restrict__ coefdiag,
                            const double* __restrict__ vol, Rect rc, int compact) {
-  // i-slabs: il = local column, i = global column (see k_scatter)
-  const int iml = g.im, im = g.img, jm = g.jm, gh = g.gh, s = 2 * gh + 1;
+  // i-slabs / strip windows: il, jl = local indices (addresses), i, j = global indices (numbering, nearest-seed rules; see k_scatter)
+  const int iml = g.im, jml = g.jm, im = g.img, jm = g.jmg, gh = g.gh, s = 2 * gh + 1;
   const int wi = rc.i1 - rc.i0 + 1, wj = rc.j1 - rc.j0 + 1;
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= 5LL * wi * wj) return;
   const int il = (int)(t % wi) + rc.i0;
   const int i = il + g.ioff;
-  const int j = (int)((t / wi) % wj) + rc.j0;
+  const int jl = (int)((t / wi) % wj) + rc.j0;
+  const int j = jl + g.joff;
   const int e = (int)(t / ((long long)wi * wj)) + 1;
   const bool withjn = kind == SCATTER_JV_RELAXED_JN || kind == SCATTER_JV_JN;
   const int dummy_ia = 5 * im * jm - (withjn ? 2 : 1);
@@ -113,10 +114,10 @@ __global__ void k_scatter5(GridDesc g, int kind, double* __restrict__ jac, int* 
     }
   }
   // reference slot order (ComputeJacobian.f90:524), over the whole grid or (compact) over the rectangle only
-  const long long n = compact ? 5LL * wi * wj : 5LL * iml * jm;
-  const long long cell = compact ? (long long)(il - rc.i0) + (long long)(j - rc.j0) * wi + (long long)(e - 1) * wi * wj
-                                 : (long long)(il - 1) + (long long)(j - 1) * iml + (long long)(e - 1) * iml * jm;
-  const long long kc = g.cidx(il, j);
+  const long long n = compact ? 5LL * wi * wj : 5LL * iml * jml;
+  const long long cell = compact ? (long long)(il - rc.i0) + (long long)(jl - rc.j0) * wi + (long long)(e - 1) * wi * wj
+                                 : (long long)(il - 1) + (long long)(jl - 1) * iml + (long long)(e - 1) * iml * jml;
+  const long long kc = g.cidx(il, jl);
 #pragma unroll
   for (int m = 0; m < 5; ++m) {
     const long long slot = cell + (long long)k * n + (long long)l * n * s + (long long)m * n * s * s;
@@ -129,7 +130,7 @@ __global__ void k_scatter5(GridDesc g, int kind, double* __restrict__ jac, int* 
       } else {
         val = -r;
         if ((kind == SCATTER_JV_RELAXED || kind == SCATTER_JV_RELAXED_JN || kind == SCATTER_JV_RELAXED_DBYVOL) && row == col)
-          val = -r + coefdiag[(il - 1) + (long long)(j - 1) * iml];
+          val = -r + coefdiag[(il - 1) + (long long)(jl - 1) * iml];
         if (kind == SCATTER_JV_DBYVOL || kind == SCATTER_JV_RELAXED_DBYVOL) val = val / vol[kc];
       }
       jac[slot] = val;
@@ -323,15 +324,17 @@ extern "C" int bcd_dz_tangent_coo(double* jac1r, double* jac1i, int32_t* ia1, in
   return BC_OK;
 }
 
+constexpr int MAXCHAIN = 16;
+
 // The boundary strips of the Jacobian (rows within gh of a physical side) by the reference colour loop, all strips in
 // the SAME 49 passes: seeds (windows of the strips only) -> linearised boundary fills -> tangent of the strip rows with
 // one thread per (cell, face) -> scatter into one compact COO triple per strip (slot order of
 // misc/ComputeJacobian.f90:524 over the strip's own index space, ia/ja global).
-extern "C" int bcd_jacobian_strips(int nrect, const int32_t* rects /* [nrect][4] i0,i1,j0,j1 */, double* const* jac, int32_t* const* ia,
-                                   int32_t* const* ja, double* w, const double* nx, const double* ny, const double* vol, const double* volf,
-                                   int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs, double muref,
-                                   double tref, double s_suth, double k2, double k4, int im, int jm, int wall, const bc_desc_t* bcs,
-                                   int nbcs, int scatter_kind, const double* coefdiag, void* stream) {
+static int strips_impl(int nrect, const int32_t* rects /* [nrect][4] i0,i1,j0,j1 */, double* const* jac, int32_t* const* ia,
+                       int32_t* const* ja, double* w, const double* nx, const double* ny, const double* vol, const double* volf,
+                       int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs, double muref,
+                       double tref, double s_suth, double k2, double k4, int im, int jm, int wall, const bc_desc_t* bcs,
+                       int nbcs, int scatter_kind, const double* coefdiag, void* stream, int kcap) {
   if (im < 1 || jm < 1 || gh != 3 || nrect < 0 || nrect > 4) return BC_ERR_ARG;
   if (scatter_kind < 0 || scatter_kind > 6) return BC_ERR_ARG;
   if (nrect == 0) return BC_OK;
@@ -346,11 +349,12 @@ extern "C" int bcd_jacobian_strips(int nrect, const int32_t* rects /* [nrect][4]
   // each chain holds 116 full-grid planes of scratch (0.93 KB per cell): four chains up to 4.5 M cells, two up to 9 M, one beyond
   const long long ncells_ = (long long)im * jm;
   int K = chains_env > 0 ? chains_env : (ncells_ <= 4500000LL ? 4 : (ncells_ <= 9000000LL ? 2 : 1));
-  if (K > 4) K = 4;
+  if (kcap > 4 && ncells_ <= 400000LL) K = kcap;   // a strip sub-block: tiny kernels, every chain costs ~100 MB of scratch
+  if (K > MAXCHAIN) K = MAXCHAIN;
   if (no_graph) K = 1;
-  double* wd5c[4] = {nullptr, nullptr, nullptr, nullptr};
-  double* resd5c[4] = {nullptr, nullptr, nullptr, nullptr};
-  double* sc_[4][4];
+  double* wd5c[MAXCHAIN] = {};
+  double* resd5c[MAXCHAIN] = {};
+  double* sc_[MAXCHAIN][4];
   for (int c = 0; c < K; ++c) {   // every scratch slot the loop touches must exist before capture (allocation is not capturable)
     scratch_chain() = c;
     wd5c[c] = scratch_doubles(20, (size_t)g.sc * 25);
@@ -433,11 +437,11 @@ extern "C" int bcd_jacobian_strips(int nrect, const int32_t* rects /* [nrect][4]
     count_launches(nlaunch);
     return e == cudaSuccess ? BC_OK : (int)e;
   }
-  static thread_local cudaStream_t chain_st[4] = {nullptr, nullptr, nullptr, nullptr};
-  static thread_local cudaEvent_t chain_join[4] = {nullptr, nullptr, nullptr, nullptr};
+  static thread_local cudaStream_t chain_st[MAXCHAIN] = {};
+  static thread_local cudaEvent_t chain_join[MAXCHAIN] = {};
   static thread_local cudaEvent_t chain_fork = nullptr;
   if (K > 1 && !chain_fork) {
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < MAXCHAIN; ++c) {
       if (cudaStreamCreateWithFlags(&chain_st[c], cudaStreamNonBlocking) != cudaSuccess) return BC_ERR_ALLOC;
       if (cudaEventCreateWithFlags(&chain_join[c], cudaEventDisableTiming) != cudaSuccess) return BC_ERR_ALLOC;
     }
@@ -448,7 +452,7 @@ extern "C" int bcd_jacobian_strips(int nrect, const int32_t* rects /* [nrect][4]
   int dev = 0;
   cudaGetDevice(&dev);
   // (field by field: raw struct bytes would drag uninitialised padding into the key and miss the cache at random)
-  const long long gk[] = {g.im, g.jm, g.gh, g.ldc, g.ldn, g.sc, g.sn, g.ioff, g.img, g.edges};
+  const long long gk[] = {g.im, g.jm, g.gh, g.ldc, g.ldn, g.sc, g.sn, g.ioff, g.img, g.edges, g.joff, g.jmg};
   put(&dev, sizeof dev); put(gk, sizeof gk); put(&a, sizeof a); put(&wall, sizeof wall);
   for (int q = 0; q < 4; ++q) {
     const int rk[] = {rows.n, rows.r[q].i0, rows.r[q].i1, rows.r[q].j0, rows.r[q].j1};
@@ -516,11 +520,171 @@ extern "C" int bcd_jacobian_strips(int nrect, const int32_t* rects /* [nrect][4]
   cudaGraphDestroy(graph);
   if (e != cudaSuccess) return (int)e;
   cache.push_front(Entry{key, exec, nlaunch});
-  if (cache.size() > 8) {
+  if (cache.size() > 16) {
     cudaGraphExecDestroy(cache.back().exec);
     cache.pop_back();
   }
   e = cudaGraphLaunch(exec, gs);
   count_launches(nlaunch);
   return e == cudaSuccess ? BC_OK : (int)e;
+}
+
+// ---- boundary strips on SUB-BLOCKS --------------------------------------------------------------------------------------------
+// The colour loop above works on arrays indexed over the whole block: every colour chain needs 116 full-grid planes of scratch, so
+// C5 on one GPU could afford one chain and its 49 passes ran back to back -- ~370 us each, every kernel a single latency-bound wave
+// over 0.4 % of the cells (18 ms of the 64 ms assembly).  A strip of gh rows only reads cells within gh of itself:
+// each strip is therefore cut out of the block with a margin of gh + 2 rows (columns) into a compact SUB-BLOCK of its own -- state,
+// metrics and coefdiag copied by k_copy_window, the boundary list clipped to the window and re-expressed in its local indices,
+// global numbering through GridDesc::ioff / joff -- and the colour loop runs on that small grid with up to 16 chains (a chain costs
+// ~100 MB there).  The cut sides need no special treatment: the sub-block's ghost layers on a cut hold the parent's real cells, and
+// whatever the kernels do differently next to a cut (extrapolated instead of computed sensor gradients in the first layer) is
+// farther than the stencil from the strip rows.  Same COO slots and values as the full-grid loop.
+namespace {
+
+__global__ void k_copy_window(double* __restrict__ dst, int dld, long long dps, const double* __restrict__ src, int sld, long long sps,
+                              int x0, int y0, int w, int h, int planes) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)w * h * planes) return;
+  const int x = (int)(t % w), y = (int)((t / w) % h), p = (int)(t / ((long long)w * h));
+  dst[p * dps + x + (long long)y * dld] = src[p * sps + (x0 + x) + (long long)(y0 + y) * sld];
+}
+cudaError_t copy_window(double* dst, int dld, long long dps, const double* src, int sld, long long sps, int x0, int y0, int w, int h,
+                        int planes, cudaStream_t st) {
+  const long long n = (long long)w * h * planes;
+  k_copy_window<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dst, dld, dps, src, sld, sps, x0, y0, w, h, planes);
+  return cudaGetLastError();
+}
+
+struct SubBlock {
+  int ia, ib, ja, jb;   // parent-local cell range of the sub-block's interior
+  int im, jm;           // its size
+  bool ok;
+};
+
+// clip the boundary list of the parent to the sub-block [ia, ib] x [ja, jb] of a parent of im x jm cells and express the windows in
+// its local indices; false = this list cannot be windowed (the caller falls back to the full-grid loop)
+bool clip_bcs(const bc_desc_t* bcs, int nbcs, const SubBlock& sb, int pim, int pjm, int gh, bc_desc_t* out, int* nout) {
+  int m = 0;
+  for (int b = 0; b < nbcs; ++b) {
+    bc_desc_t d = bcs[b];
+    if (d.kind == BC_KIND_JOIN) return false;
+    BcLine line;
+    if (!decode_interface(d.loc, d.window, line)) return false;
+    const bool iside = line.kdir == 1, high = line.high != 0;
+    // the side must belong to the sub-block
+    if (iside && (high ? sb.ib != pim : sb.ia != 1)) continue;
+    if (!iside && (high ? sb.jb != pjm : sb.ja != 1)) continue;
+    int imin = d.window[0], jmin = d.window[1], imax = d.window[2], jmax = d.window[3];
+    int shift = 0;   // entries of the table the clipped line starts behind the original one
+    if (iside) {   // line along j
+      const int lo = sb.ja == 1 ? jmin : (jmin > sb.ja ? jmin : sb.ja);
+      const int hi = sb.jb == pjm ? jmax : (jmax < sb.jb ? jmax : sb.jb);
+      if (lo > hi) continue;
+      shift = lo - jmin;
+      // the inlet reads its table both by position on the line and by absolute row (bc.cuh): the two agree only if the shift
+      // equals the row offset of the sub-block
+      if (d.kind == BC_KIND_INLET && shift != sb.ja - 1) return false;
+      jmin = lo; jmax = hi;
+    } else {
+      const int lo = sb.ia == 1 ? imin : (imin > sb.ia ? imin : sb.ia);
+      const int hi = sb.ib == pim ? imax : (imax < sb.ib ? imax : sb.ib);
+      if (lo > hi) continue;
+      shift = lo - imin;
+      if (d.kind == BC_KIND_INLET && shift != sb.ia - 1) return false;
+      imin = lo; imax = hi;
+    }
+    d.window[0] = imin - (sb.ia - 1); d.window[1] = jmin - (sb.ja - 1); d.window[2] = imax - (sb.ia - 1); d.window[3] = jmax - (sb.ja - 1);
+    if (d.table) d.table = d.table + shift;   // leading dimension lm of the table is unchanged
+    if (m >= 16) return false;
+    out[m++] = d;
+  }
+  (void)gh;
+  *nout = m;
+  return true;
+}
+
+}  // namespace
+
+extern "C" int bcd_jacobian_strips(int nrect, const int32_t* rects /* [nrect][4] i0,i1,j0,j1 */, double* const* jac, int32_t* const* ia,
+                                   int32_t* const* ja, double* w, const double* nx, const double* ny, const double* vol, const double* volf,
+                                   int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs, double muref,
+                                   double tref, double s_suth, double k2, double k4, int im, int jm, int wall, const bc_desc_t* bcs,
+                                   int nbcs, int scatter_kind, const double* coefdiag, void* stream) {
+  if (im < 1 || jm < 1 || gh != 3 || nrect < 0 || nrect > 4) return BC_ERR_ARG;
+  const bool full_env = getenv("BROADCAST_B200_STRIPS_FULL") != nullptr;   // (read per call: the tests switch it)
+  static const bool no_graph = getenv("BROADCAST_B200_NO_GRAPH") != nullptr;
+  const GridDesc g = make_grid_ctx(im, jm, gh);
+  constexpr int M = 5;   // margin of a sub-block beyond its strip: gh for the stencil + 2 (see above)
+  bool windowed = !full_env && !no_graph && nrect > 0 && g.joff == 0 && g.jmg == jm && (long long)im * jm >= 4096 && im > 3 * gh + M &&
+                  jm > 3 * gh + M;
+  SubBlock sb[4];
+  bc_desc_t cb[4][16];
+  int ncb[4] = {0, 0, 0, 0};
+  for (int q = 0; q < nrect && windowed; ++q) {
+    const int i0 = rects[4 * q], i1 = rects[4 * q + 1], j0 = rects[4 * q + 2], j1 = rects[4 * q + 3];
+    if (i1 < i0 || j1 < j0) { windowed = false; break; }
+    SubBlock& s_ = sb[q];
+    if (i1 - i0 >= j1 - j0) {   // row-shaped strip: all columns, rows with the margin
+      s_.ia = 1; s_.ib = im;
+      s_.ja = j0 - M < 1 ? 1 : j0 - M; s_.jb = j1 + M > jm ? jm : j1 + M;
+    } else {
+      s_.ja = 1; s_.jb = jm;
+      s_.ia = i0 - M < 1 ? 1 : i0 - M; s_.ib = i1 + M > im ? im : i1 + M;
+    }
+    s_.im = s_.ib - s_.ia + 1; s_.jm = s_.jb - s_.ja + 1;
+    if (s_.im < 4 || s_.jm < 6) { windowed = false; break; }
+    if (!clip_bcs(bcs, nbcs, s_, im, jm, gh, cb[q], &ncb[q])) windowed = false;
+  }
+  if (!windowed)
+    return strips_impl(nrect, rects, jac, ia, ja, w, nx, ny, vol, volf, gh, cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4, im, jm,
+                       wall, bcs, nbcs, scatter_kind, coefdiag, stream, 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  // every ghost of the parent's w holds the value of its list before the windows are cut
+  {
+    cudaError_t e0 = apply_bc_list(g, gam, 0, w, nullptr, nx, ny, bcs, nbcs, st);
+    if (e0 != cudaSuccess) return (int)e0;
+    count_launches(nbcs);
+  }
+  const SlabInfo saved = current_slab();
+  int rc = BC_OK;
+  for (int q = 0; q < nrect && rc == BC_OK; ++q) {
+    const SubBlock& s_ = sb[q];
+    const GridDesc gs = make_grid(s_.im, s_.jm, gh);
+    // compact copies: slots 60 + 8 q .. of the scratch arena (chain 0), stable across calls so that the cached graphs replay
+    scratch_chain() = 0;
+    double* sw = scratch_doubles(60 + 8 * q, (size_t)gs.sc * 5);
+    double* snx = scratch_doubles(61 + 8 * q, (size_t)gs.sn * 2);
+    double* sny = scratch_doubles(62 + 8 * q, (size_t)gs.sn * 2);
+    double* svol = scratch_doubles(63 + 8 * q, (size_t)gs.sc);
+    double* svolf = scratch_doubles(64 + 8 * q, (size_t)gs.sc * 2);
+    double* scd = coefdiag ? scratch_doubles(65 + 8 * q, (size_t)s_.im * s_.jm) : nullptr;
+    if (!sw || !snx || !sny || !svol || !svolf || (coefdiag && !scd)) { rc = BC_ERR_ALLOC; break; }
+    const int x0 = s_.ia - 1, y0 = s_.ja - 1;   // storage offset of the window in the parent's padded arrays
+    cudaError_t e = copy_window(sw, gs.ldc, gs.sc, w, g.ldc, g.sc, x0, y0, gs.ni(), gs.nj(), 5, st);
+    if (e == cudaSuccess) e = copy_window(snx, gs.ldn, gs.sn, nx, g.ldn, g.sn, x0, y0, gs.ni() + 1, gs.nj() + 1, 2, st);
+    if (e == cudaSuccess) e = copy_window(sny, gs.ldn, gs.sn, ny, g.ldn, g.sn, x0, y0, gs.ni() + 1, gs.nj() + 1, 2, st);
+    if (e == cudaSuccess) e = copy_window(svol, gs.ldc, gs.sc, vol, g.ldc, g.sc, x0, y0, gs.ni(), gs.nj(), 1, st);
+    if (e == cudaSuccess) e = copy_window(svolf, gs.ldc, gs.sc, volf, g.ldc, g.sc, x0, y0, gs.ni(), gs.nj(), 2, st);
+    if (e == cudaSuccess && coefdiag) e = copy_window(scd, s_.im, 0, coefdiag, im, 0, s_.ia - 1, s_.ja - 1, s_.im, s_.jm, 1, st);
+    if (e != cudaSuccess) { rc = (int)e; break; }
+    count_launches(coefdiag ? 6 : 5);
+    // the sub-block in the numbering of the whole block: a cut in i is a slab-internal edge (computed gradients in the halo
+    // column, which holds the parent's cells); rows are numbered through joff / jmg
+    SlabInfo si;
+    si.ioff = g.ioff + s_.ia - 1;
+    si.img = g.img;
+    si.edges = (s_.ia > 1 ? 1 : (g.edges & 1)) | (s_.ib < im ? 2 : (g.edges & 2));
+    si.joff = s_.ja - 1;
+    si.jmg = jm;
+    current_slab() = si;
+    const int32_t lr[4] = {rects[4 * q] - (s_.ia - 1), rects[4 * q + 1] - (s_.ia - 1), rects[4 * q + 2] - (s_.ja - 1), rects[4 * q + 3] - (s_.ja - 1)};
+    double* jq[1] = {jac[q]};
+    int32_t* iq[1] = {ia[q]};
+    int32_t* kq[1] = {ja[q]};
+    rc = strips_impl(1, lr, jq, iq, kq, sw, snx, sny, svol, svolf, gh, cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4, s_.im, s_.jm,
+                     (wall && s_.ja == 1) ? 1 : 0, cb[q], ncb[q], scatter_kind, scd, stream, MAXCHAIN);
+    current_slab() = saved;
+  }
+  current_slab() = saved;
+  return rc;
 }

@@ -239,7 +239,7 @@ __global__ void k_testvector(GridDesc g, double* __restrict__ wd, int ndir, int 
   const int ii = blockIdx.x * blockDim.x + threadIdx.x + win.i0;
   const int jj = blockIdx.y * blockDim.y + threadIdx.y + win.j0;
   if (ii > win.i1 || jj > win.j1) return;
-  const int i = ii + 1 - g.gh + g.ioff, j = jj + 1 - g.gh;   // global column index (i-slabs: seeds also fall in the halo)
+  const int i = ii + 1 - g.gh + g.ioff, j = jj + 1 - g.gh + g.joff;   // global indices (i-slabs / strip windows: seeds also fall in the halo)
   const int s = 2 * g.gh + 1;
   const bool seed = i >= is + l + 1 && i <= ie && j >= js + k + 1 && j <= je && (i - (is + l + 1)) % s == 0 && (j - (js + k + 1)) % s == 0;
   const long long kk = ii + (long long)jj * g.ldc;
@@ -264,7 +264,7 @@ cudaError_t launch_testvector(const GridDesc& g, double* wd, int ndir, int m, in
                       min(g.nj() - 1, rows->r[q].j1 + 3 + g.gh)};
   }
   dim3 blk(32, 4);
-  int is = 0, ie = g.img, js = 0, je = g.jm;
+  int is = 0, ie = g.img, js = 0, je = g.jmg;
   if (zone) {  // testvector_partial: i = istart+l+1 .. iend+1, j = jstart+k+1 .. jend+1
     is = zone[0];
     ie = zone[1] + 1;

@@ -14,6 +14,7 @@ void scratch_release_all();
 // slab descriptor of the calling thread (bcd_slab_begin / bcd_slab_end); make_grid_ctx applies it
 struct SlabInfo {
   int ioff, img, edges;
+  int joff = 0, jmg = 0;   // j window (strip sub-blocks); jmg = 0: none
 };
 SlabInfo& current_slab();
 inline GridDesc make_grid_ctx(int im, int jm, int gh) {
@@ -23,6 +24,10 @@ inline GridDesc make_grid_ctx(int im, int jm, int gh) {
     g.ioff = s.ioff;
     g.img = s.img;
     g.edges = s.edges;
+  }
+  if (s.jmg > 0) {
+    g.joff = s.joff;
+    g.jmg = s.jmg;
   }
   return g;
 }

@@ -76,7 +76,7 @@ struct BulkMaps {
 };
 
 __global__ void __launch_bounds__(rf::NT, 2)
-    k_residual_fast_bulk(const __grid_constant__ BulkMaps maps, int l2dist, int ntx, int nty, GridDesc g, SchemeConsts c, double sqgr, bool wall,
+    k_residual_fast_bulk(const __grid_constant__ BulkMaps maps, int dbg, int l2dist, int ntx, int nty, GridDesc g, SchemeConsts c, double sqgr, bool wall,
                          const double* __restrict__ w, const double* __restrict__ nx, const double* __restrict__ ny,
                          const double* __restrict__ vol, const double* __restrict__ volf, double* __restrict__ res) {
   extern __shared__ __align__(128) double sm[];
@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(rf::NT, 2)
   t.wsm = sm;
   t.sm = sm + rf::WBUF;
   t.met = sm + rf::O_MET;
+  t.volbox = sm + rf::O_VOLBOX;
   t.sqgr = sqgr; t.wall = wall;
   t.w = w; t.nx = nx; t.ny = ny; t.vol = vol; t.volf = volf; t.res = res;
   t.i0 = 1 + blockIdx.x * rf::OI;
@@ -96,36 +97,45 @@ __global__ void __launch_bounds__(rf::NT, 2)
   }
   __syncthreads();
   if (tid < 32) {
-    // this lane's operations of the list: bytes first (one arrive.expect_tx per lane), then the copies
-    rf::BulkOp ops[(rf::NBULK + 31) / 32];
-    uint32_t bytes = 0;
+    // Warp 0 starts every copy: the three tensor boxes by lane 0 (their origins sit on even storage columns: a box whose first byte
+    // is not 16-byte aligned raises an illegal-instruction fault), the 4 x MN_ROWS node rows dealt to the lanes in two rounds.
+    // Every lane posts its own byte count.
+    constexpr int NROW = 4 * rf::MN_ROWS, NRND = (NROW + 31) / 32;
+    rf::BulkOp ops[NRND];
+    uint32_t bytes = 0u;
+    if (tid == 0) bytes = (uint32_t)(((dbg & 1) ? 0 : 5 * rf::NC) + ((dbg & 2) ? 0 : rf::MV_W * rf::MV_H) + ((dbg & 4) ? 0 : 2 * rf::MF_W * rf::MF_H)) * 8u;
 #pragma unroll
-    for (int k = 0; k < (rf::NBULK + 31) / 32; ++k) {
-      ops[k] = rf::bulk_op(g, nx, ny, t.i0, t.j0, tid + 32 * k);
-      if (ops[k].kind >= 0) bytes += (uint32_t)ops[k].bytes;
+    for (int k = 0; k < NRND; ++k) {
+      const int op = 3 + tid + 32 * k;
+      ops[k] = rf::bulk_op(g, nx, ny, t.i0, t.j0, op < rf::NBULK ? op : rf::NBULK);
+      if (dbg & 8) ops[k].bytes = 0;
+      bytes += (uint32_t)ops[k].bytes;
     }
     mbar_arrive_expect_tx(bar, bytes);
-#pragma unroll
-    for (int k = 0; k < (rf::NBULK + 31) / 32; ++k) {
-      const rf::BulkOp& o = ops[k];
-      if (o.kind == 0) tma_load_3d(sm, &maps.w, o.x, o.y, bar);
-      else if (o.kind == 1) tma_load_2d(sm + rf::O_MET + o.dst, &maps.vol, o.x, o.y, bar);
-      else if (o.kind == 2) tma_load_3d(sm + rf::O_MET + o.dst, &maps.volf, o.x, o.y, bar);
-      else if (o.kind == 3) bulk_load_1d(sm + rf::O_MET + o.dst, o.src, o.bytes, bar);
+    if (tid == 0) {
+      if (!(dbg & 1)) tma_load_3d(sm, &maps.w, t.i0 - 1, t.j0 - 1, bar);
+      if (!(dbg & 2)) tma_load_2d(sm + rf::O_VOLBOX, &maps.vol, t.i0 + 1, t.j0 + 1, bar);
+      if (!(dbg & 4)) tma_load_3d(sm + rf::O_MET + rf::M_VOLF, &maps.volf, t.i0 + 1, t.j0 + 2, bar);
     }
+#pragma unroll
+    for (int k = 0; k < NRND; ++k)
+      if (ops[k].bytes > 0) bulk_load_1d(sm + ops[k].dst, ops[k].src, ops[k].bytes, bar);
     // the same list for the tile `l2dist` launches ahead, as L2 prefetches (CTAs start in blockIdx order)
     if (l2dist > 0) {
       const int L = blockIdx.y * ntx + blockIdx.x + l2dist;
       const int bx = L % ntx, by = L / ntx;
       if (by < nty) {
         const int pi0 = 1 + bx * rf::OI, pj0 = 1 + by * rf::OJ;
+        if (tid == 0) {
+          tma_prefetch_3d(&maps.w, pi0 - 1, pj0 - 1);
+          tma_prefetch_2d(&maps.vol, pi0 + 1, pj0 + 1);
+          tma_prefetch_3d(&maps.volf, pi0 + 1, pj0 + 2);
+        }
 #pragma unroll
-        for (int k = 0; k < (rf::NBULK + 31) / 32; ++k) {
-          const rf::BulkOp o = rf::bulk_op(g, nx, ny, pi0, pj0, tid + 32 * k);
-          if (o.kind == 0) tma_prefetch_3d(&maps.w, o.x, o.y);
-          else if (o.kind == 1) tma_prefetch_2d(&maps.vol, o.x, o.y);
-          else if (o.kind == 2) tma_prefetch_3d(&maps.volf, o.x, o.y);
-          else if (o.kind == 3) bulk_prefetch_1d(o.src, o.bytes);
+        for (int k = 0; k < NRND; ++k) {
+          const int op = 3 + tid + 32 * k;
+          const rf::BulkOp o = rf::bulk_op(g, nx, ny, pi0, pj0, op < rf::NBULK ? op : rf::NBULK);
+          if (o.bytes > 0) bulk_prefetch_1d(o.src, o.bytes);
         }
       }
     }
@@ -206,7 +216,8 @@ cudaError_t launch_residual_fast_bulk(const GridDesc& g, const SchemeConsts& c, 
   }
   static const int l2dist = getenv("BROADCAST_B200_RESIDUAL_L2DIST") ? atoi(getenv("BROADCAST_B200_RESIDUAL_L2DIST")) : 592;
   const int ntx = (g.im + rf::OI - 1) / rf::OI, nty = (g.jm + rf::OJ - 1) / rf::OJ;
-  k_residual_fast_bulk<<<dim3(ntx, nty), rf::NT, SMEM, st>>>(maps, l2dist, ntx, nty, g, c, sqgr, wall, w, nx, ny, vol, volf, res);
+  static const int dbg = getenv("BROADCAST_B200_BULK_DEBUG") ? atoi(getenv("BROADCAST_B200_BULK_DEBUG")) : 0;
+  k_residual_fast_bulk<<<dim3(ntx, nty), rf::NT, SMEM, st>>>(maps, dbg, l2dist, ntx, nty, g, c, sqgr, wall, w, nx, ny, vol, volf, res);
   *done = true;
   return cudaGetLastError();
 }

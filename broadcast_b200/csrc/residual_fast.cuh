@@ -120,17 +120,25 @@ constexpr int NSM = WBUF + NSM_REST;          // doubles of shared memory per CT
 constexpr int NSM_TMA = 2 * WBUF + NSM_REST + 2;   // two w buffers + two mbarriers (109 520 bytes)
 // ---- bulk-staged variant (k_residual_fast_bulk): the mesh metrics of the tile in shared memory too ---------------------------------
 //   vol   box (OI+2) x (OJ+2)      cells i0-1 .. i0+32, j0-1 .. j0+OJ          (sensor cells)            TMA 2-D box
-//   volf  box (OI+2) x (OJ+1) x 2  cells i0 .. i0+33,  j0 .. j0+OJ             (faces)                   TMA 3-D box
+//   volf  box (OI+4) x (OJ+1) x 2  cells i0-1 .. i0+34, j0 .. j0+OJ            (faces)                   TMA 3-D box
+//         (box origins sit on even storage columns: TMA faults on a box whose first byte is not 16-byte aligned)
 //   node  4 planes (nx0, nx1, ny0, ny1) x (OJ+3) rows j0-1 .. j0+OJ+1, columns i0-1 .. i0+34: one 1-D bulk copy per plane and
 //         row (node planes have an odd leading dimension on even grids: no tensor map), started at the 16-byte aligned element at
 //         or below the row's first element, so a row sits shifted by `nshift` in {0, 1} entries in its slot of MN_SLOT doubles.
 constexpr int MV_W = OI + 2, MV_H = OJ + 2;
-constexpr int MF_W = OI + 2, MF_H = OJ + 1;
-constexpr int MN_ROWS = OJ + 3, MN_SLOT = 40, MN_COPY = 38;
+constexpr int MF_W = OI + 4, MF_H = OJ + 1;   // from cell i0-1: the first coordinate of a TMA box must be a multiple of 16 bytes
+constexpr int MN_ROWS = OJ + 3, MN_SLOT = 38, MN_COPY = 38;
 constexpr int up16(int n) { return (n + 15) / 16 * 16; }
-constexpr int M_VOL = 0, M_VOLF = up16(MV_W * MV_H), M_NODE = M_VOLF + up16(2 * MF_W * MF_H), NMET = M_NODE + 4 * MN_ROWS * MN_SLOT;
+// the vol box is read by the sensor phase only: it lives in the part of the flux-exchange buffer X that phases 0-1 do not use
+// (their divu / vort scratch takes the first 2 GW GH_ entries), at the first 128-byte aligned offset behind that scratch
+constexpr int O_X = WBUF + NARR * NC + NRB;      // offset of X() from the start of shared memory
+constexpr int O_VOLBOX = up16(O_X + 2 * GW * GH_);
+static_assert(O_VOLBOX + MV_W * MV_H <= O_X + NXB, "vol box inside the exchange buffer");
+constexpr int MF_PS = MF_W * MF_H;                // plane stride inside the volf box
+constexpr int M_VOLF = 0, M_NODE = up16(2 * MF_PS), NMET = M_NODE + 4 * MN_ROWS * MN_SLOT;
 constexpr int O_MET = up16(NSM);                 // metric region behind the arrays of the LDG kernel (128-byte aligned)
 constexpr int NSM_BULK = O_MET + NMET + 2;       // + one mbarrier
+static_assert(2 * ((long long)NSM_BULK * 8 + 1024) <= 228 * 1024, "two CTAs per SM");
 static_assert((MV_W * 8) % 16 == 0 && (MF_W * 8) % 16 == 0 && (MN_SLOT * 8) % 16 == 0 && (MN_COPY * 8) % 16 == 0, "bulk copy sizes");
 static_assert(OI + 4 + 1 <= MN_COPY && MN_COPY <= MN_SLOT, "node row window");
 static_assert(5 * NC <= WBUF, "w buffer");
@@ -176,7 +184,8 @@ struct TileCtx {
   int i0, j0;  // first output cell of the tile
   int i1 = 1 << 30, j1 = 1 << 30;   // last cell the tile may write (tangent build: the rows of a rectangle)
   unsigned char* flags = nullptr;   // tangent build: per staged cell, 1 if any of its five tangents is non-zero (face skipping)
-  const double* met = nullptr;      // bulk-staged variant: the metric region (vol / volf boxes, node rows)
+  const double* met = nullptr;      // bulk-staged variant: the metric region (volf box, node rows)
+  const double* volbox = nullptr;   // bulk-staged variant: the vol box (inside the exchange buffer, dead after the sensor phase)
   BC_HD TileCtx(const GridDesc& g_, const SchemeConsts& c_) : g(g_), c(c_) {}
   BC_HD real* arr(int a) const { return sm + a * NC; }
   BC_HD real* RB() const { return sm + NARR * NC; }
@@ -578,7 +587,7 @@ BC_HD void face_fast(const TileCtx& t, const real* s, const real* sw, const real
 // same list): op 0 = w box, 1 = vol box, 2 = volf box, 3 + (pl * MN_ROWS + r) = node row r of plane pl (0 nx0, 1 nx1, 2 ny0, 3 ny1).
 struct BulkOp {
   int kind;            // 0 w (3-D box PI x PJ x 5), 1 vol (2-D box), 2 volf (3-D box), 3 node row (1-D copy), -1 nothing
-  int dst;             // offset in doubles: kind 0 into wsm, kinds 1-3 into met
+  int dst;             // offset in doubles from the start of shared memory
   int x, y;            // tensor coordinates (storage indices) of the box origin (kinds 0-2)
   const double* src;   // kind 3
   int bytes;
@@ -591,8 +600,8 @@ BC_HD BulkOp bulk_op(const GridDesc& g, const double* nx, const double* ny, int 
   BulkOp o;
   o.kind = -1; o.dst = 0; o.x = 0; o.y = 0; o.src = nullptr; o.bytes = 0;
   if (op == 0) { o.kind = 0; o.x = i0 - 1; o.y = j0 - 1; o.bytes = 5 * NC * 8; }
-  else if (op == 1) { o.kind = 1; o.dst = M_VOL; o.x = i0 + 1; o.y = j0 + 1; o.bytes = MV_W * MV_H * 8; }
-  else if (op == 2) { o.kind = 2; o.dst = M_VOLF; o.x = i0 + 2; o.y = j0 + 2; o.bytes = 2 * MF_W * MF_H * 8; }
+  else if (op == 1) { o.kind = 1; o.dst = O_VOLBOX; o.x = i0 + 1; o.y = j0 + 1; o.bytes = MV_W * MV_H * 8; }
+  else if (op == 2) { o.kind = 2; o.dst = O_MET + M_VOLF; o.x = i0 + 1; o.y = j0 + 2; o.bytes = 2 * MF_W * MF_H * 8; }
   else if (op < NBULK) {
     const int pl = (op - 3) / MN_ROWS, r = (op - 3) - pl * MN_ROWS, k = pl & 1;
     const int srow = j0 + 1 + r;                                   // storage row of node row j0-1+r
@@ -601,7 +610,7 @@ BC_HD BulkOp bulk_op(const GridDesc& g, const double* nx, const double* ny, int 
     long long cnt = MN_COPY;
     const long long total = 2 * g.sn;
     if (lo + cnt > total) cnt = total - lo;                        // last row of the array (total and lo are even)
-    o.kind = 3; o.src = ((pl & 2) ? ny : nx) + lo; o.dst = M_NODE + (pl * MN_ROWS + r) * MN_SLOT; o.bytes = (int)cnt * 8;
+    o.kind = 3; o.src = ((pl & 2) ? ny : nx) + lo; o.dst = O_MET + M_NODE + (pl * MN_ROWS + r) * MN_SLOT; o.bytes = (int)cnt * 8;
   }
   return o;
 }
@@ -624,7 +633,7 @@ template <int DIR>
 BC_HD FaceGeom load_geom_sm(const TileCtx& t, int fi, int fj) {
   const NodeView nv = node_view(t);
   const int a = fi - (t.i0 - 1), r = fj - (t.j0 - 1);
-  const double volf = t.met[M_VOLF + DIR * MF_W * MF_H + (fi - t.i0) + (fj - t.j0) * MF_W];
+  const double volf = t.met[M_VOLF + DIR * MF_PS + (fi - t.i0 + 1) + (fj - t.j0) * MF_W];
   constexpr double ccross = (0.25 / 3.0) * 0.0625;
   const double sA = (0.5 / 24.0) * volf, sC = (0.5 * ccross) * volf;
   FaceGeom G;
@@ -657,7 +666,7 @@ BC_HD SensGeom sensor_geom_sm(const TileCtx& t, int tid, int round) {
   G.valid = sensor_of(t, tid, round, ga, gb);
   if (G.valid) {   // window coordinates of the sensor window = those of the vol box and of the node rows
     const NodeView nv = node_view(t);
-    G.vol = t.met[M_VOL + ga + gb * MV_W];
+    G.vol = t.volbox[ga + gb * MV_W];
     const double volm1 = 1.0 / G.vol;
     const double* x0 = nv.row(0, 0, gb) + ga;
     const double* y0 = nv.row(1, 0, gb) + ga;

@@ -49,36 +49,45 @@ def coo_to_csr(jac, ia, ja, nrows, ncols, row0=0):
     return indptr, cols, out
 
 
-def write_petsc_aij(path, indptr, indices, data, ncols, complex_scalar=True):
+def write_petsc_aij(path, indptr, indices, data, ncols, complex_scalar=True, index64=None, chunk=1 << 24):
     """PETSc binary AIJ (Mat) file, loadable with ``PETSc.Mat().load(PETSc.Viewer().createBinary(path, 'r'))``.
     The reference's stability drivers run a complex-scalar PETSc (biglobal_cyl.py, resolvent_all.py): values are
-    written as complex128 unless ``complex_scalar`` is False."""
+    written as complex128 unless ``complex_scalar`` is False.
+    ``index64``: the layout of a PETSc configured ``--with-64-bit-indices`` (header, row lengths and column indices are
+    big-endian int64); chosen automatically when the matrix does not fit 32-bit counts (C5: 6.09 G non-zeros).  The arrays are
+    written in chunks of ``chunk`` entries, so no big-endian copy of the whole matrix is ever held."""
     indptr = np.asarray(indptr, dtype=np.int64)
-    indices = np.asarray(indices)
-    data = np.asarray(data)
     m = indptr.size - 1
     nnz = int(indptr[-1])
-    if nnz >= 2 ** 31 or m >= 2 ** 31:
-        raise ValueError("PETSc's default binary format stores 32-bit counts")
+    if index64 is None:
+        index64 = nnz >= 2 ** 31 or m >= 2 ** 31 or ncols >= 2 ** 31
+    if not index64 and (nnz >= 2 ** 31 or m >= 2 ** 31):
+        raise ValueError("PETSc's default binary format stores 32-bit counts: pass index64=True (a --with-64-bit-indices PETSc)")
+    it = ">i8" if index64 else ">i4"
+
+    def put(fh, arr, dtype):
+        arr = np.asarray(arr)
+        for a in range(0, arr.shape[0], chunk):
+            arr[a:a + chunk].astype(dtype).tofile(fh)
+
     with open(path, "wb") as fh:
-        np.array([MAT_FILE_CLASSID, m, ncols, nnz], dtype=">i4").tofile(fh)
-        np.diff(indptr).astype(">i4").tofile(fh)
-        indices.astype(">i4").tofile(fh)
-        if complex_scalar:
-            data.astype(">c16").tofile(fh)
-        else:
-            data.astype(">f8").tofile(fh)
+        np.array([MAT_FILE_CLASSID, m, ncols, nnz], dtype=it).tofile(fh)
+        for a in range(0, m, chunk):
+            np.diff(indptr[a:min(a + chunk, m) + 1]).astype(it).tofile(fh)
+        put(fh, indices, it)
+        put(fh, data, ">c16" if complex_scalar else ">f8")
 
 
-def read_petsc_aij(path, complex_scalar=True):
+def read_petsc_aij(path, complex_scalar=True, index64=False):
     """inverse of write_petsc_aij -> (indptr, indices, data, (M, N))"""
+    it = ">i8" if index64 else ">i4"
     with open(path, "rb") as fh:
-        hdr = np.fromfile(fh, dtype=">i4", count=4)
+        hdr = np.fromfile(fh, dtype=it, count=4)
         if hdr[0] != MAT_FILE_CLASSID:
-            raise ValueError("not a PETSc binary Mat file")
+            raise ValueError("not a PETSc binary Mat file (or the other index width)")
         m, n, nnz = int(hdr[1]), int(hdr[2]), int(hdr[3])
-        rowlen = np.fromfile(fh, dtype=">i4", count=m).astype(np.int64)
-        indices = np.fromfile(fh, dtype=">i4", count=nnz).astype(np.int32)
+        rowlen = np.fromfile(fh, dtype=it, count=m).astype(np.int64)
+        indices = np.fromfile(fh, dtype=it, count=nnz).astype(np.int64 if index64 else np.int32)
         data = np.fromfile(fh, dtype=">c16" if complex_scalar else ">f8", count=nnz)
     indptr = np.concatenate(([0], np.cumsum(rowlen)))
     return indptr, indices, data.astype(np.complex128 if complex_scalar else np.float64), (m, n)

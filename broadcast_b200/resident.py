@@ -537,6 +537,70 @@ class HybridJacobian:
         return sp.csr_matrix((v.cpu().numpy(), (r.cpu().numpy(), c.cpu().numpy())), shape=(n, n))
 
 
+class BandedAssembly:
+    """Jacobian -> zero filter -> CSR (/ vol) of a block too large for its 29 x 25 block planes to sit in HBM next to the CSR itself
+    (C5 on one GPU: 97 GB of block values + 73 GB of CSR): the block is walked in ``nband`` i-bands, every band an i-slab of the
+    block in GLOBAL numbering (the machinery of the multi-GPU path, sharding.slab_of / bcd_slab_begin, with the halo columns copied
+    from the resident state instead of exchanged); ONE band-sized buffer of block values is reused by all bands, so the full block
+    array never exists and every CSR value is written once.  The result is the list of CSR row blocks in row order -- what the
+    reference's PETSc path consumes rank by rank (misc/PETSc_func.py:71-95); ``gather`` concatenates them on the device."""
+
+    def __init__(self, case: Case, nband: int, device="cuda:0"):
+        from . import sharding
+        self.case, self.nband, self.device = case, nband, torch.device(device)
+        self.bands = []
+        for b in range(nband):
+            sl, desc = sharding.slab_of(case, b, nband)
+            lo, hi = sharding.slab_range(case.im, b, nband)
+            self.bands.append((Block(sl, device, slab=desc if nband > 1 else None), lo, hi))
+        nmax = max(b.im for b, _, _ in self.bands)
+        self._buf = torch.empty(29 * 25 * case.jm * nmax, dtype=torch.float64, device=self.device)
+
+    def assemble_csr(self, w, coefdiag=None, divide_by_vol=True, thresh=2e-16):
+        """``w``: the state of the whole block (device tensor (5, jm+2gh, im+2gh), ghosts filled).  ``coefdiag``: optional (jm, im)
+        device tensor.  Returns [(indptr int64, indices int32, data float64), ...], one row block per band."""
+        gh, jm = self.case.gh, self.case.jm
+        out = []
+        for blk, lo, hi in self.bands:
+            blk.w.copy_(w[:, :, lo - 1:hi + 2 * gh])          # the band's columns + gh halo columns on each side
+            blocks = self._buf[:29 * 25 * jm * blk.im].view(29, 5, 5, jm, blk.im)
+            cd = coefdiag[:, lo - 1:hi].contiguous() if coefdiag is not None else None
+            H = jacobian_hybrid(blk, coefdiag=cd, blocks=blocks)
+            out.append(H.to_csr(thresh=thresh, divide_by_vol=divide_by_vol))
+        return out
+
+    @staticmethod
+    def gather(parts):
+        """one CSR triple (device) from the row blocks"""
+        ip = [parts[0][0]]
+        for p in parts[1:]:
+            ip.append(p[0][1:] + ip[-1][-1])
+        return torch.cat(ip), torch.cat([p[1] for p in parts]), torch.cat([p[2] for p in parts])
+
+
+def csr_transpose(indptr, indices, data, ncols, row0=0, stream=None):
+    """CSR of A^T (device tensors indptr int64 [ncols+1], indices int32, data) from the CSR row block (indptr int64, indices int32,
+    data float64) of A holding the rows row0 .. row0 + nrows - 1: the adjoint operator the reference's adjoint / optimal-forcing
+    drivers build with PETSc's createTranspose (cylinder.py:1090-1177).  Hand-written kernels (csrc/csr.cu: column counts, scan,
+    atomic fill, warp rank sort per transposed row); the result has ascending column indices, like scipy's csr_matrix(A.T)."""
+    L = _lib.lib()
+    dev = data.device
+    nrows = indptr.numel() - 1
+    nnz = int(indices.numel())
+    st = ctypes.c_void_p((stream or torch.cuda.current_stream(dev)).cuda_stream)
+    tptr = torch.empty(ncols + 1, dtype=torch.int64, device=dev)
+    counts = torch.empty(ncols + 1, dtype=torch.int32, device=dev)
+    cursor = torch.empty(ncols + 1, dtype=torch.int32, device=dev)
+    bsum = torch.empty(ncols // 2048 + 2, dtype=torch.int64, device=dev)
+    LL = ctypes.c_longlong
+    _lib.check(L.bcd_csr_transpose_indptr(_p(tptr), _p(counts), _p(bsum), _p(indices), LL(nnz), LL(ncols), st), "bcd_csr_transpose_indptr")
+    tind = torch.empty(nnz, dtype=torch.int32, device=dev)
+    tdat = torch.empty(nnz, dtype=torch.float64, device=dev)
+    _lib.check(L.bcd_csr_transpose_fill(_p(tind), _p(tdat), _p(cursor), _p(tptr), _p(indptr), _p(indices), _p(data), LL(nrows), LL(row0),
+                                        LL(ncols), st), "bcd_csr_transpose_fill")
+    return tptr, tind, tdat
+
+
 def jacobian_hybrid(blk: "Block", coefdiag=None, kind=None, blocks=None, interior="faces", strip_buffers=None):
     """Jacobian of the current state: interior rows by the direct block kernels (one launch per
     structural column offset, no colouring), boundary strips (gh rows/columns along each side) by the

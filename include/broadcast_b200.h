@@ -359,6 +359,16 @@ int bcd_hybrid_csr_fill(int32_t* indices, double* data, int32_t* cursor, const l
                         const int32_t* region, int nstrip, const int32_t* srect, const double* const* sjac,
                         const int32_t* const* sia, const int32_t* const* sja, const long long* slen, double thresh,
                         const double* vol, int gh, int im, int jm, void* stream);
+/* ---- adjoint operator (first step): CSR of A^T from the CSR row block of A on the device.  The adjoint-baseflow
+ *      and optimal-forcing drivers transpose the assembled Jacobian (cylinder.py:1090-1177; misc/PETSc_func.py createTranspose).
+ *      Step 1: tptr[0 .. ncols] (int64); the caller reads tptr[ncols] = nnz and allocates tind (int32) / tdat.  Step 2: fill, the
+ *      entries of every transposed row in ascending column order (= scipy's csr_matrix(A.T) on a matrix with sorted indices).
+ *      counts / cursor: ncols + 1 int32 of work space; bsum: ncols / 2048 + 2 int64.  row0: first global row of the block. */
+int bcd_csr_transpose_indptr(long long* tptr, int32_t* counts, long long* bsum, const int32_t* indices, long long nnz,
+                             long long ncols, void* stream);
+int bcd_csr_transpose_fill(int32_t* tind, double* tdat, int32_t* cursor, const long long* tptr, const long long* indptr,
+                           const int32_t* indices, const double* data, long long nrows, long long row0, long long ncols,
+                           void* stream);
 /* primal boundary fill of a whole list */
 int bcd_apply_bcs(double* w, const double* nx, const double* ny, double gam, int gh, int im, int jm,
                   const bc_desc_t* bcs, int nbcs, void* stream);

@@ -34,9 +34,11 @@ extern "C" int rf_host_residual(double* res, const double* w, const double* nx, 
       std::fill(sm.begin(), sm.end(), std::nan(""));   // reading an unwritten shared entry must show up
       if (staged == 2) {   // k_residual_fast_bulk: w box, vol / volf boxes and the node rows by the op list of rf::bulk_op
         t.met = sm.data() + rf::O_MET;
-        double* met = sm.data() + rf::O_MET;
+        t.volbox = sm.data() + rf::O_VOLBOX;
+        double* met = sm.data();
         for (int op = 0; op < rf::NBULK; ++op) {
           const rf::BulkOp o = rf::bulk_op(g, nx, ny, t.i0, t.j0, op);
+          if (o.kind >= 0 && o.kind <= 2 && (o.x & 1)) return 8;   // TMA: the first byte of a box must be 16-byte aligned (B200 faults otherwise)
           if (o.kind == 0) {
             for (int e = 0; e < 5; ++e)
               for (int b = 0; b < rf::PJ; ++b)

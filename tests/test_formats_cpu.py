@@ -49,6 +49,30 @@ def test_petsc_binary_roundtrip(tmp_path):
         assert os.path.getsize(p) == 16 + 4 * 40 + 4 * A.nnz + (16 if cplx else 8) * A.nnz
 
 
+def test_petsc_binary_64bit_indices_and_chunks(tmp_path):
+    """the layout of a --with-64-bit-indices PETSc (what C5's 6.09 G non-zeros need): int64 header / row lengths / columns,
+    written in small chunks; 32-bit counts are refused instead of wrapped"""
+    A = sp.random(300, 300, density=0.05, format="csr", random_state=2)
+    A.sort_indices()
+    p = str(tmp_path / "J64")
+    formats.write_petsc_aij(p, A.indptr, A.indices, A.data, 300, complex_scalar=False, index64=True, chunk=97)
+    raw = np.fromfile(p, dtype=">i8", count=4)
+    assert raw.tolist() == [1211216, 300, 300, A.nnz]
+    ip, idx, dat, shape = formats.read_petsc_aij(p, complex_scalar=False, index64=True)
+    assert shape == (300, 300) and np.array_equal(ip, A.indptr) and np.array_equal(idx, A.indices) and np.array_equal(dat, A.data)
+    import os
+    assert os.path.getsize(p) == 32 + 8 * 300 + 8 * A.nnz + 8 * A.nnz
+    # chunked 32-bit file == unchunked one
+    q1, q2 = str(tmp_path / "a"), str(tmp_path / "b")
+    formats.write_petsc_aij(q1, A.indptr, A.indices, A.data, 300, chunk=53)
+    formats.write_petsc_aij(q2, A.indptr, A.indices, A.data, 300)
+    assert open(q1, "rb").read() == open(q2, "rb").read()
+    big = np.array([0, 2 ** 31], dtype=np.int64)
+    import pytest
+    with pytest.raises(ValueError):
+        formats.write_petsc_aij(str(tmp_path / "c"), big, np.zeros(0, dtype=np.int32), np.zeros(0), 5, index64=False)
+
+
 def test_npz_keys(tmp_path):
     f = str(tmp_path / "run")
     np.savez(f + ".npz", im=3, jm=2)

@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
 timeout 300 compute-sanitizer --tool memcheck python tools/res_one.py 70x21 6 1 2>&1 | tail -12 | tee gpurun_out/r2_07_memcheck.log
-timeout 600 python -m pytest tests/test_residual_bulk_gpu.py -x -q 2>&1 | tail -15 | tee gpurun_out/r2_07_pytest.log
+timeout 900 python -m pytest tests/test_residual_bulk_gpu.py tests/test_two_zone_gpu.py -q 2>&1 | tail -15 | tee gpurun_out/r2_07_pytest.log
 for v in 4 6; do timeout 120 python tools/res_one.py 8192x2048 $v 10; done 2>&1 | grep variant | tee gpurun_out/r2_07_times.log
 for d in 148 296 1184; do BROADCAST_B200_RESIDUAL_L2DIST=$d timeout 120 python tools/res_one.py 8192x2048 6 10; done 2>&1 | grep variant | tee -a gpurun_out/r2_07_times.log
 for s in 1024x2048 630x300 500x150; do for v in 4 6; do timeout 120 python tools/res_one.py $s $v 20; done; done 2>&1 | grep variant | tee -a gpurun_out/r2_07_times.log

@@ -1,0 +1,11 @@
+mkdir -p gpurun_out
+timeout 120 python tools/res_one.py 96x48 6 1 2>&1 | tail -2 | tee gpurun_out/r2_11_first.log
+if grep -q "variant 6 ms" gpurun_out/r2_11_first.log; then
+  timeout 300 compute-sanitizer --tool memcheck --print-limit 3 python tools/res_one.py 70x21 6 1 2>&1 | grep -v "^=========     \(Host\|    \)" | head -20 | tee gpurun_out/r2_11_memcheck.log
+  for v in 4 6; do timeout 120 python tools/res_one.py 8192x2048 $v 10; done 2>&1 | grep variant | tee gpurun_out/r2_11_times.log
+  for d in 0 148 296 1184; do BROADCAST_B200_RESIDUAL_L2DIST=$d timeout 120 python tools/res_one.py 8192x2048 6 10; done 2>&1 | grep variant | tee -a gpurun_out/r2_11_times.log
+  for s in 1024x2048 630x300 500x150; do for v in 4 6; do timeout 120 python tools/res_one.py $s $v 20; done; done 2>&1 | grep variant | tee -a gpurun_out/r2_11_times.log
+  timeout 300 ncu --set full --import-source on --clock-control none -k regex:k_residual_fast_bulk -c 1 -o gpurun_out/r2_11_bulk python tools/res_one.py 8192x2048 6 2 > gpurun_out/r2_11_ncu.log 2>&1
+fi
+timeout 1500 python -m pytest tests -m gpu -q -x --deselect tests/test_multigpu_gpu.py 2>&1 | tail -15 | tee gpurun_out/r2_11_pytest.log
+for s in 500x150 2048x512 8192x2048; do timeout 300 python tools/jac_probe.py $s 2>&1 | tail -3; done | tee gpurun_out/r2_11_jac.log
