@@ -56,27 +56,18 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
       : "memory");
 }
-__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, int bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-               "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int x, int y) {
   asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(x), "r"(y), "r"(0) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, int y) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
 }
-__device__ __forceinline__ void bulk_prefetch_1d(const void* src, int bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-
 struct BulkMaps {
-  CUtensorMap w, vol, volf;
+  CUtensorMap w, vol, volf, nx, ny;
 };
 
 __global__ void __launch_bounds__(rf::NT, 2)
-    k_residual_fast_bulk(const __grid_constant__ BulkMaps maps, int dbg, int l2dist, int ntx, int nty, GridDesc g, SchemeConsts c, double sqgr, bool wall,
+    k_residual_fast_bulk(const __grid_constant__ BulkMaps maps, int l2dist, int ntx, int nty, GridDesc g, SchemeConsts c, double sqgr, bool wall,
                          const double* __restrict__ w, const double* __restrict__ nx, const double* __restrict__ ny,
                          const double* __restrict__ vol, const double* __restrict__ volf, double* __restrict__ res) {
   extern __shared__ __align__(128) double sm[];
@@ -92,55 +83,42 @@ __global__ void __launch_bounds__(rf::NT, 2)
   t.j0 = 1 + blockIdx.y * rf::OJ;
   const int tid = threadIdx.x;
   if (tid == 0) {
-    mbar_init(bar, 32);
+    mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (tid < 32) {
-    // Warp 0 starts every copy: the three tensor boxes by lane 0 (their origins sit on even storage columns: a box whose first byte
-    // is not 16-byte aligned raises an illegal-instruction fault), the 4 x MN_ROWS node rows dealt to the lanes in two rounds.
-    // Every lane posts its own byte count.
-    constexpr int NROW = 4 * rf::MN_ROWS, NRND = (NROW + 31) / 32;
-    rf::BulkOp ops[NRND];
-    uint32_t bytes = 0u;
-    if (tid == 0) bytes = (uint32_t)(((dbg & 1) ? 0 : 5 * rf::NC) + ((dbg & 2) ? 0 : rf::MV_W * rf::MV_H) + ((dbg & 4) ? 0 : 2 * rf::MF_W * rf::MF_H)) * 8u;
+    // Thread 0 starts every copy of the tile: eleven tensor boxes, all completing on one mbarrier.  Out-of-range parts of a box
+    // are zero-filled and still counted, so the byte total is a compile-time constant.
+    mbar_arrive_expect_tx(bar, (uint32_t)rf::BULK_BYTES);
 #pragma unroll
-    for (int k = 0; k < NRND; ++k) {
-      const int op = 3 + tid + 32 * k;
-      ops[k] = rf::bulk_op(g, nx, ny, t.i0, t.j0, op < rf::NBULK ? op : rf::NBULK);
-      if (dbg & 8) ops[k].bytes = 0;
-      bytes += (uint32_t)ops[k].bytes;
+    for (int op = 0; op < rf::NBULK; ++op) {
+      const rf::BulkOp o = rf::bulk_op(g, t.i0, t.j0, op);
+      if (op == 0) tma_load_3d(sm + o.dst, &maps.w, o.x, o.y, bar);
+      else if (op == 1) tma_load_2d(sm + o.dst, &maps.vol, o.x, o.y, bar);
+      else if (op == 2) tma_load_3d(sm + o.dst, &maps.volf, o.x, o.y, bar);
+      else tma_load_2d(sm + o.dst, ((op - 3) >> 2) ? &maps.ny : &maps.nx, o.x, o.y, bar);
     }
-    mbar_arrive_expect_tx(bar, bytes);
-    if (tid == 0) {
-      if (!(dbg & 1)) tma_load_3d(sm, &maps.w, t.i0 - 1, t.j0 - 1, bar);
-      if (!(dbg & 2)) tma_load_2d(sm + rf::O_VOLBOX, &maps.vol, t.i0 + 1, t.j0 + 1, bar);
-      if (!(dbg & 4)) tma_load_3d(sm + rf::O_MET + rf::M_VOLF, &maps.volf, t.i0 + 1, t.j0 + 2, bar);
-    }
-#pragma unroll
-    for (int k = 0; k < NRND; ++k)
-      if (ops[k].bytes > 0) bulk_load_1d(sm + ops[k].dst, ops[k].src, ops[k].bytes, bar);
     // the same list for the tile `l2dist` launches ahead, as L2 prefetches (CTAs start in blockIdx order)
     if (l2dist > 0) {
       const int L = blockIdx.y * ntx + blockIdx.x + l2dist;
       const int bx = L % ntx, by = L / ntx;
       if (by < nty) {
         const int pi0 = 1 + bx * rf::OI, pj0 = 1 + by * rf::OJ;
-        if (tid == 0) {
-          tma_prefetch_3d(&maps.w, pi0 - 1, pj0 - 1);
-          tma_prefetch_2d(&maps.vol, pi0 + 1, pj0 + 1);
-          tma_prefetch_3d(&maps.volf, pi0 + 1, pj0 + 2);
-        }
 #pragma unroll
-        for (int k = 0; k < NRND; ++k) {
-          const int op = 3 + tid + 32 * k;
-          const rf::BulkOp o = rf::bulk_op(g, nx, ny, pi0, pj0, op < rf::NBULK ? op : rf::NBULK);
-          if (o.bytes > 0) bulk_prefetch_1d(o.src, o.bytes);
+        for (int op = 0; op < rf::NBULK; ++op) {
+          const rf::BulkOp o = rf::bulk_op(g, pi0, pj0, op);
+          if (op == 0) tma_prefetch_3d(&maps.w, o.x, o.y);
+          else if (op == 1) tma_prefetch_2d(&maps.vol, o.x, o.y);
+          else if (op == 2) tma_prefetch_3d(&maps.volf, o.x, o.y);
+          else tma_prefetch_2d(((op - 3) >> 2) ? &maps.ny : &maps.nx, o.x, o.y);
         }
       }
     }
   }
-  mbar_wait(bar, 0u);
+  // ONE thread polls the mbarrier, the others sleep in the hardware barrier behind it: ten polling warps woke up up to a microsecond
+  // apart (ncu r2_11: 17 % of all stall samples in the polling loop + 11 % at the barrier after the primitives, waiting for the last
+  // warp to notice), and their try_wait / branch pairs were 210 of the kernel's 2 540 thread instructions per cell.  bar.sync orders the
+  // copies that thread 0 has observed complete for every thread of the CTA.
+  if (tid == 0) mbar_wait(bar, 0u);   // (the thread that initialised the mbarrier and started the copies)
+  __syncthreads();
   rf::phase0<true>(t, tid);
   __syncthreads();
   rf::phase1(t, tid, rf::sensor_geom_sm(t, tid, 0), rf::sensor_geom_sm(t, tid, 1));
@@ -186,6 +164,18 @@ bool make_map(const GridDesc& g, const double* base, int planes, int bx, int by,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// a node-layout array (2 planes of (nj + 1) rows of ldn doubles, ldn odd on even grids) seen as (nj + 1) rows of 2 ldn doubles
+bool make_node_map(const GridDesc& g, const double* base, CUtensorMap* map) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)(2 * g.ldn), (cuuint64_t)(g.nj() + 1)};
+  const cuuint64_t strides[1] = {(cuuint64_t)(2 * g.ldn) * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)rf::MN_SLOT, (cuuint32_t)rf::MN_HALF};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace
 
 // *done = true when the bulk kernel was launched; false when the bulk-copy engine cannot describe the arrays (the caller falls back to
@@ -196,14 +186,14 @@ cudaError_t launch_residual_fast_bulk(const GridDesc& g, const SchemeConsts& c, 
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if ((g.ldc & 1) || !al16(w) || !al16(vol) || !al16(volf) || !al16(nx) || !al16(ny)) return cudaSuccess;
   // the maps depend on the base pointers and the grid only: cache the last set (a Newton loop calls with the same arrays)
-  struct Key { const void *w, *vol, *volf; int im, jm; };
-  static thread_local Key key{nullptr, nullptr, nullptr, 0, 0};
+  struct Key { const void *w, *vol, *volf, *nx, *ny; int im, jm; };
+  static thread_local Key key{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
   static thread_local BulkMaps maps;
-  if (key.w != w || key.vol != vol || key.volf != volf || key.im != g.im || key.jm != g.jm) {
+  if (key.w != w || key.vol != vol || key.volf != volf || key.nx != nx || key.ny != ny || key.im != g.im || key.jm != g.jm) {
     if (!make_map(g, w, 5, rf::PI, rf::PJ, &maps.w) || !make_map(g, vol, 1, rf::MV_W, rf::MV_H, &maps.vol) ||
-        !make_map(g, volf, 2, rf::MF_W, rf::MF_H, &maps.volf))
+        !make_map(g, volf, 2, rf::MF_W, rf::MF_H, &maps.volf) || !make_node_map(g, nx, &maps.nx) || !make_node_map(g, ny, &maps.ny))
       return cudaSuccess;
-    key = Key{w, vol, volf, g.im, g.jm};
+    key = Key{w, vol, volf, nx, ny, g.im, g.jm};
   }
   constexpr size_t SMEM = (size_t)rf::NSM_BULK * sizeof(double);
   static bool ready = false;
@@ -216,8 +206,7 @@ cudaError_t launch_residual_fast_bulk(const GridDesc& g, const SchemeConsts& c, 
   }
   static const int l2dist = getenv("BROADCAST_B200_RESIDUAL_L2DIST") ? atoi(getenv("BROADCAST_B200_RESIDUAL_L2DIST")) : 592;
   const int ntx = (g.im + rf::OI - 1) / rf::OI, nty = (g.jm + rf::OJ - 1) / rf::OJ;
-  static const int dbg = getenv("BROADCAST_B200_BULK_DEBUG") ? atoi(getenv("BROADCAST_B200_BULK_DEBUG")) : 0;
-  k_residual_fast_bulk<<<dim3(ntx, nty), rf::NT, SMEM, st>>>(maps, dbg, l2dist, ntx, nty, g, c, sqgr, wall, w, nx, ny, vol, volf, res);
+  k_residual_fast_bulk<<<dim3(ntx, nty), rf::NT, SMEM, st>>>(maps, l2dist, ntx, nty, g, c, sqgr, wall, w, nx, ny, vol, volf, res);
   *done = true;
   return cudaGetLastError();
 }

@@ -122,12 +122,17 @@ constexpr int NSM_TMA = 2 * WBUF + NSM_REST + 2;   // two w buffers + two mbarri
 //   vol   box (OI+2) x (OJ+2)      cells i0-1 .. i0+32, j0-1 .. j0+OJ          (sensor cells)            TMA 2-D box
 //   volf  box (OI+4) x (OJ+1) x 2  cells i0-1 .. i0+34, j0 .. j0+OJ            (faces)                   TMA 3-D box
 //         (box origins sit on even storage columns: TMA faults on a box whose first byte is not 16-byte aligned)
-//   node  4 planes (nx0, nx1, ny0, ny1) x (OJ+3) rows j0-1 .. j0+OJ+1, columns i0-1 .. i0+34: one 1-D bulk copy per plane and
-//         row (node planes have an odd leading dimension on even grids: no tensor map), started at the 16-byte aligned element at
-//         or below the row's first element, so a row sits shifted by `nshift` in {0, 1} entries in its slot of MN_SLOT doubles.
+//   node  4 planes (nx0, nx1, ny0, ny1) x (OJ+3) rows j0-1 .. j0+OJ+1, columns i0-1 .. i0+34.  Node planes have an odd leading
+//         dimension ldn on even grids, which no tensor map can describe (strides must be multiples of 16 bytes) -- but the array
+//         seen as rows of 2 ldn elements can: node row s of plane k is then the half (t & 1) of "double row" t >> 1 with
+//         t = k (nj + 1) + s, and the rows of one parity class of a tile are consecutive double rows.  Two TMA boxes of
+//         MN_SLOT x MN_HALF per plane (one per parity class) deliver the window; a box starts at the even element at or below its
+//         first element, so its rows sit shifted by `sh` in {0, 1} entries and readers add the shift.  (The first version issued
+//         one 1-D bulk copy per row: 48 copies, each an election loop of ~13 instructions on one warp -- 1 300 warp instructions
+//         before the first byte moved, profiles/r2_b_summary.md.)
 constexpr int MV_W = OI + 2, MV_H = OJ + 2;
 constexpr int MF_W = OI + 4, MF_H = OJ + 1;   // from cell i0-1: the first coordinate of a TMA box must be a multiple of 16 bytes
-constexpr int MN_ROWS = OJ + 3, MN_SLOT = 38, MN_COPY = 38;
+constexpr int MN_ROWS = OJ + 3, MN_HALF = (MN_ROWS + 1) / 2, MN_SLOT = OI + 4;   // columns i0-1 .. i0+33 (+ shift)
 constexpr int up16(int n) { return (n + 15) / 16 * 16; }
 // the vol box is read by the sensor phase only: it lives in the part of the flux-exchange buffer X that phases 0-1 do not use
 // (their divu / vort scratch takes the first 2 GW GH_ entries), at the first 128-byte aligned offset behind that scratch
@@ -135,12 +140,13 @@ constexpr int O_X = WBUF + NARR * NC + NRB;      // offset of X() from the start
 constexpr int O_VOLBOX = up16(O_X + 2 * GW * GH_);
 static_assert(O_VOLBOX + MV_W * MV_H <= O_X + NXB, "vol box inside the exchange buffer");
 constexpr int MF_PS = MF_W * MF_H;                // plane stride inside the volf box
-constexpr int M_VOLF = 0, M_NODE = up16(2 * MF_PS), NMET = M_NODE + 4 * MN_ROWS * MN_SLOT;
+constexpr int M_VOLF = 0, M_NODE = up16(2 * MF_PS), MN_BOX = up16(MN_HALF * MN_SLOT), NMET = M_NODE + 8 * MN_BOX;   // (a TMA box lands on a 128-byte aligned address)
 constexpr int O_MET = up16(NSM);                 // metric region behind the arrays of the LDG kernel (128-byte aligned)
 constexpr int NSM_BULK = O_MET + NMET + 2;       // + one mbarrier
 static_assert(2 * ((long long)NSM_BULK * 8 + 1024) <= 228 * 1024, "two CTAs per SM");
-static_assert((MV_W * 8) % 16 == 0 && (MF_W * 8) % 16 == 0 && (MN_SLOT * 8) % 16 == 0 && (MN_COPY * 8) % 16 == 0, "bulk copy sizes");
-static_assert(OI + 4 + 1 <= MN_COPY && MN_COPY <= MN_SLOT, "node row window");
+static_assert((MV_W * 8) % 16 == 0 && (MF_W * 8) % 16 == 0 && (MN_SLOT * 8) % 16 == 0, "box rows: multiples of 16 bytes");
+static_assert(OI + 3 + 1 <= MN_SLOT, "node row window: columns a = 0 .. OI + 2 and the shift");
+constexpr int BULK_BYTES = (5 * NC + MV_W * MV_H + 2 * MF_W * MF_H + 8 * MN_HALF * MN_SLOT) * 8;   // what one tile receives
 static_assert(5 * NC <= WBUF, "w buffer");
 static_assert(5 * OJ * XI_P <= NXB, "exchange buffer");
 static_assert(OJ <= 32 && GW * OJ <= NT + 0 && (RI_W + 3) <= NT && RJ_W <= NT && 2 * OI <= NT, "thread mappings");
@@ -251,7 +257,7 @@ BC_HD void phase0(const TileCtx& t, int tid) {
     const int a = idx % PI, b = idx / PI;
     const int gi = t.i0 - H + a, gj = t.j0 - H + b;
     q[it][0] = rf_const(1.0); q[it][1] = rf_const(0.0); q[it][2] = rf_const(0.0); q[it][3] = rf_const(0.0); q[it][4] = rf_const(1.0);
-    if (idx < NC && gi <= g.im + g.gh && gj <= g.jm + g.gh) {   // cells beyond the padded array (TMA: zero fill) get a sane state
+    if (STAGED ? idx < NC : (idx < NC && gi <= g.im + g.gh && gj <= g.jm + g.gh)) {   // cells beyond the padded array get a sane state
 #ifdef BCAST_RF_DUAL
       const long long k = g.cidx(gi, gj);
 #pragma unroll
@@ -260,6 +266,7 @@ BC_HD void phase0(const TileCtx& t, int tid) {
       if constexpr (STAGED) {
 #pragma unroll
         for (int e = 0; e < 5; ++e) q[it][e] = t.wsm[e * NC + idx];
+        if (q[it][0] == 0.0) { q[it][0] = 1.0; q[it][4] = 1.0; }   // TMA zero fill outside the array (a real density is positive)
       } else {
         const double* p = t.w + g.cidx(gi, gj);
 #pragma unroll
@@ -338,7 +345,7 @@ BC_HD SensGeom prefetch_sensor(const TileCtx& t, int tid, int round) {
     const int ci = t.i0 - 1 + ga, cj = t.j0 - 1 + gb;
     const long long n = g.nidx(ci, cj);
     G.vol = BC_LDG(t.vol + g.cidx(ci, cj));
-    const double volm1 = 1.0 / G.vol;
+    const double volm1 = 1.0 / G.vol;   // (a true division: the reference's volm1, geom/dxdy.F)
     G.dxm1 = 0.5 * (BC_LDG(t.nx + n) + BC_LDG(t.nx + n + 1)) * volm1;
     G.dxm2 = 0.5 * (BC_LDG(t.nx + g.sn + n) + BC_LDG(t.nx + g.sn + n + g.ldn)) * volm1;
     G.dym1 = 0.5 * (BC_LDG(t.ny + n) + BC_LDG(t.ny + n + 1)) * volm1;
@@ -583,50 +590,48 @@ BC_HD void face_fast(const TileCtx& t, const real* s, const real* sw, const real
 }
 
 // ---- bulk-staged variant: metrics from shared memory ---------------------------------------------------------------------------
-// The copies of one tile as a flat list of operations (one per lane and round of the issuing warp; the host emulation executes the
-// same list): op 0 = w box, 1 = vol box, 2 = volf box, 3 + (pl * MN_ROWS + r) = node row r of plane pl (0 nx0, 1 nx1, 2 ny0, 3 ny1).
+// The copies of one tile as a list of tensor boxes (the host emulation executes the same list): op 0 = w, 1 = vol, 2 = volf,
+// 3 + 2 pl + p = the rows of parity class p (r = p, p + 2, ...) of node plane pl (0 nx0, 1 nx1, 2 ny0, 3 ny1).
 struct BulkOp {
-  int kind;            // 0 w (3-D box PI x PJ x 5), 1 vol (2-D box), 2 volf (3-D box), 3 node row (1-D copy), -1 nothing
+  int kind;            // 0 w (3-D box PI x PJ x 5), 1 vol (2-D box), 2 volf (3-D box), 3 node box of nx, 4 node box of ny
   int dst;             // offset in doubles from the start of shared memory
-  int x, y;            // tensor coordinates (storage indices) of the box origin (kinds 0-2)
-  const double* src;   // kind 3
-  int bytes;
+  int x, y;            // tensor coordinates of the box origin (always even x: the first byte of a box must be 16-byte aligned)
 };
-constexpr int NBULK = 3 + 4 * MN_ROWS;
-BC_HD int node_first_par(const GridDesc& g, int i0, int j0, int k, int r) {   // parity of the element index of node (i0-1, j0-1+r) of plane k
-  return (int)(((long long)(i0 + 1) + (long long)(j0 + 1 + r) * g.ldn + (long long)k * g.sn) & 1);
-}
-BC_HD BulkOp bulk_op(const GridDesc& g, const double* nx, const double* ny, int i0, int j0, int op) {
+constexpr int NBULK = 11;
+// node planes as rows of 2 ldn elements: double row and half of storage row s of plane k
+BC_HD int node_t(const GridDesc& g, int k, int s) { return k * (g.jm + 2 * g.gh + 1) + s; }
+BC_HD int node_x(const GridDesc& g, int i0, int t) { return (t & 1) * g.ldn + i0 + 1; }   // element of node column i0-1 inside its double row
+BC_HD BulkOp bulk_op(const GridDesc& g, int i0, int j0, int op) {
   BulkOp o;
-  o.kind = -1; o.dst = 0; o.x = 0; o.y = 0; o.src = nullptr; o.bytes = 0;
-  if (op == 0) { o.kind = 0; o.x = i0 - 1; o.y = j0 - 1; o.bytes = 5 * NC * 8; }
-  else if (op == 1) { o.kind = 1; o.dst = O_VOLBOX; o.x = i0 + 1; o.y = j0 + 1; o.bytes = MV_W * MV_H * 8; }
-  else if (op == 2) { o.kind = 2; o.dst = O_MET + M_VOLF; o.x = i0 + 1; o.y = j0 + 2; o.bytes = 2 * MF_W * MF_H * 8; }
+  o.kind = -1; o.dst = 0; o.x = 0; o.y = 0;
+  if (op == 0) { o.kind = 0; o.x = i0 - 1; o.y = j0 - 1; }
+  else if (op == 1) { o.kind = 1; o.dst = O_VOLBOX; o.x = i0 + 1; o.y = j0 + 1; }
+  else if (op == 2) { o.kind = 2; o.dst = O_MET + M_VOLF; o.x = i0 + 1; o.y = j0 + 2; }
   else if (op < NBULK) {
-    const int pl = (op - 3) / MN_ROWS, r = (op - 3) - pl * MN_ROWS, k = pl & 1;
-    const int srow = j0 + 1 + r;                                   // storage row of node row j0-1+r
-    if (srow > g.jm + 2 * g.gh || i0 + 1 > g.im + 2 * g.gh) return o;   // beyond the array: never read by an active face
-    const long long first = (long long)(i0 + 1) + (long long)srow * g.ldn + (long long)k * g.sn, lo = first & ~1LL;
-    long long cnt = MN_COPY;
-    const long long total = 2 * g.sn;
-    if (lo + cnt > total) cnt = total - lo;                        // last row of the array (total and lo are even)
-    o.kind = 3; o.src = ((pl & 2) ? ny : nx) + lo; o.dst = O_MET + M_NODE + (pl * MN_ROWS + r) * MN_SLOT; o.bytes = (int)cnt * 8;
+    const int pl = (op - 3) >> 1, p = (op - 3) & 1, k = pl & 1;
+    const int t = node_t(g, k, j0 + 1 + p);                        // first row of the class: storage row of node row j0-1+p
+    o.kind = 3 + (pl >> 1);
+    o.x = node_x(g, i0, t) & ~1;
+    o.y = t >> 1;
+    o.dst = O_MET + M_NODE + (op - 3) * MN_BOX;
   }
   return o;
 }
 // value of node plane (isy ? ny : nx)[k] at window coordinates (a, r) = node (i0-1+a, j0-1+r)
 struct NodeView {
   const double* m;   // met + M_NODE
-  int sb0, sb1, odd; // parity of the first element of row 0 of planes k = 0 / 1; ldn & 1
-  BC_HD int sh(int k, int r) const { return ((k ? sb1 : sb0) + (r & odd)) & 1; }
-  BC_HD const double* row(int isy, int k, int r) const { return m + ((2 * isy + k) * MN_ROWS + r) * MN_SLOT + sh(k, r); }
+  int sh[2][2];      // shift of the rows of plane k, parity class p
+  BC_HD const double* row(int isy, int k, int r) const {
+    return m + ((2 * isy + k) * 2 + (r & 1)) * MN_BOX + (r >> 1) * MN_SLOT + sh[k][r & 1];
+  }
 };
 BC_HD NodeView node_view(const TileCtx& t) {
   NodeView v;
   v.m = t.met + M_NODE;
-  v.sb0 = node_first_par(t.g, t.i0, t.j0, 0, 0);
-  v.sb1 = node_first_par(t.g, t.i0, t.j0, 1, 0);
-  v.odd = t.g.ldn & 1;
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int p = 0; p < 2; ++p) v.sh[k][p] = node_x(t.g, t.i0, node_t(t.g, k, t.j0 + 1 + p)) & 1;
   return v;
 }
 template <int DIR>

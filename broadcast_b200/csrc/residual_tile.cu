@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(TI* TJ, 3)
 }  // namespace
 
 // which kernel RES_DEFAULT names for whole-block launches: decided by measurement (profiles/r2_b_summary.md)
-constexpr bool BULK_IS_DEFAULT = false;
+constexpr bool BULK_IS_DEFAULT = true;   // C5: 2.25 ms against 2.39 ms for the LDG tile kernel (first bulk version, r2_11)
 
 cudaError_t launch_residual_tiled(const GridDesc& g, const SchemeArgs& a, bool wall, double* res, const double* w, const double* nx,
                                   const double* ny, const double* vol, const double* volf, cudaStream_t st, int variant, int part) {

@@ -37,8 +37,9 @@ extern "C" int rf_host_residual(double* res, const double* w, const double* nx, 
         t.volbox = sm.data() + rf::O_VOLBOX;
         double* met = sm.data();
         for (int op = 0; op < rf::NBULK; ++op) {
-          const rf::BulkOp o = rf::bulk_op(g, nx, ny, t.i0, t.j0, op);
-          if (o.kind >= 0 && o.kind <= 2 && (o.x & 1)) return 8;   // TMA: the first byte of a box must be 16-byte aligned (B200 faults otherwise)
+          const rf::BulkOp o = rf::bulk_op(g, t.i0, t.j0, op);
+          if (o.kind < 0 || (o.x & 1)) return 8;   // TMA: the first byte of a box must be 16-byte aligned (B200 faults otherwise)
+          if (o.dst % 16) return 9;                // ... and its shared-memory destination 128-byte aligned
           if (o.kind == 0) {
             for (int e = 0; e < 5; ++e)
               for (int b = 0; b < rf::PJ; ++b)
@@ -59,9 +60,14 @@ extern "C" int rf_host_residual(double* res, const double* w, const double* nx, 
                   const int si = o.x + a, sj = o.y + b;
                   met[o.dst + (e * rf::MF_H + b) * rf::MF_W + a] = (si < g.ni() && sj < g.nj()) ? volf[e * g.sc + si + (long long)sj * g.ldc] : 0.0;
                 }
-          } else if (o.kind == 3) {
-            if (o.bytes % 16 != 0 || (reinterpret_cast<uintptr_t>(o.src) - reinterpret_cast<uintptr_t>((op - 3) / rf::MN_ROWS >= 2 ? ny : nx)) % 16 != 0) return 7;
-            for (int q = 0; q < o.bytes / 8; ++q) met[o.dst + q] = o.src[q];
+          } else {   // node box: the array seen as (nj + 1) rows of 2 ldn elements, zero fill outside
+            const double* src = o.kind == 3 ? nx : ny;
+            const long long rowlen = 2LL * g.ldn, nrows = g.nj() + 1;
+            for (int b = 0; b < rf::MN_HALF; ++b)
+              for (int a = 0; a < rf::MN_SLOT; ++a) {
+                const long long xx = o.x + a, yy = o.y + b;
+                met[o.dst + b * rf::MN_SLOT + a] = (xx < rowlen && yy < nrows) ? src[yy * rowlen + xx] : 0.0;
+              }
           }
         }
         for (int tid = 0; tid < rf::NT; ++tid) rf::phase0<true>(t, tid);
