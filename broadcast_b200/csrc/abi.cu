@@ -416,6 +416,34 @@ int bc_flux_num_dnc5_nowall_2d_d(double*, double* residud, const double* w, cons
                       jm);
 }
 
+// isothermal-wall variant of the scheme (flux_num_dnc5_iso.F90, tangent/flux_num_dnc5_iso_d.f90): the same kernels with the wall
+// flux of rhs/fluxwall_iso.F, selected through the calling thread's wall context for the duration of the call
+struct WallIsoScope {
+  WallIso saved;
+  WallIsoScope(double twall) : saved(current_wall_iso()) { current_wall_iso() = WallIso{1, twall}; }
+  ~WallIsoScope() { current_wall_iso() = saved; }
+};
+int bc_flux_num_dnc5_iso_2d(double* residu, const double* w, double twall, const double*, const double*, const double* nx,
+                            const double* ny, const double*, const double*, const double* vol, const double* volf, int gh, double cp,
+                            double cv, double prandtl, double gam, double rgaz, double cs, double muref, double tref, double s_suth,
+                            double k2, double k4, int im, int jm) {
+  WallIsoScope scope(twall);
+  return residual_host(true, residu, w, nx, ny, vol, volf, gh, sargs(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4), im, jm);
+}
+int bc_flux_num_dnc5_iso_2d_d(double*, double* residud, const double* w, const double* wd, double twall, const double*, const double*,
+                              const double* nx, const double* ny, const double*, const double*, const double* vol, const double* volf,
+                              int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs, double muref,
+                              double tref, double s_suth, double k2, double k4, int im, int jm) {
+  WallIsoScope scope(twall);
+  return tangent_host(true, residud, w, wd, nx, ny, vol, volf, gh, sargs(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4), im,
+                      jm);
+}
+// resident mode: the wall flux of the calling thread's next bcd_* launches (on != 0: rhs/fluxwall_iso.F with this twall)
+int bcd_wall_iso(int on, double twall) {
+  current_wall_iso() = WallIso{on ? 1 : 0, on ? twall : 0.0};
+  return BC_OK;
+}
+
 int bc_bc_wall_viscous_adia_2d(double* w, const char* loc, double gam, const int32_t* interf, int gh, int im, int jm) {
   return bc_host(w, nullptr, gh, im, jm,
                  [&](const GridDesc&, double* dw, double*) { return bcd_bc_wall_viscous_adia(dw, nullptr, 0, loc, gam, interf, gh, im, jm, nullptr); });

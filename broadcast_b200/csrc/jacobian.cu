@@ -454,6 +454,10 @@ static int strips_impl(int nrect, const int32_t* rects /* [nrect][4] i0,i1,j0,j1
   // (field by field: raw struct bytes would drag uninitialised padding into the key and miss the cache at random)
   const long long gk[] = {g.im, g.jm, g.gh, g.ldc, g.ldn, g.sc, g.sn, g.ioff, g.img, g.edges, g.joff, g.jmg};
   put(&dev, sizeof dev); put(gk, sizeof gk); put(&a, sizeof a); put(&wall, sizeof wall);
+  {
+    const WallIso wi = current_wall_iso();   // baked into the captured kernel arguments (SchemeConsts)
+    put(&wi.on, sizeof wi.on); put(&wi.twall, sizeof wi.twall);
+  }
   for (int q = 0; q < 4; ++q) {
     const int rk[] = {rows.n, rows.r[q].i0, rows.r[q].i1, rows.r[q].j0, rows.r[q].j1};
     put(rk, sizeof rk);

@@ -82,42 +82,38 @@ __global__ void __launch_bounds__(rf::NT, 2)
   t.i0 = 1 + blockIdx.x * rf::OI;
   t.j0 = 1 + blockIdx.y * rf::OJ;
   const int tid = threadIdx.x;
+  t.nsh = rf::node_shift_mask(g, t.i0, t.j0);
   if (tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    // Thread 0 starts every copy of the tile: eleven tensor boxes, all completing on one mbarrier.  Out-of-range parts of a box
-    // are zero-filled and still counted, so the byte total is a compile-time constant.
+    // out-of-range parts of a box are zero-filled and still counted: the byte total of a tile is a compile-time constant
     mbar_arrive_expect_tx(bar, (uint32_t)rf::BULK_BYTES);
-#pragma unroll
-    for (int op = 0; op < rf::NBULK; ++op) {
+  }
+  __syncthreads();
+  // The eleven tensor boxes of the tile, one mbarrier; lane 0 of warp w starts boxes w, w + 10 (one thread issuing all of them kept
+  // the other nine warps at the barrier for ~250 instructions: 7.5 % of all stall samples, ncu r2_13), then the same boxes of the
+  // tile `l2dist` launches ahead as L2 prefetches (CTAs start in blockIdx order).
+  if ((tid & 31) == 0) {
+    const int L = blockIdx.y * ntx + blockIdx.x + l2dist;
+    const int pbx = L % ntx, pby = L / ntx;
+    const bool pf = l2dist > 0 && pby < nty;
+    const int pi0 = 1 + pbx * rf::OI, pj0 = 1 + pby * rf::OJ;
+    for (int op = tid >> 5; op < rf::NBULK; op += rf::NT / 32) {
       const rf::BulkOp o = rf::bulk_op(g, t.i0, t.j0, op);
-      if (op == 0) tma_load_3d(sm + o.dst, &maps.w, o.x, o.y, bar);
-      else if (op == 1) tma_load_2d(sm + o.dst, &maps.vol, o.x, o.y, bar);
-      else if (op == 2) tma_load_3d(sm + o.dst, &maps.volf, o.x, o.y, bar);
-      else tma_load_2d(sm + o.dst, ((op - 3) >> 2) ? &maps.ny : &maps.nx, o.x, o.y, bar);
-    }
-    // the same list for the tile `l2dist` launches ahead, as L2 prefetches (CTAs start in blockIdx order)
-    if (l2dist > 0) {
-      const int L = blockIdx.y * ntx + blockIdx.x + l2dist;
-      const int bx = L % ntx, by = L / ntx;
-      if (by < nty) {
-        const int pi0 = 1 + bx * rf::OI, pj0 = 1 + by * rf::OJ;
-#pragma unroll
-        for (int op = 0; op < rf::NBULK; ++op) {
-          const rf::BulkOp o = rf::bulk_op(g, pi0, pj0, op);
-          if (op == 0) tma_prefetch_3d(&maps.w, o.x, o.y);
-          else if (op == 1) tma_prefetch_2d(&maps.vol, o.x, o.y);
-          else if (op == 2) tma_prefetch_3d(&maps.volf, o.x, o.y);
-          else tma_prefetch_2d(((op - 3) >> 2) ? &maps.ny : &maps.nx, o.x, o.y);
-        }
+      const CUtensorMap* mp = op == 0 ? &maps.w : op == 1 ? &maps.vol : op == 2 ? &maps.volf : ((op - 3) >> 2) ? &maps.ny : &maps.nx;
+      if (op == 0 || op == 2) tma_load_3d(sm + o.dst, mp, o.x, o.y, bar);
+      else tma_load_2d(sm + o.dst, mp, o.x, o.y, bar);
+      if (pf) {
+        const rf::BulkOp q = rf::bulk_op(g, pi0, pj0, op);
+        if (op == 0 || op == 2) tma_prefetch_3d(mp, q.x, q.y);
+        else tma_prefetch_2d(mp, q.x, q.y);
       }
     }
   }
   // ONE thread polls the mbarrier, the others sleep in the hardware barrier behind it: ten polling warps woke up up to a microsecond
-  // apart (ncu r2_11: 17 % of all stall samples in the polling loop + 11 % at the barrier after the primitives, waiting for the last
-  // warp to notice), and their try_wait / branch pairs were 210 of the kernel's 2 540 thread instructions per cell.  bar.sync orders the
-  // copies that thread 0 has observed complete for every thread of the CTA.
-  if (tid == 0) mbar_wait(bar, 0u);   // (the thread that initialised the mbarrier and started the copies)
+  // apart and their try_wait / branch pairs were 210 of the 2 540 thread instructions per cell of the first bulk version (ncu r2_11).
+  // bar.sync orders the copies that thread 0 has observed complete for every thread of the CTA.
+  if (tid == 0) mbar_wait(bar, 0u);
   __syncthreads();
   rf::phase0<true>(t, tid);
   __syncthreads();

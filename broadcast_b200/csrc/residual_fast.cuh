@@ -192,6 +192,7 @@ struct TileCtx {
   unsigned char* flags = nullptr;   // tangent build: per staged cell, 1 if any of its five tangents is non-zero (face skipping)
   const double* met = nullptr;      // bulk-staged variant: the metric region (volf box, node rows)
   const double* volbox = nullptr;   // bulk-staged variant: the vol box (inside the exchange buffer, dead after the sensor phase)
+  int nsh = 0;                      // bulk-staged variant: bit 2 k + p = shift of the rows of node plane k, parity class p (node_shift_mask)
   BC_HD TileCtx(const GridDesc& g_, const SchemeConsts& c_) : g(g_), c(c_) {}
   BC_HD real* arr(int a) const { return sm + a * NC; }
   BC_HD real* RB() const { return sm + NARR * NC; }
@@ -345,7 +346,7 @@ BC_HD SensGeom prefetch_sensor(const TileCtx& t, int tid, int round) {
     const int ci = t.i0 - 1 + ga, cj = t.j0 - 1 + gb;
     const long long n = g.nidx(ci, cj);
     G.vol = BC_LDG(t.vol + g.cidx(ci, cj));
-    const double volm1 = 1.0 / G.vol;   // (a true division: the reference's volm1, geom/dxdy.F)
+    const double volm1 = frcp(G.vol);
     G.dxm1 = 0.5 * (BC_LDG(t.nx + n) + BC_LDG(t.nx + n + 1)) * volm1;
     G.dxm2 = 0.5 * (BC_LDG(t.nx + g.sn + n) + BC_LDG(t.nx + g.sn + n + g.ldn)) * volm1;
     G.dym1 = 0.5 * (BC_LDG(t.ny + n) + BC_LDG(t.ny + n + 1)) * volm1;
@@ -387,11 +388,17 @@ BC_HD void phase1(const TileCtx& t, int tid, const SensGeom& G0, const SensGeom&
     constexpr int HALF = (RI_H + 1) / 2;
     for (int grp = tid / (RI_W + 3); grp < 8; grp += NG) {
       const int q = grp >> 1, frow0 = (grp & 1) * HALF, nrow = (grp & 1) ? RI_H - HALF : HALF;
-      const real* src = t.arr(A_U + q) + (fcol + H) + (frow0 + 1) * PI;  // face (i0 + fcol, j0 - 2 + frow0)
-      real* dst = t.RB() + q * RQ + frow0 * RI_W + fcol;
+      // (restrict: source arrays and R buffer are disjoint parts of shared memory; without it every store orders the loads of the
+      //  next row behind it and the loop runs one shared-memory latency per row)
+      const real* __restrict__ src = t.arr(A_U + q) + (fcol + H) + (frow0 + 1) * PI;  // face (i0 + fcol, j0 - 2 + frow0)
+      real* __restrict__ dst = t.RB() + q * RQ + frow0 * RI_W + fcol;
+      real rv[HALF];
 #pragma unroll
       for (int n = 0; n < HALF; ++n)
-        if (n < nrow) dst[n * RI_W] = rrow(src + n * PI, 1);
+        if (n < nrow) rv[n] = rrow(src + n * PI, 1);
+#pragma unroll
+      for (int n = 0; n < HALF; ++n)
+        if (n < nrow) dst[n * RI_W] = rv[n];
     }
   }
 }
@@ -432,17 +439,15 @@ BC_HD void phase_rj(const TileCtx& t, int tid) {
   if (tid / RJ_W >= NG) return;
   for (int grp = tid / RJ_W; grp < 8; grp += NG) {
     const int q = grp >> 1, frow0 = (grp & 1) * HALF, nrow = (grp & 1) ? RJ_H - HALF : HALF;
-    const real* src = t.arr(A_U + q) + (fcol + 1) + (frow0 + H) * PI;  // face (i0 - 2 + fcol, j0 + frow0)
-    real* dst = t.RB() + q * RQ + frow0 * RJ_W + fcol;
-    real m2 = src[-2 * PI], m1 = src[-PI], c0 = src[0];
+    const real* __restrict__ src = t.arr(A_U + q) + (fcol + 1) + (frow0 + H) * PI;  // face (i0 - 2 + fcol, j0 + frow0)
+    real* __restrict__ dst = t.RB() + q * RQ + frow0 * RJ_W + fcol;
+    real col[HALF + 3];   // the column of the source array this thread slides along: all loads first
 #pragma unroll
-    for (int n = 0; n < HALF; ++n) {
-      if (n < nrow) {
-        const real p1 = src[(n + 1) * PI];
-        dst[n * RJ_W] = 9.0 * (m1 + c0) - (m2 + p1);
-        m2 = m1; m1 = c0; c0 = p1;
-      }
-    }
+    for (int n = 0; n < HALF + 3; ++n)
+      if (n < nrow + 3) col[n] = src[(n - 2) * PI];
+#pragma unroll
+    for (int n = 0; n < HALF; ++n)
+      if (n < nrow) dst[n * RJ_W] = 9.0 * (col[n + 1] + col[n + 2]) - (col[n] + col[n + 3]);
   }
 }
 
@@ -620,20 +625,21 @@ BC_HD BulkOp bulk_op(const GridDesc& g, int i0, int j0, int op) {
 // value of node plane (isy ? ny : nx)[k] at window coordinates (a, r) = node (i0-1+a, j0-1+r)
 struct NodeView {
   const double* m;   // met + M_NODE
-  int sh[2][2];      // shift of the rows of plane k, parity class p
+  int nsh;           // bit 2 k + p: shift of the rows of plane k, parity class p
   BC_HD const double* row(int isy, int k, int r) const {
-    return m + ((2 * isy + k) * 2 + (r & 1)) * MN_BOX + (r >> 1) * MN_SLOT + sh[k][r & 1];
+    const int c = 2 * k + (r & 1);
+    return m + (4 * isy + c) * MN_BOX + (r >> 1) * MN_SLOT + ((nsh >> c) & 1);
   }
 };
-BC_HD NodeView node_view(const TileCtx& t) {
-  NodeView v;
-  v.m = t.met + M_NODE;
+BC_HD int node_shift_mask(const GridDesc& g, int i0, int j0) {   // once per tile
+  int mask = 0;
 #pragma unroll
   for (int k = 0; k < 2; ++k)
 #pragma unroll
-    for (int p = 0; p < 2; ++p) v.sh[k][p] = node_x(t.g, t.i0, node_t(t.g, k, t.j0 + 1 + p)) & 1;
-  return v;
+    for (int p = 0; p < 2; ++p) mask |= (node_x(g, i0, node_t(g, k, j0 + 1 + p)) & 1) << (2 * k + p);
+  return mask;
 }
+BC_HD NodeView node_view(const TileCtx& t) { return NodeView{t.met + M_NODE, t.nsh}; }
 template <int DIR>
 BC_HD FaceGeom load_geom_sm(const TileCtx& t, int fi, int fj) {
   const NodeView nv = node_view(t);
@@ -672,7 +678,7 @@ BC_HD SensGeom sensor_geom_sm(const TileCtx& t, int tid, int round) {
   if (G.valid) {   // window coordinates of the sensor window = those of the vol box and of the node rows
     const NodeView nv = node_view(t);
     G.vol = t.volbox[ga + gb * MV_W];
-    const double volm1 = 1.0 / G.vol;
+    const double volm1 = frcp(G.vol);
     const double* x0 = nv.row(0, 0, gb) + ga;
     const double* y0 = nv.row(1, 0, gb) + ga;
     G.dxm1 = 0.5 * (x0[0] + x0[1]) * volm1;

@@ -22,7 +22,22 @@ namespace bcast {
 struct SchemeConsts {
   double gam, rgaz, cpprandtl, cvm1, betas, s_suth, k2, k4;
   double gam1;  // gam - 1
+  // isothermal-wall variant of the scheme (flux_num_dnc5_iso.F90: rhs/fluxwall_iso.F instead of rhs/fluxwall.F): the wall face
+  // carries a heat flux towards the wall temperature twall
+  double twall;
+  int wall_iso;
 };
+
+// Which wall flux the calling HOST thread's next launches use: set by bc_flux_num_dnc5_iso_2d(_d) / bcd_wall_iso around their
+// calls (the scheme arguments of every other entry point are the reference's and have no place for twall).
+struct WallIso {
+  int on;
+  double twall;
+};
+inline WallIso& current_wall_iso() {   // host function (declared in both compilation passes, called from host code only)
+  static thread_local WallIso w{0, 0.0};
+  return w;
+}
 
 BC_HD SchemeConsts make_consts(double cp, double cv, double prandtl, double gam, double rgaz, double cs, double muref,
                                double tref, double s_suth, double k2, double k4) {
@@ -36,6 +51,12 @@ BC_HD SchemeConsts make_consts(double cp, double cv, double prandtl, double gam,
   c.k2 = k2;
   c.k4 = k4;
   c.gam1 = gam - 1.0;
+  c.twall = 0.0;
+  c.wall_iso = 0;
+#if !defined(__CUDA_ARCH__)
+  c.twall = current_wall_iso().twall;
+  c.wall_iso = current_wall_iso().on;
+#endif
   return c;
 }
 
@@ -345,7 +366,17 @@ BC_HD void face_flux(const A& a, const SchemeConsts& c, Var<RD> (&hn)[5]) {
     hn[1] = promote<RD>(pw * nxf - (fvrou * nxf + gvrou * nyf));
     hn[2] = promote<RD>(pw * nyf - (fvrov * nxf + gvrov * nyf));
     hn[3] = promote<RD>(-(fvrow * nxf + gvrow * nyf));
-    hn[4] = promote<RD>(cst(0.0));
+    if (c.wall_iso) {
+      // fluxwall_iso.F:29-53.  Kept as the reference computes it: no factor 2 in the temperature gradient, and `lambda` is the
+      // value the i-face viscous fragment of the same cell left behind (flux_visqueux_o2_i.F:61: the AVERAGE of mu over the
+      // cells (i-1, 1) and (i, 1), not mu(i, 1)).
+      auto lambda = 0.5 * (a.template Mu<0, 0>() + a.template Mu<AT(0, -1)>()) * c.cpprandtl;
+      auto tx = (a.template T<0, 0>() - c.twall) * nxf * vf;
+      auto ty = (a.template T<0, 0>() - c.twall) * nyf * vf;
+      hn[4] = promote<RD>(-(lambda * tx * nxf + lambda * ty * nyf));
+    } else {
+      hn[4] = promote<RD>(cst(0.0));
+    }
     return;
   } else {
     constexpr double denom = 1.0 / 60.0;

@@ -89,9 +89,38 @@ def build(backend):
         f.__name__ = name
         return f
 
+    def flux_num_dnc5_iso_2d(res, w, twall, x0, y0, nx, ny, xc, yc, vol, volf, gh, cp, cv, prandtl, gam, rgaz, cs, muref, tref,
+                             s_suth, k2, k4, im=None, jm=None):
+        """srcfv/rhs/flux_num_dnc5_iso.F90: the order-5 scheme with the isothermal wall flux (twall follows w)"""
+        gh = int(gh)
+        im = int(im) if im is not None else w.shape[0] - 2 * gh
+        jm = int(jm) if jm is not None else w.shape[1] - 2 * gh
+        _state(res, "residu")
+        _check_cells(res, im, jm, gh, "residu")
+        w = _in(w)
+        _check_cells(w, im, jm, gh, "w")
+        B("flux_num_dnc5_iso_2d", res, w, twall, _in(x0), _in(y0), _in(nx), _in(ny), _in(xc), _in(yc), _in(vol), _in(volf), gh, cp, cv,
+          prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4, im, jm)
+
+    def flux_num_dnc5_iso_2d_d(res, resd, w, wd, twall, x0, y0, nx, ny, xc, yc, vol, volf, gh, cp, cv, prandtl, gam, rgaz, cs, muref,
+                               tref, s_suth, k2, k4, im=None, jm=None):
+        """srcfv/tangent/flux_num_dnc5_iso_d.f90 (twall passive)"""
+        gh = int(gh)
+        im = int(im) if im is not None else w.shape[0] - 2 * gh
+        jm = int(jm) if jm is not None else w.shape[1] - 2 * gh
+        _state(res, "residu")
+        _state(resd, "residud")
+        _check_cells(resd, im, jm, gh, "residud")
+        w, wd = _in(w), _in(wd)
+        _check_cells(w, im, jm, gh, "w")
+        _check_cells(wd, im, jm, gh, "wd")
+        B("flux_num_dnc5_iso_2d_d", res, resd, w, wd, twall, _in(x0), _in(y0), _in(nx), _in(ny), _in(xc), _in(yc), _in(vol), _in(volf), gh,
+          cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4, im, jm)
+
     f_sch = types.SimpleNamespace(
         flux_num_dnc5_2d=_scheme("flux_num_dnc5_2d"),
         flux_num_dnc5_nowall_2d=_scheme("flux_num_dnc5_nowall_2d"),
+        flux_num_dnc5_iso_2d=flux_num_dnc5_iso_2d,
     )
 
     # ------------------------------------------------------------------ f_bnd (primal boundary fills)
@@ -269,6 +298,7 @@ def build(backend):
     f_lin = types.SimpleNamespace(
         flux_num_dnc5_2d_d=_scheme_d("flux_num_dnc5_2d_d"),
         flux_num_dnc5_nowall_2d_d=_scheme_d("flux_num_dnc5_nowall_2d_d"),
+        flux_num_dnc5_iso_2d_d=flux_num_dnc5_iso_2d_d,
         bc_wall_viscous_adia_2d_d=bc_wall_viscous_adia_2d_d, bc_no_reflexion_2d_d=bc_no_reflexion_2d_d,
         bc_wall_viscous_iso_2d_d=bc_wall_viscous_iso_2d_d, bc_symmetry_2d_d=bc_symmetry_2d_d,
         bc_antisymmetry_2d_d=bc_antisymmetry_2d_d, bc_pressure_2d_d=bc_pressure_2d_d,

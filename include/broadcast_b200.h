@@ -68,6 +68,20 @@ int bc_flux_num_dnc5_nowall_2d_d(double* residu, double* residud, const double* 
                                  double prandtl, double gam, double rgaz, double cs, double muref, double tref,
                                  double s_suth, double k2, double k4, int im, int jm);
 
+/* ---- isothermal-wall variant of the scheme (`_iso`): srcfv/rhs/flux_num_dnc5_iso.F90:7-227 =
+ *      flux_num_dnc5_2d with rhs/fluxwall_iso.F (heat flux lambda (T - twall) n / vol_face through the wall face, lambda as the
+ *      i-face viscous fragment left it: flux_visqueux_o2_i.F:61) and its tangent srcfv/tangent/flux_num_dnc5_iso_d.f90:15-3877
+ *      (twall passive).  Same argument lists as the reference: twall follows w (and wd). */
+int bc_flux_num_dnc5_iso_2d(double* residu, const double* w, double twall, const double* x0, const double* y0, const double* nx,
+                            const double* ny, const double* xc, const double* yc, const double* vol, const double* volf,
+                            int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
+                            double muref, double tref, double s_suth, double k2, double k4, int im, int jm);
+int bc_flux_num_dnc5_iso_2d_d(double* residu, double* residud, const double* w, const double* wd, double twall,
+                              const double* x0, const double* y0, const double* nx, const double* ny, const double* xc,
+                              const double* yc, const double* vol, const double* volf, int gh, double cp, double cv,
+                              double prandtl, double gam, double rgaz, double cs, double muref, double tref, double s_suth,
+                              double k2, double k4, int im, int jm);
+
 /* ---- boundary fills (f_bnd.*) and their tangents (f_lin.*_d): srcfv/borders/ (.F90), srcfv/tangent/bc_*_d.f90 */
 int bc_bc_wall_viscous_adia_2d(double* w, const char* loc, double gam, const int32_t* interf, int gh, int im, int jm);
 int bc_bc_wall_viscous_adia_2d_d(double* w, double* wd, const char* loc, double gam, const int32_t* interf, int gh,
@@ -369,6 +383,9 @@ int bcd_csr_transpose_indptr(long long* tptr, int32_t* counts, long long* bsum, 
 int bcd_csr_transpose_fill(int32_t* tind, double* tdat, int32_t* cursor, const long long* tptr, const long long* indptr,
                            const int32_t* indices, const double* data, long long nrows, long long row0, long long ncols,
                            void* stream);
+/* isothermal-wall scheme variant in resident mode: the wall flux of the calling thread's next bcd_* launches (residual, tangent,
+ * colour loops, strips) is rhs/fluxwall_iso.F with this twall while on != 0 (bc_flux_num_dnc5_iso_2d sets it around its own call) */
+int bcd_wall_iso(int on, double twall);
 /* primal boundary fill of a whole list */
 int bcd_apply_bcs(double* w, const double* nx, const double* ny, double gam, int gh, int im, int jm,
                   const bc_desc_t* bcs, int nbcs, void* stream);

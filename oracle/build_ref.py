@@ -30,6 +30,8 @@ FILES = [
     ("srcfv/prepro/flux_num_dnc5_nowall.f90", None),
     ("srcfv/tangent/flux_num_dnc5_d.f90", None),
     ("srcfv/tangent/flux_num_dnc5_nowall_d.f90", None),
+    ("srcfv/prepro/flux_num_dnc5_iso.f90", None),
+    ("srcfv/tangent/flux_num_dnc5_iso_d.f90", None),
     ("srcfv/prepro/bc_wall_viscous.f90", ["bc_wall_viscous_adia_2d"]),
     ("srcfv/prepro/bc_no_reflexion.f90", ["bc_no_reflexion_2d"]),
     ("srcfv/prepro/bc_supandsubinlet.f90", ["bc_supandsubinlet_2d"]),

@@ -8,6 +8,9 @@
 
 using namespace bcast;
 
+// isothermal-wall scheme variant (flux_num_dnc5_iso.F90): wall context of the calling thread for the next rf_host_residual calls
+extern "C" void rf_host_wall_iso(int on, double twall) { current_wall_iso() = WallIso{on, twall}; }
+
 extern "C" int rf_host_residual(double* res, const double* w, const double* nx, const double* ny, const double* vol, const double* volf,
                                 int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs, double muref,
                                 double tref, double s_suth, double k2, double k4, int im, int jm, int wall, int ioff, int img, int edges, int staged) {
@@ -35,6 +38,7 @@ extern "C" int rf_host_residual(double* res, const double* w, const double* nx, 
       if (staged == 2) {   // k_residual_fast_bulk: w box, vol / volf boxes and the node rows by the op list of rf::bulk_op
         t.met = sm.data() + rf::O_MET;
         t.volbox = sm.data() + rf::O_VOLBOX;
+        t.nsh = rf::node_shift_mask(g, t.i0, t.j0);
         double* met = sm.data();
         for (int op = 0; op < rf::NBULK; ++op) {
           const rf::BulkOp o = rf::bulk_op(g, t.i0, t.j0, op);

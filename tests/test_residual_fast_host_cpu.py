@@ -89,3 +89,26 @@ def test_fast_tile_residual_on_an_i_slab_equals_the_single_block(ref, hostlib):
         part = host_residual(hostlib, cs, np.asfortranarray(cs.w), slab=slab)
         lo = slab[0]
         assert np.array_equal(part[gh:-gh, gh:-gh], full[gh + lo:gh + lo + cs.im, gh:-gh])
+
+
+def test_isothermal_wall_scheme_variant(ref, hostlib):
+    """flux_num_dnc5_iso_2d (srcfv/rhs/flux_num_dnc5_iso.F90: rhs/fluxwall_iso.F instead of rhs/fluxwall.F) through the product's wall-row
+    templates (scheme.cuh, host build) against the reference routine: only the energy flux through the wall face differs"""
+    c = H.make_case("bl", 70, 21, ref, with_w=True)
+    w, res_adia = H.residual_sequence(ref, c)
+    twall = 1.2 * float(c.phys.get("tinf", 1.0)) if "tinf" in c.phys else 1.1
+    res_ref = c.zeros_state()
+    ref["f_sch"].flux_num_dnc5_iso_2d(res_ref, w, twall, *c.scheme_args())
+    hostlib.rf_host_wall_iso(1, ctypes.c_double(twall))
+    try:
+        res = host_residual(hostlib, c, w)
+        res_b = host_residual(hostlib, c, w, staged=2)
+    finally:
+        hostlib.rf_host_wall_iso(0, ctypes.c_double(0.0))
+    gh = c.gh
+    err = H.rel_err(res[gh:-gh, gh:-gh], res_ref[gh:-gh, gh:-gh])
+    assert np.all(err < 1e-12), err
+    assert np.array_equal(res, res_b)
+    # the variant really differs from the adiabatic scheme, and only in the energy equation of the first row
+    d = np.abs(res_ref - res_adia)
+    assert d[gh:-gh, gh, 4].max() > 0 and d[gh:-gh, gh + 1:-gh].max() == 0 and d[..., :4].max() == 0
