@@ -33,7 +33,7 @@ def kernel_source_hash():
     """sha256 over the sources of the default residual kernel: the key that ties an ncu capture to the code that ran"""
     import hashlib
     h = hashlib.sha256()
-    for f in ("residual_fast.cuh", "residual_fast.cu", "scheme.cuh", "grid.cuh"):
+    for f in ("residual_fast.cuh", "residual_bulk.cu", "residual_tile.cu", "scheme.cuh", "grid.cuh"):
         h.update(open(os.path.join(ROOT, "broadcast_b200", "csrc", f), "rb").read())
     return h.hexdigest()[:16]
 
@@ -399,10 +399,10 @@ def main():
     # roofline of the dominant kernel (fused residual tile kernel), per launch, per GPU
     achieved = RES_BYTES_PER_CELL * cells_local / (k_ms * 1e-3) / 1e9
     traffic, traffic_src = measured_traffic(a.im, a.jm, world)
-    roofline = {"bound": "hbm", "kernel": "k_residual_fast (32x9 tile, 320 threads)" + ("; inner tiles + ring of tiles = 2 launches per step overlapping the halo exchange and boundary fills, timed first launch to end of last" if overlap else ""), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "kernel": "k_residual_fast_bulk (32x9 tile, 320 threads, every input of the tile by TMA)" + ("; inner tiles + ring of tiles = 2 launches per step overlapping the halo exchange and boundary fills, timed first launch to end of last" if overlap else ""), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_kind": peak_kind, "kernel_timing": kernel_timing, "traffic": traffic, "traffic_capture": traffic_src, "kernel_ms": k_ms,
                 "algorithmic_bytes_per_cell": RES_BYTES_PER_CELL,
-                "fp64_pipe_note": "FP64-pipe bound at ~11 flop/B (ridge 5.8): see DESIGN.md section 4 and profiles/"}
+                "fp64_pipe_note": "970 FP64 instructions per cell (0.87 ms at 100 % of the FP64 pipe): on-chip bound, see DESIGN.md section 4 and profiles/r2_b_summary.md"}
 
     # Jacobian assembly of the same state (BASELINE.json metric, second half): regular rows by face linearisation into the
     # fixed 29-block pattern + the four boundary strips by the reference colour loop; algorithmic bytes 5904 B per cell

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Write profiles/residual_traffic.json from an `ncu --set full --page raw --csv` export of the default residual kernel:
 
-    ncu --set full --clock-control none -k regex:k_residual_fast -c 1 -o gpurun_out/res_full python tools/res_one.py 8192x2048 0 2
+    ncu --set full --clock-control none -k regex:k_residual_fast_bulk -c 1 -o gpurun_out/res_full python tools/res_one.py 8192x2048 0 2
     ncu -i gpurun_out/res_full.ncu-rep --page raw --csv > profiles/rX_residual_fast_full_raw.csv
     python tools/ncu_traffic.py profiles/rX_residual_fast_full_raw.csv 8192 2048
 
@@ -17,7 +17,8 @@ lines = [l for l in open(path) if not l.startswith("==")]
 rows = list(csv.reader(lines))
 hdr, units = rows[0], rows[1]
 data = [r for r in rows[2:] if len(r) == len(hdr)]
-pick = [r for r in data if "k_residual_fast" in r[hdr.index("Kernel Name")] and "tma" not in r[hdr.index("Kernel Name")]]
+pick = [r for r in data if "k_residual_fast_bulk" in r[hdr.index("Kernel Name")]] or \
+       [r for r in data if "k_residual_fast" in r[hdr.index("Kernel Name")] and "tma" not in r[hdr.index("Kernel Name")]]
 r = pick[-1]
 
 
