@@ -33,9 +33,22 @@ int check_device() {
   if (e != cudaSuccess || n <= 0) return fail(BC_ERR_NODEV, "no CUDA device available (broadcast_b200 has no CPU fallback)");
   return BC_OK;
 }
+// gh = 2 / 3 / 4 / 5: the scheme family flux_num_dnc3 / 5 / 7 / 9 (gh = (order + 1) / 2, BROADCAST_npz.py:501-502).  The boundary fills,
+// seeds, scatters, norms, the residual and the tangent exist for every member; the fused kernels and the block Jacobian are order 5.
 int check_dims(int im, int jm, int gh) {
   if (im < 1 || jm < 1) return fail(BC_ERR_ARG, "im and jm must be positive");
-  if (gh != 3) return fail(BC_ERR_UNSUPPORTED, "only the order-5 scheme (gh = 3) is implemented");
+  if (gh < 2 || gh > 5) return fail(BC_ERR_UNSUPPORTED, "gh must be 2, 3, 4 or 5 (schemes flux_num_dnc3 / 5 / 7 / 9)");
+  return BC_OK;
+}
+int check_order5(int gh) {
+  if (gh != 3) return fail(BC_ERR_UNSUPPORTED, "this entry point exists for the order-5 scheme (gh = 3) only");
+  return BC_OK;
+}
+// the scheme routine named `order` on a block with `gh` ghost layers: the off-centred wall rows read the cell rows 1 .. NP
+int check_scheme(int order, int gh, int jm, bool wall) {
+  if (gh != (order + 1) / 2) return fail(BC_ERR_UNSUPPORTED, "the dnc schemes run with gh = (order + 1) / 2 ghost layers");
+  const int np = order == 3 ? 2 : order == 5 ? 5 : order == 7 ? 9 : 11;
+  if (wall && jm + gh < np) return fail(BC_ERR_ARG, "jm too small for the wall rows of this order");
   return BC_OK;
 }
 
@@ -240,8 +253,9 @@ int bcd_residual(double* residu, const double* w, const double* nx, const double
   if (int rc = check_dims(im, jm, gh)) return rc;
   const GridDesc g = make_grid_ctx(im, jm, gh);
   const SchemeArgs a = sargs(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4);
+  if (int rc = check_scheme(2 * gh - 1, gh, jm, wall != 0)) return rc;
   cudaError_t e;
-  if (use_generic == RES_GENERIC) {
+  if (use_generic == RES_GENERIC || gh != 3) {   // orders 3 / 7 / 9: the reference-shaped pipeline on the order's stencil tables
     e = launch_residual_generic(g, a, wall != 0, 0, residu, w, nullptr, nx, ny, vol, volf, nullptr, (cudaStream_t)stream);
     g_launches += 4;
   } else {
@@ -256,6 +270,7 @@ int bcd_residual_part(double* residu, const double* w, const double* nx, const d
                       double cp, double cv, double prandtl, double gam, double rgaz, double cs, double muref, double tref, double s_suth,
                       double k2, double k4, int im, int jm, int wall, int part, void* stream) {
   if (int rc = check_dims(im, jm, gh)) return rc;
+  if (int rc = check_order5(gh)) return rc;
   if (part < 0 || part > 2) return fail(BC_ERR_ARG, "part must be 0 (all), 1 (inner tiles) or 2 (ring of tiles)");
   const GridDesc g = make_grid_ctx(im, jm, gh);
   const SchemeArgs a = sargs(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4);
@@ -270,6 +285,7 @@ int bcd_tangent(double* residud, const double* w, const double* wd, int ndir, co
                 double tref, double s_suth, double k2, double k4, int im, int jm, int wall, const int32_t* rect, void* stream) {
   if (int rc = check_dims(im, jm, gh)) return rc;
   if (ndir != 1 && ndir != 5) return fail(BC_ERR_ARG, "ndir must be 1 or 5");
+  if (int rc = check_scheme(2 * gh - 1, gh, jm, wall != 0)) return rc;
   const GridDesc g = make_grid_ctx(im, jm, gh);
   const SchemeArgs a = sargs(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4);
   Rect rc{1, im, 1, jm};
@@ -393,18 +409,21 @@ int bcd_norm_sums(double* out10, const double* rhs, int im, int jm, int gh, void
 int bc_flux_num_dnc5_2d(double* residu, const double* w, const double*, const double*, const double* nx, const double* ny, const double*,
                         const double*, const double* vol, const double* volf, int gh, double cp, double cv, double prandtl, double gam,
                         double rgaz, double cs, double muref, double tref, double s_suth, double k2, double k4, int im, int jm) {
+  if (int rc = check_scheme(5, gh, jm, true)) return rc;
   return residual_host(true, residu, w, nx, ny, vol, volf, gh, sargs(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4), im, jm);
 }
 int bc_flux_num_dnc5_nowall_2d(double* residu, const double* w, const double*, const double*, const double* nx, const double* ny,
                                const double*, const double*, const double* vol, const double* volf, int gh, double cp, double cv,
                                double prandtl, double gam, double rgaz, double cs, double muref, double tref, double s_suth, double k2,
                                double k4, int im, int jm) {
+  if (int rc = check_scheme(5, gh, jm, false)) return rc;
   return residual_host(false, residu, w, nx, ny, vol, volf, gh, sargs(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4), im, jm);
 }
 int bc_flux_num_dnc5_2d_d(double*, double* residud, const double* w, const double* wd, const double*, const double*, const double* nx,
                           const double* ny, const double*, const double*, const double* vol, const double* volf, int gh, double cp,
                           double cv, double prandtl, double gam, double rgaz, double cs, double muref, double tref, double s_suth,
                           double k2, double k4, int im, int jm) {
+  if (int rc = check_scheme(5, gh, jm, true)) return rc;
   return tangent_host(true, residud, w, wd, nx, ny, vol, volf, gh, sargs(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4), im,
                       jm);
 }
@@ -412,9 +431,50 @@ int bc_flux_num_dnc5_nowall_2d_d(double*, double* residud, const double* w, cons
                                  const double* nx, const double* ny, const double*, const double*, const double* vol, const double* volf,
                                  int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs, double muref,
                                  double tref, double s_suth, double k2, double k4, int im, int jm) {
+  if (int rc = check_scheme(5, gh, jm, false)) return rc;
   return tangent_host(false, residud, w, wd, nx, ny, vol, volf, gh, sargs(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4), im,
                       jm);
 }
+
+// the other orders of the family (srcfv/rhs/flux_num_dnc{3,7,9}.F90, _nowall variants, srcfv/tangent/flux_num_dnc{3,7,9}_d.f90): same
+// argument lists; the routine's order must agree with the ghost depth of the arrays it is handed
+#define BCAST_SCHEME_ENTRIES(ORD)                                                                                                          \
+  int bc_flux_num_dnc##ORD##_2d(double* residu, const double* w, const double*, const double*, const double* nx, const double* ny,         \
+                                const double*, const double*, const double* vol, const double* volf, int gh, double cp, double cv,       \
+                                double prandtl, double gam, double rgaz, double cs, double muref, double tref, double s_suth, double k2,   \
+                                double k4, int im, int jm) {                                                                              \
+    if (int rc = check_scheme(ORD, gh, jm, true)) return rc;                                                                              \
+    return residual_host(true, residu, w, nx, ny, vol, volf, gh, sargs(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4), im,  \
+                         jm);                                                                                                             \
+  }                                                                                                                                       \
+  int bc_flux_num_dnc##ORD##_nowall_2d(double* residu, const double* w, const double*, const double*, const double* nx, const double* ny,  \
+                                       const double*, const double*, const double* vol, const double* volf, int gh, double cp, double cv, \
+                                       double prandtl, double gam, double rgaz, double cs, double muref, double tref, double s_suth,      \
+                                       double k2, double k4, int im, int jm) {                                                            \
+    if (int rc = check_scheme(ORD, gh, jm, false)) return rc;                                                                             \
+    return residual_host(false, residu, w, nx, ny, vol, volf, gh, sargs(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4), im, \
+                         jm);                                                                                                             \
+  }                                                                                                                                       \
+  int bc_flux_num_dnc##ORD##_2d_d(double*, double* residud, const double* w, const double* wd, const double*, const double*,              \
+                                  const double* nx, const double* ny, const double*, const double*, const double* vol,                    \
+                                  const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,   \
+                                  double muref, double tref, double s_suth, double k2, double k4, int im, int jm) {                       \
+    if (int rc = check_scheme(ORD, gh, jm, true)) return rc;                                                                              \
+    return tangent_host(true, residud, w, wd, nx, ny, vol, volf, gh, sargs(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4),  \
+                        im, jm);                                                                                                          \
+  }                                                                                                                                       \
+  int bc_flux_num_dnc##ORD##_nowall_2d_d(double*, double* residud, const double* w, const double* wd, const double*, const double*,       \
+                                         const double* nx, const double* ny, const double*, const double*, const double* vol,             \
+                                         const double* volf, int gh, double cp, double cv, double prandtl, double gam, double rgaz,       \
+                                         double cs, double muref, double tref, double s_suth, double k2, double k4, int im, int jm) {     \
+    if (int rc = check_scheme(ORD, gh, jm, false)) return rc;                                                                             \
+    return tangent_host(false, residud, w, wd, nx, ny, vol, volf, gh, sargs(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4), \
+                        im, jm);                                                                                                          \
+  }
+BCAST_SCHEME_ENTRIES(3)
+BCAST_SCHEME_ENTRIES(7)
+BCAST_SCHEME_ENTRIES(9)
+#undef BCAST_SCHEME_ENTRIES
 
 // isothermal-wall variant of the scheme (flux_num_dnc5_iso.F90, tangent/flux_num_dnc5_iso_d.f90): the same kernels with the wall
 // flux of rhs/fluxwall_iso.F, selected through the calling thread's wall context for the duration of the call
@@ -427,6 +487,7 @@ int bc_flux_num_dnc5_iso_2d(double* residu, const double* w, double twall, const
                             const double* ny, const double*, const double*, const double* vol, const double* volf, int gh, double cp,
                             double cv, double prandtl, double gam, double rgaz, double cs, double muref, double tref, double s_suth,
                             double k2, double k4, int im, int jm) {
+  if (int rc = check_scheme(5, gh, jm, true)) return rc;
   WallIsoScope scope(twall);
   return residual_host(true, residu, w, nx, ny, vol, volf, gh, sargs(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4), im, jm);
 }
@@ -434,6 +495,7 @@ int bc_flux_num_dnc5_iso_2d_d(double*, double* residud, const double* w, const d
                               const double* nx, const double* ny, const double*, const double*, const double* vol, const double* volf,
                               int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs, double muref,
                               double tref, double s_suth, double k2, double k4, int im, int jm) {
+  if (int rc = check_scheme(5, gh, jm, true)) return rc;
   WallIsoScope scope(twall);
   return tangent_host(true, residud, w, wd, nx, ny, vol, volf, gh, sargs(cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4), im,
                       jm);

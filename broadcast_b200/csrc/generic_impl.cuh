@@ -3,6 +3,12 @@
 #include "kernels.cuh"
 #include <cstdlib>
 
+// scheme order of this translation unit (row f2 of SURVEY.md section 8): 5 unless the unit says otherwise.  The colour-loop helpers
+// and the spanwise operators below exist for order 5 only; the other orders get the residual / tangent pipeline.
+#ifndef BCAST_ORD
+#define BCAST_ORD 5
+#endif
+
 namespace bcast {
 
 // ---------------------------------------------------------------------------------------------
@@ -42,7 +48,7 @@ __global__ void k_prims(GridDesc g, SchemeConsts c, RectList rl /* storage (0-ba
 // ---------------------------------------------------------------------------------------------
 // gradients of velx, vely on interior cells (flux_num_dnc5.F90:124-137)
 // ---------------------------------------------------------------------------------------------
-template <int N>
+template <int N, int ORD>
 __global__ void k_grads(GridDesc g, FieldPtrs f, RectList rl /* interior cells, Fortran indices */, double* __restrict__ grad,
                         double* __restrict__ gradd) {
   const Rect rc = rl.r[blockIdx.z];
@@ -50,7 +56,7 @@ __global__ void k_grads(GridDesc g, FieldPtrs f, RectList rl /* interior cells, 
   const int j = blockIdx.y * blockDim.y + threadIdx.y + rc.j0;
   if (i > rc.i1 || j > rc.j1) return;
   GlobalAcc<N> a(f, g, i, j);
-  const auto r = cell_gradients<0, 0>(a);
+  const auto r = cell_gradients<0, 0, ORD>(a);
   const long long k = g.cidx(i, j);
   const decltype(r.u0) out[NGRAD] = {r.u0, r.u1, r.v0, r.v1};
 #pragma unroll
@@ -85,38 +91,26 @@ static __global__ void k_grad_ghost(GridDesc g, double* __restrict__ grad, int n
 // ---------------------------------------------------------------------------------------------
 // cell-centred balance (rhs/balance.F:2-15) of the four face fluxes of each cell
 // ---------------------------------------------------------------------------------------------
-template <int N, int DIR, class RD>
+template <int N, int DIR, class RD, int ORD = 5>
 __device__ __forceinline__ void face_dispatch(const FieldPtrs& f, const GridDesc& g, const SchemeConsts& c, bool wall, int i, int j,
                                               Var<RD> (&hn)[5]) {
   GlobalAcc<N> a(f, g, i, j);
-  if (DIR == 0) {
-    if (wall && j <= 2)
-      face_flux<0, true, FACE_MAIN>(a, c, hn);
-    else
-      face_flux<0, false, FACE_MAIN>(a, c, hn);
-  } else {
-    if (wall && j == 1)
-      face_flux<1, true, FACE_WALL>(a, c, hn);
-    else if (wall && j == 2)
-      face_flux<1, true, FACE_NEAR3>(a, c, hn);
-    else if (wall && j == 3)
-      face_flux<1, false, FACE_NEAR5>(a, c, hn);
-    else
-      face_flux<1, false, FACE_MAIN>(a, c, hn);
-  }
+  face_by_row<DIR, ORD>(a, c, wall, j, hn);
 }
 
-template <int N>
+// (ORD is part of the kernel's name: every order has its own translation unit, and two instantiations that differ only through a
+// macro would be ONE symbol to the linker)
+template <int N, int ORD>
 __global__ void __launch_bounds__(128) k_balance(GridDesc g, SchemeConsts c, FieldPtrs f, bool wall, Rect rc, double* __restrict__ out) {
   using DT = TanOf<N>;
   const int i = blockIdx.x * blockDim.x + threadIdx.x + rc.i0;
   const int j = blockIdx.y * blockDim.y + threadIdx.y + rc.j0;
   if (i > rc.i1 || j > rc.j1) return;
   Var<DT> a0[5], a1[5], b0[5], b1[5];
-  face_dispatch<N, 0>(f, g, c, wall, i, j, a0);
-  face_dispatch<N, 0>(f, g, c, wall, i + 1, j, a1);
-  face_dispatch<N, 1>(f, g, c, wall, i, j, b0);
-  face_dispatch<N, 1>(f, g, c, wall, i, j + 1, b1);
+  face_dispatch<N, 0, DT, ORD>(f, g, c, wall, i, j, a0);
+  face_dispatch<N, 0, DT, ORD>(f, g, c, wall, i + 1, j, a1);
+  face_dispatch<N, 1, DT, ORD>(f, g, c, wall, i, j, b0);
+  face_dispatch<N, 1, DT, ORD>(f, g, c, wall, i, j + 1, b1);
   const long long k = g.cidx(i, j);
 #pragma unroll
   for (int e = 0; e < 5; ++e) {
@@ -130,7 +124,7 @@ __global__ void __launch_bounds__(128) k_balance(GridDesc g, SchemeConsts c, Fie
   }
 }
 
-template <int N>
+template <int N, int ORD>
 cudaError_t residual_generic_t(const GridDesc& g, const SchemeArgs& a, bool wall, double* out, const double* w, const double* wd,
                                       const double* nx, const double* ny, const double* vol, const double* volf, const Rect* rect,
                                       cudaStream_t st) {
@@ -143,15 +137,17 @@ cudaError_t residual_generic_t(const GridDesc& g, const SchemeArgs& a, bool wall
   dim3 blk(32, 4);
   Rect rc = rect ? *rect : Rect{1, g.im, 1, g.jm};
   if (rc.i1 < rc.i0 || rc.j1 < rc.j0) return cudaSuccess;
-  // the balance of a cell reads gradients of its 4-neighbourhood (sensor) and primitives up to gh = 3
-  // cells away; a gradient reads primitives 2 cells away: restrict both passes to what `rect` needs
+  // the balance of a cell reads gradients of its 4-neighbourhood (sensor) and primitives up to the scheme's GH
+  // cells away; a gradient reads primitives NB cells away: restrict both passes to what `rect` needs
   const Rect rg{max(g.glo(), rc.i0 - 1), min(g.ghi(), rc.i1 + 1), max(1, rc.j0 - 1), min(g.jm, rc.j1 + 1)};
-  const Rect rp{max(0, rc.i0 - 5 + g.gh), min(g.ni() - 1, rc.i1 + 3 + g.gh), max(0, rc.j0 - 5 + g.gh), min(g.nj() - 1, rc.j1 + 3 + g.gh)};  // +-4 (wall row 1 reads row 5)
+  // order 5: +-4 (wall row 1 reads row 5); other orders: the off-centred wall rows read cell rows 1 .. NP
+  constexpr int PM = ORD == 5 ? 4 : (SchemeOrd<ORD>::NP > SchemeOrd<ORD>::GH + 1 ? SchemeOrd<ORD>::NP : SchemeOrd<ORD>::GH + 1);
+  const Rect rp{max(0, rc.i0 - 1 - PM + g.gh), min(g.ni() - 1, rc.i1 - 1 + PM + g.gh), max(0, rc.j0 - 1 - PM + g.gh), min(g.nj() - 1, rc.j1 - 1 + PM + g.gh)};
   dim3 gall((rp.i1 - rp.i0 + 32) / 32, (rp.j1 - rp.j0 + 4) / 4);
   k_prims<N><<<gall, blk, 0, st>>>(g, c, one_rect(rp), w, wd, prim, primd);
   FieldPtrs f{w, prim, grad, nx, ny, vol, volf, wd, primd, gradd};
   dim3 gint((rg.i1 - rg.i0 + 32) / 32, (rg.j1 - rg.j0 + 4) / 4);
-  k_grads<N><<<gint, blk, 0, st>>>(g, f, one_rect(rg), grad, gradd);
+  k_grads<N, ORD><<<gint, blk, 0, st>>>(g, f, one_rect(rg), grad, gradd);
   {
     const int nt = g.im + g.jm;
     k_grad_ghost<<<dim3((nt + 127) / 128, NGRAD), 128, 0, st>>>(g, grad, NGRAD);
@@ -159,7 +155,7 @@ cudaError_t residual_generic_t(const GridDesc& g, const SchemeArgs& a, bool wall
   }
   {
     dim3 gb((rc.i1 - rc.i0 + 32) / 32, (rc.j1 - rc.j0 + 4) / 4);
-    k_balance<N><<<gb, blk, 0, st>>>(g, c, f, wall, rc, out);
+    k_balance<N, ORD><<<gb, blk, 0, st>>>(g, c, f, wall, rc, out);
   }
   return cudaGetLastError();
 }
@@ -175,7 +171,7 @@ cudaError_t residual_generic_t(const GridDesc& g, const SchemeArgs& a, bool wall
 // matrix_dz2/function_dz2.F (their tangents: dz/function_5p_dz_d.f90:155-401, function_5p_dz2_d.f90).
 // WHICH = 1: d/dz rows (cell + 5-point cross), WHICH = 2: d2/dz2 rows (cell-local).
 // ---------------------------------------------------------------------------------------------
-#if BCAST_N > 0
+#if BCAST_N > 0 && BCAST_ORD == 5
 template <int N, int WHICH>
 __global__ void __launch_bounds__(128) k_dz(GridDesc g, SchemeConsts c, FieldPtrs f, Rect rc, double* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + rc.i0;
@@ -290,7 +286,7 @@ cudaError_t BCAST_CAT(dz_generic_, BCAST_N)(const GridDesc& g, const SchemeArgs&
 }
 #endif
 
-#if BCAST_N == 5
+#if BCAST_N == 5 && BCAST_ORD == 5
 // ---------------------------------------------------------------------------------------------
 // Tangent of the rows of up to four rectangles (the boundary strips of the Jacobian assembly) in ONE pass:
 // block = 32 cells x 4 faces, thread (x, z) evaluates ONE face flux of cell x in 5-direction tangent arithmetic
@@ -470,7 +466,7 @@ cudaError_t tangent_strips_5(const GridDesc& g, const SchemeArgs& a, bool wall, 
   dim3 blk(32, 4);
   for_each_rect(rp, st, [&](const RectList& r1, int, cudaStream_t s1) { k_prims<N><<<grid_of(r1, 32, 4), blk, 0, s1>>>(g, c, r1, w, wd5, prim, primd); });
   FieldPtrs f{w, prim, grad, nx, ny, vol, volf, wd5, primd, gradd};
-  for_each_rect(rg, st, [&](const RectList& r1, int, cudaStream_t s1) { k_grads<N><<<grid_of(r1, 32, 4), blk, 0, s1>>>(g, f, r1, grad, gradd); });
+  for_each_rect(rg, st, [&](const RectList& r1, int, cudaStream_t s1) { k_grads<N, 5><<<grid_of(r1, 32, 4), blk, 0, s1>>>(g, f, r1, grad, gradd); });
   const int nt = g.im + g.jm;
   k_grad_ghost<<<dim3((nt + 127) / 128, NGRAD), 128, 0, st>>>(g, grad, NGRAD);
   k_grad_ghost<<<dim3((nt + 127) / 128, NGRAD * N), 128, 0, st>>>(g, gradd, NGRAD * N);
@@ -503,7 +499,7 @@ cudaError_t tangent_strips_5(const GridDesc& g, const SchemeArgs& a, bool wall, 
 }
 #endif
 
-#if BCAST_N == 0
+#if BCAST_N == 0 && BCAST_ORD == 5
 // passive prims + gradients into the scratch arena, for kernels that read them (jac_interior.cu)
 cudaError_t prepare_prims_grads(const GridDesc& g, const SchemeArgs& a, const double* w, const double* nx, const double* ny,
                                 const double* vol, const double* volf, FieldPtrs& f, cudaStream_t st) {
@@ -516,16 +512,21 @@ cudaError_t prepare_prims_grads(const GridDesc& g, const SchemeArgs& a, const do
   k_prims<0><<<gall, blk, 0, st>>>(g, c, one_rect(Rect{0, g.ni() - 1, 0, g.nj() - 1}), w, nullptr, prim, nullptr);
   f = FieldPtrs{w, prim, grad, nx, ny, vol, volf, nullptr, nullptr, nullptr};
   dim3 gint((g.im + 2 + 31) / 32, (g.jm + 3) / 4);
-  k_grads<0><<<gint, blk, 0, st>>>(g, f, one_rect(Rect{g.glo(), g.ghi(), 1, g.jm}), grad, nullptr);
+  k_grads<0, 5><<<gint, blk, 0, st>>>(g, f, one_rect(Rect{g.glo(), g.ghi(), 1, g.jm}), grad, nullptr);
   k_grad_ghost<<<dim3((g.im + g.jm + 127) / 128, NGRAD), 128, 0, st>>>(g, grad, NGRAD);
   return cudaGetLastError();
 }
 #endif
 
-cudaError_t BCAST_CAT(residual_generic_, BCAST_N)(const GridDesc& g, const SchemeArgs& a, bool wall, double* out, const double* w,
-                                                 const double* wd, const double* nx, const double* ny, const double* vol,
-                                                 const double* volf, const Rect* rect, cudaStream_t st) {
-  return residual_generic_t<BCAST_N>(g, a, wall, out, w, wd, nx, ny, vol, volf, rect, st);
+#if BCAST_ORD == 5
+#define BCAST_RESIDUAL_GENERIC BCAST_CAT(residual_generic_, BCAST_N)
+#else
+#define BCAST_RESIDUAL_GENERIC BCAST_CAT(BCAST_CAT(BCAST_CAT(residual_generic_, BCAST_N), _o), BCAST_ORD)
+#endif
+cudaError_t BCAST_RESIDUAL_GENERIC(const GridDesc& g, const SchemeArgs& a, bool wall, double* out, const double* w, const double* wd,
+                                   const double* nx, const double* ny, const double* vol, const double* volf, const Rect* rect,
+                                   cudaStream_t st) {
+  return residual_generic_t<BCAST_N, BCAST_ORD>(g, a, wall, out, w, wd, nx, ny, vol, volf, rect, st);
 }
 
 }  // namespace bcast

@@ -1,0 +1,4 @@
+// order-7 member of the scheme family (flux_num_dnc7.F90), tangent width 5: see generic_impl.cuh
+#define BCAST_N 5
+#define BCAST_ORD 7
+#include "generic_impl.cuh"

@@ -150,7 +150,7 @@ using namespace bcast;
 
 extern "C" int bcd_apply_bcs(double* w, const double* nx, const double* ny, double gam, int gh, int im, int jm, const bc_desc_t* bcs,
                              int nbcs, void* stream) {
-  if (im < 1 || jm < 1 || gh != 3) return BC_ERR_ARG;
+  if (im < 1 || jm < 1 || gh < 2 || gh > 5) return BC_ERR_ARG;
   const GridDesc g = make_grid_ctx(im, jm, gh);
   cudaError_t e = apply_bc_list(g, gam, 0, w, nullptr, nx, ny, bcs, nbcs, (cudaStream_t)stream);
   return e == cudaSuccess ? BC_OK : (int)e;
@@ -161,7 +161,9 @@ extern "C" int bcd_jacobian_coo(double* jac, int32_t* ia, int32_t* ja, double* w
                                 double muref, double tref, double s_suth, double k2, double k4, int im, int jm, int wall,
                                 const bc_desc_t* bcs, int nbcs, int scatter_kind, const double* coefdiag, const int32_t* rect,
                                 int compact, void* stream) {
-  if (im < 1 || jm < 1 || gh != 3) return BC_ERR_ARG;
+  // gh = 2 / 4 / 5: the colour loop of the orders 3 / 7 / 9 ((2 gh + 1)^2 passes of five directions), tangent by the order-templated
+  // pipeline of generic_impl.cuh; the fused tile tangent and the face skipping below are order 5
+  if (im < 1 || jm < 1 || gh < 2 || gh > 5) return BC_ERR_ARG;
   if (scatter_kind < 0 || scatter_kind > 6) return BC_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const GridDesc g = make_grid_ctx(im, jm, gh);
@@ -199,7 +201,7 @@ extern "C" int bcd_jacobian_coo(double* jac, int32_t* ia, int32_t* ja, double* w
       // tangent of the rows of rc, five directions: one face per thread, every face once, faces without a tangent input skipped
       // (k_strip_faces5 over bands of three rows); BROADCAST_B200_COO_GENERIC=1: the cell-centred k_balance<5>
       static const bool coo_generic = getenv("BROADCAST_B200_COO_GENERIC") != nullptr;
-      if (coo_generic) e = launch_residual_generic(g, a, wall != 0, 5, resd5, w, wd5, nx, ny, vol, volf, &rc, st);
+      if (coo_generic || gh != 3) e = launch_residual_generic(g, a, wall != 0, 5, resd5, w, wd5, nx, ny, vol, volf, &rc, st);
       else e = launch_tangent_strips5(g, a, wall != 0, one_rect(rc), resd5, w, wd5, nx, ny, vol, volf, st);
       if (e != cudaSuccess) return (int)e;
       k_scatter5<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(g, scatter_kind, jac, ia, ja, resd5, l, k, coefdiag, vol, rc, (rect && compact) ? 1 : 0);

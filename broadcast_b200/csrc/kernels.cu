@@ -87,15 +87,31 @@ cudaError_t launch_tangent_strips5(const GridDesc& g, const SchemeArgs& a, bool 
   return tangent_strips_5(g, a, wall, rows, out5, w, wd5, nx, ny, vol, volf, st);
 }
 
+#define BCAST_DECL_GENERIC(NAME)                                                                                              \
+  cudaError_t NAME(const GridDesc&, const SchemeArgs&, bool, double*, const double*, const double*, const double*, const double*, \
+                   const double*, const double*, const Rect*, cudaStream_t);
+BCAST_DECL_GENERIC(residual_generic_0_o3) BCAST_DECL_GENERIC(residual_generic_1_o3) BCAST_DECL_GENERIC(residual_generic_5_o3)
+BCAST_DECL_GENERIC(residual_generic_0_o7) BCAST_DECL_GENERIC(residual_generic_1_o7) BCAST_DECL_GENERIC(residual_generic_5_o7)
+BCAST_DECL_GENERIC(residual_generic_0_o9) BCAST_DECL_GENERIC(residual_generic_1_o9) BCAST_DECL_GENERIC(residual_generic_5_o9)
+#undef BCAST_DECL_GENERIC
+
+// The scheme order follows the ghost depth of the block, as in the reference's drivers (BROADCAST_npz.py:501-502: gh = (order + 1) / 2
+// for the dnc family): gh = 2 / 3 / 4 / 5 = flux_num_dnc3 / 5 / 7 / 9.
 cudaError_t launch_residual_generic(const GridDesc& g, const SchemeArgs& a, bool wall, int ndir, double* out, const double* w,
                                     const double* wd, const double* nx, const double* ny, const double* vol, const double* volf,
                                     const Rect* rect, cudaStream_t st) {
-  switch (ndir) {
-    case 0: return residual_generic_0(g, a, wall, out, w, nullptr, nx, ny, vol, volf, rect, st);
-    case 1: return residual_generic_1(g, a, wall, out, w, wd, nx, ny, vol, volf, rect, st);
-    case 5: return residual_generic_5(g, a, wall, out, w, wd, nx, ny, vol, volf, rect, st);
+  if (ndir != 0 && ndir != 1 && ndir != 5) return cudaErrorInvalidValue;
+  const double* wdn = ndir ? wd : nullptr;
+#define BCAST_CALL(F0, F1, F5) \
+  return ndir == 0 ? F0(g, a, wall, out, w, nullptr, nx, ny, vol, volf, rect, st) : ndir == 1 ? F1(g, a, wall, out, w, wdn, nx, ny, vol, volf, rect, st) : F5(g, a, wall, out, w, wdn, nx, ny, vol, volf, rect, st)
+  switch (g.gh) {
+    case 2: BCAST_CALL(residual_generic_0_o3, residual_generic_1_o3, residual_generic_5_o3);
+    case 3: BCAST_CALL(residual_generic_0, residual_generic_1, residual_generic_5);
+    case 4: BCAST_CALL(residual_generic_0_o7, residual_generic_1_o7, residual_generic_5_o7);
+    case 5: BCAST_CALL(residual_generic_0_o9, residual_generic_1_o9, residual_generic_5_o9);
     default: return cudaErrorInvalidValue;
   }
+#undef BCAST_CALL
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -16,6 +16,7 @@
 #pragma once
 #include "dual.cuh"
 #include "grid.cuh"
+#include <utility>
 
 namespace bcast {
 
@@ -68,6 +69,131 @@ struct Off {
 #define AT(S, T) Off<DIR, (S), (T)>::i, Off<DIR, (S), (T)>::j
 
 // ---------------------------------------------------------------------------------------------
+// The scheme family (row f2 of SURVEY.md section 8): orders 3 / 5 / 7 / 9 share every fragment except the stencil tables.
+//   c(k)   centred Euler flux, pair k = cells (k, -k-1)            euler_o4 / o6 / o8 / o10_{i,j}.F
+//   d(k)   predictor (the (ORD+2)-point difference), alternating   predictor_5p / 7p / 9p / 11p_{i,j}.F
+//   b(k)   cell-centred gradient of the sensor velocities          gradop_3p / 5p / 7p / 9p{i,j}.F
+//   near(row, r)  off-centred Euler flux of the j-face `row` (2 .. GH) over the cell rows r = 1 .. NP next to a wall
+//                 nearbndfluxes{3,5,7,9}demi_{5,7,9,11}p.F with coefnearbnd_{7,9,11}p.F (order 3: flux_num_dnc3.F90:171-172)
+// Every value is formed by the same floating-point operations as the reference's coefficient statements
+// (flux_num_dnc3.F90:105-124, flux_num_dnc5.F90:90-106, flux_num_dnc7.F90:94-126, flux_num_dnc9.F90:100-129).
+// ---------------------------------------------------------------------------------------------
+template <int ORD>
+struct SchemeOrd;
+
+template <>
+struct SchemeOrd<3> {
+  static constexpr int GH = 2, NB = 1, NP = 2;
+  static constexpr bool VISC_O4 = false;   // flux_visqueux_o2 on every face (flux_num_dnc3.F90:160)
+  static BC_HD constexpr double c(int k) { return k == 0 ? 7.0 * (1.0 / 12.0) : -(1.0 / 12.0); }
+  static BC_HD constexpr double d(int k) { return k == 0 ? 3.0 * (1.0 / 12.0) : (1.0 / 12.0); }
+  static BC_HD constexpr double b(int) { return 0.5; }
+  static BC_HD constexpr double near(int, int) { return 0.5; }
+};
+
+template <>
+struct SchemeOrd<5> {
+  static constexpr int GH = 3, NB = 2, NP = 5;
+  static constexpr bool VISC_O4 = true;
+  static BC_HD constexpr double c(int k) { return k == 0 ? 37.0 * (1.0 / 60.0) : k == 1 ? -8.0 * (1.0 / 60.0) : (1.0 / 60.0); }
+  static BC_HD constexpr double d(int k) { return k == 0 ? 10.0 * (1.0 / 60.0) : k == 1 ? 5.0 * (1.0 / 60.0) : (1.0 / 60.0); }
+  static BC_HD constexpr double b(int k) { return k == 0 ? 8.0 * (1.0 / 12.0) : -(1.0 / 12.0); }
+  static BC_HD constexpr double near(int row, int r) {
+    constexpr double denom = 1.0 / 60.0;
+    constexpr double t3[5] = {-3.0, 27.0, 47.0, -13.0, 2.0}, t2[5] = {12.0, 77.0, -43.0, 17.0, -3.0};
+    return (row == 3 ? t3[r - 1] : t2[r - 1]) * denom;
+  }
+};
+
+template <>
+struct SchemeOrd<7> {
+  static constexpr int GH = 4, NB = 3, NP = 9;
+  static constexpr bool VISC_O4 = true;
+  static BC_HD constexpr double c(int k) {
+    constexpr double denom = 1.0 / 840.0;
+    return k == 0 ? 533.0 * denom : k == 1 ? -139.0 * denom : k == 2 ? 29.0 * denom : -3.0 * denom;
+  }
+  static BC_HD constexpr double d(int k) {
+    constexpr double denom = 1.0 / 280.0;
+    return k == 0 ? 35.0 * denom : k == 1 ? 21.0 * denom : k == 2 ? 7.0 * denom : 1.0 * denom;
+  }
+  static BC_HD constexpr double b(int k) {
+    constexpr double denom = 1.0 / 60.0;
+    return k == 0 ? 45.0 * denom : k == 1 ? -9.0 * denom : denom;
+  }
+  static BC_HD constexpr double near(int row, int r) {   // coefnearbnd_9p.F
+    constexpr double denom = 1.0 / 840.0;
+    constexpr double t4[9] = {2.0, -31.0, 281.0, 911.0, -517.0, 281.0, -111.0, 27.0, -3.0};
+    constexpr double t3[9] = {-13.0, 209.0, 1079.0, -769.0, 533.0, -279.0, 99.0, -21.0, 2.0};
+    constexpr double t2[9] = {92.0, 1547.0, -1861.0, 2171.0, -1917.0, 1191.0, -489.0, 119.0, -13.0};
+    return (row == 4 ? t4[r - 1] : row == 3 ? t3[r - 1] : t2[r - 1]) * denom;
+  }
+};
+
+template <>
+struct SchemeOrd<9> {
+  static constexpr int GH = 5, NB = 4, NP = 11;
+  static constexpr bool VISC_O4 = true;
+  static BC_HD constexpr double c(int k) {
+    constexpr double denom = 1.0 / 2520.0;
+    return k == 0 ? 1627.0 * denom : k == 1 ? -473.0 * denom : k == 2 ? 127.0 * denom : k == 3 ? -23.0 * denom : 2.0 * denom;
+  }
+  static BC_HD constexpr double d(int k) {
+    constexpr double denom = 1.0 / 1260.0;
+    return k == 0 ? 126.0 * denom : k == 1 ? 84.0 * denom : k == 2 ? 36.0 * denom : k == 3 ? 9.0 * denom : denom;
+  }
+  static BC_HD constexpr double b(int k) {
+    constexpr double denom = 1.0 / 840.0;
+    return k == 0 ? 672.0 * denom : k == 1 ? -168.0 * denom : k == 2 ? 32.0 * denom : -3.0 * denom;
+  }
+  // coefnearbnd_11p.F: the face coefficients are built at run time by successive subtraction of the difference weights a0 .. a10
+  // from the centred flux of face 11/2; the same chain of subtractions here (compile time, IEEE double)
+  static BC_HD constexpr double a9(int r) {
+    constexpr double a[11] = {1.0 / 840.0, -1.0 / 63.0, 3.0 / 28.0, -4.0 / 7.0, -11.0 / 30.0, 6.0 / 5.0, -0.5, 4.0 / 21.0, -3.0 / 56.0,
+                              1.0 / 105.0, -1.0 / 1260.0};
+    return a[r];
+  }
+  static BC_HD constexpr double a7(int r) {
+    constexpr double a[11] = {-1.0 / 360.0, 1.0 / 24.0, -3.0 / 8.0, -319.0 / 420.0, 1.75, -21.0 / 20.0, 7.0 / 12.0, -0.25, 0.075,
+                              -1.0 / 72.0, 1.0 / 840.0};
+    return a[r];
+  }
+  static BC_HD constexpr double a5(int r) {
+    constexpr double a[11] = {1.0 / 90.0, -2.0 / 9.0, -341.0 / 280.0, 8.0 / 3.0, -7.0 / 3.0, 28.0 / 15.0, -7.0 / 6.0, 8.0 / 15.0, -1.0 / 6.0,
+                              2.0 / 63.0, -1.0 / 360.0};
+    return a[r];
+  }
+  static BC_HD constexpr double a3(int r) {
+    constexpr double a[11] = {-0.1, -4609.0 / 2520.0, 4.5, -6.0, 7.0, -6.3, 21.0 * 0.2, -2.0, 9.0 / 14.0, -0.125, 1.0 / 90.0};
+    return a[r];
+  }
+  static BC_HD constexpr double c9(int r) { return r == 10 ? -a9(10) : c(r <= 4 ? 4 - r : r - 5) - a9(r); }
+  static BC_HD constexpr double near(int row, int r) {
+    const int q = r - 1;
+    double v = c9(q);
+    if (row <= 4) v = v - a7(q);
+    if (row <= 3) v = v - a5(q);
+    if (row <= 2) v = v - a3(q);
+    return v;
+  }
+};
+
+// left-to-right sums over compile-time index packs (the reference's statements add their terms in source order)
+template <int... K>
+using ISeq = std::integer_sequence<int, K...>;
+template <int N>
+using MakeISeq = std::make_integer_sequence<int, N>;
+template <int ORD, int K> struct EulerC { static constexpr double v = SchemeOrd<ORD>::c(K); };
+template <int ORD, int K> struct GradC { static constexpr double v = SchemeOrd<ORD>::b(K); };
+template <int ORD, int ROW, int R> struct NearC { static constexpr double v = SchemeOrd<ORD>::near(ROW, R); };
+// predictor weight of the cell at offset O from the face cell: ... + d2 w(-2) - d1 w(-1) + d1 w(0) - d2 w(1) + ...
+template <int ORD, int O> struct PredC {
+  static constexpr int k = O < 0 ? -O : O + 1;
+  static constexpr double sgn = ((k & 1) != 0) == (O >= 0) ? 1.0 : -1.0;
+  static constexpr double v = sgn * SchemeOrd<ORD>::d(k - 1);
+};
+
+// ---------------------------------------------------------------------------------------------
 // cell-local primitives (phys/Primitives.F:2-34, phys/viscosity.F:1)
 // ---------------------------------------------------------------------------------------------
 template <class D>
@@ -101,14 +227,23 @@ struct Grad4 {
   Var<D> u0, u1, v0, v1;  // gradu(.,1), gradu(.,2), gradv(.,1), gradv(.,2)
 };
 
-template <int CI, int CJ, class A>
+// centred differences of the sensor velocities over 2 NB + 1 points (gradop_{3,5,7,9}p{i,j}.F), terms in source order
+template <int ORD, int CI, int CJ, class A, int... K>
+BC_HD auto grad_diff_ui(const A& a, ISeq<K...>) { return (... + (GradC<ORD, K>::v * (a.template U<CI + K + 1, CJ>() - a.template U<CI - K - 1, CJ>()))); }
+template <int ORD, int CI, int CJ, class A, int... K>
+BC_HD auto grad_diff_vi(const A& a, ISeq<K...>) { return (... + (GradC<ORD, K>::v * (a.template V<CI + K + 1, CJ>() - a.template V<CI - K - 1, CJ>()))); }
+template <int ORD, int CI, int CJ, class A, int... K>
+BC_HD auto grad_diff_uj(const A& a, ISeq<K...>) { return (... + (GradC<ORD, K>::v * (a.template U<CI, CJ + K + 1>() - a.template U<CI, CJ - K - 1>()))); }
+template <int ORD, int CI, int CJ, class A, int... K>
+BC_HD auto grad_diff_vj(const A& a, ISeq<K...>) { return (... + (GradC<ORD, K>::v * (a.template V<CI, CJ + K + 1>() - a.template V<CI, CJ - K - 1>()))); }
+
+template <int CI, int CJ, int ORD = 5, class A>
 BC_HD auto cell_gradients(const A& a) {
-  constexpr double b1 = 8.0 * (1.0 / 12.0);
-  constexpr double b2 = -(1.0 / 12.0);
-  auto gui = b1 * (a.template U<CI + 1, CJ>() - a.template U<CI - 1, CJ>()) + b2 * (a.template U<CI + 2, CJ>() - a.template U<CI - 2, CJ>());
-  auto gvi = b1 * (a.template V<CI + 1, CJ>() - a.template V<CI - 1, CJ>()) + b2 * (a.template V<CI + 2, CJ>() - a.template V<CI - 2, CJ>());
-  auto guj = b1 * (a.template U<CI, CJ + 1>() - a.template U<CI, CJ - 1>()) + b2 * (a.template U<CI, CJ + 2>() - a.template U<CI, CJ - 2>());
-  auto gvj = b1 * (a.template V<CI, CJ + 1>() - a.template V<CI, CJ - 1>()) + b2 * (a.template V<CI, CJ + 2>() - a.template V<CI, CJ - 2>());
+  using NBS = MakeISeq<SchemeOrd<ORD>::NB>;
+  auto gui = grad_diff_ui<ORD, CI, CJ>(a, NBS{});
+  auto gvi = grad_diff_vi<ORD, CI, CJ>(a, NBS{});
+  auto guj = grad_diff_uj<ORD, CI, CJ>(a, NBS{});
+  auto gvj = grad_diff_vj<ORD, CI, CJ>(a, NBS{});
   const double volm1 = 1.0 / a.template VOL<CI, CJ>();
   const double dxm1 = 0.5 * (a.template NX<CI, CJ>(0) + a.template NX<CI + 1, CJ>(0)) * volm1;
   const double dxm2 = 0.5 * (a.template NX<CI, CJ>(1) + a.template NX<CI, CJ + 1>(1)) * volm1;
@@ -339,7 +474,28 @@ enum FaceMode { FACE_MAIN = 0, FACE_NEAR5 = 1, FACE_NEAR3 = 2, FACE_WALL = 3 };
 //             FACE_WALL  wall flux (j-face at j = 1)             -- DIR must be 1 for the last three
 // Result type RD is the accessor's widest tangent type.
 // ---------------------------------------------------------------------------------------------
-template <int DIR, bool VISC_O2, int MODE, class A, class RD>
+// centred Euler flux of component e over the 2 GH cells along the face normal (euler_o{4,6,8,10}_{i,j}.F)
+template <int DIR, int ORD, class A, int... K>
+BC_HD auto euler_centred(const A& a, int e, double nxf, double nyf, ISeq<K...>) {
+  return (... + (EulerC<ORD, K>::v * (flux_f<AT(K, 0)>(a, e) + flux_f<AT(-K - 1, 0)>(a, e)))) * nxf +
+         (... + (EulerC<ORD, K>::v * (flux_g<AT(K, 0)>(a, e) + flux_g<AT(-K - 1, 0)>(a, e)))) * nyf;
+}
+// off-centred Euler flux of the j-face ROW next to a wall: cell rows 1 .. NP = offsets 1 - ROW .. NP - ROW from the face cell
+template <int DIR, int ORD, int ROW, class A, int... R>
+BC_HD auto euler_near_wall(const A& a, int e, double nxf, double nyf, ISeq<R...>) {
+  return (... + (NearC<ORD, ROW, R + 1>::v * flux_f<AT(R + 1 - ROW, 0)>(a, e))) * nxf +
+         (... + (NearC<ORD, ROW, R + 1>::v * flux_g<AT(R + 1 - ROW, 0)>(a, e))) * nyf;
+}
+// predictor_{5,7,9,11}p_{i,j}.F over the offsets -GH .. GH - 1
+template <int DIR, int ORD, class A, int... Q>
+BC_HD auto predictor_diff(const A& a, int e, ISeq<Q...>) {
+  return (... + (PredC<ORD, Q - SchemeOrd<ORD>::GH>::v * a.template W<AT(Q - SchemeOrd<ORD>::GH, 0)>(e)));
+}
+
+// j-face rows 2 .. GH of a wall block for orders other than 5: MODE = FACE_NEAR_ROW + row
+constexpr int FACE_NEAR_ROW = 10;
+
+template <int DIR, bool VISC_O2, int MODE, int ORD = 5, class A, class RD>
 BC_HD void face_flux(const A& a, const SchemeConsts& c, Var<RD> (&hn)[5]) {
   const double nxf = a.template NX<0, 0>(DIR);
   const double nyf = a.template NY<0, 0>(DIR);
@@ -379,10 +535,6 @@ BC_HD void face_flux(const A& a, const SchemeConsts& c, Var<RD> (&hn)[5]) {
     }
     return;
   } else {
-    constexpr double denom = 1.0 / 60.0;
-    constexpr double c1 = 37.0 * denom, c2 = -8.0 * denom, c3 = denom;
-    constexpr double d1 = 10.0 * denom, d2 = 5.0 * denom, d3 = denom;
-
     // ---- viscous face gradients, stresses --------------------------------------------------------
     const DualNormals dn = dual_normals<DIR>(a);
     const auto vsc = visc_scalars<DIR, VISC_O2>(a, dn);
@@ -414,28 +566,16 @@ BC_HD void face_flux(const A& a, const SchemeConsts& c, Var<RD> (&hn)[5]) {
       // Euler flux
       auto euler = [&]() {
         if constexpr (MODE == FACE_MAIN) {
-          // euler_o6_{i,j}.F
-          return (c1 * (flux_f<AT(0, 0)>(a, e) + flux_f<AT(-1, 0)>(a, e)) + c2 * (flux_f<AT(1, 0)>(a, e) + flux_f<AT(-2, 0)>(a, e)) +
-                  c3 * (flux_f<AT(2, 0)>(a, e) + flux_f<AT(-3, 0)>(a, e))) * nxf +
-                 (c1 * (flux_g<AT(0, 0)>(a, e) + flux_g<AT(-1, 0)>(a, e)) + c2 * (flux_g<AT(1, 0)>(a, e) + flux_g<AT(-2, 0)>(a, e)) +
-                  c3 * (flux_g<AT(2, 0)>(a, e) + flux_g<AT(-3, 0)>(a, e))) * nyf;
+          return euler_centred<DIR, ORD>(a, e, nxf, nyf, MakeISeq<SchemeOrd<ORD>::GH>{});
         } else {
-          // nearbndfluxes5demi_7p.F (face j = 3: rows 1..5 = offsets -2..2) / nearbndfluxes3demi_7p.F
-          // (face j = 2: rows 1..5 = offsets -1..3); coefficients coefnearbnd_7p.F
-          constexpr bool five = (MODE == FACE_NEAR5);
-          constexpr double k0 = (five ? -3.0 : 12.0) * denom, k1 = (five ? 27.0 : 77.0) * denom, k2_ = (five ? 47.0 : -43.0) * denom,
-                           k3 = (five ? -13.0 : 17.0) * denom, k4_ = (five ? 2.0 : -3.0) * denom;
-          constexpr int o = five ? -2 : -1;
-          return (k0 * flux_f<AT(o, 0)>(a, e) + k1 * flux_f<AT(o + 1, 0)>(a, e) + k2_ * flux_f<AT(o + 2, 0)>(a, e) +
-                  k3 * flux_f<AT(o + 3, 0)>(a, e) + k4_ * flux_f<AT(o + 4, 0)>(a, e)) * nxf +
-                 (k0 * flux_g<AT(o, 0)>(a, e) + k1 * flux_g<AT(o + 1, 0)>(a, e) + k2_ * flux_g<AT(o + 2, 0)>(a, e) +
-                  k3 * flux_g<AT(o + 3, 0)>(a, e) + k4_ * flux_g<AT(o + 4, 0)>(a, e)) * nyf;
+          // FACE_NEAR5 / FACE_NEAR3: rows 3 / 2 of the order-5 scheme (nearbndfluxes5demi_7p.F, nearbndfluxes3demi_7p.F)
+          constexpr int row = MODE == FACE_NEAR5 ? 3 : MODE == FACE_NEAR3 ? 2 : MODE - FACE_NEAR_ROW;
+          return euler_near_wall<DIR, ORD, row>(a, e, nxf, nyf, MakeISeq<SchemeOrd<ORD>::NP>{});
         }
       };
       auto fx = euler();
       // predictor_7p_{i,j}.F
-      auto pred = -d3 * a.template W<AT(-3, 0)>(e) + d2 * a.template W<AT(-2, 0)>(e) - d1 * a.template W<AT(-1, 0)>(e) +
-                  d1 * a.template W<AT(0, 0)>(e) - d2 * a.template W<AT(1, 0)>(e) + d3 * a.template W<AT(2, 0)>(e);
+      auto pred = predictor_diff<DIR, ORD>(a, e, MakeISeq<2 * SchemeOrd<ORD>::GH>{});
       auto diff = 0.5 * (a.template W<AT(0, 0)>(e) - a.template W<AT(-1, 0)>(e));
       auto diss = rspec * (eps2 * diff + eps4 * pred);
       if (e == 0)
@@ -443,6 +583,42 @@ BC_HD void face_flux(const A& a, const SchemeConsts& c, Var<RD> (&hn)[5]) {
       else
         hn[e] = promote<RD>(fx - diss - (vs.f[e] * nxloc + vs.g[e] * nyloc) * sn);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Which face formula the reference's driver applies on row j of a block (flux_num_dnc{3,5,7,9}.F90: main loop from j = GH + 1,
+// off-centred Euler j-fluxes on rows GH .. 2, wall flux on row 1; 2nd-order viscous gradients on rows <= 2 and everywhere for
+// order 3).  `wall` false = the _nowall variants (main loop from j = 1).
+// ---------------------------------------------------------------------------------------------
+template <int DIR, int ORD, int ROW, class A, class RD>
+BC_HD void face_near_rows(const A& a, const SchemeConsts& c, int j, Var<RD> (&hn)[5]) {
+  if constexpr (ROW >= 3) {
+    if (j == ROW) {
+      face_flux<1, !SchemeOrd<ORD>::VISC_O4, FACE_NEAR_ROW + ROW, ORD>(a, c, hn);
+      return;
+    }
+    face_near_rows<DIR, ORD, ROW - 1>(a, c, j, hn);
+  } else {
+    face_flux<1, true, FACE_NEAR_ROW + 2, ORD>(a, c, hn);   // row 2
+  }
+}
+
+template <int DIR, int ORD, class A, class RD>
+BC_HD void face_by_row(const A& a, const SchemeConsts& c, bool wall, int j, Var<RD> (&hn)[5]) {
+  constexpr bool o2 = !SchemeOrd<ORD>::VISC_O4;
+  if constexpr (DIR == 0) {
+    if (o2 || (wall && j <= 2))
+      face_flux<0, true, FACE_MAIN, ORD>(a, c, hn);
+    else
+      face_flux<0, false, FACE_MAIN, ORD>(a, c, hn);
+  } else {
+    if (wall && j == 1)
+      face_flux<1, true, FACE_WALL, ORD>(a, c, hn);
+    else if (wall && j <= SchemeOrd<ORD>::GH)
+      face_near_rows<1, ORD, SchemeOrd<ORD>::GH>(a, c, j, hn);
+    else
+      face_flux<1, o2, FACE_MAIN, ORD>(a, c, hn);
   }
 }
 

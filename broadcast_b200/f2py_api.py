@@ -121,6 +121,8 @@ def build(backend):
         flux_num_dnc5_2d=_scheme("flux_num_dnc5_2d"),
         flux_num_dnc5_nowall_2d=_scheme("flux_num_dnc5_nowall_2d"),
         flux_num_dnc5_iso_2d=flux_num_dnc5_iso_2d,
+        # the other orders of the scheme family (srcfv/rhs/flux_num_dnc{3,7,9}.F90 and their _nowall variants); gh = (order + 1) / 2
+        **{f"flux_num_dnc{o}{v}_2d": _scheme(f"flux_num_dnc{o}{v}_2d") for o in (3, 7, 9) for v in ("", "_nowall")},
     )
 
     # ------------------------------------------------------------------ f_bnd (primal boundary fills)
@@ -299,6 +301,8 @@ def build(backend):
         flux_num_dnc5_2d_d=_scheme_d("flux_num_dnc5_2d_d"),
         flux_num_dnc5_nowall_2d_d=_scheme_d("flux_num_dnc5_nowall_2d_d"),
         flux_num_dnc5_iso_2d_d=flux_num_dnc5_iso_2d_d,
+        # srcfv/tangent/flux_num_dnc{3,7,9}_d.f90, flux_num_dnc{3,7,9}_nowall_d.f90
+        **{f"flux_num_dnc{o}{v}_2d_d": _scheme_d(f"flux_num_dnc{o}{v}_2d_d") for o in (3, 7, 9) for v in ("", "_nowall")},
         bc_wall_viscous_adia_2d_d=bc_wall_viscous_adia_2d_d, bc_no_reflexion_2d_d=bc_no_reflexion_2d_d,
         bc_wall_viscous_iso_2d_d=bc_wall_viscous_iso_2d_d, bc_symmetry_2d_d=bc_symmetry_2d_d,
         bc_antisymmetry_2d_d=bc_antisymmetry_2d_d, bc_pressure_2d_d=bc_pressure_2d_d,

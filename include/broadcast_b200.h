@@ -68,6 +68,74 @@ int bc_flux_num_dnc5_nowall_2d_d(double* residu, double* residud, const double* 
                                  double prandtl, double gam, double rgaz, double cs, double muref, double tref,
                                  double s_suth, double k2, double k4, int im, int jm);
 
+/* ---- the other members of the scheme family: orders 3 / 7 / 9, gh = (order + 1) / 2 = 2 / 4 / 5
+ *      (BROADCAST_npz.py:501-502).  Same argument lists and conventions as the order-5 routines above; a routine called with a
+ *      ghost depth other than its own returns BC_ERR_UNSUPPORTED.  The resident entry points (bcd_residual, bcd_tangent,
+ *      bcd_jacobian_coo, the boundary fills, seeds, scatters, norms) select the member from gh. */
+/* order 3: srcfv/rhs/flux_num_dnc3.F90:7-219 (f_sch.flux_num_dnc3_2d), srcfv/rhs/flux_num_dnc3_nowall.F90 (f_sch.flux_num_dnc3_nowall_2d),
+ *      srcfv/tangent/flux_num_dnc3_d.f90 and flux_num_dnc3_nowall_d.f90 (f_lin): euler_o4 / predictor_5p / gradop_3p, 2nd-order viscous gradients on every face, wall rows 2 and 1 */
+int bc_flux_num_dnc3_2d(double* residu, const double* w, const double* x0, const double* y0, const double* nx,
+                        const double* ny, const double* xc, const double* yc, const double* vol, const double* volf,
+                        int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
+                        double muref, double tref, double s_suth, double k2, double k4, int im, int jm);
+int bc_flux_num_dnc3_nowall_2d(double* residu, const double* w, const double* x0, const double* y0, const double* nx,
+                               const double* ny, const double* xc, const double* yc, const double* vol,
+                               const double* volf, int gh, double cp, double cv, double prandtl, double gam,
+                               double rgaz, double cs, double muref, double tref, double s_suth, double k2, double k4,
+                               int im, int jm);
+int bc_flux_num_dnc3_2d_d(double* residu, double* residud, const double* w, const double* wd, const double* x0,
+                          const double* y0, const double* nx, const double* ny, const double* xc, const double* yc,
+                          const double* vol, const double* volf, int gh, double cp, double cv, double prandtl,
+                          double gam, double rgaz, double cs, double muref, double tref, double s_suth, double k2,
+                          double k4, int im, int jm);
+int bc_flux_num_dnc3_nowall_2d_d(double* residu, double* residud, const double* w, const double* wd, const double* x0,
+                                 const double* y0, const double* nx, const double* ny, const double* xc,
+                                 const double* yc, const double* vol, const double* volf, int gh, double cp, double cv,
+                                 double prandtl, double gam, double rgaz, double cs, double muref, double tref,
+                                 double s_suth, double k2, double k4, int im, int jm);
+/* order 7: srcfv/rhs/flux_num_dnc7.F90:7-238 (f_sch.flux_num_dnc7_2d), srcfv/rhs/flux_num_dnc7_nowall.F90 (f_sch.flux_num_dnc7_nowall_2d),
+ *      srcfv/tangent/flux_num_dnc7_d.f90 and flux_num_dnc7_nowall_d.f90 (f_lin): euler_o8 / predictor_9p / gradop_7p, off-centred wall rows 4, 3, 2 (coefnearbnd_9p.F) */
+int bc_flux_num_dnc7_2d(double* residu, const double* w, const double* x0, const double* y0, const double* nx,
+                        const double* ny, const double* xc, const double* yc, const double* vol, const double* volf,
+                        int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
+                        double muref, double tref, double s_suth, double k2, double k4, int im, int jm);
+int bc_flux_num_dnc7_nowall_2d(double* residu, const double* w, const double* x0, const double* y0, const double* nx,
+                               const double* ny, const double* xc, const double* yc, const double* vol,
+                               const double* volf, int gh, double cp, double cv, double prandtl, double gam,
+                               double rgaz, double cs, double muref, double tref, double s_suth, double k2, double k4,
+                               int im, int jm);
+int bc_flux_num_dnc7_2d_d(double* residu, double* residud, const double* w, const double* wd, const double* x0,
+                          const double* y0, const double* nx, const double* ny, const double* xc, const double* yc,
+                          const double* vol, const double* volf, int gh, double cp, double cv, double prandtl,
+                          double gam, double rgaz, double cs, double muref, double tref, double s_suth, double k2,
+                          double k4, int im, int jm);
+int bc_flux_num_dnc7_nowall_2d_d(double* residu, double* residud, const double* w, const double* wd, const double* x0,
+                                 const double* y0, const double* nx, const double* ny, const double* xc,
+                                 const double* yc, const double* vol, const double* volf, int gh, double cp, double cv,
+                                 double prandtl, double gam, double rgaz, double cs, double muref, double tref,
+                                 double s_suth, double k2, double k4, int im, int jm);
+/* order 9: srcfv/rhs/flux_num_dnc9.F90:7-251 (f_sch.flux_num_dnc9_2d), srcfv/rhs/flux_num_dnc9_nowall.F90 (f_sch.flux_num_dnc9_nowall_2d),
+ *      srcfv/tangent/flux_num_dnc9_d.f90 and flux_num_dnc9_nowall_d.f90 (f_lin): euler_o10 / predictor_11p / gradop_9p, off-centred wall rows 5 .. 2 (coefnearbnd_11p.F) */
+int bc_flux_num_dnc9_2d(double* residu, const double* w, const double* x0, const double* y0, const double* nx,
+                        const double* ny, const double* xc, const double* yc, const double* vol, const double* volf,
+                        int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs,
+                        double muref, double tref, double s_suth, double k2, double k4, int im, int jm);
+int bc_flux_num_dnc9_nowall_2d(double* residu, const double* w, const double* x0, const double* y0, const double* nx,
+                               const double* ny, const double* xc, const double* yc, const double* vol,
+                               const double* volf, int gh, double cp, double cv, double prandtl, double gam,
+                               double rgaz, double cs, double muref, double tref, double s_suth, double k2, double k4,
+                               int im, int jm);
+int bc_flux_num_dnc9_2d_d(double* residu, double* residud, const double* w, const double* wd, const double* x0,
+                          const double* y0, const double* nx, const double* ny, const double* xc, const double* yc,
+                          const double* vol, const double* volf, int gh, double cp, double cv, double prandtl,
+                          double gam, double rgaz, double cs, double muref, double tref, double s_suth, double k2,
+                          double k4, int im, int jm);
+int bc_flux_num_dnc9_nowall_2d_d(double* residu, double* residud, const double* w, const double* wd, const double* x0,
+                                 const double* y0, const double* nx, const double* ny, const double* xc,
+                                 const double* yc, const double* vol, const double* volf, int gh, double cp, double cv,
+                                 double prandtl, double gam, double rgaz, double cs, double muref, double tref,
+                                 double s_suth, double k2, double k4, int im, int jm);
+
 /* ---- isothermal-wall variant of the scheme (`_iso`): srcfv/rhs/flux_num_dnc5_iso.F90:7-227 =
  *      flux_num_dnc5_2d with rhs/fluxwall_iso.F (heat flux lambda (T - twall) n / vol_face through the wall face, lambda as the
  *      i-face viscous fragment left it: flux_visqueux_o2_i.F:61) and its tangent srcfv/tangent/flux_num_dnc5_iso_d.f90:15-3877

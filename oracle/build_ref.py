@@ -32,6 +32,19 @@ FILES = [
     ("srcfv/tangent/flux_num_dnc5_nowall_d.f90", None),
     ("srcfv/prepro/flux_num_dnc5_iso.f90", None),
     ("srcfv/tangent/flux_num_dnc5_iso_d.f90", None),
+    # row f2 of SURVEY.md section 8: the other orders of the scheme family (3 / 7 / 9) and their Tapenade tangents
+    ("srcfv/prepro/flux_num_dnc3.f90", None),
+    ("srcfv/prepro/flux_num_dnc3_nowall.f90", None),
+    ("srcfv/tangent/flux_num_dnc3_d.f90", None),
+    ("srcfv/tangent/flux_num_dnc3_nowall_d.f90", None),
+    ("srcfv/prepro/flux_num_dnc7.f90", None),
+    ("srcfv/prepro/flux_num_dnc7_nowall.f90", None),
+    ("srcfv/tangent/flux_num_dnc7_d.f90", None),
+    ("srcfv/tangent/flux_num_dnc7_nowall_d.f90", None),
+    ("srcfv/prepro/flux_num_dnc9.f90", None),
+    ("srcfv/prepro/flux_num_dnc9_nowall.f90", None),
+    ("srcfv/tangent/flux_num_dnc9_d.f90", None),
+    ("srcfv/tangent/flux_num_dnc9_nowall_d.f90", None),
     ("srcfv/prepro/bc_wall_viscous.f90", ["bc_wall_viscous_adia_2d"]),
     ("srcfv/prepro/bc_no_reflexion.f90", ["bc_no_reflexion_2d"]),
     ("srcfv/prepro/bc_supandsubinlet.f90", ["bc_supandsubinlet_2d"]),

@@ -38,7 +38,7 @@ def tangent_sequence(mods, case, w, wd, scheme="flux_num_dnc5_2d_d"):
     return wd, resd
 
 
-def jacobian_sequence(mods, case, w, colours=None, coefdiag=None):
+def jacobian_sequence(mods, case, w, colours=None, coefdiag=None, scheme_d="flux_num_dnc5_2d_d"):
     """Colour loop of BROADCAST_npz.py:1068-1127 (or cylinder.py:941-978 for periodic-in-i cases).
     Returns the COO lists restricted to the visited colours (full lists if colours is None)."""
     im, jm, gh = case.im, case.jm, case.gh
@@ -61,7 +61,7 @@ def jacobian_sequence(mods, case, w, colours=None, coefdiag=None):
         f_misc.testvector(wd, m, l, k, gh, im, jm)
         ww = w.copy(order="F")
         cases.apply_bcs_lin(case, ww, wd, mods["f_bnd"], f_lin)
-        f_lin.flux_num_dnc5_2d_d(res, resd, ww, wd, *case.scheme_args())
+        getattr(f_lin, scheme_d)(res, resd, ww, wd, *case.scheme_args())
         if case.periodic_i:
             f_misc.computejacobianfromjv_relaxed_withjn(jac, ia, ja, resd, m, l, k, gh, coefdiag)
         else:
