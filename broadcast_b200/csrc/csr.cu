@@ -56,11 +56,16 @@ __global__ void __launch_bounds__(128) k_csr_count_interior(GridDesc g, Rect rc,
   for (int e = 0; e < 5; ++e) counts[row + e] = cnt[e];
 }
 
+// (a strip list may hold rows of other row blocks too -- the banded assembly hands the lists of the whole block to every band:
+// entries outside the nrows rows of this block are skipped)
 __global__ void k_csr_count_strip(const double* __restrict__ jac, const int* __restrict__ ia, long long n, double thresh, long long row0,
-                                  int* __restrict__ counts) {
+                                  long long nrows, int* __restrict__ counts) {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= n) return;
-  if (::fabs(jac[t]) > thresh) atomicAdd(&counts[ia[t] - row0], 1);
+  if (::fabs(jac[t]) > thresh) {
+    const long long r = ia[t] - row0;
+    if (r >= 0 && r < nrows) atomicAdd(&counts[r], 1);
+  }
 }
 
 // ---- 2. exclusive scan int32 -> int64 ---------------------------------------------------------------------------------
@@ -155,10 +160,15 @@ __global__ void __launch_bounds__(256) k_csr_fill_interior(GridDesc g, Rect rc, 
 #pragma unroll 1
   for (int e = 0; e < 5; ++e) {
     __syncthreads();
+    // asynchronous copies straight into shared memory (LDGSTS): all ~18 loads of a thread are in flight at once, no registers
     for (int c = w; c < NCAND; c += 8) {   // candidate c = (slot c / 5, variable c % 5): plane slot * 25 + e * 5 + m
       const long long plane = (long long)(c / 5) * 25 + e * 5 + c % 5;
-      sv[c * FILL_PITCH + lane] = lane < nc ? __ldg(V + plane * ncell + cell0 + lane) : 0.0;
+      if (lane < nc) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&sv[c * FILL_PITCH + lane]);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(V + plane * ncell + cell0 + lane) : "memory");
+      }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     for (int q = w; q < nc; q += 8) {
       const int i = ib + q;
@@ -189,13 +199,14 @@ __global__ void __launch_bounds__(256) k_csr_fill_interior(GridDesc g, Rect rc, 
 }
 
 __global__ void k_csr_fill_strip(const double* __restrict__ jac, const int* __restrict__ ia, const int* __restrict__ ja, long long n,
-                                 double thresh, long long row0, const long long* __restrict__ indptr, int* __restrict__ cursor,
-                                 int* __restrict__ indices, double* __restrict__ data) {
+                                 double thresh, long long row0, long long nrows, const long long* __restrict__ indptr,
+                                 int* __restrict__ cursor, int* __restrict__ indices, double* __restrict__ data) {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= n) return;
   const double v = jac[t];
   if (::fabs(v) > thresh) {
     const long long r = ia[t] - row0;
+    if (r < 0 || r >= nrows) return;
     const long long p = indptr[r] + atomicAdd(&cursor[r], 1);
     data[p] = v;
     indices[p] = ja[t];
@@ -305,9 +316,23 @@ using namespace bcast;
 
 // Step 1 + 2: indptr[0 .. 5 im jm] (int64, device) of the CSR row block; counts / bsum are device work arrays of
 // 5 im jm + 1 ints and ceil(5 im jm / 2048) + 1 int64.  The caller reads indptr[5 im jm] (= nnz) and allocates indices / data.
+static int hybrid_csr_indptr(long long* indptr, int32_t* counts, long long* bsum, const double* values, const int32_t* region, int nstrip,
+                             const double* const* sjac, const int32_t* const* sia, const long long* slen, double thresh, int gh, int im,
+                             int jm, int counted, void* stream);
 extern "C" int bcd_hybrid_csr_indptr(long long* indptr, int32_t* counts, long long* bsum, const double* values, const int32_t* region,
                                      int nstrip, const double* const* sjac, const int32_t* const* sia, const long long* slen, double thresh,
                                      int gh, int im, int jm, void* stream) {
+  return hybrid_csr_indptr(indptr, counts, bsum, values, region, nstrip, sjac, sia, slen, thresh, gh, im, jm, 0, stream);
+}
+// the same with the counts of the regular rows already in `counts` (bcd_jacobian_interior_counted): only the strip rows are counted
+extern "C" int bcd_hybrid_csr_indptr_counted(long long* indptr, int32_t* counts, long long* bsum, const int32_t* region, int nstrip,
+                                             const double* const* sjac, const int32_t* const* sia, const long long* slen, double thresh,
+                                             int gh, int im, int jm, void* stream) {
+  return hybrid_csr_indptr(indptr, counts, bsum, nullptr, region, nstrip, sjac, sia, slen, thresh, gh, im, jm, 1, stream);
+}
+static int hybrid_csr_indptr(long long* indptr, int32_t* counts, long long* bsum, const double* values, const int32_t* region, int nstrip,
+                             const double* const* sjac, const int32_t* const* sia, const long long* slen, double thresh, int gh, int im,
+                             int jm, int counted, void* stream) {
   if (im < 1 || jm < 1 || gh != 3 || nstrip < 0 || nstrip > 4) return BC_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const GridDesc g = make_grid_ctx(im, jm, gh);
@@ -315,13 +340,13 @@ extern "C" int bcd_hybrid_csr_indptr(long long* indptr, int32_t* counts, long lo
   if (jm > 65535 || 5LL * g.img * jm >= (1LL << 31)) return BC_ERR_UNSUPPORTED;
   const long long n = 5LL * im * jm;
   const long long row0 = 5LL * jm * g.ioff;
-  cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int) * (n + 1), st);
+  cudaError_t e = counted ? cudaSuccess : cudaMemsetAsync(counts, 0, sizeof(int) * (n + 1), st);
   if (e != cudaSuccess) return (int)e;
   const Rect rc{region[0], region[1], region[2], region[3]};
-  if (rc.i1 >= rc.i0 && rc.j1 >= rc.j0 && values)
+  if (!counted && rc.i1 >= rc.i0 && rc.j1 >= rc.j0 && values)
     k_csr_count_interior<<<dim3((rc.i1 - rc.i0 + 128) / 128, rc.j1 - rc.j0 + 1), 128, 0, st>>>(g, rc, values, thresh, counts);
   for (int q = 0; q < nstrip; ++q)
-    if (slen[q] > 0) k_csr_count_strip<<<(unsigned)((slen[q] + 255) / 256), 256, 0, st>>>(sjac[q], sia[q], slen[q], thresh, row0, counts);
+    if (slen[q] > 0) k_csr_count_strip<<<(unsigned)((slen[q] + 255) / 256), 256, 0, st>>>(sjac[q], sia[q], slen[q], thresh, row0, n, counts);
   const int nb = (int)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
   k_scan_reduce<<<nb, SCAN_T, 0, st>>>(counts, n, bsum);
   k_scan_blocks<<<1, 1024, 0, st>>>(bsum, nb);
@@ -360,8 +385,8 @@ extern "C" int bcd_hybrid_csr_fill(int32_t* indices, double* data, int32_t* curs
     }
     for (int q = 0; q < nstrip; ++q)
       if (slen[q] > 0)
-        k_csr_fill_strip<<<(unsigned)((slen[q] + 255) / 256), 256, 0, st>>>(sjac[q], sia[q], sja[q], slen[q], thresh, row0, indptr, cursor,
-                                                                           indices, data);
+        k_csr_fill_strip<<<(unsigned)((slen[q] + 255) / 256), 256, 0, st>>>(sjac[q], sia[q], sja[q], slen[q], thresh, row0, n, indptr,
+                                                                           cursor, indices, data);
     // cursor[n] doubles as the overflow flag of the sort (zeroed by the memset above)
     k_csr_sort_strip_rows<<<(unsigned)((nrows + 3) / 4), 128, 0, st>>>(g, rl, vol, indptr, indices, data, cursor + n);
     int ovf = 0;

@@ -77,10 +77,13 @@ __constant__ JacTab kJacTabDev = fj::make_jac_tab();
 // ST = first staged field (27: DEG + SE + viscous = 27 fields, 62.8 KB; 35: SE + viscous = 19 fields, 44.2 KB; 40: viscous only),
 // MINB = CTAs per SM the register allocation aims at.
 constexpr int JT_I = 32, JT_J = 4;
-template <int ST, int MINB>
+// COUNT: the thread also counts, per equation row of its cell, the entries the CSR conversion will keep (|v| > thresh, the
+// reference's remove_zero_jac) while the block values are still in registers: the conversion's counting pass over the 5.8 KB of
+// block values per cell (csr.cu: k_csr_count_interior) is then not needed.
+template <int ST, int MINB, bool COUNT = false>
 __global__ void __launch_bounds__(JT_I* JT_J, MINB)
     k_jac_assemble_rt(GridDesc g, SchemeConsts c, FieldPtrs f, Rect rc, const double* __restrict__ pkg, double* __restrict__ V,
-                      const double* __restrict__ coefdiag) {
+                      const double* __restrict__ coefdiag, int* __restrict__ counts = nullptr, double thresh = 0.0) {
   constexpr int FPK_NVS = FPK_N - ST;
   constexpr int FPK_VS = ST;
   using FaceCtx = FaceCtxT<ST>;
@@ -144,6 +147,7 @@ __global__ void __launch_bounds__(JT_I* JT_J, MINB)
   const long long ncell = (long long)g.im * g.jm;
   const long long cell = (long long)(i - 1) + (long long)(j - 1) * g.im;
   const double cd = coefdiag ? coefdiag[cell] : 0.0;
+  int cnt[5] = {0, 0, 0, 0, 0};
   double wn[5];   // state of the next slot's column cell: loaded one slot ahead
   {
     const long long kc = g.cidx(i + kJacTabDev.di[0], j + kJacTabDev.dj[0]);
@@ -168,12 +172,21 @@ __global__ void __launch_bounds__(JT_I* JT_J, MINB)
     double* out = V + ((long long)s * 25) * ncell + cell;
 #pragma unroll
     for (int q = 0; q < 25; ++q) out[q * ncell] = B[q];
+    if constexpr (COUNT) {
+#pragma unroll
+      for (int q = 0; q < 25; ++q) cnt[q / 5] += ::fabs(B[q]) > thresh ? 1 : 0;
+    }
+  }
+  if constexpr (COUNT) {
+    const long long row = 5LL * (j - 1) + 5LL * g.jm * (i - 1);
+#pragma unroll
+    for (int e = 0; e < 5; ++e) counts[row + e] = cnt[e];
   }
 }
 
 cudaError_t launch_jacobian_faces(const GridDesc& g, const SchemeArgs& a, const double* w, const double* nx, const double* ny,
                                   const double* vol, const double* volf, const Rect& rc, double* values, const double* coefdiag,
-                                  cudaStream_t st) {
+                                  cudaStream_t st, int* counts, double thresh) {
   const SchemeConsts c = make_consts(a.cp, a.cv, a.prandtl, a.gam, a.rgaz, a.cs, a.muref, a.tref, a.s_suth, a.k2, a.k4);
   FieldPtrs f;
   cudaError_t e = prepare_prims_grads(g, a, w, nx, ny, vol, volf, f, st);
@@ -192,15 +205,18 @@ cudaError_t launch_jacobian_faces(const GridDesc& g, const SchemeArgs& a, const 
   {
     static const int cfg = getenv("BROADCAST_B200_JAC_CFG") ? atoi(getenv("BROADCAST_B200_JAC_CFG")) : 5;
     const dim3 grd((rc.i1 - rc.i0 + JT_I) / JT_I, (rc.j1 - rc.j0 + JT_J) / JT_J), blk2(JT_I, JT_J);
-    auto go = [&](auto kern, int st_field) -> cudaError_t {
+    auto go = [&](auto kern, int st_field, bool counted = false) -> cudaError_t {
       const size_t smem = (size_t)(FPK_N - st_field) * (JT_J * (JT_I + 1) + (JT_J + 1) * JT_I) * sizeof(double);
       cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e2 != cudaSuccess) return e2;
       e2 = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
       if (e2 != cudaSuccess) return e2;
-      kern<<<grd, blk2, smem, st>>>(g, c, f, rc, pkg, values, coefdiag);
+      if (counted) kern<<<grd, blk2, smem, st>>>(g, c, f, rc, pkg, values, coefdiag, counts, thresh);
+      else kern<<<grd, blk2, smem, st>>>(g, c, f, rc, pkg, values, coefdiag, nullptr, 0.0);
       return cudaGetLastError();
     };
+    if (counts) e = go(k_jac_assemble_rt<27, 2, true>, 27, true);
+    else
     if (cfg == 1) e = go(k_jac_assemble_rt<35, 4>, 35);        // 19 staged fields, 128 registers, 16 warps per SM
     else if (cfg == 2) e = go(k_jac_assemble_rt<40, 4>, 40);   // 14 staged fields, 128 registers
     else if (cfg == 3) e = go(k_jac_assemble_rt<40, 5>, 40);   // 14 staged fields, 96 registers, 20 warps per SM

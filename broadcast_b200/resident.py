@@ -452,9 +452,11 @@ class HybridJacobian:
     (gh+1..im-gh x gh+1..jm-gh; other rows of ``blocks`` are unused) and reference-ordered COO lists for
     the four boundary strips."""
 
-    def __init__(self, blk, blocks, offsets, strips, region, strip_rects=()):
+    def __init__(self, blk, blocks, offsets, strips, region, strip_rects=(), counts=None, count_thresh=None):
         self.blk, self.blocks, self.offsets, self.strips, self.region = blk, blocks, offsets, strips, region
         self.strip_rects = list(strip_rects)
+        # per-row counts of the regular rows taken by the assembly kernel itself (jacobian_hybrid(count_thresh=...))
+        self.counts, self.count_thresh = counts, count_thresh
 
     def to_coo(self, thresh=2e-16):
         """filtered COO (remove_zero_jac semantics) on the device, reference numbering of rows/columns"""
@@ -483,11 +485,12 @@ class HybridJacobian:
             cols.append(ja[keep].to(torch.int64))
         return torch.cat(vals), torch.cat(rows), torch.cat(cols)
 
-    def to_csr(self, thresh=2e-16, divide_by_vol=False):
+    def to_csr(self, thresh=2e-16, divide_by_vol=False, out=None, slack=False):
         """device-side CSR row block of this (slab's) rows: (indptr, indices, data) torch tensors, columns ascending in a row,
         optionally divided by the row cell's volume (``Jacsurvol``, BROADCAST_npz.py:1206-1210).  Hand-written kernels
-        (``to_csr_device``); ``to_csr_torch`` is the same result by torch ops (the cross-check, ~150x slower at C1)."""
-        return self.to_csr_device(thresh, divide_by_vol)
+        (``to_csr_device``); ``to_csr_torch`` is the same result by torch ops (the cross-check, ~150x slower at C1).
+        ``out`` = (indices, data) buffers of a previous assembly: reused when they hold the new non-zero count."""
+        return self.to_csr_device(thresh, divide_by_vol, out, slack)
 
     def to_csr_torch(self, thresh=2e-16, divide_by_vol=False):
         """``to_csr`` by torch ops (masked selects per block plane, sort-based COO -> CSR): cross-check of the kernels"""
@@ -501,7 +504,7 @@ class HybridJacobian:
         n = 5 * blk.im_global * blk.jm
         return formats.coo_to_csr(v, r, c, 5 * blk.im * blk.jm, n, row0=5 * blk.jm * blk.ioff)
 
-    def to_csr_device(self, thresh=2e-16, divide_by_vol=False):
+    def to_csr_device(self, thresh=2e-16, divide_by_vol=False, out=None, slack=False):
         """the same CSR row block as ``to_csr`` by hand-written kernels (csrc/csr.cu): per-row counts, warp-shuffle scan, ballot-
         compacted fill in column order, warp rank sort of the strip rows -- no sort of the whole matrix, no Python loop over the
         725 block planes.  Returns (indptr int64, indices int32, data float64) device tensors."""
@@ -509,7 +512,8 @@ class HybridJacobian:
         dev = blk.device
         n = 5 * blk.im * blk.jm
         indptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
-        counts = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        counted = self.counts is not None and self.count_thresh == thresh
+        counts = self.counts if counted else torch.empty(n + 1, dtype=torch.int32, device=dev)
         bsum = torch.empty(n // 2048 + 2, dtype=torch.int64, device=dev)
         region = np.asarray(self.region, dtype=np.int32)
         ns = len(self.strips)
@@ -520,11 +524,23 @@ class HybridJacobian:
         slen = (ctypes.c_longlong * max(ns, 1))(*[t[0].numel() for t in self.strips])
         srect = np.asarray(self.strip_rects, dtype=np.int32).reshape(-1) if ns else np.zeros(4, dtype=np.int32)
         VP = ctypes.c_void_p
-        blk.call("bcd_hybrid_csr_indptr", _p(indptr), _p(counts), _p(bsum), _p(self.blocks), region.ctypes.data_as(VP), ns, sj, si, slen,
-                 ctypes.c_double(thresh), blk.gh, blk.im, blk.jm, blk._stream())
+        if counted:
+            blk.call("bcd_hybrid_csr_indptr_counted", _p(indptr), _p(counts), _p(bsum), region.ctypes.data_as(VP), ns, sj, si, slen,
+                     ctypes.c_double(thresh), blk.gh, blk.im, blk.jm, blk._stream())
+            self.counts = None     # the fill below uses the array as its cursor work space
+        else:
+            blk.call("bcd_hybrid_csr_indptr", _p(indptr), _p(counts), _p(bsum), _p(self.blocks), region.ctypes.data_as(VP), ns, sj, si, slen,
+                     ctypes.c_double(thresh), blk.gh, blk.im, blk.jm, blk._stream())
         nnz = int(indptr[-1].item())
-        indices = torch.empty(nnz, dtype=torch.int32, device=dev)
-        data = torch.empty(nnz, dtype=torch.float64, device=dev)
+        if out is not None and out[0].numel() >= nnz and out[1].numel() >= nnz:
+            # the pattern is value dependent, so the count moves a little from one Newton iterate to the next: the buffers of the
+            # previous assembly serve as long as they are large enough (a cudaMalloc of tens of GB costs more than the fill)
+            indices, data = out[0][:nnz], out[1][:nnz]
+            self.csr_storage = out
+        else:
+            cap = nnz + (nnz // 100 + 1024 if out is not None or slack else 0)   # head room for the next iterate's count
+            self.csr_storage = (torch.empty(cap, dtype=torch.int32, device=dev), torch.empty(cap, dtype=torch.float64, device=dev))
+            indices, data = self.csr_storage[0][:nnz], self.csr_storage[1][:nnz]
         blk.call("bcd_hybrid_csr_fill", _p(indices), _p(data), _p(counts), _p(indptr), _p(self.blocks), region.ctypes.data_as(VP), ns,
                  srect.ctypes.data_as(VP), sj, si, sk, slen, ctypes.c_double(thresh), _p(blk.vol if divide_by_vol else None), blk.gh,
                  blk.im, blk.jm, blk._stream())
@@ -555,18 +571,48 @@ class BandedAssembly:
             self.bands.append((Block(sl, device, slab=desc if nband > 1 else None), lo, hi))
         nmax = max(b.im for b, _, _ in self.bands)
         self._buf = torch.empty(29 * 25 * case.jm * nmax, dtype=torch.float64, device=self.device)
+        self._csr = [None] * nband      # (indices, data) storage of every band's row block, reused by the next assembly
+        # the boundary strips are assembled ONCE on the whole block (49 latency-bound colour passes: run per band they cost nband
+        # times as much) and every band's CSR conversion picks its rows out of these lists
+        self.whole = Block(case, device) if nband > 1 else None
 
-    def assemble_csr(self, w, coefdiag=None, divide_by_vol=True, thresh=2e-16):
+    def assemble_csr(self, w, coefdiag=None, divide_by_vol=True, thresh=2e-16, reuse=True):
         """``w``: the state of the whole block (device tensor (5, jm+2gh, im+2gh), ghosts filled).  ``coefdiag``: optional (jm, im)
-        device tensor.  Returns [(indptr int64, indices int32, data float64), ...], one row block per band."""
+        device tensor.  Returns [(indptr int64, indices int32, data float64), ...], one row block per band.  With ``reuse`` the
+        index / value arrays of the previous assembly are overwritten when they are large enough (the Newton loop assembles the
+        same block again and again); pass ``reuse=False`` to get arrays of your own."""
         gh, jm = self.case.gh, self.case.jm
         out = []
+        strips = None
+        if self.whole is not None:
+            wb = self.whole
+            wb.w.copy_(w)
+            im = wb.im
+            rects = [(1, im, 1, gh), (1, im, jm - gh + 1, jm)]
+            if not self.case.periodic_i:     # the bands of an i-periodic block have no irregular columns: the cut is a slab edge
+                rects += [(1, gh, gh + 1, jm - gh), (im - gh + 1, im, gh + 1, jm - gh)]
+            rects = [r for r in rects if r[1] >= r[0] and r[3] >= r[2]]
+            kind = "jv_relaxed_withjn" if self.case.periodic_i else "jv_relaxed"
+            cdw = coefdiag
+            if cdw is None:
+                cdw = getattr(self, "_zero_cd", None)
+                if cdw is None:
+                    cdw = self._zero_cd = torch.zeros((jm, im), dtype=torch.float64, device=self.device)
+            if getattr(self, "_strip_out", None) is None:
+                s_ = 2 * gh + 1
+                self._strip_out = [tuple(torch.zeros(25 * s_ * s_ * (r[1] - r[0] + 1) * (r[3] - r[2] + 1), dtype=dt, device=self.device)
+                                         for dt in (torch.float64, torch.int32, torch.int32)) for r in rects]
+            strips = jacobian_strips(wb, rects, coefdiag=cdw, kind=kind, out=self._strip_out)
         for blk, lo, hi in self.bands:
             blk.w.copy_(w[:, :, lo - 1:hi + 2 * gh])          # the band's columns + gh halo columns on each side
             blocks = self._buf[:29 * 25 * jm * blk.im].view(29, 5, 5, jm, blk.im)
             cd = coefdiag[:, lo - 1:hi].contiguous() if coefdiag is not None else None
-            H = jacobian_hybrid(blk, coefdiag=cd, blocks=blocks)
-            out.append(H.to_csr(thresh=thresh, divide_by_vol=divide_by_vol))
+            H = jacobian_hybrid(blk, coefdiag=cd, blocks=blocks, count_thresh=thresh, strips=strips)
+            b = len(out)
+            ip, idx, dat = H.to_csr(thresh=thresh, divide_by_vol=divide_by_vol, out=self._csr[b] if reuse else None, slack=reuse)
+            if reuse:
+                self._csr[b] = H.csr_storage
+            out.append((ip, idx, dat))
         return out
 
     @staticmethod
@@ -601,7 +647,8 @@ def csr_transpose(indptr, indices, data, ncols, row0=0, stream=None):
     return tptr, tind, tdat
 
 
-def jacobian_hybrid(blk: "Block", coefdiag=None, kind=None, blocks=None, interior="faces", strip_buffers=None):
+def jacobian_hybrid(blk: "Block", coefdiag=None, kind=None, blocks=None, interior="faces", strip_buffers=None, count_thresh=None,
+                    strips=None):
     """Jacobian of the current state: interior rows by the direct block kernels (one launch per
     structural column offset, no colouring), boundary strips (gh rows/columns along each side) by the
     reference colour loop restricted to those rows.
@@ -625,14 +672,32 @@ def jacobian_hybrid(blk: "Block", coefdiag=None, kind=None, blocks=None, interio
     region = (ilo, ihi, gh + 1, jm - gh)
     if blocks is None:
         blocks = torch.zeros((29, 5, 5, jm, im), dtype=torch.float64, device=blk.device)
-    blk.call("bcd_jacobian_interior" if interior == "faces" else "bcd_jacobian_interior_ad", _p(blocks), _p(blk.w), _p(blk.nx), _p(blk.ny),
-             _p(blk.vol), _p(blk.volf), gh, *blk._phys, im, jm, _p(cd if relaxed else None), ctypes.c_void_p(None), blk._stream())
+    counts = None
+    if count_thresh is not None and interior == "faces":
+        # the assembly kernel also counts the entries |v| > count_thresh of every regular row (what to_csr would otherwise do in a
+        # pass of its own over the block values)
+        counts = torch.empty(5 * im * jm + 1, dtype=torch.int32, device=blk.device)
+        blk.call("bcd_jacobian_interior_counted", _p(blocks), _p(counts), ctypes.c_double(count_thresh), _p(blk.w), _p(blk.nx), _p(blk.ny),
+                 _p(blk.vol), _p(blk.volf), gh, *blk._phys, im, jm, _p(cd if relaxed else None), ctypes.c_void_p(None), blk._stream())
+    else:
+        blk.call("bcd_jacobian_interior" if interior == "faces" else "bcd_jacobian_interior_ad", _p(blocks), _p(blk.w), _p(blk.nx), _p(blk.ny),
+                 _p(blk.vol), _p(blk.volf), gh, *blk._phys, im, jm, _p(cd if relaxed else None), ctypes.c_void_p(None), blk._stream())
     rects = [(1, im, 1, gh), (1, im, jm - gh + 1, jm)]
     if not edges & 1:
         rects.append((1, gh, gh + 1, jm - gh))
     if not edges & 2:
         rects.append((im - gh + 1, im, gh + 1, jm - gh))
     rects = [r for r in rects if r[1] >= r[0] and r[3] >= r[2]]
+    if strips is not None:
+        # strip lists computed elsewhere in GLOBAL numbering (BandedAssembly: once on the whole block; the CSR conversion of this
+        # row block takes its own rows out of them): only the regular rows are assembled here
+        strips = list(strips)
+        if len(rects) > len(strips):
+            raise ValueError("fewer strip lists than irregular sides of this block")
+        # the conversion sorts the rows of `rects` and reads one rectangle per list: empty rectangles for the lists of other bands
+        rects = rects + [(1, 0, 1, 0)] * (len(strips) - len(rects))
+        return HybridJacobian(blk, blocks, jacobian_slots(blk), strips, region, strip_rects=rects, counts=counts,
+                              count_thresh=count_thresh)
     if strip_buffers == "fresh":
         strip_buffers = None
     elif strip_buffers is None:
@@ -646,7 +711,7 @@ def jacobian_hybrid(blk: "Block", coefdiag=None, kind=None, blocks=None, interio
                           for r in rects]
         strip_buffers = cache[key]
     strips = jacobian_strips(blk, rects, coefdiag=cd, kind=kind, out=strip_buffers)
-    return HybridJacobian(blk, blocks, jacobian_slots(blk), strips, region, strip_rects=rects)
+    return HybridJacobian(blk, blocks, jacobian_slots(blk), strips, region, strip_rects=rects, counts=counts, count_thresh=count_thresh)
 
 
 def jacobian_strips(blk: "Block", rects, coefdiag=None, kind="jv_relaxed", out=None):

@@ -437,6 +437,16 @@ int bcd_jacobian_interior_ad(double* values, const double* w, const double* nx, 
 int bcd_hybrid_csr_indptr(long long* indptr, int32_t* counts, long long* bsum, const double* values, const int32_t* region,
                           int nstrip, const double* const* sjac, const int32_t* const* sia, const long long* slen, double thresh,
                           int gh, int im, int jm, void* stream);
+/* Counting fused into the assembly: bcd_jacobian_interior that also leaves, in counts[0 .. 5 im jm] (zeroed first), the number of
+ * entries |v| > thresh of every regular row, taken while the block values are in registers; bcd_hybrid_csr_indptr_counted then only
+ * adds the strip rows and scans (one pass over the block values less: 5.8 KB per cell). */
+int bcd_jacobian_interior_counted(double* values, int32_t* counts, double thresh, const double* w, const double* nx,
+                                  const double* ny, const double* vol, const double* volf, int gh, double cp, double cv,
+                                  double prandtl, double gam, double rgaz, double cs, double muref, double tref, double s_suth,
+                                  double k2, double k4, int im, int jm, const double* coefdiag, const int32_t* rect, void* stream);
+int bcd_hybrid_csr_indptr_counted(long long* indptr, int32_t* counts, long long* bsum, const int32_t* region, int nstrip,
+                                  const double* const* sjac, const int32_t* const* sia, const long long* slen, double thresh,
+                                  int gh, int im, int jm, void* stream);
 int bcd_hybrid_csr_fill(int32_t* indices, double* data, int32_t* cursor, const long long* indptr, const double* values,
                         const int32_t* region, int nstrip, const int32_t* srect, const double* const* sjac,
                         const int32_t* const* sia, const int32_t* const* sja, const long long* slen, double thresh,

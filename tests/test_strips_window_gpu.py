@@ -88,3 +88,16 @@ def test_banded_assembly_equals_whole_block_csr(gpu):
         ip2, idx2, dat2 = BandedAssembly.gather(parts)
         assert torch.equal(ip, ip2) and torch.equal(idx, idx2)
         assert (dat - dat2).abs().max().item() <= 1e-13 * dat.abs().max().item()
+        # a second assembly on a changed state overwrites the index / value arrays of the first (reuse) and must equal the
+        # whole-block CSR of that state; the row counts come from the assembly kernel itself (jacobian_hybrid(count_thresh=...))
+        w2 = blk.w.clone()
+        blk.w[:, c.gh:-c.gh, c.gh:-c.gh] *= 1.0 + 1e-3 * torch.rand_like(blk.w[:, c.gh:-c.gh, c.gh:-c.gh])
+        blk.apply_bcs()
+        ipb, idxb, datb = jacobian_hybrid(blk).to_csr(divide_by_vol=True)
+        store = [t[1].untyped_storage().data_ptr() for t in parts]
+        parts = ba.assemble_csr(blk.w)
+        ip3, idx3, dat3 = BandedAssembly.gather(parts)
+        assert torch.equal(ipb, ip3) and torch.equal(idxb, idx3)
+        assert (datb - dat3).abs().max().item() <= 1e-13 * datb.abs().max().item()
+        assert any(t[1].untyped_storage().data_ptr() == s_ for t, s_ in zip(parts, store))
+        blk.w.copy_(w2)

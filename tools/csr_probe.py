@@ -51,5 +51,17 @@ for im, jm in sizes:
     torch.cuda.synchronize()
     out.update(assembly_ms=e[0].elapsed_time(e[1]), count_scan_ms=e[2].elapsed_time(e[3]), fill_ms=e[4].elapsed_time(e[5]), nnz=nnz,
                blocks_GB=blocks.numel() * 8 / 1e9, csr_GB=nnz * 12 / 1e9)
+    # counting fused into the assembly kernel
+    del indices, data
+    f0, f1, f2 = ev(), ev(), ev()
+    f0.record()
+    H2 = jacobian_hybrid(blk, blocks=blocks, count_thresh=2e-16)
+    f1.record()
+    ip2, idx2, dat2 = H2.to_csr(divide_by_vol=True)
+    f2.record()
+    torch.cuda.synchronize()
+    out.update(assembly_counted_ms=f0.elapsed_time(f1), to_csr_counted_ms=f1.elapsed_time(f2), same_indptr=bool(torch.equal(ip2, indptr)))
+    del H2, ip2, idx2, dat2
+    indices = data = None
     print(json.dumps(out), flush=True)
     del blk, blocks, H, indices, data; torch.cuda.empty_cache()
