@@ -559,7 +559,8 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"C5 synthetic 2-D boundary layer {a.im}x{a.jm}, order 5 (gh=3), i-slabs over {world} GPU(s)",
                        "step": "halo exchange (N>1) + 4 boundary fills + 1 residual (flux_num_dnc5_2d)" + (", fills and exchange overlapped with the inner tiles" if overlap else ""),
-                       "halo": halo_kind, "step_issue": "one CUDA-graph replay per step" if sgraph is not None else "separate launches",
+                       "halo": halo_kind, "step_issue": (("one CUDA-graph replay per step" + (", exchange + fills forked beside the inner residual tiles" if getattr(sgraph, "overlap", False) else ""))
+                                      if sgraph is not None else "separate launches"),
                        "l2": f"inputs larger than L2 ({blk.w.numel() * 8 / 2**20:.0f} MiB state per GPU)"},
             "roofline": roofline, "jacobian": jac, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "checksum": checksum,
         }

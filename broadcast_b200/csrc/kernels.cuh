@@ -177,7 +177,8 @@ cudaError_t launch_residual_fast(const GridDesc& g, const SchemeArgs& a, bool wa
 
 // bulk-staged tile kernel (residual_bulk.cu); *done = false -> caller falls back to the LDG tile kernel
 cudaError_t launch_residual_fast_bulk(const GridDesc& g, const SchemeConsts& c, double sqgr, bool wall, double* res, const double* w,
-                                      const double* nx, const double* ny, const double* vol, const double* volf, cudaStream_t st, bool* done);
+                                      const double* nx, const double* ny, const double* vol, const double* volf, cudaStream_t st, bool* done,
+                                      int part = 0);
 
 // third-generation fused residual (residual_march.cu): persistent j-marching CTAs; *done = false -> caller falls back
 cudaError_t launch_residual_march(const GridDesc& g, const SchemeConsts& c, double sqgr, bool wall, double* res, const double* w,

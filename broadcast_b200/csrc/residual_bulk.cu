@@ -67,7 +67,7 @@ struct BulkMaps {
 };
 
 __global__ void __launch_bounds__(rf::NT, 2)
-    k_residual_fast_bulk(const __grid_constant__ BulkMaps maps, int l2dist, int ntx, int nty, GridDesc g, SchemeConsts c, double sqgr, bool wall,
+    k_residual_fast_bulk(const __grid_constant__ BulkMaps maps, int l2dist, int ox, int oy, GridDesc g, SchemeConsts c, double sqgr, bool wall,
                          const double* __restrict__ w, const double* __restrict__ nx, const double* __restrict__ ny,
                          const double* __restrict__ vol, const double* __restrict__ volf, double* __restrict__ res) {
   extern __shared__ __align__(128) double sm[];
@@ -79,8 +79,9 @@ __global__ void __launch_bounds__(rf::NT, 2)
   t.volbox = sm + rf::O_VOLBOX;
   t.sqgr = sqgr; t.wall = wall;
   t.w = w; t.nx = nx; t.ny = ny; t.vol = vol; t.volf = volf; t.res = res;
-  t.i0 = 1 + blockIdx.x * rf::OI;
-  t.j0 = 1 + blockIdx.y * rf::OJ;
+  // (ox, oy): first tile of this launch in the tile grid of the block (whole block: 0, 0; inner tiles of the overlapped step: 1, 1)
+  t.i0 = 1 + (blockIdx.x + ox) * rf::OI;
+  t.j0 = 1 + (blockIdx.y + oy) * rf::OJ;
   const int tid = threadIdx.x;
   t.nsh = rf::node_shift_mask(g, t.i0, t.j0);
   if (tid == 0) {
@@ -94,10 +95,10 @@ __global__ void __launch_bounds__(rf::NT, 2)
   // the other nine warps at the barrier for ~250 instructions: 7.5 % of all stall samples, ncu r2_13), then the same boxes of the
   // tile `l2dist` launches ahead as L2 prefetches (CTAs start in blockIdx order).
   if ((tid & 31) == 0) {
-    const int L = blockIdx.y * ntx + blockIdx.x + l2dist;
-    const int pbx = L % ntx, pby = L / ntx;
-    const bool pf = l2dist > 0 && pby < nty;
-    const int pi0 = 1 + pbx * rf::OI, pj0 = 1 + pby * rf::OJ;
+    const int L = blockIdx.y * gridDim.x + blockIdx.x + l2dist;
+    const int pbx = L % gridDim.x, pby = L / gridDim.x;
+    const bool pf = l2dist > 0 && pby < gridDim.y;
+    const int pi0 = 1 + (pbx + ox) * rf::OI, pj0 = 1 + (pby + oy) * rf::OJ;
     for (int op = tid >> 5; op < rf::NBULK; op += rf::NT / 32) {
       const rf::BulkOp o = rf::bulk_op(g, t.i0, t.j0, op);
       const CUtensorMap* mp = op == 0 ? &maps.w : op == 1 ? &maps.vol : op == 2 ? &maps.volf : ((op - 3) >> 2) ? &maps.ny : &maps.nx;
@@ -177,8 +178,10 @@ bool make_node_map(const GridDesc& g, const double* base, CUtensorMap* map) {
 // *done = true when the bulk kernel was launched; false when the bulk-copy engine cannot describe the arrays (the caller falls back to
 // the LDG kernel)
 cudaError_t launch_residual_fast_bulk(const GridDesc& g, const SchemeConsts& c, double sqgr, bool wall, double* res, const double* w,
-                                      const double* nx, const double* ny, const double* vol, const double* volf, cudaStream_t st, bool* done) {
+                                      const double* nx, const double* ny, const double* vol, const double* volf, cudaStream_t st, bool* done,
+                                      int part) {
   *done = false;
+  if (part == 2) return cudaSuccess;   // the ring of tiles stays with the LDG kernel's 1-D ring launch (bit-identical results)
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if ((g.ldc & 1) || !al16(w) || !al16(vol) || !al16(volf) || !al16(nx) || !al16(ny)) return cudaSuccess;
   // the maps depend on the base pointers and the grid only: cache the last set (a Newton loop calls with the same arrays)
@@ -202,7 +205,14 @@ cudaError_t launch_residual_fast_bulk(const GridDesc& g, const SchemeConsts& c, 
   }
   static const int l2dist = getenv("BROADCAST_B200_RESIDUAL_L2DIST") ? atoi(getenv("BROADCAST_B200_RESIDUAL_L2DIST")) : 592;
   const int ntx = (g.im + rf::OI - 1) / rf::OI, nty = (g.jm + rf::OJ - 1) / rf::OJ;
-  k_residual_fast_bulk<<<dim3(ntx, nty), rf::NT, SMEM, st>>>(maps, l2dist, ntx, nty, g, c, sqgr, wall, w, nx, ny, vol, volf, res);
+  if (part == 1) {
+    // inner tiles (same rectangle as launch_residual_fast: every cell they read is an interior cell of the block)
+    const int bx1 = (g.im - rf::OI - 3) / rf::OI, by1 = (g.jm - rf::OJ - 3) / rf::OJ;
+    if (bx1 < 1 || by1 < 1) return cudaSuccess;   // no inner tile: the ring call (LDG kernel) does everything
+    k_residual_fast_bulk<<<dim3(bx1, by1), rf::NT, SMEM, st>>>(maps, l2dist, 1, 1, g, c, sqgr, wall, w, nx, ny, vol, volf, res);
+  } else {
+    k_residual_fast_bulk<<<dim3(ntx, nty), rf::NT, SMEM, st>>>(maps, l2dist, 0, 0, g, c, sqgr, wall, w, nx, ny, vol, volf, res);
+  }
   *done = true;
   return cudaGetLastError();
 }

@@ -213,7 +213,7 @@ constexpr bool BULK_IS_DEFAULT = true;   // C5: 2.25 ms against 2.39 ms for the 
 
 cudaError_t launch_residual_tiled(const GridDesc& g, const SchemeArgs& a, bool wall, double* res, const double* w, const double* nx,
                                   const double* ny, const double* vol, const double* volf, cudaStream_t st, int variant, int part) {
-  if (g.im < 4 || g.jm < 6 || (part != 0 && (variant == RES_TILE_V1 || variant == RES_FAST_TMA || variant == RES_MARCH || variant == RES_FAST_BULK))) {
+  if (g.im < 4 || g.jm < 6 || (part != 0 && (variant == RES_TILE_V1 || variant == RES_FAST_TMA || variant == RES_MARCH))) {
     if (part == 1) return cudaSuccess;   // kernels without a tile split do everything in the "ring" call
     if (g.im < 4 || g.jm < 6) return launch_residual_generic(g, a, wall, 0, res, w, nullptr, nx, ny, vol, volf, nullptr, st);
     part = 0;
@@ -231,11 +231,13 @@ cudaError_t launch_residual_tiled(const GridDesc& g, const SchemeArgs& a, bool w
   }
   // bulk-staged tile kernel: the default for whole-block launches (BROADCAST_B200_RESIDUAL_LDG=1 keeps the LDG tile kernel)
   static const bool ldg_default = getenv("BROADCAST_B200_RESIDUAL_LDG") != nullptr;
-  if ((variant == RES_FAST_BULK || (variant == RES_DEFAULT && BULK_IS_DEFAULT && !ldg_default && !v1 && !tma && !march_default)) && part == 0) {
+  if (variant == RES_FAST_BULK || (variant == RES_DEFAULT && BULK_IS_DEFAULT && !ldg_default && !v1 && !tma && !march_default)) {
+    // part 1 (inner tiles) runs on the bulk kernel too; part 2 (the ring) falls through to the LDG kernel's ring launch
     const SchemeConsts c = make_consts(a.cp, a.cv, a.prandtl, a.gam, a.rgaz, a.cs, a.muref, a.tref, a.s_suth, a.k2, a.k4);
     bool done = false;
-    cudaError_t e = launch_residual_fast_bulk(g, c, ::sqrt(a.gam * a.rgaz), wall, res, w, nx, ny, vol, volf, st, &done);
+    cudaError_t e = launch_residual_fast_bulk(g, c, ::sqrt(a.gam * a.rgaz), wall, res, w, nx, ny, vol, volf, st, &done, part);
     if (done || e != cudaSuccess) return e;
+    // part 1 not launched by the bulk kernel (TMA cannot describe the arrays, or no inner tile): the LDG kernel takes it
   }
   if (variant != RES_TILE_V1 && !(variant == RES_DEFAULT && v1))
     return launch_residual_fast(g, a, wall, res, w, nx, ny, vol, volf, st, variant == RES_FAST_TMA || (variant == RES_DEFAULT && tma), part);

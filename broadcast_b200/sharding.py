@@ -11,6 +11,8 @@ backend, which is how tests/test_sharding_cpu.py covers it without a GPU.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from .cases import Case
@@ -270,7 +272,29 @@ class StepGraph:
 
         after = bool(getattr(blk.case, "slab_periodic", False))   # periodic slabs: the exchange replaces the join, which follows the fills
 
+        # BROADCAST_B200_STEP_OVERLAP=1: the step forks inside the graph -- [exchange, boundary fills] on a side stream WHILE the inner
+        # tiles of the residual (which read no ghost cell and no halo column) run on the bulk kernel; the ring of tiles follows both.
+        # Measured on 8 B200 (profiles/r2_c_summary.md): 0.3072 ms against 0.3062 ms for the plain sequence, same checksum -- the
+        # ~38 us a step takes beyond its residual kernel are node-to-node latencies and the kernel's own ramp / tail, not the
+        # exchange; what the fork hides the extra ring launch costs again.  Off by default.
+        overlap = halo is not None and os.environ.get("BROADCAST_B200_STEP_OVERLAP", "0") == "1"
+        self.overlap = overlap
+        side = torch.cuda.Stream(device=blk.device) if overlap else None
+
         def seq():
+            if overlap:
+                main = torch.cuda.current_stream(blk.device)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    if not after:
+                        halo(blk.w)
+                    blk.apply_bcs()
+                    if after:
+                        halo(blk.w)
+                blk.residual_part(1)
+                main.wait_stream(side)
+                blk.residual_part(2)
+                return
             if halo is not None and not after:
                 halo(blk.w)
             blk.apply_bcs()
