@@ -737,3 +737,90 @@ def jacobian_strips(blk: "Block", rects, coefdiag=None, kind="jv_relaxed", out=N
     blk.call("bcd_jacobian_strips", n, ra.ctypes.data_as(ctypes.c_void_p), jp, ip, kp, _p(blk.w), _p(blk.nx), _p(blk.ny), _p(blk.vol),
              _p(blk.volf), gh, *blk._phys, blk.im, blk.jm, blk.wall, descs, nb_, SCATTER[kind], _p(coefdiag), blk._stream())
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# the step after the assembly: Newton correction on the device (csrc/solve.cu)
+# ----------------------------------------------------------------------------------------------
+def csr_spmv(indptr, indices, data, x, out=None, stream=None):
+    """y = A x for a device CSR row block (indptr int64, indices int32, data float64): hand-written warp-per-row kernel"""
+    L = _lib.lib()
+    nrows = indptr.numel() - 1
+    y = out if out is not None else torch.empty(nrows, dtype=torch.float64, device=data.device)
+    st = ctypes.c_void_p((stream or torch.cuda.current_stream(data.device)).cuda_stream)
+    _lib.check(L.bcd_csr_spmv(_p(y), _p(indptr), _p(indices), _p(data), _p(x), ctypes.c_longlong(nrows), st), "bcd_csr_spmv")
+    return y
+
+
+def block_jacobi(indptr, indices, data, col0=0, stream=None):
+    """inverse 5 x 5 diagonal blocks of a CSR row block, (25, ncell) device tensor (bcd_block_jacobi_setup); raises if a block is
+    singular"""
+    L = _lib.lib()
+    n = indptr.numel() - 1
+    if n % 5:
+        raise ValueError("the row block must hold whole cells (5 rows each)")
+    ncell = n // 5
+    dinv = torch.empty((25, ncell), dtype=torch.float64, device=data.device)
+    nbad = torch.zeros(1, dtype=torch.int32, device=data.device)
+    st = ctypes.c_void_p((stream or torch.cuda.current_stream(data.device)).cuda_stream)
+    _lib.check(L.bcd_block_jacobi_setup(_p(dinv), _p(nbad), _p(indptr), _p(indices), _p(data), ctypes.c_longlong(ncell),
+                                        ctypes.c_longlong(col0), st), "bcd_block_jacobi_setup")
+    if int(nbad.item()):
+        raise _lib.BroadcastB200Error(f"{int(nbad.item())} singular diagonal blocks")
+    return dinv
+
+
+def gmres(indptr, indices, data, b, x0=None, restart=40, maxit=2000, rtol=1e-10, precond=True, side="left", stream=None):
+    """Solve A x = b on the device (whole square matrix on this GPU): restarted GMRES preconditioned by the inverse diagonal blocks
+    (``precond``: True, False, or a tensor from ``block_jacobi``) on the ``side`` "left" (default: the iteration then controls
+    M^-1 (b - A x), which is free of the cell-size scaling of the rows) or "right".  Returns (x, info) with info = dict(matvecs,
+    converged, relres = true ||b - A x|| / ||b||, relres_iter = the controlled one).  The reference's counterpart is the
+    PETSc / MUMPS LU solve of misc/PETSc_func.py:137-152, 247-263."""
+    L = _lib.lib()
+    L.bcd_gmres_work_doubles.restype = ctypes.c_longlong
+    dev = data.device
+    n = indptr.numel() - 1
+    if b.numel() != n:
+        raise ValueError("right-hand side and matrix sizes differ")
+    dinv = None
+    if isinstance(precond, torch.Tensor):
+        dinv = precond
+    elif precond:
+        dinv = block_jacobi(indptr, indices, data, stream=stream)
+    nw = int(L.bcd_gmres_work_doubles(ctypes.c_longlong(n), int(restart)))
+    if nw < 0:
+        raise ValueError("restart must be in 1 .. 63")
+    work = torch.empty(nw, dtype=torch.float64, device=dev)
+    x = torch.zeros(n, dtype=torch.float64, device=dev) if x0 is None else x0.to(dtype=torch.float64, device=dev, copy=True).contiguous()
+    b = b.contiguous()
+    info = (ctypes.c_int32 * 2)()
+    relres = (ctypes.c_double * 2)()
+    st = ctypes.c_void_p((stream or torch.cuda.current_stream(dev)).cuda_stream)
+    _lib.check(L.bcd_gmres(_p(x), _p(b), _p(indptr), _p(indices), _p(data), _p(dinv), ctypes.c_longlong(n), int(restart), int(maxit),
+                           ctypes.c_double(rtol), {"left": 1, "right": 0}[side], _p(work), ctypes.c_longlong(nw), info, relres, st),
+               "bcd_gmres")
+    return x, {"matvecs": int(info[0]), "converged": bool(info[1]), "relres": float(relres[0]), "relres_iter": float(relres[1])}
+
+
+def newton_step(blk: "Block", coefdiag=None, restart=40, maxit=2000, rtol=1e-10, update=True):
+    """One Newton iteration of the reference's loop (BROADCAST_npz.py:1018-1172) with every stage on the device: boundary fills,
+    residual, relaxed Jacobian -> zero filter -> CSR (not divided by the volume: the matrix of iterNewton), solve A dw = res,
+    w += dw.  ``coefdiag``: the pseudo-time term cflm1 * vol (:1067) as a (jm, im) device tensor or an (im, jm) numpy array, or None.
+    Returns (dw as an (im, jm, 5) tensor, info)."""
+    gh, im, jm = blk.gh, blk.im, blk.jm
+    blk.apply_bcs()
+    blk.residual()
+    cd = None
+    if coefdiag is not None:
+        cd = coefdiag if isinstance(coefdiag, torch.Tensor) else _t(coefdiag, blk.device)
+    H = jacobian_hybrid(blk, coefdiag=cd, count_thresh=2e-16)
+    indptr, indices, data = H.to_csr(thresh=2e-16, divide_by_vol=False)
+    # right-hand side in the row numbering of the matrix: row = e + 5 (j - 1) + 5 jm (i - 1) (misc/ComputeJacobian.f90:526) =
+    # ravel(res[gh:-gh, gh:-gh, :]) of the Fortran array (BROADCAST_npz.py:1157)
+    rhs = blk.res[:, gh:gh + jm, gh:gh + im].permute(2, 1, 0).contiguous().view(-1)
+    dw, info = gmres(indptr, indices, data, rhs, restart=restart, maxit=maxit, rtol=rtol)
+    dw3 = dw.view(im, jm, 5)
+    if update and info["converged"]:
+        blk.w[:, gh:gh + jm, gh:gh + im] += dw3.permute(2, 1, 0)
+    info["nnz"] = int(data.numel())
+    return dw3, info

@@ -461,6 +461,29 @@ int bcd_csr_transpose_indptr(long long* tptr, int32_t* counts, long long* bsum, 
 int bcd_csr_transpose_fill(int32_t* tind, double* tdat, int32_t* cursor, const long long* tptr, const long long* indptr,
                            const int32_t* indices, const double* data, long long nrows, long long row0, long long ncols,
                            void* stream);
+
+/* ---- the step after the assembly: Newton correction A dw = res on the device.  The reference hands the CSR to
+ *      PETSc / MUMPS LU on the host (misc/PETSc_func.py:137-152 kspLUPetsc, :247-263 iterNewton: dw = A^-1 res, then
+ *      w += dw, BROADCAST_npz.py:1157-1172) and leaves its `lasolver == 'gmres'` branch unimplemented (:1043-1047).  Here: restarted
+ *      GMRES, right-preconditioned by the inverse 5 x 5 diagonal blocks, everything resident (csrc/solve.cu).  The adjoint systems
+ *      (cylinder.py:1090-1177) run the same entry points on the transposed CSR (bcd_csr_transpose_*).  One device, whole matrix. */
+/* y = A x for a CSR row block (indptr int64, global int32 columns) */
+int bcd_csr_spmv(double* y, const long long* indptr, const int32_t* indices, const double* data, const double* x,
+                 long long nrows, void* stream);
+/* dinv[25][ncell]: inverse of the diagonal 5 x 5 block of every cell (rows 5 c .. 5 c + 4 of the block, columns col0 + 5 c ...);
+ * *nbad (device int) = number of singular blocks, replaced by the identity */
+int bcd_block_jacobi_setup(double* dinv, int32_t* nbad, const long long* indptr, const int32_t* indices, const double* data,
+                           long long ncell, long long col0, void* stream);
+int bcd_block_jacobi_apply(double* z, const double* dinv, const double* r, long long ncell, void* stream);
+/* doubles of device work space bcd_gmres needs for n unknowns and the given restart length (1 <= restart < 64); -1 if invalid */
+long long bcd_gmres_work_doubles(long long n, int restart);
+/* x: start vector in, solution out; dinv: bcd_block_jacobi_setup output or null; side = 1: preconditioner on the left (the residual
+ * the iteration controls is M^-1 (b - A x): free of the row scaling of the finite-volume Jacobian), 0: on the right; stops at a
+ * relative (preconditioned) residual of rtol or after maxit products; info[0] = matrix-vector products, info[1] = 1 if converged (host
+ * ints); relres[0] = final TRUE relative residual ||b - A x|| / ||b||, relres[1] = the controlled one (host doubles) */
+int bcd_gmres(double* x, const double* b, const long long* indptr, const int32_t* indices, const double* data,
+              const double* dinv, long long n, int restart, int maxit, double rtol, int side, double* work,
+              long long work_len, int32_t* info, double* relres, void* stream);
 /* isothermal-wall scheme variant in resident mode: the wall flux of the calling thread's next bcd_* launches (residual, tangent,
  * colour loops, strips) is rhs/fluxwall_iso.F with this twall while on != 0 (bc_flux_num_dnc5_iso_2d sets it around its own call) */
 int bcd_wall_iso(int on, double twall);
