@@ -149,7 +149,7 @@ static_assert(OI + 3 + 1 <= MN_SLOT, "node row window: columns a = 0 .. OI + 2 a
 constexpr int BULK_BYTES = (5 * NC + MV_W * MV_H + 2 * MF_W * MF_H + 8 * MN_HALF * MN_SLOT) * 8;   // what one tile receives
 static_assert(5 * NC <= WBUF, "w buffer");
 static_assert(5 * OJ * XI_P <= NXB, "exchange buffer");
-static_assert(OJ <= 32 && GW * OJ <= NT + 0 && (RI_W + 3) <= NT && RJ_W <= NT && 2 * OI <= NT, "thread mappings");
+static_assert(OJ <= 16 && NT % 32 == 0 && NT / 32 == OJ + 1 && 2 * OI <= NT && OI == 32, "thread mappings (warp-aligned sensor / R_q tasks)");
 static_assert(2 * GW * GH_ <= NXB, "scratch aliasing");
 static_assert(RJ_W * RJ_H <= RQ, "R buffer");
 
@@ -323,11 +323,20 @@ struct SensGeom {
   bool valid;
 };
 BC_HD bool sensor_of(const TileCtx& t, int tid, int round, int& ga, int& gb) {   // window coordinates of the thread's sensor cell
+  // Warp-aligned mapping (r2_c: the former `tid % 34` mapping let every warp straddle two rows -- 28 % excess shared-memory
+  // wavefronts in this phase, ncu r2_15 -- and gave warp OJ - 1 three work items where the others have two):
+  //   round 0: warp r < OJ owns row j0 + r, columns i0-1 .. i0+30 (one per lane); the last warp owns the two columns i0+31, i0+32
+  //            of all OJ rows (2 OJ lanes)
+  //   round 1: the two rows j0-1 and j0+OJ, columns i0 .. i0+31: warps OJ - 1 and OJ (neither has a main R_q task in phase 1)
   if (round == 0) {
-    if (tid >= GW * OJ) return false;
-    ga = tid % GW;
-    gb = 1 + tid / GW;
-  } else {   // the two rows j0-1 and j0+OJ, columns i0 .. i0+31: the last two warps (the lightest ones in this phase)
+    const int wrp = tid >> 5, lane = tid & 31;
+    if (wrp < OJ) { ga = lane; gb = 1 + wrp; }
+    else {
+      if (lane >= 2 * OJ) return false;
+      ga = OI + lane / OJ;
+      gb = 1 + lane % OJ;
+    }
+  } else {
     const int u = tid - (NT - 2 * OI);
     if (u < 0) return false;
     ga = 1 + (u & (OI - 1));
@@ -381,17 +390,19 @@ BC_HD void sensor_cell(const TileCtx& t, int tid, int round, const SensGeom& G) 
 BC_HD void phase1(const TileCtx& t, int tid, const SensGeom& G0, const SensGeom& G1) {
   sensor_cell(t, tid, 0, G0);
   sensor_cell(t, tid, 1, G1);
-  // R_q of the i-faces: eight tasks (quantity q, half of the face rows) spread over the NT / 36 thread groups of 36 (33 active)
-  const int fcol = tid % (RI_W + 3);
-  constexpr int NG = NT / (RI_W + 3) < 8 ? NT / (RI_W + 3) : 8;
-  if (fcol < RI_W) {
+  // R_q of the i-faces (face columns i0 .. i0+32, rows j0-2 .. j0+OJ+1): eight tasks (quantity q, half of the face rows) of 32
+  // columns each, one per warp (lane = column: conflict free), on the warps before the last one; the last warp takes the 33rd
+  // column (4 RI_H values)
+  const int wrp = tid >> 5, lane = tid & 31;
+  constexpr int NW = NT / 32, RW = NW - 1 < 8 ? NW - 1 : 8;
+  if (wrp < RW) {
     constexpr int HALF = (RI_H + 1) / 2;
-    for (int grp = tid / (RI_W + 3); grp < 8; grp += NG) {
+    for (int grp = wrp; grp < 8; grp += RW) {
       const int q = grp >> 1, frow0 = (grp & 1) * HALF, nrow = (grp & 1) ? RI_H - HALF : HALF;
       // (restrict: source arrays and R buffer are disjoint parts of shared memory; without it every store orders the loads of the
       //  next row behind it and the loop runs one shared-memory latency per row)
-      const real* __restrict__ src = t.arr(A_U + q) + (fcol + H) + (frow0 + 1) * PI;  // face (i0 + fcol, j0 - 2 + frow0)
-      real* __restrict__ dst = t.RB() + q * RQ + frow0 * RI_W + fcol;
+      const real* __restrict__ src = t.arr(A_U + q) + (lane + H) + (frow0 + 1) * PI;  // face (i0 + lane, j0 - 2 + frow0)
+      real* __restrict__ dst = t.RB() + q * RQ + frow0 * RI_W + lane;
       real rv[HALF];
 #pragma unroll
       for (int n = 0; n < HALF; ++n)
@@ -399,6 +410,11 @@ BC_HD void phase1(const TileCtx& t, int tid, const SensGeom& G0, const SensGeom&
 #pragma unroll
       for (int n = 0; n < HALF; ++n)
         if (n < nrow) dst[n * RI_W] = rv[n];
+    }
+  } else if (wrp == NW - 1) {
+    for (int idx = lane; idx < 4 * RI_H; idx += 32) {
+      const int q = idx / RI_H, frow = idx % RI_H;
+      t.RB()[q * RQ + frow * RI_W + OI] = rrow(t.arr(A_U + q) + (OI + H) + (frow + 1) * PI, 1);
     }
   }
 }
@@ -433,21 +449,31 @@ BC_HD void phase1b(const TileCtx& t, int tid) {
 // R_q of the j-faces (columns i0-2 .. i0+33, rows j0 .. j0+8): thread (fcol = tid % 36, grp = tid / 36) owns quantity grp/2
 // and five (even grp) or four (odd grp) consecutive face rows, sliding along j
 BC_HD void phase_rj(const TileCtx& t, int tid) {
-  const int fcol = tid % RJ_W;
-  constexpr int NG = NT / RJ_W < 8 ? NT / RJ_W : 8;
+  // warp-aligned like the R_q of the i-faces: (quantity, half of the rows) x 32 columns per warp, the four remaining columns
+  // (i0+30 .. i0+33) on the last warp
+  const int wrp = tid >> 5, lane = tid & 31;
+  constexpr int NW = NT / 32, RW = NW - 1 < 8 ? NW - 1 : 8;
   constexpr int HALF = (RJ_H + 1) / 2;
-  if (tid / RJ_W >= NG) return;
-  for (int grp = tid / RJ_W; grp < 8; grp += NG) {
-    const int q = grp >> 1, frow0 = (grp & 1) * HALF, nrow = (grp & 1) ? RJ_H - HALF : HALF;
-    const real* __restrict__ src = t.arr(A_U + q) + (fcol + 1) + (frow0 + H) * PI;  // face (i0 - 2 + fcol, j0 + frow0)
-    real* __restrict__ dst = t.RB() + q * RQ + frow0 * RJ_W + fcol;
-    real col[HALF + 3];   // the column of the source array this thread slides along: all loads first
+  if (wrp < RW) {
+    for (int grp = wrp; grp < 8; grp += RW) {
+      const int q = grp >> 1, frow0 = (grp & 1) * HALF, nrow = (grp & 1) ? RJ_H - HALF : HALF;
+      const real* __restrict__ src = t.arr(A_U + q) + (lane + 1) + (frow0 + H) * PI;  // face (i0 - 2 + lane, j0 + frow0)
+      real* __restrict__ dst = t.RB() + q * RQ + frow0 * RJ_W + lane;
+      real col[HALF + 3];   // the column of the source array this thread slides along: all loads first
 #pragma unroll
-    for (int n = 0; n < HALF + 3; ++n)
-      if (n < nrow + 3) col[n] = src[(n - 2) * PI];
+      for (int n = 0; n < HALF + 3; ++n)
+        if (n < nrow + 3) col[n] = src[(n - 2) * PI];
 #pragma unroll
-    for (int n = 0; n < HALF; ++n)
-      if (n < nrow) dst[n * RJ_W] = 9.0 * (col[n + 1] + col[n + 2]) - (col[n] + col[n + 3]);
+      for (int n = 0; n < HALF; ++n)
+        if (n < nrow) dst[n * RJ_W] = 9.0 * (col[n + 1] + col[n + 2]) - (col[n] + col[n + 3]);
+    }
+  } else if (wrp == NW - 1) {
+    constexpr int XC = RJ_W - 32;   // 4
+    for (int idx = lane; idx < 4 * RJ_H * XC; idx += 32) {
+      const int q = idx / (RJ_H * XC), rem = idx % (RJ_H * XC), frow = rem / XC, fcol = 32 + rem % XC;
+      const real* src = t.arr(A_U + q) + (fcol + 1) + (frow + H) * PI;
+      t.RB()[q * RQ + frow * RJ_W + fcol] = 9.0 * (src[-PI] + src[0]) - (src[-2 * PI] + src[PI]);
+    }
   }
 }
 
