@@ -533,12 +533,26 @@ def main():
         # slab k-1 overlap on three streams).  Every slab's gh halo columns come straight from the HOST array (which holds the
         # rank's columns plus its halo columns, as a rank of the reference's host would hold them), so no device exchange is needed.
         from broadcast_b200.resident import StreamedBlock
-        nslab = int(os.environ.get("BROADCAST_B200_E2E_SLABS", "8" if world == 1 else "4"))
-        sb = StreamedBlock(gcase_e2e, nslab=nslab * world, device=dev, first=rank * nslab, count=nslab)
+        nslab = int(os.environ.get("BROADCAST_B200_E2E_SLABS", "16" if world == 1 else "4"))
+        # one GPU: slab widths doubling from both ends towards the middle, so that the first device-to-host copy starts after a
+        # short upload and the step ends with a short download (BROADCAST_B200_E2E_TAPER=0: even slabs)
+        bounds = None
+        rows_mode = world == 1 and os.environ.get("BROADCAST_B200_E2E_ROWS", "1") == "1"
+        if rows_mode:
+            # one GPU: pipeline over ROW windows, every host-link copy one contiguous run per plane (resident.RowStreamedBlock;
+            # the pitched copies of the i-slab pipeline reach 29.6 GB/s each way with both directions busy, contiguous ones 43)
+            from broadcast_b200.resident import RowStreamedBlock
+            sb = RowStreamedBlock(gcase_e2e, nwin=nslab, device=dev)
+            api = ("broadcast_b200.resident.RowStreamedBlock.step_from_host (pinned host w in, residual out, " + str(nslab) +
+                   " pipelined row windows with contiguous host-link copies; mesh metrics resident)")
+        else:
+            if world == 1 and os.environ.get("BROADCAST_B200_E2E_TAPER", "1") == "1":
+                bounds = StreamedBlock.tapered_bounds(gcase_e2e.im, nslab)
+            sb = StreamedBlock(gcase_e2e, nslab=nslab * world, device=dev, first=rank * nslab, count=nslab, bounds=bounds)
+            api = ("broadcast_b200.resident.StreamedBlock.step_from_host per rank (pinned host w in, residual out, " + str(nslab) +
+                   " pipelined i-slabs per GPU" + (", widths tapered towards both ends" if bounds else "") + "; mesh metrics resident)")
         run = lambda: sb.step_from_host(wp, rp)
         h2d, d2h = sb.bytes_per_step()
-        api = ("broadcast_b200.resident.StreamedBlock.step_from_host per rank (pinned host w in, residual out, " + str(nslab) +
-               " pipelined i-slabs per GPU; mesh metrics resident)")
         for _ in range(2):
             run()
         barrier()
@@ -551,6 +565,12 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": cells_global / float(dt[0]), "unit": "cell-updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": float(dt[0]) * 1e3, "api": api, "host_numa_node": numa}
+        if world == 1:
+            # what came back through the host buffers is the resident step's residual, bit for bit (same checksum as above)
+            gh_ = case.gh
+            hb = rp[:, gh_:gh_ + case.jm, gh_:gh_ + case.im].contiguous().view(torch.int64).sum()
+            e2e["result_bits_sum_i64"] = int(hb.item())
+            e2e["result_matches_resident"] = bool(int(hb.item()) == checksum["res_bits_sum_i64"])
 
     if rank == 0:
         line = {

@@ -235,19 +235,39 @@ class StreamedBlock:
     device-to-host copy of slab k-1's residual overlap the boundary fill + residual kernels of slab k (three streams,
     both copy engines busy).  Same results as ``Block.step_from_host`` (slab-internal edges compute their gradients)."""
 
-    def __init__(self, case: Case, nslab: int = 8, device="cuda:0", first: int = 0, count: int = None):
+    @staticmethod
+    def tapered_bounds(im: int, nslab: int, unit: int = 32):
+        """column boundaries of ``nslab`` slabs whose widths double from both ends towards the middle (multiples of ``unit``): the
+        step then starts its first device-to-host copy after a SHORT first upload and ends with a SHORT last download -- with even
+        slabs the pipeline costs (nslab + 1) slab transfers, one of them with only one direction of the link busy at each end"""
+        half = nslab // 2
+        w = [2 ** min(k, nslab - 1 - k) for k in range(nslab)]
+        # cap the doubling so that the widest slabs are at most ~4x the even width (device memory per slab, pipeline granularity)
+        cap = max(1, 4 * sum(w) // nslab) if nslab > 2 else max(w)
+        w = [min(x, cap) for x in w]
+        tot = sum(w)
+        cols = [max(unit, int(round(im * x / tot / unit)) * unit) for x in w]
+        cols[half] += im - sum(cols)                      # the remainder goes to a middle slab
+        if cols[half] < unit or any(c < 2 * 3 + 1 for c in cols):
+            return None
+        b = [0]
+        for c in cols:
+            b.append(b[-1] + c)
+        return b
+
+    def __init__(self, case: Case, nslab: int = 8, device="cuda:0", first: int = 0, count: int = None, bounds=None):
         """``first`` / ``count``: this object drives only the slabs first .. first+count-1 of the ``nslab`` slabs of ``case`` (one
         rank of a multi-GPU run pipelining ITS part of the block: the host arrays then hold the columns of those slabs plus gh
-        halo columns on each side, i.e. the rank's own slab image)."""
+        halo columns on each side, i.e. the rank's own slab image).  ``bounds``: uneven slab boundaries (``tapered_bounds``)."""
         from . import sharding
         self.case, self.device = case, torch.device(device)
         self.gh, self.im, self.jm = case.gh, case.im, case.jm
         count = nslab - first if count is None else count
-        self.col0 = sharding.slab_range(case.im, first, nslab)[0] - 1     # storage column of the host arrays' first column
+        self.col0 = sharding.slab_range(case.im, first, nslab, bounds)[0] - 1     # storage column of the host arrays' first column
         self.slabs = []
         for k in range(first, first + count):
-            sl, desc = sharding.slab_of(case, k, nslab)
-            lo, hi = sharding.slab_range(case.im, k, nslab)
+            sl, desc = sharding.slab_of(case, k, nslab, bounds)
+            lo, hi = sharding.slab_range(case.im, k, nslab, bounds)
             self.slabs.append((Block(sl, device, slab=desc if nslab > 1 else None), lo - self.col0, hi - self.col0))
         # one stream per ROLE (host-to-device copies, kernels, device-to-host copies) and one event pair per slab: the H2D queue
         # never waits behind a D2H copy, both copy engines stay busy for the whole step (measured: 45.9 GB/s each way at once)
@@ -289,6 +309,76 @@ class StreamedBlock:
             self.s_out.wait_event(self.ev_k[k])
             dst = res_pinned.data_ptr() + (lo - 1 + gh) * 8                   # owned columns only
             _lib.check(self.lib.bcd_memcpy2d(VP(dst), LL(ni * 8), VP(b.res.data_ptr() + gh * 8), LL(nl * 8), LL(b.im * 8), LL(rows), 2,
+                                             VP(self.s_out.cuda_stream)), "bcd_memcpy2d")
+        main.wait_stream(self.s_out)
+        main.synchronize()
+
+
+class RowStreamedBlock:
+    """Plugin-level residual step on HOST buffers pipelined over row windows of the block: ``nwin`` windows in j, so that every
+    host-link transfer is CONTIGUOUS -- rows are the slow index of the Fortran planes: a window is one run of memory per plane, five
+    runs per copy, where an i-slab is 10 270 pitched rows of 8 KB.  Measured on B200 (profiles/r2_c_summary.md): with both directions
+    busy the pitched copies of ``StreamedBlock`` move 29.6 GB/s each way, contiguous ones 43 GB/s.
+    Window k owns the output rows [a, b]; it is computed on the rows [a - M, b + M] (clipped to the block; M = ``margin``) plus gh
+    ghost rows that arrive with the same copy, as a block of its
+    own (``sharding.row_window_of``: clipped boundary list, ``_nowall`` scheme away from the wall).  Only the owned rows travel back.
+    Same result as ``Block.step_from_host``, bit for bit (tests/test_parity_gpu.py)."""
+
+    def __init__(self, case: Case, nwin: int = 8, device="cuda:0", margin: int = 2, taper: bool = False):
+        """``margin``: rows computed beyond the owned ones on a cut side: at least TWO (the sensor gradient of a cut window's first
+        ghost row is extrapolated, which reaches the two outermost rows: a margin of one row is NOT bit-identical on the GPU,
+        margins 2 and gh + 2 are, tests/test_parity_gpu.py).  ``taper``: window heights doubling from both ends towards the middle
+        (short first upload, short last download); measured slower than even windows at C5 (18.5 vs 17.7 ms: the thin end windows
+        cost more than the shorter fill and drain save), so off by default."""
+        from . import sharding
+        self.case, self.device = case, torch.device(device)
+        self.gh, self.im, self.jm = case.gh, case.im, case.jm
+        M = int(margin)
+        if M < 2:
+            raise ValueError("a cut window needs a margin of at least two rows")
+        bounds = StreamedBlock.tapered_bounds(case.jm, nwin, unit=8) if (taper and nwin > 2) else None
+        self.wins = []
+        for k in range(nwin):
+            a, b = sharding.slab_range(case.jm, k, nwin, bounds)
+            la, lb = max(1, a - M), min(case.jm, b + M)
+            self.wins.append((Block(sharding.row_window_of(case, la, lb), device), a, b, la, lb))
+        self.s_in, self.s_k, self.s_out = (torch.cuda.Stream(device=self.device) for _ in range(3))
+        self.ev_in = [torch.cuda.Event() for _ in range(nwin)]
+        self.ev_k = [torch.cuda.Event() for _ in range(nwin)]
+        self.lib = _lib.lib()
+
+    def bytes_per_step(self):
+        ni = self.im + 2 * self.gh
+        h2d = sum((lb - la + 1 + 2 * self.gh) * ni * 5 * 8 for _, _, _, la, lb in self.wins)
+        d2h = sum((b - a + 1) * ni * 5 * 8 for _, a, b, _, _ in self.wins)
+        return h2d, d2h
+
+    def step_from_host(self, w_pinned: torch.Tensor, res_pinned: torch.Tensor):
+        """``w_pinned`` / ``res_pinned``: pinned host tensors (5, jm+2gh, im+2gh) = memory image of the Fortran arrays.  The rows
+        1 .. jm of ``res_pinned`` are written (all columns; the ghost columns receive the zeros of the device buffer)."""
+        gh, nj, ni = self.gh, self.jm + 2 * self.gh, self.im + 2 * self.gh
+        main = torch.cuda.current_stream(self.device)
+        for s in (self.s_in, self.s_k, self.s_out):
+            s.wait_stream(main)
+        LL, VP = ctypes.c_longlong, ctypes.c_void_p
+        plane = nj * ni * 8
+        for k, (blk, a, b, la, lb) in enumerate(self.wins):      # all host-to-device copies, back to back
+            nr = lb - la + 1 + 2 * gh                           # storage rows la-1 .. lb+2gh-1 of every plane: one run of memory
+            src = w_pinned.data_ptr() + (la - 1) * ni * 8
+            _lib.check(self.lib.bcd_memcpy2d(_p(blk.w), LL(nr * ni * 8), VP(src), LL(plane), LL(nr * ni * 8), LL(5), 1,
+                                             VP(self.s_in.cuda_stream)), "bcd_memcpy2d")
+            self.ev_in[k].record(self.s_in)
+        for k, (blk, a, b, la, lb) in enumerate(self.wins):
+            self.s_k.wait_event(self.ev_in[k])
+            with torch.cuda.stream(self.s_k):
+                blk.apply_bcs()
+                blk.residual()
+            self.ev_k[k].record(self.s_k)
+            self.s_out.wait_event(self.ev_k[k])
+            nr = lb - la + 1 + 2 * gh
+            src = blk.res.data_ptr() + (a - la + gh) * ni * 8                 # owned rows only
+            dst = res_pinned.data_ptr() + (a - 1 + gh) * ni * 8
+            _lib.check(self.lib.bcd_memcpy2d(VP(dst), LL(plane), VP(src), LL(nr * ni * 8), LL((b - a + 1) * ni * 8), LL(5), 2,
                                              VP(self.s_out.cuda_stream)), "bcd_memcpy2d")
         main.wait_stream(self.s_out)
         main.synchronize()

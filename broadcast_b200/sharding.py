@@ -18,23 +18,30 @@ import numpy as np
 from .cases import Case
 
 
-def slab_range(im: int, rank: int, world: int):
-    """global (1-based, inclusive) column range [lo, hi] owned by ``rank``"""
+def slab_range(im: int, rank: int, world: int, bounds=None):
+    """global (1-based, inclusive) column range [lo, hi] owned by ``rank``; ``bounds`` (world + 1 increasing column counts from 0 to
+    im) replaces the even split (the tapered pipeline of resident.StreamedBlock)"""
+    if bounds is not None:
+        if len(bounds) != world + 1 or bounds[0] != 0 or bounds[-1] != im or any(b <= a for a, b in zip(bounds[:-1], bounds[1:])):
+            raise ValueError("bounds must be world + 1 increasing column counts from 0 to im")
+        return int(bounds[rank]) + 1, int(bounds[rank + 1])
     base, rem = divmod(im, world)
     lo = rank * base + min(rank, rem) + 1
     n = base + (1 if rank < rem else 0)
     return lo, lo + n - 1
 
 
-def slab_of(case: Case, rank: int, world: int):
+def slab_of(case: Case, rank: int, world: int, bounds=None):
     """The i-slab of ``case`` owned by ``rank`` as a Case of its own (local indices), with its gh halo columns, plus the
     slab descriptor (ioff, im_global, edges) the device entry points need (include/broadcast_b200.h, bcd_slab_begin)."""
     if world == 1:
         return case, (0, case.im, 0)
     gh, im, jm = case.gh, case.im, case.jm
     if case.periodic_i:
+        if bounds is not None:
+            raise NotImplementedError("uneven slabs of an i-periodic block")
         return _periodic_slab_of(case, rank, world)
-    lo, hi = slab_range(im, rank, world)
+    lo, hi = slab_range(im, rank, world, bounds)
     n = hi - lo + 1
     if n < 2 * gh + 1:
         raise ValueError(f"slab of {n} columns is narrower than the stencil ({2 * gh + 1}): use fewer ranks")
@@ -70,6 +77,48 @@ def slab_of(case: Case, rank: int, world: int):
               vol=F(case.vol[cs]), volf=F(case.volf[cs]), w=F(case.w[cs]), bcs=bcs, periodic_i=False, scheme=case.scheme)
     edges = (0 if first else 1) | (0 if last else 2)
     return sl, (lo - 1, im, edges)
+
+
+def row_window_of(case: Case, la: int, lb: int):
+    """Rows la .. lb (1-based, inclusive) of ``case`` as a Case of their own: a window in j.  Its gh ghost rows on a cut side hold
+    the parent's real rows (the caller copies them in), the boundary list is clipped to the window and re-expressed in local rows,
+    and a window that does not start at the wall runs the ``_nowall`` form of the scheme.  The kernels treat a j-cut like a physical
+    side without a fill (sensor gradients of the first ghost row extrapolated), so the residual of the FIRST and LAST rows of a cut
+    window differs from the parent's: callers keep a margin of at least one row (resident.RowStreamedBlock) and use the rows
+    inside it, which are bit-identical to the parent's."""
+    gh, im, jm = case.gh, case.im, case.jm
+    if case.periodic_i:
+        raise NotImplementedError("row windows of an i-periodic block")
+    if not (1 <= la <= lb <= jm):
+        raise ValueError("row window out of range")
+    n = lb - la + 1
+    first, last = la == 1, lb == jm
+    cs = (slice(None), slice(la - 1, lb + 2 * gh))          # storage rows of cell rows la-gh .. lb+gh
+    ns = (slice(None), slice(la - 1, lb + 2 * gh + 1))
+    F = np.asfortranarray
+    bcs = []
+    for bc in case.bcs:
+        kind = bc[0]
+        itf = np.array(bc[2], dtype=float)
+        if kind == "inflow":           # Ilo, rows 1 .. jm: the window's rows, table rows sliced
+            it = itf.copy(); it[0, 1] = 1; it[1, 1] = n
+            bcs.append((kind, bc[1], F(it), F(bc[3][la - 1:lb])))
+        elif kind == "outflow":        # Ihi, rows 1 .. jm + gh (corner ownership of the top ghost rows)
+            it = itf.copy(); it[0, 1] = 1; it[1, 1] = n + gh if last else n
+            bcs.append((kind, bc[1], F(it)))
+        elif kind == "noref":          # Jhi
+            if last:
+                it = itf.copy(); it[0, 1] = n; it[1, 1] = n
+                bcs.append((kind, bc[1], F(it), bc[3]))
+        elif kind == "wall":           # Jlo
+            if first:
+                bcs.append(bc)
+        else:
+            raise NotImplementedError(kind)
+    scheme = case.scheme if first else case.scheme.replace("_2d", "_nowall_2d") if "nowall" not in case.scheme else case.scheme
+    return Case(name=f"{case.name}_rows{la}to{lb}", im=im, jm=n, gh=gh, phys=case.phys, k2=case.k2, k4=case.k4,
+                x0=F(case.x0[ns]), y0=F(case.y0[ns]), nx=F(case.nx[ns]), ny=F(case.ny[ns]), xc=F(case.xc[cs]), yc=F(case.yc[cs]),
+                vol=F(case.vol[cs]), volf=F(case.volf[cs]), w=F(case.w[cs]), bcs=bcs, periodic_i=False, scheme=scheme)
 
 
 def _periodic_slab_of(case: Case, rank: int, world: int):

@@ -524,6 +524,37 @@ def test_streamed_host_step_matches_resident_block(gpu):
     a, b = r1[:, gh:-gh, gh:-gh], r2[:, gh:-gh, gh:-gh]
     assert (a - b).abs().max().item() <= 1e-13 * a.abs().max().item()
     assert a.abs().max().item() > 0
+    # tapered slabs (short first upload / last download): same residual as the even split, bit for bit
+    bounds = [0, 10, 30, 70, 110, 122, 130]
+    r3 = torch.zeros(blk.w.shape, dtype=torch.float64).pin_memory()
+    StreamedBlock(g, nslab=6, bounds=bounds).step_from_host(wp, r3)
+    assert torch.equal(r3[:, gh:-gh, gh:-gh], b)
+    tb = StreamedBlock.tapered_bounds(8192, 8)
+    assert tb[0] == 0 and tb[-1] == 8192 and all(w % 32 == 0 for w in np.diff(tb)) and tb[1] < 8192 // 8
+
+
+@pytest.mark.parametrize("im,jm,nwin,margin,taper", [(130, 120, 3, 2, False), (64, 97, 4, 2, False), (70, 40, 1, 2, False),
+                                                     (96, 200, 6, 2, True), (64, 128, 8, 5, True), (40, 300, 9, 3, False)])
+def test_row_streamed_host_step_is_bit_identical(gpu, im, jm, nwin, margin, taper):
+    """host step pipelined over ROW windows (contiguous host-link copies, windows computed with a margin of gh + 2 rows as blocks of
+    their own: wall rows only in the first, top fill only in the last, clipped side fills) == the single-block host step, bit for bit"""
+    import torch
+    from broadcast_b200.resident import Block, RowStreamedBlock
+    g = H.make_case("bl", im, jm, gpu, with_w=True)
+    blk = Block(g)
+    wp = torch.empty(blk.w.shape, dtype=torch.float64).pin_memory()
+    wp.copy_(blk.w.cpu())
+    r1 = torch.zeros(blk.w.shape, dtype=torch.float64).pin_memory()
+    r2 = torch.full(blk.w.shape, 7.0, dtype=torch.float64).pin_memory()
+    blk.step_from_host(wp, r1)
+    rb = RowStreamedBlock(g, nwin=nwin, margin=margin, taper=taper)
+    rb.step_from_host(wp, r2)
+    gh = g.gh
+    assert torch.equal(r1[:, gh:-gh, gh:-gh], r2[:, gh:-gh, gh:-gh])
+    assert r1[:, gh:-gh, gh:-gh].abs().max().item() > 0
+    assert bool((r2[:, :gh] == 7.0).all()) and bool((r2[:, -gh:] == 7.0).all())     # ghost rows of the host array untouched
+    rb.step_from_host(wp, r2)                                                         # a second step on the same object
+    assert torch.equal(r1[:, gh:-gh, gh:-gh], r2[:, gh:-gh, gh:-gh])
 
 
 def test_csr_row_blocks_and_petsc_file(gpu, tmp_path):
