@@ -52,8 +52,8 @@ int check_scheme(int order, int gh, int jm, bool wall) {
   return BC_OK;
 }
 
-// host-API device buffers (scratch slots >= 10)
-enum { S_W = 10, S_WD, S_RES, S_NX, S_NY, S_VOL, S_VOLF, S_AUX, S_AUX2, S_SEG, S_IA, S_JA, S_OUT10, S_GEOM };
+// host-API device buffers (scratch slots >= 100: disjoint from the slots the device loops use, 0-3 / 20-22 / 30 / 40)
+enum { S_W = 100, S_WD, S_RES, S_NX, S_NY, S_VOL, S_VOLF, S_AUX, S_AUX2, S_SEG, S_IA, S_JA, S_OUT10, S_GEOM };
 
 template <class T>
 T* dbuf(int slot, size_t count) {
