@@ -94,46 +94,37 @@ __global__ void __launch_bounds__(JT_I* JT_J, MINB)
   const int bi0 = blockIdx.x * JT_I + rc.i0, bj0 = blockIdx.y * JT_J + rc.j0;
   const double* pI = pkg + (long long)FPK_VS * g.sc;
   const double* pJ = pkg + (long long)(FPK_N + FPK_VS) * g.sc;
-  // staging: eight loads in flight per thread before the first store (the loop was load -> store, one latency per element)
-  constexpr int NTH = JT_I * JT_J, UNR = 8;
+  // staging by asynchronous copies straight into shared memory (LDGSTS): every copy of a thread is in flight at once and no
+  // register holds staged data (r2_c; the register-staged loop -- eight loads, then eight stores -- held 8 % of the kernel's stall
+  // samples on its first store, ncu r2_30)
+  constexpr int NTH = JT_I * JT_J;
   {
     constexpr int NI = FPK_NVS * JT_J * (JT_I + 1);
-    for (int base = tid; base < NI; base += NTH * UNR) {
-      double v[UNR];
-#pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        const int idx = base + u * NTH;
-        v[u] = 0.0;
-        if (idx < NI) {
-          const int k = idx / (JT_J * (JT_I + 1)), r = idx % (JT_J * (JT_I + 1));
-          const int fi = bi0 + r % (JT_I + 1), fj = bj0 + r / (JT_I + 1);
-          if (fi <= rc.i1 + 1 && fj <= rc.j1) v[u] = __ldg(pI + k * g.sc + g.cidx(fi, fj));
-        }
+    for (int idx = tid; idx < NI; idx += NTH) {
+      const int k = idx / (JT_J * (JT_I + 1)), r = idx % (JT_J * (JT_I + 1));
+      const int fi = bi0 + r % (JT_I + 1), fj = bj0 + r / (JT_I + 1);
+      if (fi <= rc.i1 + 1 && fj <= rc.j1) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(sI + idx);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(pI + k * g.sc + g.cidx(fi, fj)) : "memory");
+      } else {
+        sI[idx] = 0.0;
       }
-#pragma unroll
-      for (int u = 0; u < UNR; ++u)
-        if (base + u * NTH < NI) sI[base + u * NTH] = v[u];
     }
   }
   {
     constexpr int NJ = FPK_NVS * (JT_J + 1) * JT_I;
-    for (int base = tid; base < NJ; base += NTH * UNR) {
-      double v[UNR];
-#pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        const int idx = base + u * NTH;
-        v[u] = 0.0;
-        if (idx < NJ) {
-          const int k = idx / ((JT_J + 1) * JT_I), r = idx % ((JT_J + 1) * JT_I);
-          const int fi = bi0 + r % JT_I, fj = bj0 + r / JT_I;
-          if (fi <= rc.i1 && fj <= rc.j1 + 1) v[u] = __ldg(pJ + k * g.sc + g.cidx(fi, fj));
-        }
+    for (int idx = tid; idx < NJ; idx += NTH) {
+      const int k = idx / ((JT_J + 1) * JT_I), r = idx % ((JT_J + 1) * JT_I);
+      const int fi = bi0 + r % JT_I, fj = bj0 + r / JT_I;
+      if (fi <= rc.i1 && fj <= rc.j1 + 1) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(sJ + idx);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(pJ + k * g.sc + g.cidx(fi, fj)) : "memory");
+      } else {
+        sJ[idx] = 0.0;
       }
-#pragma unroll
-      for (int u = 0; u < UNR; ++u)
-        if (base + u * NTH < NJ) sJ[base + u * NTH] = v[u];
     }
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int i = bi0 + tx, j = bj0 + ty;
@@ -215,14 +206,17 @@ cudaError_t launch_jacobian_faces(const GridDesc& g, const SchemeArgs& a, const 
       else kern<<<grd, blk2, smem, st>>>(g, c, f, rc, pkg, values, coefdiag, nullptr, 0.0);
       return cudaGetLastError();
     };
-    if (counts) e = go(k_jac_assemble_rt<27, 2, true>, 27, true);
+    // default since r2_c: 33 staged fields (FPK_LS: the along-line / face-value fields too, 77 KB, two CTAs per SM), 255 registers
+    static const bool st27 = cfg == 6;
+    if (counts) e = st27 ? go(k_jac_assemble_rt<27, 2, true>, 27, true) : go(k_jac_assemble_rt<FPK_LS, 2, true>, FPK_LS, true);
+    else if (cfg == 5) e = go(k_jac_assemble_rt<FPK_LS, 2>, FPK_LS);
     else
     if (cfg == 1) e = go(k_jac_assemble_rt<35, 4>, 35);        // 19 staged fields, 128 registers, 16 warps per SM
     else if (cfg == 2) e = go(k_jac_assemble_rt<40, 4>, 40);   // 14 staged fields, 128 registers
     else if (cfg == 3) e = go(k_jac_assemble_rt<40, 5>, 40);   // 14 staged fields, 96 registers, 20 warps per SM
     else if (cfg == 4) e = go(k_jac_assemble_rt<35, 3>, 35);   // 19 staged fields, 168 registers
     else if (cfg == 0) e = go(k_jac_assemble_rt<27, 3>, 27);   // 27 staged fields, 168 registers, 12 warps per SM
-    else e = go(k_jac_assemble_rt<27, 2>, 27);                 // DEFAULT: 27 staged fields, 255 registers (no spills), 8 warps per SM
+    else e = go(k_jac_assemble_rt<27, 2>, 27);                 // cfg 6 (the r1 / r2_b default): 27 staged fields, 255 registers, 8 warps per SM
     // measured at 4096x1024 (profiles/r1_g_summary.md, r1_h): 12.17 ms (168 registers) vs 11.43 ms (255 registers)
     if (e != cudaSuccess) return e;
   }

@@ -32,12 +32,16 @@ namespace bcast {
 constexpr int JAC_NSLOT = 29;
 constexpr int FPK_N = 54;
 enum {
-  FPK_RSE2 = 0,   // rspec * eps2
-  FPK_RSE4 = 1,   // rspec * eps4
-  FPK_SD = 2,     // [5] eps2 diff_e + eps4 pred_e              (x d rspec)
-  FPK_DRS = 7,    // [2][5] d rspec / d w_m of along-cells -1, 0
-  FPK_DEP = 17,   // [4] d eps2 / d p(s), s = -2..1
-  FPK_DET = 21,   // [2] d eps2 / d T(s), s = -1, 0
+  // fields only the two or four column cells next to the face read (rare: they stay in global memory)
+  FPK_SD = 0,     // [5] eps2 diff_e + eps4 pred_e              (x d rspec)
+  FPK_DRS = 5,    // [2][5] d rspec / d w_m of along-cells -1, 0
+  FPK_DEP = 15,   // [4] d eps2 / d p(s), s = -2..1
+  FPK_DET = 19,   // [2] d eps2 / d T(s), s = -1, 0
+  // fields the six cells of the face's along-line / the four cells of its face-value row read: staged too since r2_c (FPK_LS:
+  // the compiler hoists their loads above the slot's branches, ~130 of the ~460 package loads per cell were these six fields)
+  FPK_LS = 21,
+  FPK_RSE2 = 21,  // rspec * eps2
+  FPK_RSE4 = 22,  // rspec * eps4
   FPK_V1M = 23, FPK_V2M = 24, FPK_V3M = 25, FPK_V4M = 26,  // visc_e / mmu
   // "staged subset": the 27 fields that many column cells of a face's stencil read (14 of its 22 cells read SE and DEG, all
   // 20 cells of the viscous box read the last 14); the assembly kernel stages them in shared memory
@@ -520,7 +524,7 @@ BC_HD void face_contrib_rt(const FC& f, const FaceTab& t, const SchemeConsts& c,
     acc.gT[4] -= c.cpprandtl * ep;
   }
   if (t.flags & FT_C0) {
-    const double v1m = f(FPK_V1M), v2m = f(FPK_V2M), v3m = f(FPK_V3M), v4m = f(FPK_V4M);
+    const double v1m = f.v(FPK_V1M), v2m = f.v(FPK_V2M), v3m = f.v(FPK_V3M), v4m = f.v(FPK_V4M);
     const double k = sgn * t.c0;
     const double km = k * f.v(FPK_MMU);
     acc.gU[4] -= km * v1m;
@@ -534,7 +538,7 @@ BC_HD void face_contrib_rt(const FC& f, const FaceTab& t, const SchemeConsts& c,
   if (t.flags & FT_LINE) {
     acc.Nx += sgn * t.cE * nxf;
     acc.Ny += sgn * t.cE * nyf;
-    acc.diag -= sgn * (f(FPK_RSE2) * t.dd + f(FPK_RSE4) * t.dp);
+    acc.diag -= sgn * (f.v(FPK_RSE2) * t.dd + f.v(FPK_RSE4) * t.dp);
   }
   if (t.side >= 0 || t.pk >= 0 || (t.flags & FT_SENS)) {
     double se[5];
