@@ -195,3 +195,43 @@ def test_periodic_slabs_and_exchange_gloo(world, ref):
     assert len(out) == world
     for r in range(world):
         assert out[r] < 1e-13, (r, out[r])
+
+
+def test_row_windows_reproduce_the_block_residual_on_the_oracle(ref):
+    """sharding.row_window_of (the windows of resident.RowStreamedBlock): every window run as a block of its own on the ORACLE -- fills
+    of its clipped boundary list, `_nowall` scheme away from the wall -- gives, inside a margin of two rows, exactly the rows of the
+    whole-block residual (and a margin of zero rows does not: the cut is visible in the outermost rows)"""
+    im, jm = 36, 64
+    c = H.make_case("bl", im, jm, ref, with_w=True)
+    gh = c.gh
+    w, res = H.residual_sequence(ref, c)
+    M = 2
+    seen = np.zeros(jm, dtype=bool)
+    for a, b in [(1, 20), (21, 45), (46, 64)]:
+        la, lb = max(1, a - M), min(jm, b + M)
+        wc = sharding.row_window_of(c, la, lb)
+        assert wc.jm == lb - la + 1 and ("nowall" in wc.scheme) == (la != 1)
+        kinds = [bc[0] for bc in wc.bcs]
+        assert ("wall" in kinds) == (la == 1) and ("noref" in kinds) == (lb == jm) and "inflow" in kinds and "outflow" in kinds
+        # the window's state = the parent's rows (ghost rows of a cut side hold real rows), as the host copy delivers them
+        wc.w[:] = c.w[:, la - 1:lb + 2 * gh]
+        ww, rw = H.residual_sequence(ref, wc, wc.scheme)
+        own = slice(gh + (a - la), gh + (a - la) + (b - a + 1))
+        assert np.array_equal(rw[gh:-gh, own], res[gh:-gh, gh + a - 1:gh + b])
+        seen[a - 1:b] = True
+        if la != 1:   # without the margin the first row of a cut window differs
+            assert not np.array_equal(rw[gh:-gh, gh], res[gh:-gh, gh + la - 1])
+    assert seen.all()
+
+
+def test_slab_bounds_and_tapered_widths():
+    from broadcast_b200.resident import StreamedBlock
+    b = StreamedBlock.tapered_bounds(8192, 8)
+    assert b[0] == 0 and b[-1] == 8192 and len(b) == 9
+    w = np.diff(b)
+    assert all(x % 32 == 0 for x in w) and w[0] < w[3] and w[-1] < w[4] and list(w[:4]) == sorted(w[:4])
+    for k in range(8):
+        lo, hi = sharding.slab_range(8192, k, 8, b)
+        assert (lo, hi) == (b[k] + 1, b[k + 1])
+    with pytest.raises(ValueError):
+        sharding.slab_range(100, 0, 2, [0, 60, 90])
