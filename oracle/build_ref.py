@@ -113,7 +113,7 @@ def expand_includes(path: str, incdir: str, depth: int = 0) -> str:
     return "".join(out)
 
 
-def build(verbose: bool = True) -> bool:
+def build(verbose: bool = True, force: bool = False) -> bool:
     if not have_reference():
         if verbose:
             print(f"[oracle/_ref] reference tree {REF} absent: keeping prebuilt files, nothing to do")
@@ -122,6 +122,21 @@ def build(verbose: bool = True) -> bool:
     import f90_to_c
 
     os.makedirs(OUT, exist_ok=True)
+    # up to date?  stamp = the file list, the translator and this recipe (contents), the reference sources (size + mtime)
+    import hashlib
+    h = hashlib.sha256()
+    h.update(repr(FILES).encode())
+    for src in (os.path.join(HERE, "f90_to_c.py"), os.path.abspath(__file__)):
+        h.update(open(src, "rb").read())
+    for p, _ in FILES:
+        st = os.stat(os.path.join(REF, p[4:] if p.startswith("cpp:") else p))
+        h.update(f"{p}:{st.st_size}:{int(st.st_mtime)}".encode())
+    stamp, stamp_path = h.hexdigest(), os.path.join(OUT, "stamp")
+    outs = [os.path.join(OUT, n) for n in ("libbroadcast_ref.so", "libbroadcast_ref_fast.so", "manifest.json", "broadcast_ref.c")]
+    if not force and all(os.path.exists(o) for o in outs) and os.path.exists(stamp_path) and open(stamp_path).read().strip() == stamp:
+        if verbose:
+            print("[oracle/_ref] up to date")
+        return True
     files = []
     for p, subs in FILES:
         if p.startswith("cpp:"):
@@ -152,6 +167,8 @@ def build(verbose: bool = True) -> bool:
         if verbose:
             print("[oracle/_ref]", " ".join(cmd))
         subprocess.check_call(cmd)
+    with open(stamp_path, "w") as fh:
+        fh.write(stamp)
     return True
 
 
