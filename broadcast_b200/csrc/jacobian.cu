@@ -336,7 +336,9 @@ static int strips_impl(int nrect, const int32_t* rects /* [nrect][4] i0,i1,j0,j1
                        int32_t* const* ja, double* w, const double* nx, const double* ny, const double* vol, const double* volf,
                        int gh, double cp, double cv, double prandtl, double gam, double rgaz, double cs, double muref,
                        double tref, double s_suth, double k2, double k4, int im, int jm, int wall, const bc_desc_t* bcs,
-                       int nbcs, int scatter_kind, const double* coefdiag, void* stream, int kcap) {
+                       int nbcs, int scatter_kind, const double* coefdiag, void* stream, int kcap, int chain0 = 0) {
+  // chain0: first scratch chain of this call (the sub-block loops of the four strips run CONCURRENTLY on streams of their own:
+  // each needs its own set of chain buffers)
   if (im < 1 || jm < 1 || gh != 3 || nrect < 0 || nrect > 4) return BC_ERR_ARG;
   if (scatter_kind < 0 || scatter_kind > 6) return BC_ERR_ARG;
   if (nrect == 0) return BC_OK;
@@ -358,7 +360,7 @@ static int strips_impl(int nrect, const int32_t* rects /* [nrect][4] i0,i1,j0,j1
   double* resd5c[MAXCHAIN] = {};
   double* sc_[MAXCHAIN][4];
   for (int c = 0; c < K; ++c) {   // every scratch slot the loop touches must exist before capture (allocation is not capturable)
-    scratch_chain() = c;
+    scratch_chain() = chain0 + c;
     wd5c[c] = scratch_doubles(20, (size_t)g.sc * 25);
     resd5c[c] = scratch_doubles(21, (size_t)g.sc * 25);
     sc_[c][0] = scratch_doubles(0, (size_t)g.sc * NPRIM);
@@ -381,7 +383,7 @@ static int strips_impl(int nrect, const int32_t* rects /* [nrect][4] i0,i1,j0,j1
   auto pass = [&](int l, int k, int c, cudaStream_t s_) -> cudaError_t {
     double* wd5 = wd5c[c];
     double* resd5 = resd5c[c];
-    scratch_chain() = c;
+    scratch_chain() = chain0 + c;
     cudaError_t e = launch_testvector(g, wd5, 5, 0, l, k, nullptr, s_, has_join ? nullptr : &rows);
     if (e == cudaSuccess) {
       bc_desc_t act[16];
@@ -498,20 +500,20 @@ static int strips_impl(int nrect, const int32_t* rects /* [nrect][4] i0,i1,j0,j1
     }
   static const bool no_fork = getenv("BROADCAST_B200_NO_GRAPH_FORK") != nullptr;
   for (int c = 0; c < K; ++c) {   // side streams and events exist before the capture starts
-    scratch_chain() = c;
+    scratch_chain() = chain0 + c;
     rect_fork().ready();
   }
   scratch_chain() = 0;
   cudaError_t e = cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal);
   if (e != cudaSuccess) return (int)e;
   for (int c = 0; c < K; ++c) {   // per-rectangle launches become parallel branches of the graph
-    scratch_chain() = c;
+    scratch_chain() = chain0 + c;
     rect_fork().on = !no_fork;
   }
   scratch_chain() = 0;
   const cudaError_t er = run(gs, chain_st, chain_fork, chain_join);
   for (int c = 0; c < K; ++c) {
-    scratch_chain() = c;
+    scratch_chain() = chain0 + c;
     rect_fork().on = false;
   }
   scratch_chain() = 0;
@@ -651,10 +653,30 @@ extern "C" int bcd_jacobian_strips(int nrect, const int32_t* rects /* [nrect][4]
     if (e0 != cudaSuccess) return (int)e0;
     count_launches(nbcs);
   }
+  // the four sub-block loops run side by side: the two thin column strips are latency bound (49 passes of small launches on 6 k
+  // cells) and hide behind the two long row strips, which are throughput bound
+  static thread_local cudaStream_t wstream[4] = {};
+  static thread_local cudaEvent_t wjoin[4] = {};
+  static thread_local cudaEvent_t wfork = nullptr;
+  static const bool serial_env = getenv("BROADCAST_B200_STRIPS_SERIAL") != nullptr;
+  const bool concurrent = !serial_env && nrect > 1;   // (events order the window streams with the legacy default stream as well)
+  if (concurrent && !wfork) {
+    for (int q = 0; q < 4; ++q) {
+      if (cudaStreamCreateWithFlags(&wstream[q], cudaStreamNonBlocking) != cudaSuccess) return BC_ERR_ALLOC;
+      if (cudaEventCreateWithFlags(&wjoin[q], cudaEventDisableTiming) != cudaSuccess) return BC_ERR_ALLOC;
+    }
+    if (cudaEventCreateWithFlags(&wfork, cudaEventDisableTiming) != cudaSuccess) return BC_ERR_ALLOC;
+  }
+  if (concurrent) {
+    cudaEventRecord(wfork, st);
+    for (int q = 0; q < nrect; ++q) cudaStreamWaitEvent(wstream[q], wfork, 0);
+  }
+  cudaStream_t st_main = st;
   const SlabInfo saved = current_slab();
   int rc = BC_OK;
   for (int q = 0; q < nrect && rc == BC_OK; ++q) {
     const SubBlock& s_ = sb[q];
+    if (concurrent) st = wstream[q];
     const GridDesc gs = make_grid(s_.im, s_.jm, gh);
     // compact copies: slots 60 + 8 q .. of the scratch arena (chain 0), stable across calls so that the cached graphs replay
     scratch_chain() = 0;
@@ -688,9 +710,14 @@ extern "C" int bcd_jacobian_strips(int nrect, const int32_t* rects /* [nrect][4]
     int32_t* iq[1] = {ia[q]};
     int32_t* kq[1] = {ja[q]};
     rc = strips_impl(1, lr, jq, iq, kq, sw, snx, sny, svol, svolf, gh, cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4, s_.im, s_.jm,
-                     (wall && s_.ja == 1) ? 1 : 0, cb[q], ncb[q], scatter_kind, scd, stream, MAXCHAIN);
+                     (wall && s_.ja == 1) ? 1 : 0, cb[q], ncb[q], scatter_kind, scd, (void*)st, MAXCHAIN, concurrent ? MAXCHAIN * q : 0);
     current_slab() = saved;
   }
   current_slab() = saved;
+  if (concurrent)
+    for (int q = 0; q < nrect; ++q) {   // join every window's stream, also after an error (no work may outlive the call's stream order)
+      cudaEventRecord(wjoin[q], wstream[q]);
+      cudaStreamWaitEvent(st_main, wjoin[q], 0);
+    }
   return rc;
 }
