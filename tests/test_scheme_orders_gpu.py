@@ -74,3 +74,14 @@ def test_order_and_ghost_depth_must_agree(gpu):
     res = c.zeros_state()
     with pytest.raises(BroadcastB200Error):
         gpu["f_sch"].flux_num_dnc5_2d(res, c.w, *c.scheme_args())
+
+
+@pytest.mark.parametrize("order", ORDERS)
+def test_residual_orders_at_the_c1_grid(gpu, ref, order):
+    """the other orders at the size of BASELINE.json's C1 (500 x 150 boundary layer): same parity bar as the order-5 configs"""
+    a = H.make_case("bl", 500, 150, gpu, with_w=True, order=order)
+    b = H.make_case("bl", 500, 150, ref, with_w=True, order=order)
+    name = f"flux_num_dnc{order}_2d"
+    wa, ra = H.residual_sequence(gpu, a, name)
+    wb, rb = H.residual_sequence(ref, b, name)
+    H.assert_residual_parity(ra, rb, b, wb, floor=H.fma_floor(b, name), what=name + " 500x150")
