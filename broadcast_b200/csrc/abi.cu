@@ -366,6 +366,15 @@ int bcd_bc_extrapolate_o2(double* w, double* wd, int ndir, const char* loc, cons
   return e == cudaSuccess ? BC_OK : cuda_fail(e, "bcd_bc_extrapolate_o2");
 }
 
+int bcd_bc_general(double* w, double* wd, int ndir, const char* loc, const int32_t* interf, const double* field, int gh, int im, int jm,
+                   int lm, void* stream) {
+  BCD_PROLOGUE();
+  if (!field || lm < b.lmax) return fail(BC_ERR_ARG, "field is null or has fewer rows than the interface");
+  cudaError_t e = launch_bc_general(g, b, ndir, w, wd, field, lm, (cudaStream_t)stream);
+  g_launches += 1;
+  return e == cudaSuccess ? BC_OK : cuda_fail(e, "bcd_bc_general");
+}
+
 int bcd_jn_match(double* wr, const int32_t* prr, int gh1r, int gh2r, int gh3r, int gh4r, int imr, int jmr, const double* wd,
                  const int32_t* prd, int gh1d, int gh2d, int gh3d, int gh4d, int imd, int jmd, const int32_t* tr, int em, void* stream) {
   if (!prr || !prd || !tr || em < 1) return fail(BC_ERR_ARG, "jn_match: null window or em < 1");
@@ -668,6 +677,25 @@ int bc_bc_extrapolate_o2_2d_d(double* w, double* wd, const char* loc, const int3
   if (!wd) return fail(BC_ERR_ARG, "wd is null");
   return bc_host(w, wd, gh, im, jm,
                  [&](const GridDesc&, double* dw, double* dwd) { return bcd_bc_extrapolate_o2(dw, dwd, 1, loc, interf, im, jm, gh, nullptr); });
+}
+
+static int general_host(double* w, double* wd, const char* loc, const int32_t* interf, const double* field, int gh, int im, int jm, int lm) {
+  if (lm < 1) return fail(BC_ERR_ARG, "lm must be positive");
+  return bc_host(w, wd, gh, im, jm, [&](const GridDesc&, double* dw, double* dwd) -> int {
+    double* dfield = dbuf<double>(S_AUX, (size_t)lm * gh * 5);
+    if (!dfield) return fail(BC_ERR_ALLOC, "device allocation failed");
+    CK(cudaMemcpyAsync(dfield, field, sizeof(double) * lm * gh * 5, cudaMemcpyHostToDevice, 0));
+    return bcd_bc_general(dw, dwd, wd ? 1 : 0, loc, interf, dfield, gh, im, jm, lm, nullptr);
+  });
+}
+int bc_bc_general_2d(double* w, const char* loc, const int32_t* interf, const double* field, int gh, int im, int jm, int lm, int em,
+                     int gh1) {
+  if (em != 5 || gh1 != gh) return fail(BC_ERR_UNSUPPORTED, "bc_general_2d: field must be (lm, gh, 5)");
+  return general_host(w, nullptr, loc, interf, field, gh, im, jm, lm);
+}
+int bc_bc_general_2d_d(double* w, double* wd, const char* loc, const int32_t* interf, const double* field, int gh, int im, int jm, int lm) {
+  if (!wd) return fail(BC_ERR_ARG, "wd is null");
+  return general_host(w, wd, loc, interf, field, gh, im, jm, lm);
 }
 
 int bc_jn_match_2d(double* wr, const int32_t* prr, int gh1r, int gh2r, int gh3r, int gh4r, int imr, int jmr, const double* wd,

@@ -594,4 +594,24 @@ __device__ void bc_extrapolate_o2_line(const StateRW<N>& s, const BcLine& b, int
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dirichlet fill from a table (bc_general.F90:6-31; tangent/bc_general_d.f90): ghost layer de of line cell l takes field(l, de, :);
+// the tangent routine zeroes the ghost tangents and leaves w alone.  field: (lm, gh, 5), Fortran order.
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__device__ void bc_general_line(const StateRW<N>& s, const BcLine& b, const double* __restrict__ field, int lm, int l) {
+  using DT = TanOf<N>;
+  const int i = b.imin + l * b.j0 * b.j0;
+  const int j = b.jmin + l * b.i0 * b.i0;
+  const int i0 = b.i0, j0 = b.j0, gh = s.g.gh;
+  for (int de = 1; de <= gh; ++de) {
+#pragma unroll
+    for (int e = 0; e < 5; ++e) {
+      Var<DT> x{};
+      x.v = field[l + (long long)(de - 1) * lm + (long long)e * lm * gh];
+      s.set(i - i0 * de, j - j0 * de, e, x, /*primal=*/N == 0);
+    }
+  }
+}
+
 }  // namespace bcast

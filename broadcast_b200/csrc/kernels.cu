@@ -139,6 +139,12 @@ __global__ void k_bc_extrap(StateRW<N> s, BcLine b) {
 }
 
 template <int N>
+__global__ void k_bc_general(StateRW<N> s, BcLine b, const double* field, int lm) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < b.lmax) bc_general_line<N>(s, b, field, lm, l);
+}
+
+template <int N>
 __global__ void k_bc_wall_iso(StateRW<N> s, BcLine b, double twall, double gam, double rgaz) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l < b.lmax) bc_wall_viscous_iso_line<N>(s, b, twall, gam, rgaz, l);
@@ -211,6 +217,10 @@ cudaError_t launch_bc_wall_profile(const GridDesc& g, const BcLine& b, bool blow
 }
 cudaError_t launch_bc_extrap(const GridDesc& g, const BcLine& b, int ndir, double* w, double* wd, cudaStream_t st) {
   BC_DISPATCH(k_bc_extrap);
+}
+cudaError_t launch_bc_general(const GridDesc& g, const BcLine& b, int ndir, double* w, double* wd, const double* field, int lm,
+                              cudaStream_t st) {
+  BC_DISPATCH(k_bc_general, field, lm);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -113,6 +113,8 @@ cudaError_t launch_bc_noref(const GridDesc& g, const BcLine& b, double gam, int 
 cudaError_t launch_bc_inlet(const GridDesc& g, const BcLine& b, double gam, int ndir, double* w, double* wd, const double* field, int lm,
                             const double* nx, const double* ny, cudaStream_t st);
 cudaError_t launch_bc_extrap(const GridDesc& g, const BcLine& b, int ndir, double* w, double* wd, cudaStream_t st);
+cudaError_t launch_bc_general(const GridDesc& g, const BcLine& b, int ndir, double* w, double* wd, const double* field, int lm,
+                              cudaStream_t st);
 cudaError_t launch_bc_wall_iso(const GridDesc& g, const BcLine& b, double twall, double gam, double rgaz, int ndir, double* w, double* wd,
                                cudaStream_t st);
 cudaError_t launch_bc_wall_profile(const GridDesc& g, const BcLine& b, bool blow, const double* prof, const double* profd, double gam,

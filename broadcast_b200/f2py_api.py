@@ -187,6 +187,17 @@ def build(backend):
         _check_cells(_state(w, "w"), im, jm, gh, "w")
         B("bc_supandsubinlet_2d", w, _loc(loc), _interf(interf), field, _in(nx), _in(ny), gam, int(im), int(jm), lm, gh)
 
+    def bc_general_2d(w, loc, interf, field, gh, im, jm, lm=None, em=None, gh1=None):
+        """srcfv/borders/bc_general.F90: ghost layers from the table field(lm, gh1, em)"""
+        field = _in(field)
+        if field.ndim != 3:
+            raise ValueError("field must have shape (lm, gh1, em)")
+        lm = int(lm) if lm is not None else field.shape[0]
+        em = int(em) if em is not None else field.shape[2]
+        gh1 = int(gh1) if gh1 is not None else field.shape[1]
+        _check_cells(_state(w, "w"), im, jm, gh, "w", planes=em)
+        B("bc_general_2d", w, _loc(loc), _interf(interf), field, int(gh), int(im), int(jm), lm, em, gh1)
+
     def bc_extrapolate_o2_2d(w, loc, interf, im, jm, gh, em=None):
         _state(w, "w")
         em = int(em) if em is not None else w.shape[2]
@@ -211,7 +222,7 @@ def build(backend):
         bc_wall_viscous_iso_2d=bc_wall_viscous_iso_2d, bc_symmetry_2d=bc_symmetry_2d, bc_antisymmetry_2d=bc_antisymmetry_2d,
         bc_pressure_2d=bc_pressure_2d, bc_wall_blow_profile_2d=bc_wall_blow_profile_2d,
         bc_wall_viscous_iso_profile_2d=bc_wall_viscous_iso_profile_2d,
-        bc_supandsubinlet_2d=bc_supandsubinlet_2d, bc_extrapolate_o2_2d=bc_extrapolate_o2_2d,
+        bc_supandsubinlet_2d=bc_supandsubinlet_2d, bc_extrapolate_o2_2d=bc_extrapolate_o2_2d, bc_general_2d=bc_general_2d,
         jn_match_2d=jn_match_2d, jn_match_geom_2d=jn_match_geom_2d)
 
     # ------------------------------------------------------------------ f_lin (tangents)
@@ -291,6 +302,14 @@ def build(backend):
         _check_cells(_state(wd, "wd"), im, jm, gh, "wd")
         B("bc_supandsubinlet_2d_d", w, wd, _loc(loc), _interf(interf), field, _in(nx), _in(ny), gam, int(im), int(jm), lm, gh)
 
+    def bc_general_2d_d(w, wd, loc, interf, field, gh, im, jm, lm=None):
+        """srcfv/tangent/bc_general_d.f90: the ghost tangents of the Dirichlet fill are zero"""
+        field = _in(field)
+        lm = int(lm) if lm is not None else field.shape[0]
+        _check_cells(_state(w, "w"), im, jm, gh, "w")
+        _check_cells(_state(wd, "wd"), im, jm, gh, "wd")
+        B("bc_general_2d_d", w, wd, _loc(loc), _interf(interf), field, int(gh), int(im), int(jm), lm)
+
     def bc_extrapolate_o2_2d_d(w, wd, loc, interf, im, jm, gh, em=None):
         _state(w, "w")
         _state(wd, "wd")
@@ -307,7 +326,8 @@ def build(backend):
         bc_wall_viscous_iso_2d_d=bc_wall_viscous_iso_2d_d, bc_symmetry_2d_d=bc_symmetry_2d_d,
         bc_antisymmetry_2d_d=bc_antisymmetry_2d_d, bc_pressure_2d_d=bc_pressure_2d_d,
         bc_wall_blow_profile_2d_d=bc_wall_blow_profile_2d_d, bc_wall_viscous_iso_profile_2d_d=bc_wall_viscous_iso_profile_2d_d,
-        bc_supandsubinlet_2d_d=bc_supandsubinlet_2d_d, bc_extrapolate_o2_2d_d=bc_extrapolate_o2_2d_d)
+        bc_supandsubinlet_2d_d=bc_supandsubinlet_2d_d, bc_extrapolate_o2_2d_d=bc_extrapolate_o2_2d_d,
+        bc_general_2d_d=bc_general_2d_d)
 
     # ------------------------------------------------------------------ f_geom
     def computegeom_2d(x0, y0, nx, ny, xc, yc, vol, volf, im, jm, gh):

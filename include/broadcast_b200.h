@@ -200,6 +200,14 @@ int bc_bc_wall_viscous_iso_profile_2d(double* w, const double* twallprof, const 
 int bc_bc_wall_viscous_iso_profile_2d_d(double* w, double* wd, const double* twallprof, const double* twallprofd, const char* loc,
                                         double gam, double gamd, double rgaz, double rgazd, const int32_t* interf, int gh, int im,
                                         int jm, int lm);
+/* ---- Dirichlet fill from a table: srcfv/borders/bc_general.F90:6-31 (f_bnd.bc_general_2d: ghost layer de of line cell l takes
+ *      field(l, de, :); the cards name it as the alternative inlet routine, card_bl2d_fv.py:107) and srcfv/tangent/bc_general_d.f90
+ *      (f_lin.bc_general_2d_d: ghost tangents zeroed, w untouched).  field: (lm, gh1, em) Fortran order; em = 5, gh1 = gh. */
+int bc_bc_general_2d(double* w, const char* loc, const int32_t* interf, const double* field, int gh, int im, int jm, int lm, int em,
+                     int gh1);
+int bc_bc_general_2d_d(double* w, double* wd, const char* loc, const int32_t* interf, const double* field, int gh, int im, int jm,
+                       int lm);
+
 /* srcfv/borders/jn_match.F90:3-66 (3-D arrays, em planes) and jn_match_geom.F90:7-69 (2-D arrays) */
 int bc_jn_match_2d(double* wr, const int32_t* prr, int gh1r, int gh2r, int gh3r, int gh4r, int imr, int jmr,
                    const double* wd, const int32_t* prd, int gh1d, int gh2d, int gh3d, int gh4d, int imd, int jmd,
@@ -315,6 +323,8 @@ int bcd_bc_supandsubinlet(double* w, double* wd, int ndir, const char* loc, cons
                           int gh, void* stream);
 int bcd_bc_extrapolate_o2(double* w, double* wd, int ndir, const char* loc, const int32_t* interf, int im, int jm,
                           int gh, void* stream);
+int bcd_bc_general(double* w, double* wd, int ndir, const char* loc, const int32_t* interf, const double* field, int gh, int im,
+                   int jm, int lm, void* stream);
 int bcd_bc_wall_viscous_iso(double* w, double* wd, int ndir, double twall, const char* loc, double gam, double rgaz,
                             const int32_t* interf, int gh, int im, int jm, void* stream);
 int bcd_bc_symmetry(double* w, double* wd, int ndir, const char* loc, const int32_t* interf, const double* nx,
