@@ -32,7 +32,7 @@ _WINDOW_ARGS = {
     "bc_wall_viscous_iso_2d": (5,), "bc_wall_viscous_iso_2d_d": (6,), "bc_symmetry_2d": (2,), "bc_symmetry_2d_d": (3,),
     "bc_antisymmetry_2d": (2,), "bc_antisymmetry_2d_d": (3,), "bc_pressure_2d": (2,), "bc_pressure_2d_d": (3,),
     "bc_wall_blow_profile_2d": (4,), "bc_wall_blow_profile_2d_d": (7,), "bc_wall_viscous_iso_profile_2d": (5,),
-    "bc_wall_viscous_iso_profile_2d_d": (9,),
+    "bc_wall_viscous_iso_profile_2d_d": (9,), "bc_general_2d": (2,), "bc_general_2d_d": (3,),
 }
 
 
