@@ -182,3 +182,35 @@ def test_profile_wall_tangents_accept_the_driver_arity(ref):
             outs.append((w, wd))
         assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
         assert not np.array_equal(outs[0][1], d)
+
+
+@pytest.mark.parametrize("loc", ["Ilo", "Ihi", "Jlo", "Jhi"])
+def test_bc_general_is_the_dirichlet_fill_it_names(ref, loc):
+    """bc_general_2d (srcfv/borders/bc_general.F90): ghost layer de of line cell l = field(l, de, :), nothing else touched; its tangent
+    zeroes the same ghosts and leaves w alone -- the defining property pins the oracle's binding (interface array in Fortran order)"""
+    import helpers as H
+    c = H.make_case("bl", 19, 13, ref, with_w=True)
+    gh, im, jm = c.gh, c.im, c.jm
+    rng = np.random.default_rng(1)
+    lm = jm if loc[0] == "I" else im
+    if loc[0] == "I":
+        i = 1 if loc == "Ilo" else im
+        itf = np.array([[i, 1], [i, jm]], dtype=float)
+    else:
+        j = 1 if loc == "Jlo" else jm
+        itf = np.array([[1, j], [im, j]], dtype=float)
+    field = np.asfortranarray(rng.standard_normal((lm, gh, 5)))
+    w = c.w.copy(order="F")
+    ref["f_bnd"].bc_general_2d(w, loc, itf, field, gh, im, jm)
+    exp = c.w.copy(order="F")
+    ghost = np.zeros(exp.shape[:2], dtype=bool)
+    for de in range(1, gh + 1):
+        sl = {"Ilo": (gh - de, slice(gh, gh + jm)), "Ihi": (gh + im - 1 + de, slice(gh, gh + jm)),
+              "Jlo": (slice(gh, gh + im), gh - de), "Jhi": (slice(gh, gh + im), gh + jm - 1 + de)}[loc]
+        exp[sl] = field[:, de - 1, :]
+        ghost[sl] = True
+    assert np.array_equal(w, exp)
+    wd = np.asfortranarray(rng.standard_normal(w.shape))
+    wd0, w0 = wd.copy(order="F"), w.copy(order="F")
+    ref["f_lin"].bc_general_2d_d(w, wd, loc, itf, field, gh, im, jm)
+    assert np.array_equal(w, w0) and not wd[ghost].any() and np.array_equal(wd[~ghost], wd0[~ghost])
