@@ -67,7 +67,8 @@ extern "C" int bcast_ctx_create(bcast_ctx_t** out, int im, int jm, int gh, doubl
   *out = nullptr;
   if (bc_device_count() <= 0) return BC_ERR_NODEV;
   if (im < 1 || jm < 1) return BC_ERR_ARG;
-  if (gh != 3) return BC_ERR_UNSUPPORTED;
+  // gh = 2 / 3 / 4 / 5: flux_num_dnc3 / 5 / 7 / 9 (state, fills, residual, norms); the block-Jacobian -> CSR entry is order 5
+  if (gh < 2 || gh > 5) return BC_ERR_UNSUPPORTED;
   bcast_ctx* c = new bcast_ctx();
   c->im = im; c->jm = jm; c->gh = gh; c->wall = wall ? 1 : 0;
   const double p[11] = {cp, cv, prandtl, gam, rgaz, cs, muref, tref, s_suth, k2, k4};
@@ -223,6 +224,7 @@ extern "C" int bcast_ctx_jacobian_csr(bcast_ctx_t* c, const double* coefdiag, in
                                       long long* nnz) {
   if (!c || !nnz || !c->have_state || !c->have_geom) return BC_ERR_ARG;
   const int im = c->im, jm = c->jm, gh = c->gh;
+  if (gh != 3) return BC_ERR_UNSUPPORTED;   // (the other orders assemble through bcd_jacobian_coo on device pointers)
   if (im < 2 * gh || jm < 2 * gh) return BC_ERR_UNSUPPORTED;
   if (scatter_kind < 0) scatter_kind = c->has_join ? 3 : 1;
   if (scatter_kind != 1 && scatter_kind != 3) return BC_ERR_ARG;

@@ -85,3 +85,25 @@ def test_residual_orders_at_the_c1_grid(gpu, ref, order):
     wa, ra = H.residual_sequence(gpu, a, name)
     wb, rb = H.residual_sequence(ref, b, name)
     H.assert_residual_parity(ra, rb, b, wb, floor=H.fma_floor(b, name), what=name + " 500x150")
+
+
+@pytest.mark.parametrize("order", [3, 7])
+def test_c_abi_context_runs_the_other_orders(gpu, ref, order):
+    """the resident C-ABI context (bcast_ctx_*: what a C / Fortran host binds) with gh = 2 / 4: state, boundary fills, residual
+    and norms of the order-3 / 7 scheme; its block-Jacobian entry is order 5 and says so"""
+    from broadcast_b200.cabi_ctx import Context
+    from broadcast_b200._lib import BroadcastB200Error
+    a = H.make_case("bl", 60, 31, gpu, with_w=True, order=order)
+    b = H.make_case("bl", 60, 31, ref, with_w=True, order=order)
+    name = f"flux_num_dnc{order}_2d"
+    wb, rb = H.residual_sequence(ref, b, name)
+    ctx = Context(a)
+    ctx.upload_state(a.w)
+    ra = ctx.residual()
+    H.assert_residual_parity(ra, rb, b, wb, floor=H.fma_floor(b, name), what="context " + name)
+    n2, ninf = ctx.norms()
+    n2b, ninfb = ref["f_norm"].compute_norml2inf(rb, b.im, b.jm, b.gh)
+    assert np.allclose(n2, n2b, rtol=1e-10) and np.allclose(ninf, ninfb, rtol=1e-10)
+    with pytest.raises(BroadcastB200Error):
+        ctx.jacobian_csr()
+    ctx.close()
