@@ -71,19 +71,30 @@ __global__ void __launch_bounds__(rf::NT, 2)
   // l2dist < 0: ring launch, a 1-D grid over the tiles outside the inner rectangle [1, ox] x [1, oy] (= bx1, by1):
   // first tile row, last tile rows, first tile column, last tile columns.
   int bx_ = blockIdx.x + ox, by_ = blockIdx.y + oy;
-  if (l2dist < 0) {
+  const bool ring = l2dist < 0;
+  // ring launch: tile of ring index u (first tile row, last tile rows, first tile column, last tile columns)
+  auto ring_tile = [&](int u, int& bx, int& by) {
     const int bx1 = ox, by1 = oy;
-    int u = blockIdx.x;
     const int nA = ntx, nB = ntx * (nty - by1 - 1), nC = by1;
-    if (u < nA) { bx_ = u; by_ = 0; }
-    else if ((u -= nA) < nB) { bx_ = u % ntx; by_ = by1 + 1 + u / ntx; }
-    else if ((u -= nB) < nC) { bx_ = 0; by_ = 1 + u; }
-    else { u -= nC; const int wr = ntx - bx1 - 1; bx_ = bx1 + 1 + u % wr; by_ = 1 + u / wr; }
-  }
+    if (u < nA) { bx = u; by = 0; }
+    else if ((u -= nA) < nB) { bx = u % ntx; by = by1 + 1 + u / ntx; }
+    else if ((u -= nB) < nC) { bx = 0; by = 1 + u; }
+    else { u -= nC; const int wr = ntx - bx1 - 1; bx = bx1 + 1 + u % wr; by = 1 + u / wr; }
+  };
+  if (ring) ring_tile((int)blockIdx.x, bx_, by_);
   t.i0 = 1 + bx_ * rf::OI;
   t.j0 = 1 + by_ * rf::OJ;
   const int tid = threadIdx.x;
-  if (l2dist > 0) {
+  if (ring) {
+    // the ring follows the halo exchange and the boundary fills, which have just written what its tiles read: pull the tile one
+    // wave of CTAs ahead (in ring order) into L2, as the whole-block launch does with its own distance
+    const int u2 = (int)blockIdx.x - l2dist;   // l2dist = -(distance) in ring mode
+    if (u2 < (int)gridDim.x) {
+      int bx, by;
+      ring_tile(u2, bx, by);
+      prefetch_tile_l2(g, w, nx, ny, vol, volf, 1 + bx * rf::OI, 1 + by * rf::OJ, tid);
+    }
+  } else if (l2dist > 0) {
     const int L = by_ * ntx + bx_ + l2dist;
     const int bx = L % ntx, by = L / ntx;
     if (by < nty) prefetch_tile_l2(g, w, nx, ny, vol, volf, 1 + bx * rf::OI, 1 + by * rf::OJ, tid);
@@ -166,7 +177,7 @@ cudaError_t launch_residual_fast(const GridDesc& g, const SchemeArgs& a, bool wa
     if (has_inner) go(1, 1, bx1, by1, l2dist);
   } else {   // the ring in ONE launch (1-D grid, tile found from the block index)
     const int nring = ntx + ntx * (nty - by1 - 1) + by1 + (ntx - bx1 - 1) * by1;
-    k_residual_fast<<<nring, rf::NT, SMEM, st>>>(-1, early, bx1, by1, ntx, nty, g, c, sqgr, wall, w, nx, ny, vol, volf, res);
+    k_residual_fast<<<nring, rf::NT, SMEM, st>>>(-296, early, bx1, by1, ntx, nty, g, c, sqgr, wall, w, nx, ny, vol, volf, res);   // -(prefetch distance): one wave
   }
   return cudaGetLastError();
 }
