@@ -914,3 +914,45 @@ def newton_step(blk: "Block", coefdiag=None, restart=40, maxit=2000, rtol=1e-10,
         blk.w[:, gh:gh + jm, gh:gh + im] += dw3.permute(2, 1, 0)
     info["nnz"] = int(data.numel())
     return dw3, info
+
+
+def newton_loop(blk: "Block", cfl: float, nit: int, restart=40, maxit=4000, rtol=1e-8, verbose=False):
+    """The reference's fixed-point (pseudo-transient Newton) loop, BROADCAST_npz.py:1007-1172, with every stage on the device:
+    dt = cfl (yc(1,2) - yc(1,1)) / (1 / Mach + 1); per iteration: boundary fills, residual, norms; the relaxation follows the residual,
+    cflm1 = max(norm / norm0, ninf / ninf0 over the first three equations) / dt (:1059-1061), coefdiag = cflm1 vol (:1067);
+    Jacobian -> zero filter -> CSR; dw = A^-1 res (here: GMRES + block Jacobi on the resident matrix instead of MUMPS);
+    w += dw -- or, when the correction is not finite or the solve did not converge, the previous correction is taken back and
+    the CFL number halved (:1164-1169).  Returns the history [(iteration, norm[5], ninf[5], cflm1, matvecs), ...] (matvecs <= 0: the
+    step was rejected).  This is the reference's iteration PROTOCOL; the cards run it at CFL = 1e10 (card_bl2d_fv_npz.py:56: the
+    un-relaxed Jacobian, a direct solver's job), which the block-Jacobi iteration does not reach -- use moderate CFL numbers here and
+    the CSR / PETSc output with the reference's LU for the final Newton iterations."""
+    c = blk.case
+    gh, im, jm = blk.gh, blk.im, blk.jm
+    dt = cfl * float(c.yc[gh, gh + 1] - c.yc[gh, gh]) / (1.0 / float(c.phys["mach"]) + 1.0)
+    dtm1 = 1.0 / dt
+    vol = blk.vol[gh:gh + jm, gh:gh + im].contiguous()
+    hist, norm0m1, ninf0m1, dw_old = [], None, None, None
+    for it in range(1, nit + 1):
+        blk.apply_bcs()
+        blk.residual()
+        norm, ninf = blk.norms()
+        if it == 1:
+            norm0m1, ninf0m1 = 1.0 / np.maximum(norm, 1e-15), 1.0 / np.maximum(ninf, 1e-15)
+        r = float(max((norm[:3] * norm0m1[:3]).max(), (ninf[:3] * ninf0m1[:3]).max()))
+        cflm1 = r * dtm1
+        try:
+            dw, info = newton_step(blk, coefdiag=cflm1 * vol, restart=restart, maxit=maxit, rtol=rtol, update=False)
+            ok = info["converged"] and bool(torch.isfinite(dw).all())
+        except _lib.BroadcastB200Error:      # a state that has left the physical range (singular diagonal blocks): rejected like a NaN
+            dw, info, ok = None, {"matvecs": 0}, False
+        if ok:
+            blk.w[:, gh:gh + jm, gh:gh + im] += dw.permute(2, 1, 0)
+            dw_old = dw.clone()
+        else:
+            if dw_old is not None:
+                blk.w[:, gh:gh + jm, gh:gh + im] -= dw_old.permute(2, 1, 0)
+            dtm1 *= 2.0          # cfl = cfl / 2
+        hist.append((it, norm, ninf, cflm1, info["matvecs"] if ok else -info["matvecs"]))
+        if verbose:
+            print(f"newton {it}: |res|_2 = {norm}, 1/cfl = {cflm1:.3e}, matvecs = {info['matvecs']}, {'ok' if ok else 'rejected'}", flush=True)
+    return hist

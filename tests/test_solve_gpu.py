@@ -113,3 +113,30 @@ def test_newton_step_against_the_reference_loop(gpu, ref):
     # w += dw on the interior cells
     upd = (blk.w - w0)[:, gh:gh + jm, gh:gh + im].permute(2, 1, 0).cpu().numpy()
     assert np.abs(upd - dw.cpu().numpy()).max() <= 1e-15 * max(1.0, float(blk.w.abs().max()))
+
+
+def test_newton_loop_follows_the_reference_protocol(gpu):
+    """resident.newton_loop = the iteration protocol of BROADCAST_npz.py:1007-1172 on the device: the first pass is newton_step
+    with coefdiag = vol / dt (relaxation factor 1), dt from the CFL number and the first cell height; later passes scale the
+    relaxation by the residual ratios of the first three equations; every solve converges at a moderate CFL number"""
+    import torch
+    from broadcast_b200.resident import Block, newton_loop, newton_step
+    c = H.make_case("bl", 48, 30, gpu, with_w=True)
+    gh, im, jm = c.gh, c.im, c.jm
+    cfl = 1.0
+    dt = cfl * float(c.yc[gh, gh + 1] - c.yc[gh, gh]) / (1.0 / float(c.phys["mach"]) + 1.0)
+    blk = Block(c)
+    hist = newton_loop(blk, cfl=cfl, nit=3, rtol=1e-10)
+    assert len(hist) == 3 and all(h[4] > 0 for h in hist), [h[4] for h in hist]
+    assert abs(hist[0][3] * dt - 1.0) < 1e-12                                  # first pass: cflm1 = 1 / dt
+    n0, i0 = hist[0][1], hist[0][2]
+    for it, norm, ninf, cflm1, _ in hist[1:]:
+        r = max((norm[:3] / n0[:3]).max(), (ninf[:3] / i0[:3]).max())
+        assert abs(cflm1 * dt / r - 1.0) < 1e-12
+    # the first pass alone, through newton_step on a fresh block: same state afterwards
+    blk2 = Block(c)
+    vol = blk2.vol[gh:gh + jm, gh:gh + im].contiguous()
+    newton_step(blk2, coefdiag=(1.0 / dt) * vol, rtol=1e-10)
+    blk3 = Block(c)
+    newton_loop(blk3, cfl=cfl, nit=1, rtol=1e-10)
+    assert torch.equal(blk2.w, blk3.w)
